@@ -1,0 +1,47 @@
+# Top-level build.
+#   make lib      -> primme_b200/libprimme_b200.so   (product: host C + sm_100a kernels, no CPU path)
+#   make oracle   -> oracle/_build/*.so (+ oracle/_ref/libprimme_ref.so when /root/reference exists)
+#   make all      -> both
+# LAPACK/BLAS for the small host-side dense algebra: any LP64 Fortran-ABI library; the only one in
+# this image is the OpenBLAS bundled with opencv.
+OB     ?= /opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs
+OBLIB  ?= libopenblasp-r0-59ffcd50.3.15.so
+LAPACK ?= -L$(OB) -l:$(OBLIB) -Wl,--disable-new-dtags,-rpath,$(OB)
+NVCC   ?= nvcc
+CC     ?= gcc
+ARCH   := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -Xcompiler -fPIC -std=c++17
+CFLAGS := -O2 -fPIC -std=c99 -Wall -Wno-unused-function -D_POSIX_C_SOURCE=200809L
+
+HOST_SRC := $(wildcard primme_b200/src/*.c)
+HOST_OBJ := $(patsubst primme_b200/src/%.c,build/host/%.o,$(HOST_SRC))
+CU_SRC   := $(wildcard primme_b200/csrc/*.cu)
+CU_OBJ   := $(patsubst primme_b200/csrc/%.cu,build/cu/%.o,$(CU_SRC))
+
+all: lib oracle
+
+lib: primme_b200/libprimme_b200.so
+
+build/host/%.o: primme_b200/src/%.c primme_b200/src/pb_host.h primme_b200/src/hostla.h include/primme_b200.h include/primme_eigs.h
+	@mkdir -p build/host
+	$(CC) $(CFLAGS) -c $< -o $@
+
+build/cu/%.o: primme_b200/csrc/%.cu primme_b200/csrc/pb200_internal.cuh include/primme_b200.h
+	@mkdir -p build/cu
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+primme_b200/libprimme_b200.so: $(HOST_OBJ) $(CU_OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(HOST_OBJ) $(CU_OBJ) -Xlinker --disable-new-dtags -Xlinker -rpath -Xlinker $(OB) -L$(OB) -l:$(OBLIB) -lcudart -ldl -lm
+
+oracle: oracle/_build/libprimme_hostcheck.so
+	$(MAKE) -C oracle all
+
+# host control code linked against the CPU restatement of the kernels: TEST ONLY
+oracle/_build/libprimme_hostcheck.so: $(HOST_OBJ) oracle/kernels_ref.c
+	@mkdir -p oracle/_build
+	$(CC) -O2 -fPIC -shared -o $@ $(HOST_OBJ) oracle/kernels_ref.c $(LAPACK) -lm
+
+clean:
+	rm -rf build primme_b200/libprimme_b200.so oracle/_build
+
+.PHONY: all lib oracle clean

@@ -1,0 +1,248 @@
+// ctx.cu -- device context, memory helpers, deterministic panel reduction and the NCCL hook.
+// Replaces the per-call cudaMalloc/cudaMemcpy2D/cudaDeviceSynchronize pattern of the reference's
+// cuBLAS back end (reference src/linalg/cublas_wrapper.c:187-232,335-392): one pinned staging
+// buffer, one device coefficient buffer and one partials buffer live for the whole solve.
+#include "pb200_internal.cuh"
+#include <dlfcn.h>
+#include <stdlib.h>
+#include <string.h>
+
+extern "C" int pb200_device_count(void) {
+   int n = 0;
+   if (cudaGetDeviceCount(&n) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+   }
+   return n;
+}
+
+extern "C" int pb200_ctx_create(pb200_ctx **out, int device) {
+   *out = NULL;
+   if (pb200_device_count() <= 0) {
+      fprintf(stderr, "primme_b200: no CUDA device visible -- this library has no CPU path\n");
+      return PB200_ERR_NO_DEVICE;
+   }
+   if (device >= 0) PB_CUDA(cudaSetDevice(device));
+   pb200_ctx *ctx = (pb200_ctx *)calloc(1, sizeof(pb200_ctx));
+   if (!ctx) return PB200_ERR_ALLOC;
+   PB_CUDA(cudaGetDevice(&ctx->device));
+   cudaDeviceProp prop;
+   PB_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+   ctx->num_sms = prop.multiProcessorCount;
+   PB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+   ctx->small_cap = 1 << 16; // 64 Ki doubles = 512 KB
+   PB_CUDA(cudaMallocHost((void **)&ctx->h_pinned, ctx->small_cap * sizeof(double)));
+   PB_CUDA(cudaMalloc((void **)&ctx->d_small, ctx->small_cap * sizeof(double)));
+   PB_CUDA(cudaMalloc((void **)&ctx->d_panel, ctx->small_cap * sizeof(double)));
+   ctx->partials_cap = 0;
+   ctx->d_partials = NULL;
+   ctx->nranks = 1;
+   *out = ctx;
+   return 0;
+}
+
+extern "C" int pb200_ctx_destroy(pb200_ctx *ctx) {
+   if (!ctx) return 0;
+   cudaStreamSynchronize(ctx->stream);
+   cudaFreeHost(ctx->h_pinned);
+   cudaFree(ctx->d_small);
+   cudaFree(ctx->d_panel);
+   cudaFree(ctx->d_partials);
+   cudaFree(ctx->d_scratch);
+   cudaStreamDestroy(ctx->stream);
+   free(ctx);
+   return 0;
+}
+
+extern "C" int pb200_ctx_sync(pb200_ctx *ctx) {
+   PB_CUDA(cudaStreamSynchronize(ctx->stream));
+   return 0;
+}
+extern "C" void *pb200_ctx_stream(pb200_ctx *ctx) { return (void *)ctx->stream; }
+extern "C" int64_t pb200_ctx_launches(pb200_ctx *ctx) { return ctx->launches; }
+extern "C" int pb200_ctx_nranks(pb200_ctx *ctx) { return ctx->nranks; }
+
+int pb_ensure_partials(pb200_ctx *ctx, size_t doubles) {
+   if (doubles <= ctx->partials_cap) return 0;
+   PB_CUDA(cudaStreamSynchronize(ctx->stream));
+   if (ctx->d_partials) PB_CUDA(cudaFree(ctx->d_partials));
+   size_t cap = doubles + doubles / 2;
+   PB_CUDA(cudaMalloc((void **)&ctx->d_partials, cap * sizeof(double)));
+   ctx->partials_cap = cap;
+   return 0;
+}
+int pb_ensure_scratch(pb200_ctx *ctx, size_t bytes) {
+   if (bytes <= ctx->scratch_cap) return 0;
+   PB_CUDA(cudaStreamSynchronize(ctx->stream));
+   if (ctx->d_scratch) PB_CUDA(cudaFree(ctx->d_scratch));
+   PB_CUDA(cudaMalloc(&ctx->d_scratch, bytes));
+   ctx->scratch_cap = bytes;
+   return 0;
+}
+int pb_ensure_small(pb200_ctx *ctx, size_t doubles) {
+   if (doubles <= ctx->small_cap) return 0;
+   PB_CUDA(cudaStreamSynchronize(ctx->stream));
+   size_t cap = doubles * 2;
+   cudaFreeHost(ctx->h_pinned);
+   cudaFree(ctx->d_small);
+   cudaFree(ctx->d_panel);
+   PB_CUDA(cudaMallocHost((void **)&ctx->h_pinned, cap * sizeof(double)));
+   PB_CUDA(cudaMalloc((void **)&ctx->d_small, cap * sizeof(double)));
+   PB_CUDA(cudaMalloc((void **)&ctx->d_panel, cap * sizeof(double)));
+   ctx->small_cap = cap;
+   return 0;
+}
+
+// out[e] = sum over parts p (ascending) of partials[p*cnt + e]: fixed order => reproducible.
+__global__ void pb_reduce_partials_kernel(
+      const double *__restrict__ partials, int nparts, int cnt, double *__restrict__ out) {
+   int e = blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= cnt) return;
+   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+   int p = 0;
+   for (; p + 4 <= nparts; p += 4) {
+      s0 += partials[(size_t)(p + 0) * cnt + e];
+      s1 += partials[(size_t)(p + 1) * cnt + e];
+      s2 += partials[(size_t)(p + 2) * cnt + e];
+      s3 += partials[(size_t)(p + 3) * cnt + e];
+   }
+   for (; p < nparts; p++) s0 += partials[(size_t)p * cnt + e];
+   out[e] = (s0 + s1) + (s2 + s3);
+}
+
+int pb_finish_panel(pb200_ctx *ctx, int nparts, int cnt) {
+   if (cnt <= 0) return 0;
+   PB_CHK(pb_ensure_small(ctx, (size_t)cnt));
+   pb_reduce_partials_kernel<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(
+         ctx->d_partials, nparts, cnt, ctx->d_panel);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   if (ctx->nranks > 1) PB_CHK(pb_nccl_allreduce_dev(ctx, ctx->d_panel, cnt));
+   PB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_panel, (size_t)cnt * sizeof(double),
+         cudaMemcpyDeviceToHost, ctx->stream));
+   PB_CUDA(cudaStreamSynchronize(ctx->stream));
+   return 0;
+}
+
+// ---------------------------------------------------------------------------- memory ------
+extern "C" int pb200_malloc(pb200_ctx *ctx, size_t bytes, void **dptr) {
+   (void)ctx;
+   cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 16);
+   if (e != cudaSuccess) {
+      cudaGetLastError();
+      *dptr = NULL;
+      return PB200_ERR_ALLOC;
+   }
+   return 0;
+}
+extern "C" int pb200_free(pb200_ctx *ctx, void *dptr) {
+   if (!dptr) return 0;
+   if (ctx) PB_CUDA(cudaStreamSynchronize(ctx->stream));
+   PB_CUDA(cudaFree(dptr));
+   return 0;
+}
+extern "C" int pb200_memset0(pb200_ctx *ctx, void *dptr, size_t bytes) {
+   PB_CUDA(cudaMemsetAsync(dptr, 0, bytes, ctx->stream));
+   return 0;
+}
+static int copy2d(pb200_ctx *ctx, const void *s, int64_t lds, void *d, int64_t ldd, int64_t rows,
+      int cols, int es, cudaMemcpyKind kind) {
+   if (rows <= 0 || cols <= 0) return 0;
+   PB_CUDA(cudaMemcpy2DAsync(d, (size_t)ldd * es, s, (size_t)lds * es, (size_t)rows * es,
+         (size_t)cols, kind, ctx->stream));
+   // host-visible copies complete before returning (pageable host memory may be reused)
+   if (kind != cudaMemcpyDeviceToDevice) PB_CUDA(cudaStreamSynchronize(ctx->stream));
+   return 0;
+}
+extern "C" int pb200_copy_h2d(pb200_ctx *ctx, const void *s, int64_t lds, void *d, int64_t ldd,
+      int64_t rows, int cols, int es) {
+   return copy2d(ctx, s, lds, d, ldd, rows, cols, es, cudaMemcpyHostToDevice);
+}
+extern "C" int pb200_copy_d2h(pb200_ctx *ctx, const void *s, int64_t lds, void *d, int64_t ldd,
+      int64_t rows, int cols, int es) {
+   return copy2d(ctx, s, lds, d, ldd, rows, cols, es, cudaMemcpyDeviceToHost);
+}
+extern "C" int pb200_copy_d2d(pb200_ctx *ctx, const void *s, int64_t lds, void *d, int64_t ldd,
+      int64_t rows, int cols, int es) {
+   return copy2d(ctx, s, lds, d, ldd, rows, cols, es, cudaMemcpyDeviceToDevice);
+}
+extern "C" int pb200_is_device_pointer(const void *p) {
+   cudaPointerAttributes a;
+   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+   }
+   return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------ NCCL ------
+// NCCL is resolved at run time (dlopen) so that single-GPU users need no libnccl at link time.
+typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_bcast_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+static nccl_allreduce_fn p_ncclAllReduce = NULL;
+static nccl_bcast_fn p_ncclBroadcast = NULL;
+enum { PB_NCCL_FLOAT64 = 8, PB_NCCL_SUM = 0 };
+
+static int pb_nccl_load(void) {
+   if (p_ncclAllReduce) return 0;
+   void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+   if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+   if (!h) {
+      fprintf(stderr, "primme_b200: cannot dlopen libnccl: %s\n", dlerror());
+      return PB200_ERR_CUDA;
+   }
+   p_ncclAllReduce = (nccl_allreduce_fn)dlsym(h, "ncclAllReduce");
+   p_ncclBroadcast = (nccl_bcast_fn)dlsym(h, "ncclBroadcast");
+   return (p_ncclAllReduce && p_ncclBroadcast) ? 0 : PB200_ERR_CUDA;
+}
+
+extern "C" int pb200_ctx_set_comm(pb200_ctx *ctx, void *nccl_comm, int nranks, int rank) {
+   if (nranks <= 1) {
+      ctx->comm = NULL, ctx->nranks = 1, ctx->rank = 0;
+      return 0;
+   }
+   PB_CHK(pb_nccl_load());
+   ctx->comm = nccl_comm, ctx->nranks = nranks, ctx->rank = rank;
+   return 0;
+}
+
+int pb_nccl_allreduce_dev(pb200_ctx *ctx, double *dbuf, int count) {
+   if (ctx->nranks <= 1) return 0;
+   int r = p_ncclAllReduce(dbuf, dbuf, (size_t)count, PB_NCCL_FLOAT64, PB_NCCL_SUM, ctx->comm,
+         ctx->stream);
+   if (r != 0) {
+      fprintf(stderr, "primme_b200: ncclAllReduce failed (%d)\n", r);
+      return PB200_ERR_CUDA;
+   }
+   return 0;
+}
+
+extern "C" int pb200_allreduce_host(pb200_ctx *ctx, double *buf, int count) {
+   if (ctx->nranks <= 1 || count <= 0) return 0;
+   PB_CHK(pb_ensure_small(ctx, (size_t)count));
+   memcpy(ctx->h_pinned, buf, sizeof(double) * count);
+   PB_CUDA(cudaMemcpyAsync(ctx->d_panel, ctx->h_pinned, sizeof(double) * count,
+         cudaMemcpyHostToDevice, ctx->stream));
+   PB_CHK(pb_nccl_allreduce_dev(ctx, ctx->d_panel, count));
+   PB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_panel, sizeof(double) * count,
+         cudaMemcpyDeviceToHost, ctx->stream));
+   PB_CUDA(cudaStreamSynchronize(ctx->stream));
+   memcpy(buf, ctx->h_pinned, sizeof(double) * count);
+   return 0;
+}
+
+extern "C" int pb200_bcast_host(pb200_ctx *ctx, double *buf, int count, int root) {
+   if (ctx->nranks <= 1 || count <= 0) return 0;
+   PB_CHK(pb_ensure_small(ctx, (size_t)count));
+   memcpy(ctx->h_pinned, buf, sizeof(double) * count);
+   PB_CUDA(cudaMemcpyAsync(ctx->d_panel, ctx->h_pinned, sizeof(double) * count,
+         cudaMemcpyHostToDevice, ctx->stream));
+   int r = p_ncclBroadcast(ctx->d_panel, ctx->d_panel, (size_t)count, PB_NCCL_FLOAT64, root,
+         ctx->comm, ctx->stream);
+   if (r != 0) return PB200_ERR_CUDA;
+   PB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_panel, sizeof(double) * count,
+         cudaMemcpyDeviceToHost, ctx->stream));
+   PB_CUDA(cudaStreamSynchronize(ctx->stream));
+   memcpy(buf, ctx->h_pinned, sizeof(double) * count);
+   return 0;
+}

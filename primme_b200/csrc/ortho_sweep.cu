@@ -1,0 +1,336 @@
+// ortho_sweep.cu -- K2/K3/K4: fused block-orthogonalisation row sweep (fp64).
+//
+//    X <- (X - [Q V] C) Y        (optional update;  reference src/eigs/ortho.c:1017-1038)
+//    P  = [Q V (X)]^H X          (optional Gram panel; ortho.c:1043-1059, and
+//                                 update_projection.c:99-102 when X is the new W block)
+//
+// HBM-bound (0.5-2 flop/B): the basis is streamed exactly once per sweep.  Work decomposition
+// per CTA (256 threads, persistent over 256-row tiles):
+//   phase 1 (update): thread <-> row.  Coalesced column reads of [Q V], C and Y broadcast from
+//            shared memory, new X row written back and parked in shared memory.
+//   phase 2 (Gram):   warp <-> CPW basis columns, lane <-> rows of the tile.  k*b accumulators
+//            are spread over the CTA (CPW*BT per thread) and live in registers across all
+//            tiles; the tile of [Q V] touched in phase 1 is re-read through L1/L2, not HBM.
+//   epilogue: warp-shuffle reduction, one partial panel per CTA, fixed-order second stage
+//            (pb_finish_panel) => bitwise reproducible panels.
+#include "pb200_internal.cuh"
+#include <string.h>
+
+namespace {
+
+constexpr int TILE = 256;  // rows per tile == threads per CTA
+constexpr int NWARP = TILE / 32;
+
+struct SweepArgs {
+   const double *Q;
+   const double *V;
+   double *X;
+   int64_t n, ldq, ldv, ldx;
+   int q, mv, b;
+   int do_update, has_Y, do_gram, xx;
+   const double *Cdev;  // (q+mv) x BT, column stride = (q+mv)
+   const double *Ydev;  // BT x BT, column stride BT
+   double *partials;    // [gridDim.x][(k + xx*b) * b]
+};
+
+__device__ __forceinline__ const double *col_ptr(const SweepArgs &a, int j) {
+   return j < a.q ? a.Q + (size_t)j * a.ldq : a.V + (size_t)(j - a.q) * a.ldv;
+}
+
+template <int BT, int CPW>
+__global__ void __launch_bounds__(TILE) ortho_sweep_kernel(SweepArgs a) {
+   extern __shared__ double smem[];
+   const int k = a.q + a.mv;
+   double *Cs = smem;                 // k * BT
+   double *Ys = Cs + (size_t)k * BT;  // BT * BT
+   double *xs = Ys + BT * BT;         // BT * TILE  (new X tile, [c][row])
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+   if (a.do_update) {
+      for (int i = tid; i < k * BT; i += TILE) {
+         int j = i % k, c = i / k;
+         Cs[j * BT + c] = (c < a.b) ? a.Cdev[j + (size_t)c * k] : 0.0;
+      }
+      for (int i = tid; i < BT * BT; i += TILE) {
+         int r = i % BT, c = i / BT;
+         double y = (r == c) ? 1.0 : 0.0;
+         if (a.has_Y) y = (r < a.b && c < a.b) ? a.Ydev[r + c * BT] : 0.0;
+         Ys[r * BT + c] = y;
+      }
+   }
+   __syncthreads();
+
+   // Gram accumulators: this warp owns basis columns [warp*CPW, warp*CPW+CPW)
+   double acc[CPW][BT];
+   double accx[BT];
+#pragma unroll
+   for (int j = 0; j < CPW; j++)
+#pragma unroll
+      for (int c = 0; c < BT; c++) acc[j][c] = 0.0;
+#pragma unroll
+   for (int c = 0; c < BT; c++) accx[c] = 0.0;
+
+   const double *cols[CPW];
+#pragma unroll
+   for (int j = 0; j < CPW; j++) {
+      int jj = warp * CPW + j;
+      cols[j] = jj < k ? col_ptr(a, jj) : nullptr;
+   }
+
+   const int64_t ntiles = (a.n + TILE - 1) / TILE;
+   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t r0 = tile * TILE;
+      // ---------------- phase 1: per-row update, park new X rows in shared memory -------
+      {
+         const int64_t r = r0 + tid;
+         double x[BT];
+#pragma unroll
+         for (int c = 0; c < BT; c++)
+            x[c] = (r < a.n && c < a.b) ? a.X[r + (size_t)c * a.ldx] : 0.0;
+         if (a.do_update && r < a.n) {
+            int j = 0;
+            for (; j + 4 <= k; j += 4) {  // 4 independent loads in flight per step
+               double v0 = col_ptr(a, j)[r], v1 = col_ptr(a, j + 1)[r];
+               double v2 = col_ptr(a, j + 2)[r], v3 = col_ptr(a, j + 3)[r];
+#pragma unroll
+               for (int c = 0; c < BT; c++) {
+                  x[c] -= v0 * Cs[(j + 0) * BT + c];
+                  x[c] -= v1 * Cs[(j + 1) * BT + c];
+                  x[c] -= v2 * Cs[(j + 2) * BT + c];
+                  x[c] -= v3 * Cs[(j + 3) * BT + c];
+               }
+            }
+            for (; j < k; j++) {
+               double v0 = col_ptr(a, j)[r];
+#pragma unroll
+               for (int c = 0; c < BT; c++) x[c] -= v0 * Cs[j * BT + c];
+            }
+            if (a.has_Y) {
+               double y[BT];
+#pragma unroll
+               for (int c = 0; c < BT; c++) {
+                  double s = 0.0;
+#pragma unroll
+                  for (int cc = 0; cc < BT; cc++) s += x[cc] * Ys[cc * BT + c];
+                  y[c] = s;
+               }
+#pragma unroll
+               for (int c = 0; c < BT; c++) x[c] = y[c];
+            }
+#pragma unroll
+            for (int c = 0; c < BT; c++)
+               if (c < a.b) a.X[r + (size_t)c * a.ldx] = x[c];
+         }
+#pragma unroll
+         for (int c = 0; c < BT; c++) xs[c * TILE + tid] = x[c];
+      }
+      __syncthreads();
+      // ---------------- phase 2: Gram accumulation, columns split over warps ------------
+      if (a.do_gram) {
+#pragma unroll 2
+         for (int i = 0; i < TILE / 32; i++) {
+            const int row = i * 32 + lane;
+            const int64_t r = r0 + row;
+            double xv[BT];
+#pragma unroll
+            for (int c = 0; c < BT; c++) xv[c] = xs[c * TILE + row];
+            double av[CPW];
+#pragma unroll
+            for (int j = 0; j < CPW; j++) av[j] = (cols[j] && r < a.n) ? cols[j][r] : 0.0;
+#pragma unroll
+            for (int j = 0; j < CPW; j++)
+#pragma unroll
+               for (int c = 0; c < BT; c++) acc[j][c] += av[j] * xv[c];
+            if (a.xx && warp < a.b) {
+               double xw = xs[warp * TILE + row];
+#pragma unroll
+               for (int c = 0; c < BT; c++) accx[c] += xw * xv[c];
+            }
+         }
+      }
+      __syncthreads();
+   }
+
+   if (!a.do_gram) return;
+   // ---------------- epilogue: lane reduction, one partial panel per CTA ----------------
+   const int rows = k + (a.xx ? a.b : 0);
+   double *out = a.partials + (size_t)blockIdx.x * rows * a.b;
+#pragma unroll
+   for (int j = 0; j < CPW; j++) {
+#pragma unroll
+      for (int c = 0; c < BT; c++) {
+         double v = acc[j][c];
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+         int jj = warp * CPW + j;
+         if (lane == 0 && jj < k && c < a.b) out[jj + (size_t)c * rows] = v;
+      }
+   }
+   if (a.xx) {
+#pragma unroll
+      for (int c = 0; c < BT; c++) {
+         double v = accx[c];
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+         if (lane == 0 && warp < a.b && c < a.b) out[k + warp + (size_t)c * rows] = v;
+      }
+   }
+}
+
+template <int BT, int CPW>
+int launch_sweep(pb200_ctx *ctx, const SweepArgs &a, int grid, size_t shmem) {
+   auto kern = ortho_sweep_kernel<BT, CPW>;
+   if (shmem > 48 * 1024)
+      PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+   kern<<<grid, TILE, shmem, ctx->stream>>>(a);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   return 0;
+}
+
+template <int BT>
+int dispatch_cpw(pb200_ctx *ctx, const SweepArgs &a, int cpw, int grid, size_t shmem) {
+   switch (cpw) {
+   case 1: return launch_sweep<BT, 1>(ctx, a, grid, shmem);
+   case 2: return launch_sweep<BT, 2>(ctx, a, grid, shmem);
+   case 3: return launch_sweep<BT, 3>(ctx, a, grid, shmem);
+   case 4: return launch_sweep<BT, 4>(ctx, a, grid, shmem);
+   case 5: return launch_sweep<BT, 5>(ctx, a, grid, shmem);
+   case 6: return launch_sweep<BT, 6>(ctx, a, grid, shmem);
+   case 7:
+   case 8: return launch_sweep<BT, 8>(ctx, a, grid, shmem);
+   case 9:
+   case 10: return launch_sweep<BT, 10>(ctx, a, grid, shmem);
+   case 11:
+   case 12: return launch_sweep<BT, 12>(ctx, a, grid, shmem);
+   default: return PB200_ERR_ARG;
+   }
+}
+
+}  // namespace
+
+// Maximum number of basis columns one launch handles (NWARP * 12); more are chunked.
+static const int KMAX = NWARP * 12;
+
+static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t ldq,
+      const double *V, int mv, int64_t ldv, double *X, int b, int64_t ldx, const double *C_host,
+      int ldc, const double *Y_host, int ldy, int xx, double *P_host, int ldp) {
+   const int k = q + mv;
+   const int BT = b <= 1 ? 1 : b <= 2 ? 2 : b <= 4 ? 4 : 8;
+   SweepArgs a;
+   memset(&a, 0, sizeof(a));
+   a.Q = Q, a.V = V, a.X = X, a.n = n, a.ldq = ldq, a.ldv = ldv, a.ldx = ldx;
+   a.q = q, a.mv = mv, a.b = b;
+   a.do_update = C_host != NULL || Y_host != NULL;
+   a.has_Y = Y_host != NULL;
+   a.do_gram = P_host != NULL;
+   a.xx = xx ? 1 : 0;
+
+   // stage C (k x b, compacted to ld k) and Y (b x b, ld BT) through the pinned buffer
+   if (a.do_update) {
+      size_t need = (size_t)k * BT + BT * BT;
+      PB_CHK(pb_ensure_small(ctx, need));
+      // the pinned staging buffer may still feed an earlier async copy
+      PB_CUDA(cudaStreamSynchronize(ctx->stream));
+      double *hp = ctx->h_pinned;
+      for (int c = 0; c < b; c++)
+         for (int j = 0; j < k; j++) hp[j + (size_t)c * k] = C_host ? C_host[j + (size_t)c * ldc] : 0.0;
+      double *hy = hp + (size_t)k * BT;
+      for (int i = 0; i < BT * BT; i++) hy[i] = 0.0;
+      if (Y_host)
+         for (int c = 0; c < b; c++)
+            for (int r = 0; r < b; r++) hy[r + c * BT] = Y_host[r + (size_t)c * ldy];
+      PB_CUDA(cudaMemcpyAsync(ctx->d_small, hp, need * sizeof(double), cudaMemcpyHostToDevice,
+            ctx->stream));
+      a.Cdev = ctx->d_small;
+      a.Ydev = ctx->d_small + (size_t)k * BT;
+   }
+
+   const int64_t ntiles = (n + TILE - 1) / TILE;
+   int grid = (int)(ntiles < (int64_t)ctx->num_sms * 3 ? ntiles : (int64_t)ctx->num_sms * 3);
+   if (grid < 1) grid = 1;
+   const int rows = k + (a.xx ? b : 0);
+   if (a.do_gram) {
+      PB_CHK(pb_ensure_partials(ctx, (size_t)grid * rows * b));
+      a.partials = ctx->d_partials;
+   }
+   int cpw = (k + NWARP - 1) / NWARP;
+   if (cpw < 1) cpw = 1;
+   size_t shmem = ((size_t)k * BT + BT * BT + (size_t)BT * TILE) * sizeof(double);
+   int rc;
+   switch (BT) {
+   case 1: rc = dispatch_cpw<1>(ctx, a, cpw, grid, shmem); break;
+   case 2: rc = dispatch_cpw<2>(ctx, a, cpw, grid, shmem); break;
+   case 4: rc = dispatch_cpw<4>(ctx, a, cpw, grid, shmem); break;
+   default: rc = dispatch_cpw<8>(ctx, a, cpw, grid, shmem); break;
+   }
+   PB_CHK(rc);
+   if (a.do_gram) {
+      PB_CHK(pb_finish_panel(ctx, grid, rows * b));
+      for (int c = 0; c < b; c++)
+         for (int j = 0; j < rows; j++) P_host[j + (size_t)c * ldp] = ctx->h_pinned[j + (size_t)c * rows];
+   }
+   return 0;
+}
+
+extern "C" int pb200_dortho_sweep(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t ldq,
+      const double *V, int mv, int64_t ldv, double *X, int b, int64_t ldx, const double *C_host,
+      int ldc, const double *Y_host, int ldy, int xx, double *P_host, int ldp) {
+   if (b <= 0) return 0;
+   if (b > 8 || q < 0 || mv < 0) return PB200_ERR_ARG;
+   if (n <= 0) {
+      // empty local part (a rank may own no rows): the panel is all zeros
+      if (P_host) {
+         int rows = q + mv + (xx ? b : 0);
+         for (int c = 0; c < b; c++)
+            for (int j = 0; j < rows; j++) P_host[j + (size_t)c * ldp] = 0.0;
+         if (ctx->nranks > 1) {
+            /* still take part in the collective */
+            PB_CHK(pb_ensure_small(ctx, (size_t)rows * b));
+            PB_CUDA(cudaMemsetAsync(ctx->d_panel, 0, sizeof(double) * rows * b, ctx->stream));
+            PB_CHK(pb_nccl_allreduce_dev(ctx, ctx->d_panel, rows * b));
+            PB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_panel, sizeof(double) * rows * b,
+                  cudaMemcpyDeviceToHost, ctx->stream));
+            PB_CUDA(cudaStreamSynchronize(ctx->stream));
+            for (int c = 0; c < b; c++)
+               for (int j = 0; j < rows; j++)
+                  P_host[j + (size_t)c * ldp] = ctx->h_pinned[j + (size_t)c * rows];
+         }
+      }
+      return 0;
+   }
+   const int k = q + mv;
+   if (k <= KMAX)
+      return sweep_once(ctx, n, Q, q, ldq, V, mv, ldv, X, b, ldx, C_host, ldc, Y_host, ldy, xx,
+            P_host, ldp);
+
+   // More basis columns than one launch covers: (1) apply the update chunk by chunk (Y only
+   // with the last chunk), (2) compute the Gram panel chunk by chunk.
+   const bool upd = C_host != NULL || Y_host != NULL;
+   if (upd) {
+      for (int j0 = 0; j0 < k; j0 += KMAX) {
+         int j1 = j0 + KMAX < k ? j0 + KMAX : k;
+         int qa = j0 < q ? (j1 < q ? j1 : q) - j0 : 0;
+         int va0 = j0 > q ? j0 - q : 0;
+         int va = j1 > q ? (j1 - q) - va0 : 0;
+         bool last = j1 == k;
+         PB_CHK(sweep_once(ctx, n, Q + (size_t)j0 * ldq * (qa > 0), qa, ldq,
+               V + (size_t)va0 * ldv, va, ldv, X, b, ldx, C_host ? C_host + j0 : NULL, ldc,
+               last ? Y_host : NULL, ldy, 0, NULL, 0));
+         if (!C_host && !last) continue;
+      }
+   }
+   if (P_host) {
+      for (int j0 = 0; j0 < k; j0 += KMAX) {
+         int j1 = j0 + KMAX < k ? j0 + KMAX : k;
+         int qa = j0 < q ? (j1 < q ? j1 : q) - j0 : 0;
+         int va0 = j0 > q ? j0 - q : 0;
+         int va = j1 > q ? (j1 - q) - va0 : 0;
+         bool last = j1 == k;
+         PB_CHK(sweep_once(ctx, n, Q + (size_t)j0 * ldq * (qa > 0), qa, ldq,
+               V + (size_t)va0 * ldv, va, ldv, X, b, ldx, NULL, 0, NULL, 0, last ? xx : 0,
+               P_host + j0, ldp));
+      }
+   }
+   return 0;
+}

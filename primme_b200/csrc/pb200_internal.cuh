@@ -1,0 +1,52 @@
+// pb200_internal.cuh -- shared internals of the sm_100a kernel layer (context, error macros,
+// deterministic two-stage panel reduction).  Everything public is declared in
+// include/primme_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/primme_b200.h"
+
+#define PB_CUDA(call)                                                                  \
+   do {                                                                                \
+      cudaError_t e_ = (call);                                                         \
+      if (e_ != cudaSuccess) {                                                         \
+         fprintf(stderr, "primme_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), \
+               __FILE__, __LINE__);                                                    \
+         return PB200_ERR_CUDA;                                                        \
+      }                                                                                \
+   } while (0)
+
+#define PB_CHK(call)            \
+   do {                         \
+      int r_ = (call);          \
+      if (r_ != 0) return r_;   \
+   } while (0)
+
+struct pb200_ctx {
+   int device;
+   int num_sms;
+   cudaStream_t stream;
+   // staging for small operands and panels
+   double *h_pinned;      // pinned host buffer
+   double *d_small;       // device buffer for coefficient blocks (h, C, Y, theta, perms)
+   double *d_panel;       // device buffer for reduced panels
+   double *d_partials;    // per-CTA partial panels
+   size_t small_cap;      // capacity (doubles) of h_pinned / d_small / d_panel
+   size_t partials_cap;   // capacity (doubles) of d_partials
+   void *d_scratch;       // growable scratch (permute etc.)
+   size_t scratch_cap;
+   int64_t launches;
+   // NCCL (dlopen'ed lazily)
+   void *comm;
+   int nranks, rank;
+};
+
+// grow helpers (host side)
+int pb_ensure_partials(pb200_ctx *ctx, size_t doubles);
+int pb_ensure_scratch(pb200_ctx *ctx, size_t bytes);
+int pb_ensure_small(pb200_ctx *ctx, size_t doubles);
+// reduce ctx->d_partials [nparts x cnt] -> ctx->d_panel [cnt] (fixed order), optional NCCL
+// allreduce, copy to h_pinned and synchronize.  Result readable at ctx->h_pinned[0..cnt).
+int pb_finish_panel(pb200_ctx *ctx, int nparts, int cnt);
+int pb_nccl_allreduce_dev(pb200_ctx *ctx, double *dbuf, int count);

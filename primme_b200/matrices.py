@@ -1,0 +1,106 @@
+"""Deterministic synthetic CSR matrices of the benchmark configurations.
+
+All generators return (indptr int64, indices int32, data float64) with sorted column indices per
+row, 0-based, symmetric where stated.  The same bytes feed the reference CPU path and the GPU.
+"""
+import numpy as np
+
+
+def laplacian_1d(n):
+    """tridiag(-1, 2, -1) (reference examples/ex_eigs_dseq.c:160-178)"""
+    return laplacian_nd((n,))
+
+
+def laplacian_nd(shape):
+    """d-dimensional 2d+1 point Laplacian, natural ordering (first index fastest), Dirichlet.
+    3-D with N=100: the matrix of config C2 (nnz = 7N^3 - 6N^2)."""
+    shape = tuple(int(s) for s in shape)
+    d = len(shape)
+    n = int(np.prod(shape))
+    idx = np.arange(n, dtype=np.int64)
+    coords = []
+    rem = idx.copy()
+    for s in shape:
+        coords.append(rem % s)
+        rem //= s
+    strides = np.cumprod((1,) + shape[:-1]).astype(np.int64)
+    rows = [idx]
+    cols = [idx]
+    vals = [np.full(n, 2.0 * d)]
+    for ax in range(d):
+        m = coords[ax] > 0
+        rows.append(idx[m]); cols.append(idx[m] - strides[ax]); vals.append(np.full(m.sum(), -1.0))
+        m = coords[ax] < shape[ax] - 1
+        rows.append(idx[m]); cols.append(idx[m] + strides[ax]); vals.append(np.full(m.sum(), -1.0))
+    return _assemble(n, np.concatenate(rows), np.concatenate(cols), np.concatenate(vals))
+
+
+def _assemble(n, rows, cols, vals):
+    order = np.lexsort((cols, rows))
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(indptr, rows + 1, 1)
+    indptr = np.cumsum(indptr)
+    return indptr, cols.astype(np.int32), vals.astype(np.float64)
+
+
+def power_law_symmetric(n, mean_degree=15.0, exponent=2.1, seed=7):
+    """Chung-Lu style symmetric graph with expected degrees ~ k^-exponent, values U(0,1),
+    mirrored (config C5 family).  Duplicate edges are merged (values summed)."""
+    rng = np.random.default_rng(seed)
+    # expected degree sequence
+    u = rng.random(n)
+    kmin = 1.0
+    w = kmin * (1.0 - u) ** (-1.0 / (exponent - 1.0))
+    w = np.minimum(w, np.sqrt(n * mean_degree))
+    w *= mean_degree / w.mean()
+    m = int(n * mean_degree / 2)
+    p = w / w.sum()
+    cdf = np.cumsum(p)
+    a = np.searchsorted(cdf, rng.random(m)).astype(np.int64)
+    b = np.searchsorted(cdf, rng.random(m)).astype(np.int64)
+    a = np.minimum(a, n - 1); b = np.minimum(b, n - 1)
+    keep = a != b
+    a, b = a[keep], b[keep]
+    v = rng.random(a.size)
+    rows = np.concatenate([a, b]); cols = np.concatenate([b, a]); vals = np.concatenate([v, v])
+    # merge duplicates
+    key = rows * n + cols
+    order = np.argsort(key, kind="stable")
+    key, vals = key[order], vals[order]
+    uniq, start = np.unique(key, return_index=True)
+    vals = np.add.reduceat(vals, start)
+    rows, cols = uniq // n, uniq % n
+    return _assemble(n, rows, cols, vals)
+
+
+def random_rectangular(m, n, per_row=20, seed=2024):
+    """m x n rectangular CSR, per_row nonzeros per row at LCG-random columns, values U(-1,1)
+    (config C4 family)."""
+    rng = np.random.default_rng(seed)
+    cols = rng.integers(0, n, size=(m, per_row), dtype=np.int64)
+    cols.sort(axis=1)
+    vals = rng.uniform(-1.0, 1.0, size=(m, per_row))
+    rows = np.repeat(np.arange(m, dtype=np.int64), per_row)
+    key = rows * n + cols.ravel()
+    uniq, start = np.unique(key, return_index=True)
+    v = np.add.reduceat(vals.ravel()[np.argsort(key, kind="stable")], start)
+    return _assemble_rect(m, uniq // n, uniq % n, v)
+
+
+def _assemble_rect(m, rows, cols, vals):
+    order = np.lexsort((cols, rows))
+    rows, cols, vals = rows[order], cols[order], vals[order]
+    indptr = np.zeros(m + 1, dtype=np.int64)
+    np.add.at(indptr, rows + 1, 1)
+    return np.cumsum(indptr), cols.astype(np.int32), vals.astype(np.float64)
+
+
+def csr_matvec(indptr, indices, data, x):
+    """plain numpy y = A x (1-D or 2-D column block), for tests"""
+    x = np.asarray(x)
+    rows = np.repeat(np.arange(len(indptr) - 1), np.diff(indptr))
+    if x.ndim == 1:
+        return np.bincount(rows, weights=data * x[indices], minlength=len(indptr) - 1)
+    return np.stack([np.bincount(rows, weights=data * x[indices, j], minlength=len(indptr) - 1)
+                     for j in range(x.shape[1])], axis=1)

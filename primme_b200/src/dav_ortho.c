@@ -1,0 +1,409 @@
+/* dav_ortho.c -- block orthogonalisation of new basis columns.
+ *
+ * Restates reference src/eigs/ortho.c:
+ *   Bortho_block_gen (:497-803)  iterated CholQR / SVQB driven by the maintained Gram matrix
+ *                                VtBV and its Cholesky factor; the n-long work of every sweep
+ *                                (Num_ortho_kernel :963-1072) is ONE fused device launch
+ *                                pb200_dortho_sweep, the b x b algebra stays on the host.
+ *   Bortho_gen (:124-371)        classical Gram-Schmidt with reorthogonalisation (Daniel test)
+ *                                used when no Gram matrix is carried (orth implicit); each pass
+ *                                is one fused sweep: update with the previous overlaps + the
+ *                                overlaps/norm of the updated vector.
+ *   ortho_single_iteration (:826-934), update_cholesky (:1200-1220), rank_estimation (:1165),
+ *   decomposition (:1097), Bortho_local (:395-413).
+ * B = I only (no mass matrix).
+ */
+#include "pb_host.h"
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* Number of leading columns n0..i-1 judged linearly independent from the Gram matrix G:
+ * positive diagonal and |cos| to every earlier column below 0.8/maxRank (:1165-1181). */
+static int rank_estimation(const double *G, int n0, int n1, int maxRank, int ldG) {
+   int i, j;
+   for (i = n0; i < n1; i++) {
+      double gii = G[(size_t)i * ldG + i];
+      if (!isfinite(gii) || gii <= 0.0) break;
+      for (j = 0; j < i; j++)
+         if (fabs(G[(size_t)i * ldG + j]) > .8 / maxRank * sqrt(gii * G[(size_t)j * ldG + j])) break;
+      if (j < i) break;
+   }
+   return i;
+}
+
+/* Cholesky if possible, else eigen-decomposition with descending eigenvalues (:1097-1137). */
+static int decomposition(const double *C, int n, int ldC, double *Y, int ldY, double *evals,
+      int *Yortho) {
+   hl_copy(C, n, n, ldC, Y, ldY);
+   if (hl_potrf_upper(n, Y, ldY) == 0) {
+      *Yortho = 0;
+      for (int i = 0; i < n; i++) evals[i] = 1.0;
+      return 0;
+   }
+   for (int i = 0; i < n; i++)
+      for (int j = 0; j <= i; j++) Y[(size_t)ldY * i + j] = -C[(size_t)ldC * i + j];
+   if (hl_sygv_upper(n, Y, ldY, NULL, 0, evals) != 0) return PRIMME_LAPACK_FAILURE;
+   for (int i = 0; i < n; i++) evals[i] = -evals[i];
+   *Yortho = 1;
+   return 0;
+}
+
+/* Append columns n0..n-1 to the Cholesky factor of VtBV (:1200-1220). */
+int pb_update_cholesky(pb_solver *S, int n0, int n) {
+   if (!S->fVtBV || n <= n0) return 0;
+   const int ld = S->maxRank;
+   double *A = (double *)malloc(sizeof(double) * (size_t)n * (n - n0));
+   if (!A) return PRIMME_MALLOC_FAILURE;
+   hl_copy(&S->VtBV[(size_t)ld * n0], n, n - n0, ld, A, n);
+   hl_trsm('L', 'U', 'C', 'N', n0, n - n0, 1.0, S->fVtBV, ld, A, n);
+   hl_gemm('C', 'N', n - n0, n - n0, n0, -1.0, A, n, A, n, 1.0, &A[n0], n);
+   hl_potrf_upper(n - n0, &A[n0], n); /* failure is tolerated exactly as in the reference */
+   hl_copy(A, n, n - n0, n, &S->fVtBV[(size_t)ld * n0], ld);
+   free(A);
+   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * CGS with reorthogonalisation, device version (no Gram matrix carried).
+ * ---------------------------------------------------------------------------------------- */
+static int ortho_cgs(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const double *locked,
+      int64_t ldLocked, int numLocked, double *RLocked, int ldRLocked, int *b2_out) {
+   primme_params *primme = S->primme;
+   const int maxNumOrthos = 3, maxNumRandoms = 10;
+   const double tol = sqrt(2.0) / 2.0; /* Daniel et al. test */
+   const double eps_orth = PB_EPS;
+   const double t0 = hl_wtime();
+   int rc = 0;
+
+   if (RLocked) hl_zero(RLocked, numLocked, b2 - b1 + 1, ldRLocked);
+   double *panel = (double *)calloc((size_t)(numLocked + b2 + 2), sizeof(double));
+   double *coef = (double *)calloc((size_t)(numLocked + b2 + 2), sizeof(double));
+   if (!panel || !coef) return PRIMME_MALLOC_FAILURE;
+   *b2_out = b1;
+
+   for (int i = b1; i <= b2; i++) {
+      double *v = V + (size_t)ldV * i;
+      const int k = numLocked + i;
+      int nOrth = 0, randomizations = 0, updateR = RLocked ? 1 : 0, have_panel = 0;
+      double s0 = 0.0, s02 = 0.0, s1 = 0.0, s12 = 0.0;
+      for (;;) {
+         if (nOrth >= maxNumOrthos) {
+            updateR = 0;
+            if (randomizations >= maxNumRandoms) goto done;
+            rc = pb_fill_random(S, v, ldV, 1);
+            if (rc) goto done;
+            randomizations++;
+            nOrth = 0;
+            have_panel = 0;
+         }
+         nOrth++;
+         if (!have_panel) {
+            /* overlaps [locked V(:,0:i)]' v and v'v in one sweep (:230-250) */
+            rc = pb200_dortho_sweep(S->dev, S->n, locked, numLocked, ldLocked, V, i, ldV, v, 1,
+                  ldV, NULL, 0, NULL, 0, 1, panel, k + 1);
+            if (rc) goto done;
+            rc = pb_reduce_panel(S, panel, k + 1, 1, k + 1);
+            if (rc) goto done;
+            primme->stats.numOrthoInnerProds += k + 1;
+         }
+         if (nOrth == 1) s02 = panel[k];
+         if (updateR)
+            for (int j = 0; j < numLocked; j++) RLocked[(size_t)ldRLocked * (i - b1) + j] += panel[j];
+         memcpy(coef, panel, sizeof(double) * k);
+         /* v -= [locked V] * overlaps, then the overlaps and norm of the new v (:262-291) */
+         rc = pb200_dortho_sweep(S->dev, S->n, locked, numLocked, ldLocked, V, i, ldV, v, 1, ldV,
+               coef, k, NULL, 0, 1, panel, k + 1);
+         if (rc) goto done;
+         rc = pb_reduce_panel(S, panel, k + 1, 1, k + 1);
+         if (rc) goto done;
+         have_panel = 1;
+         primme->stats.numOrthoInnerProds += 2 * k + 1;
+         if (nOrth == 1) s0 = sqrt(s02);
+         s12 = panel[k];
+         s1 = sqrt(s12);
+
+         if (!isfinite(s0) || !isfinite(s1) || s1 <= eps_orth * s0) {
+            nOrth = maxNumOrthos; /* lost all significant digits: randomise */
+         } else if (s1 <= tol * s0) {
+            s0 = s1, s02 = s12; /* reorthogonalise */
+         } else {
+            double inv = 1.0 / s1;
+            if (isfinite(inv)) {
+               rc = pb200_dscale_columns(S->dev, S->n, &inv, v, ldV, 1);
+               if (rc) goto done;
+               break;
+            }
+            nOrth = maxNumOrthos;
+         }
+      }
+      *b2_out = i + 1;
+   }
+done:
+   primme->stats.timeOrtho += hl_wtime() - t0;
+   free(panel), free(coef);
+   return rc;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Block orthogonalisation of V(:,b1:b2) (b2 inclusive) against [locked V(:,0:b1)] and itself.
+ * With S->VtBV: iterated CholQR/SVQB (:497-803); columns b1..b2 of the Gram matrix
+ * [locked V]'[locked V] and of its Cholesky factor are updated.  Without: CGS.
+ * ---------------------------------------------------------------------------------------- */
+int pb_ortho_block(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const double *locked,
+      int64_t ldLocked, int numLocked, double *RLocked, int ldRLocked, int *b2_out) {
+   primme_params *primme = S->primme;
+   b2++; /* C range convention from here on */
+   if (b2 <= b1) {
+      *b2_out = b2;
+      return 0;
+   }
+   if (!S->VtBV)
+      return ortho_cgs(S, V, ldV, b1, b2 - 1, locked, ldLocked, numLocked, RLocked, ldRLocked, b2_out);
+
+   /* the device sweep handles at most 8 columns at a time: larger blocks (initial guesses,
+    * re-orthogonalisation of the whole basis) go chunk by chunk */
+   if (b2 - b1 > 8) {
+      int cur = b1;
+      while (cur < b2) {
+         int hi = PB_MIN(cur + 8, b2), out = 0;
+         CHK(pb_ortho_block(S, V, ldV, cur, hi - 1, locked, ldLocked, numLocked,
+               RLocked ? RLocked + (size_t)ldRLocked * (cur - b1) : NULL, ldRLocked, &out));
+         if (out < hi) {
+            *b2_out = out;
+            return 0;
+         }
+         cur = hi;
+      }
+      *b2_out = b2;
+      return 0;
+   }
+
+   const double eps_orth = PB_EPS;
+   const double t0 = hl_wtime();
+   const int nb = b2 - b1, nVL = b1 + numLocked, ldG = S->maxRank;
+   double *G = S->VtBV, *fG = S->fVtBV;
+   double *A = &G[(size_t)ldG * nVL]; /* new columns of the Gram matrix */
+   int rc = 0;
+
+   double *D = (double *)malloc(sizeof(double) * nb), *N = (double *)malloc(sizeof(double) * nb);
+   double *GdA = (double *)malloc(sizeof(double) * (size_t)(nVL > 0 ? nVL : 1) * nb);
+   double *Y = (double *)malloc(sizeof(double) * nb * nb), *Yapply = (double *)malloc(sizeof(double) * nb * nb);
+   double *C = (double *)malloc(sizeof(double) * nb * nb), *r = NULL;
+   if (!D || !N || !GdA || !Y || !C || !Yapply) return PRIMME_MALLOC_FAILURE;
+   if (RLocked) {
+      hl_zero(RLocked, numLocked, nb, ldRLocked);
+      r = (double *)calloc((size_t)nb * nb, sizeof(double));
+      for (int i = 0; i < nb; i++) r[(size_t)nb * i + i] = 1.0;
+   }
+
+   *b2_out = b2;
+   const int maxits = 5;
+   int plus1 = 5, Yortho = 1;
+   for (int its = 0; its < maxits; its++) {
+      /* one row sweep: X <- (X - [locked V] GdA) Yapply (not in the first pass), then the
+       * Gram panel A = [locked V(:,0:b2)]' X  (:631-636, kernel :963-1072) */
+      const double *Cc = NULL, *Yc = NULL;
+      if (its > 0) {
+         Cc = GdA;
+         if (Yortho) {
+            /* X*Y*diag(1/D) (:1008-1012,1030-1034) */
+            for (int j = 0; j < nb; j++)
+               for (int i = 0; i < nb; i++) Yapply[(size_t)nb * j + i] = Y[(size_t)nb * j + i] * (1.0 / D[j]);
+         } else if (nb == 1) {
+            Yapply[0] = 1.0 / Y[0]; /* (:976-981) */
+         } else {
+            /* X*inv(U), U upper triangular Cholesky factor (:1035-1038) */
+            hl_zero(Yapply, nb, nb, nb);
+            for (int i = 0; i < nb; i++) Yapply[(size_t)nb * i + i] = 1.0;
+            hl_trsm('R', 'U', 'N', 'N', nb, nb, 1.0, Y, nb, Yapply, nb);
+         }
+         Yc = Yapply;
+      }
+      rc = pb200_dortho_sweep(S->dev, S->n, locked, numLocked, ldLocked, V, b1, ldV,
+            V + (size_t)ldV * b1, nb, ldV, Cc, nVL > 0 ? nVL : 1, Yc, nb, 1, A, ldG);
+      if (rc) goto done;
+      rc = pb_reduce_panel(S, A, nVL + nb, nb, ldG);
+      if (rc) goto done;
+      primme->stats.numOrthoInnerProds += (double)nVL * nb + (double)nb * nb;
+
+      /* stop one sweep after the block first looks well conditioned (:652-665) */
+      if (rank_estimation(G, nVL, numLocked + b2, S->maxRank, ldG) == numLocked + b2) {
+         if (its >= plus1) {
+            int i;
+            for (i = b1; i < b2 && fabs(G[(size_t)ldG * (numLocked + i) + numLocked + i] - 1.0) < .8; i++)
+               ;
+            if (i >= b2) break;
+         } else
+            plus1 = PB_MIN(its + 1, plus1);
+      }
+
+      /* overflowed norms: drop the inner products with the other vectors (:668-674) */
+      for (int i = 0; i < nb; i++) {
+         if (A[(size_t)ldG * i + i] < DBL_MAX) continue;
+         hl_zero(&G[(size_t)ldG * (numLocked + i)], numLocked + i, 1, ldG);
+         A[(size_t)ldG * i + i] = DBL_MAX;
+      }
+
+      /* C = X'X - (X'Vp) inv(Vp'Vp) (Vp'X), GdA = inv(Vp'Vp) Vp'X  (:682-691) */
+      hl_copy(&A[nVL], nb, nb, ldG, C, nb);
+      hl_copy(A, nVL, nb, ldG, GdA, nVL > 0 ? nVL : 1);
+      hl_trsm('L', 'U', 'C', 'N', nVL, nb, 1.0, fG, ldG, GdA, nVL > 0 ? nVL : 1);
+      hl_gemm('C', 'N', nb, nb, nVL, -1.0, GdA, nVL > 0 ? nVL : 1, GdA, nVL > 0 ? nVL : 1, 1.0, C, nb);
+      hl_trsm('L', 'U', 'N', 'N', nVL, nb, 1.0, fG, ldG, GdA, nVL > 0 ? nVL : 1);
+
+      for (int i = 0; i < nb; i++) N[i] = sqrt(PB_MAX(fabs(C[(size_t)nb * i + i]), eps_orth));
+      for (int i = 0; i < nb; i++)
+         for (int j = 0; j <= i; j++) C[(size_t)nb * i + j] /= N[i] * N[j];
+
+      rc = decomposition(C, nb, nb, Y, nb, D, &Yortho);
+      if (rc) goto done;
+      for (int i = 0; i < nb; i++) D[i] = sqrt(PB_MAX(D[i], eps_orth * nb));
+
+      if (RLocked) {
+         /* accumulate the rotations applied to the block (:718-757) */
+         hl_gemm('N', 'N', numLocked, nb, nb, 1.0, GdA, nVL > 0 ? nVL : 1, r, nb, 1.0, RLocked, ldRLocked);
+         for (int i = 0; i < nb; i++)
+            for (int j = 0; j < nb; j++) r[(size_t)nb * i + j] *= N[j];
+         if (Yortho)
+            hl_gemm('C', 'N', nb, nb, nb, 1.0, Y, nb, r, nb, 0.0, C, nb);
+         else {
+            /* C = U * r */
+            for (int j = 0; j < nb; j++)
+               for (int i = 0; i < nb; i++) {
+                  double s = 0.0;
+                  for (int l = i; l < nb; l++) s += Y[(size_t)nb * l + i] * r[(size_t)nb * j + l];
+                  C[(size_t)nb * j + i] = s;
+               }
+         }
+         for (int i = 0; i < nb; i++)
+            for (int j = 0; j < nb; j++) r[(size_t)nb * i + j] = D[j] * C[(size_t)nb * i + j];
+      }
+
+      /* fold the column scaling into Y (:760-772) */
+      if (Yortho) {
+         for (int i = 0; i < nb; i++)
+            for (int j = 0; j < nb; j++) Y[(size_t)nb * i + j] /= N[j];
+      } else {
+         for (int i = 0; i < nb; i++)
+            for (int j = 0; j < nb; j++) Y[(size_t)nb * i + j] *= N[i];
+      }
+   }
+
+   b2 = rank_estimation(G, nVL, numLocked + b2, S->maxRank, ldG) - numLocked;
+   *b2_out = b2;
+   rc = pb_update_cholesky(S, nVL, numLocked + b2);
+done:
+   free(D), free(N), free(GdA), free(Y), free(Yapply), free(C), free(r);
+   primme->stats.timeOrtho += hl_wtime() - t0;
+   return rc;
+}
+
+/* X(:,inX) <- (I - Q inv(Q'Q) Q') X(:,inX), norms of the results (:826-934). */
+int pb_ortho_single_iteration(pb_solver *S, const double *Q, int nQ, int64_t ldQ,
+      const double *QtQ, int ldQtQ, double *X, const int *inX, int nX, int64_t ldX,
+      double *norms) {
+   primme_params *primme = S->primme;
+   const double t0 = hl_wtime();
+   (void)QtQ, (void)ldQtQ; /* reference computes z = QtQ\y but applies y (:885-906): same here */
+   double *panel = (double *)malloc(sizeof(double) * (size_t)(nQ + 1));
+   if (!panel) return PRIMME_MALLOC_FAILURE;
+   for (int j = 0; j < nX; j++) {
+      double *x = X + (size_t)ldX * (inX ? inX[j] : j);
+      CHK(pb200_dortho_sweep(S->dev, S->n, Q, nQ, ldQ, NULL, 0, 0, x, 1, ldX, NULL, 0, NULL, 0, 0,
+            panel, nQ + 1));
+      CHK(pb_reduce_panel(S, panel, nQ, 1, nQ + 1));
+      CHK(pb200_dortho_sweep(S->dev, S->n, Q, nQ, ldQ, NULL, 0, 0, x, 1, ldX, panel, nQ + 1, NULL,
+            0, 1, norms ? panel : NULL, nQ + 1));
+      if (norms) {
+         CHK(pb_reduce_panel(S, panel, nQ + 1, 1, nQ + 1));
+         norms[j] = sqrt(panel[nQ]);
+      }
+   }
+   primme->stats.numOrthoInnerProds += (double)nQ * nX + (norms ? nX : 0);
+   free(panel);
+   primme->stats.timeOrtho += hl_wtime() - t0;
+   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Host-only Gram-Schmidt on small coefficient vectors with inner product B (upper stored) or
+ * identity (reference Bortho_local :395-413 -> Bortho_gen with primme == NULL: up to 7
+ * passes, always reorthogonalise).  Orthonormalises V(:,b1..b2) against locked(:,0:numLocked)
+ * and V(:,0:b1).  R (column stride 1 x 1 use only) receives the final norm or 0 if the vector
+ * had to be replaced by a random one.  Returns 0 or -3.
+ * ---------------------------------------------------------------------------------------- */
+int pb_ortho_local(double *V, int ldV, double *R, int b1, int b2, double *locked, int ldLocked,
+      int numLocked, int n, const double *B, int ldB, long long *iseed) {
+   const int maxNumOrthos = 7, maxNumRandoms = 10;
+   const double tol = sqrt(2.0) / 2.0, eps_orth = PB_EPS;
+   double *overlaps = (double *)calloc((size_t)(b2 + 2 + numLocked), sizeof(double));
+   double *Bx = (double *)malloc(sizeof(double) * (n > 0 ? n : 1));
+   int ok = 1;
+   if (R) R[0] = 0.0; /* callers use ldR == 1, b1 == b2 == 0 */
+   for (int i = b1; i <= b2 && ok; i++) {
+      double *v = &V[(size_t)ldV * i];
+      int nOrth = 0, randomizations = 0, updateR = R ? 1 : 0, Bx_update = 0;
+      double s0 = 0, s02 = 0, s1 = 0, s12 = 0;
+      for (;;) {
+         if (nOrth >= maxNumOrthos) {
+            if (updateR) {
+               if (R) R[0] = 0.0;
+               updateR = 0;
+            }
+            if (randomizations >= maxNumRandoms) {
+               ok = 0;
+               break;
+            }
+            hl_larnv2(iseed, n, v);
+            randomizations++;
+            nOrth = 0;
+            Bx_update = 0;
+         }
+         nOrth++;
+         const double *bx = v;
+         if (B) {
+            if (!Bx_update) {
+               hl_zero(Bx, n, 1, n);
+               hl_symm_lu(n, 1, 1.0, B, ldB, v, ldV > n ? ldV : n, 0.0, Bx, n);
+            }
+            bx = Bx;
+         }
+         if (nOrth == 1) s02 = hl_dot(n, v, bx);
+         if (i > 0) hl_gemm('C', 'N', i, 1, n, 1.0, V, ldV, bx, n, 0.0, overlaps, i);
+         if (numLocked > 0)
+            hl_gemm('C', 'N', numLocked, 1, n, 1.0, locked, ldLocked, bx, n, 0.0, &overlaps[i], numLocked);
+         overlaps[i + numLocked] = s02;
+         if (numLocked > 0)
+            hl_gemm('N', 'N', n, 1, numLocked, -1.0, locked, ldLocked, &overlaps[i], numLocked, 1.0, v, n);
+         if (i > 0) hl_gemm('N', 'N', n, 1, i, -1.0, V, ldV, overlaps, i, 1.0, v, n);
+         Bx_update = 0;
+         if (nOrth == 1) s0 = sqrt(s02 = overlaps[i + numLocked]);
+         if (B) {
+            hl_zero(Bx, n, 1, n);
+            hl_symm_lu(n, 1, 1.0, B, ldB, v, ldV > n ? ldV : n, 0.0, Bx, n);
+            Bx_update = 1;
+            bx = Bx;
+         } else
+            bx = v;
+         s12 = hl_dot(n, v, bx);
+         s1 = sqrt(s12);
+         if (!isfinite(s0) || !isfinite(s1) || s1 <= eps_orth * s0) {
+            nOrth = maxNumOrthos;
+         } else if (s1 <= tol * s0 || nOrth < maxNumOrthos) {
+            s0 = s1, s02 = s12;
+         } else {
+            if (updateR && R) R[0] = s1;
+            double inv = 1.0 / s1;
+            if (isfinite(inv)) {
+               for (int t = 0; t < n; t++) v[t] *= inv;
+               break;
+            }
+            nOrth = maxNumOrthos;
+         }
+      }
+   }
+   free(overlaps), free(Bx);
+   return ok ? 0 : -3;
+}

@@ -1,0 +1,811 @@
+/* davidson.c -- outer block (Generalized/Jacobi-)Davidson iteration: the caller of the hot path.
+ *
+ * Restates the control flow of reference src/eigs/main_iter.c (main_iter_Sprimme :176-1444,
+ * prepare_candidates :1470-1709, copy_back_candidates :1745-1841, verify_norms :1864-1894),
+ * src/eigs/init.c (init_basis :125-238, init_block_krylov :258-323) and the GD/Olsen branch of
+ * src/eigs/correction.c (:134-381, computeRobustShift :524-601, mergeSort :637-693) for the
+ * configuration this library covers: Hermitian standard problem (B = I), Rayleigh-Ritz
+ * extraction, GD-family corrections (no inner QMR yet).  Decisions (flags, block selection,
+ * restart sizes, tolerances) follow the reference line by line so that iteration counts match;
+ * every n-long operation is a call into the sm_100a kernel layer (include/primme_b200.h):
+ *     candidates X,R,|R|   -> pb200_dvwxr            (Num_update_VWXR)
+ *     block ortho          -> pb200_dortho_sweep     (Num_ortho_kernel), see dav_ortho.c
+ *     W = A V              -> user matrixMatvec (pb200_dspmm for the built-in CSR operator)
+ *     H(:,new) = V' W      -> pb200_dortho_sweep     (update_projection), see dav_project.c
+ *     restart              -> pb200_dvwxr            (Num_aux_update_VWXR), see dav_restart.c
+ */
+#include "pb_host.h"
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define VtBV_BLK(S, off) ((S)->VtBV ? &(S)->VtBV[(size_t)(S)->maxRank * (off) + (off)] : NULL)
+
+/* ------------------------------------------------------------------------------------------
+ * Initial basis (init.c:125-323)
+ * ---------------------------------------------------------------------------------------- */
+static int init_block_krylov(pb_solver *S, int dv1, int dv2, int numLocked) {
+   primme_params *primme = S->primme;
+   const int numNew = dv2 - dv1 + 1;
+   if (numNew <= 0) return 0;
+   const int bs = numNew <= primme->maxBlockSize ? 1 : primme->maxBlockSize;
+   int nV = 0;
+
+   CHK(pb_fill_random(S, S->V + (size_t)S->ld * dv1, S->ld, bs));
+   CHK(pb_ortho_block(S, S->V, S->ld, dv1, dv1 + bs - 1, S->evecs, S->ldevecs, numLocked, NULL, 0, &nV));
+   if (nV != dv1 + bs) return PRIMME_UNEXPECTED_FAILURE;
+
+   int m = bs;
+   for (int i = dv1 + bs, mm = PB_MIN(m, dv2 - i + 1); i <= dv2; i += mm, mm = PB_MIN(mm, dv2 - i + 1)) {
+      /* next Krylov block: A*V(:,i-bs:...) lands in V(:,i:...), and is also W(:,i-bs:...) */
+      CHK(pb_apply_matvec(S, S->V + (size_t)S->ld * (i - bs), S->ld, S->V + (size_t)S->ld * i, S->ld, mm));
+      CHK(pb200_copy_d2d(S->dev, S->V + (size_t)S->ld * i, S->ld, S->W + (size_t)S->ld * (i - bs),
+            S->ld, S->n, mm, 8));
+      CHK(pb_ortho_block(S, S->V, S->ld, i, i + mm - 1, S->evecs, S->ldevecs, numLocked, NULL, 0, &nV));
+      if (nV < i + mm) {
+         CHK(pb_fill_random(S, S->V + (size_t)S->ld * nV, S->ld, i + mm - nV));
+         CHK(pb_ortho_block(S, S->V, S->ld, nV, i + mm - 1, S->evecs, S->ldevecs, numLocked, NULL, 0, &nV));
+      } else {
+         /* the reference re-enters Bortho_block with an empty range here: no-op */
+      }
+      if (nV != i + mm) return PRIMME_UNEXPECTED_FAILURE;
+   }
+   CHK(pb_apply_matvec(S, S->V + (size_t)S->ld * (dv2 - bs + 1), S->ld,
+         S->W + (size_t)S->ld * (dv2 - bs + 1), S->ld, bs));
+   return 0;
+}
+
+static int init_basis(pb_solver *S, int *basisSize, int *nextGuess, int *numGuesses) {
+   primme_params *primme = S->primme;
+   int initSize, random = 0;
+
+   if (primme->numOrthoConst > 0) {
+      int nV = 0;
+      CHK(pb_ortho_block(S, S->evecs, S->ldevecs, 0, primme->numOrthoConst - 1, NULL, 0, 0, NULL, 0, &nV));
+      if (nV != primme->numOrthoConst) return PRIMME_ORTHO_CONST_FAILURE;
+   }
+   initSize = PB_MIN(primme->locking ? primme->minRestartSize : primme->maxBasisSize, primme->initSize);
+   {
+      PRIMME_INT room = primme->n - primme->numOrthoConst;
+      if (room < initSize) initSize = (int)room;
+      if (initSize < 0) initSize = 0;
+   }
+   *numGuesses = primme->initSize - initSize;
+   *nextGuess = primme->numOrthoConst + initSize;
+   CHK(pb200_copy_d2d(S->dev, S->evecs + (size_t)S->ldevecs * primme->numOrthoConst, S->ldevecs,
+         S->V, S->ld, S->n, initSize, 8));
+
+   switch (primme->initBasisMode) {
+   case primme_init_krylov: random = 0; break;
+   case primme_init_random: random = PB_MAX(0, primme->minRestartSize - initSize); break;
+   case primme_init_user: random = PB_MAX(primme->maxBlockSize - initSize, 0); break;
+   default: return PRIMME_UNEXPECTED_FAILURE;
+   }
+   {
+      PRIMME_INT room = primme->n - primme->numOrthoConst - initSize;
+      if (room < random) random = (int)room;
+      if (random < 0) random = 0;
+   }
+   if (random > 0) CHK(pb_fill_random(S, S->V + (size_t)S->ld * initSize, S->ld, random));
+   *basisSize = initSize + random;
+
+   CHK(pb_ortho_block(S, S->V, S->ld, 0, *basisSize - 1, S->evecs, S->ldevecs,
+         primme->numOrthoConst, NULL, 0, basisSize));
+   CHK(pb_apply_matvec(S, S->V, S->ld, S->W, S->ld, *basisSize));
+
+   if (primme->initBasisMode == primme_init_krylov) {
+      int minRestartSize = primme->minRestartSize;
+      if (primme->n - primme->numOrthoConst < minRestartSize)
+         minRestartSize = (int)(primme->n - primme->numOrthoConst);
+      CHK(init_block_krylov(S, *basisSize, minRestartSize - 1, primme->numOrthoConst));
+      *basisSize = minRestartSize;
+   }
+   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * One candidates sweep: X = V*h, R = W*h - X*diag(theta), norms (main_iter.c:1656-1688)
+ * ---------------------------------------------------------------------------------------- */
+static int candidates_sweep(pb_solver *S, int basisSize, const double *hblk, const double *theta,
+      int nb, double *X, double *R, int computeXR, double *norms) {
+   primme_params *primme = S->primme;
+   const double t0 = hl_wtime();
+   pb200_vwxr_out o;
+   memset(&o, 0, sizeof(o));
+   if (computeXR) {
+      o.X[0].ptr = X, o.X[0].ld = S->ld, o.X[0].cb = 0, o.X[0].ce = nb;
+      o.R.ptr = R, o.R.ld = S->ld, o.R.cb = 0, o.R.ce = nb;
+      o.Rnorms_host = norms;
+   } else {
+      o.rb = 0, o.re = nb, o.rnorms_host = norms;
+   }
+   CHK(pb200_dvwxr(S->dev, S->n, S->V, S->W, basisSize, S->ld, hblk, S->maxBasis, nb, theta, &o));
+   if (primme->numProcs > 1 && pb200_ctx_nranks(S->dev) <= 1) {
+      for (int i = 0; i < nb; i++) norms[i] *= norms[i];
+      CHK(pb_global_sum(S, norms, nb));
+      for (int i = 0; i < nb; i++) norms[i] = sqrt(norms[i]);
+   }
+   primme->stats.timeDense += hl_wtime() - t0;
+   primme->stats.flopsDense += 2.0 * (double)S->n * basisSize * nb + 2.0 * (double)S->n * nb;
+   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * prepare_candidates (main_iter.c:1470-1709): fill the block with the first unconverged Ritz
+ * pairs, computing residuals as needed.
+ * ---------------------------------------------------------------------------------------- */
+static int prepare_candidates(pb_solver *S, int basisSize, double *X, double *R, int computeXR,
+      int remainedEvals, int blockNormsSize, int maxBlockSize, int numLocked, double *evals,
+      double *resNorms, int targetShiftIndex, int *blockSize, int *recentlyConverged,
+      double *smallestResNorm, int numConverged, int *reset, int nprevhVecs,
+      int practConvChecking) {
+   primme_params *primme = S->primme;
+   int *flags = S->flags, *iev = S->iev, *map = S->map;
+   double *hVals = S->hVals, *blockNorms = S->blockNorms, *basisNorms = S->basisNorms;
+   const int ldh = S->maxBasis;
+   int i, blki, lasti = -1, rc = 0;
+   (void)targetShiftIndex;
+
+   *blockSize = 0;
+   double *hValsBlock = (double *)malloc(sizeof(double) * (maxBlockSize > 0 ? maxBlockSize : 1));
+   double *hVecsBlock = (double *)malloc(sizeof(double) * (size_t)ldh * (maxBlockSize > 0 ? maxBlockSize : 1));
+   int *flagsBlock = (int *)malloc(sizeof(int) * (maxBlockSize > 0 ? maxBlockSize : 1));
+
+   for (i = 0; i < blockNormsSize; i++) hValsBlock[i] = hVals[iev[*blockSize + i]];
+   if (blockNormsSize > 0) {
+      for (*smallestResNorm = HUGE_VAL, i = 0; i < blockNormsSize; i++)
+         *smallestResNorm = PB_MIN(*smallestResNorm, blockNorms[i]);
+   }
+
+   /* carry the flags of the previous iteration to the pairs closest in angle (:1524-1533) */
+   pb_map_vecs(S->prevhVecs, basisSize, nprevhVecs, ldh, S->hVecs, 0, basisSize, ldh, map);
+   hl_permute_ints(flags, basisSize, map);
+
+   *recentlyConverged = 0;
+   for (;;) {
+      for (i = *blockSize; i < *blockSize + blockNormsSize; i++) flagsBlock[i - *blockSize] = flags[iev[i]];
+      rc = pb_check_convergence(S, X ? X + (size_t)S->ld * *blockSize : NULL, S->ld, computeXR,
+            R ? R + (size_t)S->ld * *blockSize : NULL, S->ld, computeXR, numLocked, 0,
+            blockNormsSize, flagsBlock, &blockNorms[*blockSize], hValsBlock, reset,
+            practConvChecking);
+      if (rc) goto done;
+
+      for (blki = *blockSize, i = 0; i < blockNormsSize && *blockSize < maxBlockSize; i++, blki++) {
+         flags[iev[blki]] = flagsBlock[i];
+         basisNorms[iev[blki]] = blockNorms[blki];
+         double shift = primme->targetShifts ? primme->targetShifts[targetShiftIndex] : 0.0;
+         if ((primme->target == primme_closest_leq && hVals[iev[blki]] - blockNorms[blki] > shift) ||
+               (primme->target == primme_closest_geq && hVals[iev[blki]] + blockNorms[blki] < shift)) {
+            /* wrong side of the shift: ignore */
+         } else if (flagsBlock[i] != UNCONVERGED && *recentlyConverged < remainedEvals &&
+                    (iev[blki] < primme->numEvals - numLocked ||
+                          primme->target == primme_closest_geq ||
+                          primme->target == primme_closest_leq)) {
+            if (!primme->locking) {
+               evals[iev[blki]] = hVals[iev[blki]];
+               resNorms[iev[blki]] = blockNorms[blki];
+               if (flagsBlock[i] == CONVERGED)
+                  primme->stats.maxConvTol = PB_MAX(primme->stats.maxConvTol, blockNorms[blki]);
+            }
+            (*recentlyConverged)++;
+            if (*blockSize == 0) *smallestResNorm = HUGE_VAL;
+            maxBlockSize = PB_MIN(maxBlockSize,
+                  primme->numEvals + 1 - *recentlyConverged - numConverged);
+            rc = pb_monitor(S, hVals, basisSize, flags, &iev[blki], 1, basisNorms,
+                  numConverged + *recentlyConverged, NULL, 0, NULL, NULL, -1, -1.0, NULL, 0.0,
+                  primme_event_converged);
+            if (rc) goto done;
+         } else if (flagsBlock[i] == UNCONVERGED) {
+            if (*blockSize == 0) *smallestResNorm = HUGE_VAL;
+            *smallestResNorm = PB_MIN(*smallestResNorm, blockNorms[blki]);
+            blockNorms[*blockSize] = blockNorms[blki];
+            iev[*blockSize] = iev[blki];
+            if (computeXR && blki != *blockSize) {
+               rc = pb200_copy_d2d(S->dev, X + (size_t)S->ld * blki, S->ld,
+                     X + (size_t)S->ld * *blockSize, S->ld, S->n, 1, 8);
+               if (!rc)
+                  rc = pb200_copy_d2d(S->dev, R + (size_t)S->ld * blki, S->ld,
+                        R + (size_t)S->ld * *blockSize, S->ld, S->n, 1, 8);
+               if (rc) goto done;
+            }
+            (*blockSize)++;
+         }
+         lasti = iev[blki];
+      }
+
+      /* next candidates after the last pair visited (:1629-1643; prepare_vecs is a no-op for
+       * Rayleigh-Ritz) */
+      blki = *blockSize;
+      for (i = lasti + 1; i < basisSize && blki < maxBlockSize; i++)
+         if (flags[i] == UNCONVERGED) iev[blki++] = i;
+      if (blki == *blockSize || *recentlyConverged >= remainedEvals) break;
+      blockNormsSize = blki - *blockSize;
+
+      for (i = 0; i < blockNormsSize; i++) {
+         hValsBlock[i] = hVals[iev[*blockSize + i]];
+         memcpy(&hVecsBlock[(size_t)ldh * i], &S->hVecs[(size_t)ldh * iev[*blockSize + i]],
+               sizeof(double) * basisSize);
+      }
+      rc = candidates_sweep(S, basisSize, hVecsBlock, hValsBlock, blockNormsSize,
+            X ? X + (size_t)S->ld * *blockSize : NULL, R ? R + (size_t)S->ld * *blockSize : NULL,
+            computeXR, &blockNorms[*blockSize]);
+      if (rc) goto done;
+
+      /* the reference's clamp loop (:1686-1688) runs over i in [*blockSize, blockNormsSize) */
+      for (i = *blockSize; i < blockNormsSize; i++)
+         blockNorms[i] = PB_MAX(blockNorms[i], primme->stats.estimateResidualError);
+   }
+done:
+   free(hValsBlock), free(hVecsBlock), free(flagsBlock);
+   return rc;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * GD / Olsen correction (correction.c:134-381 with maxInnerIterations == 0)
+ * ---------------------------------------------------------------------------------------- */
+static void merge_sort(const double *lockedEvals, int numLocked, const double *ritzVals,
+      const int *flags, int basisSize, double *sorted, int *ilev, int blockSize,
+      primme_params *primme) {
+   int count = 0, eval = 0, ritzVal = 0, blockIndex = 0;
+   while (count < numLocked + basisSize) {
+      if (eval >= numLocked ||
+            (ritzVal < basisSize &&
+                  ((primme->target == primme_largest && ritzVals[ritzVal] >= lockedEvals[eval]) ||
+                        (primme->target == primme_smallest && ritzVals[ritzVal] <= lockedEvals[eval])))) {
+         sorted[count] = ritzVals[ritzVal];
+         if (blockIndex < blockSize && flags[ritzVal] == UNCONVERGED) ilev[blockIndex++] = count;
+         ritzVal++;
+      } else if (ritzVal >= basisSize ||
+                 (primme->target == primme_largest && lockedEvals[eval] >= ritzVals[ritzVal]) ||
+                 (primme->target == primme_smallest && lockedEvals[eval] <= ritzVals[ritzVal])) {
+         sorted[count] = lockedEvals[eval];
+         eval++;
+      }
+      count++;
+   }
+}
+
+static double robust_shift(int blockIndex, double resNorm, const double *prevRitzVals,
+      int numPrevRitzVals, const double *sorted, double *approxOlsenShift, int numSorted,
+      const int *ilev, primme_params *primme) {
+   const double invB = primme->stats.estimateInvBNorm;
+   if (primme->stats.numOuterIterations <= 1) {
+      *approxOlsenShift = resNorm * sqrt(invB);
+      return resNorm * sqrt(invB);
+   }
+   int si = ilev[blockIndex];
+   double gap, lowerGap, upperGap, delta, epsilon;
+   if (si == 0 && numSorted >= 2) {
+      lowerGap = DBL_MAX;
+      gap = fabs(sorted[1] - sorted[0]);
+   } else if (si > 0 && numSorted >= 2 && si + 1 < numSorted) {
+      lowerGap = fabs(sorted[si] - sorted[si - 1]);
+      upperGap = fabs(sorted[si + 1] - sorted[si]);
+      gap = PB_MIN(lowerGap, upperGap);
+   } else {
+      lowerGap = fabs(sorted[si] - sorted[si - 1]);
+      gap = lowerGap;
+   }
+   delta = si < numPrevRitzVals ? fabs(prevRitzVals[si] - sorted[si]) : DBL_MAX;
+   if (gap > resNorm)
+      epsilon = PB_MIN(delta, PB_MIN(resNorm * resNorm * invB / gap, lowerGap));
+   else
+      epsilon = PB_MIN(resNorm * sqrt(invB), lowerGap);
+   *approxOlsenShift = PB_MIN(delta, epsilon);
+   return epsilon;
+}
+
+static int solve_correction(pb_solver *S, double *evals, int numLocked, int basisSize,
+      int blockSize) {
+   primme_params *primme = S->primme;
+   const correction_params *cp = &primme->correctionParams;
+   double *ritzVals = S->hVals, *prevRitzVals = S->prevRitzVals, *blockNorms = S->blockNorms;
+   int *iev = S->iev;
+   const double sqrtInvB = sqrt(primme->stats.estimateInvBNorm);
+   const int extremal = primme->target == primme_smallest || primme->target == primme_largest;
+   double *shifts = (double *)malloc(sizeof(double) * blockSize);
+   double *olsenEps = (double *)malloc(sizeof(double) * blockSize);
+   double *sorted = ritzVals;
+   int *ilev = iev, owns = 0, rc = 0;
+
+   if (primme->locking && extremal) {
+      sorted = (double *)malloc(sizeof(double) * (numLocked + basisSize));
+      ilev = (int *)malloc(sizeof(int) * blockSize);
+      owns = 1;
+      merge_sort(evals, numLocked, ritzVals, S->flags, basisSize, sorted, ilev, blockSize, primme);
+   }
+
+   if (!extremal) {
+      for (int b = 0; b < blockSize; b++) {
+         double t = primme->numTargetShifts > 0
+                          ? primme->targetShifts[PB_MIN(primme->numTargetShifts - 1, numLocked)]
+                          : 0.0;
+         int si = ilev[b];
+         if (fabs(sorted[si] - t) < blockNorms[b] * sqrtInvB)
+            shifts[b] = t;
+         else
+            shifts[b] = sorted[si] + (blockNorms[b] * sqrtInvB) * (t - sorted[si]) / fabs(t - sorted[si]);
+         olsenEps[b] = si < S->numPrevRitzVals ? fabs(prevRitzVals[si] - sorted[si])
+                                               : blockNorms[b] * sqrtInvB;
+      }
+      S->numPrevRitzVals = basisSize;
+      memcpy(prevRitzVals, sorted, sizeof(double) * basisSize);
+   } else {
+      if (cp->robustShifts) {
+         for (int b = 0; b < blockSize; b++) {
+            int si = ilev[b];
+            double rs = robust_shift(b, blockNorms[b], prevRitzVals, S->numPrevRitzVals, sorted,
+                  &olsenEps[b], numLocked + basisSize, ilev, primme);
+            if (primme->target == primme_smallest) {
+               shifts[b] = sorted[si] - rs;
+               if (si > 0) shifts[b] = PB_MAX(shifts[b], sorted[si - 1]);
+            } else {
+               shifts[b] = sorted[si] + rs;
+               if (si > 0) shifts[b] = PB_MIN(shifts[b], sorted[si - 1]);
+            }
+         }
+      } else {
+         for (int b = 0; b < blockSize; b++) {
+            int si = ilev[b];
+            shifts[b] = ritzVals[iev[b]];
+            olsenEps[b] = si < S->numPrevRitzVals ? fabs(prevRitzVals[si] - sorted[si])
+                                                  : blockNorms[b] * sqrtInvB;
+         }
+      }
+      S->numPrevRitzVals = numLocked + basisSize;
+      memcpy(prevRitzVals, sorted, sizeof(double) * S->numPrevRitzVals);
+   }
+
+   primme->ShiftsForPreconditioner = shifts;
+
+   double *r = S->W + (size_t)S->ld * basisSize; /* block residuals */
+   double *x = S->V + (size_t)S->ld * basisSize; /* block Ritz vectors, receives the corrections */
+   if (cp->projectors.RightX && cp->projectors.SkewX) {
+      /* exact Olsen projector (correction.c:695-774): x <- K^{-1}r - (x'K^{-1}r / x'K^{-1}x) K^{-1}x */
+      double *tmp = NULL;
+      rc = pb200_malloc(S->dev, sizeof(double) * (size_t)S->ld * blockSize * 2, (void **)&tmp);
+      if (!rc) {
+         double *Kx = tmp, *Kr = tmp + (size_t)S->ld * blockSize;
+         double *xKx = (double *)malloc(sizeof(double) * 2 * blockSize), *xKr = xKx + blockSize;
+         rc = pb_apply_precond(S, x, S->ld, Kx, S->ld, blockSize);
+         if (!rc) rc = pb_apply_precond(S, r, S->ld, Kr, S->ld, blockSize);
+         if (!rc) rc = pb200_dcolumn_dots(S->dev, S->n, x, S->ld, Kx, S->ld, blockSize, xKx);
+         if (!rc) rc = pb_reduce_panel(S, xKx, blockSize, 1, blockSize);
+         if (!rc) rc = pb200_dcolumn_dots(S->dev, S->n, x, S->ld, Kr, S->ld, blockSize, xKr);
+         if (!rc) rc = pb_reduce_panel(S, xKr, blockSize, 1, blockSize);
+         if (!rc) rc = pb200_copy_d2d(S->dev, Kr, S->ld, x, S->ld, S->n, blockSize, 8);
+         if (!rc) {
+            for (int b = 0; b < blockSize; b++) xKr[b] = fabs(xKx[b]) > 0.0 ? -xKr[b] / xKx[b] : 0.0;
+            rc = pb200_daxpy_columns(S->dev, S->n, xKr, Kx, S->ld, x, S->ld, blockSize);
+         }
+         free(xKx);
+         pb200_free(S->dev, tmp);
+      }
+   } else {
+      /* approximate Olsen: r <- r - eps*x before preconditioning (:356-372) */
+      if (cp->projectors.RightX &&
+            ((cp->precondition && primme->applyPreconditioner) ||
+                  (primme->locking && primme->orth == primme_orth_implicit_I))) {
+         for (int b = 0; b < blockSize; b++) olsenEps[b] = -olsenEps[b];
+         rc = pb200_daxpy_columns(S->dev, S->n, olsenEps, x, S->ld, r, S->ld, blockSize);
+      }
+      if (!rc) rc = pb_apply_precond(S, r, S->ld, x, S->ld, blockSize);
+   }
+   primme->ShiftsForPreconditioner = NULL;
+   if (owns) free(sorted), free(ilev);
+   free(shifts), free(olsenEps);
+   return rc;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * verify_norms (main_iter.c:1864-1894) -- destroys W(:,0:nv) (it holds residuals afterwards)
+ * ---------------------------------------------------------------------------------------- */
+static int verify_norms(pb_solver *S, int nv, double *resNorms, int *numConverged) {
+   CHK(pb200_dresidual_inplace(S->dev, S->n, S->hVals, S->V, S->ld, S->W, S->ld, nv, resNorms));
+   CHK(pb_reduce_panel(S, resNorms, nv, 1, nv));
+   for (int i = 0; i < nv; i++) resNorms[i] = sqrt(resNorms[i]);
+   CHK(pb_check_convergence(S, S->V, S->ld, 1, S->W, S->ld, 1, 0, 0, nv, S->flags, resNorms,
+         S->hVals, NULL, 0));
+   int i;
+   for (i = 0; i < nv && S->flags[i] != UNCONVERGED; i++)
+      ;
+   *numConverged = i;
+   return 0;
+}
+
+/* copy_back_candidates (main_iter.c:1745-1841): with locking, hand back unconverged Ritz pairs
+ * when the iteration budget ran out */
+static int copy_back_candidates(pb_solver *S, int basisSize, double *evals, double *resNorms,
+      int targetShiftIndex, int numConverged, int *numRet) {
+   primme_params *primme = S->primme;
+   if (numConverged >= primme->numEvals || basisSize <= 0) return 0;
+   double *ev = S->evecs + (size_t)S->ldevecs * primme->numOrthoConst;
+   int i = 0;
+   while (i < basisSize && numConverged < primme->numEvals) {
+      int bs = PB_MAX(0, PB_MIN(primme->numEvals - numConverged, basisSize - i));
+      bs = PB_MIN(bs, 8);
+      pb200_vwxr_out o;
+      memset(&o, 0, sizeof(o));
+      o.X[0].ptr = ev + (size_t)S->ldevecs * numConverged, o.X[0].ld = S->ldevecs, o.X[0].cb = 0, o.X[0].ce = bs;
+      o.rb = 0, o.re = bs, o.rnorms_host = &resNorms[numConverged];
+      CHK(pb200_dvwxr(S->dev, S->n, S->V, S->W, basisSize, S->ld, &S->hVecs[(size_t)S->maxBasis * i],
+            S->maxBasis, bs, &S->hVals[i], &o));
+      if (primme->numProcs > 1 && pb200_ctx_nranks(S->dev) <= 1) {
+         double *rn = &resNorms[numConverged];
+         for (int t = 0; t < bs; t++) rn[t] *= rn[t];
+         CHK(pb_global_sum(S, rn, bs));
+         for (int t = 0; t < bs; t++) rn[t] = sqrt(rn[t]);
+      }
+      int numConverged0 = numConverged;
+      for (int blki = 0; blki < bs; blki++, i++) {
+         double shift = primme->targetShifts ? primme->targetShifts[targetShiftIndex] : 0.0;
+         double rn = resNorms[numConverged0 + blki];
+         if ((primme->target == primme_closest_leq && S->hVals[i] - rn > shift) ||
+               (primme->target == primme_closest_geq && S->hVals[i] + rn < shift))
+            continue;
+         evals[numConverged] = S->hVals[i];
+         resNorms[numConverged] = rn;
+         if (numConverged != numConverged0 + blki)
+            CHK(pb200_copy_d2d(S->dev, ev + (size_t)S->ldevecs * (numConverged0 + blki), S->ldevecs,
+                  ev + (size_t)S->ldevecs * numConverged, S->ldevecs, S->n, 1, 8));
+         numConverged++;
+      }
+   }
+   for (i = numConverged; i < primme->numEvals; i++) resNorms[i] = -1;
+   *numRet = numConverged;
+   return 0;
+}
+
+/* ==========================================================================================
+ * The outer iteration (main_iter.c:176-1444)
+ * ======================================================================================== */
+int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *numRet) {
+   primme_params *primme = S->primme;
+   int i, rc = 0;
+   int blockSize = 0, availableBlockSize = 0, basisSize = 0, numLocked = 0, numGuesses = 0,
+       nextGuess = 0, numConverged = 0, targetShiftIndex = 0, recentlyConverged = 0,
+       maxRecentlyConverged = 0, LockingProblem = 0, restartLimitReached, nprevhVecs = 0,
+       reset = 0, restartsSinceReset = 0, wholeSpace = 0;
+   const int maxNumRandoms = 10;
+   const int maxBasis = primme->maxBasisSize, ldh = maxBasis;
+   double smallestResNorm;
+   int *flags = S->flags, *iev = S->iev, *map = S->map;
+   const int gdNoPrecLocking = primme->locking && !primme->correctionParams.precondition &&
+                               primme->correctionParams.maxInnerIterations == 0;
+
+   *ret = PRIMME_MAIN_ITER_FAILURE;
+   *numRet = 0;
+
+   /* counters (main_iter.c:371-396) */
+   memset(&primme->stats, 0, sizeof(primme->stats));
+   primme->stats.estimateMinEVal = HUGE_VAL;
+   primme->stats.estimateMaxEVal = -HUGE_VAL;
+   primme->stats.estimateLargestSVal = -HUGE_VAL;
+   primme->stats.estimateBNorm = 1.0;
+   primme->stats.estimateInvBNorm = 1.0;
+   for (i = 0; i < primme->numEvals; i++) S->perm[i] = i;
+   for (i = 0; i < maxBasis; i++) S->basisNorms[i] = 0.0;
+
+   if (primme->numEvals == 0) {
+      primme->initSize = 0;
+      *ret = 0;
+      goto clean;
+   }
+
+   rc = init_basis(S, &basisSize, &nextGuess, &numGuesses);
+   if (rc) return rc;
+   primme->initSize = 0;
+
+   /* dynamic method switching (main_iter.c:427-437) is driven by wall-clock timings in the
+    * reference; here the GD+k side of the switch is always taken (see front.c) */
+
+   while (primme->stats.numMatvecs < primme->maxMatvecs &&
+          (primme->maxOuterIterations == 0 ||
+                primme->stats.numOuterIterations < primme->maxOuterIterations)) {
+
+      primme->initSize = numConverged = numLocked;
+      reset = 0;
+      for (i = 0; i < maxBasis; i++) flags[i] = UNCONVERGED;
+      targetShiftIndex = 0;
+
+      CHK(pb_update_projection(S, 0, basisSize));
+      CHK(pb_solve_H(S, S->H, ldh, basisSize, VtBV_BLK(S, primme->numOrthoConst + numLocked),
+            S->maxRank, S->hVecs, ldh, S->hVals, numConverged, 1));
+
+      maxRecentlyConverged = availableBlockSize = blockSize = 0;
+      smallestResNorm = HUGE_VAL;
+      primme->stats.estimateResidualError = 0.0;
+      if (!primme->locking) primme->stats.maxConvTol = 0.0;
+      restartsSinceReset = 0;
+
+      /* ---- restart loop ---- */
+      while (numConverged < primme->numEvals && primme->stats.numMatvecs < primme->maxMatvecs &&
+             (primme->maxOuterIterations == 0 ||
+                   primme->stats.numOuterIterations < primme->maxOuterIterations) &&
+             !wholeSpace) {
+
+         nprevhVecs = 0;
+         int candidates_prepared = 0;
+
+         /* ---- expansion loop: grow the basis block by block ---- */
+         while (basisSize < maxBasis && primme->stats.numMatvecs < primme->maxMatvecs &&
+                (primme->maxOuterIterations == 0 ||
+                      primme->stats.numOuterIterations < primme->maxOuterIterations)) {
+
+            primme->stats.numOuterIterations++;
+
+            availableBlockSize = primme->maxBlockSize;
+            maxRecentlyConverged = PB_MAX(0, primme->numEvals - numConverged);
+            availableBlockSize = PB_MIN(availableBlockSize, maxBasis - basisSize);
+            availableBlockSize = PB_MIN(availableBlockSize, maxRecentlyConverged + 1);
+
+            if (availableBlockSize > 0) {
+               int practConvCheck = 0;
+               if (primme->n <= basisSize + numLocked + primme->numOrthoConst)
+                  practConvCheck = 1;
+               else if (gdNoPrecLocking)
+                  practConvCheck = -1;
+               CHK(prepare_candidates(S, basisSize, S->V + (size_t)S->ld * basisSize,
+                     S->W + (size_t)S->ld * basisSize, 1, maxRecentlyConverged, blockSize,
+                     availableBlockSize, numLocked, evals, resNorms, targetShiftIndex, &blockSize,
+                     &recentlyConverged, &smallestResNorm, numConverged, &reset, nprevhVecs,
+                     practConvCheck));
+               candidates_prepared = 1;
+            } else {
+               blockSize = recentlyConverged = 0;
+            }
+
+            numConverged += recentlyConverged;
+
+            CHK(pb_monitor(S, S->hVals, basisSize, flags, iev, blockSize, S->basisNorms,
+                  numConverged, evals, numLocked, S->lockedFlags, resNorms, -1, -1.0, NULL, 0.0,
+                  primme_event_outer_iteration));
+
+            if (numConverged >= primme->numEvals ||
+                  (primme->locking && numConverged > numLocked &&
+                        primme->target != primme_smallest && primme->target != primme_largest) ||
+                  targetShiftIndex < 0 || (blockSize == 0 && recentlyConverged > 0) ||
+                  (numConverged >= nextGuess - primme->numOrthoConst && numGuesses > 0)) {
+               break;
+            }
+
+            if (blockSize > 0) CHK(solve_correction(S, evals, numLocked, basisSize, blockSize));
+
+            /* with locking, GD and no preconditioner the practical convergence of the block is
+             * judged after orthogonalisation from V_locked' r (main_iter.c:674-797) */
+            double *Rlocked = NULL;
+            const int ldRlocked = primme->numOrthoConst + numLocked;
+            const int blockSize0 = blockSize;
+            if (gdNoPrecLocking)
+               Rlocked = (double *)calloc((size_t)(ldRlocked > 0 ? ldRlocked : 1) * (blockSize > 0 ? blockSize : 1), sizeof(double));
+
+            for (i = 0; i < maxNumRandoms; i++) {
+               int basisSizeOut;
+               CHK(pb_ortho_block(S, S->V, S->ld, basisSize, basisSize + blockSize - 1, S->evecs,
+                     S->ldevecs, primme->numOrthoConst + numLocked, i == 0 ? Rlocked : NULL,
+                     ldRlocked, &basisSizeOut));
+               blockSize = basisSizeOut - basisSize;
+               if (blockSize > 0 || availableBlockSize <= 0) break;
+               CHK(pb_fill_random(S, S->V + (size_t)S->ld * basisSize, S->ld, 1));
+               blockSize = 1;
+            }
+            if (i >= maxNumRandoms) {
+               if (availableBlockSize > 0 && blockSize0 <= 0 && reset == 0)
+                  wholeSpace = 1;
+               else
+                  reset = 2;
+               blockSize = 0;
+               free(Rlocked);
+               break;
+            }
+
+            if (gdNoPrecLocking) {
+               if (numLocked > 0) {
+                  for (i = 0; i < blockSize0 && numConverged < primme->numEvals; i++) {
+                     double normXx = 0.0;
+                     if (primme->orth == primme_orth_explicit_I) {
+                        /* Xx = VtBV(0:numLocked, numLocked: ) * hVecs(:,iev[i]) */
+                        double *Xx = (double *)calloc(numLocked, sizeof(double));
+                        hl_gemm('N', 'N', numLocked, 1, basisSize, 1.0,
+                              &S->VtBV[(size_t)S->maxRank * numLocked], S->maxRank,
+                              &S->hVecs[(size_t)ldh * iev[i]], ldh, 0.0, Xx, numLocked);
+                        normXx = fabs(hl_dot(numLocked, Xx, Xx));
+                        free(Xx);
+                     }
+                     double normR = fabs(hl_dot(ldRlocked, &Rlocked[(size_t)ldRlocked * i],
+                           &Rlocked[(size_t)ldRlocked * i]));
+                     double bn = S->blockNorms[i];
+                     double newBlockNorm = sqrt(PB_MAX(bn * bn - normR * (1. + normXx), 0.0));
+                     CHK(pb_check_convergence(S, S->V + (size_t)S->ld * (basisSize + i), S->ld, 1,
+                           NULL, 0, 0, numLocked, 0, 1, &flags[iev[i]], &newBlockNorm,
+                           &S->hVals[iev[i]], &reset, -1));
+                     S->basisNorms[iev[i]] = newBlockNorm;
+                     if (flags[iev[i]] == CONVERGED) {
+                        flags[iev[i]] = PRACTICALLY_CONVERGED;
+                        numConverged++;
+                        CHK(pb_monitor(S, S->hVals, basisSize, flags, &iev[i], 1, S->basisNorms,
+                              numConverged, NULL, 0, NULL, NULL, -1, -1.0, NULL, 0.0,
+                              primme_event_converged));
+                     }
+                  }
+               }
+               free(Rlocked);
+               Rlocked = NULL;
+               if (numConverged > numLocked && primme->target != primme_smallest &&
+                     primme->target != primme_largest)
+                  break;
+            }
+
+            /* W(:,new) = A V(:,new);  H(:,new) = V' W(:,new) */
+            CHK(pb_apply_matvec(S, S->V + (size_t)S->ld * basisSize, S->ld,
+                  S->W + (size_t)S->ld * basisSize, S->ld, blockSize));
+            CHK(pb_update_projection(S, basisSize, blockSize));
+
+            hl_copy(S->hVecs, basisSize, basisSize, ldh, S->prevhVecs, ldh);
+            hl_zero(&S->prevhVecs[basisSize], maxBasis - basisSize, basisSize, ldh);
+            nprevhVecs = basisSize;
+
+            basisSize += blockSize;
+            blockSize = 0;
+
+            CHK(pb_solve_H(S, S->H, ldh, basisSize,
+                  VtBV_BLK(S, primme->numOrthoConst + numLocked), S->maxRank, S->hVecs, ldh,
+                  S->hVals, numConverged, 1));
+            candidates_prepared = 0;
+         } /* expansion loop */
+
+         if (basisSize >= primme->n - primme->numOrthoConst - numLocked) {
+            if (primme->stats.maxConvTol < primme->stats.estimateResidualError) reset = 1;
+         }
+         if (reset > 0) break;
+
+         /* ---- make hVecs/iev ready for the restart (main_iter.c:908-1073) ---- */
+         if (!candidates_prepared) {
+            if (blockSize > 0) {
+               availableBlockSize = blockSize;
+               maxRecentlyConverged = 0;
+            } else if (primme->numTargetShifts > numConverged + 1) {
+               if (primme->locking)
+                  maxRecentlyConverged = PB_MAX(PB_MIN(primme->numEvals, numLocked + 1) - numConverged, 0);
+               else
+                  maxRecentlyConverged = PB_MAX(PB_MIN(primme->numEvals, numConverged + 1) - numConverged, 0);
+               availableBlockSize = maxRecentlyConverged;
+            } else {
+               maxRecentlyConverged = PB_MAX(0, primme->numEvals - numConverged);
+               availableBlockSize = PB_MAX(0, PB_MIN(primme->maxBlockSize, maxBasis - (numConverged - numLocked)));
+               availableBlockSize = PB_MIN(availableBlockSize, maxRecentlyConverged + 1);
+            }
+            {
+               PRIMME_INT room = primme->n - numLocked - primme->numOrthoConst;
+               if (room < availableBlockSize) availableBlockSize = (int)room;
+               if (availableBlockSize < 0) availableBlockSize = 0;
+            }
+
+            if (availableBlockSize <= 0 ||
+                  primme->minRestartSize + primme->restartingParams.maxPrevRetain + availableBlockSize < maxBasis ||
+                  primme->numOrthoConst + numLocked + basisSize >= primme->n) {
+               double dummyZero = 0.0;
+               double *srn = (primme->target == primme_closest_abs || primme->target == primme_largest_abs)
+                                   ? &dummyZero
+                                   : &smallestResNorm;
+               CHK(prepare_candidates(S, basisSize, NULL, NULL, 0, maxRecentlyConverged, blockSize,
+                     availableBlockSize, numLocked, evals, resNorms, targetShiftIndex, &blockSize,
+                     &recentlyConverged, srn, numConverged, &reset, nprevhVecs, 0));
+
+               for (i = 0, numConverged = numLocked; i < basisSize; i++)
+                  if (flags[i] != UNCONVERGED && numConverged < primme->numEvals &&
+                        (i < primme->numEvals - numLocked || primme->target == primme_closest_geq ||
+                              primme->target == primme_closest_leq))
+                     numConverged++;
+
+               /* converged pairs and the block first */
+               int *iwork = (int *)malloc(sizeof(int) * basisSize);
+               int j, k, l, m;
+               for (i = k = l = m = 0; i < basisSize; i++) {
+                  int inIev = 0;
+                  for (j = 0; j < blockSize; j++)
+                     if (iev[j] == i) inIev = 1;
+                  if ((flags[i] != UNCONVERGED && m++ < numConverged - numLocked) || inIev)
+                     iwork[k++] = i;
+                  else
+                     iwork[numConverged - numLocked + blockSize + l++] = i;
+               }
+               hl_permute_cols(S->hVals, 1, basisSize, 1, iwork);
+               hl_permute_cols(S->hVecs, basisSize, basisSize, ldh, iwork);
+               hl_permute_ints(flags, basisSize, iwork);
+               free(iwork);
+            } else {
+               blockSize = availableBlockSize;
+               for (i = 0; i < blockSize; i++) iev[i] = i;
+               pb_map_vecs(S->prevhVecs, basisSize, nprevhVecs, ldh, S->hVecs, 0, basisSize, ldh, map);
+            }
+         }
+         if (reset > 0) break;
+
+         hl_permute_cols(S->prevhVecs, basisSize, nprevhVecs, ldh, map);
+
+         CHK(pb_restart(S, basisSize, &blockSize, evals, resNorms, &numConverged, &numLocked,
+               nprevhVecs, numGuesses, &basisSize, &targetShiftIndex, &restartsSinceReset));
+         restartsSinceReset++;
+
+         /* feed remaining initial guesses into the basis (main_iter.c:1098-1168) */
+         if (numGuesses > 0) {
+            int numNew = PB_MAX(0, PB_MIN(primme->minRestartSize + numConverged - (nextGuess - primme->numOrthoConst), numGuesses));
+            numNew = PB_MAX(0, PB_MIN(basisSize + numNew, maxBasis) - basisSize);
+            {
+               PRIMME_INT cap = basisSize + numNew + primme->numOrthoConst + numLocked;
+               if (cap > primme->n) cap = primme->n;
+               cap -= primme->numOrthoConst + numLocked + basisSize;
+               numNew = cap > 0 ? (int)cap : 0;
+            }
+            CHK(pb200_copy_d2d(S->dev, S->evecs + (size_t)S->ldevecs * nextGuess, S->ldevecs,
+                  S->V + (size_t)S->ld * basisSize, S->ld, S->n, numNew, 8));
+            nextGuess += numNew;
+            numGuesses -= numNew;
+            int basisSizeOut;
+            CHK(pb_ortho_block(S, S->V, S->ld, basisSize, basisSize + numNew - 1, S->evecs,
+                  S->ldevecs, numLocked + primme->numOrthoConst, NULL, 0, &basisSizeOut));
+            numNew = basisSizeOut - basisSize;
+            CHK(pb_apply_matvec(S, S->V + (size_t)S->ld * basisSize, S->ld,
+                  S->W + (size_t)S->ld * basisSize, S->ld, numNew));
+            CHK(pb_update_projection(S, basisSize, numNew));
+            basisSize += numNew;
+            CHK(pb_solve_H(S, S->H, ldh, basisSize,
+                  VtBV_BLK(S, primme->numOrthoConst + numLocked), S->maxRank, S->hVecs, ldh,
+                  S->hVals, numConverged, 1));
+         }
+
+         primme->stats.numRestarts++;
+         primme->initSize = numConverged;
+         for (i = 0; i < maxBasis; i++) map[i] = i;
+      } /* restart loop */
+
+      if (reset > 0) continue;
+
+      if (primme->locking) {
+         CHK(copy_back_candidates(S, basisSize, evals, resNorms, targetShiftIndex, numConverged, numRet));
+         primme->stats.lockingIssue = LockingProblem;
+         *ret = (numConverged == primme->numEvals || wholeSpace) ? 0 : PRIMME_MAIN_ITER_FAILURE;
+         goto clean;
+      }
+
+      /* no locking: all returned pairs must still pass the test after the last restart */
+      restartLimitReached = !(primme->stats.numMatvecs < primme->maxMatvecs &&
+                              (primme->maxOuterIterations == 0 ||
+                                    primme->stats.numOuterIterations < primme->maxOuterIterations));
+      CHK(verify_norms(S, restartLimitReached ? primme->numEvals : numConverged, resNorms, &numConverged));
+
+      if (restartLimitReached || numConverged >= primme->numEvals || wholeSpace) {
+         for (i = 0; i < primme->numEvals; i++) {
+            evals[i] = S->hVals[i];
+            S->perm[i] = i;
+         }
+         CHK(pb200_copy_d2d(S->dev, S->V, S->ld,
+               S->evecs + (size_t)S->ldevecs * primme->numOrthoConst, S->ldevecs, S->n,
+               primme->numEvals, 8));
+         *numRet = primme->numEvals;
+         primme->initSize = numConverged;
+         *ret = numConverged >= primme->numEvals ? 0 : PRIMME_MAIN_ITER_FAILURE;
+         goto clean;
+      }
+
+      /* some pairs slipped: re-orthogonalise the basis, recompute W = A V, keep iterating */
+      CHK(pb_ortho_block(S, S->V, S->ld, 0, basisSize - 1, S->evecs, S->ldevecs,
+            primme->numOrthoConst, NULL, 0, &basisSize));
+      CHK(pb_apply_matvec(S, S->V, S->ld, S->W, S->ld, basisSize));
+      restartsSinceReset = 0;
+      reset = 0;
+      primme->stats.estimateResidualError = 0.0;
+      numConverged = 0;
+   } /* verification loop */
+
+clean:
+   if (primme->aNorm <= 0.0)
+      primme->aNorm = primme->stats.estimateLargestSVal / primme->stats.estimateInvBNorm;
+   /* locked vectors are stored in order of convergence: sort them like evals (:1355-1357) */
+   rc = pb200_dpermute_columns(S->dev, S->n,
+         S->evecs + (size_t)S->ldevecs * primme->numOrthoConst, S->ldevecs, S->perm,
+         primme->initSize);
+   return rc;
+}

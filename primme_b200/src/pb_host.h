@@ -1,0 +1,106 @@
+/* pb_host.h -- internal declarations of the host control code (C99).
+ *
+ * The host side keeps PRIMME's structure: a front end that validates primme_params
+ * (front.c), the outer block-Davidson iteration (davidson.c) and the small projected problem on
+ * the host with LAPACK (hostla.c).  Every n-long operation goes through the C-ABI of
+ * include/primme_b200.h, i.e. the sm_100a kernels in the product library.
+ */
+#ifndef PB_HOST_H
+#define PB_HOST_H
+
+#include "../../include/primme.h"
+#include "../../include/primme_b200.h"
+#include "hostla.h"
+
+/* convergence flags (reference src/eigs/common_eigs.h:41-46) */
+enum { UNCONVERGED = 0, SKIP_UNTIL_RESTART = 1, CONVERGED = 2, PRACTICALLY_CONVERGED = 3 };
+
+void primme_set_defaults(primme_params *primme);
+void primme_display_params_prefix(const char *prefix, primme_params primme);
+
+/* Solver state shared by the pieces of the outer iteration. */
+typedef struct pb_solver {
+   primme_params *primme;
+   pb200_ctx *dev;
+   int device_callbacks; /* 1: user callbacks take device pointers (cublas_dprimme contract) */
+   int64_t n;            /* nLocal */
+   int64_t ld;           /* leading dimension of V and W (ldOPs) */
+   double *V, *W;        /* device, ld x maxBasisSize */
+   double *evecs;        /* device, ldevecs x (numOrthoConst + max(numEvals, initSize)) */
+   int64_t ldevecs;
+   double *hstage;       /* host staging for host callbacks / random vectors: n x maxBlockSize */
+   double *hstage2;
+   int hstage_cols;
+   /* replicated small matrices (host) */
+   int maxBasis, maxRank;
+   double *H;         /* maxBasis x maxBasis, upper triangle of V'AV */
+   double *hVecs;     /* maxBasis x maxBasis (leading dimension maxBasis) */
+   double *prevhVecs; /* maxBasis x maxBasis */
+   double *VtBV;      /* maxRank x maxRank or NULL (orth implicit) */
+   double *fVtBV;     /* Cholesky factor of VtBV */
+   double *hVals, *prevRitzVals, *blockNorms, *basisNorms;
+   int *flags, *map, *iev, *perm, *lockedFlags;
+   double t0;
+   int numPrevRitzVals;
+} pb_solver;
+
+/* error propagation in the style of the reference's CHKERR (common.h:484-494) */
+#define CHK(call)                                                                        \
+   do {                                                                                  \
+      int chk_err_ = (call);                                                             \
+      if (chk_err_ != 0) {                                                               \
+         pb_report(S ? S->primme : NULL, __FILE__, __LINE__, chk_err_, #call);           \
+         return chk_err_;                                                                \
+      }                                                                                  \
+   } while (0)
+void pb_report(primme_params *primme, const char *file, int line, int err, const char *what);
+
+/* davidson.c */
+int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *numRet);
+/* front.c helpers used by davidson.c */
+int pb_apply_matvec(pb_solver *S, double *Vblk, int64_t ldv, double *Wblk, int64_t ldw, int bs);
+int pb_apply_precond(pb_solver *S, double *X, int64_t ldx, double *Y, int64_t ldy, int bs);
+int pb_global_sum(pb_solver *S, double *buf, int count);
+int pb_bcast(pb_solver *S, double *buf, int count);
+int pb_bcast_int(pb_solver *S, int *buf, int count);
+int pb_conv_test(pb_solver *S, double eval, double rnorm, int *isconv);
+int pb_monitor(pb_solver *S, double *basisEvals, int basisSize, int *basisFlags, int *iblock,
+      int blockSize, double *basisNorms, int numConverged, double *lockedEvals, int numLocked,
+      int *lockedFlags, double *lockedNorms, int inner_its, double LSRes, const char *msg,
+      double time, primme_event event);
+double pb_problem_norm(int overrideUserEstimations, primme_params *primme);
+int pb_fill_random(pb_solver *S, double *X, int64_t ldx, int ncols);
+
+
+/* operators.c */
+void pb_registry_set_solver(const primme_params *primme, pb200_ctx *ctx);
+
+/* dav_project.c */
+int pb_update_projection(pb_solver *S, int numCols, int blockSize);
+int pb_solve_H(pb_solver *S, const double *H, int ldH, int n, const double *VtBVblk, int ldVtBV,
+      double *hVecs, int ldhVecs, double *hVals, int numConverged, int updateStats);
+int pb_map_vecs(const double *V, int m, int nV, int ldV, const double *W, int n0, int n, int ldW,
+      int *p);
+int pb_reduce_panel(pb_solver *S, double *P, int rows, int cols, int ldp);
+
+/* dav_ortho.c */
+int pb_ortho_block(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const double *locked,
+      int64_t ldLocked, int numLocked, double *RLocked, int ldRLocked, int *b2_out);
+int pb_update_cholesky(pb_solver *S, int n0, int n);
+int pb_ortho_single_iteration(pb_solver *S, const double *Q, int nQ, int64_t ldQ,
+      const double *QtQ, int ldQtQ, double *X, const int *inX, int nX, int64_t ldX,
+      double *norms);
+int pb_ortho_local(double *V, int ldV, double *R, int b1, int b2, double *locked, int ldLocked,
+      int numLocked, int n, const double *B, int ldB, long long *iseed);
+
+/* dav_restart.c */
+int pb_restart(pb_solver *S, int basisSize, int *ievSize, double *evals, double *resNorms,
+      int *numConverged, int *numLocked, int nprevhVecs, int numGuesses, int *restartSizeOut,
+      int *targetShiftIndex, int *restartsSinceReset);
+int pb_check_convergence(pb_solver *S, double *X, int64_t ldX, int givenX, double *R,
+      int64_t ldR, int givenR, int numLocked, int left, int right, int *flags,
+      double *blockNorms, double *hVals, int *reset, int practConvCheck);
+int pb_insertion_sort(double newVal, double *evals, double newNorm, double *resNorms,
+      int newFlag, int *flags, int *perm, int n, int initialShift, primme_params *primme);
+
+#endif

@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the Davidson inner-loop hot path on B200.
+
+Workload (BASELINE.json configs[1], "C2"): dprimme, 3-D 7-point Laplacian CSR n = 10^6
+(nnz = 6 940 000), 10 smallest eigenpairs, GD_Olsen_plusK, maxBasisSize 40, maxBlockSize 4,
+eps 1e-10, aNorm 12.  A "step" is one complete solve (time-to-converge); the metric is
+matvecs/s = stats.numMatvecs / elapsed, summed over ranks.
+
+  value     : matrix and eigenvector storage already resident in HBM (cublas_dprimme contract)
+  e2e       : the same solve through the host-facing C-ABI call primme_b200_dprimme_csr: the
+              host CSR upload and the eigenvector download are inside the timed region
+  roofline  : the kernel kind with the largest share of device time, algorithmic bytes / CUDA-
+              event time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline / --impl reference : the UNMODIFIED reference (oracle/_ref, built from
+              /root/reference by oracle/Makefile) on the host cores, on a bounded sample
+              (maxMatvecs) of the same workload
+
+Multi-GPU (--gpus N under torchrun): this round every rank runs an independent replica of the
+solve on its own GPU ("replicas only", weak scaling, no data-path collective) -- the row-sharded
+solve with NCCL panel all-reduce is exercised by tests/test_multi_rank.py and is not yet the
+bench path.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--side", type=int, default=100, help="grid points per side (n = side^3)")
+    ap.add_argument("--ref-matvecs", type=int, default=160,
+                    help="bounded sample of the reference arm: matvecs per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+WORKLOAD = dict(numEvals=10, maxBasisSize=40, maxBlockSize=4, eps=1e-10, aNorm=12.0)
+
+
+def workload_name(side):
+    return (f"dprimme 3D 7-pt Laplacian CSR n={side}^3, 10 smallest, GD_Olsen_plusK, "
+            f"maxBasisSize=40, blockSize=4, eps=1e-10")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    def __init__(self, index):
+        self.rows = []
+        self.stop = False
+        self.index = index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=3)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_reference(args, csr, rank):
+    """the reference's own CPU path on a bounded sample of the workload"""
+    import harness as H
+    from primme_b200 import api
+    ncores = os.cpu_count() or 1
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(ncores))
+    times, mvs = [], []
+    for step in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = H.solve("reference", csr, WORKLOAD["numEvals"], method=api.PRIMME_GD_Olsen_plusK, nthreads=ncores,
+                    maxMatvecs=args.ref_matvecs, **{k: v for k, v in WORKLOAD.items() if k != "numEvals"})
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            times.append(r["stats"]["elapsedTime"] or dt)
+            mvs.append(r["stats"]["numMatvecs"])
+    return sum(mvs) / sum(times), sum(times) / len(times), ncores, mvs[0]
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from primme_b200 import api, matrices as M
+
+    csr = M.laplacian_nd((args.side,) * 3)
+    n = len(csr[0]) - 1
+    nnz = len(csr[1])
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        val, sec, ncores, mv = run_reference(args, csr, rank)
+        line = {"impl": "reference", "metric": "matvecs_per_s", "value": val, "unit": "matvecs/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(args.side), "n": n, "nnz": nnz},
+                "cpu_baseline": {"value": val, "unit": "matvecs/s", "cores": ncores, "kind": "reference",
+                                 "sample": f"first {mv} matvecs of the solve (maxMatvecs bound), "
+                                           f"OpenBLAS {ncores} threads + {ncores}-thread CSR callback"},
+                "e2e": {"value": val, "unit": "matvecs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    lib = api.load_library()
+    if lib.pb200_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+
+    rp = np.ascontiguousarray(csr[0], dtype=np.int64)
+    ci = np.ascontiguousarray(csr[1], dtype=np.int32)
+    va = np.ascontiguousarray(csr[2], dtype=np.float64)
+    k = WORKLOAD["numEvals"]
+
+    ctx = C.c_void_p()
+    assert lib.pb200_ctx_create(C.byref(ctx), local) == 0
+    A = C.c_void_p()
+    assert lib.pb200_csr_create(ctx, n, n, nnz, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, 0, 0, C.byref(A)) == 0
+    devecs = C.c_void_p()
+    assert lib.pb200_malloc(ctx, 8 * n * k, C.byref(devecs)) == 0
+    evals, rn = np.zeros(k), np.zeros(k)
+
+    def make_params():
+        p = api.new_params(lib, n, target=api.primme_smallest, **WORKLOAD)
+        assert lib.primme_set_method(api.PRIMME_GD_Olsen_plusK, C.byref(p)) == 0
+        p.ldevecs = n
+        return p
+
+    def resident_solve():
+        p = make_params()
+        p.matrix = A
+        p.matrixMatvec = C.cast(lib.primme_b200_csr_matvec, C.c_void_p).value
+        lib.primme_b200_attach_ctx(C.byref(p), ctx)
+        rc = lib.cublas_dprimme(evals.ctypes.data, devecs, rn.ctypes.data, C.byref(p))
+        lib.primme_b200_attach_ctx(C.byref(p), None)
+        assert rc == 0, rc
+        return p
+
+    # pinned host buffers for the end-to-end leg
+    hevecs = torch.empty((k, n), dtype=torch.float64).pin_memory()
+    h_rp = torch.from_numpy(rp).pin_memory()
+    h_ci = torch.from_numpy(ci).pin_memory()
+    h_va = torch.from_numpy(va).pin_memory()
+
+    def e2e_solve():
+        p = make_params()
+        lib.primme_b200_attach_ctx(C.byref(p), ctx)
+        rc = lib.primme_b200_dprimme_csr(evals.ctypes.data, hevecs.data_ptr(), rn.ctypes.data, C.byref(p),
+                                         h_rp.data_ptr(), h_ci.data_ptr(), h_va.data_ptr(), 0)
+        lib.primme_b200_attach_ctx(C.byref(p), None)
+        assert rc == 0, rc
+        return p
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.pb200_ctx_launches(ctx)
+        ev0.record()
+        mv = 0
+        for _ in range(steps):
+            p = fn()
+            mv += p.stats.numMatvecs
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            m = torch.tensor([mv], device="cuda", dtype=torch.float64)
+            dist.all_reduce(m, op=dist.ReduceOp.SUM)
+            mv = float(m.item())
+        return ms, mv, lib.pb200_ctx_launches(ctx) - l0, p
+
+    for _ in range(args.warmup):
+        resident_solve()
+    with ClockSampler(local) as cs:
+        ms, mv, launches, p = timed(resident_solve, args.steps)
+    clocks = cs.summary()
+    value = mv / (ms * 1e-3)
+    stats = api.stats_dict(p)
+
+    e2e_solve()  # warm the pinned-path once
+    ms_e, mv_e, _, _ = timed(e2e_solve, max(1, min(args.steps, 3)))
+    e2e_value = mv_e / (ms_e * 1e-3)
+    h2d = rp.nbytes + ci.nbytes + va.nbytes
+    d2h = 8 * n * k + 16 * k
+
+    # per-kernel roofline from one profiled solve (CUDA events on the kernels' stream)
+    lib.pb200_ctx_set_profiling.restype = C.c_int
+    lib.pb200_ctx_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    lib.pb200_ctx_get_profile.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.pb200_ctx_set_profiling(ctx, 1)
+    t0 = time.perf_counter()
+    resident_solve()
+    prof_wall = time.perf_counter() - t0
+    kinds = ["spmm", "ortho_sweep", "vwxr", "utils", "panel_reduce"]
+    prof = {}
+    for i, name in enumerate(kinds):
+        cnt, pms, pby = C.c_int64(), C.c_double(), C.c_double()
+        lib.pb200_ctx_get_profile(ctx, i, C.byref(cnt), C.byref(pms), C.byref(pby))
+        prof[name] = dict(launches=cnt.value, ms=pms.value, bytes=pby.value,
+                          gbs=(pby.value / 1e9) / (pms.value / 1e3) if pms.value > 0 else 0.0)
+    lib.pb200_ctx_set_profiling(ctx, 0)
+    dom = max(("spmm", "ortho_sweep", "vwxr"), key=lambda kname: prof[kname]["ms"])
+    peak, peak_src = measured_peak()
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": prof[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": prof[dom]["gbs"] / peak, "peak_source": peak_src, "traffic": None,
+                "launches": prof[dom]["launches"], "avg_launch_us": 1e3 * prof[dom]["ms"] / max(1, prof[dom]["launches"]),
+                "algorithmic_bytes_per_launch": prof[dom]["bytes"] / max(1, prof[dom]["launches"]),
+                "all_kernels": {kname: {"GBps": round(v["gbs"], 1), "ms": round(v["ms"], 3), "launches": v["launches"]}
+                                for kname, v in prof.items()},
+                "device_time_share_of_solve": sum(v["ms"] for v in prof.values()) / (prof_wall * 1e3)}
+
+    cpu_baseline = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+        try:
+            a2 = argparse.Namespace(**vars(args))
+            a2.warmup, a2.steps = 0, 1
+            val, sec, ncores, mvr = run_reference(a2, csr, 0)
+            cpu_baseline = {"value": val, "unit": "matvecs/s", "cores": ncores, "kind": "reference",
+                            "sample": f"first {mvr} matvecs of the same solve ({sec:.1f} s), "
+                                      f"OpenBLAS {ncores} threads + {ncores}-thread CSR callback"}
+        except Exception as e:  # the reference build is test infrastructure; never fatal here
+            cpu_baseline = {"value": None, "unit": "matvecs/s", "cores": os.cpu_count(), "kind": "reference",
+                            "sample": f"unavailable: {e}"}
+
+    if rank == 0:
+        line = {"metric": "matvecs_per_s", "value": value, "unit": "matvecs/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": workload_name(args.side), "n": n, "nnz": nnz,
+                           "parallelism": "replicas only" if args.gpus > 1 else "single GPU",
+                           "l2": "working set per sweep (V,W 2x320 MB at n=1e6) exceeds the 126 MB L2; no flush",
+                           "outer_iterations": stats["numOuterIterations"], "restarts": stats["numRestarts"],
+                           "matvecs_per_solve": stats["numMatvecs"], "time_to_converge_s": ms / args.steps / 1e3},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "matvecs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e / max(1, min(args.steps, 3))},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line))
+
+    lib.pb200_free(ctx, devecs)
+    lib.pb200_csr_destroy(ctx, A)
+    lib.pb200_ctx_destroy(ctx)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -43,6 +43,11 @@ int pb200_ctx_sync(pb200_ctx *ctx);
 void *pb200_ctx_stream(pb200_ctx *ctx); /* cudaStream_t */
 /* kernel-launch counter (bench.py reports it as gpu_launches) */
 int64_t pb200_ctx_launches(pb200_ctx *ctx);
+/* Per-kernel-kind CUDA-event timing on the context's stream (kind: 0 spmm, 1 ortho sweep,
+ * 2 vwxr, 3 utilities, 4 panel reduction): number of launches, total milliseconds and total
+ * algorithmic bytes since profiling was switched on.  Used by bench.py for the roofline. */
+int pb200_ctx_set_profiling(pb200_ctx *ctx, int on);
+int pb200_ctx_get_profile(pb200_ctx *ctx, int kind, int64_t *count, double *ms, double *bytes);
 /* Attach an NCCL communicator (ncclComm_t as void*): every *_host panel is then all-reduced
  * (sum) across ranks on the device before it is copied back; nranks==1 detaches. */
 int pb200_ctx_set_comm(pb200_ctx *ctx, void *nccl_comm, int nranks, int rank);

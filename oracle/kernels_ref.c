@@ -62,6 +62,15 @@ int pb200_ctx_set_comm(pb200_ctx *ctx, void *comm, int nranks, int rank) {
    return nranks == 1 ? 0 : PB200_ERR_ARG; /* the oracle is sequential */
 }
 int pb200_ctx_nranks(pb200_ctx *ctx) { return ctx->nranks; }
+int pb200_ctx_set_profiling(pb200_ctx *ctx, int on) {
+   (void)ctx, (void)on;
+   return 0;
+}
+int pb200_ctx_get_profile(pb200_ctx *ctx, int kind, int64_t *count, double *ms, double *bytes) {
+   (void)ctx, (void)kind;
+   *count = 0, *ms = 0.0, *bytes = 0.0;
+   return 0;
+}
 int pb200_allreduce_host(pb200_ctx *ctx, double *buf, int count) {
    (void)ctx, (void)buf, (void)count;
    return 0;

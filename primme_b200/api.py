@@ -123,6 +123,8 @@ def _declare(lib):
         "pb200_ctx_sync": (i32, [vp]),
         "pb200_ctx_launches": (i64, [vp]),
         "pb200_ctx_nranks": (i32, [vp]),
+        "pb200_ctx_set_profiling": (i32, [vp, i32]),
+        "pb200_ctx_get_profile": (i32, [vp, i32, P(i64), P(dbl), P(dbl)]),
         "pb200_malloc": (i32, [vp, C.c_size_t, P(vp)]),
         "pb200_free": (i32, [vp, vp]),
         "pb200_copy_h2d": (i32, [vp, vp, i64, vp, i64, i64, i32, i32]),

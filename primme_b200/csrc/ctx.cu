@@ -29,7 +29,7 @@ extern "C" int pb200_ctx_create(pb200_ctx **out, int device) {
    cudaDeviceProp prop;
    PB_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
    ctx->num_sms = prop.multiProcessorCount;
-   PB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+   PB_CUDA(cudaStreamCreate(&ctx->stream));  // blocking: ordered with default-stream work of callbacks
    ctx->small_cap = 1 << 16; // 64 Ki doubles = 512 KB
    PB_CUDA(cudaMallocHost((void **)&ctx->h_pinned, ctx->small_cap * sizeof(double)));
    PB_CUDA(cudaMalloc((void **)&ctx->d_small, ctx->small_cap * sizeof(double)));
@@ -49,6 +49,10 @@ extern "C" int pb200_ctx_destroy(pb200_ctx *ctx) {
    cudaFree(ctx->d_panel);
    cudaFree(ctx->d_partials);
    cudaFree(ctx->d_scratch);
+   if (ctx->prof_ev) {
+      for (int i = 0; i < 2 * PB_PROF_RING; i++) cudaEventDestroy(ctx->prof_ev[i]);
+      free(ctx->prof_ev), free(ctx->prof_kind);
+   }
    cudaStreamDestroy(ctx->stream);
    free(ctx);
    return 0;
@@ -93,6 +97,53 @@ int pb_ensure_small(pb200_ctx *ctx, size_t doubles) {
    return 0;
 }
 
+// ------------------------------------------------------------------- event profiling ----
+int pb_prof_flush(pb200_ctx *ctx) {
+   if (!ctx->prof_ev || ctx->prof_pending == 0) return 0;
+   PB_CUDA(cudaStreamSynchronize(ctx->stream));
+   for (int i = 0; i < ctx->prof_pending; i++) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]) == cudaSuccess)
+         ctx->prof_ms[ctx->prof_kind[i]] += ms;
+   }
+   ctx->prof_pending = 0;
+   return 0;
+}
+int pb_prof_begin(pb200_ctx *ctx, int kind) {
+   if (!ctx->prof_on) return -1;
+   if (!ctx->prof_ev) {
+      ctx->prof_ev = (cudaEvent_t *)calloc(2 * PB_PROF_RING, sizeof(cudaEvent_t));
+      ctx->prof_kind = (int *)calloc(PB_PROF_RING, sizeof(int));
+      for (int i = 0; i < 2 * PB_PROF_RING; i++) cudaEventCreate(&ctx->prof_ev[i]);
+   }
+   if (ctx->prof_pending >= PB_PROF_RING) pb_prof_flush(ctx);
+   int slot = ctx->prof_pending++;
+   ctx->prof_kind[slot] = kind;
+   cudaEventRecord(ctx->prof_ev[2 * slot], ctx->stream);
+   return slot;
+}
+void pb_prof_end(pb200_ctx *ctx, int slot, double bytes) {
+   if (slot < 0) return;
+   cudaEventRecord(ctx->prof_ev[2 * slot + 1], ctx->stream);
+   int kind = ctx->prof_kind[slot];
+   ctx->prof_bytes[kind] += bytes;
+   ctx->prof_cnt[kind] += 1;
+}
+extern "C" int pb200_ctx_set_profiling(pb200_ctx *ctx, int on) {
+   pb_prof_flush(ctx);
+   ctx->prof_on = on;
+   if (on) {
+      for (int k = 0; k < 8; k++) ctx->prof_ms[k] = ctx->prof_bytes[k] = 0.0, ctx->prof_cnt[k] = 0;
+   }
+   return 0;
+}
+extern "C" int pb200_ctx_get_profile(pb200_ctx *ctx, int kind, int64_t *count, double *ms, double *bytes) {
+   if (kind < 0 || kind >= 8) return PB200_ERR_ARG;
+   pb_prof_flush(ctx);
+   *count = ctx->prof_cnt[kind], *ms = ctx->prof_ms[kind], *bytes = ctx->prof_bytes[kind];
+   return 0;
+}
+
 // out[e] = sum over parts p (ascending) of partials[p*cnt + e]: fixed order => reproducible.
 __global__ void pb_reduce_partials_kernel(
       const double *__restrict__ partials, int nparts, int cnt, double *__restrict__ out) {
@@ -113,8 +164,10 @@ __global__ void pb_reduce_partials_kernel(
 int pb_finish_panel(pb200_ctx *ctx, int nparts, int cnt) {
    if (cnt <= 0) return 0;
    PB_CHK(pb_ensure_small(ctx, (size_t)cnt));
+   int ps = pb_prof_begin(ctx, PB_K_REDUCE);
    pb_reduce_partials_kernel<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(
          ctx->d_partials, nparts, cnt, ctx->d_panel);
+   pb_prof_end(ctx, ps, 8.0 * nparts * cnt);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
    if (ctx->nranks > 1) PB_CHK(pb_nccl_allreduce_dev(ctx, ctx->d_panel, cnt));

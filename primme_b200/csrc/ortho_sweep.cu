@@ -258,12 +258,16 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
    if (cpw < 1) cpw = 1;
    size_t shmem = ((size_t)k * BT + BT * BT + (size_t)BT * TILE) * sizeof(double);
    int rc;
+   // algorithmic bytes: basis read once, X read (+written when updated)  
+   const double abytes = 8.0 * (double)n * (k + b * (a.do_update ? 2 : 1));
+   int ps = pb_prof_begin(ctx, PB_K_ORTHO);
    switch (BT) {
    case 1: rc = dispatch_cpw<1>(ctx, a, cpw, grid, shmem); break;
    case 2: rc = dispatch_cpw<2>(ctx, a, cpw, grid, shmem); break;
    case 4: rc = dispatch_cpw<4>(ctx, a, cpw, grid, shmem); break;
    default: rc = dispatch_cpw<8>(ctx, a, cpw, grid, shmem); break;
    }
+   pb_prof_end(ctx, ps, abytes);
    PB_CHK(rc);
    if (a.do_gram) {
       PB_CHK(pb_finish_panel(ctx, grid, rows * b));

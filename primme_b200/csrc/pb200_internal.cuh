@@ -37,6 +37,14 @@ struct pb200_ctx {
    void *d_scratch;       // growable scratch (permute etc.)
    size_t scratch_cap;
    int64_t launches;
+   // optional per-kernel-kind CUDA-event timing (bench.py's roofline numbers)
+   int prof_on;
+   int prof_pending;
+   cudaEvent_t *prof_ev;   // 2 * PB_PROF_RING events
+   int *prof_kind;
+   double prof_ms[8];
+   double prof_bytes[8];
+   int64_t prof_cnt[8];
    // NCCL (dlopen'ed lazily)
    void *comm;
    int nranks, rank;
@@ -50,3 +58,10 @@ int pb_ensure_small(pb200_ctx *ctx, size_t doubles);
 // allreduce, copy to h_pinned and synchronize.  Result readable at ctx->h_pinned[0..cnt).
 int pb_finish_panel(pb200_ctx *ctx, int nparts, int cnt);
 int pb_nccl_allreduce_dev(pb200_ctx *ctx, double *dbuf, int count);
+
+// kernel kinds for profiling
+enum { PB_K_SPMM = 0, PB_K_ORTHO = 1, PB_K_VWXR = 2, PB_K_UTIL = 3, PB_K_REDUCE = 4, PB_K_NKINDS = 5 };
+#define PB_PROF_RING 2048
+int pb_prof_begin(pb200_ctx *ctx, int kind);              // returns slot or -1
+void pb_prof_end(pb200_ctx *ctx, int slot, double bytes); // algorithmic bytes of the launch
+int pb_prof_flush(pb200_ctx *ctx);

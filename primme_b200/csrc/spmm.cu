@@ -301,10 +301,15 @@ extern "C" int pb200_dspmm(pb200_ctx *ctx, const pb200_csr *A, const double *X, 
       const double *Xc = X + (size_t)c0 * ldx;
       double *Yc = Y + (size_t)c0 * ldy;
       int rc;
+      // algorithmic bytes: nnz*(8+4) + (n+1)*8 (64-bit row pointers) + 2*n*b*8  
+      const double abytes = 12.0 * (double)A->nnz + 8.0 * (double)(A->nrows + 1) +
+                            8.0 * (double)b * (double)(A->nrows + A->ncols);
+      int ps = pb_prof_begin(ctx, PB_K_SPMM);
       if (b <= 1) rc = launch_spmm<1>(ctx, A, Xc, ldx, Yc, ldy, b);
       else if (b <= 2) rc = launch_spmm<2>(ctx, A, Xc, ldx, Yc, ldy, b);
       else if (b <= 4) rc = launch_spmm<4>(ctx, A, Xc, ldx, Yc, ldy, b);
       else rc = launch_spmm<8>(ctx, A, Xc, ldx, Yc, ldy, b);
+      pb_prof_end(ctx, ps, abytes);
       PB_CHK(rc);
       if (A->nlongrows > 0) {
          int tot = A->nlongrows * 8;

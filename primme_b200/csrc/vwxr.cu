@@ -311,6 +311,13 @@ extern "C" int pb200_dvwxr(pb200_ctx *ctx, int64_t n, const double *V, const dou
    if (shd < VT) shd = VT;
    size_t shmem = shd * sizeof(double);
    int rc;
+   // algorithmic bytes: V (and W) read once + every output column written once
+   double ocols = 0;
+   for (int t = 0; t < 3; t++) if (a.X[t].ptr) ocols += a.X[t].ce - a.X[t].cb;
+   if (a.Wo.ptr) ocols += a.Wo.ce - a.Wo.cb;
+   if (a.R.ptr) ocols += a.R.ce - a.R.cb;
+   const double abytes = 8.0 * (double)n * ((a.need_y ? 2.0 : 1.0) * m + ocols);
+   int ps = pb_prof_begin(ctx, PB_K_VWXR);
    switch (NT) {
    case 4: rc = launch_vwxr<4>(ctx, a, grid, shmem); break;
    case 8: rc = launch_vwxr<8>(ctx, a, grid, shmem); break;
@@ -321,6 +328,7 @@ extern "C" int pb200_dvwxr(pb200_ctx *ctx, int64_t n, const double *V, const dou
    case 48: rc = launch_vwxr<48>(ctx, a, grid, shmem); break;
    default: rc = launch_vwxr<64>(ctx, a, grid, shmem); break;
    }
+   pb_prof_end(ctx, ps, abytes);
    PB_CHK(rc);
    if (cnt > 0) {
       PB_CHK(pb_finish_panel(ctx, grid, cnt));

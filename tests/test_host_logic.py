@@ -1,0 +1,77 @@
+"""CPU tests (no GPU): the product's host control code (primme_b200/src/*.c) linked against the
+oracle kernels (oracle/_build/libprimme_hostcheck.so) must reproduce the UNMODIFIED reference:
+eigenvalues to 1e-10 relative, and identical outer-iteration / restart / matvec counts on
+non-degenerate spectra.  The fixture comes from tests/golden/make_golden.py; when the reference
+build is available (build container) it is also re-run live."""
+import numpy as np
+import pytest
+
+import harness as H
+import solver_checks as SC
+from golden.cases import CASES
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_hostcheck_matches_reference_fixture(name):
+    r = SC.run_case("hostcheck", name)
+    SC.check_against_golden(name, r, counts="exact")
+
+
+@pytest.mark.skipif(not H.have_reference(), reason="reference build (oracle/_ref) not available")
+@pytest.mark.parametrize("name", ["aniso_b4_smallest", "lap2d_b3_locking", "lap2d_b1_jacobi"])
+def test_fixture_is_current(name):
+    """the committed fixture equals what the reference produces here (pins the oracle)"""
+    r = SC.run_case("reference", name)
+    g = SC.GOLDEN[name]
+    assert np.allclose(r["evals"], g["evals"], rtol=1e-13, atol=0)
+    s = r["stats"]
+    assert (s["numOuterIterations"], s["numRestarts"], s["numMatvecs"]) == (
+        g["numOuterIterations"], g["numRestarts"], g["numMatvecs"])
+
+
+def test_dynamic_method_runs_as_gdk():
+    """PRIMME_DYNAMIC: the reference switches GD+k <-> JDQMR from wall-clock timings
+    (main_iter.c:427-437), so only eigenvalues/residuals are a parity criterion"""
+    from primme_b200 import api, matrices as M
+    csr = M.laplacian_1d(100)
+    r = H.solve("hostcheck", csr, 10, method=api.PRIMME_DYNAMIC, eps=1e-9, jacobi=True)
+    SC.check_invariants(csr, r, 1e-9, 0.0)
+    exact = 2 - 2 * np.cos(np.pi * np.arange(1, 11) / 101)
+    assert np.allclose(r["evals"], exact, rtol=1e-10)
+    assert r["params"].dynamicMethodSwitch == -1
+
+
+def test_initial_guesses_and_constraints():
+    """warm start (initSize) and orthogonality constraints (numOrthoConst), init.c:173-208"""
+    from primme_b200 import api, matrices as M
+    csr = M.laplacian_nd((12, 15))
+    n = 180
+    base = H.solve("hostcheck", csr, 4, method=api.PRIMME_GD_Olsen_plusK, eps=1e-10)
+    ref = H.solve("reference", csr, 4, method=api.PRIMME_GD_Olsen_plusK, eps=1e-10) if H.have_reference() else None
+    # warm start with slightly perturbed solutions converges in far fewer iterations
+    rng = np.random.default_rng(0)
+    guess = base["evecs"] + 1e-6 * rng.standard_normal((n, 4))
+    warm = H.solve("hostcheck", csr, 4, method=api.PRIMME_GD_Olsen_plusK, eps=1e-10, initSize=4, init_vecs=guess)
+    SC.check_invariants(csr, warm, 1e-10, 0.0)
+    assert warm["stats"]["numMatvecs"] < base["stats"]["numMatvecs"]
+    if ref is not None:
+        rw = H.solve("reference", csr, 4, method=api.PRIMME_GD_Olsen_plusK, eps=1e-10, initSize=4, init_vecs=guess)
+        assert rw["stats"]["numMatvecs"] == warm["stats"]["numMatvecs"]
+    # constraints: deflate the two lowest, the solver must return pairs 3.. of the spectrum
+    cons = base["evecs"][:, :2]
+    defl = H.solve("hostcheck", csr, 2, method=api.PRIMME_GD_Olsen_plusK, eps=1e-10, numOrthoConst=2, init_vecs=cons)
+    assert defl["ret"] == 0
+    assert np.allclose(defl["evals"], base["evals"][2:4], rtol=1e-9)
+
+
+def test_error_codes():
+    """input validation returns the reference's codes (primme_c.c:438-538)"""
+    import ctypes as C
+    from primme_b200 import api
+    lib = H.lib_hostcheck()
+    p = api.new_params(lib, 10, numEvals=20, method=api.PRIMME_GD)
+    ev = np.zeros(20)
+    assert lib.dprimme(ev.ctypes.data, ev.ctypes.data, ev.ctypes.data, C.byref(p)) == -7  # no matvec
+    p = api.new_params(lib, 10, numEvals=2, method=api.PRIMME_JDQMR)
+    p.matrixMatvec = 1
+    assert lib.dprimme(ev.ctypes.data, ev.ctypes.data, ev.ctypes.data, C.byref(p)) == -44  # out of scope

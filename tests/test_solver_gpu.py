@@ -1,0 +1,57 @@
+"""GPU parity of the whole hot path through the C-ABI: cublas_dprimme / dprimme of the product
+against the committed reference fixture and the invariants of the reference's check_solution."""
+import numpy as np
+import pytest
+
+import harness as H
+import solver_checks as SC
+from golden.cases import CASES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_product_matches_reference_fixture(name):
+    r = SC.run_case("product", name)
+    got, want = SC.check_against_golden(name, r, counts="close")
+    assert r["launches"] > 0  # the CUDA path did the work
+    print(name, "counts", got, "reference", want)
+
+
+def test_c2_full_size_properties():
+    """config C2 at full size (n = 10^6): analytic eigenvalues of the 3-D Laplacian,
+    orthonormality and residuals (no CPU oracle at this size)."""
+    from primme_b200 import api, matrices as M
+    N = 100
+    csr = M.laplacian_nd((N, N, N))
+    r = H.solve("product", csr, 10, method=api.PRIMME_GD_Olsen_plusK, maxBlockSize=4, maxBasisSize=40,
+                eps=1e-10, aNorm=12.0)
+    assert r["ret"] == 0
+    lam1 = 4 * np.sin(np.pi * np.arange(1, 4) / (2 * (N + 1))) ** 2
+    exact = np.sort([lam1[i] + lam1[j] + lam1[k] for i in range(3) for j in range(3) for k in range(3)])[:10]
+    assert np.allclose(r["evals"], exact, rtol=1e-10, atol=0)
+    SC.check_invariants(csr, r, 1e-10, 12.0)
+    s = r["stats"]
+    # reference on this container: 1045 outer / 195 restarts / 3919 matvecs
+    assert abs(s["numMatvecs"] - 3919) < 0.1 * 3919, s
+
+
+def test_host_contract_dprimme():
+    """dprimme with HOST evecs and a HOST matvec callback (reference dprimme contract)"""
+    import ctypes as C
+    from primme_b200 import api, matrices as M
+    lib = H.lib_product()
+    ok = H.lib_oracle_kernels()  # only its host CSR callback is used (test infrastructure)
+    ip, ix, da = M.laplacian_nd((13, 17, 19))
+    n = len(ip) - 1
+    A = H.CsrHost(n, ip.ctypes.data, ix.ctypes.data, da.ctypes.data, 1, None, 0.0, 0)
+    p = api.new_params(lib, n, numEvals=8, maxBlockSize=4, maxBasisSize=40, eps=1e-10)
+    p.matrix = C.addressof(A)
+    p.matrixMatvec = C.cast(ok.csr_host_matvec, C.c_void_p).value
+    assert lib.primme_set_method(api.PRIMME_GD_Olsen_plusK, C.byref(p)) == 0
+    evals, rn, evecs = np.zeros(8), np.zeros(8), np.zeros((8, n))
+    rc = lib.dprimme(evals.ctypes.data, evecs.ctypes.data, rn.ctypes.data, C.byref(p))
+    assert rc == 0
+    g = SC.GOLDEN["aniso_b4_smallest"]
+    assert np.allclose(evals, g["evals"], rtol=1e-10)
+    assert p.stats.numMatvecs == g["numMatvecs"] or abs(p.stats.numMatvecs - g["numMatvecs"]) < 0.05 * g["numMatvecs"]

@@ -11,7 +11,7 @@ NVCC   ?= nvcc
 CC     ?= gcc
 ARCH   := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -Xcompiler -fPIC -std=c++17
-CFLAGS := -O2 -fPIC -std=c99 -Wall -Wno-unused-function -D_POSIX_C_SOURCE=200809L
+CFLAGS := -O2 -fPIC -std=c99 -Wall -Wno-unused-function -D_GNU_SOURCE
 
 HOST_SRC := $(wildcard primme_b200/src/*.c)
 HOST_OBJ := $(patsubst primme_b200/src/%.c,build/host/%.o,$(HOST_SRC))

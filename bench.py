@@ -43,8 +43,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--side", type=int, default=100, help="grid points per side (n = side^3)")
-    ap.add_argument("--ref-matvecs", type=int, default=160,
+    ap.add_argument("--ref-matvecs", type=int, default=120,
                     help="bounded sample of the reference arm: matvecs per step")
+    ap.add_argument("--ref-threads", type=int, default=0,
+                    help="host threads of the reference arm (0: min(cores, 16); OpenBLAS on 100+ "
+                         "threads is slower on these tall-skinny panels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -107,12 +110,15 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ref_threads(args):
+    return args.ref_threads if args.ref_threads > 0 else min(os.cpu_count() or 1, 16)
+
+
 def run_reference(args, csr, rank):
     """the reference's own CPU path on a bounded sample of the workload"""
     import harness as H
     from primme_b200 import api
-    ncores = os.cpu_count() or 1
-    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(ncores))
+    ncores = ref_threads(args)
     times, mvs = [], []
     for step in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -127,6 +133,9 @@ def run_reference(args, csr, rank):
 
 def main():
     args = parse()
+    # OpenBLAS reads its thread count when the library is first loaded (the product links the same
+    # OpenBLAS for its tiny host-side algebra and pins it to one thread during a solve)
+    os.environ["OPENBLAS_NUM_THREADS"] = str(ref_threads(args))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -294,7 +303,9 @@ def main():
                            "parallelism": "replicas only" if args.gpus > 1 else "single GPU",
                            "l2": "working set per sweep (V,W 2x320 MB at n=1e6) exceeds the 126 MB L2; no flush",
                            "outer_iterations": stats["numOuterIterations"], "restarts": stats["numRestarts"],
-                           "matvecs_per_solve": stats["numMatvecs"], "time_to_converge_s": ms / args.steps / 1e3},
+                           "matvecs_per_solve": stats["numMatvecs"], "time_to_converge_s": ms / args.steps / 1e3,
+                           "host_timers_s": {"matvec": stats["timeMatvec"], "ortho": stats["timeOrtho"],
+                                             "dense_vwxr": stats["timeDense"], "elapsed": stats["elapsedTime"]}},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "matvecs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e / max(1, min(args.steps, 3))},

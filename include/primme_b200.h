@@ -87,6 +87,20 @@ int pb200_csr_build_transpose(pb200_ctx *ctx, pb200_csr *A);
 int pb200_dspmm_t(pb200_ctx *ctx, const pb200_csr *A, const double *X, int64_t ldx, double *Y,
       int64_t ldy, int ncols);
 
+/* ---- row-sharded operator (one process per GPU) --------------------------------
+ * A_local holds this rank's rows with GLOBAL column indices; counts_host[r] = rows of rank r.
+ * Y_local = A_local * allgather(X_local): the SpMV halo is one grouped NCCL exchange over
+ * NVLink.  Replaces the MPI matvec of reference examples/ex_eigs_mpi.c. */
+typedef struct pb200_dist_csr pb200_dist_csr;
+int pb200_comm_unique_id(void *id128);
+int pb200_ctx_comm_init(pb200_ctx *ctx, int nranks, int rank, const void *id128);
+int pb200_ctx_comm_free(pb200_ctx *ctx);
+int pb200_dist_csr_create(pb200_ctx *ctx, pb200_csr *A_local, const int64_t *counts_host,
+      int nranks, pb200_dist_csr **D);
+int pb200_dist_csr_destroy(pb200_ctx *ctx, pb200_dist_csr *D);
+int pb200_ddist_spmm(pb200_ctx *ctx, pb200_dist_csr *D, const double *X, int64_t ldx, double *Y,
+      int64_t ldy, int ncols);
+
 /* ------------------------------------------------- K2/K3/K4: fused block-ortho row sweep -- */
 /* One pass over the rows of [Q V X]:
  *    if C_host:  X <- (X - [Q V(:,0:mv)] * C) * Y      (Y = identity if Y_host == NULL)
@@ -164,6 +178,9 @@ int pb200_djacobi(pb200_ctx *ctx, int64_t n, const double *diag, const double *s
 struct primme_params;
 /* primme.matrix = pb200_csr*;  primme.matrixMatvec = primme_b200_csr_matvec */
 void primme_b200_csr_matvec(void *x, int64_t *ldx, void *y, int64_t *ldy, int *blockSize,
+      struct primme_params *primme, int *ierr);
+/* primme.matrix = pb200_dist_csr*; primme.matrixMatvec = primme_b200_dist_csr_matvec */
+void primme_b200_dist_csr_matvec(void *x, int64_t *ldx, void *y, int64_t *ldy, int *blockSize,
       struct primme_params *primme, int *ierr);
 /* primme.preconditioner = primme_b200_jacobi*;  primme.applyPreconditioner = ..._jacobi_apply
  * (Davidson diagonal preconditioner of the reference test driver, tests/COMMON/mat.c:137-165) */

@@ -80,6 +80,15 @@ int pb200_bcast_host(pb200_ctx *ctx, double *buf, int count, int root) {
    return 0;
 }
 
+/* multi-rank pieces: the oracle is sequential (N > 1 host logic is tested with gloo callbacks) */
+int pb200_comm_unique_id(void *id128) { (void)id128; return PB200_ERR_ARG; }
+int pb200_ctx_comm_init(pb200_ctx *ctx, int nranks, int rank, const void *id) { (void)ctx, (void)nranks, (void)rank, (void)id; return PB200_ERR_ARG; }
+int pb200_ctx_comm_free(pb200_ctx *ctx) { (void)ctx; return 0; }
+int pb200_dist_csr_create(pb200_ctx *ctx, pb200_csr *A, const int64_t *c, int nr, pb200_dist_csr **D) { (void)ctx, (void)A, (void)c, (void)nr, (void)D; return PB200_ERR_ARG; }
+int pb200_dist_csr_destroy(pb200_ctx *ctx, pb200_dist_csr *D) { (void)ctx, (void)D; return 0; }
+int pb200_ddist_spmm(pb200_ctx *ctx, pb200_dist_csr *D, const double *X, int64_t ldx, double *Y, int64_t ldy, int nc) { (void)ctx, (void)D, (void)X, (void)ldx, (void)Y, (void)ldy, (void)nc; return PB200_ERR_ARG; }
+void primme_b200_dist_csr_matvec(void *x, int64_t *ldx, void *y, int64_t *ldy, int *bs, struct primme_params *p, int *ierr) { (void)x, (void)ldx, (void)y, (void)ldy, (void)bs, (void)p; *ierr = -1; }
+
 int pb200_malloc(pb200_ctx *ctx, size_t bytes, void **dptr) {
    (void)ctx;
    *dptr = malloc(bytes ? bytes : 1);

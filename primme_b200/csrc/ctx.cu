@@ -37,6 +37,7 @@ extern "C" int pb200_ctx_create(pb200_ctx **out, int device) {
    ctx->partials_cap = 0;
    ctx->d_partials = NULL;
    ctx->nranks = 1;
+   ctx->use_tma = getenv("PB200_NO_TMA") ? 0 : 1;
    *out = ctx;
    return 0;
 }
@@ -44,6 +45,7 @@ extern "C" int pb200_ctx_create(pb200_ctx **out, int device) {
 extern "C" int pb200_ctx_destroy(pb200_ctx *ctx) {
    if (!ctx) return 0;
    cudaStreamSynchronize(ctx->stream);
+   if (ctx->comm && ctx->owns_comm) pb200_ctx_comm_free(ctx);
    cudaFreeHost(ctx->h_pinned);
    cudaFree(ctx->d_small);
    cudaFree(ctx->d_panel);
@@ -144,28 +146,41 @@ extern "C" int pb200_ctx_get_profile(pb200_ctx *ctx, int kind, int64_t *count, d
    return 0;
 }
 
-// out[e] = sum over parts p (ascending) of partials[p*cnt + e]: fixed order => reproducible.
-__global__ void pb_reduce_partials_kernel(
+// out[e] = sum over the per-CTA partial panels, in a FIXED order => bitwise reproducible.
+// One CTA of 8 warps per 32 consecutive elements: lane <-> element (coalesced rows of the
+// partials array), warp w sums parts w, w+8, w+16, ... (4 independent chains), the 8 warp sums
+// are combined in warp order through shared memory.
+__global__ void __launch_bounds__(256) pb_reduce_partials_kernel(
       const double *__restrict__ partials, int nparts, int cnt, double *__restrict__ out) {
-   int e = blockIdx.x * blockDim.x + threadIdx.x;
-   if (e >= cnt) return;
+   __shared__ double red[8][33];
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+   const int e = blockIdx.x * 32 + lane;
    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-   int p = 0;
-   for (; p + 4 <= nparts; p += 4) {
-      s0 += partials[(size_t)(p + 0) * cnt + e];
-      s1 += partials[(size_t)(p + 1) * cnt + e];
-      s2 += partials[(size_t)(p + 2) * cnt + e];
-      s3 += partials[(size_t)(p + 3) * cnt + e];
+   if (e < cnt) {
+      int p = warp;
+      for (; p + 24 < nparts; p += 32) {
+         s0 += partials[(size_t)(p + 0) * cnt + e];
+         s1 += partials[(size_t)(p + 8) * cnt + e];
+         s2 += partials[(size_t)(p + 16) * cnt + e];
+         s3 += partials[(size_t)(p + 24) * cnt + e];
+      }
+      for (; p < nparts; p += 8) s0 += partials[(size_t)p * cnt + e];
    }
-   for (; p < nparts; p++) s0 += partials[(size_t)p * cnt + e];
-   out[e] = (s0 + s1) + (s2 + s3);
+   red[warp][lane] = (s0 + s1) + (s2 + s3);
+   __syncthreads();
+   if (warp == 0 && e < cnt) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) s += red[w][lane];
+      out[e] = s;
+   }
 }
 
 int pb_finish_panel(pb200_ctx *ctx, int nparts, int cnt) {
    if (cnt <= 0) return 0;
    PB_CHK(pb_ensure_small(ctx, (size_t)cnt));
    int ps = pb_prof_begin(ctx, PB_K_REDUCE);
-   pb_reduce_partials_kernel<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(
+   pb_reduce_partials_kernel<<<(cnt + 31) / 32, 256, 0, ctx->stream>>>(
          ctx->d_partials, nparts, cnt, ctx->d_panel);
    pb_prof_end(ctx, ps, 8.0 * nparts * cnt);
    ctx->launches++;
@@ -232,8 +247,17 @@ extern "C" int pb200_is_device_pointer(const void *p) {
 // NCCL is resolved at run time (dlopen) so that single-GPU users need no libnccl at link time.
 typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
 typedef int (*nccl_bcast_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_void_fn)(void);
+typedef int (*nccl_uid_fn)(void *);
+typedef struct { char internal[128]; } pb_nccl_uid;
+typedef int (*nccl_init_fn)(void **, int, pb_nccl_uid, int);
+typedef int (*nccl_destroy_fn)(void *);
 static nccl_allreduce_fn p_ncclAllReduce = NULL;
 static nccl_bcast_fn p_ncclBroadcast = NULL;
+static nccl_void_fn p_ncclGroupStart = NULL, p_ncclGroupEnd = NULL;
+static nccl_uid_fn p_ncclGetUniqueId = NULL;
+static nccl_init_fn p_ncclCommInitRank = NULL;
+static nccl_destroy_fn p_ncclCommDestroy = NULL;
 enum { PB_NCCL_FLOAT64 = 8, PB_NCCL_SUM = 0 };
 
 static int pb_nccl_load(void) {
@@ -246,7 +270,57 @@ static int pb_nccl_load(void) {
    }
    p_ncclAllReduce = (nccl_allreduce_fn)dlsym(h, "ncclAllReduce");
    p_ncclBroadcast = (nccl_bcast_fn)dlsym(h, "ncclBroadcast");
-   return (p_ncclAllReduce && p_ncclBroadcast) ? 0 : PB200_ERR_CUDA;
+   p_ncclGroupStart = (nccl_void_fn)dlsym(h, "ncclGroupStart");
+   p_ncclGroupEnd = (nccl_void_fn)dlsym(h, "ncclGroupEnd");
+   p_ncclGetUniqueId = (nccl_uid_fn)dlsym(h, "ncclGetUniqueId");
+   p_ncclCommInitRank = (nccl_init_fn)dlsym(h, "ncclCommInitRank");
+   p_ncclCommDestroy = (nccl_destroy_fn)dlsym(h, "ncclCommDestroy");
+   return (p_ncclAllReduce && p_ncclBroadcast && p_ncclGroupStart && p_ncclGroupEnd &&
+                p_ncclGetUniqueId && p_ncclCommInitRank && p_ncclCommDestroy)
+                ? 0
+                : PB200_ERR_CUDA;
+}
+
+// 128-byte NCCL unique id, to be created on rank 0 and shared by the launcher
+extern "C" int pb200_comm_unique_id(void *id128) {
+   PB_CHK(pb_nccl_load());
+   return p_ncclGetUniqueId(id128) == 0 ? 0 : PB200_ERR_CUDA;
+}
+// Create this rank's communicator and attach it to the context
+extern "C" int pb200_ctx_comm_init(pb200_ctx *ctx, int nranks, int rank, const void *id128) {
+   PB_CHK(pb_nccl_load());
+   pb_nccl_uid uid;
+   memcpy(&uid, id128, sizeof(uid));
+   void *comm = NULL;
+   PB_CUDA(cudaSetDevice(ctx->device));
+   if (p_ncclCommInitRank(&comm, nranks, uid, rank) != 0) return PB200_ERR_CUDA;
+   ctx->comm = comm, ctx->nranks = nranks, ctx->rank = rank;
+   ctx->owns_comm = 1;
+   return 0;
+}
+extern "C" int pb200_ctx_comm_free(pb200_ctx *ctx) {
+   if (ctx->comm && ctx->owns_comm) {
+      cudaStreamSynchronize(ctx->stream);
+      p_ncclCommDestroy(ctx->comm);
+   }
+   ctx->comm = NULL, ctx->nranks = 1, ctx->rank = 0, ctx->owns_comm = 0;
+   return 0;
+}
+// Y(displs[r] .. +counts[r]) on every rank <- X of rank r, for each of ncols columns:
+// all-gather with unequal counts as grouped broadcasts (halo exchange of the SpMV block).
+int pb_nccl_allgatherv_cols(pb200_ctx *ctx, const double *X, int64_t ldx, double *Y, int64_t ldy,
+      const int64_t *counts, const int64_t *displs, int ncols) {
+   if (ctx->nranks <= 1) return 0;
+   if (p_ncclGroupStart() != 0) return PB200_ERR_CUDA;
+   for (int c = 0; c < ncols; c++)
+      for (int r = 0; r < ctx->nranks; r++) {
+         const double *src = (r == ctx->rank) ? X + (size_t)c * ldx : Y + (size_t)c * ldy + displs[r];
+         if (p_ncclBroadcast(src, Y + (size_t)c * ldy + displs[r], (size_t)counts[r], PB_NCCL_FLOAT64, r,
+                   ctx->comm, ctx->stream) != 0)
+            return PB200_ERR_CUDA;
+      }
+   if (p_ncclGroupEnd() != 0) return PB200_ERR_CUDA;
+   return 0;
 }
 
 extern "C" int pb200_ctx_set_comm(pb200_ctx *ctx, void *nccl_comm, int nranks, int rank) {

@@ -14,6 +14,7 @@
 //   epilogue: warp-shuffle reduction, one partial panel per CTA, fixed-order second stage
 //            (pb_finish_panel) => bitwise reproducible panels.
 #include "pb200_internal.cuh"
+#include "tma_pipe.cuh"
 #include <string.h>
 
 namespace {
@@ -177,6 +178,221 @@ __global__ void __launch_bounds__(TILE) ortho_sweep_kernel(SweepArgs a) {
    }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// v2: TMA-staged variant.  A dedicated producer warp streams 128-row tiles of [Q V X] into a
+// ring of shared-memory stages with one bulk copy (cp.async.bulk, SASS UBLKCP) per column
+// segment, completion tracked by mbarriers; 8 consumer warps do the update and the Gram from
+// shared memory.  Memory-level parallelism no longer depends on registers/occupancy: up to
+// 4 tiles (~200 KB) are in flight per SM.  Requires 16-byte aligned columns (even leading
+// dimensions) and handles full tiles only; the < 128-row tail goes through the v1 kernel.
+constexpr int TR = 128;          // rows per tile
+constexpr int NCW = 8;           // consumer warps
+constexpr int NCT = NCW * 32;    // consumer threads
+
+template <int BT, int CPW>
+__global__ void __launch_bounds__(NCT + 32) ortho_sweep_tma_kernel(SweepArgs a, int nstages) {
+   extern __shared__ __align__(128) unsigned char smraw[];
+   const int k = a.q + a.mv;
+   const int kc = k + a.b;
+   double *stage0 = reinterpret_cast<double *>(smraw);
+   double *Cs = stage0 + (size_t)nstages * kc * TR;  // k * BT
+   double *Ys = Cs + (size_t)k * BT;                 // BT * BT
+   double *xs = Ys + BT * BT;                        // BT * TR (updated X tile)
+   double *exch = xs + BT * TR;                      // 2 * TR * BT (partial updates)
+   uint64_t *full = reinterpret_cast<uint64_t *>(exch + 2 * TR * BT);
+   uint64_t *empty = full + nstages;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+   if (tid == 0) {
+      for (int s = 0; s < nstages; s++) {
+         pbtma::mbar_init(&full[s], 1);
+         pbtma::mbar_init(&empty[s], NCW);
+      }
+      pbtma::fence_barrier_init();
+   }
+   if (a.do_update) {
+      for (int i = tid; i < k * BT; i += NCT + 32) {
+         int j = i % k, c = i / k;
+         Cs[j * BT + c] = (c < a.b) ? a.Cdev[j + (size_t)c * k] : 0.0;
+      }
+      for (int i = tid; i < BT * BT; i += NCT + 32) {
+         int r = i % BT, c = i / BT;
+         double y = (r == c) ? 1.0 : 0.0;
+         if (a.has_Y) y = (r < a.b && c < a.b) ? a.Ydev[r + c * BT] : 0.0;
+         Ys[r * BT + c] = y;
+      }
+   }
+   __syncthreads();
+
+   const int64_t ntiles = a.n / TR;  // full tiles only
+   if (warp == NCW) {
+      // ------------------------------ producer warp ------------------------------
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+         if (lane == 0) {
+            pbtma::mbar_wait(&empty[s], ph ^ 1);
+            pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(kc * TR * sizeof(double)));
+         }
+         __syncwarp();
+         double *dst = stage0 + (size_t)s * kc * TR;
+         const int64_t r0 = tile * TR;
+         for (int c = lane; c < kc; c += 32) {
+            const double *src = c < k ? col_ptr(a, c) + r0 : a.X + (size_t)(c - k) * a.ldx + r0;
+            pbtma::bulk_g2s(dst + (size_t)c * TR, src, TR * sizeof(double), &full[s]);
+         }
+         if (++s == nstages) s = 0, ph ^= 1;
+      }
+      return;
+   }
+
+   // ------------------------------ consumer warps ------------------------------
+   double acc[CPW][BT];
+   double accx[BT];
+#pragma unroll
+   for (int j = 0; j < CPW; j++)
+#pragma unroll
+      for (int c = 0; c < BT; c++) acc[j][c] = 0.0;
+#pragma unroll
+   for (int c = 0; c < BT; c++) accx[c] = 0.0;
+
+   const int row1 = tid & (TR - 1), half = tid >> 7;  // phase-1 mapping: 2 threads per row
+   const int kh = (k + 1) / 2, j0 = half * kh, j1 = (j0 + kh < k) ? j0 + kh : k;
+
+   int s = 0;
+   uint32_t ph = 0;
+   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      pbtma::mbar_wait(&full[s], ph);
+      const double *st = stage0 + (size_t)s * kc * TR;
+      const double *xsrc = st + (size_t)k * TR;  // X columns of this tile, [c][row]
+      if (a.do_update) {
+         // phase 1: each half of the CTA applies half of the basis columns to its row
+         double t[BT];
+#pragma unroll
+         for (int c = 0; c < BT; c++) t[c] = 0.0;
+         int j = j0;
+         for (; j + 2 <= j1; j += 2) {
+            double v0 = st[(size_t)j * TR + row1], v1 = st[(size_t)(j + 1) * TR + row1];
+#pragma unroll
+            for (int c = 0; c < BT; c++) t[c] += v0 * Cs[j * BT + c] + v1 * Cs[(j + 1) * BT + c];
+         }
+         if (j < j1) {
+            double v0 = st[(size_t)j * TR + row1];
+#pragma unroll
+            for (int c = 0; c < BT; c++) t[c] += v0 * Cs[j * BT + c];
+         }
+#pragma unroll
+         for (int c = 0; c < BT; c++) exch[(size_t)(half * TR + row1) * BT + c] = t[c];
+         pbtma::named_bar_sync(1, NCT);
+         if (half == 0) {
+            double x[BT];
+#pragma unroll
+            for (int c = 0; c < BT; c++)
+               x[c] = (c < a.b ? xsrc[(size_t)c * TR + row1] : 0.0) - exch[(size_t)row1 * BT + c] -
+                      exch[(size_t)(TR + row1) * BT + c];
+            if (a.has_Y) {
+               double y[BT];
+#pragma unroll
+               for (int c = 0; c < BT; c++) {
+                  double sum = 0.0;
+#pragma unroll
+                  for (int cc = 0; cc < BT; cc++) sum += x[cc] * Ys[cc * BT + c];
+                  y[c] = sum;
+               }
+#pragma unroll
+               for (int c = 0; c < BT; c++) x[c] = y[c];
+            }
+            const int64_t r = tile * TR + row1;
+#pragma unroll
+            for (int c = 0; c < BT; c++) {
+               if (c < a.b) a.X[r + (size_t)c * a.ldx] = x[c];
+               xs[(size_t)c * TR + row1] = x[c];
+            }
+         }
+         pbtma::named_bar_sync(1, NCT);
+         xsrc = xs;
+      }
+      if (a.do_gram) {
+#pragma unroll
+         for (int i = 0; i < TR / 32; i++) {
+            const int row = i * 32 + lane;
+            double xv[BT];
+#pragma unroll
+            for (int c = 0; c < BT; c++) xv[c] = (c < a.b) ? xsrc[(size_t)c * TR + row] : 0.0;
+#pragma unroll
+            for (int j = 0; j < CPW; j++) {
+               const int jj = warp * CPW + j;
+               const double av = jj < k ? st[(size_t)jj * TR + row] : 0.0;
+#pragma unroll
+               for (int c = 0; c < BT; c++) acc[j][c] += av * xv[c];
+            }
+            if (a.xx && warp < a.b) {
+               const double xw = xsrc[(size_t)warp * TR + row];
+#pragma unroll
+               for (int c = 0; c < BT; c++) accx[c] += xw * xv[c];
+            }
+         }
+      }
+      __syncwarp();
+      if (lane == 0) pbtma::mbar_arrive(&empty[s]);  // this warp is done with the stage
+      if (++s == nstages) s = 0, ph ^= 1;
+   }
+
+   if (!a.do_gram) return;
+   const int rows = k + (a.xx ? a.b : 0);
+   double *out = a.partials + (size_t)blockIdx.x * rows * a.b;
+#pragma unroll
+   for (int j = 0; j < CPW; j++) {
+#pragma unroll
+      for (int c = 0; c < BT; c++) {
+         double v = acc[j][c];
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+         int jj = warp * CPW + j;
+         if (lane == 0 && jj < k && c < a.b) out[jj + (size_t)c * rows] = v;
+      }
+   }
+   if (a.xx) {
+#pragma unroll
+      for (int c = 0; c < BT; c++) {
+         double v = accx[c];
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+         if (lane == 0 && warp < a.b && c < a.b) out[k + warp + (size_t)c * rows] = v;
+      }
+   }
+}
+
+template <int BT, int CPW>
+int launch_sweep_tma(pb200_ctx *ctx, const SweepArgs &a, int grid, size_t shmem, int nstages) {
+   auto kern = ortho_sweep_tma_kernel<BT, CPW>;
+   PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+   kern<<<grid, NCT + 32, shmem, ctx->stream>>>(a, nstages);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   return 0;
+}
+
+template <int BT>
+int dispatch_cpw_tma(pb200_ctx *ctx, const SweepArgs &a, int cpw, int grid, size_t shmem, int nst) {
+   switch (cpw) {
+   case 1: return launch_sweep_tma<BT, 1>(ctx, a, grid, shmem, nst);
+   case 2: return launch_sweep_tma<BT, 2>(ctx, a, grid, shmem, nst);
+   case 3: return launch_sweep_tma<BT, 3>(ctx, a, grid, shmem, nst);
+   case 4: return launch_sweep_tma<BT, 4>(ctx, a, grid, shmem, nst);
+   case 5: return launch_sweep_tma<BT, 5>(ctx, a, grid, shmem, nst);
+   case 6: return launch_sweep_tma<BT, 6>(ctx, a, grid, shmem, nst);
+   case 7:
+   case 8: return launch_sweep_tma<BT, 8>(ctx, a, grid, shmem, nst);
+   case 9:
+   case 10: return launch_sweep_tma<BT, 10>(ctx, a, grid, shmem, nst);
+   case 11:
+   case 12: return launch_sweep_tma<BT, 12>(ctx, a, grid, shmem, nst);
+   default: return PB200_ERR_ARG;
+   }
+}
+
 template <int BT, int CPW>
 int launch_sweep(pb200_ctx *ctx, const SweepArgs &a, int grid, size_t shmem) {
    auto kern = ortho_sweep_kernel<BT, CPW>;
@@ -246,29 +462,87 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
       a.Ydev = ctx->d_small + (size_t)k * BT;
    }
 
-   const int64_t ntiles = (n + TILE - 1) / TILE;
-   int grid = (int)(ntiles < (int64_t)ctx->num_sms * 3 ? ntiles : (int64_t)ctx->num_sms * 3);
-   if (grid < 1) grid = 1;
    const int rows = k + (a.xx ? b : 0);
-   if (a.do_gram) {
-      PB_CHK(pb_ensure_partials(ctx, (size_t)grid * rows * b));
-      a.partials = ctx->d_partials;
-   }
    int cpw = (k + NWARP - 1) / NWARP;
    if (cpw < 1) cpw = 1;
-   size_t shmem = ((size_t)k * BT + BT * BT + (size_t)BT * TILE) * sizeof(double);
-   int rc;
    // algorithmic bytes: basis read once, X read (+written when updated)  
    const double abytes = 8.0 * (double)n * (k + b * (a.do_update ? 2 : 1));
+
+   // ---- v2 (TMA-staged) eligibility: 16-byte aligned column segments, enough rows, tile ring
+   // of >= 2 stages in shared memory ----
+   const int kc = k + b;
+   auto aligned16 = [](const void *p) { return (((uintptr_t)p) & 15) == 0; };
+   bool tma_ok = ctx->use_tma && n >= 4 * TR && kc <= 96 && aligned16(X) && (ldx % 2 == 0) &&
+                 (q == 0 || (aligned16(Q) && ldq % 2 == 0)) && (mv == 0 || (aligned16(V) && ldv % 2 == 0));
+   int nstages = 0, ctas_per_sm = 1;
+   size_t fixed_sm = ((size_t)k * BT + BT * BT + (size_t)BT * TR + 2 * (size_t)TR * BT) * sizeof(double) + 64;
+   if (tma_ok) {
+      const size_t stage_b = (size_t)kc * TR * sizeof(double);
+      if (3 * stage_b + fixed_sm <= 110 * 1024) {
+         nstages = 3, ctas_per_sm = 2;
+      } else {
+         nstages = (int)((220 * 1024 - fixed_sm) / stage_b);
+         if (nstages > 4) nstages = 4;
+      }
+      if (nstages < 2) tma_ok = false;
+   }
+
+   int grid = 0, nparts = 0, rc = 0;
    int ps = pb_prof_begin(ctx, PB_K_ORTHO);
-   switch (BT) {
-   case 1: rc = dispatch_cpw<1>(ctx, a, cpw, grid, shmem); break;
-   case 2: rc = dispatch_cpw<2>(ctx, a, cpw, grid, shmem); break;
-   case 4: rc = dispatch_cpw<4>(ctx, a, cpw, grid, shmem); break;
-   default: rc = dispatch_cpw<8>(ctx, a, cpw, grid, shmem); break;
+   if (tma_ok) {
+      const int64_t ntiles = n / TR;
+      const int64_t n_main = ntiles * TR;
+      grid = (int)(ntiles < (int64_t)ctx->num_sms * ctas_per_sm ? ntiles : (int64_t)ctx->num_sms * ctas_per_sm);
+      const int tail = n_main < n ? 1 : 0;
+      if (a.do_gram) {
+         PB_CHK(pb_ensure_partials(ctx, (size_t)(grid + tail) * rows * b));
+         a.partials = ctx->d_partials;
+      }
+      SweepArgs am = a;
+      am.n = n_main;
+      size_t shmem = (size_t)nstages * kc * TR * sizeof(double) + fixed_sm + 2 * nstages * sizeof(uint64_t);
+      switch (BT) {
+      case 1: rc = dispatch_cpw_tma<1>(ctx, am, cpw, grid, shmem, nstages); break;
+      case 2: rc = dispatch_cpw_tma<2>(ctx, am, cpw, grid, shmem, nstages); break;
+      case 4: rc = dispatch_cpw_tma<4>(ctx, am, cpw, grid, shmem, nstages); break;
+      default: rc = dispatch_cpw_tma<8>(ctx, am, cpw, grid, shmem, nstages); break;
+      }
+      nparts = grid;
+      if (!rc && tail) {
+         // rows [n_main, n): one CTA of the v1 kernel, its partial panel goes to slot `grid`
+         SweepArgs at = a;
+         at.n = n - n_main;
+         at.Q = Q ? Q + n_main : Q, at.V = V ? V + n_main : V, at.X = X + n_main;
+         if (a.do_gram) at.partials = ctx->d_partials + (size_t)grid * rows * b;
+         size_t shmem1 = ((size_t)k * BT + BT * BT + (size_t)BT * TILE) * sizeof(double);
+         switch (BT) {
+         case 1: rc = dispatch_cpw<1>(ctx, at, cpw, 1, shmem1); break;
+         case 2: rc = dispatch_cpw<2>(ctx, at, cpw, 1, shmem1); break;
+         case 4: rc = dispatch_cpw<4>(ctx, at, cpw, 1, shmem1); break;
+         default: rc = dispatch_cpw<8>(ctx, at, cpw, 1, shmem1); break;
+         }
+         nparts = grid + 1;
+      }
+   } else {
+      const int64_t ntiles = (n + TILE - 1) / TILE;
+      grid = (int)(ntiles < (int64_t)ctx->num_sms * 3 ? ntiles : (int64_t)ctx->num_sms * 3);
+      if (grid < 1) grid = 1;
+      if (a.do_gram) {
+         PB_CHK(pb_ensure_partials(ctx, (size_t)grid * rows * b));
+         a.partials = ctx->d_partials;
+      }
+      size_t shmem = ((size_t)k * BT + BT * BT + (size_t)BT * TILE) * sizeof(double);
+      switch (BT) {
+      case 1: rc = dispatch_cpw<1>(ctx, a, cpw, grid, shmem); break;
+      case 2: rc = dispatch_cpw<2>(ctx, a, cpw, grid, shmem); break;
+      case 4: rc = dispatch_cpw<4>(ctx, a, cpw, grid, shmem); break;
+      default: rc = dispatch_cpw<8>(ctx, a, cpw, grid, shmem); break;
+      }
+      nparts = grid;
    }
    pb_prof_end(ctx, ps, abytes);
    PB_CHK(rc);
+   grid = nparts;
    if (a.do_gram) {
       PB_CHK(pb_finish_panel(ctx, grid, rows * b));
       for (int c = 0; c < b; c++)

@@ -37,6 +37,7 @@ struct pb200_ctx {
    void *d_scratch;       // growable scratch (permute etc.)
    size_t scratch_cap;
    int64_t launches;
+   int use_tma;           // 1: TMA-staged kernels where eligible (default), 0: LDG kernels only
    // optional per-kernel-kind CUDA-event timing (bench.py's roofline numbers)
    int prof_on;
    int prof_pending;
@@ -48,6 +49,7 @@ struct pb200_ctx {
    // NCCL (dlopen'ed lazily)
    void *comm;
    int nranks, rank;
+   int owns_comm;
 };
 
 // grow helpers (host side)
@@ -58,6 +60,8 @@ int pb_ensure_small(pb200_ctx *ctx, size_t doubles);
 // allreduce, copy to h_pinned and synchronize.  Result readable at ctx->h_pinned[0..cnt).
 int pb_finish_panel(pb200_ctx *ctx, int nparts, int cnt);
 int pb_nccl_allreduce_dev(pb200_ctx *ctx, double *dbuf, int count);
+int pb_nccl_allgatherv_cols(pb200_ctx *ctx, const double *X, int64_t ldx, double *Y, int64_t ldy,
+      const int64_t *counts, const int64_t *displs, int ncols);
 
 // kernel kinds for profiling
 enum { PB_K_SPMM = 0, PB_K_ORTHO = 1, PB_K_VWXR = 2, PB_K_UTIL = 3, PB_K_REDUCE = 4, PB_K_NKINDS = 5 };

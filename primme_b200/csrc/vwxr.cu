@@ -133,12 +133,9 @@ __global__ void __launch_bounds__(VT) vwxr_kernel(VwxrArgs a) {
 #pragma unroll
          for (int c = 0; c < NT; c++) {
             double res = y[c] - x[c] * th[c];
-            if (a.R.ptr && c >= a.R.cb && c < a.R.ce) {
-               a.R.ptr[r + (size_t)(c - a.R.cb) * a.R.ld] = res;
-               nrm[c] += res * res;
-            } else if (c >= a.rb && c < a.re) {
-               nrm[c] += res * res;
-            }
+            const bool inR = a.R.ptr && c >= a.R.cb && c < a.R.ce;
+            if (inR) a.R.ptr[r + (size_t)(c - a.R.cb) * a.R.ld] = res;
+            if (inR || (c >= a.rb && c < a.re)) nrm[c] += res * res;
          }
       }
       // ---- G / H ----
@@ -186,7 +183,9 @@ __global__ void __launch_bounds__(VT) vwxr_kernel(VwxrArgs a) {
    }
 
    // ---------------- epilogue: per-CTA partials ----------------
-   const int cnt = nR + nr + a.nG * a.nG + a.nH * a.nH;
+   // slots: squared norm of column c at out[c] for c < nn (nn = a.nh if any norm is wanted), G, H
+   const int nn = (nR + nr) > 0 ? a.nh : 0;
+   const int cnt = nn + a.nG * a.nG + a.nH * a.nH;
    double *out = a.partials + (size_t)blockIdx.x * cnt;
    // norms: block reduction through shared memory (reuse xs region is unsafe if nblk==0: use hs)
    __syncthreads();
@@ -204,13 +203,12 @@ __global__ void __launch_bounds__(VT) vwxr_kernel(VwxrArgs a) {
       if (tid == 0) {
          double s = 0.0;
          for (int w = 0; w < VT / 32; w++) s += red[w];
-         int slot = isR ? (c - a.R.cb) : nR + (c - a.rb);
-         out[slot] = s;
+         out[c] = s;
       }
       __syncthreads();
    }
    if (nblk > 0) {
-      double *Gout = out + nR + nr;
+      double *Gout = out + nn;
       double *Hout = Gout + a.nG * a.nG;
 #pragma unroll
       for (int t = 0; t < MAXBLK; t++) {
@@ -269,7 +267,8 @@ extern "C" int pb200_dvwxr(pb200_ctx *ctx, int64_t n, const double *V, const dou
    a.nH = o->H_host ? o->nH : 0;
    a.need_y = (a.Wo.ptr || a.R.ptr || a.re > a.rb || a.nH > 0) ? 1 : 0;
    const int nR = a.R.ptr ? a.R.ce - a.R.cb : 0, nr = a.re - a.rb;
-   const int cnt = nR + nr + a.nG * a.nG + a.nH * a.nH;
+   const int nn = (nR + nr) > 0 ? nh : 0;
+   const int cnt = nn + a.nG * a.nG + a.nH * a.nH;
    {
       int gb = (a.nG + 1) / 2, hb = (a.nH + 1) / 2;
       if (gb * gb + hb * hb > 4 * VT) return PB200_ERR_ARG;  // nG,nH <= 32 each
@@ -334,9 +333,9 @@ extern "C" int pb200_dvwxr(pb200_ctx *ctx, int64_t n, const double *V, const dou
       PB_CHK(pb_finish_panel(ctx, grid, cnt));
       const double *p = ctx->h_pinned;
       if (o->Rnorms_host)
-         for (int c = 0; c < nR; c++) o->Rnorms_host[c] = sqrt(p[c]);
-      for (int c = 0; c < nr; c++) o->rnorms_host[c] = sqrt(p[nR + c]);
-      const double *pg = p + nR + nr;
+         for (int c = 0; c < nR; c++) o->Rnorms_host[c] = sqrt(p[a.R.cb + c]);
+      for (int c = 0; c < nr; c++) o->rnorms_host[c] = sqrt(p[a.rb + c]);
+      const double *pg = p + nn;
       for (int j = 0; j < a.nG; j++)
          for (int i = 0; i < a.nG; i++) o->G_host[i + (size_t)j * o->ldG] = pg[i + (size_t)j * a.nG];
       const double *ph = pg + a.nG * a.nG;

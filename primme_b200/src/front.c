@@ -355,7 +355,9 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
    }
    if (primme->orth == primme_orth_default)
       primme->orth = primme->maxBlockSize > 1 ? primme_orth_explicit_I : primme_orth_implicit_I;
-   if (primme->ldOPs == -1) primme->ldOPs = primme->nLocal; /* min(roundup(nLocal,512), nLocal) */
+   /* free to choose (reference primme_c.c:325-332 takes nLocal): round up to 16 elements so every
+    * basis column starts on a 128-byte boundary (bulk-copy / vector-load alignment) */
+   if (primme->ldOPs == -1) primme->ldOPs = (primme->nLocal + 15) / 16 * 16;
    if (evals == NULL && evecs == NULL && resNorms == NULL) return 0;
 
    if (primme->iseed[0] < 0 || primme->iseed[0] > 4095) primme->iseed[0] = primme->procID % 4096;
@@ -457,7 +459,9 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
    }
 
    int ret = 0, numRet = 0;
+   const int blas_threads = hl_blas_threads(1);
    rc = pb_main_iter(S, evals, resNorms, &ret, &numRet);
+   if (blas_threads > 0) hl_blas_threads(blas_threads);
    if (rc == 0) {
       rc = ret;
       if (!device_mode && numRet > 0)

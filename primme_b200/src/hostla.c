@@ -145,3 +145,13 @@ double hl_wtime(void) {
    gettimeofday(&tv, NULL);
    return (double)tv.tv_sec + (double)tv.tv_usec / 1e6;
 }
+
+/* The projected problems are tiny (<= 64 x 64): a threaded BLAS spends far more time waking its
+ * pool than computing.  If the linked BLAS is OpenBLAS, run it single-threaded during a solve. */
+extern void openblas_set_num_threads(int) __attribute__((weak));
+extern int openblas_get_num_threads(void) __attribute__((weak));
+int hl_blas_threads(int nthreads) {
+   int prev = openblas_get_num_threads ? openblas_get_num_threads() : 0;
+   if (openblas_set_num_threads && nthreads > 0) openblas_set_num_threads(nthreads);
+   return prev;
+}

@@ -41,5 +41,7 @@ int hl_sygv_upper(int n, double *A, int lda, const double *B, int ldb, double *w
 void hl_larnv2(long long iseed[4], long long n, double *x);
 double hl_dot(int n, const double *x, const double *y);
 double hl_wtime(void);
+/* set the BLAS thread count (OpenBLAS only); returns the previous value or 0 */
+int hl_blas_threads(int nthreads);
 
 #endif

@@ -52,6 +52,14 @@ def off(p, nbytes):
 
 
 @pytest.mark.parametrize("n,q,mv,b,update,useY,xx", [
+    # even n with pad 4 => even leading dimension, 16-byte aligned columns: TMA-staged kernel
+    (3000 + 4j, 0, 28, 4, True, True, True),
+    (3000 + 4j, 0, 28, 4, False, False, True),
+    (5000 + 4j, 0, 40, 4, False, False, False),
+    (2500 + 2j, 4, 60, 8, True, True, True),
+    (6002 + 4j, 2, 30, 1, True, False, True),
+    (10000 + 0j, 0, 12, 2, True, True, True),
+    (70000 + 0j, 0, 36, 4, True, True, True),
     (1000, 0, 12, 4, False, False, True),
     (1000, 0, 12, 4, True, True, True),
     (4097, 3, 20, 4, True, True, True),
@@ -67,8 +75,11 @@ def off(p, nbytes):
     (0, 0, 4, 2, False, False, True),        # empty local part
 ])
 def test_ortho_sweep(libs, n, q, mv, b, update, useY, xx):
+    pad = 3
+    if isinstance(n, complex):  # n + pad*1j: explicit padding of the leading dimension
+        n, pad = int(n.real), int(n.imag)
     rng = np.random.default_rng(1234 + n + q + mv + b)
-    ld = n + 3
+    ld = n + pad
     Q = rng.standard_normal((max(q, 1), ld))
     V = rng.standard_normal((mv + b, ld))  # X = V(:, mv:mv+b)
     Cm = rng.standard_normal((b, q + mv + 2)) * 0.1  # ldc = q+mv+2

@@ -15,10 +15,11 @@ matvecs/s = stats.numMatvecs / elapsed, summed over ranks.
               /root/reference by oracle/Makefile) on the host cores, on a bounded sample
               (maxMatvecs) of the same workload
 
-Multi-GPU (--gpus N under torchrun): this round every rank runs an independent replica of the
-solve on its own GPU ("replicas only", weak scaling, no data-path collective) -- the row-sharded
-solve with NCCL panel all-reduce is exercised by tests/test_multi_rank.py and is not yet the
-bench path.
+Multi-GPU (--gpus N under torchrun, one rank per GPU): the SAME problem is row-sharded over the
+ranks (PRIMME's SPMD model): every rank owns n/N rows of A, V, W and the eigenvectors; panels are
+all-reduced on the device with NCCL and the SpMV halo is one grouped NCCL exchange per block
+(primme_b200_dist_csr_matvec).  Total work is fixed => "scaling": "strong".  --multi replicas runs
+N independent solves instead (weak).
 """
 import argparse
 import ctypes as C
@@ -49,6 +50,8 @@ def parse():
                     help="host threads of the reference arm (0: min(cores, 16); OpenBLAS on 100+ "
                          "threads is slower on these tall-skinny panels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
+                    help="N>1: row-sharded solve with NCCL (strong scaling) or independent replicas")
     return ap.parse_args()
 
 
@@ -176,12 +179,21 @@ def main():
     va = np.ascontiguousarray(csr[2], dtype=np.float64)
     k = WORKLOAD["numEvals"]
 
-    ctx = C.c_void_p()
-    assert lib.pb200_ctx_create(C.byref(ctx), local) == 0
-    A = C.c_void_p()
-    assert lib.pb200_csr_create(ctx, n, n, nnz, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, 0, 0, C.byref(A)) == 0
+    sharded = world > 1 and args.multi == "sharded"
+    D = None
+    nloc = n
+    if sharded:
+        import multi_gpu_worker as MG
+        MG.declare(lib)
+        ctx, A, D, counts, (lo, hi) = MG.setup_rank(lib, api, csr, rank, world, local)
+        nloc = hi - lo
+    else:
+        ctx = C.c_void_p()
+        assert lib.pb200_ctx_create(C.byref(ctx), local) == 0
+        A = C.c_void_p()
+        assert lib.pb200_csr_create(ctx, n, n, nnz, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, 0, 0, C.byref(A)) == 0
     devecs = C.c_void_p()
-    assert lib.pb200_malloc(ctx, 8 * n * k, C.byref(devecs)) == 0
+    assert lib.pb200_malloc(ctx, 8 * max(nloc, 1) * k, C.byref(devecs)) == 0
     evals, rn = np.zeros(k), np.zeros(k)
 
     def make_params():
@@ -192,8 +204,13 @@ def main():
 
     def resident_solve():
         p = make_params()
-        p.matrix = A
-        p.matrixMatvec = C.cast(lib.primme_b200_csr_matvec, C.c_void_p).value
+        if sharded:
+            p.numProcs, p.procID, p.nLocal, p.ldevecs = world, rank, nloc, max(nloc, 1)
+            p.matrix = D
+            p.matrixMatvec = C.cast(lib.primme_b200_dist_csr_matvec, C.c_void_p).value
+        else:
+            p.matrix = A
+            p.matrixMatvec = C.cast(lib.primme_b200_csr_matvec, C.c_void_p).value
         lib.primme_b200_attach_ctx(C.byref(p), ctx)
         rc = lib.cublas_dprimme(evals.ctypes.data, devecs, rn.ctypes.data, C.byref(p))
         lib.primme_b200_attach_ctx(C.byref(p), None)
@@ -236,9 +253,10 @@ def main():
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-            m = torch.tensor([mv], device="cuda", dtype=torch.float64)
-            dist.all_reduce(m, op=dist.ReduceOp.SUM)
-            mv = float(m.item())
+            if not sharded:  # replicas: every rank did its own matvecs
+                m = torch.tensor([mv], device="cuda", dtype=torch.float64)
+                dist.all_reduce(m, op=dist.ReduceOp.SUM)
+                mv = float(m.item())
         return ms, mv, lib.pb200_ctx_launches(ctx) - l0, p
 
     for _ in range(args.warmup):
@@ -249,11 +267,43 @@ def main():
     value = mv / (ms * 1e-3)
     stats = api.stats_dict(p)
 
-    e2e_solve()  # warm the pinned-path once
-    ms_e, mv_e, _, _ = timed(e2e_solve, max(1, min(args.steps, 3)))
+    if sharded:
+        # end to end at N > 1: upload this rank's CSR shard, solve, download its eigenvector rows
+        hl = torch.empty((k, max(nloc, 1)), dtype=torch.float64).pin_memory()
+        lo_nz, hi_nz = int(rp[lo]), int(rp[hi])
+        s_rp = torch.from_numpy(np.ascontiguousarray(rp[lo:hi + 1] - rp[lo])).pin_memory()
+        s_ci = torch.from_numpy(np.ascontiguousarray(ci[lo_nz:hi_nz])).pin_memory()
+        s_va = torch.from_numpy(np.ascontiguousarray(va[lo_nz:hi_nz])).pin_memory()
+        cnts = np.ascontiguousarray(counts, dtype=np.int64)
+
+        def e2e_sharded():
+            A2, D2 = C.c_void_p(), C.c_void_p()
+            assert lib.pb200_csr_create(ctx, nloc, n, hi_nz - lo_nz, s_rp.data_ptr(), s_ci.data_ptr(), s_va.data_ptr(),
+                                        0, 0, C.byref(A2)) == 0
+            assert lib.pb200_dist_csr_create(ctx, A2, cnts.ctypes.data, world, C.byref(D2)) == 0
+            p = make_params()
+            p.numProcs, p.procID, p.nLocal, p.ldevecs = world, rank, nloc, max(nloc, 1)
+            p.matrix = D2
+            p.matrixMatvec = C.cast(lib.primme_b200_dist_csr_matvec, C.c_void_p).value
+            lib.primme_b200_attach_ctx(C.byref(p), ctx)
+            rc = lib.cublas_dprimme(evals.ctypes.data, devecs, rn.ctypes.data, C.byref(p))
+            lib.primme_b200_attach_ctx(C.byref(p), None)
+            assert rc == 0, rc
+            assert lib.pb200_copy_d2h(ctx, devecs, nloc, hl.data_ptr(), nloc, nloc, k, 8) == 0
+            lib.pb200_dist_csr_destroy(ctx, D2)
+            lib.pb200_csr_destroy(ctx, A2)
+            return p
+
+        e2e_fn = e2e_sharded
+        h2d = (s_rp.numel() * 8 + s_ci.numel() * 4 + s_va.numel() * 8) * world
+        d2h = 8 * n * k + 16 * k
+    else:
+        e2e_fn = e2e_solve
+        h2d = rp.nbytes + ci.nbytes + va.nbytes
+        d2h = 8 * n * k + 16 * k
+    e2e_fn()  # warm the pinned-path once
+    ms_e, mv_e, _, _ = timed(e2e_fn, max(1, min(args.steps, 3)))
     e2e_value = mv_e / (ms_e * 1e-3)
-    h2d = rp.nbytes + ci.nbytes + va.nbytes
-    d2h = 8 * n * k + 16 * k
 
     # per-kernel roofline from one profiled solve (CUDA events on the kernels' stream)
     lib.pb200_ctx_set_profiling.restype = C.c_int
@@ -297,10 +347,11 @@ def main():
     if rank == 0:
         line = {"metric": "matvecs_per_s", "value": value, "unit": "matvecs/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args.side), "n": n, "nnz": nnz,
-                           "parallelism": "replicas only" if args.gpus > 1 else "single GPU",
+                           "parallelism": (f"row-sharded x{world}, NCCL panel all-reduce + NCCL halo exchange" if sharded
+                                           else "replicas only" if args.gpus > 1 else "single GPU"),
                            "l2": "working set per sweep (V,W 2x320 MB at n=1e6) exceeds the 126 MB L2; no flush",
                            "outer_iterations": stats["numOuterIterations"], "restarts": stats["numRestarts"],
                            "matvecs_per_solve": stats["numMatvecs"], "time_to_converge_s": ms / args.steps / 1e3,
@@ -313,6 +364,8 @@ def main():
         print(json.dumps(line))
 
     lib.pb200_free(ctx, devecs)
+    if D is not None:
+        lib.pb200_dist_csr_destroy(ctx, D)
     lib.pb200_csr_destroy(ctx, A)
     lib.pb200_ctx_destroy(ctx)
     if world > 1:

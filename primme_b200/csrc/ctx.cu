@@ -38,6 +38,7 @@ extern "C" int pb200_ctx_create(pb200_ctx **out, int device) {
    ctx->d_partials = NULL;
    ctx->nranks = 1;
    ctx->use_tma = getenv("PB200_NO_TMA") ? 0 : 1;
+   ctx->use_tma_vwxr = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_VWXR")) ? 0 : 1;
    *out = ctx;
    return 0;
 }

@@ -365,9 +365,14 @@ __global__ void __launch_bounds__(NCT + 32) ortho_sweep_tma_kernel(SweepArgs a, 
 }
 
 template <int BT, int CPW>
-int launch_sweep_tma(pb200_ctx *ctx, const SweepArgs &a, int grid, size_t shmem, int nstages) {
+int launch_sweep_tma(pb200_ctx *ctx, const SweepArgs &a, int &grid, size_t shmem, int nstages) {
    auto kern = ortho_sweep_tma_kernel<BT, CPW>;
    PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+   // persistent grid = resident CTAs only (a second wave would serialise half of the tiles)
+   int occ = 1;
+   PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NCT + 32, shmem));
+   if (occ < 1) occ = 1;
+   if (grid > occ * ctx->num_sms) grid = occ * ctx->num_sms;
    kern<<<grid, NCT + 32, shmem, ctx->stream>>>(a, nstages);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
@@ -375,7 +380,7 @@ int launch_sweep_tma(pb200_ctx *ctx, const SweepArgs &a, int grid, size_t shmem,
 }
 
 template <int BT>
-int dispatch_cpw_tma(pb200_ctx *ctx, const SweepArgs &a, int cpw, int grid, size_t shmem, int nst) {
+int dispatch_cpw_tma(pb200_ctx *ctx, const SweepArgs &a, int cpw, int &grid, size_t shmem, int nst) {
    switch (cpw) {
    case 1: return launch_sweep_tma<BT, 1>(ctx, a, grid, shmem, nst);
    case 2: return launch_sweep_tma<BT, 2>(ctx, a, grid, shmem, nst);

@@ -37,6 +37,7 @@ struct pb200_ctx {
    void *d_scratch;       // growable scratch (permute etc.)
    size_t scratch_cap;
    int64_t launches;
+   int use_tma_vwxr;      // same switch for the VWXR kernel alone
    int use_tma;           // 1: TMA-staged kernels where eligible (default), 0: LDG kernels only
    // optional per-kernel-kind CUDA-event timing (bench.py's roofline numbers)
    int prof_on;

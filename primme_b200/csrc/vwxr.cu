@@ -14,8 +14,10 @@
 // xrow/yrow in shared memory and accumulates 2x2 register blocks per thread across all tiles;
 // per-CTA partials are reduced in fixed order (pb_finish_panel).
 #include "pb200_internal.cuh"
+#include "tma_pipe.cuh"
 #include <math.h>
 #include <string.h>
+#include <vector>
 
 namespace {
 
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(VT) vwxr_kernel(VwxrArgs a) {
    for (int c = 0; c < NT; c++) nrm[c] = 0.0;
 
    // G/H accumulators: 2x2 blocks, block id = tid + VT*t
-   constexpr int MAXBLK = 4;  // up to 4 blocks of 2x2 per thread => covers 2*(nGb^2) <= 512 blocks
+   constexpr int MAXBLK = 6;  // 2x2 blocks per thread: nGb^2 + nHb^2 <= 768 (nG, nH <= 38)
    double gacc[MAXBLK][4];
 #pragma unroll
    for (int t = 0; t < MAXBLK; t++)
@@ -236,6 +238,241 @@ __global__ void __launch_bounds__(VT) vwxr_kernel(VwxrArgs a) {
    }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// v2: TMA-staged variant.  A producer warp streams TR-row tiles of V and W (2m column segments,
+// one bulk copy each) through a shared-memory ring; 256 consumer threads = TPR threads per row:
+// half of them form V*h, the other half W*h (each thread NTH of the nh columns), the products
+// are parked in shared memory for the residual (needs both) and for the G/H blocks.  Outputs are
+// written after the whole tile has been read, so in-place restart (V <- V*h) stays safe.
+template <int NTH, int TPR>
+__global__ void __launch_bounds__(256 + 32) vwxr_tma_kernel(VwxrArgs a, int nstages) {
+   constexpr int TR = 256 / TPR;        // rows per tile
+   constexpr int NSUB = TPR / 2;        // column groups per operand
+   constexpr int NT = NTH * NSUB;       // padded number of h columns
+   extern __shared__ __align__(128) unsigned char smraw[];
+   const int m = a.m;
+   double *stage0 = reinterpret_cast<double *>(smraw);       // nstages * 2m * TR
+   double *hs = stage0 + (size_t)nstages * 2 * m * TR;       // m * NT
+   double *th = hs + (size_t)m * NT;                         // NT
+   double *xs = th + NT;                                     // NT * TR
+   double *ys = xs + (size_t)NT * TR;                        // NT * TR
+   uint64_t *full = reinterpret_cast<uint64_t *>(ys + (size_t)NT * TR);
+   uint64_t *empty = full + nstages;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+   if (tid == 0) {
+      for (int s = 0; s < nstages; s++) {
+         pbtma::mbar_init(&full[s], 1);
+         pbtma::mbar_init(&empty[s], 8);
+      }
+      pbtma::fence_barrier_init();
+   }
+   for (int i = tid; i < m * NT; i += 288) {
+      int k = i / NT, c = i % NT;
+      hs[i] = c < a.nh ? a.hdev[k + (size_t)c * m] : 0.0;
+   }
+   for (int i = tid; i < NT; i += 288) th[i] = i < a.nh ? a.thetadev[i] : 0.0;
+   __syncthreads();
+
+   const int64_t ntiles = a.n / TR;
+   if (warp == 8) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+         if (lane == 0) {
+            pbtma::mbar_wait(&empty[s], ph ^ 1);
+            pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * m * TR * sizeof(double)));
+         }
+         __syncwarp();
+         double *dst = stage0 + (size_t)s * 2 * m * TR;
+         const int64_t r0 = tile * TR;
+         for (int c = lane; c < 2 * m; c += 32) {
+            const double *src = (c < m ? a.V + (size_t)c * a.ld : a.W + (size_t)(c - m) * a.ld) + r0;
+            pbtma::bulk_g2s(dst + (size_t)c * TR, src, TR * sizeof(double), &full[s]);
+         }
+         if (++s == nstages) s = 0, ph ^= 1;
+      }
+      return;
+   }
+
+   const int row = tid % TR, part = tid / TR;
+   const int op = part / NSUB, csub = part % NSUB;  // op 0: V*h, op 1: W*h
+   const int c0 = csub * NTH;
+   const int nR = a.R.ptr ? a.R.ce - a.R.cb : 0;
+   const int nr = a.re - a.rb;
+   double nrm[NTH];
+#pragma unroll
+   for (int c = 0; c < NTH; c++) nrm[c] = 0.0;
+   constexpr int MAXBLK = 3;  // 2x2 blocks per thread: nGb^2 + nHb^2 <= 768 (nG, nH <= 38)
+   double gacc[MAXBLK][4];
+#pragma unroll
+   for (int t = 0; t < MAXBLK; t++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) gacc[t][e] = 0.0;
+   const int nGb = (a.nG + 1) / 2, nHb = (a.nH + 1) / 2;
+   const int nblkG = nGb * nGb, nblk = nblkG + nHb * nHb;
+
+   int s = 0;
+   uint32_t ph = 0;
+   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      pbtma::mbar_wait(&full[s], ph);
+      const double *src = stage0 + (size_t)s * 2 * m * TR + (size_t)op * m * TR + row;
+      double acc[NTH];
+#pragma unroll
+      for (int c = 0; c < NTH; c++) acc[c] = 0.0;
+      int k = 0;
+      for (; k + 2 <= m; k += 2) {
+         const double v0 = src[(size_t)k * TR], v1 = src[(size_t)(k + 1) * TR];
+         const double *h0 = hs + (size_t)k * NT + c0;
+#pragma unroll
+         for (int c = 0; c < NTH; c++) acc[c] += v0 * h0[c] + v1 * h0[NT + c];
+      }
+      if (k < m) {
+         const double v0 = src[(size_t)k * TR];
+         const double *h0 = hs + (size_t)k * NT + c0;
+#pragma unroll
+         for (int c = 0; c < NTH; c++) acc[c] += v0 * h0[c];
+      }
+      __syncwarp();
+      if (lane == 0) pbtma::mbar_arrive(&empty[s]);  // stage consumed by this warp
+      if (++s == nstages) s = 0, ph ^= 1;
+
+      double *park = op == 0 ? xs : ys;
+#pragma unroll
+      for (int c = 0; c < NTH; c++) park[(size_t)(c0 + c) * TR + row] = acc[c];
+      pbtma::named_bar_sync(1, 256);
+
+      const int64_t r = tile * TR + row;
+      if (op == 0) {
+#pragma unroll
+         for (int t = 0; t < 3; t++) {
+            if (a.X[t].ptr) {
+#pragma unroll
+               for (int c = 0; c < NTH; c++) {
+                  const int cc = c0 + c;
+                  if (cc >= a.X[t].cb && cc < a.X[t].ce)
+                     a.X[t].ptr[r + (size_t)(cc - a.X[t].cb) * a.X[t].ld] = acc[c];
+               }
+            }
+         }
+      } else {
+#pragma unroll
+         for (int c = 0; c < NTH; c++) {
+            const int cc = c0 + c;
+            if (a.Wo.ptr && cc >= a.Wo.cb && cc < a.Wo.ce)
+               a.Wo.ptr[r + (size_t)(cc - a.Wo.cb) * a.Wo.ld] = acc[c];
+            const bool inR = a.R.ptr && cc >= a.R.cb && cc < a.R.ce;
+            const bool inr = cc >= a.rb && cc < a.re;
+            if (inR || inr) {
+               const double res = acc[c] - xs[(size_t)cc * TR + row] * th[cc];
+               if (inR) a.R.ptr[r + (size_t)(cc - a.R.cb) * a.R.ld] = res;
+               nrm[c] += res * res;
+            }
+         }
+      }
+      if (nblk > 0) {
+#pragma unroll
+         for (int t = 0; t < MAXBLK; t++) {
+            const int blk = tid + 256 * t;
+            if (blk < nblk) {
+               const double *L = xs, *Rr;
+               int bi, bj, nn;
+               if (blk < nblkG) {
+                  bi = blk % nGb, bj = blk / nGb, nn = a.nG, Rr = xs;
+               } else {
+                  const int bb = blk - nblkG;
+                  bi = bb % nHb, bj = bb / nHb, nn = a.nH, Rr = ys;
+               }
+               if (blk >= nblkG || bi <= bj) {
+                  const int i0 = 2 * bi, jj0 = 2 * bj;
+                  const int i1 = i0 + 1 < nn ? i0 + 1 : i0, jj1 = jj0 + 1 < nn ? jj0 + 1 : jj0;
+                  const double *li0 = L + (size_t)i0 * TR, *li1 = L + (size_t)i1 * TR;
+                  const double *rj0 = Rr + (size_t)jj0 * TR, *rj1 = Rr + (size_t)jj1 * TR;
+                  double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+#pragma unroll 4
+                  for (int rr = 0; rr < TR; rr++) {
+                     const double l0 = li0[rr], l1 = li1[rr], q0 = rj0[rr], q1 = rj1[rr];
+                     s00 += l0 * q0, s01 += l0 * q1, s10 += l1 * q0, s11 += l1 * q1;
+                  }
+                  gacc[t][0] += s00, gacc[t][1] += s01, gacc[t][2] += s10, gacc[t][3] += s11;
+               }
+            }
+         }
+      }
+      pbtma::named_bar_sync(1, 256);  // xs/ys are rewritten by the next tile
+   }
+
+   // ---------------- epilogue ----------------
+   const int nn = (nR + nr) > 0 ? a.nh : 0;
+   const int cnt = nn + a.nG * a.nG + a.nH * a.nH;
+   double *out = a.partials + (size_t)blockIdx.x * cnt;
+   if (nn > 0) {
+      // park the per-thread squared norms ([column][row], W*h threads only) and sum each column
+      // over the rows in a fixed order
+#pragma unroll
+      for (int c = 0; c < NTH; c++)
+         if (op == 1) ys[(size_t)(c0 + c) * TR + row] = nrm[c];
+      pbtma::named_bar_sync(1, 256);
+      if (tid < a.nh) {
+         const bool want = (a.R.ptr && tid >= a.R.cb && tid < a.R.ce) || (tid >= a.rb && tid < a.re);
+         double sum = 0.0;
+         if (want)
+            for (int rr = 0; rr < TR; rr++) sum += ys[(size_t)tid * TR + rr];
+         out[tid] = sum;
+      }
+   }
+   if (nblk > 0) {
+      double *Gout = out + nn;
+      double *Hout = Gout + a.nG * a.nG;
+#pragma unroll
+      for (int t = 0; t < MAXBLK; t++) {
+         const int blk = tid + 256 * t;
+         if (blk >= nblk) continue;
+         if (blk < nblkG) {
+            const int bi = blk % nGb, bj = blk / nGb;
+            if (bi > bj) continue;
+            for (int e = 0; e < 4; e++) {
+               const int i = 2 * bi + (e >> 1), j = 2 * bj + (e & 1);
+               if (i < a.nG && j < a.nG) {
+                  Gout[i + (size_t)j * a.nG] = gacc[t][e];
+                  if (bi != bj) Gout[j + (size_t)i * a.nG] = gacc[t][e];
+               }
+            }
+         } else {
+            const int bb = blk - nblkG;
+            const int bi = bb % nHb, bj = bb / nHb;
+            for (int e = 0; e < 4; e++) {
+               const int i = 2 * bi + (e >> 1), j = 2 * bj + (e & 1);
+               if (i < a.nH && j < a.nH) Hout[i + (size_t)j * a.nH] = gacc[t][e];
+            }
+         }
+      }
+   }
+}
+
+template <int NTH, int TPR>
+int launch_vwxr_tma(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem, int nstages) {
+   auto kern = vwxr_tma_kernel<NTH, TPR>;
+   PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+   kern<<<grid, 288, shmem, ctx->stream>>>(a, nstages);  // grid <= #SMs: one resident CTA per SM
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   return 0;
+}
+
+// shared memory of the v2 kernel for a (NTH, TPR) choice; returns stages (0 = does not fit)
+static int vwxr_tma_plan(int m, int nth, int tpr, size_t *shmem) {
+   const int TR = 256 / tpr, NT = nth * (tpr / 2);
+   const size_t fixed = ((size_t)m * NT + NT + 2 * (size_t)NT * TR) * sizeof(double) + 128;
+   const size_t stage = (size_t)2 * m * TR * sizeof(double);
+   if (fixed + 2 * stage > 227 * 1024) return 0;
+   int nst = (int)((227 * 1024 - fixed) / stage);
+   if (nst > 4) nst = 4;
+   *shmem = fixed + nst * stage;
+   return nst;
+}
+
 template <int NT>
 int launch_vwxr(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem) {
    auto kern = vwxr_kernel<NT>;
@@ -249,7 +486,8 @@ int launch_vwxr(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem) {
 
 }  // namespace
 
-extern "C" int pb200_dvwxr(pb200_ctx *ctx, int64_t n, const double *V, const double *W, int m,
+// single-launch path: nh <= 64 columns of h, Gram blocks up to 38 x 38
+static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W, int m,
       int64_t ld, const double *h_host, int ldh, int nh, const double *theta_host,
       const pb200_vwxr_out *o) {
    if (nh <= 0 || m < 0) return 0;
@@ -271,7 +509,7 @@ extern "C" int pb200_dvwxr(pb200_ctx *ctx, int64_t n, const double *V, const dou
    const int cnt = nn + a.nG * a.nG + a.nH * a.nH;
    {
       int gb = (a.nG + 1) / 2, hb = (a.nH + 1) / 2;
-      if (gb * gb + hb * hb > 4 * VT) return PB200_ERR_ARG;  // nG,nH <= 32 each
+      if (gb * gb + hb * hb > 768) return PB200_ERR_ARG;
    }
 
    // stage h (compacted to ld m) and theta
@@ -288,47 +526,113 @@ extern "C" int pb200_dvwxr(pb200_ctx *ctx, int64_t n, const double *V, const dou
    a.hdev = ctx->d_small;
    a.thetadev = ctx->d_small + (size_t)m * nh;
 
-   int grid = 1;
-   if (n > 0) {
-      const int64_t ntiles = (n + VT - 1) / VT;
-      int64_t g = (int64_t)ctx->num_sms * 4;
-      grid = (int)(ntiles < g ? ntiles : g);
-   }
-   if (cnt > 0) {
-      PB_CHK(pb_ensure_partials(ctx, (size_t)grid * cnt));
-      a.partials = ctx->d_partials;
-      // G partial slots below the diagonal blocks are written by mirroring; zero everything
-      PB_CUDA(cudaMemsetAsync(ctx->d_partials, 0, (size_t)grid * cnt * sizeof(double), ctx->stream));
-   } else {
-      PB_CHK(pb_ensure_partials(ctx, 16));
-      a.partials = ctx->d_partials;
-   }
-   const int NT = nh <= 4 ? 4 : nh <= 8 ? 8 : nh <= 16 ? 16 : nh <= 24 ? 24 : nh <= 32 ? 32
-                 : nh <= 40 ? 40 : nh <= 48 ? 48 : 64;
-   const int ngh = a.nG > a.nH ? a.nG : a.nH;
-   size_t shd = (size_t)m * NT + NT + (size_t)ngh * VT + (size_t)a.nH * VT;
-   if (shd < VT) shd = VT;
-   size_t shmem = shd * sizeof(double);
-   int rc;
    // algorithmic bytes: V (and W) read once + every output column written once
    double ocols = 0;
-   for (int t = 0; t < 3; t++) if (a.X[t].ptr) ocols += a.X[t].ce - a.X[t].cb;
+   for (int t = 0; t < 3; t++)
+      if (a.X[t].ptr) ocols += a.X[t].ce - a.X[t].cb;
    if (a.Wo.ptr) ocols += a.Wo.ce - a.Wo.cb;
    if (a.R.ptr) ocols += a.R.ce - a.R.cb;
    const double abytes = 8.0 * (double)n * ((a.need_y ? 2.0 : 1.0) * m + ocols);
+
+   // ---- v2 plan: (columns per thread, threads per row) ----
+   int nth = 0, tpr = 0, nst = 0;
+   size_t shm2 = 0;
+   {
+      const bool al = ctx->use_tma_vwxr && m > 0 && (((uintptr_t)V) & 15) == 0 && (((uintptr_t)W) & 15) == 0 && ld % 2 == 0;
+      int gb = (a.nG + 1) / 2, hb = (a.nH + 1) / 2;
+      if (al && gb * gb + hb * hb <= 768) {
+         const int c2[][2] = {{4, 2}, {8, 2}, {16, 2}, {24, 2}, {12, 4}, {16, 4}, {20, 4}, {24, 4}};
+         for (int i = 0; i < 8 && !nst; i++) {
+            const int cap = c2[i][0] * (c2[i][1] / 2);
+            if (nh > cap) continue;
+            size_t sh = 0;
+            int st = vwxr_tma_plan(m, c2[i][0], c2[i][1], &sh);
+            if (st >= 2 && n >= 4 * (256 / c2[i][1])) nth = c2[i][0], tpr = c2[i][1], nst = st, shm2 = sh;
+         }
+      }
+   }
+
+   int grid = 1, nparts = 1, rc = 0;
    int ps = pb_prof_begin(ctx, PB_K_VWXR);
-   switch (NT) {
-   case 4: rc = launch_vwxr<4>(ctx, a, grid, shmem); break;
-   case 8: rc = launch_vwxr<8>(ctx, a, grid, shmem); break;
-   case 16: rc = launch_vwxr<16>(ctx, a, grid, shmem); break;
-   case 24: rc = launch_vwxr<24>(ctx, a, grid, shmem); break;
-   case 32: rc = launch_vwxr<32>(ctx, a, grid, shmem); break;
-   case 40: rc = launch_vwxr<40>(ctx, a, grid, shmem); break;
-   case 48: rc = launch_vwxr<48>(ctx, a, grid, shmem); break;
-   default: rc = launch_vwxr<64>(ctx, a, grid, shmem); break;
+   if (nst >= 2) {
+      const int TR = 256 / tpr;
+      const int64_t ntiles = n / TR, n_main = ntiles * TR;
+      grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
+      const int tail = n_main < n ? 1 : 0;
+      PB_CHK(pb_ensure_partials(ctx, (size_t)(grid + tail) * (cnt > 0 ? cnt : 1) + 16));
+      a.partials = ctx->d_partials;
+      if (cnt > 0)
+         PB_CUDA(cudaMemsetAsync(ctx->d_partials, 0, (size_t)(grid + tail) * cnt * sizeof(double), ctx->stream));
+      VwxrArgs am = a;
+      am.n = n_main;
+#define VW2(NTH_, TPR_) \
+   if (nth == NTH_ && tpr == TPR_) rc = launch_vwxr_tma<NTH_, TPR_>(ctx, am, grid, shm2, nst);
+      VW2(4, 2) VW2(8, 2) VW2(16, 2) VW2(24, 2) VW2(12, 4) VW2(16, 4) VW2(20, 4) VW2(24, 4)
+#undef VW2
+      nparts = grid;
+      if (!rc && tail) {
+         // remaining rows through one CTA of the v1 kernel (pointers shifted by n_main rows)
+         VwxrArgs at = a;
+         at.n = n - n_main;
+         at.V = V + n_main, at.W = W + n_main;
+         for (int t = 0; t < 3; t++)
+            if (at.X[t].ptr) at.X[t].ptr += n_main;
+         if (at.Wo.ptr) at.Wo.ptr += n_main;
+         if (at.R.ptr) at.R.ptr += n_main;
+         at.partials = ctx->d_partials + (size_t)grid * cnt;
+         const int NT1 = nh <= 4 ? 4 : nh <= 8 ? 8 : nh <= 16 ? 16 : nh <= 24 ? 24 : nh <= 32 ? 32
+                        : nh <= 40 ? 40 : nh <= 48 ? 48 : 64;
+         const int ngh1 = a.nG > a.nH ? a.nG : a.nH;
+         size_t shd = (size_t)m * NT1 + NT1 + (size_t)ngh1 * VT + (size_t)a.nH * VT;
+         if (shd < VT) shd = VT;
+         switch (NT1) {
+         case 4: rc = launch_vwxr<4>(ctx, at, 1, shd * 8); break;
+         case 8: rc = launch_vwxr<8>(ctx, at, 1, shd * 8); break;
+         case 16: rc = launch_vwxr<16>(ctx, at, 1, shd * 8); break;
+         case 24: rc = launch_vwxr<24>(ctx, at, 1, shd * 8); break;
+         case 32: rc = launch_vwxr<32>(ctx, at, 1, shd * 8); break;
+         case 40: rc = launch_vwxr<40>(ctx, at, 1, shd * 8); break;
+         case 48: rc = launch_vwxr<48>(ctx, at, 1, shd * 8); break;
+         default: rc = launch_vwxr<64>(ctx, at, 1, shd * 8); break;
+         }
+         nparts = grid + 1;
+      }
+   } else {
+      if (n > 0) {
+         const int64_t ntiles = (n + VT - 1) / VT;
+         int64_t g = (int64_t)ctx->num_sms * 4;
+         grid = (int)(ntiles < g ? ntiles : g);
+      }
+      if (cnt > 0) {
+         PB_CHK(pb_ensure_partials(ctx, (size_t)grid * cnt));
+         a.partials = ctx->d_partials;
+         // G partial slots below the diagonal blocks are written by mirroring; zero everything
+         PB_CUDA(cudaMemsetAsync(ctx->d_partials, 0, (size_t)grid * cnt * sizeof(double), ctx->stream));
+      } else {
+         PB_CHK(pb_ensure_partials(ctx, 16));
+         a.partials = ctx->d_partials;
+      }
+      const int NT = nh <= 4 ? 4 : nh <= 8 ? 8 : nh <= 16 ? 16 : nh <= 24 ? 24 : nh <= 32 ? 32
+                    : nh <= 40 ? 40 : nh <= 48 ? 48 : 64;
+      const int ngh = a.nG > a.nH ? a.nG : a.nH;
+      size_t shd = (size_t)m * NT + NT + (size_t)ngh * VT + (size_t)a.nH * VT;
+      if (shd < VT) shd = VT;
+      size_t shmem = shd * sizeof(double);
+      switch (NT) {
+      case 4: rc = launch_vwxr<4>(ctx, a, grid, shmem); break;
+      case 8: rc = launch_vwxr<8>(ctx, a, grid, shmem); break;
+      case 16: rc = launch_vwxr<16>(ctx, a, grid, shmem); break;
+      case 24: rc = launch_vwxr<24>(ctx, a, grid, shmem); break;
+      case 32: rc = launch_vwxr<32>(ctx, a, grid, shmem); break;
+      case 40: rc = launch_vwxr<40>(ctx, a, grid, shmem); break;
+      case 48: rc = launch_vwxr<48>(ctx, a, grid, shmem); break;
+      default: rc = launch_vwxr<64>(ctx, a, grid, shmem); break;
+      }
+      nparts = grid;
    }
    pb_prof_end(ctx, ps, abytes);
    PB_CHK(rc);
+   grid = nparts;
    if (cnt > 0) {
       PB_CHK(pb_finish_panel(ctx, grid, cnt));
       const double *p = ctx->h_pinned;
@@ -343,4 +647,83 @@ extern "C" int pb200_dvwxr(pb200_ctx *ctx, int64_t n, const double *V, const dou
          for (int i = 0; i < a.nH; i++) o->H_host[i + (size_t)j * o->ldH] = ph[i + (size_t)j * a.nH];
    }
    return 0;
+}
+
+// General path for wide coefficient blocks (more than 64 columns of h, or Gram blocks larger
+// than the single-launch kernel holds; e.g. a restart that keeps an almost full basis):
+// the products P = V*h and Q = W*h go to scratch in chunks of 32 columns through the fast kernel,
+// then every output is derived from P and Q with the other fused kernels.  Rare and off the
+// steady-state path (it runs once per solve for the benchmark configurations).
+static int vwxr_general(pb200_ctx *ctx, int64_t n, const double *V, const double *W, int m,
+      int64_t ld, const double *h_host, int ldh, int nh, const double *theta_host,
+      const pb200_vwxr_out *o) {
+   const int64_t lds = (n + 15) / 16 * 16 > 0 ? (n + 15) / 16 * 16 : 16;
+   const bool need_y = (o->Wo.ptr && o->Wo.ce > o->Wo.cb) || (o->R.ptr && o->R.ce > o->R.cb) ||
+                       (o->rnorms_host && o->re > o->rb) || (o->H_host && o->nH > 0);
+   PB_CHK(pb_ensure_scratch(ctx, sizeof(double) * (size_t)lds * nh * (need_y ? 2 : 1)));
+   double *P = (double *)ctx->d_scratch, *Q = need_y ? P + (size_t)lds * nh : NULL;
+   for (int c0 = 0; c0 < nh; c0 += 32) {
+      const int nc = nh - c0 < 32 ? nh - c0 : 32;
+      pb200_vwxr_out oc;
+      memset(&oc, 0, sizeof(oc));
+      oc.X[0].ptr = P + (size_t)lds * c0, oc.X[0].ld = lds, oc.X[0].cb = 0, oc.X[0].ce = nc;
+      if (need_y) oc.Wo.ptr = Q + (size_t)lds * c0, oc.Wo.ld = lds, oc.Wo.cb = 0, oc.Wo.ce = nc;
+      PB_CHK(vwxr_fast(ctx, n, V, W, m, ld, h_host + (size_t)ldh * c0, ldh, nc,
+            theta_host ? theta_host + c0 : NULL, &oc));
+   }
+   // Gram blocks G = P(:,0:nG)' P(:,0:nG), H = P(:,0:nH)' Q(:,0:nH): panels of <= 8 columns
+   if (o->G_host && o->nG > 0)
+      for (int c0 = 0; c0 < o->nG; c0 += 8) {
+         const int nc = o->nG - c0 < 8 ? o->nG - c0 : 8;
+         PB_CHK(pb200_dortho_sweep(ctx, n, NULL, 0, 0, P, o->nG, lds, P + (size_t)lds * c0, nc, lds,
+               NULL, 0, NULL, 0, 0, o->G_host + (size_t)o->ldG * c0, o->ldG));
+      }
+   if (o->H_host && o->nH > 0)
+      for (int c0 = 0; c0 < o->nH; c0 += 8) {
+         const int nc = o->nH - c0 < 8 ? o->nH - c0 : 8;
+         PB_CHK(pb200_dortho_sweep(ctx, n, NULL, 0, 0, P, o->nH, lds, Q + (size_t)lds * c0, nc, lds,
+               NULL, 0, NULL, 0, 0, o->H_host + (size_t)o->ldH * c0, o->ldH));
+      }
+   // column-range outputs (may alias V / W: every product has been formed by now)
+   for (int t = 0; t < 3; t++)
+      if (o->X[t].ptr && o->X[t].ce > o->X[t].cb)
+         PB_CHK(pb200_copy_d2d(ctx, P + (size_t)lds * o->X[t].cb, lds, o->X[t].ptr, o->X[t].ld, n,
+               o->X[t].ce - o->X[t].cb, 8));
+   if (o->Wo.ptr && o->Wo.ce > o->Wo.cb)
+      PB_CHK(pb200_copy_d2d(ctx, Q + (size_t)lds * o->Wo.cb, lds, o->Wo.ptr, o->Wo.ld, n,
+            o->Wo.ce - o->Wo.cb, 8));
+   // residuals: Q_j <- Q_j - theta_j P_j in scratch, squared norms from the same pass
+   std::vector<double> n2(nh, -1.0);
+   auto residual_cols = [&](int cb, int ce) -> int {
+      for (int c0 = cb; c0 < ce; c0 += 8) {
+         int c1 = c0 + 8 < ce ? c0 + 8 : ce, lo = c0;
+         while (lo < c1 && n2[lo] >= 0.0) lo++;  // already done (overlapping ranges)
+         if (lo >= c1) continue;
+         PB_CHK(pb200_dresidual_inplace(ctx, n, theta_host + lo, P + (size_t)lds * lo, lds,
+               Q + (size_t)lds * lo, lds, c1 - lo, &n2[lo]));
+      }
+      return 0;
+   };
+   if (o->R.ptr && o->R.ce > o->R.cb) {
+      PB_CHK(residual_cols(o->R.cb, o->R.ce));
+      PB_CHK(pb200_copy_d2d(ctx, Q + (size_t)lds * o->R.cb, lds, o->R.ptr, o->R.ld, n, o->R.ce - o->R.cb, 8));
+      if (o->Rnorms_host)
+         for (int c = o->R.cb; c < o->R.ce; c++) o->Rnorms_host[c - o->R.cb] = sqrt(n2[c]);
+   }
+   if (o->rnorms_host && o->re > o->rb) {
+      PB_CHK(residual_cols(o->rb, o->re));
+      for (int c = o->rb; c < o->re; c++) o->rnorms_host[c - o->rb] = sqrt(n2[c]);
+   }
+   return 0;
+}
+
+extern "C" int pb200_dvwxr(pb200_ctx *ctx, int64_t n, const double *V, const double *W, int m,
+      int64_t ld, const double *h_host, int ldh, int nh, const double *theta_host,
+      const pb200_vwxr_out *o) {
+   if (nh <= 0 || m < 0) return 0;
+   const int nG = o->G_host ? o->nG : 0, nH = o->H_host ? o->nH : 0;
+   const int gb = (nG + 1) / 2, hb = (nH + 1) / 2;
+   if (nh <= 64 && gb * gb + hb * hb <= 768)
+      return vwxr_fast(ctx, n, V, W, m, ld, h_host, ldh, nh, theta_host, o);
+   return vwxr_general(ctx, n, V, W, m, ld, h_host, ldh, nh, theta_host, o);
 }

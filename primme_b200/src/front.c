@@ -19,6 +19,7 @@
 #include <string.h>
 
 void pb_report(primme_params *primme, const char *file, int line, int err, const char *what) {
+   if (getenv("PB200_DEBUG")) fprintf(stderr, "PRIMME-B200: error %d at %s:%d in '%s'\n", err, file, line, what);
    if (primme && primme->procID == 0 && primme->outputFile && primme->printLevel >= 1) {
       fprintf(primme->outputFile, "PRIMME-B200: error %d at %s:%d in '%s'\n", err, file, line, what);
       fflush(primme->outputFile);

@@ -113,12 +113,18 @@ def test_ortho_sweep(libs, n, q, mv, b, update, useY, xx):
     (5001, 40, 24, "restart"),  # in-place V,W <- V*h, W*h ; X,R block ; G,H
     (2000, 64, 36, "restart"),  # C5-like restart (restart size 32 + block 4)
     (1999, 16, 12, "lock"),     # restart + columns to evecs + extra norms
+    (3000, 40, 40, "restart"),  # restart keeping 36 vectors (basis not full): larger Gram blocks
+    (3000, 64, 60, "restart"),  # Gram blocks beyond the single-launch kernel: general path
+    (700, 150, 140, "lock"),    # more than 64 columns of h (reference test_001 keeps 140)
+    (6144, 28, 4, "cand"),      # aligned, full tiles only: TMA-staged kernel
+    (6144 + 70, 40, 24, "restart"),
+    (4096, 64, 36, "restart"),
     (257, 9, 3, "cand"),
     (0, 8, 2, "cand"),
 ])
 def test_vwxr(libs, n, m, nh, case):
     rng = np.random.default_rng(99 + n + m + nh)
-    ld = n + 5
+    ld = n + 5 if n % 2 else n + 16
     V = rng.standard_normal((m + 8, ld))
     W = rng.standard_normal((m + 8, ld))
     h = rng.standard_normal((nh, m + 1))  # ldh = m+1
@@ -132,9 +138,9 @@ def test_vwxr(libs, n, m, nh, case):
         o = api.VwxrOut()
         nR = 0
         Rn = np.zeros(16)
-        rn = np.zeros(64)
-        G = np.zeros((40, 33))
-        Hm = np.zeros((40, 35))
+        rn = np.zeros(200)
+        G = np.zeros((160, 161))
+        Hm = np.zeros((160, 163))
         if case == "cand":
             o.X[0] = api.VwxrCols(off(dV, 8 * ld * m).value, ld, 0, nh)
             o.R = api.VwxrCols(off(dW, 8 * ld * m).value, ld, 0, nh)
@@ -151,8 +157,8 @@ def test_vwxr(libs, n, m, nh, case):
             o.R = api.VwxrCols(off(dW, 8 * ld * rs).value, ld, nconv, nconv + 4)
             o.Rnorms_host = Rn.ctypes.data
             nR = 4
-            o.nG, o.G_host, o.ldG = rs, G.ctypes.data, 33
-            o.nH, o.H_host, o.ldH = rs, Hm.ctypes.data, 35
+            o.nG, o.G_host, o.ldG = rs, G.ctypes.data, 161
+            o.nH, o.H_host, o.ldH = rs, Hm.ctypes.data, 163
             if case == "lock":
                 o.X[2] = api.VwxrCols(dE.value, ld, rs - 3, rs)
                 o.rb, o.re, o.rnorms_host = rs - 3, rs, rn.ctypes.data

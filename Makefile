@@ -35,6 +35,18 @@ primme_b200/libprimme_b200.so: $(HOST_OBJ) $(CU_OBJ)
 
 oracle: oracle/_build/libprimme_hostcheck.so
 	$(MAKE) -C oracle all
+	$(MAKE) examples
+
+# The reference's own examples, compiled UNCHANGED from where they lie under $(REF) against our
+# headers and linked against the product library (only when the reference is mounted; the
+# binaries are git-ignored under oracle/_ref/ and travel to the GPU box).
+REF ?= /root/reference
+EXAMPLES := ex_eigs_dseq
+examples: $(if $(wildcard $(REF)/examples/ex_eigs_dseq.c),$(addprefix oracle/_ref/examples/,$(EXAMPLES)),)
+
+oracle/_ref/examples/%: $(REF)/examples/%.c primme_b200/libprimme_b200.so
+	@mkdir -p oracle/_ref/examples
+	$(CC) -O1 -Iinclude $< -o $@ -Lprimme_b200 -lprimme_b200 -Wl,--disable-new-dtags,-rpath,'$$ORIGIN/../../../primme_b200' -Wl,-rpath-link,$(OB) -lm
 
 # host control code linked against the CPU restatement of the kernels: TEST ONLY
 oracle/_build/libprimme_hostcheck.so: $(HOST_OBJ) oracle/kernels_ref.c
@@ -44,4 +56,4 @@ oracle/_build/libprimme_hostcheck.so: $(HOST_OBJ) oracle/kernels_ref.c
 clean:
 	rm -rf build primme_b200/libprimme_b200.so oracle/_build
 
-.PHONY: all lib oracle clean
+.PHONY: all lib oracle clean examples

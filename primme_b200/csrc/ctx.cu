@@ -31,12 +31,20 @@ extern "C" int pb200_ctx_create(pb200_ctx **out, int device) {
    ctx->num_sms = prop.multiProcessorCount;
    PB_CUDA(cudaStreamCreate(&ctx->stream));  // blocking: ordered with default-stream work of callbacks
    ctx->small_cap = 1 << 16; // 64 Ki doubles = 512 KB
-   PB_CUDA(cudaMallocHost((void **)&ctx->h_pinned, ctx->small_cap * sizeof(double)));
+   PB_CUDA(cudaHostAlloc((void **)&ctx->h_pinned, ctx->small_cap * sizeof(double), cudaHostAllocMapped));
+   PB_CUDA(cudaHostGetDevicePointer((void **)&ctx->d_hpinned, ctx->h_pinned, 0));
+   PB_CUDA(cudaHostAlloc((void **)&ctx->h_flag, 64, cudaHostAllocMapped));
+   PB_CUDA(cudaHostGetDevicePointer((void **)&ctx->d_hflag, (void *)ctx->h_flag, 0));
+   *ctx->h_flag = 0;
+   PB_CUDA(cudaMalloc((void **)&ctx->d_counter, sizeof(unsigned int)));
+   PB_CUDA(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)));
    PB_CUDA(cudaMalloc((void **)&ctx->d_small, ctx->small_cap * sizeof(double)));
    PB_CUDA(cudaMalloc((void **)&ctx->d_panel, ctx->small_cap * sizeof(double)));
    ctx->partials_cap = 0;
    ctx->d_partials = NULL;
    ctx->nranks = 1;
+   ctx->no_poll = getenv("PB200_NO_POLL") ? 1 : 0;
+   ctx->use_ws = getenv("PB200_NO_WS") ? 0 : 1;
    ctx->use_tma = getenv("PB200_NO_TMA") ? 0 : 1;
    ctx->use_tma_vwxr = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_VWXR")) ? 0 : 1;
    *out = ctx;
@@ -48,6 +56,8 @@ extern "C" int pb200_ctx_destroy(pb200_ctx *ctx) {
    cudaStreamSynchronize(ctx->stream);
    if (ctx->comm && ctx->owns_comm) pb200_ctx_comm_free(ctx);
    cudaFreeHost(ctx->h_pinned);
+   cudaFreeHost((void *)ctx->h_flag);
+   cudaFree(ctx->d_counter);
    cudaFree(ctx->d_small);
    cudaFree(ctx->d_panel);
    cudaFree(ctx->d_partials);
@@ -93,7 +103,8 @@ int pb_ensure_small(pb200_ctx *ctx, size_t doubles) {
    cudaFreeHost(ctx->h_pinned);
    cudaFree(ctx->d_small);
    cudaFree(ctx->d_panel);
-   PB_CUDA(cudaMallocHost((void **)&ctx->h_pinned, cap * sizeof(double)));
+   PB_CUDA(cudaHostAlloc((void **)&ctx->h_pinned, cap * sizeof(double), cudaHostAllocMapped));
+   PB_CUDA(cudaHostGetDevicePointer((void **)&ctx->d_hpinned, ctx->h_pinned, 0));
    PB_CUDA(cudaMalloc((void **)&ctx->d_small, cap * sizeof(double)));
    PB_CUDA(cudaMalloc((void **)&ctx->d_panel, cap * sizeof(double)));
    ctx->small_cap = cap;
@@ -152,7 +163,8 @@ extern "C" int pb200_ctx_get_profile(pb200_ctx *ctx, int kind, int64_t *count, d
 // partials array), warp w sums parts w, w+8, w+16, ... (4 independent chains), the 8 warp sums
 // are combined in warp order through shared memory.
 __global__ void __launch_bounds__(256) pb_reduce_partials_kernel(
-      const double *__restrict__ partials, int nparts, int cnt, double *__restrict__ out) {
+      const double *__restrict__ partials, int nparts, int cnt, double *__restrict__ out,
+      unsigned int *counter, long long *flag, long long seq) {
    __shared__ double red[8][33];
    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
    const int e = blockIdx.x * 32 + lane;
@@ -175,21 +187,59 @@ __global__ void __launch_bounds__(256) pb_reduce_partials_kernel(
       for (int w = 0; w < 8; w++) s += red[w][lane];
       out[e] = s;
    }
+   if (flag) {
+      // `out` is mapped host memory: publish a sequence number once every CTA's results are
+      // visible system-wide (last-block ticket), so the host can poll instead of synchronising
+      __syncthreads();
+      if (threadIdx.x == 0) {
+         __threadfence_system();
+         const unsigned int ticket = atomicAdd(counter, 1u);
+         if (ticket == gridDim.x - 1) {
+            *counter = 0;
+            __threadfence_system();
+            *(volatile long long *)flag = seq;
+         }
+      }
+   }
 }
 
 int pb_finish_panel(pb200_ctx *ctx, int nparts, int cnt) {
    if (cnt <= 0) return 0;
    PB_CHK(pb_ensure_small(ctx, (size_t)cnt));
    int ps = pb_prof_begin(ctx, PB_K_REDUCE);
+   if (ctx->nranks > 1 || ctx->no_poll) {
+      pb_reduce_partials_kernel<<<(cnt + 31) / 32, 256, 0, ctx->stream>>>(
+            ctx->d_partials, nparts, cnt, ctx->d_panel, NULL, NULL, 0);
+      pb_prof_end(ctx, ps, 8.0 * nparts * cnt);
+      ctx->launches++;
+      PB_CUDA(cudaGetLastError());
+      if (ctx->nranks > 1) PB_CHK(pb_nccl_allreduce_dev(ctx, ctx->d_panel, cnt));
+      PB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_panel, (size_t)cnt * sizeof(double),
+            cudaMemcpyDeviceToHost, ctx->stream));
+      PB_CUDA(cudaStreamSynchronize(ctx->stream));
+      return 0;
+   }
+   // single rank: the reduction writes straight into mapped pinned memory and raises a flag; the
+   // host polls the flag (a few microseconds less than memcpy + stream synchronisation, 10+
+   // times per outer iteration)
+   const long long seq = ++ctx->seq;
    pb_reduce_partials_kernel<<<(cnt + 31) / 32, 256, 0, ctx->stream>>>(
-         ctx->d_partials, nparts, cnt, ctx->d_panel);
+         ctx->d_partials, nparts, cnt, ctx->d_hpinned, ctx->d_counter, ctx->d_hflag, seq);
    pb_prof_end(ctx, ps, 8.0 * nparts * cnt);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
-   if (ctx->nranks > 1) PB_CHK(pb_nccl_allreduce_dev(ctx, ctx->d_panel, cnt));
-   PB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_panel, (size_t)cnt * sizeof(double),
-         cudaMemcpyDeviceToHost, ctx->stream));
-   PB_CUDA(cudaStreamSynchronize(ctx->stream));
+   unsigned long spins = 0;
+   while (*ctx->h_flag != seq) {
+      if ((++spins & 0xfffff) == 0) {
+         cudaError_t q = cudaStreamQuery(ctx->stream);
+         if (q == cudaSuccess) {
+            if (*ctx->h_flag == seq) break;
+         } else if (q != cudaErrorNotReady) {
+            fprintf(stderr, "primme_b200: CUDA error %s while waiting for a panel\n", cudaGetErrorString(q));
+            return PB200_ERR_CUDA;
+         }
+      }
+   }
    return 0;
 }
 

@@ -367,11 +367,18 @@ __global__ void __launch_bounds__(NCT + 32) ortho_sweep_tma_kernel(SweepArgs a, 
 template <int BT, int CPW>
 int launch_sweep_tma(pb200_ctx *ctx, const SweepArgs &a, int &grid, size_t shmem, int nstages) {
    auto kern = ortho_sweep_tma_kernel<BT, CPW>;
-   PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-   // persistent grid = resident CTAs only (a second wave would serialise half of the tiles)
-   int occ = 1;
-   PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NCT + 32, shmem));
-   if (occ < 1) occ = 1;
+   // persistent grid = resident CTAs only (a second wave would serialise half of the tiles);
+   // attribute + occupancy are queried once per (instantiation, shared-memory size)
+   static size_t cached_shmem = 0;
+   static int cached_occ = 0;
+   if (cached_shmem != shmem || cached_occ == 0) {
+      PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+      int o = 1;
+      PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, NCT + 32, shmem));
+      cached_occ = o < 1 ? 1 : o;
+      cached_shmem = shmem;
+   }
+   const int occ = cached_occ;
    if (grid > occ * ctx->num_sms) grid = occ * ctx->num_sms;
    kern<<<grid, NCT + 32, shmem, ctx->stream>>>(a, nstages);
    ctx->launches++;
@@ -398,11 +405,289 @@ int dispatch_cpw_tma(pb200_ctx *ctx, const SweepArgs &a, int cpw, int &grid, siz
    }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// v3: warp-specialised TMA pipeline.  Roles inside a CTA of 9 warps:
+//   warp 8      producer: one bulk copy per column segment into the stage ring (as v2)
+//   warps 0-1   update (only when C/Y are given): thread <-> two consecutive rows, 16-byte
+//               shared-memory loads, X <- (X - [Q V] C) Y, new rows to global and to a double-
+//               buffered shared tile
+//   others      Gram: warp <-> CPW basis columns, lane <-> row pairs, 16-byte loads
+// The roles are chained with mbarriers only (no CTA-wide barrier): the update of tile t+1
+// overlaps the Gram of tile t, and the bulk copies of tiles t+2.. are in flight meanwhile.
+template <int BT, int CPW>
+__global__ void __launch_bounds__(NCT + 32) ortho_sweep_ws_kernel(SweepArgs a, int nstages) {
+   extern __shared__ __align__(128) unsigned char smraw[];
+   const int k = a.q + a.mv;
+   const int kc = k + a.b;
+   double *stage0 = reinterpret_cast<double *>(smraw);
+   double *Cs = stage0 + (size_t)nstages * kc * TR;  // k * BT
+   double *Ys = Cs + (size_t)k * BT;                 // BT * BT
+   double *xs = Ys + BT * BT;                        // 2 * BT * TR
+   uint64_t *full = reinterpret_cast<uint64_t *>(xs + 2 * BT * TR);
+   uint64_t *empty = full + nstages;
+   uint64_t *xfull = empty + nstages;  // [2]
+   uint64_t *xempty = xfull + 2;       // [2]
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int nupd = a.do_update ? 2 : 0;                 // update warps
+   const int ngw = a.do_gram ? NCW - nupd : 0;           // Gram warps
+
+   if (tid == 0) {
+      for (int s = 0; s < nstages; s++) {
+         pbtma::mbar_init(&full[s], 1);
+         pbtma::mbar_init(&empty[s], nupd + ngw);
+      }
+      for (int i = 0; i < 2; i++) {
+         pbtma::mbar_init(&xfull[i], 2);
+         pbtma::mbar_init(&xempty[i], ngw > 0 ? ngw : 1);
+      }
+      pbtma::fence_barrier_init();
+   }
+   if (a.do_update) {
+      for (int i = tid; i < k * BT; i += NCT + 32) {
+         int j = i % k, c = i / k;
+         Cs[j * BT + c] = (c < a.b) ? a.Cdev[j + (size_t)c * k] : 0.0;
+      }
+      for (int i = tid; i < BT * BT; i += NCT + 32) {
+         int r = i % BT, c = i / BT;
+         double y = (r == c) ? 1.0 : 0.0;
+         if (a.has_Y) y = (r < a.b && c < a.b) ? a.Ydev[r + c * BT] : 0.0;
+         Ys[r * BT + c] = y;
+      }
+   }
+   __syncthreads();
+
+   const int64_t ntiles = a.n / TR;
+   if (warp == NCW) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+         if (lane == 0) {
+            pbtma::mbar_wait(&empty[s], ph ^ 1);
+            pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(kc * TR * sizeof(double)));
+         }
+         __syncwarp();
+         double *dst = stage0 + (size_t)s * kc * TR;
+         const int64_t r0 = tile * TR;
+         for (int c = lane; c < kc; c += 32) {
+            const double *src = c < k ? col_ptr(a, c) + r0 : a.X + (size_t)(c - k) * a.ldx + r0;
+            pbtma::bulk_g2s(dst + (size_t)c * TR, src, TR * sizeof(double), &full[s]);
+         }
+         if (++s == nstages) s = 0, ph ^= 1;
+      }
+      return;
+   }
+
+   if (warp < nupd) {
+      // ------------------------------ update warps ------------------------------
+      const int p2 = 2 * tid;  // first of this thread's two rows (tid < 64)
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+         const int buf = it & 1;
+         const uint32_t xph = (it >> 1) & 1;
+         pbtma::mbar_wait(&full[s], ph);
+         const double *st = stage0 + (size_t)s * kc * TR;
+         double t0[BT], t1[BT];
+#pragma unroll
+         for (int c = 0; c < BT; c++) t0[c] = 0.0, t1[c] = 0.0;
+#pragma unroll 4
+         for (int j = 0; j < k; j++) {
+            const double2 v = *reinterpret_cast<const double2 *>(st + (size_t)j * TR + p2);
+#pragma unroll
+            for (int c = 0; c < BT; c++) {
+               const double cj = Cs[j * BT + c];
+               t0[c] += v.x * cj;
+               t1[c] += v.y * cj;
+            }
+         }
+         double x0[BT], x1[BT];
+#pragma unroll
+         for (int c = 0; c < BT; c++) {
+            double2 xv = make_double2(0.0, 0.0);
+            if (c < a.b) xv = *reinterpret_cast<const double2 *>(st + (size_t)(k + c) * TR + p2);
+            x0[c] = xv.x - t0[c], x1[c] = xv.y - t1[c];
+         }
+         if (a.has_Y) {
+            double y0[BT], y1[BT];
+#pragma unroll
+            for (int c = 0; c < BT; c++) {
+               double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+               for (int cc = 0; cc < BT; cc++) {
+                  const double ycc = Ys[cc * BT + c];
+                  s0 += x0[cc] * ycc, s1 += x1[cc] * ycc;
+               }
+               y0[c] = s0, y1[c] = s1;
+            }
+#pragma unroll
+            for (int c = 0; c < BT; c++) x0[c] = y0[c], x1[c] = y1[c];
+         }
+         // the stage is no longer needed by this warp
+         __syncwarp();
+         if (lane == 0) pbtma::mbar_arrive(&empty[s]);
+         if (++s == nstages) s = 0, ph ^= 1;
+
+         const int64_t r = tile * TR + p2;
+#pragma unroll
+         for (int c = 0; c < BT; c++)
+            if (c < a.b) *reinterpret_cast<double2 *>(a.X + r + (size_t)c * a.ldx) = make_double2(x0[c], x1[c]);
+         if (ngw > 0) {
+            pbtma::mbar_wait(&xempty[buf], xph ^ 1);  // Gram warps are done with this buffer
+            double *xb = xs + (size_t)buf * BT * TR;
+#pragma unroll
+            for (int c = 0; c < BT; c++)
+               *reinterpret_cast<double2 *>(xb + (size_t)c * TR + p2) = make_double2(x0[c], x1[c]);
+            __syncwarp();
+            if (lane == 0) pbtma::mbar_arrive(&xfull[buf]);
+         }
+      }
+      return;
+   }
+
+   if (ngw == 0) {
+      return;  // update-only sweep: the remaining warps have nothing to do
+   }
+
+   // ------------------------------ Gram warps ------------------------------
+   const int gw = warp - nupd;
+   double acc[CPW][BT];
+   double accx[2][BT];
+#pragma unroll
+   for (int j = 0; j < CPW; j++)
+#pragma unroll
+      for (int c = 0; c < BT; c++) acc[j][c] = 0.0;
+#pragma unroll
+   for (int c = 0; c < BT; c++) accx[0][c] = 0.0, accx[1][c] = 0.0;
+   const int xr0 = gw, xr1 = gw + ngw;  // rows of the X'X block owned by this warp
+
+   {
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+         const int buf = it & 1;
+         const uint32_t xph = (it >> 1) & 1;
+         pbtma::mbar_wait(&full[s], ph);
+         const double *st = stage0 + (size_t)s * kc * TR;
+         const double *xsrc = st + (size_t)k * TR;
+         if (nupd) {
+            pbtma::mbar_wait(&xfull[buf], xph);
+            xsrc = xs + (size_t)buf * BT * TR;
+         }
+#pragma unroll
+         for (int i2 = 0; i2 < TR / 64; i2++) {
+            const int p2 = 2 * (i2 * 32 + lane);
+            double xv0[BT], xv1[BT];
+#pragma unroll
+            for (int c = 0; c < BT; c++) {
+               double2 xv = make_double2(0.0, 0.0);
+               if (c < a.b) xv = *reinterpret_cast<const double2 *>(xsrc + (size_t)c * TR + p2);
+               xv0[c] = xv.x, xv1[c] = xv.y;
+            }
+#pragma unroll
+            for (int j = 0; j < CPW; j++) {
+               const int jj = gw * CPW + j;
+               double2 av = make_double2(0.0, 0.0);
+               if (jj < k) av = *reinterpret_cast<const double2 *>(st + (size_t)jj * TR + p2);
+#pragma unroll
+               for (int c = 0; c < BT; c++) acc[j][c] += av.x * xv0[c] + av.y * xv1[c];
+            }
+            if (a.xx) {
+               if (xr0 < a.b) {
+                  const double2 xw = *reinterpret_cast<const double2 *>(xsrc + (size_t)xr0 * TR + p2);
+#pragma unroll
+                  for (int c = 0; c < BT; c++) accx[0][c] += xw.x * xv0[c] + xw.y * xv1[c];
+               }
+               if (xr1 < a.b) {
+                  const double2 xw = *reinterpret_cast<const double2 *>(xsrc + (size_t)xr1 * TR + p2);
+#pragma unroll
+                  for (int c = 0; c < BT; c++) accx[1][c] += xw.x * xv0[c] + xw.y * xv1[c];
+               }
+            }
+         }
+         __syncwarp();
+         if (lane == 0) {
+            if (nupd) pbtma::mbar_arrive(&xempty[buf]);
+            pbtma::mbar_arrive(&empty[s]);
+         }
+         if (++s == nstages) s = 0, ph ^= 1;
+      }
+   }
+
+   const int rows = k + (a.xx ? a.b : 0);
+   double *out = a.partials + (size_t)blockIdx.x * rows * a.b;
+#pragma unroll
+   for (int j = 0; j < CPW; j++) {
+#pragma unroll
+      for (int c = 0; c < BT; c++) {
+         double v = acc[j][c];
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+         const int jj = gw * CPW + j;
+         if (lane == 0 && jj < k && c < a.b) out[jj + (size_t)c * rows] = v;
+      }
+   }
+   if (a.xx) {
+#pragma unroll
+      for (int h2 = 0; h2 < 2; h2++) {
+         const int xr = h2 == 0 ? xr0 : xr1;
+#pragma unroll
+         for (int c = 0; c < BT; c++) {
+            double v = accx[h2][c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && xr < a.b && c < a.b) out[k + xr + (size_t)c * rows] = v;
+         }
+      }
+   }
+}
+
+template <int BT, int CPW>
+int launch_sweep_ws(pb200_ctx *ctx, const SweepArgs &a, int &grid, size_t shmem, int nstages) {
+   auto kern = ortho_sweep_ws_kernel<BT, CPW>;
+   static size_t cached_shmem = 0;
+   static int cached_occ = 0;
+   if (cached_shmem != shmem || cached_occ == 0) {
+      PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+      int o = 1;
+      PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, NCT + 32, shmem));
+      cached_occ = o < 1 ? 1 : o;
+      cached_shmem = shmem;
+   }
+   if (grid > cached_occ * ctx->num_sms) grid = cached_occ * ctx->num_sms;
+   kern<<<grid, NCT + 32, shmem, ctx->stream>>>(a, nstages);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   return 0;
+}
+
+template <int BT>
+int dispatch_cpw_ws(pb200_ctx *ctx, const SweepArgs &a, int cpw, int &grid, size_t shmem, int nst) {
+   switch (cpw) {
+   case 1: return launch_sweep_ws<BT, 1>(ctx, a, grid, shmem, nst);
+   case 2: return launch_sweep_ws<BT, 2>(ctx, a, grid, shmem, nst);
+   case 3: return launch_sweep_ws<BT, 3>(ctx, a, grid, shmem, nst);
+   case 4: return launch_sweep_ws<BT, 4>(ctx, a, grid, shmem, nst);
+   case 5: return launch_sweep_ws<BT, 5>(ctx, a, grid, shmem, nst);
+   case 6: return launch_sweep_ws<BT, 6>(ctx, a, grid, shmem, nst);
+   case 7:
+   case 8: return launch_sweep_ws<BT, 8>(ctx, a, grid, shmem, nst);
+   case 9:
+   case 10: return launch_sweep_ws<BT, 10>(ctx, a, grid, shmem, nst);
+   default: return PB200_ERR_ARG;
+   }
+}
+
 template <int BT, int CPW>
 int launch_sweep(pb200_ctx *ctx, const SweepArgs &a, int grid, size_t shmem) {
    auto kern = ortho_sweep_kernel<BT, CPW>;
-   if (shmem > 48 * 1024)
+   static size_t attr_shmem = 48 * 1024;
+   if (shmem > attr_shmem) {
       PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+      attr_shmem = shmem;
+   }
    kern<<<grid, TILE, shmem, ctx->stream>>>(a);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
@@ -446,6 +731,7 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
    a.has_Y = Y_host != NULL;
    a.do_gram = P_host != NULL;
    a.xx = xx ? 1 : 0;
+   if (!a.do_update && !a.do_gram) return 0;
 
    // stage C (k x b, compacted to ld k) and Y (b x b, ld BT) through the pinned buffer
    if (a.do_update) {
@@ -480,7 +766,7 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
    bool tma_ok = ctx->use_tma && n >= 4 * TR && kc <= 96 && aligned16(X) && (ldx % 2 == 0) &&
                  (q == 0 || (aligned16(Q) && ldq % 2 == 0)) && (mv == 0 || (aligned16(V) && ldv % 2 == 0));
    int nstages = 0, ctas_per_sm = 1;
-   size_t fixed_sm = ((size_t)k * BT + BT * BT + (size_t)BT * TR + 2 * (size_t)TR * BT) * sizeof(double) + 64;
+   size_t fixed_sm = ((size_t)k * BT + BT * BT + (size_t)BT * TR + 2 * (size_t)TR * BT) * sizeof(double) + 128;
    if (tma_ok) {
       const size_t stage_b = (size_t)kc * TR * sizeof(double);
       if (3 * stage_b + fixed_sm <= 110 * 1024) {
@@ -506,11 +792,24 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
       SweepArgs am = a;
       am.n = n_main;
       size_t shmem = (size_t)nstages * kc * TR * sizeof(double) + fixed_sm + 2 * nstages * sizeof(uint64_t);
-      switch (BT) {
-      case 1: rc = dispatch_cpw_tma<1>(ctx, am, cpw, grid, shmem, nstages); break;
-      case 2: rc = dispatch_cpw_tma<2>(ctx, am, cpw, grid, shmem, nstages); break;
-      case 4: rc = dispatch_cpw_tma<4>(ctx, am, cpw, grid, shmem, nstages); break;
-      default: rc = dispatch_cpw_tma<8>(ctx, am, cpw, grid, shmem, nstages); break;
+      // v3 (warp-specialised) when its column split fits the register budget
+      const int ngw = a.do_gram ? NCW - (a.do_update ? 2 : 0) : 0;
+      const int cpw_ws = ngw > 0 ? (k + ngw - 1) / ngw : 1;
+      if (ctx->use_ws && cpw_ws <= 10 && (ngw == 0 || 2 * ngw >= b)) {
+         const int cw = cpw_ws < 1 ? 1 : cpw_ws;
+         switch (BT) {
+         case 1: rc = dispatch_cpw_ws<1>(ctx, am, cw, grid, shmem, nstages); break;
+         case 2: rc = dispatch_cpw_ws<2>(ctx, am, cw, grid, shmem, nstages); break;
+         case 4: rc = dispatch_cpw_ws<4>(ctx, am, cw, grid, shmem, nstages); break;
+         default: rc = dispatch_cpw_ws<8>(ctx, am, cw, grid, shmem, nstages); break;
+         }
+      } else {
+         switch (BT) {
+         case 1: rc = dispatch_cpw_tma<1>(ctx, am, cpw, grid, shmem, nstages); break;
+         case 2: rc = dispatch_cpw_tma<2>(ctx, am, cpw, grid, shmem, nstages); break;
+         case 4: rc = dispatch_cpw_tma<4>(ctx, am, cpw, grid, shmem, nstages); break;
+         default: rc = dispatch_cpw_tma<8>(ctx, am, cpw, grid, shmem, nstages); break;
+         }
       }
       nparts = grid;
       if (!rc && tail) {

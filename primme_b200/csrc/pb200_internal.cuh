@@ -28,7 +28,13 @@ struct pb200_ctx {
    int num_sms;
    cudaStream_t stream;
    // staging for small operands and panels
-   double *h_pinned;      // pinned host buffer
+   double *h_pinned;      // pinned host buffer (mapped: kernels may write panels into it directly)
+   double *d_hpinned;     // device alias of h_pinned
+   volatile long long *h_flag;  // completion sequence number written by the last reducing CTA
+   long long *d_hflag;
+   unsigned int *d_counter;     // CTA ticket for the last-block pattern
+   long long seq;
+   int no_poll;           // 1: classic memcpy + stream synchronise for panels
    double *d_small;       // device buffer for coefficient blocks (h, C, Y, theta, perms)
    double *d_panel;       // device buffer for reduced panels
    double *d_partials;    // per-CTA partial panels
@@ -37,6 +43,7 @@ struct pb200_ctx {
    void *d_scratch;       // growable scratch (permute etc.)
    size_t scratch_cap;
    int64_t launches;
+   int use_ws;            // warp-specialised ortho sweep (v3) where eligible
    int use_tma_vwxr;      // same switch for the VWXR kernel alone
    int use_tma;           // 1: TMA-staged kernels where eligible (default), 0: LDG kernels only
    // optional per-kernel-kind CUDA-event timing (bench.py's roofline numbers)

@@ -451,10 +451,381 @@ __global__ void __launch_bounds__(256 + 32) vwxr_tma_kernel(VwxrArgs a, int nsta
    }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// v3 for narrow coefficient blocks (nh <= 8, no Gram outputs): the candidates sweep, executed
+// every outer iteration.  Producer warp as in v2; the 8 consumer warps form 4 groups of 2 warps
+// and group g owns the CTA's tiles g, g+4, ... : thread <-> two consecutive rows, BOTH products
+// (V*h and W*h) in registers, 16-byte shared-memory loads, residual and norms formed in-thread,
+// 16-byte global stores.  No exchange between threads until the final norm reduction.
+template <int NTH>
+__global__ void __launch_bounds__(256 + 32) vwxr_narrow_kernel(VwxrArgs a, int nstages) {
+   constexpr int TR = 128;
+   extern __shared__ __align__(128) unsigned char smraw[];
+   const int m = a.m;
+   double *stage0 = reinterpret_cast<double *>(smraw);   // nstages * 2m * TR
+   double *hs = stage0 + (size_t)nstages * 2 * m * TR;   // m * NTH
+   double *th = hs + (size_t)m * NTH;                    // NTH
+   double *red = th + NTH;                               // 8 * NTH
+   uint64_t *full = reinterpret_cast<uint64_t *>(red + 8 * NTH);
+   uint64_t *empty = full + nstages;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+   if (tid == 0) {
+      for (int s = 0; s < nstages; s++) {
+         pbtma::mbar_init(&full[s], 1);
+         pbtma::mbar_init(&empty[s], 2);
+      }
+      pbtma::fence_barrier_init();
+   }
+   for (int i = tid; i < m * NTH; i += 288) {
+      int k = i / NTH, c = i % NTH;
+      hs[i] = c < a.nh ? a.hdev[k + (size_t)c * m] : 0.0;
+   }
+   for (int i = tid; i < NTH; i += 288) th[i] = i < a.nh ? a.thetadev[i] : 0.0;
+   __syncthreads();
+
+   const int64_t ntiles = a.n / TR;
+   // CTA-local tile i <-> global tile blockIdx.x + i*gridDim.x, stage i % nstages
+   if (warp == 8) {
+      int64_t i = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, i++) {
+         const int s = (int)(i % nstages);
+         const uint32_t ph = (uint32_t)((i / nstages) & 1);
+         if (lane == 0) {
+            pbtma::mbar_wait(&empty[s], ph ^ 1);
+            pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * m * TR * sizeof(double)));
+         }
+         __syncwarp();
+         double *dst = stage0 + (size_t)s * 2 * m * TR;
+         const int64_t r0 = tile * TR;
+         for (int c = lane; c < 2 * m; c += 32) {
+            const double *src = (c < m ? a.V + (size_t)c * a.ld : a.W + (size_t)(c - m) * a.ld) + r0;
+            pbtma::bulk_g2s(dst + (size_t)c * TR, src, TR * sizeof(double), &full[s]);
+         }
+      }
+      return;
+   }
+
+   const int grp = warp >> 1;               // 0..3
+   const int p2 = 2 * (tid & 63);           // first of this thread's two rows within the tile
+   double nrm[NTH];
+#pragma unroll
+   for (int c = 0; c < NTH; c++) nrm[c] = 0.0;
+
+   int64_t i = grp;
+   for (int64_t tile = blockIdx.x + (int64_t)grp * gridDim.x; tile < ntiles; tile += 4 * (int64_t)gridDim.x, i += 4) {
+      const int s = (int)(i % nstages);
+      const uint32_t ph = (uint32_t)((i / nstages) & 1);
+      pbtma::mbar_wait(&full[s], ph);
+      const double *sv = stage0 + (size_t)s * 2 * m * TR + p2;
+      const double *sw = sv + (size_t)m * TR;
+      double x0[NTH], x1[NTH], y0[NTH], y1[NTH];
+#pragma unroll
+      for (int c = 0; c < NTH; c++) x0[c] = x1[c] = y0[c] = y1[c] = 0.0;
+#pragma unroll 2
+      for (int k = 0; k < m; k++) {
+         const double2 v = *reinterpret_cast<const double2 *>(sv + (size_t)k * TR);
+         const double2 w = *reinterpret_cast<const double2 *>(sw + (size_t)k * TR);
+         const double *hk = hs + (size_t)k * NTH;
+#pragma unroll
+         for (int c = 0; c < NTH; c++) {
+            const double hc = hk[c];
+            x0[c] += v.x * hc, x1[c] += v.y * hc;
+            y0[c] += w.x * hc, y1[c] += w.y * hc;
+         }
+      }
+      __syncwarp();
+      if (lane == 0) pbtma::mbar_arrive(&empty[s]);
+
+      const int64_t r = tile * TR + p2;
+#pragma unroll
+      for (int c = 0; c < NTH; c++) {
+#pragma unroll
+         for (int t = 0; t < 3; t++)
+            if (a.X[t].ptr && c >= a.X[t].cb && c < a.X[t].ce)
+               *reinterpret_cast<double2 *>(a.X[t].ptr + r + (size_t)(c - a.X[t].cb) * a.X[t].ld) = make_double2(x0[c], x1[c]);
+         if (a.Wo.ptr && c >= a.Wo.cb && c < a.Wo.ce)
+            *reinterpret_cast<double2 *>(a.Wo.ptr + r + (size_t)(c - a.Wo.cb) * a.Wo.ld) = make_double2(y0[c], y1[c]);
+         const bool inR = a.R.ptr && c >= a.R.cb && c < a.R.ce;
+         if (inR || (c >= a.rb && c < a.re)) {
+            const double r0 = y0[c] - x0[c] * th[c], r1 = y1[c] - x1[c] * th[c];
+            if (inR) *reinterpret_cast<double2 *>(a.R.ptr + r + (size_t)(c - a.R.cb) * a.R.ld) = make_double2(r0, r1);
+            nrm[c] += r0 * r0 + r1 * r1;
+         }
+      }
+   }
+
+   // norms: lanes -> warp -> CTA (fixed order)
+   const int nR = a.R.ptr ? a.R.ce - a.R.cb : 0;
+   const int nn = (nR + (a.re - a.rb)) > 0 ? a.nh : 0;
+   if (nn > 0) {
+#pragma unroll
+      for (int c = 0; c < NTH; c++) {
+         double v = nrm[c];
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+         if (lane == 0) red[warp * NTH + c] = v;
+      }
+      pbtma::named_bar_sync(1, 256);
+      if (tid < a.nh) {
+         double sum = 0.0;
+         for (int w = 0; w < 8; w++) sum += red[w * NTH + tid];
+         a.partials[(size_t)blockIdx.x * nn + tid] = sum;
+      }
+   }
+}
+
+template <int NTH>
+int launch_vwxr_narrow(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem, int nstages) {
+   auto kern = vwxr_narrow_kernel<NTH>;
+   static size_t attr_shmem = 0;
+   if (shmem > attr_shmem) {
+      PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+      attr_shmem = shmem;
+   }
+   kern<<<grid, 288, shmem, ctx->stream>>>(a, nstages);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// v3 for wide coefficient blocks (restart: V <- V*h, W <- W*h, next block, G = X'X, H = X'Y).
+// fp64-FLOP bound on B200 (5.3 flop/B), so the goal is to keep the DFMA pipe busy:
+//   * producer warp streams 64-row tiles of V and W (2m bulk copies) through a stage ring;
+//   * the 8 consumer warps form 8/NG groups of NG warps; a group owns every (8/NG)-th tile;
+//     inside a group warp cg owns NTH columns of h and lane <-> two consecutive rows, so a thread
+//     accumulates 2 rows x NTH columns x {V*h, W*h} from 16-byte shared loads with h broadcast,
+//     writes its outputs with 16-byte stores, keeps residual norms in registers and parks x/y
+//     for the Gram phase;
+//   * Gram phase per group: one 4x4 block of G (upper) or H per thread, row pairs visited in a
+//     lane-rotated order (conflict-free 16-byte loads), accumulators live across all tiles.
+template <int NTH, int NG>
+__global__ void __launch_bounds__(256 + 32) vwxr_wide_kernel(VwxrArgs a, int nstages, int park_cols) {
+   constexpr int TR = 64;
+   constexpr int NT = NTH * NG;
+   constexpr int NTG = 8 / NG;      // tile groups
+   constexpr int GS = 32 * NG;      // threads per group
+   extern __shared__ __align__(128) unsigned char smraw[];
+   const int m = a.m;
+   double *stage0 = reinterpret_cast<double *>(smraw);                 // nstages * 2m * TR
+   double *hs = stage0 + (size_t)nstages * 2 * m * TR;                 // m * NT
+   double *th = hs + (size_t)m * NT;                                   // NT
+   double *park0 = th + NT;                                            // NTG * 2 * park_cols * TR
+   uint64_t *full = reinterpret_cast<uint64_t *>(park0 + (size_t)NTG * 2 * park_cols * TR);
+   uint64_t *empty = full + nstages;
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+   if (tid == 0) {
+      for (int s = 0; s < nstages; s++) {
+         pbtma::mbar_init(&full[s], 1);
+         pbtma::mbar_init(&empty[s], NG);
+      }
+      pbtma::fence_barrier_init();
+   }
+   for (int i = tid; i < m * NT; i += 288) {
+      int k = i / NT, c = i % NT;
+      hs[i] = c < a.nh ? a.hdev[k + (size_t)c * m] : 0.0;
+   }
+   for (int i = tid; i < NT; i += 288) th[i] = i < a.nh ? a.thetadev[i] : 0.0;
+   __syncthreads();
+
+   const int64_t ntiles = a.n / TR;
+   if (warp == 8) {
+      int64_t i = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, i++) {
+         const int s = (int)(i % nstages);
+         const uint32_t ph = (uint32_t)((i / nstages) & 1);
+         if (lane == 0) {
+            pbtma::mbar_wait(&empty[s], ph ^ 1);
+            pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * m * TR * sizeof(double)));
+         }
+         __syncwarp();
+         double *dst = stage0 + (size_t)s * 2 * m * TR;
+         const int64_t r0 = tile * TR;
+         for (int c = lane; c < 2 * m; c += 32) {
+            const double *src = (c < m ? a.V + (size_t)c * a.ld : a.W + (size_t)(c - m) * a.ld) + r0;
+            pbtma::bulk_g2s(dst + (size_t)c * TR, src, TR * sizeof(double), &full[s]);
+         }
+      }
+      return;
+   }
+
+   const int grp = warp / NG, cg = warp % NG;  // tile group, column group
+   const int tg = cg * 32 + lane;              // thread index inside the group
+   const int p2 = 2 * lane;                    // first of this thread's two rows
+   const int c0 = cg * NTH;
+   double *xs = park0 + (size_t)grp * 2 * park_cols * TR;
+   double *ys = xs + (size_t)park_cols * TR;
+
+   double nrm[NTH];
+#pragma unroll
+   for (int c = 0; c < NTH; c++) nrm[c] = 0.0;
+
+   // Gram block of this thread: G upper blocks first, then all H blocks
+   const int nb4g = (a.nG + 3) / 4, nb4h = (a.nH + 3) / 4;
+   const int nblkG = nb4g * (nb4g + 1) / 2, nblk = nblkG + nb4h * nb4h;
+   int bi = 0, bj = 0, isH = 0;
+   const bool has_blk = tg < nblk;
+   if (has_blk) {
+      if (tg < nblkG) {
+         int t = tg;  // enumerate (bi <= bj) column by column
+         bj = 0;
+         while (t > bj) t -= bj + 1, bj++;
+         bi = t;
+      } else {
+         isH = 1;
+         bi = (tg - nblkG) % nb4h, bj = (tg - nblkG) / nb4h;
+      }
+   }
+   double gacc[4][4];
+#pragma unroll
+   for (int e = 0; e < 4; e++)
+#pragma unroll
+      for (int f = 0; f < 4; f++) gacc[e][f] = 0.0;
+
+   int64_t i = grp;
+   for (int64_t tile = blockIdx.x + (int64_t)grp * gridDim.x; tile < ntiles;
+         tile += (int64_t)NTG * gridDim.x, i += NTG) {
+      const int s = (int)(i % nstages);
+      const uint32_t ph = (uint32_t)((i / nstages) & 1);
+      pbtma::mbar_wait(&full[s], ph);
+      const double *sv = stage0 + (size_t)s * 2 * m * TR + p2;
+      const double *sw = sv + (size_t)m * TR;
+      double x0[NTH], x1[NTH], y0[NTH], y1[NTH];
+#pragma unroll
+      for (int c = 0; c < NTH; c++) x0[c] = x1[c] = y0[c] = y1[c] = 0.0;
+#pragma unroll 2
+      for (int k = 0; k < m; k++) {
+         const double2 v = *reinterpret_cast<const double2 *>(sv + (size_t)k * TR);
+         const double2 w = *reinterpret_cast<const double2 *>(sw + (size_t)k * TR);
+         const double *hk = hs + (size_t)k * NT + c0;
+#pragma unroll
+         for (int c = 0; c < NTH; c++) {
+            const double hc = hk[c];
+            x0[c] += v.x * hc, x1[c] += v.y * hc;
+            y0[c] += w.x * hc, y1[c] += w.y * hc;
+         }
+      }
+      __syncwarp();
+      if (lane == 0) pbtma::mbar_arrive(&empty[s]);
+
+      const int64_t r = tile * TR + p2;
+#pragma unroll
+      for (int c = 0; c < NTH; c++) {
+         const int cc = c0 + c;
+#pragma unroll
+         for (int t = 0; t < 3; t++)
+            if (a.X[t].ptr && cc >= a.X[t].cb && cc < a.X[t].ce)
+               *reinterpret_cast<double2 *>(a.X[t].ptr + r + (size_t)(cc - a.X[t].cb) * a.X[t].ld) =
+                     make_double2(x0[c], x1[c]);
+         if (a.Wo.ptr && cc >= a.Wo.cb && cc < a.Wo.ce)
+            *reinterpret_cast<double2 *>(a.Wo.ptr + r + (size_t)(cc - a.Wo.cb) * a.Wo.ld) =
+                  make_double2(y0[c], y1[c]);
+         const bool inR = a.R.ptr && cc >= a.R.cb && cc < a.R.ce;
+         if (inR || (cc >= a.rb && cc < a.re)) {
+            const double r0 = y0[c] - x0[c] * th[cc], r1 = y1[c] - x1[c] * th[cc];
+            if (inR)
+               *reinterpret_cast<double2 *>(a.R.ptr + r + (size_t)(cc - a.R.cb) * a.R.ld) = make_double2(r0, r1);
+            nrm[c] += r0 * r0 + r1 * r1;
+         }
+      }
+      if (nblk > 0) {
+#pragma unroll
+         for (int c = 0; c < NTH; c++) {
+            const int cc = c0 + c;
+            if (cc < park_cols) {
+               *reinterpret_cast<double2 *>(xs + (size_t)cc * TR + p2) = make_double2(x0[c], x1[c]);
+               *reinterpret_cast<double2 *>(ys + (size_t)cc * TR + p2) = make_double2(y0[c], y1[c]);
+            }
+         }
+         pbtma::named_bar_sync(1 + grp, GS);
+         if (has_blk) {
+            const double *L = xs + (size_t)(4 * bi) * TR;
+            const double *Rr = (isH ? ys : xs) + (size_t)(4 * bj) * TR;
+            // entries past the matrix edge are discarded in the epilogue: clamp their column
+            // index to a valid parked column so that only initialised data is read
+            const int nn = isH ? a.nH : a.nG;
+            int li[4], rj[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+               li[e] = (4 * bi + e < nn ? e : 0) * TR;
+               rj[e] = (4 * bj + e < nn ? e : 0) * TR;
+            }
+#pragma unroll 4
+            for (int it = 0; it < TR / 2; it++) {
+               const int q2 = 2 * ((it + lane) & (TR / 2 - 1));  // lane-rotated row pair
+               double2 l[4], rr[4];
+#pragma unroll
+               for (int e = 0; e < 4; e++) {
+                  l[e] = *reinterpret_cast<const double2 *>(L + li[e] + q2);
+                  rr[e] = *reinterpret_cast<const double2 *>(Rr + rj[e] + q2);
+               }
+#pragma unroll
+               for (int e = 0; e < 4; e++)
+#pragma unroll
+                  for (int f = 0; f < 4; f++) gacc[e][f] += l[e].x * rr[f].x + l[e].y * rr[f].y;
+            }
+         }
+         pbtma::named_bar_sync(1 + grp, GS);  // the parked tile is rewritten by the group's next tile
+      }
+   }
+
+   // ---------------- epilogue: one partial slot per (CTA, tile group) ----------------
+   const int nR = a.R.ptr ? a.R.ce - a.R.cb : 0;
+   const int nn = (nR + (a.re - a.rb)) > 0 ? a.nh : 0;
+   const int cnt = nn + a.nG * a.nG + a.nH * a.nH;
+   double *out = a.partials + ((size_t)blockIdx.x * NTG + grp) * cnt;
+   if (nn > 0) {
+#pragma unroll
+      for (int c = 0; c < NTH; c++) {
+         double v = nrm[c];
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+         if (lane == 0 && c0 + c < a.nh) out[c0 + c] = v;
+      }
+   }
+   if (has_blk) {
+      double *Gout = out + nn, *Hout = Gout + a.nG * a.nG;
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+#pragma unroll
+         for (int f = 0; f < 4; f++) {
+            const int ii = 4 * bi + e, jj = 4 * bj + f;
+            if (isH) {
+               if (ii < a.nH && jj < a.nH) Hout[ii + (size_t)jj * a.nH] = gacc[e][f];
+            } else if (ii < a.nG && jj < a.nG) {
+               Gout[ii + (size_t)jj * a.nG] = gacc[e][f];
+               if (bi != bj) Gout[jj + (size_t)ii * a.nG] = gacc[e][f];
+            }
+         }
+   }
+}
+
+template <int NTH, int NG>
+int launch_vwxr_wide(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem, int nstages, int park_cols) {
+   auto kern = vwxr_wide_kernel<NTH, NG>;
+   static size_t attr_shmem = 0;
+   if (shmem > attr_shmem) {
+      PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+      attr_shmem = shmem;
+   }
+   kern<<<grid, 288, shmem, ctx->stream>>>(a, nstages, park_cols);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   return 0;
+}
+
 template <int NTH, int TPR>
 int launch_vwxr_tma(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem, int nstages) {
    auto kern = vwxr_tma_kernel<NTH, TPR>;
-   PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+   static size_t attr_shmem = 0;
+   if (shmem > attr_shmem) {
+      PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+      attr_shmem = shmem;
+   }
    kern<<<grid, 288, shmem, ctx->stream>>>(a, nstages);  // grid <= #SMs: one resident CTA per SM
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
@@ -476,8 +847,11 @@ static int vwxr_tma_plan(int m, int nth, int tpr, size_t *shmem) {
 template <int NT>
 int launch_vwxr(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem) {
    auto kern = vwxr_kernel<NT>;
-   if (shmem > 48 * 1024)
+   static size_t attr_shmem = 48 * 1024;
+   if (shmem > attr_shmem) {
       PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+      attr_shmem = shmem;
+   }
    kern<<<grid, VT, shmem, ctx->stream>>>(a);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
@@ -552,9 +926,124 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
       }
    }
 
+   // ---- v3 (narrow) plan: candidates sweep ----
+   int narrow_nst = 0;
+   size_t narrow_shm = 0;
+   if (ctx->use_tma_vwxr && ctx->use_ws && nh <= 8 && a.nG == 0 && a.nH == 0 && m > 0 && n >= 4 * 128 &&
+         (((uintptr_t)V) & 15) == 0 && (((uintptr_t)W) & 15) == 0 && ld % 2 == 0) {
+      bool ok = true;
+      auto al = [](const pb200_cols &c) { return !c.ptr || ((((uintptr_t)c.ptr) & 15) == 0 && c.ld % 2 == 0); };
+      for (int t = 0; t < 3; t++) ok = ok && al(a.X[t]);
+      ok = ok && al(a.Wo) && al(a.R);
+      const int NTHn = nh <= 4 ? 4 : 8;
+      const size_t fixed = ((size_t)m * NTHn + NTHn + 8 * NTHn) * sizeof(double) + 128;
+      const size_t stage = (size_t)2 * m * 128 * sizeof(double);
+      int st = (int)((227 * 1024 - fixed) / stage);
+      if (st > 4) st = 4;
+      if (ok && st >= 2) narrow_nst = st, narrow_shm = fixed + st * stage;
+   }
+
+   // ---- v3 (wide) plan: restart sweep ----
+   int wide_nst = 0, wide_nth = 0, wide_ng = 0, wide_park = 0;
+   size_t wide_shm = 0;
+   if (ctx->use_tma_vwxr && ctx->use_ws && narrow_nst < 2 && nh <= 48 && m > 0 && n >= 4 * 64 &&
+         (((uintptr_t)V) & 15) == 0 && (((uintptr_t)W) & 15) == 0 && ld % 2 == 0) {
+      bool ok = true;
+      auto al = [](const pb200_cols &c) { return !c.ptr || ((((uintptr_t)c.ptr) & 15) == 0 && c.ld % 2 == 0); };
+      for (int t = 0; t < 3; t++) ok = ok && al(a.X[t]);
+      ok = ok && al(a.Wo) && al(a.R);
+      const int cfg[][2] = {{8, 1}, {8, 2}, {12, 2}, {8, 4}, {12, 4}};
+      const int park = a.nG > a.nH ? a.nG : a.nH;
+      const int nb4g = (a.nG + 3) / 4, nb4h = (a.nH + 3) / 4;
+      const int nblk = nb4g * (nb4g + 1) / 2 + nb4h * nb4h;
+      for (int i = 0; i < 5 && ok && !wide_nst; i++) {
+         const int nth = cfg[i][0], ng = cfg[i][1];
+         if (nh > nth * ng || nblk > 32 * ng || park > nth * ng) continue;
+         const size_t fixed = ((size_t)m * nth * ng + nth * ng + (size_t)(8 / ng) * 2 * park * 64) * sizeof(double) + 128;
+         const size_t stage = (size_t)2 * m * 64 * sizeof(double);
+         if (fixed + 2 * stage > 227 * 1024) continue;
+         int st = (int)((227 * 1024 - fixed) / stage);
+         if (st > 4) st = 4;
+         wide_nst = st, wide_nth = nth, wide_ng = ng, wide_park = park, wide_shm = fixed + st * stage;
+      }
+   }
+
    int grid = 1, nparts = 1, rc = 0;
    int ps = pb_prof_begin(ctx, PB_K_VWXR);
-   if (nst >= 2) {
+   if (narrow_nst >= 2) {
+      const int TR = 128;
+      const int64_t ntiles = n / TR, n_main = ntiles * TR;
+      grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
+      const int tail = n_main < n ? 1 : 0;
+      PB_CHK(pb_ensure_partials(ctx, (size_t)(grid + tail) * (cnt > 0 ? cnt : 1) + 16));
+      a.partials = ctx->d_partials;
+      if (cnt > 0)
+         PB_CUDA(cudaMemsetAsync(ctx->d_partials, 0, (size_t)(grid + tail) * cnt * sizeof(double), ctx->stream));
+      VwxrArgs am = a;
+      am.n = n_main;
+      if (nh <= 4) rc = launch_vwxr_narrow<4>(ctx, am, grid, narrow_shm, narrow_nst);
+      else rc = launch_vwxr_narrow<8>(ctx, am, grid, narrow_shm, narrow_nst);
+      nparts = grid;
+      if (!rc && tail) {
+         VwxrArgs at = a;
+         at.n = n - n_main;
+         at.V = V + n_main, at.W = W + n_main;
+         for (int t = 0; t < 3; t++)
+            if (at.X[t].ptr) at.X[t].ptr += n_main;
+         if (at.Wo.ptr) at.Wo.ptr += n_main;
+         if (at.R.ptr) at.R.ptr += n_main;
+         at.partials = ctx->d_partials + (size_t)grid * cnt;
+         const int NT1 = nh <= 4 ? 4 : 8;
+         size_t shd = (size_t)m * NT1 + NT1;
+         if (shd < VT) shd = VT;
+         if (NT1 == 4) rc = launch_vwxr<4>(ctx, at, 1, shd * 8);
+         else rc = launch_vwxr<8>(ctx, at, 1, shd * 8);
+         nparts = grid + 1;
+      }
+   } else if (wide_nst >= 2) {
+      const int TR = 64;
+      const int NTG = 8 / wide_ng;
+      const int64_t ntiles = n / TR, n_main = ntiles * TR;
+      grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
+      const int tail = n_main < n ? 1 : 0;
+      PB_CHK(pb_ensure_partials(ctx, (size_t)(grid * NTG + tail) * (cnt > 0 ? cnt : 1) + 16));
+      a.partials = ctx->d_partials;
+      if (cnt > 0)
+         PB_CUDA(cudaMemsetAsync(ctx->d_partials, 0, (size_t)(grid * NTG + tail) * cnt * sizeof(double), ctx->stream));
+      VwxrArgs am = a;
+      am.n = n_main;
+#define VW3(NTH_, NG_) \
+   if (wide_nth == NTH_ && wide_ng == NG_) rc = launch_vwxr_wide<NTH_, NG_>(ctx, am, grid, wide_shm, wide_nst, wide_park);
+      VW3(8, 1) VW3(8, 2) VW3(12, 2) VW3(8, 4) VW3(12, 4)
+#undef VW3
+      nparts = grid * NTG;
+      if (!rc && tail) {
+         VwxrArgs at = a;
+         at.n = n - n_main;
+         at.V = V + n_main, at.W = W + n_main;
+         for (int t = 0; t < 3; t++)
+            if (at.X[t].ptr) at.X[t].ptr += n_main;
+         if (at.Wo.ptr) at.Wo.ptr += n_main;
+         if (at.R.ptr) at.R.ptr += n_main;
+         at.partials = ctx->d_partials + (size_t)nparts * cnt;
+         const int NT1 = nh <= 4 ? 4 : nh <= 8 ? 8 : nh <= 16 ? 16 : nh <= 24 ? 24 : nh <= 32 ? 32
+                        : nh <= 40 ? 40 : nh <= 48 ? 48 : 64;
+         const int ngh1 = a.nG > a.nH ? a.nG : a.nH;
+         size_t shd = (size_t)m * NT1 + NT1 + (size_t)ngh1 * VT + (size_t)a.nH * VT;
+         if (shd < VT) shd = VT;
+         switch (NT1) {
+         case 4: rc = launch_vwxr<4>(ctx, at, 1, shd * 8); break;
+         case 8: rc = launch_vwxr<8>(ctx, at, 1, shd * 8); break;
+         case 16: rc = launch_vwxr<16>(ctx, at, 1, shd * 8); break;
+         case 24: rc = launch_vwxr<24>(ctx, at, 1, shd * 8); break;
+         case 32: rc = launch_vwxr<32>(ctx, at, 1, shd * 8); break;
+         case 40: rc = launch_vwxr<40>(ctx, at, 1, shd * 8); break;
+         case 48: rc = launch_vwxr<48>(ctx, at, 1, shd * 8); break;
+         default: rc = launch_vwxr<64>(ctx, at, 1, shd * 8); break;
+         }
+         nparts += 1;
+      }
+   } else if (nst >= 2) {
       const int TR = 256 / tpr;
       const int64_t ntiles = n / TR, n_main = ntiles * TR;
       grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);

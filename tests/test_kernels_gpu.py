@@ -117,6 +117,9 @@ def test_ortho_sweep(libs, n, q, mv, b, update, useY, xx):
     (3000, 64, 60, "restart"),  # Gram blocks beyond the single-launch kernel: general path
     (700, 150, 140, "lock"),    # more than 64 columns of h (reference test_001 keeps 140)
     (6144, 28, 4, "cand"),      # aligned, full tiles only: TMA-staged kernel
+    (8192 + 34, 36, 4, "norms"),
+    (5120 + 2, 56, 8, "cand"),
+    (66000, 16, 3, "cand"),
     (6144 + 70, 40, 24, "restart"),
     (4096, 64, 36, "restart"),
     (257, 9, 3, "cand"),

@@ -3,6 +3,7 @@
 // cuBLAS back end (reference src/linalg/cublas_wrapper.c:187-232,335-392): one pinned staging
 // buffer, one device coefficient buffer and one partials buffer live for the whole solve.
 #include "pb200_internal.cuh"
+#include <time.h>
 #include <dlfcn.h>
 #include <stdlib.h>
 #include <string.h>
@@ -47,6 +48,7 @@ extern "C" int pb200_ctx_create(pb200_ctx **out, int device) {
    ctx->use_ws = getenv("PB200_NO_WS") ? 0 : 1;
    ctx->use_tma = getenv("PB200_NO_TMA") ? 0 : 1;
    ctx->use_tma_vwxr = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_VWXR")) ? 0 : 1;
+   ctx->use_tma_spmm = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_SPMM")) ? 0 : 1;
    *out = ctx;
    return 0;
 }
@@ -229,11 +231,21 @@ int pb_finish_panel(pb200_ctx *ctx, int nparts, int cnt) {
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
    unsigned long spins = 0;
+   time_t t0 = 0;
    while (*ctx->h_flag != seq) {
       if ((++spins & 0xfffff) == 0) {
+         // watchdog: a panel never takes seconds; give up instead of spinning for ever
+         const time_t now = time(NULL);
+         if (!t0) t0 = now;
+         if (now - t0 > 120) {
+            fprintf(stderr, "primme_b200: timed out waiting for a panel (kernel hung?)\n");
+            return PB200_ERR_CUDA;
+         }
          cudaError_t q = cudaStreamQuery(ctx->stream);
          if (q == cudaSuccess) {
             if (*ctx->h_flag == seq) break;
+            fprintf(stderr, "primme_b200: panel reduction finished without raising its flag\n");
+            return PB200_ERR_CUDA;
          } else if (q != cudaErrorNotReady) {
             fprintf(stderr, "primme_b200: CUDA error %s while waiting for a panel\n", cudaGetErrorString(q));
             return PB200_ERR_CUDA;

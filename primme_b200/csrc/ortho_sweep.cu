@@ -457,22 +457,35 @@ __global__ void __launch_bounds__(NCT + 32) ortho_sweep_ws_kernel(SweepArgs a, i
    }
    __syncthreads();
 
-   const int64_t ntiles = a.n / TR;
+   const int64_t ntiles = (a.n + TR - 1) / TR;  // the last tile may be partial
    if (warp == NCW) {
       int s = 0;
       uint32_t ph = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-         if (lane == 0) {
-            pbtma::mbar_wait(&empty[s], ph ^ 1);
-            pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(kc * TR * sizeof(double)));
-         }
+         if (lane == 0) pbtma::mbar_wait(&empty[s], ph ^ 1);
          __syncwarp();
          double *dst = stage0 + (size_t)s * kc * TR;
          const int64_t r0 = tile * TR;
-         for (int c = lane; c < kc; c += 32) {
-            const double *src = c < k ? col_ptr(a, c) + r0 : a.X + (size_t)(c - k) * a.ldx + r0;
-            pbtma::bulk_g2s(dst + (size_t)c * TR, src, TR * sizeof(double), &full[s]);
+         const int rows = (int)((a.n - r0) < TR ? (a.n - r0) : TR);
+         const int rows_even = rows & ~1;
+         if (rows < TR) {
+            // partial tile: bulk copies take the even part, the odd last row and the zero
+            // padding are written with plain stores (padded rows then contribute nothing)
+            for (int c = lane; c < kc; c += 32) {
+               const double *src = c < k ? col_ptr(a, c) + r0 : a.X + (size_t)(c - k) * a.ldx + r0;
+               double *d = dst + (size_t)c * TR;
+               for (int rr = rows_even; rr < TR; rr++) d[rr] = rr < rows ? src[rr] : 0.0;
+            }
+            __syncwarp();
          }
+         if (lane == 0)
+            pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(kc * rows_even * sizeof(double)));
+         __syncwarp();
+         if (rows_even > 0)
+            for (int c = lane; c < kc; c += 32) {
+               const double *src = c < k ? col_ptr(a, c) + r0 : a.X + (size_t)(c - k) * a.ldx + r0;
+               pbtma::bulk_g2s(dst + (size_t)c * TR, src, rows_even * sizeof(double), &full[s]);
+            }
          if (++s == nstages) s = 0, ph ^= 1;
       }
       return;
@@ -532,7 +545,12 @@ __global__ void __launch_bounds__(NCT + 32) ortho_sweep_ws_kernel(SweepArgs a, i
          const int64_t r = tile * TR + p2;
 #pragma unroll
          for (int c = 0; c < BT; c++)
-            if (c < a.b) *reinterpret_cast<double2 *>(a.X + r + (size_t)c * a.ldx) = make_double2(x0[c], x1[c]);
+            if (c < a.b) {
+               if (r + 1 < a.n)
+                  *reinterpret_cast<double2 *>(a.X + r + (size_t)c * a.ldx) = make_double2(x0[c], x1[c]);
+               else if (r < a.n)
+                  a.X[r + (size_t)c * a.ldx] = x0[c];
+            }
          if (ngw > 0) {
             pbtma::mbar_wait(&xempty[buf], xph ^ 1);  // Gram warps are done with this buffer
             double *xb = xs + (size_t)buf * BT * TR;
@@ -781,8 +799,13 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
    int grid = 0, nparts = 0, rc = 0;
    int ps = pb_prof_begin(ctx, PB_K_ORTHO);
    if (tma_ok) {
-      const int64_t ntiles = n / TR;
-      const int64_t n_main = ntiles * TR;
+      // v3 (warp-specialised) when its column split fits the register budget; it handles a
+      // partial last tile itself, the v2 kernel leaves the < 128-row tail to one v1 CTA
+      const int ngw = a.do_gram ? NCW - (a.do_update ? 2 : 0) : 0;
+      const int cpw_ws = ngw > 0 ? (k + ngw - 1) / ngw : 1;
+      const bool ws = ctx->use_ws && cpw_ws <= 10 && (ngw == 0 || 2 * ngw >= b);
+      const int64_t ntiles = ws ? (n + TR - 1) / TR : n / TR;
+      const int64_t n_main = ws ? n : ntiles * TR;
       grid = (int)(ntiles < (int64_t)ctx->num_sms * ctas_per_sm ? ntiles : (int64_t)ctx->num_sms * ctas_per_sm);
       const int tail = n_main < n ? 1 : 0;
       if (a.do_gram) {
@@ -792,10 +815,7 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
       SweepArgs am = a;
       am.n = n_main;
       size_t shmem = (size_t)nstages * kc * TR * sizeof(double) + fixed_sm + 2 * nstages * sizeof(uint64_t);
-      // v3 (warp-specialised) when its column split fits the register budget
-      const int ngw = a.do_gram ? NCW - (a.do_update ? 2 : 0) : 0;
-      const int cpw_ws = ngw > 0 ? (k + ngw - 1) / ngw : 1;
-      if (ctx->use_ws && cpw_ws <= 10 && (ngw == 0 || 2 * ngw >= b)) {
+      if (ws) {
          const int cw = cpw_ws < 1 ? 1 : cpw_ws;
          switch (BT) {
          case 1: rc = dispatch_cpw_ws<1>(ctx, am, cw, grid, shmem, nstages); break;

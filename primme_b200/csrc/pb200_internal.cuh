@@ -45,6 +45,7 @@ struct pb200_ctx {
    int64_t launches;
    int use_ws;            // warp-specialised ortho sweep (v3) where eligible
    int use_tma_vwxr;      // same switch for the VWXR kernel alone
+   int use_tma_spmm;      // persistent bulk-copy SpMM (v2)
    int use_tma;           // 1: TMA-staged kernels where eligible (default), 0: LDG kernels only
    // optional per-kernel-kind CUDA-event timing (bench.py's roofline numbers)
    int prof_on;

@@ -14,6 +14,7 @@
 //   - a row longer than SP_NNZ gets CTAs of its own (chunks), partial sums are combined in a
 //     fixed order by a second tiny kernel.
 #include "pb200_internal.cuh"
+#include "tma_pipe.cuh"
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -144,6 +145,200 @@ __global__ void spmm_long_fixup(const int64_t *__restrict__ lr_row,
    Y[lr_row[lr] + (size_t)c * ldy] = s;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// v2: persistent, warp-specialised.  One producer warp streams the row blocks of this CTA
+// (values, column indices and the row-pointer slice: three bulk copies per block, SASS UBLKCP)
+// through a ring of shared-memory stages; 16 consumer warps do the gathers and FMAs.  The matrix
+// stream never waits for the gathers of the previous block and no CTA is launched per block.
+// Bulk copies need 16-byte aligned sources: each slice starts at the aligned-down element and
+// the consumers index with the remainder (device arrays are padded for the over-read).
+constexpr int SPT_CONS = 512;                   // consumer threads
+constexpr int SPT_THREADS = SPT_CONS + 32;      // + producer warp
+constexpr int SPT_VALS = SP_NNZ + 8;            // staged values incl. alignment slack
+constexpr int SPT_RP = SP_ROWS + 4;             // staged row pointers
+constexpr size_t SPT_STAGE_BYTES = ((size_t)SPT_VALS * 12 + (size_t)SPT_RP * 8 + 64 + 127) / 128 * 128;
+
+struct SpStageHdr {
+   int64_t row0;    // first row of the block
+   int64_t nzbase;  // global index of s_val[0]
+   int64_t rpbase;  // global row index of s_rp[0]
+   int32_t nrows, nnzb, kind, slot;
+   int32_t off, pad_[3];  // off: block's first nonzero relative to nzbase
+};
+
+template <int BT, int LPR>
+__global__ void __launch_bounds__(SPT_THREADS, 2) spmm_tma_kernel(const int64_t *__restrict__ rowptr,
+      const int32_t *__restrict__ colind, const double *__restrict__ vals,
+      const int64_t *__restrict__ blk_row0, const int64_t *__restrict__ blk_nz0,
+      const int32_t *__restrict__ blk_nnz, const int32_t *__restrict__ blk_kind,
+      const int32_t *__restrict__ long_slot, double *__restrict__ long_part, int nblocks,
+      const double *__restrict__ X, int64_t ldx, double *__restrict__ Y, int64_t ldy, int b,
+      int nstages) {
+   extern __shared__ __align__(128) unsigned char smraw[];
+   __shared__ uint64_t full[8], empty[8];
+   __shared__ double s_red[SPT_CONS / 32][BT];
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   if (tid == 0) {
+      for (int s = 0; s < nstages; s++) {
+         pbtma::mbar_init(&full[s], 1);
+         pbtma::mbar_init(&empty[s], SPT_CONS / 32);
+      }
+      pbtma::fence_barrier_init();
+   }
+   __syncthreads();
+
+   if (warp == SPT_CONS / 32) {
+      // -------- producer --------
+      if (lane != 0) return;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+         const int64_t nz0 = blk_nz0[blk];
+         const int nnzb = blk_nnz[blk];
+         const int kind = blk_kind[blk];
+         const int64_t row0 = blk_row0[blk];
+         const int nrows = kind == 0 ? (int)(blk_row0[blk + 1] - row0) : 1;
+         const int slot = long_slot[blk];
+         pbtma::mbar_wait(&empty[s], ph ^ 1);
+         unsigned char *st = smraw + (size_t)s * SPT_STAGE_BYTES;
+         double *s_val = reinterpret_cast<double *>(st);
+         int32_t *s_col = reinterpret_cast<int32_t *>(st + (size_t)SPT_VALS * 8);
+         int64_t *s_rp = reinterpret_cast<int64_t *>(st + (size_t)SPT_VALS * 12);
+         SpStageHdr *hdr = reinterpret_cast<SpStageHdr *>(st + (size_t)SPT_VALS * 12 + (size_t)SPT_RP * 8);
+         const int64_t nzbase = nz0 & ~(int64_t)3;                 // 32-byte / 16-byte aligned starts
+         const int cnt = (int)((nz0 + nnzb - nzbase + 3) & ~(int64_t)3);
+         const int64_t rpbase = row0 & ~(int64_t)1;
+         const int rpcnt = kind == 0 ? (int)((row0 + nrows + 1 - rpbase + 1) & ~(int64_t)1) : 0;
+         hdr->row0 = row0, hdr->nzbase = nzbase, hdr->rpbase = rpbase;
+         hdr->nrows = nrows, hdr->nnzb = nnzb, hdr->kind = kind, hdr->slot = slot;
+         hdr->off = (int32_t)(nz0 - nzbase);
+         const uint32_t bytes = (uint32_t)cnt * 12u + (uint32_t)rpcnt * 8u;
+         pbtma::mbar_arrive_expect_tx(&full[s], bytes);
+         if (cnt > 0) {
+            pbtma::bulk_g2s(s_val, vals + nzbase, (uint32_t)cnt * 8u, &full[s]);
+            pbtma::bulk_g2s(s_col, colind + nzbase, (uint32_t)cnt * 4u, &full[s]);
+         }
+         if (rpcnt > 0) pbtma::bulk_g2s(s_rp, rowptr + rpbase, (uint32_t)rpcnt * 8u, &full[s]);
+         if (++s == nstages) s = 0, ph ^= 1;
+      }
+      return;
+   }
+
+   // -------- consumers --------
+   int s = 0;
+   uint32_t ph = 0;
+   constexpr int RPP = SPT_CONS / LPR;  // rows per pass
+   const int sub = tid % LPR;
+   for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+      pbtma::mbar_wait(&full[s], ph);
+      const unsigned char *st = smraw + (size_t)s * SPT_STAGE_BYTES;
+      const double *s_val = reinterpret_cast<const double *>(st);
+      const int32_t *s_col = reinterpret_cast<const int32_t *>(st + (size_t)SPT_VALS * 8);
+      const int64_t *s_rp = reinterpret_cast<const int64_t *>(st + (size_t)SPT_VALS * 12);
+      const SpStageHdr *hdr =
+            reinterpret_cast<const SpStageHdr *>(st + (size_t)SPT_VALS * 12 + (size_t)SPT_RP * 8);
+      const int64_t row0 = hdr->row0, nzbase = hdr->nzbase;
+      const int nrows = hdr->nrows, nnzb = hdr->nnzb, kind = hdr->kind, slot = hdr->slot;
+      const int rpoff = (int)(row0 - hdr->rpbase);
+      if (kind == 0) {
+         for (int base = 0; base < nrows; base += RPP) {
+            const int rl = base + tid / LPR;
+            const bool active = rl < nrows;
+            int sidx = 0, e = 0;
+            if (active) sidx = (int)(s_rp[rpoff + rl] - nzbase), e = (int)(s_rp[rpoff + rl + 1] - nzbase);
+            double acc[BT];
+#pragma unroll
+            for (int c = 0; c < BT; c++) acc[c] = 0.0;
+            for (int i = sidx + sub; i < e; i += LPR) {
+               const double v = s_val[i];
+               const double *xp = X + s_col[i];
+#pragma unroll
+               for (int c = 0; c < BT; c++)
+                  if (c < b) acc[c] += v * xp[(size_t)c * ldx];
+            }
+            if (LPR > 1) {
+#pragma unroll
+               for (int c = 0; c < BT; c++)
+#pragma unroll
+                  for (int o = LPR / 2; o > 0; o >>= 1)
+                     acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o, LPR);
+            }
+            if (active && sub == 0) {
+               const int64_t row = row0 + rl;
+#pragma unroll
+               for (int c = 0; c < BT; c++)
+                  if (c < b) Y[row + (size_t)c * ldy] = acc[c];
+            }
+         }
+      } else {
+         const int off = hdr->off;
+         double acc[BT];
+#pragma unroll
+         for (int c = 0; c < BT; c++) acc[c] = 0.0;
+         for (int i = tid; i < nnzb; i += SPT_CONS) {
+            const double v = s_val[off + i];
+            const double *xp = X + s_col[off + i];
+#pragma unroll
+            for (int c = 0; c < BT; c++)
+               if (c < b) acc[c] += v * xp[(size_t)c * ldx];
+         }
+#pragma unroll
+         for (int c = 0; c < BT; c++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+            if (lane == 0) s_red[warp][c] = acc[c];
+         }
+         pbtma::named_bar_sync(1, SPT_CONS);
+         if (tid < BT) {
+            double sum = 0.0;
+            for (int w = 0; w < SPT_CONS / 32; w++) sum += s_red[w][tid];
+            long_part[(size_t)slot * 8 + tid] = sum;
+         }
+         pbtma::named_bar_sync(1, SPT_CONS);  // s_red is reused by the next long chunk
+      }
+      __syncwarp();
+      if (lane == 0) pbtma::mbar_arrive(&empty[s]);
+      if (++s == nstages) s = 0, ph ^= 1;
+   }
+}
+
+template <int BT, int LPR>
+int launch_spmm_tma_l(pb200_ctx *ctx, const pb200_csr *A, const double *X, int64_t ldx, double *Y,
+      int64_t ldy, int b) {
+   auto kern = spmm_tma_kernel<BT, LPR>;
+   static int cached_occ = 0;
+   const int nstages = 4;
+   const size_t shmem = nstages * SPT_STAGE_BYTES;
+   if (!cached_occ) {
+      PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+      int occ = 0;
+      PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SPT_THREADS, shmem));
+      cached_occ = occ > 0 ? occ : 1;
+   }
+   int grid = ctx->num_sms * cached_occ;
+   if (grid > A->nblocks) grid = A->nblocks;
+   kern<<<grid, SPT_THREADS, shmem, ctx->stream>>>(A->d_rowptr, A->d_colind, A->d_vals,
+         A->d_blk_row0, A->d_blk_nz0, A->d_blk_nnz, A->d_blk_kind, A->d_long_slot, A->d_long_part,
+         A->nblocks, X, ldx, Y, ldy, b, nstages);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   return 0;
+}
+
+template <int BT>
+int launch_spmm_tma(pb200_ctx *ctx, const pb200_csr *A, const double *X, int64_t ldx, double *Y,
+      int64_t ldy, int b) {
+   switch (A->lpr) {
+   case 1: return launch_spmm_tma_l<BT, 1>(ctx, A, X, ldx, Y, ldy, b);
+   case 2: return launch_spmm_tma_l<BT, 2>(ctx, A, X, ldx, Y, ldy, b);
+   case 4: return launch_spmm_tma_l<BT, 4>(ctx, A, X, ldx, Y, ldy, b);
+   case 8: return launch_spmm_tma_l<BT, 8>(ctx, A, X, ldx, Y, ldy, b);
+   case 16: return launch_spmm_tma_l<BT, 16>(ctx, A, X, ldx, Y, ldy, b);
+   default: return launch_spmm_tma_l<BT, 32>(ctx, A, X, ldx, Y, ldy, b);
+   }
+}
+
 template <int BT>
 int launch_spmm(pb200_ctx *ctx, const pb200_csr *A, const double *X, int64_t ldx, double *Y,
       int64_t ldy, int b) {
@@ -245,9 +440,13 @@ int csr_from_host(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
    pb200_csr *A = (pb200_csr *)calloc(1, sizeof(pb200_csr));
    if (!A) return PB200_ERR_ALLOC;
    A->nrows = nrows, A->ncols = ncols, A->nnz = nnz;
-   PB_CUDA(cudaMalloc((void **)&A->d_rowptr, sizeof(int64_t) * (nrows + 1)));
-   PB_CUDA(cudaMalloc((void **)&A->d_colind, sizeof(int32_t) * (nnz ? nnz : 1)));
-   PB_CUDA(cudaMalloc((void **)&A->d_vals, sizeof(double) * (nnz ? nnz : 1)));
+   // 64 bytes of zeroed slack after each array: the bulk copies of the v2 kernel read aligned slices
+   PB_CUDA(cudaMalloc((void **)&A->d_rowptr, sizeof(int64_t) * (nrows + 1) + 64));
+   PB_CUDA(cudaMemsetAsync(A->d_rowptr, 0, sizeof(int64_t) * (nrows + 1) + 64, ctx->stream));
+   PB_CUDA(cudaMalloc((void **)&A->d_colind, sizeof(int32_t) * nnz + 64));
+   PB_CUDA(cudaMemsetAsync(A->d_colind, 0, sizeof(int32_t) * nnz + 64, ctx->stream));
+   PB_CUDA(cudaMalloc((void **)&A->d_vals, sizeof(double) * nnz + 64));
+   PB_CUDA(cudaMemsetAsync(A->d_vals, 0, sizeof(double) * nnz + 64, ctx->stream));
    PB_CUDA(cudaMemcpyAsync(A->d_rowptr, rp0, sizeof(int64_t) * (nrows + 1), cudaMemcpyHostToDevice, ctx->stream));
    if (nnz) {
       PB_CUDA(cudaMemcpyAsync(A->d_colind, ci0, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
@@ -305,7 +504,12 @@ extern "C" int pb200_dspmm(pb200_ctx *ctx, const pb200_csr *A, const double *X, 
       const double abytes = 12.0 * (double)A->nnz + 8.0 * (double)(A->nrows + 1) +
                             8.0 * (double)b * (double)(A->nrows + A->ncols);
       int ps = pb_prof_begin(ctx, PB_K_SPMM);
-      if (b <= 1) rc = launch_spmm<1>(ctx, A, Xc, ldx, Yc, ldy, b);
+      if (ctx->use_tma_spmm) {
+         if (b <= 1) rc = launch_spmm_tma<1>(ctx, A, Xc, ldx, Yc, ldy, b);
+         else if (b <= 2) rc = launch_spmm_tma<2>(ctx, A, Xc, ldx, Yc, ldy, b);
+         else if (b <= 4) rc = launch_spmm_tma<4>(ctx, A, Xc, ldx, Yc, ldy, b);
+         else rc = launch_spmm_tma<8>(ctx, A, Xc, ldx, Yc, ldy, b);
+      } else if (b <= 1) rc = launch_spmm<1>(ctx, A, Xc, ldx, Yc, ldy, b);
       else if (b <= 2) rc = launch_spmm<2>(ctx, A, Xc, ldx, Yc, ldy, b);
       else if (b <= 4) rc = launch_spmm<4>(ctx, A, Xc, ldx, Yc, ldy, b);
       else rc = launch_spmm<8>(ctx, A, Xc, ldx, Yc, ldy, b);

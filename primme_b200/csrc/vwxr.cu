@@ -452,6 +452,14 @@ __global__ void __launch_bounds__(256 + 32) vwxr_tma_kernel(VwxrArgs a, int nsta
 }
 
 
+// two consecutive rows with one 16-byte store; the very last row of an odd-length vector alone
+__device__ __forceinline__ void st2(double *p, double v0, double v1, int64_t r, int64_t n) {
+   if (r + 1 < n)
+      *reinterpret_cast<double2 *>(p) = make_double2(v0, v1);
+   else if (r < n)
+      *p = v0;
+}
+
 // ------------------------------------------------------------------------------------------
 // v3 for narrow coefficient blocks (nh <= 8, no Gram outputs): the candidates sweep, executed
 // every outer iteration.  Producer warp as in v2; the 8 consumer warps form 4 groups of 2 warps
@@ -467,14 +475,18 @@ __global__ void __launch_bounds__(256 + 32) vwxr_narrow_kernel(VwxrArgs a, int n
    double *hs = stage0 + (size_t)nstages * 2 * m * TR;   // m * NTH
    double *th = hs + (size_t)m * NTH;                    // NTH
    double *red = th + NTH;                               // 8 * NTH
+   // Barrier slots: the i-th tile of this CTA uses stage i % nstages and is consumed by tile group
+   // i % 4, so slot i % NB with NB = 4*nstages always maps to the same (stage, group) pair: the
+   // phases of one slot are consumed by one group in order, which is what parity waits require.
+   const int NB = 4 * nstages;
    uint64_t *full = reinterpret_cast<uint64_t *>(red + 8 * NTH);
-   uint64_t *empty = full + nstages;
+   uint64_t *empty = full + NB;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
    if (tid == 0) {
-      for (int s = 0; s < nstages; s++) {
-         pbtma::mbar_init(&full[s], 1);
-         pbtma::mbar_init(&empty[s], 2);
+      for (int u = 0; u < NB; u++) {
+         pbtma::mbar_init(&full[u], 1);
+         pbtma::mbar_init(&empty[u], 2);
       }
       pbtma::fence_barrier_init();
    }
@@ -485,24 +497,38 @@ __global__ void __launch_bounds__(256 + 32) vwxr_narrow_kernel(VwxrArgs a, int n
    for (int i = tid; i < NTH; i += 288) th[i] = i < a.nh ? a.thetadev[i] : 0.0;
    __syncthreads();
 
-   const int64_t ntiles = a.n / TR;
-   // CTA-local tile i <-> global tile blockIdx.x + i*gridDim.x, stage i % nstages
+   const int64_t ntiles = (a.n + TR - 1) / TR;  // the last tile may be partial
    if (warp == 8) {
       int64_t i = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, i++) {
          const int s = (int)(i % nstages);
-         const uint32_t ph = (uint32_t)((i / nstages) & 1);
-         if (lane == 0) {
-            pbtma::mbar_wait(&empty[s], ph ^ 1);
-            pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * m * TR * sizeof(double)));
+         const int u = (int)(i % NB);
+         if (lane == 0 && i >= nstages) {
+            const int64_t j = i - nstages;  // previous user of this stage
+            pbtma::mbar_wait(&empty[j % NB], (uint32_t)((j / NB) & 1));
          }
          __syncwarp();
          double *dst = stage0 + (size_t)s * 2 * m * TR;
          const int64_t r0 = tile * TR;
-         for (int c = lane; c < 2 * m; c += 32) {
-            const double *src = (c < m ? a.V + (size_t)c * a.ld : a.W + (size_t)(c - m) * a.ld) + r0;
-            pbtma::bulk_g2s(dst + (size_t)c * TR, src, TR * sizeof(double), &full[s]);
+         const int rows = (int)((a.n - r0) < TR ? (a.n - r0) : TR);
+         const int rows_even = rows & ~1;
+         if (rows < TR) {
+            // partial tile: odd last row and zero padding by plain stores (see ortho_sweep.cu)
+            for (int c = lane; c < 2 * m; c += 32) {
+               const double *src = (c < m ? a.V + (size_t)c * a.ld : a.W + (size_t)(c - m) * a.ld) + r0;
+               double *d = dst + (size_t)c * TR;
+               for (int rr = rows_even; rr < TR; rr++) d[rr] = rr < rows ? src[rr] : 0.0;
+            }
+            __syncwarp();
          }
+         if (lane == 0)
+            pbtma::mbar_arrive_expect_tx(&full[u], (uint32_t)(2 * m * rows_even * sizeof(double)));
+         __syncwarp();
+         if (rows_even > 0)
+            for (int c = lane; c < 2 * m; c += 32) {
+               const double *src = (c < m ? a.V + (size_t)c * a.ld : a.W + (size_t)(c - m) * a.ld) + r0;
+               pbtma::bulk_g2s(dst + (size_t)c * TR, src, rows_even * sizeof(double), &full[u]);
+            }
       }
       return;
    }
@@ -516,8 +542,8 @@ __global__ void __launch_bounds__(256 + 32) vwxr_narrow_kernel(VwxrArgs a, int n
    int64_t i = grp;
    for (int64_t tile = blockIdx.x + (int64_t)grp * gridDim.x; tile < ntiles; tile += 4 * (int64_t)gridDim.x, i += 4) {
       const int s = (int)(i % nstages);
-      const uint32_t ph = (uint32_t)((i / nstages) & 1);
-      pbtma::mbar_wait(&full[s], ph);
+      const int u = (int)(i % NB);
+      pbtma::mbar_wait(&full[u], (uint32_t)((i / NB) & 1));
       const double *sv = stage0 + (size_t)s * 2 * m * TR + p2;
       const double *sw = sv + (size_t)m * TR;
       double x0[NTH], x1[NTH], y0[NTH], y1[NTH];
@@ -536,7 +562,7 @@ __global__ void __launch_bounds__(256 + 32) vwxr_narrow_kernel(VwxrArgs a, int n
          }
       }
       __syncwarp();
-      if (lane == 0) pbtma::mbar_arrive(&empty[s]);
+      if (lane == 0) pbtma::mbar_arrive(&empty[u]);
 
       const int64_t r = tile * TR + p2;
 #pragma unroll
@@ -544,13 +570,13 @@ __global__ void __launch_bounds__(256 + 32) vwxr_narrow_kernel(VwxrArgs a, int n
 #pragma unroll
          for (int t = 0; t < 3; t++)
             if (a.X[t].ptr && c >= a.X[t].cb && c < a.X[t].ce)
-               *reinterpret_cast<double2 *>(a.X[t].ptr + r + (size_t)(c - a.X[t].cb) * a.X[t].ld) = make_double2(x0[c], x1[c]);
+               st2(a.X[t].ptr + r + (size_t)(c - a.X[t].cb) * a.X[t].ld, x0[c], x1[c], r, a.n);
          if (a.Wo.ptr && c >= a.Wo.cb && c < a.Wo.ce)
-            *reinterpret_cast<double2 *>(a.Wo.ptr + r + (size_t)(c - a.Wo.cb) * a.Wo.ld) = make_double2(y0[c], y1[c]);
+            st2(a.Wo.ptr + r + (size_t)(c - a.Wo.cb) * a.Wo.ld, y0[c], y1[c], r, a.n);
          const bool inR = a.R.ptr && c >= a.R.cb && c < a.R.ce;
          if (inR || (c >= a.rb && c < a.re)) {
             const double r0 = y0[c] - x0[c] * th[c], r1 = y1[c] - x1[c] * th[c];
-            if (inR) *reinterpret_cast<double2 *>(a.R.ptr + r + (size_t)(c - a.R.cb) * a.R.ld) = make_double2(r0, r1);
+            if (inR) st2(a.R.ptr + r + (size_t)(c - a.R.cb) * a.R.ld, r0, r1, r, a.n);
             nrm[c] += r0 * r0 + r1 * r1;
          }
       }
@@ -614,14 +640,15 @@ __global__ void __launch_bounds__(256 + 32) vwxr_wide_kernel(VwxrArgs a, int nst
    double *hs = stage0 + (size_t)nstages * 2 * m * TR;                 // m * NT
    double *th = hs + (size_t)m * NT;                                   // NT
    double *park0 = th + NT;                                            // NTG * 2 * park_cols * TR
+   const int NB = NTG * nstages;  // barrier slots, one per (stage, tile group) pair (see narrow kernel)
    uint64_t *full = reinterpret_cast<uint64_t *>(park0 + (size_t)NTG * 2 * park_cols * TR);
-   uint64_t *empty = full + nstages;
+   uint64_t *empty = full + NB;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
    if (tid == 0) {
-      for (int s = 0; s < nstages; s++) {
-         pbtma::mbar_init(&full[s], 1);
-         pbtma::mbar_init(&empty[s], NG);
+      for (int u = 0; u < NB; u++) {
+         pbtma::mbar_init(&full[u], 1);
+         pbtma::mbar_init(&empty[u], NG);
       }
       pbtma::fence_barrier_init();
    }
@@ -632,23 +659,38 @@ __global__ void __launch_bounds__(256 + 32) vwxr_wide_kernel(VwxrArgs a, int nst
    for (int i = tid; i < NT; i += 288) th[i] = i < a.nh ? a.thetadev[i] : 0.0;
    __syncthreads();
 
-   const int64_t ntiles = a.n / TR;
+   const int64_t ntiles = (a.n + TR - 1) / TR;  // the last tile may be partial
    if (warp == 8) {
       int64_t i = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, i++) {
          const int s = (int)(i % nstages);
-         const uint32_t ph = (uint32_t)((i / nstages) & 1);
-         if (lane == 0) {
-            pbtma::mbar_wait(&empty[s], ph ^ 1);
-            pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * m * TR * sizeof(double)));
+         const int u = (int)(i % NB);
+         if (lane == 0 && i >= nstages) {
+            const int64_t j = i - nstages;  // previous user of this stage
+            pbtma::mbar_wait(&empty[j % NB], (uint32_t)((j / NB) & 1));
          }
          __syncwarp();
          double *dst = stage0 + (size_t)s * 2 * m * TR;
          const int64_t r0 = tile * TR;
-         for (int c = lane; c < 2 * m; c += 32) {
-            const double *src = (c < m ? a.V + (size_t)c * a.ld : a.W + (size_t)(c - m) * a.ld) + r0;
-            pbtma::bulk_g2s(dst + (size_t)c * TR, src, TR * sizeof(double), &full[s]);
+         const int rows = (int)((a.n - r0) < TR ? (a.n - r0) : TR);
+         const int rows_even = rows & ~1;
+         if (rows < TR) {
+            // partial tile: odd last row and zero padding by plain stores (see ortho_sweep.cu)
+            for (int c = lane; c < 2 * m; c += 32) {
+               const double *src = (c < m ? a.V + (size_t)c * a.ld : a.W + (size_t)(c - m) * a.ld) + r0;
+               double *d = dst + (size_t)c * TR;
+               for (int rr = rows_even; rr < TR; rr++) d[rr] = rr < rows ? src[rr] : 0.0;
+            }
+            __syncwarp();
          }
+         if (lane == 0)
+            pbtma::mbar_arrive_expect_tx(&full[u], (uint32_t)(2 * m * rows_even * sizeof(double)));
+         __syncwarp();
+         if (rows_even > 0)
+            for (int c = lane; c < 2 * m; c += 32) {
+               const double *src = (c < m ? a.V + (size_t)c * a.ld : a.W + (size_t)(c - m) * a.ld) + r0;
+               pbtma::bulk_g2s(dst + (size_t)c * TR, src, rows_even * sizeof(double), &full[u]);
+            }
       }
       return;
    }
@@ -690,8 +732,8 @@ __global__ void __launch_bounds__(256 + 32) vwxr_wide_kernel(VwxrArgs a, int nst
    for (int64_t tile = blockIdx.x + (int64_t)grp * gridDim.x; tile < ntiles;
          tile += (int64_t)NTG * gridDim.x, i += NTG) {
       const int s = (int)(i % nstages);
-      const uint32_t ph = (uint32_t)((i / nstages) & 1);
-      pbtma::mbar_wait(&full[s], ph);
+      const int u = (int)(i % NB);
+      pbtma::mbar_wait(&full[u], (uint32_t)((i / NB) & 1));
       const double *sv = stage0 + (size_t)s * 2 * m * TR + p2;
       const double *sw = sv + (size_t)m * TR;
       double x0[NTH], x1[NTH], y0[NTH], y1[NTH];
@@ -710,7 +752,7 @@ __global__ void __launch_bounds__(256 + 32) vwxr_wide_kernel(VwxrArgs a, int nst
          }
       }
       __syncwarp();
-      if (lane == 0) pbtma::mbar_arrive(&empty[s]);
+      if (lane == 0) pbtma::mbar_arrive(&empty[u]);
 
       const int64_t r = tile * TR + p2;
 #pragma unroll
@@ -719,16 +761,14 @@ __global__ void __launch_bounds__(256 + 32) vwxr_wide_kernel(VwxrArgs a, int nst
 #pragma unroll
          for (int t = 0; t < 3; t++)
             if (a.X[t].ptr && cc >= a.X[t].cb && cc < a.X[t].ce)
-               *reinterpret_cast<double2 *>(a.X[t].ptr + r + (size_t)(cc - a.X[t].cb) * a.X[t].ld) =
-                     make_double2(x0[c], x1[c]);
+               st2(a.X[t].ptr + r + (size_t)(cc - a.X[t].cb) * a.X[t].ld, x0[c], x1[c], r, a.n);
          if (a.Wo.ptr && cc >= a.Wo.cb && cc < a.Wo.ce)
-            *reinterpret_cast<double2 *>(a.Wo.ptr + r + (size_t)(cc - a.Wo.cb) * a.Wo.ld) =
-                  make_double2(y0[c], y1[c]);
+            st2(a.Wo.ptr + r + (size_t)(cc - a.Wo.cb) * a.Wo.ld, y0[c], y1[c], r, a.n);
          const bool inR = a.R.ptr && cc >= a.R.cb && cc < a.R.ce;
          if (inR || (cc >= a.rb && cc < a.re)) {
             const double r0 = y0[c] - x0[c] * th[cc], r1 = y1[c] - x1[c] * th[cc];
             if (inR)
-               *reinterpret_cast<double2 *>(a.R.ptr + r + (size_t)(cc - a.R.cb) * a.R.ld) = make_double2(r0, r1);
+               st2(a.R.ptr + r + (size_t)(cc - a.R.cb) * a.R.ld, r0, r1, r, a.n);
             nrm[c] += r0 * r0 + r1 * r1;
          }
       }
@@ -936,7 +976,7 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
       for (int t = 0; t < 3; t++) ok = ok && al(a.X[t]);
       ok = ok && al(a.Wo) && al(a.R);
       const int NTHn = nh <= 4 ? 4 : 8;
-      const size_t fixed = ((size_t)m * NTHn + NTHn + 8 * NTHn) * sizeof(double) + 128;
+      const size_t fixed = ((size_t)m * NTHn + NTHn + 8 * NTHn) * sizeof(double) + 640;
       const size_t stage = (size_t)2 * m * 128 * sizeof(double);
       int st = (int)((227 * 1024 - fixed) / stage);
       if (st > 4) st = 4;
@@ -959,7 +999,7 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
       for (int i = 0; i < 5 && ok && !wide_nst; i++) {
          const int nth = cfg[i][0], ng = cfg[i][1];
          if (nh > nth * ng || nblk > 32 * ng || park > nth * ng) continue;
-         const size_t fixed = ((size_t)m * nth * ng + nth * ng + (size_t)(8 / ng) * 2 * park * 64) * sizeof(double) + 128;
+         const size_t fixed = ((size_t)m * nth * ng + nth * ng + (size_t)(8 / ng) * 2 * park * 64) * sizeof(double) + 640;
          const size_t stage = (size_t)2 * m * 64 * sizeof(double);
          if (fixed + 2 * stage > 227 * 1024) continue;
          int st = (int)((227 * 1024 - fixed) / stage);
@@ -972,77 +1012,29 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
    int ps = pb_prof_begin(ctx, PB_K_VWXR);
    if (narrow_nst >= 2) {
       const int TR = 128;
-      const int64_t ntiles = n / TR, n_main = ntiles * TR;
+      const int64_t ntiles = (n + TR - 1) / TR;
       grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
-      const int tail = n_main < n ? 1 : 0;
-      PB_CHK(pb_ensure_partials(ctx, (size_t)(grid + tail) * (cnt > 0 ? cnt : 1) + 16));
+      PB_CHK(pb_ensure_partials(ctx, (size_t)grid * (cnt > 0 ? cnt : 1) + 16));
       a.partials = ctx->d_partials;
       if (cnt > 0)
-         PB_CUDA(cudaMemsetAsync(ctx->d_partials, 0, (size_t)(grid + tail) * cnt * sizeof(double), ctx->stream));
-      VwxrArgs am = a;
-      am.n = n_main;
-      if (nh <= 4) rc = launch_vwxr_narrow<4>(ctx, am, grid, narrow_shm, narrow_nst);
-      else rc = launch_vwxr_narrow<8>(ctx, am, grid, narrow_shm, narrow_nst);
+         PB_CUDA(cudaMemsetAsync(ctx->d_partials, 0, (size_t)grid * cnt * sizeof(double), ctx->stream));
+      if (nh <= 4) rc = launch_vwxr_narrow<4>(ctx, a, grid, narrow_shm, narrow_nst);
+      else rc = launch_vwxr_narrow<8>(ctx, a, grid, narrow_shm, narrow_nst);
       nparts = grid;
-      if (!rc && tail) {
-         VwxrArgs at = a;
-         at.n = n - n_main;
-         at.V = V + n_main, at.W = W + n_main;
-         for (int t = 0; t < 3; t++)
-            if (at.X[t].ptr) at.X[t].ptr += n_main;
-         if (at.Wo.ptr) at.Wo.ptr += n_main;
-         if (at.R.ptr) at.R.ptr += n_main;
-         at.partials = ctx->d_partials + (size_t)grid * cnt;
-         const int NT1 = nh <= 4 ? 4 : 8;
-         size_t shd = (size_t)m * NT1 + NT1;
-         if (shd < VT) shd = VT;
-         if (NT1 == 4) rc = launch_vwxr<4>(ctx, at, 1, shd * 8);
-         else rc = launch_vwxr<8>(ctx, at, 1, shd * 8);
-         nparts = grid + 1;
-      }
    } else if (wide_nst >= 2) {
       const int TR = 64;
       const int NTG = 8 / wide_ng;
-      const int64_t ntiles = n / TR, n_main = ntiles * TR;
+      const int64_t ntiles = (n + TR - 1) / TR;
       grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
-      const int tail = n_main < n ? 1 : 0;
-      PB_CHK(pb_ensure_partials(ctx, (size_t)(grid * NTG + tail) * (cnt > 0 ? cnt : 1) + 16));
+      PB_CHK(pb_ensure_partials(ctx, (size_t)grid * NTG * (cnt > 0 ? cnt : 1) + 16));
       a.partials = ctx->d_partials;
       if (cnt > 0)
-         PB_CUDA(cudaMemsetAsync(ctx->d_partials, 0, (size_t)(grid * NTG + tail) * cnt * sizeof(double), ctx->stream));
-      VwxrArgs am = a;
-      am.n = n_main;
+         PB_CUDA(cudaMemsetAsync(ctx->d_partials, 0, (size_t)grid * NTG * cnt * sizeof(double), ctx->stream));
 #define VW3(NTH_, NG_) \
-   if (wide_nth == NTH_ && wide_ng == NG_) rc = launch_vwxr_wide<NTH_, NG_>(ctx, am, grid, wide_shm, wide_nst, wide_park);
+   if (wide_nth == NTH_ && wide_ng == NG_) rc = launch_vwxr_wide<NTH_, NG_>(ctx, a, grid, wide_shm, wide_nst, wide_park);
       VW3(8, 1) VW3(8, 2) VW3(12, 2) VW3(8, 4) VW3(12, 4)
 #undef VW3
       nparts = grid * NTG;
-      if (!rc && tail) {
-         VwxrArgs at = a;
-         at.n = n - n_main;
-         at.V = V + n_main, at.W = W + n_main;
-         for (int t = 0; t < 3; t++)
-            if (at.X[t].ptr) at.X[t].ptr += n_main;
-         if (at.Wo.ptr) at.Wo.ptr += n_main;
-         if (at.R.ptr) at.R.ptr += n_main;
-         at.partials = ctx->d_partials + (size_t)nparts * cnt;
-         const int NT1 = nh <= 4 ? 4 : nh <= 8 ? 8 : nh <= 16 ? 16 : nh <= 24 ? 24 : nh <= 32 ? 32
-                        : nh <= 40 ? 40 : nh <= 48 ? 48 : 64;
-         const int ngh1 = a.nG > a.nH ? a.nG : a.nH;
-         size_t shd = (size_t)m * NT1 + NT1 + (size_t)ngh1 * VT + (size_t)a.nH * VT;
-         if (shd < VT) shd = VT;
-         switch (NT1) {
-         case 4: rc = launch_vwxr<4>(ctx, at, 1, shd * 8); break;
-         case 8: rc = launch_vwxr<8>(ctx, at, 1, shd * 8); break;
-         case 16: rc = launch_vwxr<16>(ctx, at, 1, shd * 8); break;
-         case 24: rc = launch_vwxr<24>(ctx, at, 1, shd * 8); break;
-         case 32: rc = launch_vwxr<32>(ctx, at, 1, shd * 8); break;
-         case 40: rc = launch_vwxr<40>(ctx, at, 1, shd * 8); break;
-         case 48: rc = launch_vwxr<48>(ctx, at, 1, shd * 8); break;
-         default: rc = launch_vwxr<64>(ctx, at, 1, shd * 8); break;
-         }
-         nparts += 1;
-      }
    } else if (nst >= 2) {
       const int TR = 256 / tpr;
       const int64_t ntiles = n / TR, n_main = ntiles * TR;

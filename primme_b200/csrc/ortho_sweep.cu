@@ -421,10 +421,10 @@ __global__ void __launch_bounds__(NCT + 32) ortho_sweep_ws_kernel(SweepArgs a, i
    const int k = a.q + a.mv;
    const int kc = k + a.b;
    double *stage0 = reinterpret_cast<double *>(smraw);
-   double *Cs = stage0 + (size_t)nstages * kc * TR;  // k * BT
+   double *xs = stage0 + (size_t)nstages * kc * TR;  // 2 * BT * TR, 16-byte aligned (double2 access)
+   double *Cs = xs + 2 * BT * TR;                    // k * BT
    double *Ys = Cs + (size_t)k * BT;                 // BT * BT
-   double *xs = Ys + BT * BT;                        // 2 * BT * TR
-   uint64_t *full = reinterpret_cast<uint64_t *>(xs + 2 * BT * TR);
+   uint64_t *full = reinterpret_cast<uint64_t *>(Ys + BT * BT);
    uint64_t *empty = full + nstages;
    uint64_t *xfull = empty + nstages;  // [2]
    uint64_t *xempty = xfull + 2;       // [2]

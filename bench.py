@@ -73,6 +73,24 @@ class ClockSampler:
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
+        # in-process NVML when available (no process spawn, no driver re-initialisation while the
+        # launch-latency-bound solver is being timed); nvidia-smi otherwise
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = get_reasons(h)
+                act = lambda bit: "Active" if (r & bit) else "Not Active"
+                self.rows.append([str(sm), str(mx), act(0x8), act(0x40), act(0x20), act(0x4)])
+                time.sleep(0.1)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -85,7 +103,7 @@ class ClockSampler:
                     self.rows.append(parts)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.5)
 
     def __enter__(self):
         self.t.start()

@@ -34,18 +34,21 @@ extern "C" int pb200_ctx_create(pb200_ctx **out, int device) {
    ctx->small_cap = 1 << 16; // 64 Ki doubles = 512 KB
    PB_CUDA(cudaHostAlloc((void **)&ctx->h_pinned, ctx->small_cap * sizeof(double), cudaHostAllocMapped));
    PB_CUDA(cudaHostGetDevicePointer((void **)&ctx->d_hpinned, ctx->h_pinned, 0));
-   PB_CUDA(cudaHostAlloc((void **)&ctx->h_flag, 64, cudaHostAllocMapped));
-   PB_CUDA(cudaHostGetDevicePointer((void **)&ctx->d_hflag, (void *)ctx->h_flag, 0));
-   *ctx->h_flag = 0;
-   PB_CUDA(cudaMalloc((void **)&ctx->d_counter, sizeof(unsigned int)));
-   PB_CUDA(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)));
+   ctx->h_tagged = NULL, ctx->d_htagged = NULL, ctx->tagged_cap = 0;
+   PB_CHK(pb_ensure_tagged(ctx, 4096));
    PB_CUDA(cudaMalloc((void **)&ctx->d_small, ctx->small_cap * sizeof(double)));
    PB_CUDA(cudaMalloc((void **)&ctx->d_panel, ctx->small_cap * sizeof(double)));
    ctx->partials_cap = 0;
    ctx->d_partials = NULL;
    ctx->nranks = 1;
    ctx->no_poll = getenv("PB200_NO_POLL") ? 1 : 0;
-   ctx->use_ws = getenv("PB200_NO_WS") ? 0 : 1;
+   // measured on B200 (profiles/README.md): the warp-specialised ortho sweep and the narrow VWXR
+   // kernel are slower than the v2 sweep / the LDG VWXR kernel at the C2 shapes: opt-in only
+   ctx->use_ws = getenv("PB200_WS") ? 1 : 0;
+   ctx->use_narrow = getenv("PB200_NARROW") ? 1 : 0;
+   ctx->vwxr_cand_tma = getenv("PB200_CAND_TMA") ? 1 : 0;
+   ctx->use_wide = getenv("PB200_NO_WIDE") ? 0 : 1;
+   ctx->ortho_2cta = getenv("PB200_ORTHO_1CTA") ? 0 : 1;
    ctx->use_tma = getenv("PB200_NO_TMA") ? 0 : 1;
    ctx->use_tma_vwxr = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_VWXR")) ? 0 : 1;
    ctx->use_tma_spmm = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_SPMM")) ? 0 : 1;
@@ -58,8 +61,7 @@ extern "C" int pb200_ctx_destroy(pb200_ctx *ctx) {
    cudaStreamSynchronize(ctx->stream);
    if (ctx->comm && ctx->owns_comm) pb200_ctx_comm_free(ctx);
    cudaFreeHost(ctx->h_pinned);
-   cudaFreeHost((void *)ctx->h_flag);
-   cudaFree(ctx->d_counter);
+   cudaFreeHost(ctx->h_tagged);
    cudaFree(ctx->d_small);
    cudaFree(ctx->d_panel);
    cudaFree(ctx->d_partials);
@@ -110,6 +112,19 @@ int pb_ensure_small(pb200_ctx *ctx, size_t doubles) {
    PB_CUDA(cudaMalloc((void **)&ctx->d_small, cap * sizeof(double)));
    PB_CUDA(cudaMalloc((void **)&ctx->d_panel, cap * sizeof(double)));
    ctx->small_cap = cap;
+   return 0;
+}
+
+// mapped pinned buffer of (value, tag) pairs for polled panels
+int pb_ensure_tagged(pb200_ctx *ctx, size_t elems) {
+   if (elems <= ctx->tagged_cap) return 0;
+   PB_CUDA(cudaStreamSynchronize(ctx->stream));
+   size_t cap = elems * 2 > 8192 ? elems * 2 : 8192;
+   if (ctx->h_tagged) cudaFreeHost(ctx->h_tagged);
+   PB_CUDA(cudaHostAlloc((void **)&ctx->h_tagged, cap * 2 * sizeof(double), cudaHostAllocMapped));
+   memset(ctx->h_tagged, 0, cap * 2 * sizeof(double));
+   PB_CUDA(cudaHostGetDevicePointer((void **)&ctx->d_htagged, ctx->h_tagged, 0));
+   ctx->tagged_cap = cap;
    return 0;
 }
 
@@ -166,7 +181,7 @@ extern "C" int pb200_ctx_get_profile(pb200_ctx *ctx, int kind, int64_t *count, d
 // are combined in warp order through shared memory.
 __global__ void __launch_bounds__(256) pb_reduce_partials_kernel(
       const double *__restrict__ partials, int nparts, int cnt, double *__restrict__ out,
-      unsigned int *counter, long long *flag, long long seq) {
+      long long tag) {
    __shared__ double red[8][33];
    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
    const int e = blockIdx.x * 32 + lane;
@@ -187,20 +202,13 @@ __global__ void __launch_bounds__(256) pb_reduce_partials_kernel(
       double s = 0.0;
 #pragma unroll
       for (int w = 0; w < 8; w++) s += red[w][lane];
-      out[e] = s;
-   }
-   if (flag) {
-      // `out` is mapped host memory: publish a sequence number once every CTA's results are
-      // visible system-wide (last-block ticket), so the host can poll instead of synchronising
-      __syncthreads();
-      if (threadIdx.x == 0) {
-         __threadfence_system();
-         const unsigned int ticket = atomicAdd(counter, 1u);
-         if (ticket == gridDim.x - 1) {
-            *counter = 0;
-            __threadfence_system();
-            *(volatile long long *)flag = seq;
-         }
+      if (tag) {
+         // `out` is mapped host memory: every element travels with the sequence number of this
+         // panel in ONE 16-byte store, so the host can tell a fresh value from a stale one without
+         // any fence, ticket or flag on the device side (the stores of all CTAs fly in parallel)
+         reinterpret_cast<double2 *>(out)[e] = make_double2(s, __longlong_as_double(tag));
+      } else {
+         out[e] = s;
       }
    }
 }
@@ -211,7 +219,7 @@ int pb_finish_panel(pb200_ctx *ctx, int nparts, int cnt) {
    int ps = pb_prof_begin(ctx, PB_K_REDUCE);
    if (ctx->nranks > 1 || ctx->no_poll) {
       pb_reduce_partials_kernel<<<(cnt + 31) / 32, 256, 0, ctx->stream>>>(
-            ctx->d_partials, nparts, cnt, ctx->d_panel, NULL, NULL, 0);
+            ctx->d_partials, nparts, cnt, ctx->d_panel, 0);
       pb_prof_end(ctx, ps, 8.0 * nparts * cnt);
       ctx->launches++;
       PB_CUDA(cudaGetLastError());
@@ -221,36 +229,38 @@ int pb_finish_panel(pb200_ctx *ctx, int nparts, int cnt) {
       PB_CUDA(cudaStreamSynchronize(ctx->stream));
       return 0;
    }
-   // single rank: the reduction writes straight into mapped pinned memory and raises a flag; the
-   // host polls the flag (a few microseconds less than memcpy + stream synchronisation, 10+
-   // times per outer iteration)
+   // single rank: the reduction writes (value, sequence number) pairs straight into mapped pinned
+   // memory; the host spins on the sequence numbers (a few microseconds less than memcpy + stream
+   // synchronisation, 10+ times per outer iteration)
+   PB_CHK(pb_ensure_tagged(ctx, (size_t)cnt));
    const long long seq = ++ctx->seq;
    pb_reduce_partials_kernel<<<(cnt + 31) / 32, 256, 0, ctx->stream>>>(
-         ctx->d_partials, nparts, cnt, ctx->d_hpinned, ctx->d_counter, ctx->d_hflag, seq);
+         ctx->d_partials, nparts, cnt, ctx->d_htagged, seq);
    pb_prof_end(ctx, ps, 8.0 * nparts * cnt);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
+   volatile const long long *tg = (volatile const long long *)ctx->h_tagged;
+   volatile const double *tv = (volatile const double *)ctx->h_tagged;
    unsigned long spins = 0;
    time_t t0 = 0;
-   while (*ctx->h_flag != seq) {
-      if ((++spins & 0xfffff) == 0) {
-         // watchdog: a panel never takes seconds; give up instead of spinning for ever
-         const time_t now = time(NULL);
-         if (!t0) t0 = now;
-         if (now - t0 > 120) {
-            fprintf(stderr, "primme_b200: timed out waiting for a panel (kernel hung?)\n");
-            return PB200_ERR_CUDA;
-         }
-         cudaError_t q = cudaStreamQuery(ctx->stream);
-         if (q == cudaSuccess) {
-            if (*ctx->h_flag == seq) break;
-            fprintf(stderr, "primme_b200: panel reduction finished without raising its flag\n");
-            return PB200_ERR_CUDA;
-         } else if (q != cudaErrorNotReady) {
-            fprintf(stderr, "primme_b200: CUDA error %s while waiting for a panel\n", cudaGetErrorString(q));
-            return PB200_ERR_CUDA;
+   for (int e = 0; e < cnt; e++) {
+      while (tg[2 * e + 1] != seq) {
+         if ((++spins & 0xfffff) == 0) {
+            // watchdog: a panel never takes seconds; give up instead of spinning for ever
+            const time_t now = time(NULL);
+            if (!t0) t0 = now;
+            if (now - t0 > 120) {
+               fprintf(stderr, "primme_b200: timed out waiting for a panel (kernel hung?)\n");
+               return PB200_ERR_CUDA;
+            }
+            cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) {
+               fprintf(stderr, "primme_b200: CUDA error %s while waiting for a panel\n", cudaGetErrorString(q));
+               return PB200_ERR_CUDA;
+            }
          }
       }
+      ctx->h_pinned[e] = tv[2 * e];
    }
    return 0;
 }

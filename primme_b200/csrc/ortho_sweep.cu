@@ -789,6 +789,10 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
       const size_t stage_b = (size_t)kc * TR * sizeof(double);
       if (3 * stage_b + fixed_sm <= 110 * 1024) {
          nstages = 3, ctas_per_sm = 2;
+      } else if (ctx->ortho_2cta && 2 * stage_b + fixed_sm <= 110 * 1024) {
+         // two resident CTAs (16 consumer warps per SM) with a 2-deep ring each hide the
+         // shared-memory latency of the Gram warps better than one CTA with a 4-deep ring
+         nstages = 2, ctas_per_sm = 2;
       } else {
          nstages = (int)((220 * 1024 - fixed_sm) / stage_b);
          if (nstages > 4) nstages = 4;

@@ -30,9 +30,9 @@ struct pb200_ctx {
    // staging for small operands and panels
    double *h_pinned;      // pinned host buffer (mapped: kernels may write panels into it directly)
    double *d_hpinned;     // device alias of h_pinned
-   volatile long long *h_flag;  // completion sequence number written by the last reducing CTA
-   long long *d_hflag;
-   unsigned int *d_counter;     // CTA ticket for the last-block pattern
+   double *h_tagged;      // mapped pinned (value, sequence number) pairs of the polled panels
+   double *d_htagged;     // device alias of h_tagged
+   size_t tagged_cap;     // capacity in pairs
    long long seq;
    int no_poll;           // 1: classic memcpy + stream synchronise for panels
    double *d_small;       // device buffer for coefficient blocks (h, C, Y, theta, perms)
@@ -46,6 +46,10 @@ struct pb200_ctx {
    int use_ws;            // warp-specialised ortho sweep (v3) where eligible
    int use_tma_vwxr;      // same switch for the VWXR kernel alone
    int use_tma_spmm;      // persistent bulk-copy SpMM (v2)
+   int use_wide;          // v3 wide VWXR kernel for the restart sweep
+   int vwxr_cand_tma;     // 1: TMA-staged (v2) kernel also for the candidates sweep
+   int use_narrow;        // v3 narrow VWXR kernel for the candidates sweep (default off: the LDG kernel is faster)
+   int ortho_2cta;        // prefer 2 CTAs/SM x 2 stages over 1 CTA/SM x 4 stages in the ortho sweep
    int use_tma;           // 1: TMA-staged kernels where eligible (default), 0: LDG kernels only
    // optional per-kernel-kind CUDA-event timing (bench.py's roofline numbers)
    int prof_on;
@@ -65,6 +69,7 @@ struct pb200_ctx {
 int pb_ensure_partials(pb200_ctx *ctx, size_t doubles);
 int pb_ensure_scratch(pb200_ctx *ctx, size_t bytes);
 int pb_ensure_small(pb200_ctx *ctx, size_t doubles);
+int pb_ensure_tagged(pb200_ctx *ctx, size_t elems);
 // reduce ctx->d_partials [nparts x cnt] -> ctx->d_panel [cnt] (fixed order), optional NCCL
 // allreduce, copy to h_pinned and synchronize.  Result readable at ctx->h_pinned[0..cnt).
 int pb_finish_panel(pb200_ctx *ctx, int nparts, int cnt);

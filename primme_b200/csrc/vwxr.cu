@@ -954,7 +954,9 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
    {
       const bool al = ctx->use_tma_vwxr && m > 0 && (((uintptr_t)V) & 15) == 0 && (((uintptr_t)W) & 15) == 0 && ld % 2 == 0;
       int gb = (a.nG + 1) / 2, hb = (a.nH + 1) / 2;
-      if (al && gb * gb + hb * hb <= 768) {
+      // the candidates sweep (narrow h, no Gram outputs) is fastest with the plain LDG kernel
+      const bool cand = nh <= 8 && a.nG == 0 && a.nH == 0 && !ctx->vwxr_cand_tma;
+      if (al && !cand && gb * gb + hb * hb <= 768) {
          const int c2[][2] = {{4, 2}, {8, 2}, {16, 2}, {24, 2}, {12, 4}, {16, 4}, {20, 4}, {24, 4}};
          for (int i = 0; i < 8 && !nst; i++) {
             const int cap = c2[i][0] * (c2[i][1] / 2);
@@ -969,7 +971,7 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
    // ---- v3 (narrow) plan: candidates sweep ----
    int narrow_nst = 0;
    size_t narrow_shm = 0;
-   if (ctx->use_tma_vwxr && ctx->use_ws && nh <= 8 && a.nG == 0 && a.nH == 0 && m > 0 && n >= 4 * 128 &&
+   if (ctx->use_tma_vwxr && ctx->use_narrow && nh <= 8 && a.nG == 0 && a.nH == 0 && m > 0 && n >= 4 * 128 &&
          (((uintptr_t)V) & 15) == 0 && (((uintptr_t)W) & 15) == 0 && ld % 2 == 0) {
       bool ok = true;
       auto al = [](const pb200_cols &c) { return !c.ptr || ((((uintptr_t)c.ptr) & 15) == 0 && c.ld % 2 == 0); };
@@ -986,7 +988,7 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
    // ---- v3 (wide) plan: restart sweep ----
    int wide_nst = 0, wide_nth = 0, wide_ng = 0, wide_park = 0;
    size_t wide_shm = 0;
-   if (ctx->use_tma_vwxr && ctx->use_ws && narrow_nst < 2 && nh <= 48 && m > 0 && n >= 4 * 64 &&
+   if (ctx->use_tma_vwxr && ctx->use_wide && narrow_nst < 2 && nh <= 48 && m > 0 && n >= 4 * 64 &&
          (((uintptr_t)V) & 15) == 0 && (((uintptr_t)W) & 15) == 0 && ld % 2 == 0) {
       bool ok = true;
       auto al = [](const pb200_cols &c) { return !c.ptr || ((((uintptr_t)c.ptr) & 15) == 0 && c.ld % 2 == 0); };

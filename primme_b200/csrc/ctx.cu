@@ -46,6 +46,7 @@ extern "C" int pb200_ctx_create(pb200_ctx **out, int device) {
    // kernel are slower than the v2 sweep / the LDG VWXR kernel at the C2 shapes: opt-in only
    ctx->use_ws = getenv("PB200_WS") ? 1 : 0;
    ctx->use_narrow = getenv("PB200_NARROW") ? 1 : 0;
+   ctx->coef_inline = getenv("PB200_NO_INLINE_COEF") ? 0 : 1;
    ctx->vwxr_cand_tma = getenv("PB200_CAND_TMA") ? 1 : 0;
    ctx->use_wide = getenv("PB200_NO_WIDE") ? 0 : 1;
    ctx->ortho_2cta = getenv("PB200_ORTHO_1CTA") ? 0 : 1;

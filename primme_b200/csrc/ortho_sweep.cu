@@ -31,7 +31,9 @@ struct SweepArgs {
    int do_update, has_Y, do_gram, xx;
    const double *Cdev;  // (q+mv) x BT, column stride = (q+mv)
    const double *Ydev;  // BT x BT, column stride BT
+   int coef_inline;     // 1: C and Y travel in `coef` below (kernel parameter space), no H2D copy
    double *partials;    // [gridDim.x][(k + xx*b) * b]
+   double coef[PB_COEF_MAX];  // [C (k x BT) | Y (BT x BT)] when coef_inline
 };
 
 __device__ __forceinline__ const double *col_ptr(const SweepArgs &a, int j) {
@@ -39,7 +41,7 @@ __device__ __forceinline__ const double *col_ptr(const SweepArgs &a, int j) {
 }
 
 template <int BT, int CPW>
-__global__ void __launch_bounds__(TILE) ortho_sweep_kernel(SweepArgs a) {
+__global__ void __launch_bounds__(TILE) ortho_sweep_kernel(const __grid_constant__ SweepArgs a) {
    extern __shared__ double smem[];
    const int k = a.q + a.mv;
    double *Cs = smem;                 // k * BT
@@ -50,12 +52,12 @@ __global__ void __launch_bounds__(TILE) ortho_sweep_kernel(SweepArgs a) {
    if (a.do_update) {
       for (int i = tid; i < k * BT; i += TILE) {
          int j = i % k, c = i / k;
-         Cs[j * BT + c] = (c < a.b) ? a.Cdev[j + (size_t)c * k] : 0.0;
+         Cs[j * BT + c] = (c < a.b) ? (a.coef_inline ? a.coef : a.Cdev)[j + (size_t)c * k] : 0.0;
       }
       for (int i = tid; i < BT * BT; i += TILE) {
          int r = i % BT, c = i / BT;
          double y = (r == c) ? 1.0 : 0.0;
-         if (a.has_Y) y = (r < a.b && c < a.b) ? a.Ydev[r + c * BT] : 0.0;
+         if (a.has_Y) y = (r < a.b && c < a.b) ? (a.coef_inline ? a.coef + (size_t)k * BT : a.Ydev)[r + c * BT] : 0.0;
          Ys[r * BT + c] = y;
       }
    }
@@ -185,13 +187,13 @@ __global__ void __launch_bounds__(TILE) ortho_sweep_kernel(SweepArgs a) {
 // segment, completion tracked by mbarriers; 8 consumer warps do the update and the Gram from
 // shared memory.  Memory-level parallelism no longer depends on registers/occupancy: up to
 // 4 tiles (~200 KB) are in flight per SM.  Requires 16-byte aligned columns (even leading
-// dimensions) and handles full tiles only; the < 128-row tail goes through the v1 kernel.
+// dimensions); a partial last tile is completed with plain stores by the producer warp.
 constexpr int TR = 128;          // rows per tile
 constexpr int NCW = 8;           // consumer warps
 constexpr int NCT = NCW * 32;    // consumer threads
 
 template <int BT, int CPW>
-__global__ void __launch_bounds__(NCT + 32) ortho_sweep_tma_kernel(SweepArgs a, int nstages) {
+__global__ void __launch_bounds__(NCT + 32) ortho_sweep_tma_kernel(const __grid_constant__ SweepArgs a, int nstages) {
    extern __shared__ __align__(128) unsigned char smraw[];
    const int k = a.q + a.mv;
    const int kc = k + a.b;
@@ -214,34 +216,47 @@ __global__ void __launch_bounds__(NCT + 32) ortho_sweep_tma_kernel(SweepArgs a, 
    if (a.do_update) {
       for (int i = tid; i < k * BT; i += NCT + 32) {
          int j = i % k, c = i / k;
-         Cs[j * BT + c] = (c < a.b) ? a.Cdev[j + (size_t)c * k] : 0.0;
+         Cs[j * BT + c] = (c < a.b) ? (a.coef_inline ? a.coef : a.Cdev)[j + (size_t)c * k] : 0.0;
       }
       for (int i = tid; i < BT * BT; i += NCT + 32) {
          int r = i % BT, c = i / BT;
          double y = (r == c) ? 1.0 : 0.0;
-         if (a.has_Y) y = (r < a.b && c < a.b) ? a.Ydev[r + c * BT] : 0.0;
+         if (a.has_Y) y = (r < a.b && c < a.b) ? (a.coef_inline ? a.coef + (size_t)k * BT : a.Ydev)[r + c * BT] : 0.0;
          Ys[r * BT + c] = y;
       }
    }
    __syncthreads();
 
-   const int64_t ntiles = a.n / TR;  // full tiles only
+   const int64_t ntiles = (a.n + TR - 1) / TR;  // the last tile may be partial
    if (warp == NCW) {
       // ------------------------------ producer warp ------------------------------
       int s = 0;
       uint32_t ph = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-         if (lane == 0) {
-            pbtma::mbar_wait(&empty[s], ph ^ 1);
-            pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(kc * TR * sizeof(double)));
-         }
+         if (lane == 0) pbtma::mbar_wait(&empty[s], ph ^ 1);
          __syncwarp();
          double *dst = stage0 + (size_t)s * kc * TR;
          const int64_t r0 = tile * TR;
-         for (int c = lane; c < kc; c += 32) {
-            const double *src = c < k ? col_ptr(a, c) + r0 : a.X + (size_t)(c - k) * a.ldx + r0;
-            pbtma::bulk_g2s(dst + (size_t)c * TR, src, TR * sizeof(double), &full[s]);
+         const int rows = (int)((a.n - r0) < TR ? (a.n - r0) : TR);
+         const int rows_even = rows & ~1;
+         if (rows < TR) {
+            // partial tile: bulk copies take the even part, the odd last row and the zero
+            // padding are written with plain stores (padded rows then contribute nothing)
+            for (int c = lane; c < kc; c += 32) {
+               const double *src = c < k ? col_ptr(a, c) + r0 : a.X + (size_t)(c - k) * a.ldx + r0;
+               double *d = dst + (size_t)c * TR;
+               for (int rr = rows_even; rr < TR; rr++) d[rr] = rr < rows ? src[rr] : 0.0;
+            }
+            __syncwarp();
          }
+         if (lane == 0)
+            pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(kc * rows_even * sizeof(double)));
+         __syncwarp();
+         if (rows_even > 0)
+            for (int c = lane; c < kc; c += 32) {
+               const double *src = c < k ? col_ptr(a, c) + r0 : a.X + (size_t)(c - k) * a.ldx + r0;
+               pbtma::bulk_g2s(dst + (size_t)c * TR, src, rows_even * sizeof(double), &full[s]);
+            }
          if (++s == nstages) s = 0, ph ^= 1;
       }
       return;
@@ -306,7 +321,7 @@ __global__ void __launch_bounds__(NCT + 32) ortho_sweep_tma_kernel(SweepArgs a, 
             const int64_t r = tile * TR + row1;
 #pragma unroll
             for (int c = 0; c < BT; c++) {
-               if (c < a.b) a.X[r + (size_t)c * a.ldx] = x[c];
+               if (c < a.b && r < a.n) a.X[r + (size_t)c * a.ldx] = x[c];
                xs[(size_t)c * TR + row1] = x[c];
             }
          }
@@ -416,7 +431,7 @@ int dispatch_cpw_tma(pb200_ctx *ctx, const SweepArgs &a, int cpw, int &grid, siz
 // The roles are chained with mbarriers only (no CTA-wide barrier): the update of tile t+1
 // overlaps the Gram of tile t, and the bulk copies of tiles t+2.. are in flight meanwhile.
 template <int BT, int CPW>
-__global__ void __launch_bounds__(NCT + 32) ortho_sweep_ws_kernel(SweepArgs a, int nstages) {
+__global__ void __launch_bounds__(NCT + 32) ortho_sweep_ws_kernel(const __grid_constant__ SweepArgs a, int nstages) {
    extern __shared__ __align__(128) unsigned char smraw[];
    const int k = a.q + a.mv;
    const int kc = k + a.b;
@@ -446,12 +461,12 @@ __global__ void __launch_bounds__(NCT + 32) ortho_sweep_ws_kernel(SweepArgs a, i
    if (a.do_update) {
       for (int i = tid; i < k * BT; i += NCT + 32) {
          int j = i % k, c = i / k;
-         Cs[j * BT + c] = (c < a.b) ? a.Cdev[j + (size_t)c * k] : 0.0;
+         Cs[j * BT + c] = (c < a.b) ? (a.coef_inline ? a.coef : a.Cdev)[j + (size_t)c * k] : 0.0;
       }
       for (int i = tid; i < BT * BT; i += NCT + 32) {
          int r = i % BT, c = i / BT;
          double y = (r == c) ? 1.0 : 0.0;
-         if (a.has_Y) y = (r < a.b && c < a.b) ? a.Ydev[r + c * BT] : 0.0;
+         if (a.has_Y) y = (r < a.b && c < a.b) ? (a.coef_inline ? a.coef + (size_t)k * BT : a.Ydev)[r + c * BT] : 0.0;
          Ys[r * BT + c] = y;
       }
    }
@@ -751,24 +766,34 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
    a.xx = xx ? 1 : 0;
    if (!a.do_update && !a.do_gram) return 0;
 
-   // stage C (k x b, compacted to ld k) and Y (b x b, ld BT) through the pinned buffer
+   // C (k x b, compacted to ld k) and Y (b x b, ld BT): inside the kernel parameters when they fit
+   // (no H2D copy in front of the launch), else staged through the pinned buffer
    if (a.do_update) {
       size_t need = (size_t)k * BT + BT * BT;
-      PB_CHK(pb_ensure_small(ctx, need));
-      // the pinned staging buffer may still feed an earlier async copy
-      PB_CUDA(cudaStreamSynchronize(ctx->stream));
-      double *hp = ctx->h_pinned;
+      double *hp;
+      if (need <= PB_COEF_MAX && ctx->coef_inline) {
+         a.coef_inline = 1;
+         hp = a.coef;
+      } else {
+         PB_CHK(pb_ensure_small(ctx, need));
+         // the pinned staging buffer may still feed an earlier async copy
+         PB_CUDA(cudaStreamSynchronize(ctx->stream));
+         hp = ctx->h_pinned;
+      }
       for (int c = 0; c < b; c++)
          for (int j = 0; j < k; j++) hp[j + (size_t)c * k] = C_host ? C_host[j + (size_t)c * ldc] : 0.0;
+      for (size_t i = (size_t)k * b; i < (size_t)k * BT; i++) hp[i] = 0.0;
       double *hy = hp + (size_t)k * BT;
       for (int i = 0; i < BT * BT; i++) hy[i] = 0.0;
       if (Y_host)
          for (int c = 0; c < b; c++)
             for (int r = 0; r < b; r++) hy[r + c * BT] = Y_host[r + (size_t)c * ldy];
-      PB_CUDA(cudaMemcpyAsync(ctx->d_small, hp, need * sizeof(double), cudaMemcpyHostToDevice,
-            ctx->stream));
-      a.Cdev = ctx->d_small;
-      a.Ydev = ctx->d_small + (size_t)k * BT;
+      if (!a.coef_inline) {
+         PB_CUDA(cudaMemcpyAsync(ctx->d_small, hp, need * sizeof(double), cudaMemcpyHostToDevice,
+               ctx->stream));
+         a.Cdev = ctx->d_small;
+         a.Ydev = ctx->d_small + (size_t)k * BT;
+      }
    }
 
    const int rows = k + (a.xx ? b : 0);
@@ -803,13 +828,12 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
    int grid = 0, nparts = 0, rc = 0;
    int ps = pb_prof_begin(ctx, PB_K_ORTHO);
    if (tma_ok) {
-      // v3 (warp-specialised) when its column split fits the register budget; it handles a
-      // partial last tile itself, the v2 kernel leaves the < 128-row tail to one v1 CTA
+      // v3 (warp-specialised, opt-in) when its column split fits the register budget
       const int ngw = a.do_gram ? NCW - (a.do_update ? 2 : 0) : 0;
       const int cpw_ws = ngw > 0 ? (k + ngw - 1) / ngw : 1;
       const bool ws = ctx->use_ws && cpw_ws <= 10 && (ngw == 0 || 2 * ngw >= b);
-      const int64_t ntiles = ws ? (n + TR - 1) / TR : n / TR;
-      const int64_t n_main = ws ? n : ntiles * TR;
+      const int64_t ntiles = (n + TR - 1) / TR;  // both kernels handle a partial last tile
+      const int64_t n_main = n;
       grid = (int)(ntiles < (int64_t)ctx->num_sms * ctas_per_sm ? ntiles : (int64_t)ctx->num_sms * ctas_per_sm);
       const int tail = n_main < n ? 1 : 0;
       if (a.do_gram) {

@@ -23,6 +23,9 @@
       if (r_ != 0) return r_;   \
    } while (0)
 
+// capacity (doubles) of the coefficient block embedded in the kernel-argument structs
+#define PB_COEF_MAX 1024
+
 struct pb200_ctx {
    int device;
    int num_sms;
@@ -48,6 +51,7 @@ struct pb200_ctx {
    int use_tma_spmm;      // persistent bulk-copy SpMM (v2)
    int use_wide;          // v3 wide VWXR kernel for the restart sweep
    int vwxr_cand_tma;     // 1: TMA-staged (v2) kernel also for the candidates sweep
+   int coef_inline;       // small coefficient matrices travel as kernel parameters (no H2D copy)
    int use_narrow;        // v3 narrow VWXR kernel for the candidates sweep (default off: the LDG kernel is faster)
    int ortho_2cta;        // prefer 2 CTAs/SM x 2 stages over 1 CTA/SM x 4 stages in the ortho sweep
    int use_tma;           // 1: TMA-staged kernels where eligible (default), 0: LDG kernels only

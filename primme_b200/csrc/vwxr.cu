@@ -30,6 +30,7 @@ struct VwxrArgs {
    int m, nh;
    const double *hdev;      // m x nh, column stride m
    const double *thetadev;  // nh
+   int coef_inline;         // 1: h and theta travel in `coef` below (kernel parameter space)
    pb200_cols X[3];
    pb200_cols Wo;
    pb200_cols R;
@@ -38,10 +39,11 @@ struct VwxrArgs {
    int nG, nH;
    int need_y;              // whether W*h is needed at all
    double *partials;        // [grid][cnt] : Rnorms(nR) | rnorms(nr) | G(nG*nG) | H(nH*nH)
+   double coef[PB_COEF_MAX];  // [h (m x nh) | theta (nh)] when coef_inline
 };
 
 template <int NT>
-__global__ void __launch_bounds__(VT) vwxr_kernel(VwxrArgs a) {
+__global__ void __launch_bounds__(VT) vwxr_kernel(const __grid_constant__ VwxrArgs a) {
    extern __shared__ double smem[];
    double *hs = smem;                          // m * NT   ([k][c], zero padded)
    double *th = hs + (size_t)a.m * NT;         // NT
@@ -52,9 +54,9 @@ __global__ void __launch_bounds__(VT) vwxr_kernel(VwxrArgs a) {
 
    for (int i = tid; i < a.m * NT; i += VT) {
       int k = i / NT, c = i % NT;
-      hs[i] = c < a.nh ? a.hdev[k + (size_t)c * a.m] : 0.0;
+      hs[i] = c < a.nh ? (a.coef_inline ? a.coef : a.hdev)[k + (size_t)c * a.m] : 0.0;
    }
-   for (int i = tid; i < NT; i += VT) th[i] = i < a.nh ? a.thetadev[i] : 0.0;
+   for (int i = tid; i < NT; i += VT) th[i] = i < a.nh ? (a.coef_inline ? a.coef + (size_t)a.m * a.nh : a.thetadev)[i] : 0.0;
    __syncthreads();
 
    const int nR = a.R.ptr ? a.R.ce - a.R.cb : 0;
@@ -196,7 +198,10 @@ __global__ void __launch_bounds__(VT) vwxr_kernel(VwxrArgs a) {
    for (int c = 0; c < NT; c++) {
       bool isR = a.R.ptr && c >= a.R.cb && c < a.R.ce;
       bool isr = !isR && c >= a.rb && c < a.re;
-      if (!(isR || isr)) continue;  // uniform across the CTA
+      if (!(isR || isr)) {  // uniform across the CTA; unused slots are still defined
+         if (tid == 0 && c < nn) out[c] = 0.0;
+         continue;
+      }
       double v = nrm[c];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -246,7 +251,7 @@ __global__ void __launch_bounds__(VT) vwxr_kernel(VwxrArgs a) {
 // are parked in shared memory for the residual (needs both) and for the G/H blocks.  Outputs are
 // written after the whole tile has been read, so in-place restart (V <- V*h) stays safe.
 template <int NTH, int TPR>
-__global__ void __launch_bounds__(256 + 32) vwxr_tma_kernel(VwxrArgs a, int nstages) {
+__global__ void __launch_bounds__(256 + 32) vwxr_tma_kernel(const __grid_constant__ VwxrArgs a, int nstages) {
    constexpr int TR = 256 / TPR;        // rows per tile
    constexpr int NSUB = TPR / 2;        // column groups per operand
    constexpr int NT = NTH * NSUB;       // padded number of h columns
@@ -270,9 +275,9 @@ __global__ void __launch_bounds__(256 + 32) vwxr_tma_kernel(VwxrArgs a, int nsta
    }
    for (int i = tid; i < m * NT; i += 288) {
       int k = i / NT, c = i % NT;
-      hs[i] = c < a.nh ? a.hdev[k + (size_t)c * m] : 0.0;
+      hs[i] = c < a.nh ? (a.coef_inline ? a.coef : a.hdev)[k + (size_t)c * m] : 0.0;
    }
-   for (int i = tid; i < NT; i += 288) th[i] = i < a.nh ? a.thetadev[i] : 0.0;
+   for (int i = tid; i < NT; i += 288) th[i] = i < a.nh ? (a.coef_inline ? a.coef + (size_t)a.m * a.nh : a.thetadev)[i] : 0.0;
    __syncthreads();
 
    const int64_t ntiles = a.n / TR;
@@ -467,7 +472,7 @@ __device__ __forceinline__ void st2(double *p, double v0, double v1, int64_t r, 
 // (V*h and W*h) in registers, 16-byte shared-memory loads, residual and norms formed in-thread,
 // 16-byte global stores.  No exchange between threads until the final norm reduction.
 template <int NTH>
-__global__ void __launch_bounds__(256 + 32) vwxr_narrow_kernel(VwxrArgs a, int nstages) {
+__global__ void __launch_bounds__(256 + 32) vwxr_narrow_kernel(const __grid_constant__ VwxrArgs a, int nstages) {
    constexpr int TR = 128;
    extern __shared__ __align__(128) unsigned char smraw[];
    const int m = a.m;
@@ -492,9 +497,9 @@ __global__ void __launch_bounds__(256 + 32) vwxr_narrow_kernel(VwxrArgs a, int n
    }
    for (int i = tid; i < m * NTH; i += 288) {
       int k = i / NTH, c = i % NTH;
-      hs[i] = c < a.nh ? a.hdev[k + (size_t)c * m] : 0.0;
+      hs[i] = c < a.nh ? (a.coef_inline ? a.coef : a.hdev)[k + (size_t)c * m] : 0.0;
    }
-   for (int i = tid; i < NTH; i += 288) th[i] = i < a.nh ? a.thetadev[i] : 0.0;
+   for (int i = tid; i < NTH; i += 288) th[i] = i < a.nh ? (a.coef_inline ? a.coef + (size_t)a.m * a.nh : a.thetadev)[i] : 0.0;
    __syncthreads();
 
    const int64_t ntiles = (a.n + TR - 1) / TR;  // the last tile may be partial
@@ -629,7 +634,7 @@ int launch_vwxr_narrow(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem
 //   * Gram phase per group: one 4x4 block of G (upper) or H per thread, row pairs visited in a
 //     lane-rotated order (conflict-free 16-byte loads), accumulators live across all tiles.
 template <int NTH, int NG>
-__global__ void __launch_bounds__(256 + 32) vwxr_wide_kernel(VwxrArgs a, int nstages, int park_cols) {
+__global__ void __launch_bounds__(256 + 32) vwxr_wide_kernel(const __grid_constant__ VwxrArgs a, int nstages, int park_cols) {
    constexpr int TR = 64;
    constexpr int NT = NTH * NG;
    constexpr int NTG = 8 / NG;      // tile groups
@@ -654,9 +659,9 @@ __global__ void __launch_bounds__(256 + 32) vwxr_wide_kernel(VwxrArgs a, int nst
    }
    for (int i = tid; i < m * NT; i += 288) {
       int k = i / NT, c = i % NT;
-      hs[i] = c < a.nh ? a.hdev[k + (size_t)c * m] : 0.0;
+      hs[i] = c < a.nh ? (a.coef_inline ? a.coef : a.hdev)[k + (size_t)c * m] : 0.0;
    }
-   for (int i = tid; i < NT; i += 288) th[i] = i < a.nh ? a.thetadev[i] : 0.0;
+   for (int i = tid; i < NT; i += 288) th[i] = i < a.nh ? (a.coef_inline ? a.coef + (size_t)a.m * a.nh : a.thetadev)[i] : 0.0;
    __syncthreads();
 
    const int64_t ntiles = (a.n + TR - 1) / TR;  // the last tile may be partial
@@ -926,19 +931,27 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
       if (gb * gb + hb * hb > 768) return PB200_ERR_ARG;
    }
 
-   // stage h (compacted to ld m) and theta
+   // h (compacted to ld m) and theta: inside the kernel parameters when they fit, else staged
    size_t need = (size_t)m * nh + nh;
    PB_CHK(pb_ensure_small(ctx, need > (size_t)cnt ? need : (size_t)cnt));
-   // the pinned staging buffer may still feed an earlier async copy
-   PB_CUDA(cudaStreamSynchronize(ctx->stream));
-   double *hp = ctx->h_pinned;
+   double *hp;
+   if (need <= PB_COEF_MAX && ctx->coef_inline) {
+      a.coef_inline = 1;
+      hp = a.coef;
+   } else {
+      // the pinned staging buffer may still feed an earlier async copy
+      PB_CUDA(cudaStreamSynchronize(ctx->stream));
+      hp = ctx->h_pinned;
+   }
    for (int c = 0; c < nh; c++)
       for (int k = 0; k < m; k++) hp[k + (size_t)c * m] = h_host[k + (size_t)c * ldh];
    for (int c = 0; c < nh; c++) hp[(size_t)m * nh + c] = theta_host ? theta_host[c] : 0.0;
-   PB_CUDA(cudaMemcpyAsync(
-         ctx->d_small, hp, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-   a.hdev = ctx->d_small;
-   a.thetadev = ctx->d_small + (size_t)m * nh;
+   if (!a.coef_inline) {
+      PB_CUDA(cudaMemcpyAsync(
+            ctx->d_small, hp, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      a.hdev = ctx->d_small;
+      a.thetadev = ctx->d_small + (size_t)m * nh;
+   }
 
    // algorithmic bytes: V (and W) read once + every output column written once
    double ocols = 0;
@@ -988,7 +1001,8 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
    // ---- v3 (wide) plan: restart sweep ----
    int wide_nst = 0, wide_nth = 0, wide_ng = 0, wide_park = 0;
    size_t wide_shm = 0;
-   if (ctx->use_tma_vwxr && ctx->use_wide && narrow_nst < 2 && nh <= 48 && m > 0 && n >= 4 * 64 &&
+   const bool cand_shape = nh <= 8 && a.nG == 0 && a.nH == 0;  // candidates sweep: LDG kernel (fastest measured)
+   if (ctx->use_tma_vwxr && ctx->use_wide && !cand_shape && narrow_nst < 2 && nh <= 48 && m > 0 && n >= 4 * 64 &&
          (((uintptr_t)V) & 15) == 0 && (((uintptr_t)W) & 15) == 0 && ld % 2 == 0) {
       bool ok = true;
       auto al = [](const pb200_cols &c) { return !c.ptr || ((((uintptr_t)c.ptr) & 15) == 0 && c.ld % 2 == 0); };
@@ -1018,8 +1032,6 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
       grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
       PB_CHK(pb_ensure_partials(ctx, (size_t)grid * (cnt > 0 ? cnt : 1) + 16));
       a.partials = ctx->d_partials;
-      if (cnt > 0)
-         PB_CUDA(cudaMemsetAsync(ctx->d_partials, 0, (size_t)grid * cnt * sizeof(double), ctx->stream));
       if (nh <= 4) rc = launch_vwxr_narrow<4>(ctx, a, grid, narrow_shm, narrow_nst);
       else rc = launch_vwxr_narrow<8>(ctx, a, grid, narrow_shm, narrow_nst);
       nparts = grid;
@@ -1030,8 +1042,6 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
       grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
       PB_CHK(pb_ensure_partials(ctx, (size_t)grid * NTG * (cnt > 0 ? cnt : 1) + 16));
       a.partials = ctx->d_partials;
-      if (cnt > 0)
-         PB_CUDA(cudaMemsetAsync(ctx->d_partials, 0, (size_t)grid * NTG * cnt * sizeof(double), ctx->stream));
 #define VW3(NTH_, NG_) \
    if (wide_nth == NTH_ && wide_ng == NG_) rc = launch_vwxr_wide<NTH_, NG_>(ctx, a, grid, wide_shm, wide_nst, wide_park);
       VW3(8, 1) VW3(8, 2) VW3(12, 2) VW3(8, 4) VW3(12, 4)
@@ -1044,8 +1054,6 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
       const int tail = n_main < n ? 1 : 0;
       PB_CHK(pb_ensure_partials(ctx, (size_t)(grid + tail) * (cnt > 0 ? cnt : 1) + 16));
       a.partials = ctx->d_partials;
-      if (cnt > 0)
-         PB_CUDA(cudaMemsetAsync(ctx->d_partials, 0, (size_t)(grid + tail) * cnt * sizeof(double), ctx->stream));
       VwxrArgs am = a;
       am.n = n_main;
 #define VW2(NTH_, TPR_) \
@@ -1089,8 +1097,8 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
       if (cnt > 0) {
          PB_CHK(pb_ensure_partials(ctx, (size_t)grid * cnt));
          a.partials = ctx->d_partials;
-         // G partial slots below the diagonal blocks are written by mirroring; zero everything
-         PB_CUDA(cudaMemsetAsync(ctx->d_partials, 0, (size_t)grid * cnt * sizeof(double), ctx->stream));
+         // every slot is written by the kernel (unused norm slots as zeros, G below the diagonal by
+         // mirroring): no memset in front of the launch
       } else {
          PB_CHK(pb_ensure_partials(ctx, 16));
          a.partials = ctx->d_partials;

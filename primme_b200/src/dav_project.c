@@ -27,7 +27,7 @@ int pb_reduce_panel(pb_solver *S, double *P, int rows, int cols, int ldp) {
 
 /* H(0:m, numCols:m) = V(:,0:m)' * W(:,numCols:m), m = numCols + blockSize
  * (reference update_projection.c:99-102; only the upper triangle is used afterwards). */
-int pb_update_projection(pb_solver *S, int numCols, int blockSize) {
+static int update_projection_impl(pb_solver *S, int numCols, int blockSize) {
    if (blockSize <= 0) return 0;
    const int m = numCols + blockSize;
    double *Hcol = &S->H[(size_t)S->maxBasis * numCols];
@@ -44,7 +44,7 @@ int pb_update_projection(pb_solver *S, int numCols, int blockSize) {
 
 /* Solve the projected (generalized) eigenproblem and order the pairs by primme.target
  * (reference solve_projection.c:188-331). */
-int pb_solve_H(pb_solver *S, const double *H, int ldH, int n, const double *VtBVblk, int ldVtBV,
+static int solve_H_impl(pb_solver *S, const double *H, int ldH, int n, const double *VtBVblk, int ldVtBV,
       double *hVecs, int ldhVecs, double *hVals, int numConverged, int updateStats) {
    primme_params *primme = S->primme;
    if (n == 0) return 0;
@@ -143,4 +143,20 @@ int pb_map_vecs(const double *V, int m, int nV, int ldV, const double *W, int n0
    }
    free(Vnorms), free(ip);
    return 0;
+}
+
+/* timed entry points (the reference times neither phase; the PB200_DEBUG report does) */
+int pb_update_projection(pb_solver *S, int numCols, int blockSize) {
+   const double t0 = hl_wtime();
+   int rc = update_projection_impl(S, numCols, blockSize);
+   S->tProj += hl_wtime() - t0;
+   return rc;
+}
+
+int pb_solve_H(pb_solver *S, const double *H, int ldH, int n, const double *VtBVblk, int ldVtBV,
+      double *hVecs, int ldhVecs, double *hVals, int numConverged, int updateStats) {
+   const double t0 = hl_wtime();
+   int rc = solve_H_impl(S, H, ldH, n, VtBVblk, ldVtBV, hVecs, ldhVecs, hVals, numConverged, updateStats);
+   S->tSolveH += hl_wtime() - t0;
+   return rc;
 }

@@ -725,8 +725,12 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
 
          hl_permute_cols(S->prevhVecs, basisSize, nprevhVecs, ldh, map);
 
-         CHK(pb_restart(S, basisSize, &blockSize, evals, resNorms, &numConverged, &numLocked,
-               nprevhVecs, numGuesses, &basisSize, &targetShiftIndex, &restartsSinceReset));
+         {
+            const double tr0 = hl_wtime();
+            CHK(pb_restart(S, basisSize, &blockSize, evals, resNorms, &numConverged, &numLocked,
+                  nprevhVecs, numGuesses, &basisSize, &targetShiftIndex, &restartsSinceReset));
+            S->tRestart += hl_wtime() - tr0;
+         }
          restartsSinceReset++;
 
          /* feed remaining initial guesses into the basis (main_iter.c:1098-1168) */

@@ -478,6 +478,14 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
    pb200_ctx_sync(S->dev);
    pb_registry_set_solver(primme, NULL);
    primme->stats.elapsedTime = hl_wtime() - S->t0;
+   if (getenv("PB200_DEBUG") && primme->procID == 0)
+      fprintf(stderr,
+            "PRIMME-B200: phases (s): elapsed %.4f matvec %.4f ortho %.4f vwxr %.4f projection %.4f solveH %.4f "
+            "restart %.4f | outer %lld restarts %lld matvecs %lld\n",
+            primme->stats.elapsedTime, primme->stats.timeMatvec, primme->stats.timeOrtho,
+            primme->stats.timeDense, S->tProj, S->tSolveH, S->tRestart,
+            (long long)primme->stats.numOuterIterations, (long long)primme->stats.numRestarts,
+            (long long)primme->stats.numMatvecs);
    if (!own_ctx) {
       pb200_free(S->dev, S->V), pb200_free(S->dev, S->W);
       if (own_evecs) pb200_free(S->dev, S->evecs);

@@ -41,6 +41,7 @@ typedef struct pb_solver {
    double *hVals, *prevRitzVals, *blockNorms, *basisNorms;
    int *flags, *map, *iev, *perm, *lockedFlags;
    double t0;
+   double tProj, tSolveH, tRestart; /* wall-clock of the phases the reference does not time (PB200_DEBUG report) */
    int numPrevRitzVals;
 } pb_solver;
 

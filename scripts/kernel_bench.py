@@ -104,6 +104,37 @@ def main():
         return lib.pb200_dvwxr(ctx, n, V, W, mmax, ld, h.ctypes.data, mmax, rs + b, theta.ctypes.data, C.byref(o))
 
     measure(f"vwxr restart m={mmax} rs={rs} b={b}", 2, restart)
+    # host-visible latency of one call at a tiny size (launch + panel reduction + delivery): the
+    # fixed cost of every synchronisation point of the outer iteration
+    import time
+    nt = 1024
+
+    def wall(name, fn, reps=300):
+        for _ in range(20):
+            fn()
+        lib.pb200_ctx_sync(ctx)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        lib.pb200_ctx_sync(ctx)
+        us = (time.perf_counter() - t0) / reps * 1e6
+        results[name] = dict(wall_us=us)
+        print(f"{name:34s} {us:9.1f} us wall per call (n={nt})", flush=True)
+
+    wall("latency gram", lambda: lib.pb200_dortho_sweep(
+        ctx, nt, None, 0, ld, V, m, ld, off(V, m), b, ld, None, 0, None, 0, 1, P.ctypes.data, mmax + b + 1))
+    wall("latency update+gram", lambda: lib.pb200_dortho_sweep(
+        ctx, nt, None, 0, ld, V, m, ld, off(V, m), b, ld, Cm.ctypes.data, mmax + 1, Y.ctypes.data, b, 1,
+        P.ctypes.data, mmax + b + 1))
+
+    def cand_small():
+        o = api.VwxrOut()
+        o.X[0] = api.VwxrCols(off(V, m).value, ld, 0, b)
+        o.R = api.VwxrCols(off(W, m).value, ld, 0, b)
+        o.Rnorms_host = Rn.ctypes.data
+        return lib.pb200_dvwxr(ctx, nt, V, W, m, ld, h.ctypes.data, mmax, b, theta.ctypes.data, C.byref(o))
+
+    wall("latency vwxr candidates", cand_small)
     print(json.dumps(results))
 
 

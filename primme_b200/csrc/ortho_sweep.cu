@@ -33,7 +33,6 @@ struct SweepArgs {
    const double *Ydev;  // BT x BT, column stride BT
    int coef_inline;     // 1: C and Y travel in `coef` below (kernel parameter space), no H2D copy
    double *partials;    // [gridDim.x][(k + xx*b) * b]
-   double coef[PB_COEF_MAX];  // [C (k x BT) | Y (BT x BT)] when coef_inline
 };
 
 __device__ __forceinline__ const double *col_ptr(const SweepArgs &a, int j) {
@@ -41,7 +40,7 @@ __device__ __forceinline__ const double *col_ptr(const SweepArgs &a, int j) {
 }
 
 template <int BT, int CPW>
-__global__ void __launch_bounds__(TILE) ortho_sweep_kernel(const __grid_constant__ SweepArgs a) {
+__global__ void __launch_bounds__(TILE) ortho_sweep_kernel(SweepArgs a, const __grid_constant__ PbCoef coef) {
    extern __shared__ double smem[];
    const int k = a.q + a.mv;
    double *Cs = smem;                 // k * BT
@@ -52,12 +51,12 @@ __global__ void __launch_bounds__(TILE) ortho_sweep_kernel(const __grid_constant
    if (a.do_update) {
       for (int i = tid; i < k * BT; i += TILE) {
          int j = i % k, c = i / k;
-         Cs[j * BT + c] = (c < a.b) ? (a.coef_inline ? a.coef : a.Cdev)[j + (size_t)c * k] : 0.0;
+         Cs[j * BT + c] = (c < a.b) ? (a.coef_inline ? coef.v : a.Cdev)[j + (size_t)c * k] : 0.0;
       }
       for (int i = tid; i < BT * BT; i += TILE) {
          int r = i % BT, c = i / BT;
          double y = (r == c) ? 1.0 : 0.0;
-         if (a.has_Y) y = (r < a.b && c < a.b) ? (a.coef_inline ? a.coef + (size_t)k * BT : a.Ydev)[r + c * BT] : 0.0;
+         if (a.has_Y) y = (r < a.b && c < a.b) ? (a.coef_inline ? coef.v + (size_t)k * BT : a.Ydev)[r + c * BT] : 0.0;
          Ys[r * BT + c] = y;
       }
    }
@@ -193,7 +192,7 @@ constexpr int NCW = 8;           // consumer warps
 constexpr int NCT = NCW * 32;    // consumer threads
 
 template <int BT, int CPW>
-__global__ void __launch_bounds__(NCT + 32) ortho_sweep_tma_kernel(const __grid_constant__ SweepArgs a, int nstages) {
+__global__ void __launch_bounds__(NCT + 32) ortho_sweep_tma_kernel(SweepArgs a, const __grid_constant__ PbCoef coef, int nstages) {
    extern __shared__ __align__(128) unsigned char smraw[];
    const int k = a.q + a.mv;
    const int kc = k + a.b;
@@ -216,12 +215,12 @@ __global__ void __launch_bounds__(NCT + 32) ortho_sweep_tma_kernel(const __grid_
    if (a.do_update) {
       for (int i = tid; i < k * BT; i += NCT + 32) {
          int j = i % k, c = i / k;
-         Cs[j * BT + c] = (c < a.b) ? (a.coef_inline ? a.coef : a.Cdev)[j + (size_t)c * k] : 0.0;
+         Cs[j * BT + c] = (c < a.b) ? (a.coef_inline ? coef.v : a.Cdev)[j + (size_t)c * k] : 0.0;
       }
       for (int i = tid; i < BT * BT; i += NCT + 32) {
          int r = i % BT, c = i / BT;
          double y = (r == c) ? 1.0 : 0.0;
-         if (a.has_Y) y = (r < a.b && c < a.b) ? (a.coef_inline ? a.coef + (size_t)k * BT : a.Ydev)[r + c * BT] : 0.0;
+         if (a.has_Y) y = (r < a.b && c < a.b) ? (a.coef_inline ? coef.v + (size_t)k * BT : a.Ydev)[r + c * BT] : 0.0;
          Ys[r * BT + c] = y;
       }
    }
@@ -392,10 +391,16 @@ int launch_sweep_tma(pb200_ctx *ctx, const SweepArgs &a, int &grid, size_t shmem
       PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, NCT + 32, shmem));
       cached_occ = o < 1 ? 1 : o;
       cached_shmem = shmem;
+      if (getenv("PB200_DEBUG")) {
+         cudaFuncAttributes fa;
+         cudaFuncGetAttributes(&fa, kern);
+         fprintf(stderr, "primme_b200: ortho_sweep_tma<%d,%d> dyn smem %zu static %zu regs %d stages %d -> %d CTA/SM\n",
+               BT, CPW, shmem, fa.sharedSizeBytes, fa.numRegs, nstages, cached_occ);
+      }
    }
    const int occ = cached_occ;
    if (grid > occ * ctx->num_sms) grid = occ * ctx->num_sms;
-   kern<<<grid, NCT + 32, shmem, ctx->stream>>>(a, nstages);
+   kern<<<grid, NCT + 32, shmem, ctx->stream>>>(a, ctx->coef, nstages);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
    return 0;
@@ -431,7 +436,7 @@ int dispatch_cpw_tma(pb200_ctx *ctx, const SweepArgs &a, int cpw, int &grid, siz
 // The roles are chained with mbarriers only (no CTA-wide barrier): the update of tile t+1
 // overlaps the Gram of tile t, and the bulk copies of tiles t+2.. are in flight meanwhile.
 template <int BT, int CPW>
-__global__ void __launch_bounds__(NCT + 32) ortho_sweep_ws_kernel(const __grid_constant__ SweepArgs a, int nstages) {
+__global__ void __launch_bounds__(NCT + 32) ortho_sweep_ws_kernel(SweepArgs a, const __grid_constant__ PbCoef coef, int nstages) {
    extern __shared__ __align__(128) unsigned char smraw[];
    const int k = a.q + a.mv;
    const int kc = k + a.b;
@@ -461,12 +466,12 @@ __global__ void __launch_bounds__(NCT + 32) ortho_sweep_ws_kernel(const __grid_c
    if (a.do_update) {
       for (int i = tid; i < k * BT; i += NCT + 32) {
          int j = i % k, c = i / k;
-         Cs[j * BT + c] = (c < a.b) ? (a.coef_inline ? a.coef : a.Cdev)[j + (size_t)c * k] : 0.0;
+         Cs[j * BT + c] = (c < a.b) ? (a.coef_inline ? coef.v : a.Cdev)[j + (size_t)c * k] : 0.0;
       }
       for (int i = tid; i < BT * BT; i += NCT + 32) {
          int r = i % BT, c = i / BT;
          double y = (r == c) ? 1.0 : 0.0;
-         if (a.has_Y) y = (r < a.b && c < a.b) ? (a.coef_inline ? a.coef + (size_t)k * BT : a.Ydev)[r + c * BT] : 0.0;
+         if (a.has_Y) y = (r < a.b && c < a.b) ? (a.coef_inline ? coef.v + (size_t)k * BT : a.Ydev)[r + c * BT] : 0.0;
          Ys[r * BT + c] = y;
       }
    }
@@ -690,7 +695,7 @@ int launch_sweep_ws(pb200_ctx *ctx, const SweepArgs &a, int &grid, size_t shmem,
       cached_shmem = shmem;
    }
    if (grid > cached_occ * ctx->num_sms) grid = cached_occ * ctx->num_sms;
-   kern<<<grid, NCT + 32, shmem, ctx->stream>>>(a, nstages);
+   kern<<<grid, NCT + 32, shmem, ctx->stream>>>(a, ctx->coef, nstages);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
    return 0;
@@ -721,7 +726,7 @@ int launch_sweep(pb200_ctx *ctx, const SweepArgs &a, int grid, size_t shmem) {
       PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
       attr_shmem = shmem;
    }
-   kern<<<grid, TILE, shmem, ctx->stream>>>(a);
+   kern<<<grid, TILE, shmem, ctx->stream>>>(a, ctx->coef);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
    return 0;
@@ -773,7 +778,7 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
       double *hp;
       if (need <= PB_COEF_MAX && ctx->coef_inline) {
          a.coef_inline = 1;
-         hp = a.coef;
+         hp = ctx->coef.v;
       } else {
          PB_CHK(pb_ensure_small(ctx, need));
          // the pinned staging buffer may still feed an earlier async copy

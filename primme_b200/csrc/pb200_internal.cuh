@@ -24,7 +24,16 @@
    } while (0)
 
 // capacity (doubles) of the coefficient block embedded in the kernel-argument structs
+#ifndef PB_COEF_MAX
 #define PB_COEF_MAX 1024
+#endif
+
+// small coefficient matrices (C|Y of the ortho update, h|theta of VWXR) passed by value in the
+// kernel parameter space: a separate __grid_constant__ parameter, so that only this block has its
+// address taken and the scalar arguments stay plain constant-bank operands
+struct PbCoef {
+   double v[PB_COEF_MAX];
+};
 
 struct pb200_ctx {
    int device;
@@ -52,6 +61,7 @@ struct pb200_ctx {
    int use_wide;          // v3 wide VWXR kernel for the restart sweep
    int vwxr_cand_tma;     // 1: TMA-staged (v2) kernel also for the candidates sweep
    int coef_inline;       // small coefficient matrices travel as kernel parameters (no H2D copy)
+   PbCoef coef;           // host staging of that block for the next launch
    int use_narrow;        // v3 narrow VWXR kernel for the candidates sweep (default off: the LDG kernel is faster)
    int ortho_2cta;        // prefer 2 CTAs/SM x 2 stages over 1 CTA/SM x 4 stages in the ortho sweep
    int use_tma;           // 1: TMA-staged kernels where eligible (default), 0: LDG kernels only

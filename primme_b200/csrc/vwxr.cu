@@ -39,11 +39,10 @@ struct VwxrArgs {
    int nG, nH;
    int need_y;              // whether W*h is needed at all
    double *partials;        // [grid][cnt] : Rnorms(nR) | rnorms(nr) | G(nG*nG) | H(nH*nH)
-   double coef[PB_COEF_MAX];  // [h (m x nh) | theta (nh)] when coef_inline
 };
 
 template <int NT>
-__global__ void __launch_bounds__(VT) vwxr_kernel(const __grid_constant__ VwxrArgs a) {
+__global__ void __launch_bounds__(VT) vwxr_kernel(VwxrArgs a, const __grid_constant__ PbCoef coef) {
    extern __shared__ double smem[];
    double *hs = smem;                          // m * NT   ([k][c], zero padded)
    double *th = hs + (size_t)a.m * NT;         // NT
@@ -54,9 +53,9 @@ __global__ void __launch_bounds__(VT) vwxr_kernel(const __grid_constant__ VwxrAr
 
    for (int i = tid; i < a.m * NT; i += VT) {
       int k = i / NT, c = i % NT;
-      hs[i] = c < a.nh ? (a.coef_inline ? a.coef : a.hdev)[k + (size_t)c * a.m] : 0.0;
+      hs[i] = c < a.nh ? (a.coef_inline ? coef.v : a.hdev)[k + (size_t)c * a.m] : 0.0;
    }
-   for (int i = tid; i < NT; i += VT) th[i] = i < a.nh ? (a.coef_inline ? a.coef + (size_t)a.m * a.nh : a.thetadev)[i] : 0.0;
+   for (int i = tid; i < NT; i += VT) th[i] = i < a.nh ? (a.coef_inline ? coef.v + (size_t)a.m * a.nh : a.thetadev)[i] : 0.0;
    __syncthreads();
 
    const int nR = a.R.ptr ? a.R.ce - a.R.cb : 0;
@@ -251,7 +250,7 @@ __global__ void __launch_bounds__(VT) vwxr_kernel(const __grid_constant__ VwxrAr
 // are parked in shared memory for the residual (needs both) and for the G/H blocks.  Outputs are
 // written after the whole tile has been read, so in-place restart (V <- V*h) stays safe.
 template <int NTH, int TPR>
-__global__ void __launch_bounds__(256 + 32) vwxr_tma_kernel(const __grid_constant__ VwxrArgs a, int nstages) {
+__global__ void __launch_bounds__(256 + 32) vwxr_tma_kernel(VwxrArgs a, const __grid_constant__ PbCoef coef, int nstages) {
    constexpr int TR = 256 / TPR;        // rows per tile
    constexpr int NSUB = TPR / 2;        // column groups per operand
    constexpr int NT = NTH * NSUB;       // padded number of h columns
@@ -275,9 +274,9 @@ __global__ void __launch_bounds__(256 + 32) vwxr_tma_kernel(const __grid_constan
    }
    for (int i = tid; i < m * NT; i += 288) {
       int k = i / NT, c = i % NT;
-      hs[i] = c < a.nh ? (a.coef_inline ? a.coef : a.hdev)[k + (size_t)c * m] : 0.0;
+      hs[i] = c < a.nh ? (a.coef_inline ? coef.v : a.hdev)[k + (size_t)c * m] : 0.0;
    }
-   for (int i = tid; i < NT; i += 288) th[i] = i < a.nh ? (a.coef_inline ? a.coef + (size_t)a.m * a.nh : a.thetadev)[i] : 0.0;
+   for (int i = tid; i < NT; i += 288) th[i] = i < a.nh ? (a.coef_inline ? coef.v + (size_t)a.m * a.nh : a.thetadev)[i] : 0.0;
    __syncthreads();
 
    const int64_t ntiles = a.n / TR;
@@ -472,7 +471,7 @@ __device__ __forceinline__ void st2(double *p, double v0, double v1, int64_t r, 
 // (V*h and W*h) in registers, 16-byte shared-memory loads, residual and norms formed in-thread,
 // 16-byte global stores.  No exchange between threads until the final norm reduction.
 template <int NTH>
-__global__ void __launch_bounds__(256 + 32) vwxr_narrow_kernel(const __grid_constant__ VwxrArgs a, int nstages) {
+__global__ void __launch_bounds__(256 + 32) vwxr_narrow_kernel(VwxrArgs a, const __grid_constant__ PbCoef coef, int nstages) {
    constexpr int TR = 128;
    extern __shared__ __align__(128) unsigned char smraw[];
    const int m = a.m;
@@ -497,9 +496,9 @@ __global__ void __launch_bounds__(256 + 32) vwxr_narrow_kernel(const __grid_cons
    }
    for (int i = tid; i < m * NTH; i += 288) {
       int k = i / NTH, c = i % NTH;
-      hs[i] = c < a.nh ? (a.coef_inline ? a.coef : a.hdev)[k + (size_t)c * m] : 0.0;
+      hs[i] = c < a.nh ? (a.coef_inline ? coef.v : a.hdev)[k + (size_t)c * m] : 0.0;
    }
-   for (int i = tid; i < NTH; i += 288) th[i] = i < a.nh ? (a.coef_inline ? a.coef + (size_t)a.m * a.nh : a.thetadev)[i] : 0.0;
+   for (int i = tid; i < NTH; i += 288) th[i] = i < a.nh ? (a.coef_inline ? coef.v + (size_t)a.m * a.nh : a.thetadev)[i] : 0.0;
    __syncthreads();
 
    const int64_t ntiles = (a.n + TR - 1) / TR;  // the last tile may be partial
@@ -615,7 +614,7 @@ int launch_vwxr_narrow(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem
       PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
       attr_shmem = shmem;
    }
-   kern<<<grid, 288, shmem, ctx->stream>>>(a, nstages);
+   kern<<<grid, 288, shmem, ctx->stream>>>(a, ctx->coef, nstages);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
    return 0;
@@ -634,7 +633,7 @@ int launch_vwxr_narrow(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem
 //   * Gram phase per group: one 4x4 block of G (upper) or H per thread, row pairs visited in a
 //     lane-rotated order (conflict-free 16-byte loads), accumulators live across all tiles.
 template <int NTH, int NG>
-__global__ void __launch_bounds__(256 + 32) vwxr_wide_kernel(const __grid_constant__ VwxrArgs a, int nstages, int park_cols) {
+__global__ void __launch_bounds__(256 + 32) vwxr_wide_kernel(VwxrArgs a, const __grid_constant__ PbCoef coef, int nstages, int park_cols) {
    constexpr int TR = 64;
    constexpr int NT = NTH * NG;
    constexpr int NTG = 8 / NG;      // tile groups
@@ -659,9 +658,9 @@ __global__ void __launch_bounds__(256 + 32) vwxr_wide_kernel(const __grid_consta
    }
    for (int i = tid; i < m * NT; i += 288) {
       int k = i / NT, c = i % NT;
-      hs[i] = c < a.nh ? (a.coef_inline ? a.coef : a.hdev)[k + (size_t)c * m] : 0.0;
+      hs[i] = c < a.nh ? (a.coef_inline ? coef.v : a.hdev)[k + (size_t)c * m] : 0.0;
    }
-   for (int i = tid; i < NT; i += 288) th[i] = i < a.nh ? (a.coef_inline ? a.coef + (size_t)a.m * a.nh : a.thetadev)[i] : 0.0;
+   for (int i = tid; i < NT; i += 288) th[i] = i < a.nh ? (a.coef_inline ? coef.v + (size_t)a.m * a.nh : a.thetadev)[i] : 0.0;
    __syncthreads();
 
    const int64_t ntiles = (a.n + TR - 1) / TR;  // the last tile may be partial
@@ -857,7 +856,7 @@ int launch_vwxr_wide(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem, 
       PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
       attr_shmem = shmem;
    }
-   kern<<<grid, 288, shmem, ctx->stream>>>(a, nstages, park_cols);
+   kern<<<grid, 288, shmem, ctx->stream>>>(a, ctx->coef, nstages, park_cols);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
    return 0;
@@ -871,7 +870,7 @@ int launch_vwxr_tma(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem, i
       PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
       attr_shmem = shmem;
    }
-   kern<<<grid, 288, shmem, ctx->stream>>>(a, nstages);  // grid <= #SMs: one resident CTA per SM
+   kern<<<grid, 288, shmem, ctx->stream>>>(a, ctx->coef, nstages);  // grid <= #SMs: one resident CTA per SM
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
    return 0;
@@ -897,7 +896,7 @@ int launch_vwxr(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem) {
       PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
       attr_shmem = shmem;
    }
-   kern<<<grid, VT, shmem, ctx->stream>>>(a);
+   kern<<<grid, VT, shmem, ctx->stream>>>(a, ctx->coef);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
    return 0;
@@ -937,7 +936,7 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
    double *hp;
    if (need <= PB_COEF_MAX && ctx->coef_inline) {
       a.coef_inline = 1;
-      hp = a.coef;
+      hp = ctx->coef.v;
    } else {
       // the pinned staging buffer may still feed an earlier async copy
       PB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--side", type=int, default=100)
     args = ap.parse_args()
-    lib = api.load_library()
+    lib = api.load_library(os.environ.get("PB200_LIB"))  # PB200_LIB: experimental build variants
     ctx = C.c_void_p()
     assert lib.pb200_ctx_create(C.byref(ctx), 0) == 0
     if args.config == "c2":

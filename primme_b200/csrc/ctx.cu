@@ -42,12 +42,10 @@ extern "C" int pb200_ctx_create(pb200_ctx **out, int device) {
    ctx->d_partials = NULL;
    ctx->nranks = 1;
    ctx->no_poll = getenv("PB200_NO_POLL") ? 1 : 0;
-   // measured on B200 (profiles/README.md): the warp-specialised ortho sweep and the narrow VWXR
-   // kernel are slower than the v2 sweep / the LDG VWXR kernel at the C2 shapes: opt-in only
-   ctx->use_ws = getenv("PB200_WS") ? 1 : 0;
-   ctx->use_narrow = getenv("PB200_NARROW") ? 1 : 0;
+   ctx->fused_finish = getenv("PB200_NO_FUSED_FINISH") ? 0 : 1;
+   PB_CUDA(cudaMalloc((void **)&ctx->d_counters, (1 + PB_FIN_MAXGROUPS) * sizeof(unsigned int)));
+   PB_CUDA(cudaMemset(ctx->d_counters, 0, (1 + PB_FIN_MAXGROUPS) * sizeof(unsigned int)));
    ctx->coef_inline = getenv("PB200_NO_INLINE_COEF") ? 0 : 1;
-   ctx->vwxr_cand_tma = getenv("PB200_CAND_TMA") ? 1 : 0;
    ctx->use_wide = getenv("PB200_NO_WIDE") ? 0 : 1;
    ctx->ortho_2cta = getenv("PB200_ORTHO_1CTA") ? 0 : 1;
    ctx->use_tma = getenv("PB200_NO_TMA") ? 0 : 1;
@@ -66,6 +64,8 @@ extern "C" int pb200_ctx_destroy(pb200_ctx *ctx) {
    cudaFree(ctx->d_small);
    cudaFree(ctx->d_panel);
    cudaFree(ctx->d_partials);
+   cudaFree(ctx->d_gpart);
+   cudaFree(ctx->d_counters);
    cudaFree(ctx->d_scratch);
    if (ctx->prof_ev) {
       for (int i = 0; i < 2 * PB_PROF_RING; i++) cudaEventDestroy(ctx->prof_ev[i]);
@@ -127,6 +127,37 @@ int pb_ensure_tagged(pb200_ctx *ctx, size_t elems) {
    PB_CUDA(cudaHostGetDevicePointer((void **)&ctx->d_htagged, ctx->h_tagged, 0));
    ctx->tagged_cap = cap;
    return 0;
+}
+
+// ---------------------------------------------------------------------- tensor maps ----
+typedef CUresult (*pb_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+      const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int pb_tensor_map_2d(CUtensorMap *tm, const double *base, int64_t rows, int cols, int64_t ld,
+      int box_rows, int box_cols) {
+   static pb_encode_tiled_fn encode = NULL;
+   static int tried = 0;
+   if (!tried) {
+      tried = 1;
+      void *fn = NULL;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+         encode = (pb_encode_tiled_fn)fn;
+      else
+         cudaGetLastError();
+   }
+   if (!encode || rows <= 0 || cols <= 0 || box_cols > 256 || box_rows > 256) return 1;
+   if ((((uintptr_t)base) & 15) != 0 || (ld % 2) != 0 || rows > 0x7fffffffLL) return 1;
+   const cuuint64_t gdim[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
+   const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
+   const cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
+   const cuuint32_t estr[2] = {1, 1};
+   CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, gdim, gstride, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+   return r == CUDA_SUCCESS ? 0 : 1;
 }
 
 // ------------------------------------------------------------------- event profiling ----
@@ -214,6 +245,70 @@ __global__ void __launch_bounds__(256) pb_reduce_partials_kernel(
    }
 }
 
+// wait until the (value, sequence number) pairs of panel `seq` have landed in mapped host memory
+static int pb_poll_tagged(pb200_ctx *ctx, int cnt, long long seq) {
+   volatile const long long *tg = (volatile const long long *)ctx->h_tagged;
+   volatile const double *tv = (volatile const double *)ctx->h_tagged;
+   unsigned long spins = 0;
+   time_t t0 = 0;
+   for (int e = 0; e < cnt; e++) {
+      while (tg[2 * e + 1] != seq) {
+         if ((++spins & 0xfffff) == 0) {
+            // watchdog: a panel never takes seconds; give up instead of spinning for ever
+            const time_t now = time(NULL);
+            if (!t0) t0 = now;
+            if (now - t0 > 120) {
+               fprintf(stderr, "primme_b200: timed out waiting for a panel (kernel hung?)\n");
+               return PB200_ERR_CUDA;
+            }
+            cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) {
+               fprintf(stderr, "primme_b200: CUDA error %s while waiting for a panel\n", cudaGetErrorString(q));
+               return PB200_ERR_CUDA;
+            }
+         }
+      }
+      ctx->h_pinned[e] = tv[2 * e];
+   }
+   return 0;
+}
+
+int pb_fin_prepare(pb200_ctx *ctx, int grid, int ppc, int cnt, PbFin *f) {
+   memset(f, 0, sizeof(*f));
+   const int ngroups = (grid + PB_FIN_GROUP - 1) / PB_FIN_GROUP;
+   if (!ctx->fused_finish || cnt <= 0 || ngroups > PB_FIN_MAXGROUPS) return 1;
+   PB_CHK(pb_ensure_small(ctx, (size_t)cnt));
+   PB_CHK(pb_ensure_partials(ctx, (size_t)grid * ppc * cnt + 16));
+   if ((size_t)ngroups * cnt > ctx->gpart_cap) {
+      PB_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (ctx->d_gpart) PB_CUDA(cudaFree(ctx->d_gpart));
+      const size_t cap = (size_t)PB_FIN_MAXGROUPS * cnt;
+      PB_CUDA(cudaMalloc((void **)&ctx->d_gpart, cap * sizeof(double)));
+      ctx->gpart_cap = cap;
+   }
+   f->partials = ctx->d_partials, f->gpart = ctx->d_gpart, f->counters = ctx->d_counters;
+   f->cnt = cnt, f->ppc = ppc;
+   if (ctx->nranks > 1 || ctx->no_poll) {
+      f->out = ctx->d_panel, f->tag = 0;
+   } else {
+      PB_CHK(pb_ensure_tagged(ctx, (size_t)cnt));
+      f->out = ctx->d_htagged, f->tag = ++ctx->seq;
+   }
+   return 0;
+}
+
+int pb_collect_panel(pb200_ctx *ctx, const PbFin *f) {
+   if (f->cnt <= 0) return 0;
+   if (f->tag == 0) {
+      if (ctx->nranks > 1) PB_CHK(pb_nccl_allreduce_dev(ctx, ctx->d_panel, f->cnt));
+      PB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_panel, (size_t)f->cnt * sizeof(double),
+            cudaMemcpyDeviceToHost, ctx->stream));
+      PB_CUDA(cudaStreamSynchronize(ctx->stream));
+      return 0;
+   }
+   return pb_poll_tagged(ctx, f->cnt, f->tag);
+}
+
 int pb_finish_panel(pb200_ctx *ctx, int nparts, int cnt) {
    if (cnt <= 0) return 0;
    PB_CHK(pb_ensure_small(ctx, (size_t)cnt));
@@ -240,30 +335,7 @@ int pb_finish_panel(pb200_ctx *ctx, int nparts, int cnt) {
    pb_prof_end(ctx, ps, 8.0 * nparts * cnt);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
-   volatile const long long *tg = (volatile const long long *)ctx->h_tagged;
-   volatile const double *tv = (volatile const double *)ctx->h_tagged;
-   unsigned long spins = 0;
-   time_t t0 = 0;
-   for (int e = 0; e < cnt; e++) {
-      while (tg[2 * e + 1] != seq) {
-         if ((++spins & 0xfffff) == 0) {
-            // watchdog: a panel never takes seconds; give up instead of spinning for ever
-            const time_t now = time(NULL);
-            if (!t0) t0 = now;
-            if (now - t0 > 120) {
-               fprintf(stderr, "primme_b200: timed out waiting for a panel (kernel hung?)\n");
-               return PB200_ERR_CUDA;
-            }
-            cudaError_t q = cudaStreamQuery(ctx->stream);
-            if (q != cudaSuccess && q != cudaErrorNotReady) {
-               fprintf(stderr, "primme_b200: CUDA error %s while waiting for a panel\n", cudaGetErrorString(q));
-               return PB200_ERR_CUDA;
-            }
-         }
-      }
-      ctx->h_pinned[e] = tv[2 * e];
-   }
-   return 0;
+   return pb_poll_tagged(ctx, cnt, seq);
 }
 
 // ---------------------------------------------------------------------------- memory ------

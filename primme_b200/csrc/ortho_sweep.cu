@@ -29,10 +29,14 @@ struct SweepArgs {
    int64_t n, ldq, ldv, ldx;
    int q, mv, b;
    int do_update, has_Y, do_gram, xx;
+   int bt;              // leading dimension of Y / column count of the packed C (b padded to 1,2,4,8)
+   int stage_doubles;   // size of the stage ring of the MMA kernel (>= the end-of-kernel panel scratch)
+   int qpad, xcol0;     // MMA kernel: virtual column of the first V / first X column
    const double *Cdev;  // (q+mv) x BT, column stride = (q+mv)
    const double *Ydev;  // BT x BT, column stride BT
    int coef_inline;     // 1: C and Y travel in `coef` below (kernel parameter space), no H2D copy
    double *partials;    // [gridDim.x][(k + xx*b) * b]
+   PbFin fin;           // in-kernel panel finish (fin.cnt == 0: the host launches the reduction)
 };
 
 __device__ __forceinline__ const double *col_ptr(const SweepArgs &a, int j) {
@@ -177,545 +181,256 @@ __global__ void __launch_bounds__(TILE) ortho_sweep_kernel(SweepArgs a, const __
          if (lane == 0 && warp < a.b && c < a.b) out[k + warp + (size_t)c * rows] = v;
       }
    }
+   pb_finish_device(a.fin, tid, TILE, 15, reinterpret_cast<int *>(xs + BT * TILE));
 }
 
 
 // ------------------------------------------------------------------------------------------
-// v2: TMA-staged variant.  A dedicated producer warp streams 128-row tiles of [Q V X] into a
-// ring of shared-memory stages with one bulk copy (cp.async.bulk, SASS UBLKCP) per column
-// segment, completion tracked by mbarriers; 8 consumer warps do the update and the Gram from
-// shared memory.  Memory-level parallelism no longer depends on registers/occupancy: up to
-// 4 tiles (~200 KB) are in flight per SM.  Requires 16-byte aligned columns (even leading
-// dimensions); a partial last tile is completed with plain stores by the producer warp.
-constexpr int TR = 128;          // rows per tile
-constexpr int NCW = 8;           // consumer warps
-constexpr int NCT = NCW * 32;    // consumer threads
+// Main kernel: TMA-staged tiles + fp64 tensor-core (DMMA m8n8k4) contractions, warp-local rows.
+//
+// A producer warp streams TR-row tiles of [Q V X] into a ring of shared-memory stages, one bulk
+// copy (cp.async.bulk, SASS UBLKCP) per column segment, completion tracked by mbarriers.  Each of
+// the NW consumer warps owns 8 rows of the tile and does everything for them without any
+// CTA-wide barrier:
+//   update  D(8 x 8)   = X - A(8 x k) * C(k x 8)       k/4 DMMAs, A fragments straight from the
+//                                                      stage (column stride TR+4 doubles: the
+//                                                      fragment loads are bank-conflict free)
+//           D          = D * Y                         1-2 DMMAs after a quad shuffle
+//           new rows -> global and back into the stage's X columns
+//   Gram    P(kc x 8) += A(8 x kc)^T * X(8 x 8)        kc/8 accumulator tiles x 2 DMMAs, kept in
+//                                                      registers across all tiles of the CTA
+// The warps only meet at the end: per-warp panels are summed in warp order through shared
+// memory (one partial panel per CTA), then the in-kernel finish delivers the reduced panel.
+// Block widths b < 8 are zero-padded to the 8 columns of the MMA shape (the kernel is HBM-bound:
+// the fp64 pipe runs at 20-45 % of its 37 TFLOP/s).  Requires 16-byte aligned columns.
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                : "+d"(d0), "+d"(d1)
+                : "d"(a), "d"(b));
+}
 
-template <int BT, int CPW>
-__global__ void __launch_bounds__(NCT + 32) ortho_sweep_tma_kernel(SweepArgs a, const __grid_constant__ PbCoef coef, int nstages) {
+constexpr int CS_LD = 12;  // row stride (doubles) of the coefficient blocks in shared memory:
+                           // B-fragment loads (row = lane%4, column = lane/4) hit 32 distinct banks
+
+struct SweepMaps {
+   CUtensorMap q, v, x;  // boxes of (TR+4) rows x (qpad | xcol0-qpad | 8) columns
+};
+
+// Stage layout ("virtual columns", each S = TR+4 doubles): [Q | pad to a multiple of 4][V | pad so
+// that X starts at a multiple of 8 = xcol0][X padded to 8 columns].  The pads are columns past the
+// end of the respective tensor map, which the TMA unit zero-fills, so every region starts
+// 128-byte aligned (4 columns = 33 x 128 B), column addresses are linear in the virtual index and
+// no fragment load needs a bounds check.
+template <int MT, int NW>
+__global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_kernel(SweepArgs a, const __grid_constant__ PbCoef coef,
+      const __grid_constant__ SweepMaps maps, int nstages) {
+   constexpr int TR = 8 * NW;     // rows per tile
+   constexpr int S = TR + 4;      // column stride of a staged tile
+   constexpr int NCT = NW * 32;   // consumer threads
    extern __shared__ __align__(128) unsigned char smraw[];
    const int k = a.q + a.mv;
-   const int kc = k + a.b;
-   double *stage0 = reinterpret_cast<double *>(smraw);
-   double *Cs = stage0 + (size_t)nstages * kc * TR;  // k * BT
-   double *Ys = Cs + (size_t)k * BT;                 // BT * BT
-   double *xs = Ys + BT * BT;                        // BT * TR (updated X tile)
-   double *exch = xs + BT * TR;                      // 2 * TR * BT (partial updates)
-   uint64_t *full = reinterpret_cast<uint64_t *>(exch + 2 * TR * BT);
+   const int qpad = a.qpad, xcol0 = a.xcol0;
+   const int stage_sz = (xcol0 + 8) * S;
+   double *stage0 = reinterpret_cast<double *>(smraw);             // nstages * stage_sz
+   double *Cs = stage0 + a.stage_doubles;                          // xcol0 * CS_LD   (holds -C)
+   double *Ys = Cs + (size_t)xcol0 * CS_LD;                        // 8 * CS_LD
+   double *xw0 = Ys + 8 * CS_LD;                                   // NW * 8 * CS_LD: updated rows, per warp
+   uint64_t *full = reinterpret_cast<uint64_t *>(xw0 + NW * 8 * CS_LD);
    uint64_t *empty = full + nstages;
+   int *flag = reinterpret_cast<int *>(empty + nstages);
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
    if (tid == 0) {
       for (int s = 0; s < nstages; s++) {
          pbtma::mbar_init(&full[s], 1);
-         pbtma::mbar_init(&empty[s], NCW);
+         pbtma::mbar_init(&empty[s], NW);
       }
       pbtma::fence_barrier_init();
    }
    if (a.do_update) {
-      for (int i = tid; i < k * BT; i += NCT + 32) {
-         int j = i % k, c = i / k;
-         Cs[j * BT + c] = (c < a.b) ? (a.coef_inline ? coef.v : a.Cdev)[j + (size_t)c * k] : 0.0;
+      const double *cg = a.coef_inline ? coef.v : a.Cdev;
+      const double *yg = a.coef_inline ? coef.v + (size_t)k * a.bt : a.Ydev;
+      for (int i = tid; i < xcol0 * 8; i += NCT + 32) {
+         const int vc = i >> 3, c = i & 7;
+         int j = -1;  // real column of [Q V] behind virtual column vc
+         if (vc < qpad) {
+            if (vc < a.q) j = vc;
+         } else if (vc - qpad < a.mv)
+            j = a.q + vc - qpad;
+         Cs[vc * CS_LD + c] = (j >= 0 && c < a.b) ? -cg[j + (size_t)c * k] : 0.0;
       }
-      for (int i = tid; i < BT * BT; i += NCT + 32) {
-         int r = i % BT, c = i / BT;
-         double y = (r == c) ? 1.0 : 0.0;
-         if (a.has_Y) y = (r < a.b && c < a.b) ? (a.coef_inline ? coef.v + (size_t)k * BT : a.Ydev)[r + c * BT] : 0.0;
-         Ys[r * BT + c] = y;
+      for (int i = tid; i < 64; i += NCT + 32) {
+         const int r = i >> 3, c = i & 7;
+         Ys[r * CS_LD + c] = (a.has_Y && r < a.b && c < a.b) ? yg[r + c * a.bt] : 0.0;
       }
    }
    __syncthreads();
 
    const int64_t ntiles = (a.n + TR - 1) / TR;  // the last tile may be partial
-   if (warp == NCW) {
-      // ------------------------------ producer warp ------------------------------
+   if (warp == NW) {
+      // ------------------------------ producer: one elected lane ------------------------------
+      // one tensor-tile copy per operand and tile; rows past n and the pad columns are zero-filled
+      // by the TMA unit, the 4 extra rows of a box make the fragment loads bank-conflict free
+      if (lane != 0) return;
       int s = 0;
       uint32_t ph = 0;
+      const uint32_t bytes = (uint32_t)(stage_sz * sizeof(double));
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-         if (lane == 0) pbtma::mbar_wait(&empty[s], ph ^ 1);
-         __syncwarp();
-         double *dst = stage0 + (size_t)s * kc * TR;
-         const int64_t r0 = tile * TR;
-         const int rows = (int)((a.n - r0) < TR ? (a.n - r0) : TR);
-         const int rows_even = rows & ~1;
-         if (rows < TR) {
-            // partial tile: bulk copies take the even part, the odd last row and the zero
-            // padding are written with plain stores (padded rows then contribute nothing)
-            for (int c = lane; c < kc; c += 32) {
-               const double *src = c < k ? col_ptr(a, c) + r0 : a.X + (size_t)(c - k) * a.ldx + r0;
-               double *d = dst + (size_t)c * TR;
-               for (int rr = rows_even; rr < TR; rr++) d[rr] = rr < rows ? src[rr] : 0.0;
-            }
-            __syncwarp();
-         }
-         if (lane == 0)
-            pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(kc * rows_even * sizeof(double)));
-         __syncwarp();
-         if (rows_even > 0)
-            for (int c = lane; c < kc; c += 32) {
-               const double *src = c < k ? col_ptr(a, c) + r0 : a.X + (size_t)(c - k) * a.ldx + r0;
-               pbtma::bulk_g2s(dst + (size_t)c * TR, src, rows_even * sizeof(double), &full[s]);
-            }
+         pbtma::mbar_wait(&empty[s], ph ^ 1);
+         double *dst = stage0 + (size_t)s * stage_sz;
+         const int r0 = (int)(tile * TR);
+         pbtma::mbar_arrive_expect_tx(&full[s], bytes);
+         if (qpad > 0) pbtma::tensor_g2s_2d(dst, &maps.q, r0, 0, &full[s]);
+         if (xcol0 > qpad) pbtma::tensor_g2s_2d(dst + qpad * S, &maps.v, r0, 0, &full[s]);
+         pbtma::tensor_g2s_2d(dst + xcol0 * S, &maps.x, r0, 0, &full[s]);
          if (++s == nstages) s = 0, ph ^= 1;
       }
       return;
    }
 
    // ------------------------------ consumer warps ------------------------------
-   double acc[CPW][BT];
-   double accx[BT];
+   const int g = lane >> 2, t = lane & 3;  // fragment coordinates
+   const int r0w = warp * 8;               // first row of this warp inside the tile
+   const int nmtv = a.do_gram ? xcol0 >> 3 : 0;   // accumulator tiles over [Q V]
+   const int nks2 = xcol0 >> 3;                   // pairs of k-steps of the update
+   double acc[MT][2], accx[2];
 #pragma unroll
-   for (int j = 0; j < CPW; j++)
-#pragma unroll
-      for (int c = 0; c < BT; c++) acc[j][c] = 0.0;
-#pragma unroll
-   for (int c = 0; c < BT; c++) accx[c] = 0.0;
-
-   const int row1 = tid & (TR - 1), half = tid >> 7;  // phase-1 mapping: 2 threads per row
-   const int kh = (k + 1) / 2, j0 = half * kh, j1 = (j0 + kh < k) ? j0 + kh : k;
+   for (int mt = 0; mt < MT; mt++) acc[mt][0] = 0.0, acc[mt][1] = 0.0;
+   accx[0] = accx[1] = 0.0;
+   double *xw = xw0 + warp * 8 * CS_LD;
+   const int offu = r0w + t * S + g;   // update A fragment: column t of a k-step, row g
+   const int offg = r0w + g * S + t;   // Gram A fragment: column g of a tile, row t of a k-step
+   const double *cpu = Cs + t * CS_LD + g;
 
    int s = 0;
    uint32_t ph = 0;
    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       pbtma::mbar_wait(&full[s], ph);
-      const double *st = stage0 + (size_t)s * kc * TR;
-      const double *xsrc = st + (size_t)k * TR;  // X columns of this tile, [c][row]
+      const double *st = stage0 + (size_t)s * stage_sz;
+      const double *xb = st + xcol0 * S + offg;  // Gram X operand: X(row t of a k-step, column g)
       if (a.do_update) {
-         // phase 1: each half of the CTA applies half of the basis columns to its row
-         double t[BT];
-#pragma unroll
-         for (int c = 0; c < BT; c++) t[c] = 0.0;
-         int j = j0;
-         for (; j + 2 <= j1; j += 2) {
-            double v0 = st[(size_t)j * TR + row1], v1 = st[(size_t)(j + 1) * TR + row1];
-#pragma unroll
-            for (int c = 0; c < BT; c++) t[c] += v0 * Cs[j * BT + c] + v1 * Cs[(j + 1) * BT + c];
+         const double *sx = st + xcol0 * S + r0w + g;
+         double d0 = sx[(2 * t) * S], d1 = sx[(2 * t + 1) * S];
+         double e0 = 0.0, e1 = 0.0;
+         const double *pa = st + offu;
+         const double *pc = cpu;
+#pragma unroll 2
+         for (int i = 0; i < nks2; i++) {
+            const double a0 = pa[0], a1 = pa[4 * S];
+            dmma884(d0, d1, a0, pc[0]);
+            dmma884(e0, e1, a1, pc[4 * CS_LD]);
+            pa += 8 * S, pc += 8 * CS_LD;
          }
-         if (j < j1) {
-            double v0 = st[(size_t)j * TR + row1];
-#pragma unroll
-            for (int c = 0; c < BT; c++) t[c] += v0 * Cs[j * BT + c];
-         }
-#pragma unroll
-         for (int c = 0; c < BT; c++) exch[(size_t)(half * TR + row1) * BT + c] = t[c];
-         pbtma::named_bar_sync(1, NCT);
-         if (half == 0) {
-            double x[BT];
-#pragma unroll
-            for (int c = 0; c < BT; c++)
-               x[c] = (c < a.b ? xsrc[(size_t)c * TR + row1] : 0.0) - exch[(size_t)row1 * BT + c] -
-                      exch[(size_t)(TR + row1) * BT + c];
-            if (a.has_Y) {
-               double y[BT];
-#pragma unroll
-               for (int c = 0; c < BT; c++) {
-                  double sum = 0.0;
-#pragma unroll
-                  for (int cc = 0; cc < BT; cc++) sum += x[cc] * Ys[cc * BT + c];
-                  y[c] = sum;
-               }
-#pragma unroll
-               for (int c = 0; c < BT; c++) x[c] = y[c];
+         d0 += e0, d1 += e1;
+         if (a.has_Y) {
+            // D <- D * Y: the accumulator tile becomes the A operand after a shuffle inside each
+            // quad (A wants column t of row g, the accumulators hold columns 2t, 2t+1)
+            double y0 = 0.0, y1 = 0.0;
+            {
+               const int src = (lane & ~3) | (t >> 1);
+               const double v0 = __shfl_sync(0xffffffffu, d0, src), v1 = __shfl_sync(0xffffffffu, d1, src);
+               dmma884(y0, y1, (t & 1) ? v1 : v0, Ys[t * CS_LD + g]);
             }
-            const int64_t r = tile * TR + row1;
-#pragma unroll
-            for (int c = 0; c < BT; c++) {
-               if (c < a.b && r < a.n) a.X[r + (size_t)c * a.ldx] = x[c];
-               xs[(size_t)c * TR + row1] = x[c];
+            if (a.b > 4) {
+               const int src = (lane & ~3) | 2 | (t >> 1);
+               const double v0 = __shfl_sync(0xffffffffu, d0, src), v1 = __shfl_sync(0xffffffffu, d1, src);
+               dmma884(y0, y1, (t & 1) ? v1 : v0, Ys[(4 + t) * CS_LD + g]);
             }
+            d0 = y0, d1 = y1;
          }
-         pbtma::named_bar_sync(1, NCT);
-         xsrc = xs;
+         // the new rows go to global memory and to this warp's scratch ([column][row], stride
+         // CS_LD): the Gram below takes its X operand from there (the stage itself is only ever
+         // written by the TMA unit, so no proxy fence is needed before it is refilled)
+         const int64_t r = tile * TR + r0w + g;
+         if (2 * t < a.b && r < a.n) a.X[r + (size_t)(2 * t) * a.ldx] = d0;
+         if (2 * t + 1 < a.b && r < a.n) a.X[r + (size_t)(2 * t + 1) * a.ldx] = d1;
+         xw[(2 * t) * CS_LD + g] = d0;
+         xw[(2 * t + 1) * CS_LD + g] = d1;
+         __syncwarp();
+         xb = xw + g * CS_LD + t;
       }
       if (a.do_gram) {
+         const double *pg = st + offg;
 #pragma unroll
-         for (int i = 0; i < TR / 32; i++) {
-            const int row = i * 32 + lane;
-            double xv[BT];
+         for (int ks = 0; ks < 2; ks++) {
+            const double bf = xb[4 * ks];
 #pragma unroll
-            for (int c = 0; c < BT; c++) xv[c] = (c < a.b) ? xsrc[(size_t)c * TR + row] : 0.0;
-#pragma unroll
-            for (int j = 0; j < CPW; j++) {
-               const int jj = warp * CPW + j;
-               const double av = jj < k ? st[(size_t)jj * TR + row] : 0.0;
-#pragma unroll
-               for (int c = 0; c < BT; c++) acc[j][c] += av * xv[c];
-            }
-            if (a.xx && warp < a.b) {
-               const double xw = xsrc[(size_t)warp * TR + row];
-#pragma unroll
-               for (int c = 0; c < BT; c++) accx[c] += xw * xv[c];
-            }
+            for (int mt = 0; mt < MT; mt++)
+               if (mt < nmtv) dmma884(acc[mt][0], acc[mt][1], pg[mt * 8 * S + 4 * ks], bf);
+            // X'X block: A(column g, row t) and B(row t, column g) are the same element
+            if (a.xx) dmma884(accx[0], accx[1], bf, bf);
          }
       }
       __syncwarp();
-      if (lane == 0) pbtma::mbar_arrive(&empty[s]);  // this warp is done with the stage
+      if (lane == 0) pbtma::mbar_arrive(&empty[s]);
       if (++s == nstages) s = 0, ph ^= 1;
    }
 
    if (!a.do_gram) return;
-   const int rows = k + (a.xx ? a.b : 0);
-   double *out = a.partials + (size_t)blockIdx.x * rows * a.b;
+   // ---- per-warp panels -> one partial panel per CTA (warp order), through the stage memory ----
+   pbtma::named_bar_sync(1, NCT);  // every warp is done with the stages (all issued tiles consumed)
+   double *red = stage0;           // [NW][(nmtv + 1) * 8][8], virtual rows
+   const int nv = (nmtv + 1) * 8;
 #pragma unroll
-   for (int j = 0; j < CPW; j++) {
+   for (int mt = 0; mt < MT; mt++)
+      if (mt < nmtv)
+         *reinterpret_cast<double2 *>(red + ((size_t)warp * nv + mt * 8 + g) * 8 + 2 * t) =
+               make_double2(acc[mt][0], acc[mt][1]);
+   *reinterpret_cast<double2 *>(red + ((size_t)warp * nv + nmtv * 8 + g) * 8 + 2 * t) = make_double2(accx[0], accx[1]);
+   pbtma::named_bar_sync(1, NCT);
+   const int rows_out = k + (a.xx ? a.b : 0);
+   double *out = a.partials + (size_t)blockIdx.x * rows_out * a.b;
+   for (int e = tid; e < rows_out * a.b; e += NCT) {
+      const int j = e % rows_out, c = e / rows_out;
+      const int i = j < a.q ? j : j < k ? qpad + (j - a.q) : nmtv * 8 + (j - k);  // virtual row
+      double sum = 0.0;
 #pragma unroll
-      for (int c = 0; c < BT; c++) {
-         double v = acc[j][c];
-#pragma unroll
-         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-         int jj = warp * CPW + j;
-         if (lane == 0 && jj < k && c < a.b) out[jj + (size_t)c * rows] = v;
-      }
+      for (int w = 0; w < NW; w++) sum += red[((size_t)w * nv + i) * 8 + c];
+      out[e] = sum;
    }
-   if (a.xx) {
-#pragma unroll
-      for (int c = 0; c < BT; c++) {
-         double v = accx[c];
-#pragma unroll
-         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-         if (lane == 0 && warp < a.b && c < a.b) out[k + warp + (size_t)c * rows] = v;
-      }
-   }
+   pb_finish_device(a.fin, tid, NCT, 15, flag);
 }
 
-template <int BT, int CPW>
-int launch_sweep_tma(pb200_ctx *ctx, const SweepArgs &a, int &grid, size_t shmem, int nstages) {
-   auto kern = ortho_sweep_tma_kernel<BT, CPW>;
-   // persistent grid = resident CTAs only (a second wave would serialise half of the tiles);
-   // attribute + occupancy are queried once per (instantiation, shared-memory size)
-   static size_t cached_shmem = 0;
-   static int cached_occ = 0;
-   if (cached_shmem != shmem || cached_occ == 0) {
+// partial-panel storage + in-kernel finish for a launch of `grid` CTAs (cnt = 0: no panel)
+static int sweep_panel_setup(pb200_ctx *ctx, SweepArgs &a, int grid, int cnt) {
+   if (cnt <= 0) return 0;
+   const int r = pb_fin_prepare(ctx, grid, 1, cnt, &a.fin);
+   if (r < 0) return r;
+   if (r == 1) PB_CHK(pb_ensure_partials(ctx, (size_t)grid * cnt));
+   a.partials = ctx->d_partials;
+   return 0;
+}
+
+// shared memory of the MMA kernel besides the stage ring
+static size_t mma_fixed_smem(int xcol0) {
+   return ((size_t)xcol0 * CS_LD + 8 * CS_LD + 16 * 8 * CS_LD) * sizeof(double) + 2 * 8 * sizeof(uint64_t) + 64;
+}
+
+template <int MT, int NW>
+int launch_sweep_mma(pb200_ctx *ctx, SweepArgs &a, const SweepMaps &maps, int grid, size_t shmem, int nstages, int cnt) {
+   auto kern = ortho_sweep_mma_kernel<MT, NW>;
+   static size_t attr_shmem = 0;
+   if (shmem > attr_shmem) {
       PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-      int o = 1;
-      PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, NCT + 32, shmem));
-      cached_occ = o < 1 ? 1 : o;
-      cached_shmem = shmem;
-      if (getenv("PB200_DEBUG")) {
+      attr_shmem = shmem;
+   }
+   if (getenv("PB200_DEBUG")) {
+      static size_t seen = 0;
+      if (seen != shmem) {
+         seen = shmem;
+         int occ = 0;
          cudaFuncAttributes fa;
          cudaFuncGetAttributes(&fa, kern);
-         fprintf(stderr, "primme_b200: ortho_sweep_tma<%d,%d> dyn smem %zu static %zu regs %d stages %d -> %d CTA/SM\n",
-               BT, CPW, shmem, fa.sharedSizeBytes, fa.numRegs, nstages, cached_occ);
+         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32 + 32, shmem);
+         fprintf(stderr, "primme_b200: ortho_sweep_mma<%d,%d> dyn smem %zu regs %d stages %d -> %d CTA/SM\n",
+               MT, NW, shmem, fa.numRegs, nstages, occ);
       }
    }
-   const int occ = cached_occ;
-   if (grid > occ * ctx->num_sms) grid = occ * ctx->num_sms;
-   kern<<<grid, NCT + 32, shmem, ctx->stream>>>(a, ctx->coef, nstages);
+   PB_CHK(sweep_panel_setup(ctx, a, grid, cnt));
+   kern<<<grid, NW * 32 + 32, shmem, ctx->stream>>>(a, ctx->coef, maps, nstages);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
    return 0;
-}
-
-template <int BT>
-int dispatch_cpw_tma(pb200_ctx *ctx, const SweepArgs &a, int cpw, int &grid, size_t shmem, int nst) {
-   switch (cpw) {
-   case 1: return launch_sweep_tma<BT, 1>(ctx, a, grid, shmem, nst);
-   case 2: return launch_sweep_tma<BT, 2>(ctx, a, grid, shmem, nst);
-   case 3: return launch_sweep_tma<BT, 3>(ctx, a, grid, shmem, nst);
-   case 4: return launch_sweep_tma<BT, 4>(ctx, a, grid, shmem, nst);
-   case 5: return launch_sweep_tma<BT, 5>(ctx, a, grid, shmem, nst);
-   case 6: return launch_sweep_tma<BT, 6>(ctx, a, grid, shmem, nst);
-   case 7:
-   case 8: return launch_sweep_tma<BT, 8>(ctx, a, grid, shmem, nst);
-   case 9:
-   case 10: return launch_sweep_tma<BT, 10>(ctx, a, grid, shmem, nst);
-   case 11:
-   case 12: return launch_sweep_tma<BT, 12>(ctx, a, grid, shmem, nst);
-   default: return PB200_ERR_ARG;
-   }
-}
-
-
-// ------------------------------------------------------------------------------------------
-// v3: warp-specialised TMA pipeline.  Roles inside a CTA of 9 warps:
-//   warp 8      producer: one bulk copy per column segment into the stage ring (as v2)
-//   warps 0-1   update (only when C/Y are given): thread <-> two consecutive rows, 16-byte
-//               shared-memory loads, X <- (X - [Q V] C) Y, new rows to global and to a double-
-//               buffered shared tile
-//   others      Gram: warp <-> CPW basis columns, lane <-> row pairs, 16-byte loads
-// The roles are chained with mbarriers only (no CTA-wide barrier): the update of tile t+1
-// overlaps the Gram of tile t, and the bulk copies of tiles t+2.. are in flight meanwhile.
-template <int BT, int CPW>
-__global__ void __launch_bounds__(NCT + 32) ortho_sweep_ws_kernel(SweepArgs a, const __grid_constant__ PbCoef coef, int nstages) {
-   extern __shared__ __align__(128) unsigned char smraw[];
-   const int k = a.q + a.mv;
-   const int kc = k + a.b;
-   double *stage0 = reinterpret_cast<double *>(smraw);
-   double *xs = stage0 + (size_t)nstages * kc * TR;  // 2 * BT * TR, 16-byte aligned (double2 access)
-   double *Cs = xs + 2 * BT * TR;                    // k * BT
-   double *Ys = Cs + (size_t)k * BT;                 // BT * BT
-   uint64_t *full = reinterpret_cast<uint64_t *>(Ys + BT * BT);
-   uint64_t *empty = full + nstages;
-   uint64_t *xfull = empty + nstages;  // [2]
-   uint64_t *xempty = xfull + 2;       // [2]
-   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   const int nupd = a.do_update ? 2 : 0;                 // update warps
-   const int ngw = a.do_gram ? NCW - nupd : 0;           // Gram warps
-
-   if (tid == 0) {
-      for (int s = 0; s < nstages; s++) {
-         pbtma::mbar_init(&full[s], 1);
-         pbtma::mbar_init(&empty[s], nupd + ngw);
-      }
-      for (int i = 0; i < 2; i++) {
-         pbtma::mbar_init(&xfull[i], 2);
-         pbtma::mbar_init(&xempty[i], ngw > 0 ? ngw : 1);
-      }
-      pbtma::fence_barrier_init();
-   }
-   if (a.do_update) {
-      for (int i = tid; i < k * BT; i += NCT + 32) {
-         int j = i % k, c = i / k;
-         Cs[j * BT + c] = (c < a.b) ? (a.coef_inline ? coef.v : a.Cdev)[j + (size_t)c * k] : 0.0;
-      }
-      for (int i = tid; i < BT * BT; i += NCT + 32) {
-         int r = i % BT, c = i / BT;
-         double y = (r == c) ? 1.0 : 0.0;
-         if (a.has_Y) y = (r < a.b && c < a.b) ? (a.coef_inline ? coef.v + (size_t)k * BT : a.Ydev)[r + c * BT] : 0.0;
-         Ys[r * BT + c] = y;
-      }
-   }
-   __syncthreads();
-
-   const int64_t ntiles = (a.n + TR - 1) / TR;  // the last tile may be partial
-   if (warp == NCW) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-         if (lane == 0) pbtma::mbar_wait(&empty[s], ph ^ 1);
-         __syncwarp();
-         double *dst = stage0 + (size_t)s * kc * TR;
-         const int64_t r0 = tile * TR;
-         const int rows = (int)((a.n - r0) < TR ? (a.n - r0) : TR);
-         const int rows_even = rows & ~1;
-         if (rows < TR) {
-            // partial tile: bulk copies take the even part, the odd last row and the zero
-            // padding are written with plain stores (padded rows then contribute nothing)
-            for (int c = lane; c < kc; c += 32) {
-               const double *src = c < k ? col_ptr(a, c) + r0 : a.X + (size_t)(c - k) * a.ldx + r0;
-               double *d = dst + (size_t)c * TR;
-               for (int rr = rows_even; rr < TR; rr++) d[rr] = rr < rows ? src[rr] : 0.0;
-            }
-            __syncwarp();
-         }
-         if (lane == 0)
-            pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(kc * rows_even * sizeof(double)));
-         __syncwarp();
-         if (rows_even > 0)
-            for (int c = lane; c < kc; c += 32) {
-               const double *src = c < k ? col_ptr(a, c) + r0 : a.X + (size_t)(c - k) * a.ldx + r0;
-               pbtma::bulk_g2s(dst + (size_t)c * TR, src, rows_even * sizeof(double), &full[s]);
-            }
-         if (++s == nstages) s = 0, ph ^= 1;
-      }
-      return;
-   }
-
-   if (warp < nupd) {
-      // ------------------------------ update warps ------------------------------
-      const int p2 = 2 * tid;  // first of this thread's two rows (tid < 64)
-      int s = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-         const int buf = it & 1;
-         const uint32_t xph = (it >> 1) & 1;
-         pbtma::mbar_wait(&full[s], ph);
-         const double *st = stage0 + (size_t)s * kc * TR;
-         double t0[BT], t1[BT];
-#pragma unroll
-         for (int c = 0; c < BT; c++) t0[c] = 0.0, t1[c] = 0.0;
-#pragma unroll 4
-         for (int j = 0; j < k; j++) {
-            const double2 v = *reinterpret_cast<const double2 *>(st + (size_t)j * TR + p2);
-#pragma unroll
-            for (int c = 0; c < BT; c++) {
-               const double cj = Cs[j * BT + c];
-               t0[c] += v.x * cj;
-               t1[c] += v.y * cj;
-            }
-         }
-         double x0[BT], x1[BT];
-#pragma unroll
-         for (int c = 0; c < BT; c++) {
-            double2 xv = make_double2(0.0, 0.0);
-            if (c < a.b) xv = *reinterpret_cast<const double2 *>(st + (size_t)(k + c) * TR + p2);
-            x0[c] = xv.x - t0[c], x1[c] = xv.y - t1[c];
-         }
-         if (a.has_Y) {
-            double y0[BT], y1[BT];
-#pragma unroll
-            for (int c = 0; c < BT; c++) {
-               double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-               for (int cc = 0; cc < BT; cc++) {
-                  const double ycc = Ys[cc * BT + c];
-                  s0 += x0[cc] * ycc, s1 += x1[cc] * ycc;
-               }
-               y0[c] = s0, y1[c] = s1;
-            }
-#pragma unroll
-            for (int c = 0; c < BT; c++) x0[c] = y0[c], x1[c] = y1[c];
-         }
-         // the stage is no longer needed by this warp
-         __syncwarp();
-         if (lane == 0) pbtma::mbar_arrive(&empty[s]);
-         if (++s == nstages) s = 0, ph ^= 1;
-
-         const int64_t r = tile * TR + p2;
-#pragma unroll
-         for (int c = 0; c < BT; c++)
-            if (c < a.b) {
-               if (r + 1 < a.n)
-                  *reinterpret_cast<double2 *>(a.X + r + (size_t)c * a.ldx) = make_double2(x0[c], x1[c]);
-               else if (r < a.n)
-                  a.X[r + (size_t)c * a.ldx] = x0[c];
-            }
-         if (ngw > 0) {
-            pbtma::mbar_wait(&xempty[buf], xph ^ 1);  // Gram warps are done with this buffer
-            double *xb = xs + (size_t)buf * BT * TR;
-#pragma unroll
-            for (int c = 0; c < BT; c++)
-               *reinterpret_cast<double2 *>(xb + (size_t)c * TR + p2) = make_double2(x0[c], x1[c]);
-            __syncwarp();
-            if (lane == 0) pbtma::mbar_arrive(&xfull[buf]);
-         }
-      }
-      return;
-   }
-
-   if (ngw == 0) {
-      return;  // update-only sweep: the remaining warps have nothing to do
-   }
-
-   // ------------------------------ Gram warps ------------------------------
-   const int gw = warp - nupd;
-   double acc[CPW][BT];
-   double accx[2][BT];
-#pragma unroll
-   for (int j = 0; j < CPW; j++)
-#pragma unroll
-      for (int c = 0; c < BT; c++) acc[j][c] = 0.0;
-#pragma unroll
-   for (int c = 0; c < BT; c++) accx[0][c] = 0.0, accx[1][c] = 0.0;
-   const int xr0 = gw, xr1 = gw + ngw;  // rows of the X'X block owned by this warp
-
-   {
-      int s = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-         const int buf = it & 1;
-         const uint32_t xph = (it >> 1) & 1;
-         pbtma::mbar_wait(&full[s], ph);
-         const double *st = stage0 + (size_t)s * kc * TR;
-         const double *xsrc = st + (size_t)k * TR;
-         if (nupd) {
-            pbtma::mbar_wait(&xfull[buf], xph);
-            xsrc = xs + (size_t)buf * BT * TR;
-         }
-#pragma unroll
-         for (int i2 = 0; i2 < TR / 64; i2++) {
-            const int p2 = 2 * (i2 * 32 + lane);
-            double xv0[BT], xv1[BT];
-#pragma unroll
-            for (int c = 0; c < BT; c++) {
-               double2 xv = make_double2(0.0, 0.0);
-               if (c < a.b) xv = *reinterpret_cast<const double2 *>(xsrc + (size_t)c * TR + p2);
-               xv0[c] = xv.x, xv1[c] = xv.y;
-            }
-#pragma unroll
-            for (int j = 0; j < CPW; j++) {
-               const int jj = gw * CPW + j;
-               double2 av = make_double2(0.0, 0.0);
-               if (jj < k) av = *reinterpret_cast<const double2 *>(st + (size_t)jj * TR + p2);
-#pragma unroll
-               for (int c = 0; c < BT; c++) acc[j][c] += av.x * xv0[c] + av.y * xv1[c];
-            }
-            if (a.xx) {
-               if (xr0 < a.b) {
-                  const double2 xw = *reinterpret_cast<const double2 *>(xsrc + (size_t)xr0 * TR + p2);
-#pragma unroll
-                  for (int c = 0; c < BT; c++) accx[0][c] += xw.x * xv0[c] + xw.y * xv1[c];
-               }
-               if (xr1 < a.b) {
-                  const double2 xw = *reinterpret_cast<const double2 *>(xsrc + (size_t)xr1 * TR + p2);
-#pragma unroll
-                  for (int c = 0; c < BT; c++) accx[1][c] += xw.x * xv0[c] + xw.y * xv1[c];
-               }
-            }
-         }
-         __syncwarp();
-         if (lane == 0) {
-            if (nupd) pbtma::mbar_arrive(&xempty[buf]);
-            pbtma::mbar_arrive(&empty[s]);
-         }
-         if (++s == nstages) s = 0, ph ^= 1;
-      }
-   }
-
-   const int rows = k + (a.xx ? a.b : 0);
-   double *out = a.partials + (size_t)blockIdx.x * rows * a.b;
-#pragma unroll
-   for (int j = 0; j < CPW; j++) {
-#pragma unroll
-      for (int c = 0; c < BT; c++) {
-         double v = acc[j][c];
-#pragma unroll
-         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-         const int jj = gw * CPW + j;
-         if (lane == 0 && jj < k && c < a.b) out[jj + (size_t)c * rows] = v;
-      }
-   }
-   if (a.xx) {
-#pragma unroll
-      for (int h2 = 0; h2 < 2; h2++) {
-         const int xr = h2 == 0 ? xr0 : xr1;
-#pragma unroll
-         for (int c = 0; c < BT; c++) {
-            double v = accx[h2][c];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0 && xr < a.b && c < a.b) out[k + xr + (size_t)c * rows] = v;
-         }
-      }
-   }
-}
-
-template <int BT, int CPW>
-int launch_sweep_ws(pb200_ctx *ctx, const SweepArgs &a, int &grid, size_t shmem, int nstages) {
-   auto kern = ortho_sweep_ws_kernel<BT, CPW>;
-   static size_t cached_shmem = 0;
-   static int cached_occ = 0;
-   if (cached_shmem != shmem || cached_occ == 0) {
-      PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-      int o = 1;
-      PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, NCT + 32, shmem));
-      cached_occ = o < 1 ? 1 : o;
-      cached_shmem = shmem;
-   }
-   if (grid > cached_occ * ctx->num_sms) grid = cached_occ * ctx->num_sms;
-   kern<<<grid, NCT + 32, shmem, ctx->stream>>>(a, ctx->coef, nstages);
-   ctx->launches++;
-   PB_CUDA(cudaGetLastError());
-   return 0;
-}
-
-template <int BT>
-int dispatch_cpw_ws(pb200_ctx *ctx, const SweepArgs &a, int cpw, int &grid, size_t shmem, int nst) {
-   switch (cpw) {
-   case 1: return launch_sweep_ws<BT, 1>(ctx, a, grid, shmem, nst);
-   case 2: return launch_sweep_ws<BT, 2>(ctx, a, grid, shmem, nst);
-   case 3: return launch_sweep_ws<BT, 3>(ctx, a, grid, shmem, nst);
-   case 4: return launch_sweep_ws<BT, 4>(ctx, a, grid, shmem, nst);
-   case 5: return launch_sweep_ws<BT, 5>(ctx, a, grid, shmem, nst);
-   case 6: return launch_sweep_ws<BT, 6>(ctx, a, grid, shmem, nst);
-   case 7:
-   case 8: return launch_sweep_ws<BT, 8>(ctx, a, grid, shmem, nst);
-   case 9:
-   case 10: return launch_sweep_ws<BT, 10>(ctx, a, grid, shmem, nst);
-   default: return PB200_ERR_ARG;
-   }
 }
 
 template <int BT, int CPW>
@@ -807,101 +522,84 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
    // algorithmic bytes: basis read once, X read (+written when updated)  
    const double abytes = 8.0 * (double)n * (k + b * (a.do_update ? 2 : 1));
 
-   // ---- v2 (TMA-staged) eligibility: 16-byte aligned column segments, enough rows, tile ring
-   // of >= 2 stages in shared memory ----
-   const int kc = k + b;
-   auto aligned16 = [](const void *p) { return (((uintptr_t)p) & 15) == 0; };
-   bool tma_ok = ctx->use_tma && n >= 4 * TR && kc <= 96 && aligned16(X) && (ldx % 2 == 0) &&
-                 (q == 0 || (aligned16(Q) && ldq % 2 == 0)) && (mv == 0 || (aligned16(V) && ldv % 2 == 0));
-   int nstages = 0, ctas_per_sm = 1;
-   size_t fixed_sm = ((size_t)k * BT + BT * BT + (size_t)BT * TR + 2 * (size_t)TR * BT) * sizeof(double) + 128;
-   if (tma_ok) {
-      const size_t stage_b = (size_t)kc * TR * sizeof(double);
-      if (3 * stage_b + fixed_sm <= 110 * 1024) {
-         nstages = 3, ctas_per_sm = 2;
-      } else if (ctx->ortho_2cta && 2 * stage_b + fixed_sm <= 110 * 1024) {
-         // two resident CTAs (16 consumer warps per SM) with a 2-deep ring each hide the
-         // shared-memory latency of the Gram warps better than one CTA with a 4-deep ring
-         nstages = 2, ctas_per_sm = 2;
-      } else {
-         nstages = (int)((220 * 1024 - fixed_sm) / stage_b);
-         if (nstages > 4) nstages = 4;
+   // ---- main (TMA + DMMA) kernel eligibility: 16-byte aligned columns (tensor maps), enough
+   // rows, a ring of >= 2 stages in shared memory ----
+   a.bt = BT;
+   // virtual column layout of a stage (see the kernel): Q padded to 4, V padded so that X starts
+   // at a multiple of 8, X padded to 8
+   const int qpad = mv > 0 ? (q + 3) & ~3 : (q + 7) & ~7;
+   const int xcol0 = mv > 0 ? (qpad + mv + 7) & ~7 : qpad;
+   a.qpad = qpad, a.xcol0 = xcol0;
+   bool mma_ok = ctx->use_tma && n >= 256 && xcol0 <= 104;
+   int nstages = 0, nw = 16;
+   const size_t fixed_sm = mma_fixed_smem(xcol0);
+   const size_t smem_cap = 227 * 1024;
+   size_t stage_d = 0;
+   if (mma_ok) {
+      // 128-row tiles and 16 consumer warps; wide panels (C5: 64 + 8 columns) take 64-row tiles
+      // and 8 consumer warps so that the ring stays >= 3 deep.  One CTA per SM.
+      stage_d = (size_t)(xcol0 + 8) * (128 + 4);
+      nstages = (int)((smem_cap - fixed_sm) / (stage_d * sizeof(double)));
+      if (nstages < 3) {
+         nw = 8;
+         stage_d = (size_t)(xcol0 + 8) * (64 + 4);
+         nstages = (int)((smem_cap - fixed_sm) / (stage_d * sizeof(double)));
       }
-      if (nstages < 2) tma_ok = false;
+      if (nstages > 8) nstages = 8;
+      if (nstages < 2) mma_ok = false;
+   }
+   SweepMaps maps;
+   if (mma_ok) {
+      const int box = 8 * nw + 4;
+      memset(&maps, 0, sizeof(maps));
+      if (qpad > 0 && pb_tensor_map_2d(&maps.q, Q, n, q, ldq, box, qpad)) mma_ok = false;
+      if (mma_ok && xcol0 > qpad && pb_tensor_map_2d(&maps.v, V, n, mv, ldv, box, xcol0 - qpad)) mma_ok = false;
+      if (mma_ok && pb_tensor_map_2d(&maps.x, X, n, b, ldx, box, 8)) mma_ok = false;
    }
 
-   int grid = 0, nparts = 0, rc = 0;
+   int grid = 0, rc = 0;
+   const int cnt = a.do_gram ? rows * b : 0;
    int ps = pb_prof_begin(ctx, PB_K_ORTHO);
-   if (tma_ok) {
-      // v3 (warp-specialised, opt-in) when its column split fits the register budget
-      const int ngw = a.do_gram ? NCW - (a.do_update ? 2 : 0) : 0;
-      const int cpw_ws = ngw > 0 ? (k + ngw - 1) / ngw : 1;
-      const bool ws = ctx->use_ws && cpw_ws <= 10 && (ngw == 0 || 2 * ngw >= b);
-      const int64_t ntiles = (n + TR - 1) / TR;  // both kernels handle a partial last tile
-      const int64_t n_main = n;
-      grid = (int)(ntiles < (int64_t)ctx->num_sms * ctas_per_sm ? ntiles : (int64_t)ctx->num_sms * ctas_per_sm);
-      const int tail = n_main < n ? 1 : 0;
-      if (a.do_gram) {
-         PB_CHK(pb_ensure_partials(ctx, (size_t)(grid + tail) * rows * b));
-         a.partials = ctx->d_partials;
-      }
-      SweepArgs am = a;
-      am.n = n_main;
-      size_t shmem = (size_t)nstages * kc * TR * sizeof(double) + fixed_sm + 2 * nstages * sizeof(uint64_t);
-      if (ws) {
-         const int cw = cpw_ws < 1 ? 1 : cpw_ws;
-         switch (BT) {
-         case 1: rc = dispatch_cpw_ws<1>(ctx, am, cw, grid, shmem, nstages); break;
-         case 2: rc = dispatch_cpw_ws<2>(ctx, am, cw, grid, shmem, nstages); break;
-         case 4: rc = dispatch_cpw_ws<4>(ctx, am, cw, grid, shmem, nstages); break;
-         default: rc = dispatch_cpw_ws<8>(ctx, am, cw, grid, shmem, nstages); break;
-         }
+   if (mma_ok) {
+      const int tr = 8 * nw;
+      const int64_t ntiles = (n + tr - 1) / tr;  // a partial last tile is zero-filled by the TMA unit
+      grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
+      const int nmtv = xcol0 / 8;
+      size_t ring = (size_t)nstages * stage_d;
+      if (ring < (size_t)nw * (nmtv + 1) * 64) ring = (size_t)nw * (nmtv + 1) * 64;
+      a.stage_doubles = (int)ring;
+      const size_t shmem = ring * sizeof(double) + fixed_sm;
+#define PB_MMA(MT_, NW_) rc = launch_sweep_mma<MT_, NW_>(ctx, a, maps, grid, shmem, nstages, cnt)
+      if (nw == 16) {
+         if (nmtv <= 5) PB_MMA(5, 16);
+         else if (nmtv <= 9) PB_MMA(9, 16);
+         else PB_MMA(13, 16);
       } else {
-         switch (BT) {
-         case 1: rc = dispatch_cpw_tma<1>(ctx, am, cpw, grid, shmem, nstages); break;
-         case 2: rc = dispatch_cpw_tma<2>(ctx, am, cpw, grid, shmem, nstages); break;
-         case 4: rc = dispatch_cpw_tma<4>(ctx, am, cpw, grid, shmem, nstages); break;
-         default: rc = dispatch_cpw_tma<8>(ctx, am, cpw, grid, shmem, nstages); break;
-         }
+         if (nmtv <= 5) PB_MMA(5, 8);
+         else if (nmtv <= 9) PB_MMA(9, 8);
+         else PB_MMA(13, 8);
       }
-      nparts = grid;
-      if (!rc && tail) {
-         // rows [n_main, n): one CTA of the v1 kernel, its partial panel goes to slot `grid`
-         SweepArgs at = a;
-         at.n = n - n_main;
-         at.Q = Q ? Q + n_main : Q, at.V = V ? V + n_main : V, at.X = X + n_main;
-         if (a.do_gram) at.partials = ctx->d_partials + (size_t)grid * rows * b;
-         size_t shmem1 = ((size_t)k * BT + BT * BT + (size_t)BT * TILE) * sizeof(double);
-         switch (BT) {
-         case 1: rc = dispatch_cpw<1>(ctx, at, cpw, 1, shmem1); break;
-         case 2: rc = dispatch_cpw<2>(ctx, at, cpw, 1, shmem1); break;
-         case 4: rc = dispatch_cpw<4>(ctx, at, cpw, 1, shmem1); break;
-         default: rc = dispatch_cpw<8>(ctx, at, cpw, 1, shmem1); break;
-         }
-         nparts = grid + 1;
-      }
+#undef PB_MMA
    } else {
       const int64_t ntiles = (n + TILE - 1) / TILE;
       grid = (int)(ntiles < (int64_t)ctx->num_sms * 3 ? ntiles : (int64_t)ctx->num_sms * 3);
       if (grid < 1) grid = 1;
-      if (a.do_gram) {
-         PB_CHK(pb_ensure_partials(ctx, (size_t)grid * rows * b));
-         a.partials = ctx->d_partials;
-      }
-      size_t shmem = ((size_t)k * BT + BT * BT + (size_t)BT * TILE) * sizeof(double);
-      switch (BT) {
+      rc = sweep_panel_setup(ctx, a, grid, cnt);
+      size_t shmem = ((size_t)k * BT + BT * BT + (size_t)BT * TILE) * sizeof(double) + 16;
+      if (!rc) switch (BT) {
       case 1: rc = dispatch_cpw<1>(ctx, a, cpw, grid, shmem); break;
       case 2: rc = dispatch_cpw<2>(ctx, a, cpw, grid, shmem); break;
       case 4: rc = dispatch_cpw<4>(ctx, a, cpw, grid, shmem); break;
       default: rc = dispatch_cpw<8>(ctx, a, cpw, grid, shmem); break;
       }
-      nparts = grid;
    }
    pb_prof_end(ctx, ps, abytes);
    PB_CHK(rc);
-   grid = nparts;
    if (a.do_gram) {
-      PB_CHK(pb_finish_panel(ctx, grid, rows * b));
+      if (a.fin.cnt > 0)
+         PB_CHK(pb_collect_panel(ctx, &a.fin));
+      else
+         PB_CHK(pb_finish_panel(ctx, grid, cnt));
       for (int c = 0; c < b; c++)
          for (int j = 0; j < rows; j++) P_host[j + (size_t)c * ldp] = ctx->h_pinned[j + (size_t)c * rows];
    }

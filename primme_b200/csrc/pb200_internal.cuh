@@ -2,6 +2,7 @@
 // deterministic two-stage panel reduction).  Everything public is declared in
 // include/primme_b200.h.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the encoder is resolved at run time, no libcuda link)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -50,19 +51,20 @@ struct pb200_ctx {
    double *d_small;       // device buffer for coefficient blocks (h, C, Y, theta, perms)
    double *d_panel;       // device buffer for reduced panels
    double *d_partials;    // per-CTA partial panels
+   double *d_gpart;       // per-CTA-group partial panels (second level of the in-kernel reduction)
+   size_t gpart_cap;
+   unsigned int *d_counters;  // arrival counters of the in-kernel reduction (all zero between launches)
+   int fused_finish;      // 1 (default): the sweep kernels reduce and deliver their own panel
    size_t small_cap;      // capacity (doubles) of h_pinned / d_small / d_panel
    size_t partials_cap;   // capacity (doubles) of d_partials
    void *d_scratch;       // growable scratch (permute etc.)
    size_t scratch_cap;
    int64_t launches;
-   int use_ws;            // warp-specialised ortho sweep (v3) where eligible
    int use_tma_vwxr;      // same switch for the VWXR kernel alone
    int use_tma_spmm;      // persistent bulk-copy SpMM (v2)
    int use_wide;          // v3 wide VWXR kernel for the restart sweep
-   int vwxr_cand_tma;     // 1: TMA-staged (v2) kernel also for the candidates sweep
    int coef_inline;       // small coefficient matrices travel as kernel parameters (no H2D copy)
    PbCoef coef;           // host staging of that block for the next launch
-   int use_narrow;        // v3 narrow VWXR kernel for the candidates sweep (default off: the LDG kernel is faster)
    int ortho_2cta;        // prefer 2 CTAs/SM x 2 stages over 1 CTA/SM x 4 stages in the ortho sweep
    int use_tma;           // 1: TMA-staged kernels where eligible (default), 0: LDG kernels only
    // optional per-kernel-kind CUDA-event timing (bench.py's roofline numbers)
@@ -79,6 +81,101 @@ struct pb200_ctx {
    int owns_comm;
 };
 
+// ---------------------------------------------------------------- in-kernel panel finish ----
+// Every sweep kernel leaves one partial panel per CTA (or per tile group of a CTA).  Instead of a
+// second launch, the CTAs finish the panel themselves in two fixed-order levels: the last CTA of
+// each group of PB_FIN_GROUP consecutive CTAs to arrive sums its group's partials (slot order),
+// the last group to arrive sums the group panels (group order) and delivers the result -- either
+// (value, sequence number) pairs straight into mapped pinned host memory, or plain doubles into a
+// device buffer in front of an NCCL all-reduce.  The order of every sum depends on the launch
+// shape only, never on the arrival order => bitwise reproducible panels.
+#define PB_FIN_GROUP 16
+#define PB_FIN_MAXGROUPS 64
+struct PbFin {
+   double *partials;         // [nparts][cnt], CTA c owns slots [c*ppc, (c+1)*ppc)
+   double *gpart;            // [ngroups][cnt]
+   unsigned int *counters;   // [0]: groups done, [1+g]: CTAs of group g done
+   double *out;              // tagged pairs (tag != 0) or plain doubles
+   long long tag;
+   int cnt;                  // 0: no in-kernel finish
+   int ppc;                  // partial slots per CTA
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pb_fin_bar(int id, int nthreads) {
+   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void pb_fin_store(const PbFin &f, int e, double s) {
+   if (f.tag)
+      reinterpret_cast<double2 *>(f.out)[e] = make_double2(s, __longlong_as_double(f.tag));
+   else
+      f.out[e] = s;
+}
+// sum of np slots of one element, 8 independent chains in a fixed interleaving
+__device__ __forceinline__ double pb_fin_sum(const double *src, int np, int cnt) {
+   double s[8];
+#pragma unroll
+   for (int i = 0; i < 8; i++) s[i] = 0.0;
+   int p = 0;
+   for (; p + 8 <= np; p += 8) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] += __ldcg(src + (size_t)(p + i) * cnt);
+   }
+#pragma unroll
+   for (int i = 0; i < 8; i++)
+      if (p + i < np) s[i] += __ldcg(src + (size_t)(p + i) * cnt);
+   return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+// Called by threads tid = 0..nthr-1 of EVERY CTA (nthr a multiple of 32, the same set of threads
+// that wrote the CTA's partial slots) after those stores; bar_id: a named barrier free for them;
+// flag: one int of shared memory (dynamic: a static variable would change the kernels' occupancy).
+__device__ __forceinline__ void pb_finish_device(const PbFin &f, int tid, int nthr, int bar_id, volatile int *flag) {
+   if (f.cnt <= 0) return;
+   const int ncta = gridDim.x;
+   const int ngroups = (ncta + PB_FIN_GROUP - 1) / PB_FIN_GROUP;
+   const int g = blockIdx.x / PB_FIN_GROUP;
+   const int gsize = (ncta - g * PB_FIN_GROUP) < PB_FIN_GROUP ? (ncta - g * PB_FIN_GROUP) : PB_FIN_GROUP;
+   __threadfence();  // this thread's partial stores are visible device-wide
+   pb_fin_bar(bar_id, nthr);
+   if (tid == 0) {
+      __threadfence();
+      const unsigned int t = atomicAdd(&f.counters[1 + g], 1u);
+      *flag = (t == (unsigned int)(gsize - 1));
+   }
+   pb_fin_bar(bar_id, nthr);
+   if (!*flag) return;
+   __threadfence();
+   {
+      const double *src = f.partials + (size_t)g * PB_FIN_GROUP * f.ppc * f.cnt;
+      const int np = gsize * f.ppc;
+      for (int e = tid; e < f.cnt; e += nthr) {
+         const double s = pb_fin_sum(src + e, np, f.cnt);
+         if (ngroups == 1)
+            pb_fin_store(f, e, s);
+         else
+            f.gpart[(size_t)g * f.cnt + e] = s;
+      }
+   }
+   if (ngroups == 1) {
+      if (tid == 0) f.counters[1 + g] = 0u;
+      return;
+   }
+   __threadfence();
+   pb_fin_bar(bar_id, nthr);
+   if (tid == 0) {
+      __threadfence();
+      f.counters[1 + g] = 0u;
+      const unsigned int t = atomicAdd(&f.counters[0], 1u);
+      *flag = (t == (unsigned int)(ngroups - 1));
+   }
+   pb_fin_bar(bar_id, nthr);
+   if (!*flag) return;
+   __threadfence();
+   for (int e = tid; e < f.cnt; e += nthr) pb_fin_store(f, e, pb_fin_sum(f.gpart + e, ngroups, f.cnt));
+   if (tid == 0) f.counters[0] = 0u;
+}
+#endif
+
 // grow helpers (host side)
 int pb_ensure_partials(pb200_ctx *ctx, size_t doubles);
 int pb_ensure_scratch(pb200_ctx *ctx, size_t bytes);
@@ -87,9 +184,23 @@ int pb_ensure_tagged(pb200_ctx *ctx, size_t elems);
 // reduce ctx->d_partials [nparts x cnt] -> ctx->d_panel [cnt] (fixed order), optional NCCL
 // allreduce, copy to h_pinned and synchronize.  Result readable at ctx->h_pinned[0..cnt).
 int pb_finish_panel(pb200_ctx *ctx, int nparts, int cnt);
+// in-kernel finish: fill `f` for a launch of `grid` CTAs with `ppc` partial slots of `cnt` doubles
+// each (allocates partials / group panels, picks the destination, takes a sequence number); after
+// the launch pb_collect_panel waits for the panel (NCCL all-reduce first when sharded) and leaves
+// it in ctx->h_pinned[0..cnt).  Returns 1 from pb_fin_prepare when the launch shape is not
+// covered (fall back to pb_finish_panel).
+int pb_fin_prepare(pb200_ctx *ctx, int grid, int ppc, int cnt, PbFin *f);
+int pb_collect_panel(pb200_ctx *ctx, const PbFin *f);
 int pb_nccl_allreduce_dev(pb200_ctx *ctx, double *dbuf, int count);
 int pb_nccl_allgatherv_cols(pb200_ctx *ctx, const double *X, int64_t ldx, double *Y, int64_t ldy,
       const int64_t *counts, const int64_t *displs, int ncols);
+
+// 2-D tensor map over a column-major fp64 matrix (rows x cols, leading dimension ld): dimension 0
+// = rows (contiguous), dimension 1 = columns; box = box_rows x box_cols.  Returns 1 when the
+// driver entry point is unavailable or the shape is not encodable (callers fall back to the LDG
+// kernels).
+int pb_tensor_map_2d(CUtensorMap *tm, const double *base, int64_t rows, int cols, int64_t ld,
+      int box_rows, int box_cols);
 
 // kernel kinds for profiling
 enum { PB_K_SPMM = 0, PB_K_ORTHO = 1, PB_K_VWXR = 2, PB_K_UTIL = 3, PB_K_REDUCE = 4, PB_K_NKINDS = 5 };

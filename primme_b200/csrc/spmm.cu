@@ -250,12 +250,27 @@ __global__ void __launch_bounds__(SPT_THREADS, 2) spmm_tma_kernel(const int64_t 
             double acc[BT];
 #pragma unroll
             for (int c = 0; c < BT; c++) acc[c] = 0.0;
-            for (int i = sidx + sub; i < e; i += LPR) {
-               const double v = s_val[i];
-               const double *xp = X + s_col[i];
+            // four nonzeros per trip: all 4*b gathers of X are issued before the first FMA needs
+            // one, so a row of <= 4*LPR nonzeros costs one gather latency instead of four
+            for (int i = sidx + sub; i < e; i += 4 * LPR) {
+               double v[4];
+               const double *xp[4];
 #pragma unroll
-               for (int c = 0; c < BT; c++)
-                  if (c < b) acc[c] += v * xp[(size_t)c * ldx];
+               for (int u = 0; u < 4; u++) {
+                  const int iu = i + u * LPR;
+                  const bool on = iu < e;
+                  v[u] = on ? s_val[iu] : 0.0;
+                  xp[u] = X + (on ? s_col[iu] : s_col[i]);
+               }
+               double xv[4][BT];
+#pragma unroll
+               for (int u = 0; u < 4; u++)
+#pragma unroll
+                  for (int c = 0; c < BT; c++) xv[u][c] = c < b ? xp[u][(size_t)c * ldx] : 0.0;
+#pragma unroll
+               for (int u = 0; u < 4; u++)
+#pragma unroll
+                  for (int c = 0; c < BT; c++) acc[c] += v[u] * xv[u][c];
             }
             if (LPR > 1) {
 #pragma unroll

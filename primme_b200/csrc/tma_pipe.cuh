@@ -51,6 +51,16 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
          "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
          : "memory");
 }
+// global -> shared copy of one box of a 2-D tensor map (cp.async.bulk.tensor, SASS UTMALDG): the box
+// [c0, c0+box0) x [c1, c1+box1) lands densely in shared memory, elements outside the tensor are
+// zero-filled, and the FULL box byte count completes on `bar`.  dst must be 128-byte aligned.
+__device__ __forceinline__ void tensor_g2s_2d(void *dst_smem, const void *tmap, int c0, int c1, uint64_t *bar) {
+   asm volatile(
+         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+               smem_u32(dst_smem)),
+         "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+         : "memory");
+}
 // named barrier among the first `nthreads` threads of the CTA (consumer warps only)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -39,6 +39,7 @@ struct VwxrArgs {
    int nG, nH;
    int need_y;              // whether W*h is needed at all
    double *partials;        // [grid][cnt] : Rnorms(nR) | rnorms(nr) | G(nG*nG) | H(nH*nH)
+   PbFin fin;               // in-kernel panel finish (fin.cnt == 0: the host launches the reduction)
 };
 
 template <int NT>
@@ -240,219 +241,7 @@ __global__ void __launch_bounds__(VT) vwxr_kernel(VwxrArgs a, const __grid_const
          }
       }
    }
-}
-
-
-// ------------------------------------------------------------------------------------------
-// v2: TMA-staged variant.  A producer warp streams TR-row tiles of V and W (2m column segments,
-// one bulk copy each) through a shared-memory ring; 256 consumer threads = TPR threads per row:
-// half of them form V*h, the other half W*h (each thread NTH of the nh columns), the products
-// are parked in shared memory for the residual (needs both) and for the G/H blocks.  Outputs are
-// written after the whole tile has been read, so in-place restart (V <- V*h) stays safe.
-template <int NTH, int TPR>
-__global__ void __launch_bounds__(256 + 32) vwxr_tma_kernel(VwxrArgs a, const __grid_constant__ PbCoef coef, int nstages) {
-   constexpr int TR = 256 / TPR;        // rows per tile
-   constexpr int NSUB = TPR / 2;        // column groups per operand
-   constexpr int NT = NTH * NSUB;       // padded number of h columns
-   extern __shared__ __align__(128) unsigned char smraw[];
-   const int m = a.m;
-   double *stage0 = reinterpret_cast<double *>(smraw);       // nstages * 2m * TR
-   double *hs = stage0 + (size_t)nstages * 2 * m * TR;       // m * NT
-   double *th = hs + (size_t)m * NT;                         // NT
-   double *xs = th + NT;                                     // NT * TR
-   double *ys = xs + (size_t)NT * TR;                        // NT * TR
-   uint64_t *full = reinterpret_cast<uint64_t *>(ys + (size_t)NT * TR);
-   uint64_t *empty = full + nstages;
-   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-   if (tid == 0) {
-      for (int s = 0; s < nstages; s++) {
-         pbtma::mbar_init(&full[s], 1);
-         pbtma::mbar_init(&empty[s], 8);
-      }
-      pbtma::fence_barrier_init();
-   }
-   for (int i = tid; i < m * NT; i += 288) {
-      int k = i / NT, c = i % NT;
-      hs[i] = c < a.nh ? (a.coef_inline ? coef.v : a.hdev)[k + (size_t)c * m] : 0.0;
-   }
-   for (int i = tid; i < NT; i += 288) th[i] = i < a.nh ? (a.coef_inline ? coef.v + (size_t)a.m * a.nh : a.thetadev)[i] : 0.0;
-   __syncthreads();
-
-   const int64_t ntiles = a.n / TR;
-   if (warp == 8) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-         if (lane == 0) {
-            pbtma::mbar_wait(&empty[s], ph ^ 1);
-            pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * m * TR * sizeof(double)));
-         }
-         __syncwarp();
-         double *dst = stage0 + (size_t)s * 2 * m * TR;
-         const int64_t r0 = tile * TR;
-         for (int c = lane; c < 2 * m; c += 32) {
-            const double *src = (c < m ? a.V + (size_t)c * a.ld : a.W + (size_t)(c - m) * a.ld) + r0;
-            pbtma::bulk_g2s(dst + (size_t)c * TR, src, TR * sizeof(double), &full[s]);
-         }
-         if (++s == nstages) s = 0, ph ^= 1;
-      }
-      return;
-   }
-
-   const int row = tid % TR, part = tid / TR;
-   const int op = part / NSUB, csub = part % NSUB;  // op 0: V*h, op 1: W*h
-   const int c0 = csub * NTH;
-   const int nR = a.R.ptr ? a.R.ce - a.R.cb : 0;
-   const int nr = a.re - a.rb;
-   double nrm[NTH];
-#pragma unroll
-   for (int c = 0; c < NTH; c++) nrm[c] = 0.0;
-   constexpr int MAXBLK = 3;  // 2x2 blocks per thread: nGb^2 + nHb^2 <= 768 (nG, nH <= 38)
-   double gacc[MAXBLK][4];
-#pragma unroll
-   for (int t = 0; t < MAXBLK; t++)
-#pragma unroll
-      for (int e = 0; e < 4; e++) gacc[t][e] = 0.0;
-   const int nGb = (a.nG + 1) / 2, nHb = (a.nH + 1) / 2;
-   const int nblkG = nGb * nGb, nblk = nblkG + nHb * nHb;
-
-   int s = 0;
-   uint32_t ph = 0;
-   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      pbtma::mbar_wait(&full[s], ph);
-      const double *src = stage0 + (size_t)s * 2 * m * TR + (size_t)op * m * TR + row;
-      double acc[NTH];
-#pragma unroll
-      for (int c = 0; c < NTH; c++) acc[c] = 0.0;
-      int k = 0;
-      for (; k + 2 <= m; k += 2) {
-         const double v0 = src[(size_t)k * TR], v1 = src[(size_t)(k + 1) * TR];
-         const double *h0 = hs + (size_t)k * NT + c0;
-#pragma unroll
-         for (int c = 0; c < NTH; c++) acc[c] += v0 * h0[c] + v1 * h0[NT + c];
-      }
-      if (k < m) {
-         const double v0 = src[(size_t)k * TR];
-         const double *h0 = hs + (size_t)k * NT + c0;
-#pragma unroll
-         for (int c = 0; c < NTH; c++) acc[c] += v0 * h0[c];
-      }
-      __syncwarp();
-      if (lane == 0) pbtma::mbar_arrive(&empty[s]);  // stage consumed by this warp
-      if (++s == nstages) s = 0, ph ^= 1;
-
-      double *park = op == 0 ? xs : ys;
-#pragma unroll
-      for (int c = 0; c < NTH; c++) park[(size_t)(c0 + c) * TR + row] = acc[c];
-      pbtma::named_bar_sync(1, 256);
-
-      const int64_t r = tile * TR + row;
-      if (op == 0) {
-#pragma unroll
-         for (int t = 0; t < 3; t++) {
-            if (a.X[t].ptr) {
-#pragma unroll
-               for (int c = 0; c < NTH; c++) {
-                  const int cc = c0 + c;
-                  if (cc >= a.X[t].cb && cc < a.X[t].ce)
-                     a.X[t].ptr[r + (size_t)(cc - a.X[t].cb) * a.X[t].ld] = acc[c];
-               }
-            }
-         }
-      } else {
-#pragma unroll
-         for (int c = 0; c < NTH; c++) {
-            const int cc = c0 + c;
-            if (a.Wo.ptr && cc >= a.Wo.cb && cc < a.Wo.ce)
-               a.Wo.ptr[r + (size_t)(cc - a.Wo.cb) * a.Wo.ld] = acc[c];
-            const bool inR = a.R.ptr && cc >= a.R.cb && cc < a.R.ce;
-            const bool inr = cc >= a.rb && cc < a.re;
-            if (inR || inr) {
-               const double res = acc[c] - xs[(size_t)cc * TR + row] * th[cc];
-               if (inR) a.R.ptr[r + (size_t)(cc - a.R.cb) * a.R.ld] = res;
-               nrm[c] += res * res;
-            }
-         }
-      }
-      if (nblk > 0) {
-#pragma unroll
-         for (int t = 0; t < MAXBLK; t++) {
-            const int blk = tid + 256 * t;
-            if (blk < nblk) {
-               const double *L = xs, *Rr;
-               int bi, bj, nn;
-               if (blk < nblkG) {
-                  bi = blk % nGb, bj = blk / nGb, nn = a.nG, Rr = xs;
-               } else {
-                  const int bb = blk - nblkG;
-                  bi = bb % nHb, bj = bb / nHb, nn = a.nH, Rr = ys;
-               }
-               if (blk >= nblkG || bi <= bj) {
-                  const int i0 = 2 * bi, jj0 = 2 * bj;
-                  const int i1 = i0 + 1 < nn ? i0 + 1 : i0, jj1 = jj0 + 1 < nn ? jj0 + 1 : jj0;
-                  const double *li0 = L + (size_t)i0 * TR, *li1 = L + (size_t)i1 * TR;
-                  const double *rj0 = Rr + (size_t)jj0 * TR, *rj1 = Rr + (size_t)jj1 * TR;
-                  double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-#pragma unroll 4
-                  for (int rr = 0; rr < TR; rr++) {
-                     const double l0 = li0[rr], l1 = li1[rr], q0 = rj0[rr], q1 = rj1[rr];
-                     s00 += l0 * q0, s01 += l0 * q1, s10 += l1 * q0, s11 += l1 * q1;
-                  }
-                  gacc[t][0] += s00, gacc[t][1] += s01, gacc[t][2] += s10, gacc[t][3] += s11;
-               }
-            }
-         }
-      }
-      pbtma::named_bar_sync(1, 256);  // xs/ys are rewritten by the next tile
-   }
-
-   // ---------------- epilogue ----------------
-   const int nn = (nR + nr) > 0 ? a.nh : 0;
-   const int cnt = nn + a.nG * a.nG + a.nH * a.nH;
-   double *out = a.partials + (size_t)blockIdx.x * cnt;
-   if (nn > 0) {
-      // park the per-thread squared norms ([column][row], W*h threads only) and sum each column
-      // over the rows in a fixed order
-#pragma unroll
-      for (int c = 0; c < NTH; c++)
-         if (op == 1) ys[(size_t)(c0 + c) * TR + row] = nrm[c];
-      pbtma::named_bar_sync(1, 256);
-      if (tid < a.nh) {
-         const bool want = (a.R.ptr && tid >= a.R.cb && tid < a.R.ce) || (tid >= a.rb && tid < a.re);
-         double sum = 0.0;
-         if (want)
-            for (int rr = 0; rr < TR; rr++) sum += ys[(size_t)tid * TR + rr];
-         out[tid] = sum;
-      }
-   }
-   if (nblk > 0) {
-      double *Gout = out + nn;
-      double *Hout = Gout + a.nG * a.nG;
-#pragma unroll
-      for (int t = 0; t < MAXBLK; t++) {
-         const int blk = tid + 256 * t;
-         if (blk >= nblk) continue;
-         if (blk < nblkG) {
-            const int bi = blk % nGb, bj = blk / nGb;
-            if (bi > bj) continue;
-            for (int e = 0; e < 4; e++) {
-               const int i = 2 * bi + (e >> 1), j = 2 * bj + (e & 1);
-               if (i < a.nG && j < a.nG) {
-                  Gout[i + (size_t)j * a.nG] = gacc[t][e];
-                  if (bi != bj) Gout[j + (size_t)i * a.nG] = gacc[t][e];
-               }
-            }
-         } else {
-            const int bb = blk - nblkG;
-            const int bi = bb % nHb, bj = bb / nHb;
-            for (int e = 0; e < 4; e++) {
-               const int i = 2 * bi + (e >> 1), j = 2 * bj + (e & 1);
-               if (i < a.nH && j < a.nH) Hout[i + (size_t)j * a.nH] = gacc[t][e];
-            }
-         }
-      }
-   }
+   if (cnt > 0) pb_finish_device(a.fin, tid, VT, 15, reinterpret_cast<int *>(smem + 64));
 }
 
 
@@ -463,163 +252,6 @@ __device__ __forceinline__ void st2(double *p, double v0, double v1, int64_t r, 
    else if (r < n)
       *p = v0;
 }
-
-// ------------------------------------------------------------------------------------------
-// v3 for narrow coefficient blocks (nh <= 8, no Gram outputs): the candidates sweep, executed
-// every outer iteration.  Producer warp as in v2; the 8 consumer warps form 4 groups of 2 warps
-// and group g owns the CTA's tiles g, g+4, ... : thread <-> two consecutive rows, BOTH products
-// (V*h and W*h) in registers, 16-byte shared-memory loads, residual and norms formed in-thread,
-// 16-byte global stores.  No exchange between threads until the final norm reduction.
-template <int NTH>
-__global__ void __launch_bounds__(256 + 32) vwxr_narrow_kernel(VwxrArgs a, const __grid_constant__ PbCoef coef, int nstages) {
-   constexpr int TR = 128;
-   extern __shared__ __align__(128) unsigned char smraw[];
-   const int m = a.m;
-   double *stage0 = reinterpret_cast<double *>(smraw);   // nstages * 2m * TR
-   double *hs = stage0 + (size_t)nstages * 2 * m * TR;   // m * NTH
-   double *th = hs + (size_t)m * NTH;                    // NTH
-   double *red = th + NTH;                               // 8 * NTH
-   // Barrier slots: the i-th tile of this CTA uses stage i % nstages and is consumed by tile group
-   // i % 4, so slot i % NB with NB = 4*nstages always maps to the same (stage, group) pair: the
-   // phases of one slot are consumed by one group in order, which is what parity waits require.
-   const int NB = 4 * nstages;
-   uint64_t *full = reinterpret_cast<uint64_t *>(red + 8 * NTH);
-   uint64_t *empty = full + NB;
-   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-   if (tid == 0) {
-      for (int u = 0; u < NB; u++) {
-         pbtma::mbar_init(&full[u], 1);
-         pbtma::mbar_init(&empty[u], 2);
-      }
-      pbtma::fence_barrier_init();
-   }
-   for (int i = tid; i < m * NTH; i += 288) {
-      int k = i / NTH, c = i % NTH;
-      hs[i] = c < a.nh ? (a.coef_inline ? coef.v : a.hdev)[k + (size_t)c * m] : 0.0;
-   }
-   for (int i = tid; i < NTH; i += 288) th[i] = i < a.nh ? (a.coef_inline ? coef.v + (size_t)a.m * a.nh : a.thetadev)[i] : 0.0;
-   __syncthreads();
-
-   const int64_t ntiles = (a.n + TR - 1) / TR;  // the last tile may be partial
-   if (warp == 8) {
-      int64_t i = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, i++) {
-         const int s = (int)(i % nstages);
-         const int u = (int)(i % NB);
-         if (lane == 0 && i >= nstages) {
-            const int64_t j = i - nstages;  // previous user of this stage
-            pbtma::mbar_wait(&empty[j % NB], (uint32_t)((j / NB) & 1));
-         }
-         __syncwarp();
-         double *dst = stage0 + (size_t)s * 2 * m * TR;
-         const int64_t r0 = tile * TR;
-         const int rows = (int)((a.n - r0) < TR ? (a.n - r0) : TR);
-         const int rows_even = rows & ~1;
-         if (rows < TR) {
-            // partial tile: odd last row and zero padding by plain stores (see ortho_sweep.cu)
-            for (int c = lane; c < 2 * m; c += 32) {
-               const double *src = (c < m ? a.V + (size_t)c * a.ld : a.W + (size_t)(c - m) * a.ld) + r0;
-               double *d = dst + (size_t)c * TR;
-               for (int rr = rows_even; rr < TR; rr++) d[rr] = rr < rows ? src[rr] : 0.0;
-            }
-            __syncwarp();
-         }
-         if (lane == 0)
-            pbtma::mbar_arrive_expect_tx(&full[u], (uint32_t)(2 * m * rows_even * sizeof(double)));
-         __syncwarp();
-         if (rows_even > 0)
-            for (int c = lane; c < 2 * m; c += 32) {
-               const double *src = (c < m ? a.V + (size_t)c * a.ld : a.W + (size_t)(c - m) * a.ld) + r0;
-               pbtma::bulk_g2s(dst + (size_t)c * TR, src, rows_even * sizeof(double), &full[u]);
-            }
-      }
-      return;
-   }
-
-   const int grp = warp >> 1;               // 0..3
-   const int p2 = 2 * (tid & 63);           // first of this thread's two rows within the tile
-   double nrm[NTH];
-#pragma unroll
-   for (int c = 0; c < NTH; c++) nrm[c] = 0.0;
-
-   int64_t i = grp;
-   for (int64_t tile = blockIdx.x + (int64_t)grp * gridDim.x; tile < ntiles; tile += 4 * (int64_t)gridDim.x, i += 4) {
-      const int s = (int)(i % nstages);
-      const int u = (int)(i % NB);
-      pbtma::mbar_wait(&full[u], (uint32_t)((i / NB) & 1));
-      const double *sv = stage0 + (size_t)s * 2 * m * TR + p2;
-      const double *sw = sv + (size_t)m * TR;
-      double x0[NTH], x1[NTH], y0[NTH], y1[NTH];
-#pragma unroll
-      for (int c = 0; c < NTH; c++) x0[c] = x1[c] = y0[c] = y1[c] = 0.0;
-#pragma unroll 2
-      for (int k = 0; k < m; k++) {
-         const double2 v = *reinterpret_cast<const double2 *>(sv + (size_t)k * TR);
-         const double2 w = *reinterpret_cast<const double2 *>(sw + (size_t)k * TR);
-         const double *hk = hs + (size_t)k * NTH;
-#pragma unroll
-         for (int c = 0; c < NTH; c++) {
-            const double hc = hk[c];
-            x0[c] += v.x * hc, x1[c] += v.y * hc;
-            y0[c] += w.x * hc, y1[c] += w.y * hc;
-         }
-      }
-      __syncwarp();
-      if (lane == 0) pbtma::mbar_arrive(&empty[u]);
-
-      const int64_t r = tile * TR + p2;
-#pragma unroll
-      for (int c = 0; c < NTH; c++) {
-#pragma unroll
-         for (int t = 0; t < 3; t++)
-            if (a.X[t].ptr && c >= a.X[t].cb && c < a.X[t].ce)
-               st2(a.X[t].ptr + r + (size_t)(c - a.X[t].cb) * a.X[t].ld, x0[c], x1[c], r, a.n);
-         if (a.Wo.ptr && c >= a.Wo.cb && c < a.Wo.ce)
-            st2(a.Wo.ptr + r + (size_t)(c - a.Wo.cb) * a.Wo.ld, y0[c], y1[c], r, a.n);
-         const bool inR = a.R.ptr && c >= a.R.cb && c < a.R.ce;
-         if (inR || (c >= a.rb && c < a.re)) {
-            const double r0 = y0[c] - x0[c] * th[c], r1 = y1[c] - x1[c] * th[c];
-            if (inR) st2(a.R.ptr + r + (size_t)(c - a.R.cb) * a.R.ld, r0, r1, r, a.n);
-            nrm[c] += r0 * r0 + r1 * r1;
-         }
-      }
-   }
-
-   // norms: lanes -> warp -> CTA (fixed order)
-   const int nR = a.R.ptr ? a.R.ce - a.R.cb : 0;
-   const int nn = (nR + (a.re - a.rb)) > 0 ? a.nh : 0;
-   if (nn > 0) {
-#pragma unroll
-      for (int c = 0; c < NTH; c++) {
-         double v = nrm[c];
-#pragma unroll
-         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-         if (lane == 0) red[warp * NTH + c] = v;
-      }
-      pbtma::named_bar_sync(1, 256);
-      if (tid < a.nh) {
-         double sum = 0.0;
-         for (int w = 0; w < 8; w++) sum += red[w * NTH + tid];
-         a.partials[(size_t)blockIdx.x * nn + tid] = sum;
-      }
-   }
-}
-
-template <int NTH>
-int launch_vwxr_narrow(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem, int nstages) {
-   auto kern = vwxr_narrow_kernel<NTH>;
-   static size_t attr_shmem = 0;
-   if (shmem > attr_shmem) {
-      PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-      attr_shmem = shmem;
-   }
-   kern<<<grid, 288, shmem, ctx->stream>>>(a, ctx->coef, nstages);
-   ctx->launches++;
-   PB_CUDA(cudaGetLastError());
-   return 0;
-}
-
 
 // ------------------------------------------------------------------------------------------
 // v3 for wide coefficient blocks (restart: V <- V*h, W <- W*h, next block, G = X'X, H = X'Y).
@@ -846,6 +478,7 @@ __global__ void __launch_bounds__(256 + 32) vwxr_wide_kernel(VwxrArgs a, const _
             }
          }
    }
+   if (cnt > 0) pb_finish_device(a.fin, tid, 256, 15, reinterpret_cast<int *>(empty + NB));
 }
 
 template <int NTH, int NG>
@@ -860,32 +493,6 @@ int launch_vwxr_wide(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem, 
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
    return 0;
-}
-
-template <int NTH, int TPR>
-int launch_vwxr_tma(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem, int nstages) {
-   auto kern = vwxr_tma_kernel<NTH, TPR>;
-   static size_t attr_shmem = 0;
-   if (shmem > attr_shmem) {
-      PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-      attr_shmem = shmem;
-   }
-   kern<<<grid, 288, shmem, ctx->stream>>>(a, ctx->coef, nstages);  // grid <= #SMs: one resident CTA per SM
-   ctx->launches++;
-   PB_CUDA(cudaGetLastError());
-   return 0;
-}
-
-// shared memory of the v2 kernel for a (NTH, TPR) choice; returns stages (0 = does not fit)
-static int vwxr_tma_plan(int m, int nth, int tpr, size_t *shmem) {
-   const int TR = 256 / tpr, NT = nth * (tpr / 2);
-   const size_t fixed = ((size_t)m * NT + NT + 2 * (size_t)NT * TR) * sizeof(double) + 128;
-   const size_t stage = (size_t)2 * m * TR * sizeof(double);
-   if (fixed + 2 * stage > 227 * 1024) return 0;
-   int nst = (int)((227 * 1024 - fixed) / stage);
-   if (nst > 4) nst = 4;
-   *shmem = fixed + nst * stage;
-   return nst;
 }
 
 template <int NT>
@@ -960,48 +567,11 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
    if (a.R.ptr) ocols += a.R.ce - a.R.cb;
    const double abytes = 8.0 * (double)n * ((a.need_y ? 2.0 : 1.0) * m + ocols);
 
-   // ---- v2 plan: (columns per thread, threads per row) ----
-   int nth = 0, tpr = 0, nst = 0;
-   size_t shm2 = 0;
-   {
-      const bool al = ctx->use_tma_vwxr && m > 0 && (((uintptr_t)V) & 15) == 0 && (((uintptr_t)W) & 15) == 0 && ld % 2 == 0;
-      int gb = (a.nG + 1) / 2, hb = (a.nH + 1) / 2;
-      // the candidates sweep (narrow h, no Gram outputs) is fastest with the plain LDG kernel
-      const bool cand = nh <= 8 && a.nG == 0 && a.nH == 0 && !ctx->vwxr_cand_tma;
-      if (al && !cand && gb * gb + hb * hb <= 768) {
-         const int c2[][2] = {{4, 2}, {8, 2}, {16, 2}, {24, 2}, {12, 4}, {16, 4}, {20, 4}, {24, 4}};
-         for (int i = 0; i < 8 && !nst; i++) {
-            const int cap = c2[i][0] * (c2[i][1] / 2);
-            if (nh > cap) continue;
-            size_t sh = 0;
-            int st = vwxr_tma_plan(m, c2[i][0], c2[i][1], &sh);
-            if (st >= 2 && n >= 4 * (256 / c2[i][1])) nth = c2[i][0], tpr = c2[i][1], nst = st, shm2 = sh;
-         }
-      }
-   }
-
-   // ---- v3 (narrow) plan: candidates sweep ----
-   int narrow_nst = 0;
-   size_t narrow_shm = 0;
-   if (ctx->use_tma_vwxr && ctx->use_narrow && nh <= 8 && a.nG == 0 && a.nH == 0 && m > 0 && n >= 4 * 128 &&
-         (((uintptr_t)V) & 15) == 0 && (((uintptr_t)W) & 15) == 0 && ld % 2 == 0) {
-      bool ok = true;
-      auto al = [](const pb200_cols &c) { return !c.ptr || ((((uintptr_t)c.ptr) & 15) == 0 && c.ld % 2 == 0); };
-      for (int t = 0; t < 3; t++) ok = ok && al(a.X[t]);
-      ok = ok && al(a.Wo) && al(a.R);
-      const int NTHn = nh <= 4 ? 4 : 8;
-      const size_t fixed = ((size_t)m * NTHn + NTHn + 8 * NTHn) * sizeof(double) + 640;
-      const size_t stage = (size_t)2 * m * 128 * sizeof(double);
-      int st = (int)((227 * 1024 - fixed) / stage);
-      if (st > 4) st = 4;
-      if (ok && st >= 2) narrow_nst = st, narrow_shm = fixed + st * stage;
-   }
-
-   // ---- v3 (wide) plan: restart sweep ----
+   // ---- wide plan: restart sweep (TMA-staged, Gram blocks) ----
    int wide_nst = 0, wide_nth = 0, wide_ng = 0, wide_park = 0;
    size_t wide_shm = 0;
    const bool cand_shape = nh <= 8 && a.nG == 0 && a.nH == 0;  // candidates sweep: LDG kernel (fastest measured)
-   if (ctx->use_tma_vwxr && ctx->use_wide && !cand_shape && narrow_nst < 2 && nh <= 48 && m > 0 && n >= 4 * 64 &&
+   if (ctx->use_tma_vwxr && ctx->use_wide && !cand_shape && nh <= 48 && m > 0 && n >= 4 * 64 &&
          (((uintptr_t)V) & 15) == 0 && (((uintptr_t)W) & 15) == 0 && ld % 2 == 0) {
       bool ok = true;
       auto al = [](const pb200_cols &c) { return !c.ptr || ((((uintptr_t)c.ptr) & 15) == 0 && c.ld % 2 == 0); };
@@ -1023,85 +593,31 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
       }
    }
 
-   int grid = 1, nparts = 1, rc = 0;
+   int grid = 1, ppc = 1, rc = 0;
+   if (wide_nst >= 2) {
+      const int64_t ntiles = (n + 63) / 64;
+      grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
+      ppc = 8 / wide_ng;
+   } else if (n > 0) {
+      const int64_t ntiles = (n + VT - 1) / VT;
+      const int64_t g = (int64_t)ctx->num_sms * 4;
+      grid = (int)(ntiles < g ? ntiles : g);
+   }
+   // partial panels: every slot is written by the kernel (unused norm slots as zeros, G below the
+   // diagonal by mirroring), so no memset in front of the launch
+   {
+      const int r = pb_fin_prepare(ctx, grid, ppc, cnt, &a.fin);
+      if (r < 0) return r;
+      if (r == 1) PB_CHK(pb_ensure_partials(ctx, (size_t)grid * ppc * (cnt > 0 ? cnt : 1) + 16));
+      a.partials = ctx->d_partials;
+   }
    int ps = pb_prof_begin(ctx, PB_K_VWXR);
-   if (narrow_nst >= 2) {
-      const int TR = 128;
-      const int64_t ntiles = (n + TR - 1) / TR;
-      grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
-      PB_CHK(pb_ensure_partials(ctx, (size_t)grid * (cnt > 0 ? cnt : 1) + 16));
-      a.partials = ctx->d_partials;
-      if (nh <= 4) rc = launch_vwxr_narrow<4>(ctx, a, grid, narrow_shm, narrow_nst);
-      else rc = launch_vwxr_narrow<8>(ctx, a, grid, narrow_shm, narrow_nst);
-      nparts = grid;
-   } else if (wide_nst >= 2) {
-      const int TR = 64;
-      const int NTG = 8 / wide_ng;
-      const int64_t ntiles = (n + TR - 1) / TR;
-      grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
-      PB_CHK(pb_ensure_partials(ctx, (size_t)grid * NTG * (cnt > 0 ? cnt : 1) + 16));
-      a.partials = ctx->d_partials;
+   if (wide_nst >= 2) {
 #define VW3(NTH_, NG_) \
    if (wide_nth == NTH_ && wide_ng == NG_) rc = launch_vwxr_wide<NTH_, NG_>(ctx, a, grid, wide_shm, wide_nst, wide_park);
       VW3(8, 1) VW3(8, 2) VW3(12, 2) VW3(8, 4) VW3(12, 4)
 #undef VW3
-      nparts = grid * NTG;
-   } else if (nst >= 2) {
-      const int TR = 256 / tpr;
-      const int64_t ntiles = n / TR, n_main = ntiles * TR;
-      grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
-      const int tail = n_main < n ? 1 : 0;
-      PB_CHK(pb_ensure_partials(ctx, (size_t)(grid + tail) * (cnt > 0 ? cnt : 1) + 16));
-      a.partials = ctx->d_partials;
-      VwxrArgs am = a;
-      am.n = n_main;
-#define VW2(NTH_, TPR_) \
-   if (nth == NTH_ && tpr == TPR_) rc = launch_vwxr_tma<NTH_, TPR_>(ctx, am, grid, shm2, nst);
-      VW2(4, 2) VW2(8, 2) VW2(16, 2) VW2(24, 2) VW2(12, 4) VW2(16, 4) VW2(20, 4) VW2(24, 4)
-#undef VW2
-      nparts = grid;
-      if (!rc && tail) {
-         // remaining rows through one CTA of the v1 kernel (pointers shifted by n_main rows)
-         VwxrArgs at = a;
-         at.n = n - n_main;
-         at.V = V + n_main, at.W = W + n_main;
-         for (int t = 0; t < 3; t++)
-            if (at.X[t].ptr) at.X[t].ptr += n_main;
-         if (at.Wo.ptr) at.Wo.ptr += n_main;
-         if (at.R.ptr) at.R.ptr += n_main;
-         at.partials = ctx->d_partials + (size_t)grid * cnt;
-         const int NT1 = nh <= 4 ? 4 : nh <= 8 ? 8 : nh <= 16 ? 16 : nh <= 24 ? 24 : nh <= 32 ? 32
-                        : nh <= 40 ? 40 : nh <= 48 ? 48 : 64;
-         const int ngh1 = a.nG > a.nH ? a.nG : a.nH;
-         size_t shd = (size_t)m * NT1 + NT1 + (size_t)ngh1 * VT + (size_t)a.nH * VT;
-         if (shd < VT) shd = VT;
-         switch (NT1) {
-         case 4: rc = launch_vwxr<4>(ctx, at, 1, shd * 8); break;
-         case 8: rc = launch_vwxr<8>(ctx, at, 1, shd * 8); break;
-         case 16: rc = launch_vwxr<16>(ctx, at, 1, shd * 8); break;
-         case 24: rc = launch_vwxr<24>(ctx, at, 1, shd * 8); break;
-         case 32: rc = launch_vwxr<32>(ctx, at, 1, shd * 8); break;
-         case 40: rc = launch_vwxr<40>(ctx, at, 1, shd * 8); break;
-         case 48: rc = launch_vwxr<48>(ctx, at, 1, shd * 8); break;
-         default: rc = launch_vwxr<64>(ctx, at, 1, shd * 8); break;
-         }
-         nparts = grid + 1;
-      }
    } else {
-      if (n > 0) {
-         const int64_t ntiles = (n + VT - 1) / VT;
-         int64_t g = (int64_t)ctx->num_sms * 4;
-         grid = (int)(ntiles < g ? ntiles : g);
-      }
-      if (cnt > 0) {
-         PB_CHK(pb_ensure_partials(ctx, (size_t)grid * cnt));
-         a.partials = ctx->d_partials;
-         // every slot is written by the kernel (unused norm slots as zeros, G below the diagonal by
-         // mirroring): no memset in front of the launch
-      } else {
-         PB_CHK(pb_ensure_partials(ctx, 16));
-         a.partials = ctx->d_partials;
-      }
       const int NT = nh <= 4 ? 4 : nh <= 8 ? 8 : nh <= 16 ? 16 : nh <= 24 ? 24 : nh <= 32 ? 32
                     : nh <= 40 ? 40 : nh <= 48 ? 48 : 64;
       const int ngh = a.nG > a.nH ? a.nG : a.nH;
@@ -1118,13 +634,14 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
       case 48: rc = launch_vwxr<48>(ctx, a, grid, shmem); break;
       default: rc = launch_vwxr<64>(ctx, a, grid, shmem); break;
       }
-      nparts = grid;
    }
    pb_prof_end(ctx, ps, abytes);
    PB_CHK(rc);
-   grid = nparts;
    if (cnt > 0) {
-      PB_CHK(pb_finish_panel(ctx, grid, cnt));
+      if (a.fin.cnt > 0)
+         PB_CHK(pb_collect_panel(ctx, &a.fin));
+      else
+         PB_CHK(pb_finish_panel(ctx, grid * ppc, cnt));
       const double *p = ctx->h_pinned;
       if (o->Rnorms_host)
          for (int c = 0; c < nR; c++) o->Rnorms_host[c] = sqrt(p[a.R.cb + c]);

@@ -50,6 +50,9 @@ def parse():
                     help="host threads of the reference arm (0: min(cores, 16); OpenBLAS on 100+ "
                          "threads is slower on these tall-skinny panels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sampler", default="nvml", choices=["nvml", "smi", "none"],
+                    help="clock/throttle sampling during the timed region (none: measurement experiments only)")
+    ap.add_argument("--sampler-period", type=float, default=0.25)
     ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
                     help="N>1: row-sharded solve with NCCL (strong scaling) or independent replicas")
     return ap.parse_args()
@@ -66,16 +69,22 @@ def workload_name(side):
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
 
-    def __init__(self, index):
+    def __init__(self, index, mode="nvml", period=0.25):
         self.rows = []
         self.stop = False
         self.index = index
+        self.mode = mode
+        self.period = period
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
         # in-process NVML when available (no process spawn, no driver re-initialisation while the
         # launch-latency-bound solver is being timed); nvidia-smi otherwise
+        if self.mode == "none":
+            return
         try:
+            if self.mode != "nvml":
+                raise RuntimeError("nvidia-smi requested")
             import pynvml as nv
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
@@ -87,7 +96,7 @@ class ClockSampler:
                 r = get_reasons(h)
                 act = lambda bit: "Active" if (r & bit) else "Not Active"
                 self.rows.append([str(sm), str(mx), act(0x8), act(0x40), act(0x20), act(0x4)])
-                time.sleep(0.1)
+                time.sleep(self.period)
             return
         except Exception:
             pass
@@ -103,7 +112,7 @@ class ClockSampler:
                     self.rows.append(parts)
             except Exception:
                 pass
-            time.sleep(0.5)
+            time.sleep(max(self.period, 0.5))
 
     def __enter__(self):
         self.t.start()
@@ -279,7 +288,7 @@ def main():
 
     for _ in range(args.warmup):
         resident_solve()
-    with ClockSampler(local) as cs:
+    with ClockSampler(local, args.sampler, args.sampler_period) as cs:
         ms, mv, launches, p = timed(resident_solve, args.steps)
     clocks = cs.summary()
     value = mv / (ms * 1e-3)

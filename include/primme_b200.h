@@ -139,6 +139,10 @@ typedef struct pb200_vwxr_out {
    int nH;              /* H = (V*h(:,0:nH))^H (W*h(:,0:nH)) */
    double *H_host;
    int ldH;
+   double *P_host;      /* optional: P = [V R]^H R, (m + nR) x nR with nR = R.ce - R.cb: the first Gram panel
+                           of the block orthogonalisation (ortho.c:1043-1059) when the new block is the
+                           residual block itself; only when pb200_dvwxr_can_fuse_gram() says so */
+   int ldP;
 } pb200_vwxr_out;
 
 /* One sweep over the rows of V and W (both n x m, leading dimension ld):
@@ -147,6 +151,9 @@ typedef struct pb200_vwxr_out {
 int pb200_dvwxr(pb200_ctx *ctx, int64_t n, const double *V, const double *W, int m,
       int64_t ld, const double *h_host, int ldh, int nh, const double *theta_host,
       const pb200_vwxr_out *out);
+/* 1 when a sweep of this shape can also deliver out->P_host (nh <= 8, no G/H, aligned operands) */
+int pb200_dvwxr_can_fuse_gram(pb200_ctx *ctx, int64_t n, const double *V, const double *W, int m,
+      int64_t ld, int nh, const pb200_vwxr_out *out);
 
 /* ------------------------------------------------------------ K6: multivector utilities -- */
 /* X(:,i) <- X(:,perm[i]) in place (reference permute_vecs, src/linalg/auxiliary.c:716-793) */

@@ -272,6 +272,9 @@ int pb200_dvwxr(pb200_ctx *ctx, int64_t n, const double *V, const double *W, int
    if (o->H_host)
       for (int j = 0; j < o->nH; j++)
          for (int i = 0; i < o->nH; i++) o->H_host[i + (size_t)j * o->ldH] = 0.0;
+   if (o->P_host)
+      for (int j = 0; j < nR; j++)
+         for (int i = 0; i < m + nR; i++) o->P_host[i + (size_t)j * o->ldP] = 0.0;
    for (int64_t r = 0; r < n; r++) {
       /* whole row of V*h and W*h first: outputs may alias V and W (restart.c:692-705) */
       for (int c = 0; c < nh; c++) {
@@ -282,6 +285,16 @@ int pb200_dvwxr(pb200_ctx *ctx, int64_t n, const double *V, const double *W, int
          }
          xrow[c] = sx, yrow[c] = sy;
       }
+      /* optional first Gram panel of the block orthogonalisation, P = [V R]^H R
+       * (src/eigs/ortho.c:1043-1059 with X = R), before any output overwrites the row */
+      if (o->P_host)
+         for (int j = 0; j < nR; j++) {
+            const double rj = yrow[o->R.cb + j] - xrow[o->R.cb + j] * theta[o->R.cb + j];
+            for (int i = 0; i < m; i++) o->P_host[i + (size_t)j * o->ldP] += V[r + (size_t)i * ld] * rj;
+            for (int i = 0; i < nR; i++)
+               o->P_host[m + i + (size_t)j * o->ldP] +=
+                     (yrow[o->R.cb + i] - xrow[o->R.cb + i] * theta[o->R.cb + i]) * rj;
+         }
       for (int t = 0; t < 3; t++)
          if (o->X[t].ptr)
             for (int c = o->X[t].cb; c < o->X[t].ce; c++)
@@ -312,6 +325,14 @@ int pb200_dvwxr(pb200_ctx *ctx, int64_t n, const double *V, const double *W, int
    for (int c = 0; c < nr; c++) o->rnorms_host[c] = sqrt(rn[c]);
    free(Rn), free(xrow);
    return 0;
+}
+
+int pb200_dvwxr_can_fuse_gram(pb200_ctx *ctx, int64_t n, const double *V, const double *W, int m,
+      int64_t ld, int nh, const pb200_vwxr_out *o) {
+   (void)ctx, (void)V, (void)W, (void)ld, (void)n;
+   if (getenv("PB200_NO_FUSE_GRAM")) return 0;
+   return nh > 0 && nh <= 8 && !(o->G_host && o->nG > 0) && !(o->H_host && o->nH > 0) && o->R.ptr &&
+          o->R.ce > o->R.cb && m > 0;
 }
 
 /* ------------------------------------------------------------------ K6: utilities --------- */

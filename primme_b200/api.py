@@ -101,7 +101,8 @@ class VwxrOut(C.Structure):
     _fields_ = [("X", VwxrCols * 3), ("Wo", VwxrCols), ("R", VwxrCols), ("Rnorms_host", C.c_void_p),
                 ("rb", C.c_int), ("re", C.c_int), ("rnorms_host", C.c_void_p),
                 ("nG", C.c_int), ("G_host", C.c_void_p), ("ldG", C.c_int),
-                ("nH", C.c_int), ("H_host", C.c_void_p), ("ldH", C.c_int)]
+                ("nH", C.c_int), ("H_host", C.c_void_p), ("ldH", C.c_int),
+                ("P_host", C.c_void_p), ("ldP", C.c_int)]
 
 
 class Jacobi(C.Structure):
@@ -137,6 +138,7 @@ def _declare(lib):
         "pb200_dspmm_t": (i32, [vp, vp, vp, i64, vp, i64, i32]),
         "pb200_dortho_sweep": (i32, [vp, i64, vp, i32, i64, vp, i32, i64, vp, i32, i64, vp, i32, vp, i32, i32, vp, i32]),
         "pb200_dvwxr": (i32, [vp, i64, vp, vp, i32, i64, vp, i32, i32, vp, P(VwxrOut)]),
+        "pb200_dvwxr_can_fuse_gram": (i32, [vp, i64, vp, vp, i32, i64, i32, P(VwxrOut)]),
         "pb200_dpermute_columns": (i32, [vp, i64, vp, i64, vp, i32]),
         "pb200_dcopy_columns": (i32, [vp, i64, vp, i64, vp, vp, i64, vp, i32]),
         "pb200_daxpy_columns": (i32, [vp, i64, vp, vp, i64, vp, i64, i32]),

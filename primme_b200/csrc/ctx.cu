@@ -47,7 +47,9 @@ extern "C" int pb200_ctx_create(pb200_ctx **out, int device) {
    PB_CUDA(cudaMemset(ctx->d_counters, 0, (1 + PB_FIN_MAXGROUPS) * sizeof(unsigned int)));
    ctx->coef_inline = getenv("PB200_NO_INLINE_COEF") ? 0 : 1;
    ctx->use_wide = getenv("PB200_NO_WIDE") ? 0 : 1;
-   ctx->ortho_2cta = getenv("PB200_ORTHO_1CTA") ? 0 : 1;
+   ctx->use_mma_vwxr = getenv("PB200_NO_MMA_VWXR") ? 0 : 1;
+   ctx->fuse_gram = getenv("PB200_NO_FUSE_GRAM") ? 0 : 1;
+   ctx->ortho_2cta = getenv("PB200_ORTHO_2CTA") ? atoi(getenv("PB200_ORTHO_2CTA")) : 0;
    ctx->use_tma = getenv("PB200_NO_TMA") ? 0 : 1;
    ctx->use_tma_vwxr = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_VWXR")) ? 0 : 1;
    ctx->use_tma_spmm = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_SPMM")) ? 0 : 1;

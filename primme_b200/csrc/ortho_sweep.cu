@@ -16,6 +16,8 @@
 #include "pb200_internal.cuh"
 #include "tma_pipe.cuh"
 #include <string.h>
+#include <stdlib.h>
+#include <time.h>
 
 namespace {
 
@@ -32,6 +34,8 @@ struct SweepArgs {
    int bt;              // leading dimension of Y / column count of the packed C (b padded to 1,2,4,8)
    int stage_doubles;   // size of the stage ring of the MMA kernel (>= the end-of-kernel panel scratch)
    int qpad, xcol0;     // MMA kernel: virtual column of the first V / first X column
+   int dbg;             // timing experiments only (PB200_DBG): wrong results when non-zero
+   unsigned long long *trace;  // PB200_TRACE: [cta][8] %globaltimer stamps
    const double *Cdev;  // (q+mv) x BT, column stride = (q+mv)
    const double *Ydev;  // BT x BT, column stride BT
    int coef_inline;     // 1: C and Y travel in `coef` below (kernel parameter space), no H2D copy
@@ -209,6 +213,14 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
                 : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void pb_stamp(unsigned long long *trace, int slot) {
+   if (trace) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      trace[(size_t)blockIdx.x * 8 + slot] = t;
+   }
+}
+
 constexpr int CS_LD = 12;  // row stride (doubles) of the coefficient blocks in shared memory:
                            // B-fragment loads (row = lane%4, column = lane/4) hit 32 distinct banks
 
@@ -241,6 +253,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_kernel(SweepArgs
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
    if (tid == 0) {
+      pb_stamp(a.trace, 0);
       for (int s = 0; s < nstages; s++) {
          pbtma::mbar_init(&full[s], 1);
          pbtma::mbar_init(&empty[s], NW);
@@ -250,6 +263,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_kernel(SweepArgs
    if (a.do_update) {
       const double *cg = a.coef_inline ? coef.v : a.Cdev;
       const double *yg = a.coef_inline ? coef.v + (size_t)k * a.bt : a.Ydev;
+      for (int i = tid; i < NW * 8 * CS_LD; i += NCT + 32) xw0[i] = 0.0;
       for (int i = tid; i < xcol0 * 8; i += NCT + 32) {
          const int vc = i >> 3, c = i & 7;
          int j = -1;  // real column of [Q V] behind virtual column vc
@@ -267,6 +281,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_kernel(SweepArgs
    __syncthreads();
 
    const int64_t ntiles = (a.n + TR - 1) / TR;  // the last tile may be partial
+   if (tid == 0) pb_stamp(a.trace, 1);
    if (warp == NW) {
       // ------------------------------ producer: one elected lane ------------------------------
       // one tensor-tile copy per operand and tile; rows past n and the pad columns are zero-filled
@@ -306,6 +321,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_kernel(SweepArgs
    uint32_t ph = 0;
    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       pbtma::mbar_wait(&full[s], ph);
+      if (tid == 0 && tile == blockIdx.x) pb_stamp(a.trace, 2);
       const double *st = stage0 + (size_t)s * stage_sz;
       const double *xb = st + xcol0 * S + offg;  // Gram X operand: X(row t of a k-step, column g)
       if (a.do_update) {
@@ -315,7 +331,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_kernel(SweepArgs
          const double *pa = st + offu;
          const double *pc = cpu;
 #pragma unroll 2
-         for (int i = 0; i < nks2; i++) {
+         for (int i = 0; i < ((a.dbg & 2) ? 0 : nks2); i++) {
             const double a0 = pa[0], a1 = pa[4 * S];
             dmma884(d0, d1, a0, pc[0]);
             dmma884(e0, e1, a1, pc[4 * CS_LD]);
@@ -342,21 +358,21 @@ __global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_kernel(SweepArgs
          // CS_LD): the Gram below takes its X operand from there (the stage itself is only ever
          // written by the TMA unit, so no proxy fence is needed before it is refilled)
          const int64_t r = tile * TR + r0w + g;
-         if (2 * t < a.b && r < a.n) a.X[r + (size_t)(2 * t) * a.ldx] = d0;
-         if (2 * t + 1 < a.b && r < a.n) a.X[r + (size_t)(2 * t + 1) * a.ldx] = d1;
+         if (2 * t < a.b && r < a.n && !(a.dbg & 1)) a.X[r + (size_t)(2 * t) * a.ldx] = d0;
+         if (2 * t + 1 < a.b && r < a.n && !(a.dbg & 1)) a.X[r + (size_t)(2 * t + 1) * a.ldx] = d1;
          xw[(2 * t) * CS_LD + g] = d0;
          xw[(2 * t + 1) * CS_LD + g] = d1;
          __syncwarp();
          xb = xw + g * CS_LD + t;
       }
-      if (a.do_gram) {
+      if (a.do_gram && !(a.dbg & 8)) {
          const double *pg = st + offg;
 #pragma unroll
          for (int ks = 0; ks < 2; ks++) {
             const double bf = xb[4 * ks];
 #pragma unroll
             for (int mt = 0; mt < MT; mt++)
-               if (mt < nmtv) dmma884(acc[mt][0], acc[mt][1], pg[mt * 8 * S + 4 * ks], bf);
+               if (mt < nmtv) dmma884(acc[mt][0], acc[mt][1], (a.dbg & 16) ? bf : pg[mt * 8 * S + 4 * ks], bf);
             // X'X block: A(column g, row t) and B(row t, column g) are the same element
             if (a.xx) dmma884(accx[0], accx[1], bf, bf);
          }
@@ -366,6 +382,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_kernel(SweepArgs
       if (++s == nstages) s = 0, ph ^= 1;
    }
 
+   if (tid == 0) pb_stamp(a.trace, 3);
    if (!a.do_gram) return;
    // ---- per-warp panels -> one partial panel per CTA (warp order), through the stage memory ----
    pbtma::named_bar_sync(1, NCT);  // every warp is done with the stages (all issued tiles consumed)
@@ -388,7 +405,9 @@ __global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_kernel(SweepArgs
       for (int w = 0; w < NW; w++) sum += red[((size_t)w * nv + i) * 8 + c];
       out[e] = sum;
    }
+   if (tid == 0) pb_stamp(a.trace, 4);
    pb_finish_device(a.fin, tid, NCT, 15, flag);
+   if (tid == 0) pb_stamp(a.trace, 5);
 }
 
 // partial-panel storage + in-kernel finish for a launch of `grid` CTAs (cnt = 0: no panel)
@@ -426,8 +445,17 @@ int launch_sweep_mma(pb200_ctx *ctx, SweepArgs &a, const SweepMaps &maps, int gr
                MT, NW, shmem, fa.numRegs, nstages, occ);
       }
    }
+   static const int tracing = getenv("PB200_TRACE") ? atoi(getenv("PB200_TRACE")) : 0;
+   struct timespec tA, tB, tC;
+   if (tracing > 1) clock_gettime(CLOCK_MONOTONIC, &tA);
    PB_CHK(sweep_panel_setup(ctx, a, grid, cnt));
+   if (tracing > 1) clock_gettime(CLOCK_MONOTONIC, &tB);
    kern<<<grid, NW * 32 + 32, shmem, ctx->stream>>>(a, ctx->coef, maps, nstages);
+   if (tracing > 1) {
+      clock_gettime(CLOCK_MONOTONIC, &tC);
+      fprintf(stderr, "TRACE2 setup %.2f us, <<<>>> %.2f us\n", (tB.tv_sec - tA.tv_sec) * 1e6 + (tB.tv_nsec - tA.tv_nsec) * 1e-3,
+            (tC.tv_sec - tB.tv_sec) * 1e6 + (tC.tv_nsec - tB.tv_nsec) * 1e-3);
+   }
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
    return 0;
@@ -525,13 +553,14 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
    // ---- main (TMA + DMMA) kernel eligibility: 16-byte aligned columns (tensor maps), enough
    // rows, a ring of >= 2 stages in shared memory ----
    a.bt = BT;
+   a.dbg = getenv("PB200_DBG") ? atoi(getenv("PB200_DBG")) : 0;
    // virtual column layout of a stage (see the kernel): Q padded to 4, V padded so that X starts
    // at a multiple of 8, X padded to 8
    const int qpad = mv > 0 ? (q + 3) & ~3 : (q + 7) & ~7;
    const int xcol0 = mv > 0 ? (qpad + mv + 7) & ~7 : qpad;
    a.qpad = qpad, a.xcol0 = xcol0;
    bool mma_ok = ctx->use_tma && n >= 256 && xcol0 <= 104;
-   int nstages = 0, nw = 16;
+   int nstages = 0, nw = 16, ctas_per_sm = 1;
    const size_t fixed_sm = mma_fixed_smem(xcol0);
    const size_t smem_cap = 227 * 1024;
    size_t stage_d = 0;
@@ -546,6 +575,17 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
          nstages = (int)((smem_cap - fixed_sm) / (stage_d * sizeof(double)));
       }
       if (nstages > 8) nstages = 8;
+      if (nw == 16 && ctx->ortho_2cta == 2) {
+         // two CTAs of 16 consumer warps per SM, 2-3 stages each (twice the resident warps)
+         const int ns = (int)((113 * 1024 - fixed_sm) / (stage_d * sizeof(double)));
+         if (ns >= 2) nstages = ns > 3 ? 3 : ns, ctas_per_sm = 2;
+      } else if (nw == 16 && ctx->ortho_2cta) {
+         // two CTAs of 8 consumer warps (64-row tiles) per SM: the CTAs drift apart, so the MMA
+         // bursts of one overlap the shared-memory / store phases of the other
+         const size_t sd = (size_t)(xcol0 + 8) * (64 + 4);
+         const int ns = (int)((112 * 1024 - fixed_sm) / (sd * sizeof(double)));
+         if (ns >= 3) nw = 8, stage_d = sd, nstages = ns > 4 ? 4 : ns, ctas_per_sm = 2;
+      }
       if (nstages < 2) mma_ok = false;
    }
    SweepMaps maps;
@@ -559,16 +599,27 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
 
    int grid = 0, rc = 0;
    const int cnt = a.do_gram ? rows * b : 0;
+   static unsigned long long *d_trace = NULL;
+   static const int tracing = getenv("PB200_TRACE") ? atoi(getenv("PB200_TRACE")) : 0;
+   struct timespec th0, th1, th2, th3;
+   if (tracing) {
+      if (!d_trace) cudaMalloc((void **)&d_trace, 8 * 1024 * sizeof(unsigned long long));
+      cudaMemsetAsync(d_trace, 0, 8 * 1024 * sizeof(unsigned long long), ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      a.trace = mma_ok ? d_trace : NULL;
+      clock_gettime(CLOCK_MONOTONIC, &th0);
+   }
    int ps = pb_prof_begin(ctx, PB_K_ORTHO);
    if (mma_ok) {
       const int tr = 8 * nw;
       const int64_t ntiles = (n + tr - 1) / tr;  // a partial last tile is zero-filled by the TMA unit
-      grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
+      grid = (int)(ntiles < (int64_t)ctx->num_sms * ctas_per_sm ? ntiles : (int64_t)ctx->num_sms * ctas_per_sm);
       const int nmtv = xcol0 / 8;
       size_t ring = (size_t)nstages * stage_d;
       if (ring < (size_t)nw * (nmtv + 1) * 64) ring = (size_t)nw * (nmtv + 1) * 64;
       a.stage_doubles = (int)ring;
       const size_t shmem = ring * sizeof(double) + fixed_sm;
+      if (tracing) clock_gettime(CLOCK_MONOTONIC, &th1);
 #define PB_MMA(MT_, NW_) rc = launch_sweep_mma<MT_, NW_>(ctx, a, maps, grid, shmem, nstages, cnt)
       if (nw == 16) {
          if (nmtv <= 5) PB_MMA(5, 16);
@@ -595,11 +646,34 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
    }
    pb_prof_end(ctx, ps, abytes);
    PB_CHK(rc);
+   if (tracing) clock_gettime(CLOCK_MONOTONIC, &th2);
    if (a.do_gram) {
       if (a.fin.cnt > 0)
          PB_CHK(pb_collect_panel(ctx, &a.fin));
       else
          PB_CHK(pb_finish_panel(ctx, grid, cnt));
+      if (tracing && a.trace) {
+         clock_gettime(CLOCK_MONOTONIC, &th3);
+         cudaStreamSynchronize(ctx->stream);
+         static unsigned long long ht[8 * 1024];
+         cudaMemcpy(ht, d_trace, sizeof(unsigned long long) * 8 * grid, cudaMemcpyDeviceToHost);
+         unsigned long long mn[6], mx[6];
+         for (int s = 0; s < 6; s++) mn[s] = ~0ULL, mx[s] = 0;
+         for (int c = 0; c < grid; c++)
+            for (int s = 0; s < 6; s++) {
+               const unsigned long long t = ht[c * 8 + s];
+               if (t == 0) continue;
+               if (t < mn[s]) mn[s] = t;
+               if (t > mx[s]) mx[s] = t;
+            }
+         auto us = [](const timespec &x, const timespec &y) { return (y.tv_sec - x.tv_sec) * 1e6 + (y.tv_nsec - x.tv_nsec) * 1e-3; };
+         const double t0 = (double)mn[0];
+         fprintf(stderr, "TRACE n=%lld upd=%d host: prep %.1f launch %.1f wait %.1f total %.1f us | gpu (us from first CTA entry) "
+                         "entry<=%.1f setup<=%.1f first_tile %.1f..%.1f loop_done %.1f..%.1f partial %.1f..%.1f finish %.1f..%.1f\n",
+               (long long)n, a.do_update, us(th0, th1), us(th1, th2), us(th2, th3), us(th0, th3),
+               (mx[0] - t0) * 1e-3, (mx[1] - t0) * 1e-3, (mn[2] - t0) * 1e-3, (mx[2] - t0) * 1e-3, (mn[3] - t0) * 1e-3,
+               (mx[3] - t0) * 1e-3, (mn[4] - t0) * 1e-3, (mx[4] - t0) * 1e-3, (mn[5] - t0) * 1e-3, (mx[5] - t0) * 1e-3);
+      }
       for (int c = 0; c < b; c++)
          for (int j = 0; j < rows; j++) P_host[j + (size_t)c * ldp] = ctx->h_pinned[j + (size_t)c * rows];
    }

@@ -63,6 +63,8 @@ struct pb200_ctx {
    int use_tma_vwxr;      // same switch for the VWXR kernel alone
    int use_tma_spmm;      // persistent bulk-copy SpMM (v2)
    int use_wide;          // v3 wide VWXR kernel for the restart sweep
+   int use_mma_vwxr;      // tensor-map TMA + DMMA VWXR kernel (default)
+   int fuse_gram;         // candidates sweep also delivers the first Gram panel of the block ortho
    int coef_inline;       // small coefficient matrices travel as kernel parameters (no H2D copy)
    PbCoef coef;           // host staging of that block for the next launch
    int ortho_2cta;        // prefer 2 CTAs/SM x 2 stages over 1 CTA/SM x 4 stages in the ortho sweep

@@ -18,6 +18,7 @@
 #include <math.h>
 #include <string.h>
 #include <vector>
+#include <stdlib.h>
 
 namespace {
 
@@ -38,6 +39,10 @@ struct VwxrArgs {
    int rb, re;
    int nG, nH;
    int need_y;              // whether W*h is needed at all
+   int dbg;                 // timing experiments only (PB200_DBG): wrong results when non-zero
+   int nP;                  // > 0: also P = [V R]^T R, (m + nP) x nP with nP = R.ce - R.cb (MMA kernel only)
+   int mpad;                // MMA kernel: m rounded up to a multiple of 4 (k-steps of the DMMA shape)
+   int stage_doubles;       // MMA kernel: size of the stage ring (>= the end-of-kernel reduction scratch)
    double *partials;        // [grid][cnt] : Rnorms(nR) | rnorms(nr) | G(nG*nG) | H(nH*nH)
    PbFin fin;               // in-kernel panel finish (fin.cnt == 0: the host launches the reduction)
 };
@@ -481,6 +486,348 @@ __global__ void __launch_bounds__(256 + 32) vwxr_wide_kernel(VwxrArgs a, const _
    if (cnt > 0) pb_finish_device(a.fin, tid, 256, 15, reinterpret_cast<int *>(empty + NB));
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Main kernel: tensor-map TMA stages + fp64 tensor-core (DMMA m8n8k4) contractions, warp-local
+// rows -- the same skeleton as ortho_sweep_mma_kernel.  A producer thread streams TR-row tiles of
+// [V | W] (column stride TR+4 doubles: conflict-free fragment loads; columns m..mpad and rows past
+// n are zero-filled by the TMA unit) into a ring of stages.  Each consumer warp owns 8 rows:
+//   X(8 x 8 NT8) = V(8 x m) h,  Y = W h            2 * NT8 * mpad/4 DMMAs, h fragments from shared
+//   R = Y - X diag(theta), residual norms, scatter of X / Y / R column ranges (fragment layout:
+//        a warp store covers 4 columns x 8 consecutive rows)
+//   G += X^T X (upper tiles), H += X^T Y            through a per-warp transposing scratch
+//   P += [V R]^T R                                  (nP > 0) V^T fragments straight from the stage
+// and keeps every accumulator in registers across all tiles of the CTA.  The warps meet once at
+// the end (per-warp panels summed in warp order through the stage memory), then the in-kernel
+// finish delivers the reduced panel.  fp64 has no tcgen05 kind: mma.sync DMMA is the tensor path.
+__device__ __forceinline__ void vdmma884(double &d0, double &d1, double a, double b) {
+   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                : "+d"(d0), "+d"(d1)
+                : "d"(a), "d"(b));
+}
+
+struct VwxrMaps {
+   CUtensorMap v, w;  // boxes of (TR+4) rows x mpad columns
+};
+
+constexpr int XW_LD = 12;  // row stride of the per-warp transposing scratch ([column][row])
+// rows of columns 4..7 of every 8-column tile are XORed with 4: both the fragment-layout stores
+// (columns 2t, 2t+1, row g) and the operand loads (column g, row t + 4 ks) are bank-conflict free
+__device__ __forceinline__ int xw_at(int col, int row) { return col * XW_LD + (row ^ (col & 4)); }
+
+template <int NT8, int MT, int NW>
+__global__ void __launch_bounds__(NW * 32 + 32) vwxr_mma_kernel(VwxrArgs a, const __grid_constant__ PbCoef coef,
+      const __grid_constant__ VwxrMaps maps, int nstages) {
+   constexpr int TR = 8 * NW, S = TR + 4, NCT = NW * 32;
+   constexpr int NC = 8 * NT8;       // padded column count of h
+   constexpr int HS_LD = NC + 4;     // row stride of h in shared memory (= 4 or 12 mod 16)
+   constexpr int NTG = NT8;          // 8-column tiles of G / H
+   extern __shared__ __align__(128) unsigned char smraw[];
+   const int m = a.m, mpad = a.mpad;
+   const int stage_sz = 2 * mpad * S;
+   double *stage0 = reinterpret_cast<double *>(smraw);   // ring (later: reduction scratch)
+   double *hs = stage0 + a.stage_doubles;                // mpad * HS_LD
+   double *th = hs + (size_t)mpad * HS_LD;               // NC
+   double *xw0 = th + NC;                                // NW * 2 * NC * XW_LD
+   uint64_t *full = reinterpret_cast<uint64_t *>(xw0 + (size_t)NW * 2 * NC * XW_LD);
+   uint64_t *empty = full + nstages;
+   int *flag = reinterpret_cast<int *>(empty + nstages);
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+   if (tid == 0) {
+      for (int s = 0; s < nstages; s++) {
+         pbtma::mbar_init(&full[s], 1);
+         pbtma::mbar_init(&empty[s], NW);
+      }
+      pbtma::fence_barrier_init();
+   }
+   {
+      const double *hg = a.coef_inline ? coef.v : a.hdev;
+      const double *tg = a.coef_inline ? coef.v + (size_t)m * a.nh : a.thetadev;
+      for (int i = tid; i < mpad * NC; i += NCT + 32) {
+         const int k = i / NC, c = i % NC;
+         hs[k * HS_LD + c] = (k < m && c < a.nh) ? hg[k + (size_t)c * m] : 0.0;
+      }
+      for (int i = tid; i < NC; i += NCT + 32) th[i] = i < a.nh ? tg[i] : 0.0;
+   }
+   __syncthreads();
+
+   const int64_t ntiles = (a.n + TR - 1) / TR;
+   if (warp == NW) {
+      if (lane != 0) return;
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t bytes = (uint32_t)(stage_sz * sizeof(double));
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+         pbtma::mbar_wait(&empty[s], ph ^ 1);
+         double *dst = stage0 + (size_t)s * stage_sz;
+         const int r0 = (int)(tile * TR);
+         pbtma::mbar_arrive_expect_tx(&full[s], bytes);
+         pbtma::tensor_g2s_2d(dst, &maps.v, r0, 0, &full[s]);
+         pbtma::tensor_g2s_2d(dst + mpad * S, &maps.w, r0, 0, &full[s]);
+         if (++s == nstages) s = 0, ph ^= 1;
+      }
+      return;
+   }
+
+   // ------------------------------ consumer warps ------------------------------
+   const int g = lane >> 2, t = lane & 3;
+   const int r0w = warp * 8;
+   const int nks = mpad >> 2;
+   const int nR = a.R.ptr ? a.R.ce - a.R.cb : 0;
+   const bool gh = a.nG > 0 || a.nH > 0;
+   const int nmtv = a.nP > 0 ? (m + 7) >> 3 : 0;     // tiles of V in the P panel
+   double *xw = xw0 + (size_t)warp * 2 * NC * XW_LD;  // X (or R in P mode), [column][row]
+   double *yw = xw + NC * XW_LD;                      // Y
+
+   // Loop-invariant store plan of this thread's 2 NT8 columns (slot q = 2 i + j <-> column
+   // 8 i + 2 t + j): one destination for the V h value, one for the W h value or the residual.
+   // A column with more destinations than that (locking: X[2] overlapping X[0]) takes the
+   // generic path.
+   constexpr int NQ = 2 * NT8;
+   double *px[NQ], *py[NQ];
+   double thv[NQ];
+   unsigned yres = 0, wnorm = 0, slow = 0;
+#pragma unroll
+   for (int q = 0; q < NQ; q++) {
+      const int cc = 8 * (q >> 1) + 2 * t + (q & 1);
+      px[q] = py[q] = nullptr;
+      thv[q] = th[cc];
+      int nx = 0, ny = 0;
+#pragma unroll
+      for (int u = 0; u < 3; u++)
+         if (a.X[u].ptr && cc >= a.X[u].cb && cc < a.X[u].ce) {
+            if (!nx) px[q] = a.X[u].ptr + (size_t)(cc - a.X[u].cb) * a.X[u].ld;
+            nx++;
+         }
+      if (a.Wo.ptr && cc >= a.Wo.cb && cc < a.Wo.ce) py[q] = a.Wo.ptr + (size_t)(cc - a.Wo.cb) * a.Wo.ld, ny++;
+      const bool inR = nR > 0 && cc >= a.R.cb && cc < a.R.ce;
+      if (inR) {
+         if (!ny) py[q] = a.R.ptr + (size_t)(cc - a.R.cb) * a.R.ld, yres |= 1u << q;
+         ny++;
+      }
+      if (inR || (cc >= a.rb && cc < a.re)) wnorm |= 1u << q;
+      if (nx > 1 || ny > 1) slow |= 1u << q;
+   }
+   slow = __any_sync(0xffffffffu, slow != 0) ? 1u : 0u;  // warp-uniform choice of the path
+
+   double nrm[NT8][2];
+   double Gacc[NTG * (NTG + 1) / 2][2], Hacc[NTG * NTG][2];
+   double Pacc[MT > 0 ? MT : 1][2], RRacc[2];
+#pragma unroll
+   for (int i = 0; i < NT8; i++) nrm[i][0] = nrm[i][1] = 0.0;
+#pragma unroll
+   for (int i = 0; i < NTG * (NTG + 1) / 2; i++) Gacc[i][0] = Gacc[i][1] = 0.0;
+#pragma unroll
+   for (int i = 0; i < NTG * NTG; i++) Hacc[i][0] = Hacc[i][1] = 0.0;
+#pragma unroll
+   for (int i = 0; i < (MT > 0 ? MT : 1); i++) Pacc[i][0] = Pacc[i][1] = 0.0;
+   RRacc[0] = RRacc[1] = 0.0;
+
+   const int offu = r0w + t * S + g;  // A fragment of V h: column t of a k-step, row g
+   const int offg = r0w + g * S + t;  // A fragment of V^T R: column g of a tile, row t of a k-step
+   const double *hb = hs + t * HS_LD + g;
+   // scratch offsets: fragment-layout store of column 2 t + j (tile i adds 8 i XW_LD), operand
+   // load of column g, row t + 4 ks
+   const int so0 = xw_at(2 * t, g), so1 = xw_at(2 * t + 1, g);
+   const int lo0 = xw_at(g, t), lo1 = xw_at(g, t + 4);
+   const int pcol0 = xw_at((2 * t - a.R.cb) & 7, g), pcol1 = xw_at((2 * t + 1 - a.R.cb) & 7, g);
+
+   int s = 0;
+   uint32_t ph = 0;
+   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      pbtma::mbar_wait(&full[s], ph);
+      const double *st = stage0 + (size_t)s * stage_sz;
+      double X[NT8][2], Y[NT8][2];
+#pragma unroll
+      for (int i = 0; i < NT8; i++) X[i][0] = X[i][1] = Y[i][0] = Y[i][1] = 0.0;
+      {
+         const double *pv = st + offu, *pw = pv + mpad * S, *pb = hb;
+#pragma unroll 2
+         for (int ks = 0; ks < ((a.dbg & 4) ? 1 : nks); ks++) {
+            const double av = pv[0], aw = pw[0];
+#pragma unroll
+            for (int i = 0; i < NT8; i++) {
+               const double bf = pb[8 * i];
+               vdmma884(X[i][0], X[i][1], av, bf);
+               vdmma884(Y[i][0], Y[i][1], aw, bf);
+            }
+            pv += 4 * S, pw += 4 * S, pb += 4 * HS_LD;
+         }
+      }
+      if (MT == 0) {  // the stage is not needed any more (P mode reads V^T from it below)
+         __syncwarp();
+         if (lane == 0) pbtma::mbar_arrive(&empty[s]);
+      }
+      // ---- residuals, norms, scatter (fragment layout: row g, columns 8 i + 2 t + j) ----
+      const int64_t r = tile * TR + r0w + g;
+      const bool rok = r < a.n && !(a.dbg & 1);
+      if (!slow) {
+#pragma unroll
+         for (int q = 0; q < NQ; q++) {
+            const double x = X[q >> 1][q & 1], y = Y[q >> 1][q & 1];
+            const double res = y - x * thv[q];
+            if (wnorm & (1u << q)) nrm[q >> 1][q & 1] += res * res;
+            if (rok) {
+               if (px[q]) px[q][r] = x;
+               if (py[q]) py[q][r] = (yres & (1u << q)) ? res : y;
+            }
+            if (MT > 0)
+               xw[(q & 1) ? pcol1 : pcol0] = (yres & (1u << q)) ? res : 0.0;
+         }
+      } else {
+#pragma unroll
+         for (int i = 0; i < NT8; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+               const int cc = 8 * i + 2 * t + j;
+               const double x = X[i][j], y = Y[i][j];
+               const double res = y - x * th[cc];
+               const bool inR = nR > 0 && cc >= a.R.cb && cc < a.R.ce;
+               if (inR || (cc >= a.rb && cc < a.re)) nrm[i][j] += res * res;
+               if (rok) {
+#pragma unroll
+                  for (int u = 0; u < 3; u++)
+                     if (a.X[u].ptr && cc >= a.X[u].cb && cc < a.X[u].ce)
+                        a.X[u].ptr[r + (size_t)(cc - a.X[u].cb) * a.X[u].ld] = x;
+                  if (a.Wo.ptr && cc >= a.Wo.cb && cc < a.Wo.ce)
+                     a.Wo.ptr[r + (size_t)(cc - a.Wo.cb) * a.Wo.ld] = y;
+                  if (inR) a.R.ptr[r + (size_t)(cc - a.R.cb) * a.R.ld] = res;
+               }
+               if (MT > 0) xw[j ? pcol1 : pcol0] = inR ? res : 0.0;
+            }
+      }
+      if (MT > 0) {
+         // P mode (NT8 == 1): the residual block sits compacted in scratch columns 0..nR-1 (zeros
+         // in the others: cc -> (cc - R.cb) mod 8 is a bijection of the 8 columns)
+         __syncwarp();
+         const double *pg = st + offg;
+#pragma unroll
+         for (int ks = 0; ks < 2; ks++) {
+            const double bf = xw[ks ? lo1 : lo0];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+               if (mt < nmtv) vdmma884(Pacc[mt][0], Pacc[mt][1], pg[mt * 8 * S + 4 * ks], bf);
+            vdmma884(RRacc[0], RRacc[1], bf, bf);
+         }
+         __syncwarp();
+         if (lane == 0) pbtma::mbar_arrive(&empty[s]);
+      } else if (gh && !(a.dbg & 2)) {
+         // every tile of G (upper) and H is accumulated, whatever nG and nH: columns past them
+         // are simply not read back
+#pragma unroll
+         for (int i = 0; i < NT8; i++) {
+            xw[8 * i * XW_LD + so0] = X[i][0], xw[8 * i * XW_LD + so1] = X[i][1];
+            yw[8 * i * XW_LD + so0] = Y[i][0], yw[8 * i * XW_LD + so1] = Y[i][1];
+         }
+         __syncwarp();
+#pragma unroll
+         for (int ks = 0; ks < 2; ks++) {
+            double xf[NTG], yf[NTG];
+#pragma unroll
+            for (int i = 0; i < NTG; i++) {
+               xf[i] = xw[8 * i * XW_LD + (ks ? lo1 : lo0)];
+               yf[i] = yw[8 * i * XW_LD + (ks ? lo1 : lo0)];
+            }
+            int ig = 0;
+#pragma unroll
+            for (int tj = 0; tj < NTG; tj++)
+#pragma unroll
+               for (int ti = 0; ti < NTG; ti++) {
+                  if (ti <= tj) vdmma884(Gacc[ig][0], Gacc[ig][1], xf[ti], xf[tj]), ig++;
+                  vdmma884(Hacc[ti + NTG * tj][0], Hacc[ti + NTG * tj][1], xf[ti], yf[tj]);
+               }
+         }
+         __syncwarp();  // the scratch is rewritten by the next tile
+      }
+      if (++s == nstages) s = 0, ph ^= 1;
+   }
+
+   // ---- per-warp panels -> one partial panel per CTA (warp order), through the stage memory ----
+   const int nn = (nR + (a.re - a.rb)) > 0 ? a.nh : 0;
+   const int prow = m + a.nP;
+   const int cnt = nn + a.nG * a.nG + a.nH * a.nH + prow * a.nP;
+   if (cnt <= 0) return;
+   constexpr int NGT = NTG * (NTG + 1) / 2, NHT = NTG * NTG, NPT = MT > 0 ? MT + 1 : 0;
+   constexpr int WSZ = (NGT + NHT + NPT) * 64 + NC;  // doubles per warp
+   pbtma::named_bar_sync(1, NCT);  // every warp is done with the stages
+   double *red = stage0 + (size_t)warp * WSZ;
+   auto put = [&](int tile_id, const double *acc2) {
+      *reinterpret_cast<double2 *>(red + ((size_t)tile_id * 8 + g) * 8 + 2 * t) = make_double2(acc2[0], acc2[1]);
+   };
+   if (MT == 0) {
+#pragma unroll
+      for (int i = 0; i < NGT; i++) put(i, Gacc[i]);
+#pragma unroll
+      for (int i = 0; i < NHT; i++) put(NGT + i, Hacc[i]);
+   } else {
+#pragma unroll
+      for (int i = 0; i < (MT > 0 ? MT : 1); i++) put(NGT + NHT + i, Pacc[i]);
+      put(NGT + NHT + MT, RRacc);
+   }
+#pragma unroll
+   for (int i = 0; i < NT8; i++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+         double v = nrm[i][j];
+         v += __shfl_xor_sync(0xffffffffu, v, 4);
+         v += __shfl_xor_sync(0xffffffffu, v, 8);
+         v += __shfl_xor_sync(0xffffffffu, v, 16);
+         if (g == 0) red[(NGT + NHT + NPT) * 64 + 8 * i + 2 * t + j] = v;
+      }
+   pbtma::named_bar_sync(1, NCT);
+   double *out = a.partials + (size_t)blockIdx.x * cnt;
+   const int offG = nn, offH = offG + a.nG * a.nG, offP = offH + a.nH * a.nH;
+   for (int e = tid; e < cnt; e += NCT) {
+      int idx;  // index inside a warp's block of `red`
+      if (e < offG) {
+         idx = (NGT + NHT + NPT) * 64 + e;
+      } else if (e < offH) {
+         int i = (e - offG) % a.nG, j = (e - offG) / a.nG;
+         if (i > j) { const int sw = i; i = j, j = sw; }  // G is symmetric: upper tiles only
+         const int ti = i >> 3, tj = j >> 3;
+         idx = ((tj * (tj + 1) / 2 + ti) * 8 + (i & 7)) * 8 + (j & 7);
+      } else if (e < offP) {
+         const int i = (e - offH) % a.nH, j = (e - offH) / a.nH;
+         idx = ((NGT + (i >> 3) + NTG * (j >> 3)) * 8 + (i & 7)) * 8 + (j & 7);
+      } else {
+         const int i = (e - offP) % prow, j = (e - offP) / prow;
+         idx = i < m ? ((NGT + NHT + (i >> 3)) * 8 + (i & 7)) * 8 + j : ((NGT + NHT + MT) * 8 + (i - m)) * 8 + j;
+      }
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; w++) sum += stage0[(size_t)w * WSZ + idx];
+      out[e] = sum;
+   }
+   pb_finish_device(a.fin, tid, NCT, 15, flag);
+}
+
+template <int NT8, int MT, int NW>
+int launch_vwxr_mma(pb200_ctx *ctx, const VwxrArgs &a, const VwxrMaps &maps, int grid, size_t shmem, int nstages) {
+   auto kern = vwxr_mma_kernel<NT8, MT, NW>;
+   static size_t attr_shmem = 0;
+   if (shmem > attr_shmem) {
+      PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+      attr_shmem = shmem;
+   }
+   if (getenv("PB200_DEBUG")) {
+      static size_t seen = 0;
+      if (seen != shmem) {
+         seen = shmem;
+         int occ = 0;
+         cudaFuncAttributes fa;
+         cudaFuncGetAttributes(&fa, kern);
+         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32 + 32, shmem);
+         fprintf(stderr, "primme_b200: vwxr_mma<%d,%d,%d> dyn smem %zu regs %d stages %d -> %d CTA/SM\n", NT8, MT, NW,
+               shmem, fa.numRegs, nstages, occ);
+      }
+   }
+   kern<<<grid, NW * 32 + 32, shmem, ctx->stream>>>(a, ctx->coef, maps, nstages);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   return 0;
+}
+
 template <int NTH, int NG>
 int launch_vwxr_wide(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem, int nstages, int park_cols) {
    auto kern = vwxr_wide_kernel<NTH, NG>;
@@ -529,9 +876,11 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
    a.nG = o->G_host ? o->nG : 0;
    a.nH = o->H_host ? o->nH : 0;
    a.need_y = (a.Wo.ptr || a.R.ptr || a.re > a.rb || a.nH > 0) ? 1 : 0;
+   a.dbg = getenv("PB200_DBG") ? atoi(getenv("PB200_DBG")) : 0;
    const int nR = a.R.ptr ? a.R.ce - a.R.cb : 0, nr = a.re - a.rb;
    const int nn = (nR + nr) > 0 ? nh : 0;
-   const int cnt = nn + a.nG * a.nG + a.nH * a.nH;
+   int cnt = nn + a.nG * a.nG + a.nH * a.nH;
+   if (o->P_host && nR <= 0) return PB200_ERR_ARG;
    {
       int gb = (a.nG + 1) / 2, hb = (a.nH + 1) / 2;
       if (gb * gb + hb * hb > 768) return PB200_ERR_ARG;
@@ -593,8 +942,52 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
       }
    }
 
+   // ---- main plan: tensor-map TMA + DMMA kernel (candidates with nh <= 8, restart with nh <= 32) ----
+   int mma_nt8 = 0, mma_mt = 0, mma_nw = 0, mma_nst = 0;
+   size_t mma_shm = 0;
+   VwxrMaps maps;
+   {
+      const int nt8 = (nh + 7) / 8;
+      const int ngh = a.nG > a.nH ? a.nG : a.nH;
+      const bool wantP = o->P_host != NULL;
+      bool ok = ctx->use_tma_vwxr && ctx->use_mma_vwxr && a.need_y && nt8 <= 4 && ngh <= 8 * nt8 && m > 0 && m <= 96 &&
+                n >= 256 && (((uintptr_t)V) & 15) == 0 && (((uintptr_t)W) & 15) == 0 && ld % 2 == 0 &&
+                (!wantP || (nt8 == 1 && ngh == 0 && m <= 72));
+      if (ok) {
+         const int mpad = (m + 3) & ~3;
+         const int mt = wantP ? ((m + 7) / 8 <= 5 ? 5 : 9) : 0;
+         const int NC = 8 * nt8;
+         auto plan = [&](int nw, int *nst, size_t *shm) {
+            const size_t stage = (size_t)2 * mpad * (8 * nw + 4);
+            const size_t wsz = (size_t)(nt8 * (nt8 + 1) / 2 + nt8 * nt8 + (mt ? mt + 1 : 0)) * 64 + NC;
+            const size_t fixed = ((size_t)mpad * (NC + 4) + NC + (size_t)nw * 2 * NC * XW_LD) * sizeof(double) + 2 * 8 * sizeof(uint64_t) + 64;
+            int st = (int)((227 * 1024 - fixed) / (stage * sizeof(double)));
+            if (st > 6) st = 6;
+            size_t ring = (size_t)st * stage;
+            if (ring < wsz * nw) ring = wsz * nw;
+            *nst = st, *shm = ring * sizeof(double) + fixed;
+            a.stage_doubles = (int)ring;
+            return st >= 2 && *shm <= 227 * 1024;
+         };
+         int nw = (nt8 == 1 && mt <= 5) ? 16 : 8;
+         if (nw == 16 && !(plan(16, &mma_nst, &mma_shm) && mma_nst >= 3)) nw = 8;
+         ok = plan(nw, &mma_nst, &mma_shm);
+         if (ok) {
+            memset(&maps, 0, sizeof(maps));
+            ok = !pb_tensor_map_2d(&maps.v, V, n, m, ld, 8 * nw + 4, mpad) && !pb_tensor_map_2d(&maps.w, W, n, m, ld, 8 * nw + 4, mpad);
+         }
+         if (ok) mma_nt8 = nt8, mma_mt = mt, mma_nw = nw, a.mpad = mpad, a.nP = wantP ? nR : 0;
+      }
+      if (wantP && !mma_nt8) return PB200_ERR_ARG;  // callers ask for P only after pb200_dvwxr_can_fuse_gram()
+      if (mma_nt8) cnt += (m + a.nP) * a.nP;
+   }
+
    int grid = 1, ppc = 1, rc = 0;
-   if (wide_nst >= 2) {
+   if (mma_nt8) {
+      const int tr = 8 * mma_nw;
+      const int64_t ntiles = (n + tr - 1) / tr;
+      grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
+   } else if (wide_nst >= 2) {
       const int64_t ntiles = (n + 63) / 64;
       grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
       ppc = 8 / wide_ng;
@@ -612,7 +1005,12 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
       a.partials = ctx->d_partials;
    }
    int ps = pb_prof_begin(ctx, PB_K_VWXR);
-   if (wide_nst >= 2) {
+   if (mma_nt8) {
+#define VM(NT8_, MT_, NW_) \
+   if (mma_nt8 == NT8_ && mma_mt == MT_ && mma_nw == NW_) rc = launch_vwxr_mma<NT8_, MT_, NW_>(ctx, a, maps, grid, mma_shm, mma_nst);
+      VM(1, 0, 16) VM(1, 5, 16) VM(1, 0, 8) VM(1, 5, 8) VM(1, 9, 8) VM(2, 0, 8) VM(3, 0, 8) VM(4, 0, 8)
+#undef VM
+   } else if (wide_nst >= 2) {
 #define VW3(NTH_, NG_) \
    if (wide_nth == NTH_ && wide_ng == NG_) rc = launch_vwxr_wide<NTH_, NG_>(ctx, a, grid, wide_shm, wide_nst, wide_park);
       VW3(8, 1) VW3(8, 2) VW3(12, 2) VW3(8, 4) VW3(12, 4)
@@ -652,6 +1050,11 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
       const double *ph = pg + a.nG * a.nG;
       for (int j = 0; j < a.nH; j++)
          for (int i = 0; i < a.nH; i++) o->H_host[i + (size_t)j * o->ldH] = ph[i + (size_t)j * a.nH];
+      if (a.nP > 0) {
+         const double *pp = ph + a.nH * a.nH;
+         for (int j = 0; j < a.nP; j++)
+            for (int i = 0; i < m + a.nP; i++) o->P_host[i + (size_t)j * o->ldP] = pp[i + (size_t)j * (m + a.nP)];
+      }
    }
    return 0;
 }
@@ -724,12 +1127,27 @@ static int vwxr_general(pb200_ctx *ctx, int64_t n, const double *V, const double
    return 0;
 }
 
+// whether a sweep of this shape can also deliver P = [V R]^T R (out->P_host)
+extern "C" int pb200_dvwxr_can_fuse_gram(pb200_ctx *ctx, int64_t n, const double *V, const double *W, int m,
+      int64_t ld, int nh, const pb200_vwxr_out *o) {
+   const int nG = o->G_host ? o->nG : 0, nH = o->H_host ? o->nH : 0;
+   const int nR = (o->R.ptr && o->R.ce > o->R.cb) ? o->R.ce - o->R.cb : 0;
+   if (!ctx->use_tma_vwxr || !ctx->use_mma_vwxr || !ctx->fuse_gram) return 0;
+   if (nh <= 0 || nh > 8 || nG > 0 || nH > 0 || nR <= 0 || m <= 0 || m > 72 || n < 256) return 0;
+   if ((((uintptr_t)V) & 15) != 0 || (((uintptr_t)W) & 15) != 0 || ld % 2 != 0) return 0;
+   // the stage ring must hold >= 2 stages of 64-row tiles
+   const int mpad = (m + 3) & ~3;
+   const size_t stage = (size_t)2 * mpad * 68 * sizeof(double);
+   return 2 * stage + 40 * 1024 <= 227 * 1024;
+}
+
 extern "C" int pb200_dvwxr(pb200_ctx *ctx, int64_t n, const double *V, const double *W, int m,
       int64_t ld, const double *h_host, int ldh, int nh, const double *theta_host,
       const pb200_vwxr_out *o) {
    if (nh <= 0 || m < 0) return 0;
    const int nG = o->G_host ? o->nG : 0, nH = o->H_host ? o->nH : 0;
    const int gb = (nG + 1) / 2, hb = (nH + 1) / 2;
+   if (o->P_host && !pb200_dvwxr_can_fuse_gram(ctx, n, V, W, m, ld, nh, o)) return PB200_ERR_ARG;
    if (nh <= 64 && gb * gb + hb * hb <= 768)
       return vwxr_fast(ctx, n, V, W, m, ld, h_host, ldh, nh, theta_host, o);
    return vwxr_general(ctx, n, V, W, m, ld, h_host, ldh, nh, theta_host, o);

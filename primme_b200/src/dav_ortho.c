@@ -153,6 +153,12 @@ done:
  * ---------------------------------------------------------------------------------------- */
 int pb_ortho_block(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const double *locked,
       int64_t ldLocked, int numLocked, double *RLocked, int ldRLocked, int *b2_out) {
+   return pb_ortho_block_p0(S, V, ldV, b1, b2, locked, ldLocked, numLocked, RLocked, ldRLocked, b2_out, NULL, 0);
+}
+
+int pb_ortho_block_p0(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const double *locked,
+      int64_t ldLocked, int numLocked, double *RLocked, int ldRLocked, int *b2_out, const double *P0,
+      int ldP0) {
    primme_params *primme = S->primme;
    b2++; /* C range convention from here on */
    if (b2 <= b1) {
@@ -221,11 +227,16 @@ int pb_ortho_block(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const d
          }
          Yc = Yapply;
       }
-      rc = pb200_dortho_sweep(S->dev, S->n, locked, numLocked, ldLocked, V, b1, ldV,
-            V + (size_t)ldV * b1, nb, ldV, Cc, nVL > 0 ? nVL : 1, Yc, nb, 1, A, ldG);
-      if (rc) goto done;
-      rc = pb_reduce_panel(S, A, nVL + nb, nb, ldG);
-      if (rc) goto done;
+      if (its == 0 && P0 && numLocked == 0) {
+         /* the sweep that produced the block already reduced this panel (candidates sweep) */
+         hl_copy(P0, nVL + nb, nb, ldP0, A, ldG);
+      } else {
+         rc = pb200_dortho_sweep(S->dev, S->n, locked, numLocked, ldLocked, V, b1, ldV,
+               V + (size_t)ldV * b1, nb, ldV, Cc, nVL > 0 ? nVL : 1, Yc, nb, 1, A, ldG);
+         if (rc) goto done;
+         rc = pb_reduce_panel(S, A, nVL + nb, nb, ldG);
+         if (rc) goto done;
+      }
       primme->stats.numOrthoInnerProds += (double)nVL * nb + (double)nb * nb;
 
       /* stop one sweep after the block first looks well conditioned (:652-665) */

@@ -113,14 +113,28 @@ static int candidates_sweep(pb_solver *S, int basisSize, const double *hblk, con
    const double t0 = hl_wtime();
    pb200_vwxr_out o;
    memset(&o, 0, sizeof(o));
+   int fused = 0;
    if (computeXR) {
       o.X[0].ptr = X, o.X[0].ld = S->ld, o.X[0].cb = 0, o.X[0].ce = nb;
       o.R.ptr = R, o.R.ld = S->ld, o.R.cb = 0, o.R.ce = nb;
       o.Rnorms_host = norms;
+      /* the residual block becomes the new basis block unchanged (no preconditioner, no locked
+       * vectors): the same sweep delivers the first Gram panel of its orthogonalisation */
+      S->fusedP_nb = 0;
+      S->fuse_sweeps++;
+      if (S->fuse_enabled && X == S->V + (size_t)S->ld * basisSize &&
+            pb200_dvwxr_can_fuse_gram(S->dev, S->n, S->V, S->W, basisSize, S->ld, nb, &o)) {
+         o.P_host = S->fusedP, o.ldP = S->maxBasis + 8;
+         fused = 1;
+      }
    } else {
       o.rb = 0, o.re = nb, o.rnorms_host = norms;
    }
    CHK(pb200_dvwxr(S->dev, S->n, S->V, S->W, basisSize, S->ld, hblk, S->maxBasis, nb, theta, &o));
+   if (fused) {
+      CHK(pb_reduce_panel(S, S->fusedP, basisSize + nb, nb, S->maxBasis + 8));
+      S->fusedP_m = basisSize, S->fusedP_nb = nb;
+   }
    if (primme->numProcs > 1 && pb200_ctx_nranks(S->dev) <= 1) {
       for (int i = 0; i < nb; i++) norms[i] *= norms[i];
       CHK(pb_global_sum(S, norms, nb));
@@ -546,14 +560,26 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
                   practConvCheck = 1;
                else if (gdNoPrecLocking)
                   practConvCheck = -1;
+               /* fused first Gram panel: only when the correction below is a plain copy of the
+                * residuals and the block is orthogonalised against the basis alone */
+               S->fuse_enabled = S->fuse_allowed && S->VtBV != NULL && !primme->correctionParams.precondition &&
+                                 !(primme->correctionParams.projectors.RightX && primme->correctionParams.projectors.SkewX) &&
+                                 !(primme->correctionParams.projectors.RightX && primme->locking &&
+                                       primme->orth == primme_orth_implicit_I) &&
+                                 primme->numOrthoConst + numLocked == 0;
+               S->fuse_sweeps = 0, S->fusedP_nb = 0;
                CHK(prepare_candidates(S, basisSize, S->V + (size_t)S->ld * basisSize,
                      S->W + (size_t)S->ld * basisSize, 1, maxRecentlyConverged, blockSize,
                      availableBlockSize, numLocked, evals, resNorms, targetShiftIndex, &blockSize,
                      &recentlyConverged, &smallestResNorm, numConverged, &reset, nprevhVecs,
                      practConvCheck));
+               /* valid only if ONE sweep produced exactly the final block, in place and in order */
+               if (!(S->fuse_sweeps == 1 && S->fusedP_nb == blockSize && S->fusedP_m == basisSize && blockSize > 0))
+                  S->fusedP_nb = 0;
                candidates_prepared = 1;
             } else {
                blockSize = recentlyConverged = 0;
+               S->fusedP_nb = 0;
             }
 
             numConverged += recentlyConverged;
@@ -582,9 +608,11 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
 
             for (i = 0; i < maxNumRandoms; i++) {
                int basisSizeOut;
-               CHK(pb_ortho_block(S, S->V, S->ld, basisSize, basisSize + blockSize - 1, S->evecs,
+               const int useP0 = i == 0 && S->fusedP_nb == blockSize && S->fusedP_nb > 0;
+               CHK(pb_ortho_block_p0(S, S->V, S->ld, basisSize, basisSize + blockSize - 1, S->evecs,
                      S->ldevecs, primme->numOrthoConst + numLocked, i == 0 ? Rlocked : NULL,
-                     ldRlocked, &basisSizeOut));
+                     ldRlocked, &basisSizeOut, useP0 ? S->fusedP : NULL, S->maxBasis + 8));
+               S->fusedP_nb = 0;
                blockSize = basisSizeOut - basisSize;
                if (blockSize > 0 || availableBlockSize <= 0) break;
                CHK(pb_fill_random(S, S->V + (size_t)S->ld * basisSize, S->ld, 1));

@@ -324,7 +324,7 @@ static void free_solver(pb_solver *S, int own_evecs) {
       if (own_evecs) pb200_free(S->dev, S->evecs);
    }
    free(S->hstage), free(S->hstage2);
-   free(S->H), free(S->hVecs), free(S->prevhVecs), free(S->VtBV), free(S->fVtBV);
+   free(S->H), free(S->hVecs), free(S->prevhVecs), free(S->VtBV), free(S->fVtBV), free(S->fusedP);
    free(S->hVals), free(S->prevRitzVals), free(S->blockNorms), free(S->basisNorms);
    free(S->flags), free(S->map), free(S->iev), free(S->perm), free(S->lockedFlags);
    if (S->dev) pb200_ctx_destroy(S->dev);
@@ -433,6 +433,8 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
    S->H = (double *)calloc((size_t)mb * mb, sizeof(double));
    S->hVecs = (double *)calloc((size_t)mb * mb, sizeof(double));
    S->prevhVecs = (double *)calloc((size_t)mb * mb, sizeof(double));
+   S->fusedP = (double *)calloc((size_t)(mb + 8) * 8, sizeof(double));
+   S->fuse_allowed = getenv("PB200_NO_FUSE_GRAM") ? 0 : 1;
    if (primme->orth == primme_orth_explicit_I) {
       S->VtBV = (double *)calloc((size_t)mr * mr, sizeof(double));
       S->fVtBV = (double *)calloc((size_t)mr * mr, sizeof(double));

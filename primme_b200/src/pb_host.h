@@ -43,6 +43,12 @@ typedef struct pb_solver {
    double t0;
    double tProj, tSolveH, tRestart; /* wall-clock of the phases the reference does not time (PB200_DEBUG report) */
    int numPrevRitzVals;
+   /* first Gram panel of the next block orthogonalisation, delivered by the candidates sweep when
+    * the new block is the residual block itself (no preconditioner, no locked vectors):
+    * fusedP = [V(:,0:m) R]' R, (m + nb) x nb, leading dimension maxBasis + 8 */
+   double *fusedP;
+   int fusedP_m, fusedP_nb; /* fusedP_nb > 0: valid for basis size m and a block of nb columns */
+   int fuse_allowed, fuse_enabled, fuse_sweeps;
 } pb_solver;
 
 /* error propagation in the style of the reference's CHKERR (common.h:484-494) */
@@ -87,6 +93,10 @@ int pb_reduce_panel(pb_solver *S, double *P, int rows, int cols, int ldp);
 /* dav_ortho.c */
 int pb_ortho_block(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const double *locked,
       int64_t ldLocked, int numLocked, double *RLocked, int ldRLocked, int *b2_out);
+/* same, with the panel of the first sweep already known (P0 = [V(:,0:b1) X]' X, or NULL) */
+int pb_ortho_block_p0(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const double *locked,
+      int64_t ldLocked, int numLocked, double *RLocked, int ldRLocked, int *b2_out, const double *P0,
+      int ldP0);
 int pb_update_cholesky(pb_solver *S, int n0, int n);
 int pb_ortho_single_iteration(pb_solver *S, const double *Q, int nQ, int64_t ldQ,
       const double *QtQ, int ldQtQ, double *X, const int *inX, int nX, int64_t ldX,

@@ -89,6 +89,17 @@ def main():
         return lib.pb200_dvwxr(ctx, n, V, W, m, ld, h.ctypes.data, mmax, b, theta.ctypes.data, C.byref(o))
 
     measure(f"vwxr candidates m={m} b={b}", 2, cand)
+    Pp = np.zeros((b, mmax + 8))
+
+    def candp():
+        o = api.VwxrOut()
+        o.X[0] = api.VwxrCols(off(V, m).value, ld, 0, b)
+        o.R = api.VwxrCols(off(W, m).value, ld, 0, b)
+        o.Rnorms_host = Rn.ctypes.data
+        o.P_host, o.ldP = Pp.ctypes.data, mmax + 8
+        return lib.pb200_dvwxr(ctx, n, V, W, m, ld, h.ctypes.data, mmax, b, theta.ctypes.data, C.byref(o))
+
+    measure(f"vwxr candidates+gram m={m} b={b}", 2, candp)
     G = np.zeros((mmax, mmax))
     Hm = np.zeros((mmax, mmax))
 

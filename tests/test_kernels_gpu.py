@@ -124,6 +124,14 @@ def test_ortho_sweep(libs, n, q, mv, b, update, useY, xx):
     (4096, 64, 36, "restart"),
     (257, 9, 3, "cand"),
     (0, 8, 2, "cand"),
+    (6144, 28, 4, "candp"),     # candidates + first Gram panel of the block ortho, P = [V R]'R
+    (3000 + 6, 37, 3, "candp"),
+    (5120 + 2, 64, 8, "candp"),
+    (40000, 20, 4, "candp"),
+    (4096 + 8, 40, 12, "restart"),  # two 8-column tiles of h
+    (4096 + 8, 33, 29, "lock"),     # four tiles
+    (130000, 40, 24, "restart"),    # several tiles per CTA: ring wrap-around
+    (150000, 28, 4, "candp"),
 ])
 def test_vwxr(libs, n, m, nh, case):
     rng = np.random.default_rng(99 + n + m + nh)
@@ -144,11 +152,16 @@ def test_vwxr(libs, n, m, nh, case):
         rn = np.zeros(200)
         G = np.zeros((160, 161))
         Hm = np.zeros((160, 163))
-        if case == "cand":
+        Pp = np.zeros((8, m + 8 + 3))
+        if case in ("cand", "candp"):
             o.X[0] = api.VwxrCols(off(dV, 8 * ld * m).value, ld, 0, nh)
             o.R = api.VwxrCols(off(dW, 8 * ld * m).value, ld, 0, nh)
             o.Rnorms_host = Rn.ctypes.data
             nR = nh
+            if case == "candp":
+                if not lib.pb200_dvwxr_can_fuse_gram(d.ctx, n, dV, dW, m, ld, nh, C.byref(o)):
+                    pytest.skip("shape not covered by the fused kernel")
+                o.P_host, o.ldP = Pp.ctypes.data, m + 8 + 3
         elif case == "norms":
             o.rb, o.re, o.rnorms_host = 0, nh, rn.ctypes.data
         else:
@@ -168,7 +181,7 @@ def test_vwxr(libs, n, m, nh, case):
         rc = lib.pb200_dvwxr(d.ctx, n, dV, dW, m, ld, h.ctypes.data, m + 1, nh, theta.ctypes.data, C.byref(o))
         assert rc == 0
         res.append((d.down(dV, m + 8, ld)[:, :n], d.down(dW, m + 8, ld)[:, :n], d.down(dE, 8, ld)[:, :n],
-                    Rn[:nR].copy(), rn.copy(), G.copy(), Hm.copy()))
+                    Rn[:nR].copy(), rn.copy(), G.copy(), Hm.copy(), Pp.copy()))
         d.close()
     g, o_ = res
     sc = np.sqrt(m) * 3
@@ -178,6 +191,7 @@ def test_vwxr(libs, n, m, nh, case):
     assert np.allclose(g[4], o_[4], rtol=1e-11)
     assert np.allclose(g[5], o_[5], rtol=0, atol=1e-11 * max(1.0, np.abs(o_[5]).max()))
     assert np.allclose(g[6], o_[6], rtol=0, atol=1e-11 * max(1.0, np.abs(o_[6]).max()))
+    assert np.allclose(g[7], o_[7], rtol=0, atol=1e-11 * max(1.0, np.abs(o_[7]).max()))
 
 
 def _csr_case(name):

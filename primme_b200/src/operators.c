@@ -13,6 +13,7 @@
 #include "pb_host.h"
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
 
 /* ---- registry: which kernel context serves which primme_params (a handful of entries) ---- */
 #define PB_MAX_ACTIVE 64
@@ -110,7 +111,9 @@ int primme_b200_dprimme_csr(double *evals, double *evecs_host, double *resNorms,
    const int64_t nnz = rowptr_host[n] - index_base;
    pb200_csr *A = NULL;
    double *devecs = NULL;
+   const double tc0 = hl_wtime();
    rc = pb200_csr_create(ctx, n, primme->n, nnz, rowptr_host, colind_host, vals_host, index_base, 0, &A);
+   const double tc1 = hl_wtime();
    const int ncols = primme->numOrthoConst + PB_MAX(primme->numEvals, primme->initSize);
    const int64_t ldh = primme->ldevecs > 0 ? primme->ldevecs : n;
    if (!rc) rc = pb200_malloc(ctx, sizeof(double) * (size_t)PB_MAX(n, 1) * PB_MAX(ncols, 1), (void **)&devecs);
@@ -135,8 +138,12 @@ int primme_b200_dprimme_csr(double *evals, double *evecs_host, double *resNorms,
          if (r2 && !rc) rc = PRIMME_UNEXPECTED_FAILURE;
       }
    }
+   const double tc2 = hl_wtime();
    if (devecs) pb200_free(ctx, devecs);
    if (A) pb200_csr_destroy(ctx, A);
+   if (getenv("PB200_DEBUG"))
+      fprintf(stderr, "PRIMME-B200: dprimme_csr (s): csr upload+schedule %.4f, solve+download %.4f, release %.4f\n",
+            tc1 - tc0, tc2 - tc1, hl_wtime() - tc2);
    if (own) {
       primme_b200_attach_ctx(primme, NULL);
       pb200_ctx_destroy(ctx);

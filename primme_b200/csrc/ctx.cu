@@ -51,6 +51,7 @@ extern "C" int pb200_ctx_create(pb200_ctx **out, int device) {
    ctx->fuse_gram = getenv("PB200_NO_FUSE_GRAM") ? 0 : 1;
    ctx->ortho_2cta = getenv("PB200_ORTHO_2CTA") ? atoi(getenv("PB200_ORTHO_2CTA")) : 0;
    ctx->use_tma = getenv("PB200_NO_TMA") ? 0 : 1;
+   ctx->ortho_exact = getenv("PB200_NO_ORTHO_EXACT") ? 0 : 1;
    ctx->use_tma_vwxr = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_VWXR")) ? 0 : 1;
    ctx->use_tma_spmm = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_SPMM")) ? 0 : 1;
    *out = ctx;

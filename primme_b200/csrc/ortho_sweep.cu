@@ -410,6 +410,166 @@ __global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_kernel(SweepArgs
    if (tid == 0) pb_stamp(a.trace, 5);
 }
 
+// ------------------------------------------------------------------------------------------
+// Specialised instances of the main kernel for the steady-state shapes (no locked vectors, the
+// stage holds exactly NMT 8-column tiles of V, Gram panel always wanted): every DMMA is
+// unconditional (a predicated mma.sync costs a branch and a WARPSYNC), the update coefficients live
+// in registers as B fragments (shared-memory instructions compete with DMMA for the same issue
+// queue: +3 cycles per LDS on top of 16 per DMMA, scripts/micro/dmma_issue.cu), the transposing
+// scratch is swizzled so that its stores and loads are conflict free.
+template <int NMT, int NW, bool UPD, bool XX>
+__global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_exact_kernel(SweepArgs a, const __grid_constant__ PbCoef coef,
+      const __grid_constant__ SweepMaps maps, int nstages) {
+   constexpr int TR = 8 * NW, S = TR + 4, NCT = NW * 32;
+   constexpr int XC0 = 8 * NMT;              // first X column of a stage
+   constexpr int STAGE = (XC0 + 8) * S;
+   extern __shared__ __align__(128) unsigned char smraw[];
+   const int k = a.mv;  // q == 0 here
+   double *stage0 = reinterpret_cast<double *>(smraw);
+   double *Cs = stage0 + a.stage_doubles;                 // XC0 * CS_LD   (holds -C)
+   double *Ys = Cs + (size_t)XC0 * CS_LD;                 // 8 * CS_LD
+   double *xw0 = Ys + 8 * CS_LD;                          // NW * 8 * CS_LD
+   uint64_t *full = reinterpret_cast<uint64_t *>(xw0 + NW * 8 * CS_LD);
+   uint64_t *empty = full + nstages;
+   int *flag = reinterpret_cast<int *>(empty + nstages);
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+   if (tid == 0) {
+      for (int s = 0; s < nstages; s++) {
+         pbtma::mbar_init(&full[s], 1);
+         pbtma::mbar_init(&empty[s], NW);
+      }
+      pbtma::fence_barrier_init();
+   }
+   if (UPD) {
+      const double *cg = a.coef_inline ? coef.v : a.Cdev;
+      const double *yg = a.coef_inline ? coef.v + (size_t)k * a.bt : a.Ydev;
+      for (int i = tid; i < XC0 * 8; i += NCT + 32) {
+         const int vc = i >> 3, c = i & 7;
+         Cs[vc * CS_LD + c] = (vc < k && c < a.b) ? -cg[vc + (size_t)c * k] : 0.0;
+      }
+      for (int i = tid; i < 64; i += NCT + 32) {
+         const int r = i >> 3, c = i & 7;
+         Ys[r * CS_LD + c] = (r < a.b && c < a.b) ? (a.has_Y ? yg[r + c * a.bt] : (r == c ? 1.0 : 0.0)) : 0.0;
+      }
+   }
+   __syncthreads();
+
+   const int64_t ntiles = (a.n + TR - 1) / TR;
+   if (warp == NW) {
+      if (lane != 0) return;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+         pbtma::mbar_wait(&empty[s], ph ^ 1);
+         double *dst = stage0 + (size_t)s * STAGE;
+         const int r0 = (int)(tile * TR);
+         pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(STAGE * sizeof(double)));
+         pbtma::tensor_g2s_2d(dst, &maps.v, r0, 0, &full[s]);
+         pbtma::tensor_g2s_2d(dst + XC0 * S, &maps.x, r0, 0, &full[s]);
+         if (++s == nstages) s = 0, ph ^= 1;
+      }
+      return;
+   }
+
+   const int g = lane >> 2, t = lane & 3;
+   const int r0w = warp * 8;
+   double acc[NMT][2], accx[2] = {0.0, 0.0};
+#pragma unroll
+   for (int mt = 0; mt < NMT; mt++) acc[mt][0] = acc[mt][1] = 0.0;
+   double *xw = xw0 + warp * 8 * CS_LD;
+   const int offu = r0w + t * S + g;   // update A fragment: column t of a k-step, row g
+   const int offg = r0w + g * S + t;   // Gram A fragment: column g of a tile, row t of a k-step
+   // B fragments of -C for every k-step and of Y, loaded once
+   double cfr[UPD ? 2 * NMT : 1], yfr0 = 0.0, yfr1 = 0.0;
+   if (UPD) {
+#pragma unroll
+      for (int i = 0; i < 2 * NMT; i++) cfr[i] = Cs[(4 * i + t) * CS_LD + g];
+      yfr0 = Ys[t * CS_LD + g], yfr1 = Ys[(4 + t) * CS_LD + g];
+   }
+   // scratch [column][row]: rows of columns 4..7 XORed with 4 (conflict-free stores and loads)
+   const int xs0 = (2 * t) * CS_LD + (g ^ ((2 * t) & 4)), xs1 = xs0 + CS_LD;
+   const int xl0 = g * CS_LD + (t ^ (g & 4)), xl1 = g * CS_LD + ((t + 4) ^ (g & 4));
+   const bool wide = a.b > 4;
+   const bool st0 = 2 * t < a.b, st1 = 2 * t + 1 < a.b;
+   double *gx0 = a.X + (size_t)(2 * t) * a.ldx + r0w + g, *gx1 = gx0 + a.ldx;
+
+   int s = 0;
+   uint32_t ph = 0;
+   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      pbtma::mbar_wait(&full[s], ph);
+      const double *st = stage0 + (size_t)s * STAGE;
+      double bf0, bf1;  // Gram X operand: X(row t (+4) of the warp's 8 rows, column g)
+      if (UPD) {
+         const double *sx = st + XC0 * S + r0w + g;
+         double d0 = sx[(2 * t) * S], d1 = sx[(2 * t + 1) * S], e0 = 0.0, e1 = 0.0;
+         const double *pa = st + offu;
+#pragma unroll
+         for (int i = 0; i < NMT; i++) {
+            dmma884(d0, d1, pa[(8 * i) * S], cfr[2 * i]);
+            dmma884(e0, e1, pa[(8 * i + 4) * S], cfr[2 * i + 1]);
+         }
+         d0 += e0, d1 += e1;
+         // D <- D * Y: the accumulator tile becomes the A operand after a shuffle inside each quad
+         double y0 = 0.0, y1 = 0.0;
+         {
+            const int src = (lane & ~3) | (t >> 1);
+            const double v0 = __shfl_sync(0xffffffffu, d0, src), v1 = __shfl_sync(0xffffffffu, d1, src);
+            dmma884(y0, y1, (t & 1) ? v1 : v0, yfr0);
+         }
+         if (wide) {
+            const int src = (lane & ~3) | 2 | (t >> 1);
+            const double v0 = __shfl_sync(0xffffffffu, d0, src), v1 = __shfl_sync(0xffffffffu, d1, src);
+            dmma884(y0, y1, (t & 1) ? v1 : v0, yfr1);
+         }
+         const int64_t roff = tile * TR;
+         if (roff + r0w + g < a.n) {
+            if (st0) gx0[roff] = y0;
+            if (st1) gx1[roff] = y1;
+         }
+         xw[xs0] = y0, xw[xs1] = y1;
+         __syncwarp();
+         bf0 = xw[xl0], bf1 = xw[xl1];
+      } else {
+         const double *xb = st + XC0 * S + offg;
+         bf0 = xb[0], bf1 = xb[4];
+      }
+      {
+         const double *pg = st + offg;
+#pragma unroll
+         for (int mt = 0; mt < NMT; mt++) dmma884(acc[mt][0], acc[mt][1], pg[mt * 8 * S], bf0);
+         if (XX) dmma884(accx[0], accx[1], bf0, bf0);
+#pragma unroll
+         for (int mt = 0; mt < NMT; mt++) dmma884(acc[mt][0], acc[mt][1], pg[mt * 8 * S + 4], bf1);
+         if (XX) dmma884(accx[0], accx[1], bf1, bf1);
+      }
+      __syncwarp();
+      if (lane == 0) pbtma::mbar_arrive(&empty[s]);
+      if (++s == nstages) s = 0, ph ^= 1;
+   }
+
+   // ---- per-warp panels -> one partial panel per CTA (warp order), through the stage memory ----
+   pbtma::named_bar_sync(1, NCT);
+   double *red = stage0;  // [NW][(NMT + 1) * 8][8]
+   constexpr int nv = (NMT + 1) * 8;
+#pragma unroll
+   for (int mt = 0; mt < NMT; mt++)
+      *reinterpret_cast<double2 *>(red + ((size_t)warp * nv + mt * 8 + g) * 8 + 2 * t) = make_double2(acc[mt][0], acc[mt][1]);
+   *reinterpret_cast<double2 *>(red + ((size_t)warp * nv + NMT * 8 + g) * 8 + 2 * t) = make_double2(accx[0], accx[1]);
+   pbtma::named_bar_sync(1, NCT);
+   const int rows_out = k + (XX ? a.b : 0);
+   double *out = a.partials + (size_t)blockIdx.x * rows_out * a.b;
+   for (int e = tid; e < rows_out * a.b; e += NCT) {
+      const int j = e % rows_out, c = e / rows_out;
+      const int i = j < k ? j : NMT * 8 + (j - k);
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; w++) sum += red[((size_t)w * nv + i) * 8 + c];
+      out[e] = sum;
+   }
+   pb_finish_device(a.fin, tid, NCT, 15, flag);
+}
+
 // partial-panel storage + in-kernel finish for a launch of `grid` CTAs (cnt = 0: no panel)
 static int sweep_panel_setup(pb200_ctx *ctx, SweepArgs &a, int grid, int cnt) {
    if (cnt <= 0) return 0;
@@ -459,6 +619,29 @@ int launch_sweep_mma(pb200_ctx *ctx, SweepArgs &a, const SweepMaps &maps, int gr
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
    return 0;
+}
+
+
+template <int NMT, int NW, bool UPD, bool XX>
+int launch_sweep_exact(pb200_ctx *ctx, SweepArgs &a, const SweepMaps &maps, int grid, size_t shmem, int nstages, int cnt) {
+   auto kern = ortho_sweep_mma_exact_kernel<NMT, NW, UPD, XX>;
+   static size_t attr_shmem = 0;
+   if (shmem > attr_shmem) {
+      PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+      attr_shmem = shmem;
+   }
+   PB_CHK(sweep_panel_setup(ctx, a, grid, cnt));
+   kern<<<grid, NW * 32 + 32, shmem, ctx->stream>>>(a, ctx->coef, maps, nstages);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   return 0;
+}
+
+template <int NMT>
+int dispatch_exact(pb200_ctx *ctx, SweepArgs &a, const SweepMaps &maps, int grid, size_t shmem, int nstages, int cnt) {
+   if (a.do_update) return launch_sweep_exact<NMT, 16, true, true>(ctx, a, maps, grid, shmem, nstages, cnt);
+   if (a.xx) return launch_sweep_exact<NMT, 16, false, true>(ctx, a, maps, grid, shmem, nstages, cnt);
+   return launch_sweep_exact<NMT, 16, false, false>(ctx, a, maps, grid, shmem, nstages, cnt);
 }
 
 template <int BT, int CPW>
@@ -621,7 +804,14 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
       const size_t shmem = ring * sizeof(double) + fixed_sm;
       if (tracing) clock_gettime(CLOCK_MONOTONIC, &th1);
 #define PB_MMA(MT_, NW_) rc = launch_sweep_mma<MT_, NW_>(ctx, a, maps, grid, shmem, nstages, cnt)
-      if (nw == 16) {
+      // steady-state shapes (no locked vectors, Gram wanted, update always with xx): specialised
+      const bool exact = ctx->ortho_exact && nw == 16 && q == 0 && mv > 0 && a.do_gram && !a.dbg && !a.trace &&
+                         (!a.do_update || a.xx) && nmtv >= 3 && nmtv <= 5;
+      if (exact) {
+         rc = nmtv == 3 ? dispatch_exact<3>(ctx, a, maps, grid, shmem, nstages, cnt)
+            : nmtv == 4 ? dispatch_exact<4>(ctx, a, maps, grid, shmem, nstages, cnt)
+                        : dispatch_exact<5>(ctx, a, maps, grid, shmem, nstages, cnt);
+      } else if (nw == 16) {
          if (nmtv <= 5) PB_MMA(5, 16);
          else if (nmtv <= 9) PB_MMA(9, 16);
          else PB_MMA(13, 16);

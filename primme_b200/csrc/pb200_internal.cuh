@@ -67,6 +67,7 @@ struct pb200_ctx {
    int fuse_gram;         // candidates sweep also delivers the first Gram panel of the block ortho
    int coef_inline;       // small coefficient matrices travel as kernel parameters (no H2D copy)
    PbCoef coef;           // host staging of that block for the next launch
+   int ortho_exact;       // specialised (exact tile count) instances of the ortho sweep
    int ortho_2cta;        // prefer 2 CTAs/SM x 2 stages over 1 CTA/SM x 4 stages in the ortho sweep
    int use_tma;           // 1: TMA-staged kernels where eligible (default), 0: LDG kernels only
    // optional per-kernel-kind CUDA-event timing (bench.py's roofline numbers)

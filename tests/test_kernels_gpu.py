@@ -62,6 +62,12 @@ def off(p, nbytes):
     (70000 + 0j, 0, 36, 4, True, True, True),
     (1000, 0, 12, 4, False, False, True),
     (1000, 0, 12, 4, True, True, True),
+    # specialised instances (no locked vectors, 3..5 tiles of V)
+    (40000 + 4j, 0, 20, 4, True, True, True),
+    (40000 + 4j, 0, 17, 3, True, False, True),
+    (33000 + 2j, 0, 24, 8, True, True, True),
+    (33000 + 2j, 0, 33, 8, False, False, False),
+    (33000 + 2j, 0, 40, 5, False, False, True),
     (4097, 3, 20, 4, True, True, True),
     (4097, 3, 20, 3, True, False, True),
     (5000, 0, 40, 4, False, False, False),   # projection-like: X = W block, no xx

@@ -140,6 +140,19 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kind, algorithmic_bytes_per_launch):
+    """DRAM bytes per launch of the dominant kernel family: the ratio (dram__bytes_read.sum +
+    dram__bytes_write.sum) / algorithmic bytes of the committed `ncu --set full` capture
+    (profiles/ncu_traffic_r01.json, made by scripts/gpu_profile.sh) applied to this run's
+    algorithmic bytes per launch.  None when there is no capture for the family."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as f:
+            ratio = json.load(f)["family_ratio"][kind]
+        return ratio * algorithmic_bytes_per_launch
+    except Exception:
+        return None
+
+
 def ref_threads(args):
     return args.ref_threads if args.ref_threads > 0 else min(os.cpu_count() or 1, 16)
 
@@ -166,6 +179,8 @@ def main():
     # OpenBLAS reads its thread count when the library is first loaded (the product links the same
     # OpenBLAS for its tiny host-side algebra and pins it to one thread during a solve)
     os.environ["OPENBLAS_NUM_THREADS"] = str(ref_threads(args))
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # stdout carries exactly one JSON line
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -351,7 +366,9 @@ def main():
     dom = max(("spmm", "ortho_sweep", "vwxr"), key=lambda kname: prof[kname]["ms"])
     peak, peak_src = measured_peak()
     roofline = {"bound": "hbm", "kernel": dom, "achieved": prof[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": prof[dom]["gbs"] / peak, "peak_source": peak_src, "traffic": None,
+                "frac": prof[dom]["gbs"] / peak, "peak_source": peak_src,
+                "traffic": ncu_traffic(dom, prof[dom]["bytes"] / max(1, prof[dom]["launches"])),
+                "traffic_source": "profiles/ncu_traffic_r01.json (ncu --set full DRAM bytes / algorithmic bytes at the C2 shapes)",
                 "launches": prof[dom]["launches"], "avg_launch_us": 1e3 * prof[dom]["ms"] / max(1, prof[dom]["launches"]),
                 "algorithmic_bytes_per_launch": prof[dom]["bytes"] / max(1, prof[dom]["launches"]),
                 "all_kernels": {kname: {"GBps": round(v["gbs"], 1), "ms": round(v["ms"], 3), "launches": v["launches"]}

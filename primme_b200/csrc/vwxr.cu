@@ -590,7 +590,9 @@ __global__ void __launch_bounds__(NW * 32 + 32) vwxr_mma_kernel(VwxrArgs a, cons
    unsigned yres = 0, wnorm = 0, slow = 0;
 #pragma unroll
    for (int q = 0; q < NQ; q++) {
-      const int cc = 8 * (q >> 1) + 2 * t + (q & 1);
+      // (dbg & 8, timing experiment with wrong results: the store pattern of a transposed epilogue,
+      // every warp store covers 32 consecutive rows of one column)
+      const int cc = (a.dbg & 8) ? 4 * q + (warp & 3) : 8 * (q >> 1) + 2 * t + (q & 1);
       px[q] = py[q] = nullptr;
       thv[q] = th[cc];
       int nx = 0, ny = 0;
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) vwxr_mma_kernel(VwxrArgs a, cons
          if (lane == 0) pbtma::mbar_arrive(&empty[s]);
       }
       // ---- residuals, norms, scatter (fragment layout: row g, columns 8 i + 2 t + j) ----
-      const int64_t r = tile * TR + r0w + g;
+      const int64_t r = (a.dbg & 8) ? tile * TR + (warp >> 2) * 32 + lane : tile * TR + r0w + g;
       const bool rok = r < a.n && !(a.dbg & 1);
       if (!slow) {
 #pragma unroll

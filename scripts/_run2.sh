@@ -1,6 +1,3 @@
-export PB200_DEBUG=1
-timeout 600 python -m pytest tests/test_kernels_gpu.py -q -x -k "ortho" --timeout 120 2>&1 | tail -5
-echo "=== kernel bench (exact)"
-timeout 200 python scripts/kernel_bench.py --reps 10 2>&1 | grep "ortho\|projection"
-echo "=== kernel bench (generic)"
-PB200_NO_ORTHO_EXACT=1 timeout 200 python scripts/kernel_bench.py --reps 10 2>&1 | grep "ortho\|projection"
+mkdir -p gpurun_out
+t0=$(date +%s.%N); python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; t1=$(date +%s.%N); echo "default bench wall: $(echo "$t1 - $t0" | bc) s"; cat gpurun_out/bench_default.json | cut -c1-3000
+t0=$(date +%s.%N); python bench.py --impl reference > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; t1=$(date +%s.%N); echo "reference arm wall: $(echo "$t1 - $t0" | bc) s"; cat gpurun_out/bench_reference.json

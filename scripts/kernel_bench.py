@@ -115,6 +115,21 @@ def main():
         return lib.pb200_dvwxr(ctx, n, V, W, mmax, ld, h.ctypes.data, mmax, rs + b, theta.ctypes.data, C.byref(o))
 
     measure(f"vwxr restart m={mmax} rs={rs} b={b}", 2, restart)
+    if os.environ.get("PB200_BENCH_OOP"):
+        V2, W2 = dev(rs + b), dev(rs + b)
+
+        def restart_oop():
+            o = api.VwxrOut()
+            o.X[0] = api.VwxrCols(V2.value, ld, 0, rs)
+            o.Wo = api.VwxrCols(W2.value, ld, 0, rs)
+            o.X[1] = api.VwxrCols(off(V2, rs).value, ld, 0, b)
+            o.R = api.VwxrCols(off(W2, rs).value, ld, 0, b)
+            o.Rnorms_host = Rn.ctypes.data
+            o.nG, o.G_host, o.ldG = rs, G.ctypes.data, mmax
+            o.nH, o.H_host, o.ldH = rs, Hm.ctypes.data, mmax
+            return lib.pb200_dvwxr(ctx, n, V, W, mmax, ld, h.ctypes.data, mmax, rs + b, theta.ctypes.data, C.byref(o))
+
+        measure(f"vwxr restart out of place", 2, restart_oop)
     # host-visible latency of one call at a tiny size (launch + panel reduction + delivery): the
     # fixed cost of every synchronisation point of the outer iteration
     import time

@@ -1,0 +1,31 @@
+/* sparskit_stubs.c -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ * C stand-ins for the Fortran SPARSKIT entry points the reference's test driver declares in
+ * tests/COMMON/mat.c:43-55 (objects COMMON/matvec.f, ilut.f of tests/Makefile:26-30); there is no
+ * Fortran compiler in this image.  CSR arrays are 1-based, as the driver's reader produces them
+ * (tests/COMMON/csr.c:157-163). */
+#include <stdio.h>
+#include <stdlib.h>
+
+/* y = A x */
+void amux_(int *n, double *x, double *y, double *a, int *ja, int *ia) {
+   for (int i = 0; i < *n; i++) {
+      double s = 0.0;
+      for (int k = ia[i]; k < ia[i + 1]; k++) s += a[k - 1] * x[ja[k - 1] - 1];
+      y[i] = s;
+   }
+}
+/* y = A' x for an m x n matrix */
+void atmuxr_(int *m, int *n, double *x, double *y, double *a, int *ja, int *ia) {
+   for (int j = 0; j < *m; j++) y[j] = 0.0;
+   for (int i = 0; i < *n; i++)
+      for (int k = ia[i]; k < ia[i + 1]; k++) y[ja[k - 1] - 1] += a[k - 1] * x[i];
+}
+/* ILUT preconditioner: no shipped test configuration selects it (driver.PrecChoice = ilut) */
+void ilut_(void) {
+   fprintf(stderr, "ilut_: not available in this build (no Fortran SPARSKIT)\n");
+   abort();
+}
+void lusol0_(void) {
+   fprintf(stderr, "lusol0_: not available in this build (no Fortran SPARSKIT)\n");
+   abort();
+}

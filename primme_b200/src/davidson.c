@@ -433,6 +433,7 @@ static int verify_norms(pb_solver *S, int nv, double *resNorms, int *numConverge
 static int copy_back_candidates(pb_solver *S, int basisSize, double *evals, double *resNorms,
       int targetShiftIndex, int numConverged, int *numRet) {
    primme_params *primme = S->primme;
+   *numRet = numConverged; /* the locked vectors already sit in evecs: the host contract copies them back */
    if (numConverged >= primme->numEvals || basisSize <= 0) return 0;
    double *ev = S->evecs + (size_t)S->ldevecs * primme->numOrthoConst;
    int i = 0;

@@ -46,3 +46,27 @@ def test_reference_example_compiles_against_our_headers(tmp_path):
                         f"-Wl,-rpath-link,{OB}", "-lm"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/include"), reason="reference tree not mounted")
+def test_internal_context_mirror_matches_reference(tmp_path):
+    """primme_context crosses the boundary BY VALUE in the reference-internal entry points the
+    reference's test driver links (include/primme_ref_internal.h, primme_b200/src/ref_internal.c):
+    size and field offsets equal those of src/include/common.h:610-641"""
+    import subprocess
+    src = tmp_path / "c.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "common.h"\nint main(void){\n'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(primme_context), offsetof(primme_context, primme),'
+                   'offsetof(primme_context, printLevel), offsetof(primme_context, report), offsetof(primme_context, mm),'
+                   'offsetof(primme_context, numProcs), offsetof(primme_context, bcast), offsetof(primme_context, globalSum),'
+                   'offsetof(primme_context, queue));\nprintf("%zu %zu %zu\\n", sizeof(primme_frame), offsetof(primme_frame, keep_frame),'
+                   'offsetof(primme_frame, prev));return 0;}\n')
+    exe = tmp_path / "c"
+    subprocess.run(["gcc", "-DNDEBUG", "-I/root/reference/src/include", "-I/root/reference/include", str(src), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    ref = [int(x) for x in out]
+    lib = api.load_library()
+    mine = [lib.primme_b200_ref_context_size()] + [lib.primme_b200_ref_context_offset(i) for i in range(8)]
+    assert mine == ref[:9]
+    assert ref[9:] == [24, 8, 16]  # primme_frame {prev_alloc, keep_frame, prev}

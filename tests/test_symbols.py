@@ -22,6 +22,10 @@ def declared_functions():
     for base in re.findall(r"^PRIMME_DECLARE_SOLVERS_\((\w+),", eigs, flags=re.M):
         names |= {base, "magma_" + base, "cublas_" + base}
     names |= set(re.findall(r"^(?:int|void|primme_params \*)\s*\*?(primme_\w+)\(", eigs, flags=re.M))
+    # reference-internal entry points of the reference's own test driver
+    internal = open(os.path.join(ROOT, "include", "primme_ref_internal.h")).read()
+    internal = re.sub(r"/\*.*?\*/", "", internal, flags=re.S)
+    names |= set(re.findall(r"^(?:int|void|double|primme_context_mirror)\s+(\w+)\(", internal, flags=re.M))
     return names
 
 

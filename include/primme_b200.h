@@ -95,6 +95,14 @@ typedef struct pb200_dist_csr pb200_dist_csr;
 int pb200_comm_unique_id(void *id128);
 int pb200_ctx_comm_init(pb200_ctx *ctx, int nranks, int rank, const void *id128);
 int pb200_ctx_comm_free(pb200_ctx *ctx);
+/* Peer-memory panel exchange (one node, one process per GPU, after pb200_ctx_comm_init): every
+ * panel kernel then all-reduces its own panel over NVLink peer memory instead of a separate NCCL
+ * call (see PbFin in csrc/pb200_internal.cuh).  export: allocates this rank's exchange buffer and
+ * returns its cudaIpcMemHandle_t (64 bytes); the launcher all-gathers the handles; attach: opens the
+ * peers' buffers (returns 1 and keeps NCCL for the panels if peer access is not possible). */
+int pb200_ctx_peer_export(pb200_ctx *ctx, void *handle64);
+int pb200_ctx_peer_attach(pb200_ctx *ctx, int nranks, int rank, const void *handles);
+int pb200_ctx_peer_active(pb200_ctx *ctx);
 int pb200_dist_csr_create(pb200_ctx *ctx, pb200_csr *A_local, const int64_t *counts_host,
       int nranks, pb200_dist_csr **D);
 int pb200_dist_csr_destroy(pb200_ctx *ctx, pb200_dist_csr *D);
@@ -143,6 +151,10 @@ typedef struct pb200_vwxr_out {
                            of the block orthogonalisation (ortho.c:1043-1059) when the new block is the
                            residual block itself; only when pb200_dvwxr_can_fuse_gram() says so */
    int ldP;
+   double *R2;          /* optional, with P_host only: the residual columns are ALSO written here (n x nR,
+                           leading dimension ldR2, 16-byte aligned) -- the next basis block when the
+                           correction is the residual itself, so no copy kernel follows */
+   int64_t ldR2;
 } pb200_vwxr_out;
 
 /* One sweep over the rows of V and W (both n x m, leading dimension ld):

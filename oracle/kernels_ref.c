@@ -306,6 +306,7 @@ int pb200_dvwxr(pb200_ctx *ctx, int64_t n, const double *V, const double *W, int
          int cc = o->R.cb + c;
          double v = yrow[cc] - xrow[cc] * theta[cc];
          o->R.ptr[r + (size_t)c * o->R.ld] = v;
+         if (o->R2) o->R2[r + (size_t)c * o->ldR2] = v; /* second destination of the residual block */
          Rn[c] += v * v;
       }
       for (int c = 0; c < nr; c++) {

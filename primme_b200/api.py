@@ -102,7 +102,7 @@ class VwxrOut(C.Structure):
                 ("rb", C.c_int), ("re", C.c_int), ("rnorms_host", C.c_void_p),
                 ("nG", C.c_int), ("G_host", C.c_void_p), ("ldG", C.c_int),
                 ("nH", C.c_int), ("H_host", C.c_void_p), ("ldH", C.c_int),
-                ("P_host", C.c_void_p), ("ldP", C.c_int)]
+                ("P_host", C.c_void_p), ("ldP", C.c_int), ("R2", C.c_void_p), ("ldR2", C.c_int64)]
 
 
 class Jacobi(C.Structure):

@@ -70,6 +70,9 @@ extern "C" int pb200_ctx_destroy(pb200_ctx *ctx) {
    cudaFree(ctx->d_gpart);
    cudaFree(ctx->d_counters);
    cudaFree(ctx->d_scratch);
+   for (int p = 0; p < PB_MAX_PEERS; p++)
+      if (ctx->peer_on && p != ctx->rank && ctx->xchg_peer[p]) cudaIpcCloseMemHandle(ctx->xchg_peer[p]);
+   cudaFree(ctx->xchg_local);
    if (ctx->prof_ev) {
       for (int i = 0; i < 2 * PB_PROF_RING; i++) cudaEventDestroy(ctx->prof_ev[i]);
       free(ctx->prof_ev), free(ctx->prof_kind);
@@ -291,7 +294,15 @@ int pb_fin_prepare(pb200_ctx *ctx, int grid, int ppc, int cnt, PbFin *f) {
    }
    f->partials = ctx->d_partials, f->gpart = ctx->d_gpart, f->counters = ctx->d_counters;
    f->cnt = cnt, f->ppc = ppc;
-   if (ctx->nranks > 1 || ctx->no_poll) {
+   f->nranks = 1;
+   if (ctx->nranks > 1 && ctx->peer_on && !ctx->no_poll && cnt <= PB_XCHG_CAP) {
+      // the kernel all-reduces over peer memory and delivers like a single-GPU panel (the choice
+      // depends on cnt only: every rank takes the same path)
+      PB_CHK(pb_ensure_tagged(ctx, (size_t)cnt));
+      f->out = ctx->d_htagged, f->tag = ++ctx->seq;
+      f->nranks = ctx->nranks, f->rank = ctx->rank, f->slot = (int)(f->tag % PB_XCHG_SLOTS);
+      for (int p = 0; p < ctx->nranks; p++) f->peer[p] = ctx->xchg_peer[p];
+   } else if (ctx->nranks > 1 || ctx->no_poll) {
       f->out = ctx->d_panel, f->tag = 0;
    } else {
       PB_CHK(pb_ensure_tagged(ctx, (size_t)cnt));
@@ -390,6 +401,64 @@ extern "C" int pb200_is_device_pointer(const void *p) {
       return 0;
    }
    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? 1 : 0;
+}
+
+// ------------------------------------------------------------ peer-memory panel exchange ----
+extern "C" int pb200_ctx_peer_export(pb200_ctx *ctx, void *handle64) {
+   if (!ctx->xchg_local) {
+      const size_t bytes = sizeof(double2) * PB_XCHG_SLOTS * PB_MAX_PEERS * PB_XCHG_CAP;
+      PB_CUDA(cudaMalloc((void **)&ctx->xchg_local, bytes));
+      PB_CUDA(cudaMemset(ctx->xchg_local, 0, bytes));
+      PB_CUDA(cudaDeviceSynchronize());
+   }
+   cudaIpcMemHandle_t h;
+   PB_CUDA(cudaIpcGetMemHandle(&h, ctx->xchg_local));
+   memcpy(handle64, &h, sizeof(h));
+   return 0;
+}
+
+extern "C" int pb200_ctx_peer_attach(pb200_ctx *ctx, int nranks, int rank, const void *handles) {
+   if (nranks < 1 || nranks > PB_MAX_PEERS || rank < 0 || rank >= nranks || !ctx->xchg_local) return PB200_ERR_ARG;
+   if (getenv("PB200_NO_PEER_EXCHANGE")) return 0;  // keep the NCCL all-reduce of the panels
+   for (int p = 0; p < nranks; p++) {
+      if (p == rank) {
+         ctx->xchg_peer[p] = ctx->xchg_local;
+         continue;
+      }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char *)handles + (size_t)p * sizeof(h), sizeof(h));
+      void *ptr = NULL;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+         fprintf(stderr, "primme_b200: cudaIpcOpenMemHandle(rank %d) failed: %s -- panels stay on NCCL\n", p,
+               cudaGetErrorString(e));
+         cudaGetLastError();
+         for (int q = 0; q < p; q++)
+            if (q != rank && ctx->xchg_peer[q]) cudaIpcCloseMemHandle(ctx->xchg_peer[q]), ctx->xchg_peer[q] = NULL;
+         return 1;
+      }
+      ctx->xchg_peer[p] = (double2 *)ptr;
+   }
+   ctx->nranks = nranks, ctx->rank = rank;
+   ctx->peer_on = 1;
+   return 0;
+}
+
+extern "C" int pb200_ctx_peer_active(pb200_ctx *ctx) { return ctx->peer_on; }
+
+// a rank without local rows still takes part in the exchange: it contributes zeros
+__global__ void pb_fin_zero_kernel(PbFin f) {
+   for (int e = threadIdx.x; e < f.cnt; e += blockDim.x) pb_fin_store(f, e, 0.0);
+}
+int pb_fin_contribute_zeros(pb200_ctx *ctx, int cnt) {
+   PbFin f;
+   const int r = pb_fin_prepare(ctx, 1, 1, cnt, &f);
+   if (r < 0) return r;
+   if (r == 1 || f.nranks <= 1) return 1;  // not on the peer path
+   pb_fin_zero_kernel<<<1, 256, 0, ctx->stream>>>(f);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   return pb_collect_panel(ctx, &f);
 }
 
 // ------------------------------------------------------------------------------ NCCL ------

@@ -884,11 +884,15 @@ extern "C" int pb200_dortho_sweep(pb200_ctx *ctx, int64_t n, const double *Q, in
          if (ctx->nranks > 1) {
             /* still take part in the collective */
             PB_CHK(pb_ensure_small(ctx, (size_t)rows * b));
-            PB_CUDA(cudaMemsetAsync(ctx->d_panel, 0, sizeof(double) * rows * b, ctx->stream));
-            PB_CHK(pb_nccl_allreduce_dev(ctx, ctx->d_panel, rows * b));
-            PB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_panel, sizeof(double) * rows * b,
-                  cudaMemcpyDeviceToHost, ctx->stream));
-            PB_CUDA(cudaStreamSynchronize(ctx->stream));
+            const int zr = pb_fin_contribute_zeros(ctx, rows * b);
+            if (zr < 0) return zr;
+            if (zr == 1) {
+               PB_CUDA(cudaMemsetAsync(ctx->d_panel, 0, sizeof(double) * rows * b, ctx->stream));
+               PB_CHK(pb_nccl_allreduce_dev(ctx, ctx->d_panel, rows * b));
+               PB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_panel, sizeof(double) * rows * b,
+                     cudaMemcpyDeviceToHost, ctx->stream));
+               PB_CUDA(cudaStreamSynchronize(ctx->stream));
+            }
             for (int c = 0; c < b; c++)
                for (int j = 0; j < rows; j++)
                   P_host[j + (size_t)c * ldp] = ctx->h_pinned[j + (size_t)c * rows];

@@ -36,6 +36,10 @@ struct PbCoef {
    double v[PB_COEF_MAX];
 };
 
+#define PB_MAX_PEERS 8
+#define PB_XCHG_SLOTS 4
+#define PB_XCHG_CAP 4096   // pairs per (slot, rank)
+
 struct pb200_ctx {
    int device;
    int num_sms;
@@ -78,6 +82,10 @@ struct pb200_ctx {
    double prof_ms[8];
    double prof_bytes[8];
    int64_t prof_cnt[8];
+   // peer-memory panel exchange (see PbFin)
+   double2 *xchg_local;
+   double2 *xchg_peer[PB_MAX_PEERS];
+   int peer_on;
    // NCCL (dlopen'ed lazily)
    void *comm;
    int nranks, rank;
@@ -94,6 +102,13 @@ struct pb200_ctx {
 // shape only, never on the arrival order => bitwise reproducible panels.
 #define PB_FIN_GROUP 16
 #define PB_FIN_MAXGROUPS 64
+// Peer-memory panel exchange (one node, one process per GPU): the all-reduce of a panel is part of
+// the kernel that produced it.  The CTA that finishes the local panel stores every element as a
+// (value, sequence number) pair straight into the exchange buffer of EVERY rank over NVLink (one
+// 16-byte store per peer), waits until the pairs of all ranks for this sequence number have landed
+// in its own buffer, sums them in rank order (identical bits on every rank) and delivers the result
+// to the host like a single-GPU panel.  Slots rotate with the sequence number; a rank cannot get
+// two panels ahead of a peer (it needs the peer's previous panel to proceed), so 4 slots suffice.
 struct PbFin {
    double *partials;         // [nparts][cnt], CTA c owns slots [c*ppc, (c+1)*ppc)
    double *gpart;            // [ngroups][cnt]
@@ -102,6 +117,8 @@ struct PbFin {
    long long tag;
    int cnt;                  // 0: no in-kernel finish
    int ppc;                  // partial slots per CTA
+   int nranks, rank, slot;   // nranks > 1: peer-memory exchange before the delivery
+   double2 *peer[PB_MAX_PEERS];  // exchange buffers of all ranks (peer[rank] is the local one)
 };
 
 #ifdef __CUDACC__
@@ -109,6 +126,23 @@ __device__ __forceinline__ void pb_fin_bar(int id, int nthreads) {
    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void pb_fin_store(const PbFin &f, int e, double s) {
+   if (f.nranks > 1) {
+      const double tg = __longlong_as_double(f.tag);
+      const size_t mine = ((size_t)f.slot * PB_MAX_PEERS + f.rank) * PB_XCHG_CAP + e;
+      for (int p = 0; p < f.nranks; p++)
+         asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(f.peer[p] + mine), "d"(s), "d"(tg) : "memory");
+      double tot = 0.0;
+      for (int r = 0; r < f.nranks; r++) {
+         const double2 *src = f.peer[f.rank] + ((size_t)f.slot * PB_MAX_PEERS + r) * PB_XCHG_CAP + e;
+         double vx, vy;
+         unsigned long long spins = 0;
+         do {
+            asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "l"(src) : "memory");
+         } while (__double_as_longlong(vy) != f.tag && ++spins < (1ull << 28));  // bounded: a lost peer must not hang the GPU
+         tot += (__double_as_longlong(vy) == f.tag) ? vx : __longlong_as_double(0x7ff8000000000000ll);
+      }
+      s = tot;
+   }
    if (f.tag)
       reinterpret_cast<double2 *>(f.out)[e] = make_double2(s, __longlong_as_double(f.tag));
    else
@@ -194,6 +228,9 @@ int pb_finish_panel(pb200_ctx *ctx, int nparts, int cnt);
 // covered (fall back to pb_finish_panel).
 int pb_fin_prepare(pb200_ctx *ctx, int grid, int ppc, int cnt, PbFin *f);
 int pb_collect_panel(pb200_ctx *ctx, const PbFin *f);
+// all-zero contribution of a rank without local rows; returns 1 when the peer path is not active
+// (the caller then uses the NCCL path), 0 with the reduced panel in ctx->h_pinned[0..cnt)
+int pb_fin_contribute_zeros(pb200_ctx *ctx, int cnt);
 int pb_nccl_allreduce_dev(pb200_ctx *ctx, double *dbuf, int count);
 int pb_nccl_allgatherv_cols(pb200_ctx *ctx, const double *X, int64_t ldx, double *Y, int64_t ldy,
       const int64_t *counts, const int64_t *displs, int ncols);

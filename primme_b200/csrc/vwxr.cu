@@ -40,6 +40,8 @@ struct VwxrArgs {
    int nG, nH;
    int need_y;              // whether W*h is needed at all
    int dbg;                 // timing experiments only (PB200_DBG): wrong results when non-zero
+   double *R2;              // second destination of the residual columns (MMA kernel only)
+   int64_t ldR2;
    int nP;                  // > 0: also P = [V R]^T R, (m + nP) x nP with nP = R.ce - R.cb (MMA kernel only)
    int mpad;                // MMA kernel: m rounded up to a multiple of 4 (k-steps of the DMMA shape)
    int stage_doubles;       // MMA kernel: size of the stage ring (>= the end-of-kernel reduction scratch)
@@ -587,7 +589,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) vwxr_mma_kernel(VwxrArgs a, cons
    constexpr int NQ = 2 * NT8;
    double *px[NQ], *py[NQ];
    double thv[NQ];
-   unsigned yres = 0, wnorm = 0, slow = 0;
+   unsigned yres = 0, xres = 0, wnorm = 0, slow = 0;
 #pragma unroll
    for (int q = 0; q < NQ; q++) {
       // (dbg & 8, timing experiment with wrong results: the store pattern of a transposed epilogue,
@@ -607,6 +609,10 @@ __global__ void __launch_bounds__(NW * 32 + 32) vwxr_mma_kernel(VwxrArgs a, cons
       if (inR) {
          if (!ny) py[q] = a.R.ptr + (size_t)(cc - a.R.cb) * a.R.ld, yres |= 1u << q;
          ny++;
+         if (a.R2) {
+            if (!nx) px[q] = a.R2 + (size_t)(cc - a.R.cb) * a.ldR2, xres |= 1u << q;
+            nx++;
+         }
       }
       if (inR || (cc >= a.rb && cc < a.re)) wnorm |= 1u << q;
       if (nx > 1 || ny > 1) slow |= 1u << q;
@@ -671,7 +677,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) vwxr_mma_kernel(VwxrArgs a, cons
             const double res = y - x * thv[q];
             if (wnorm & (1u << q)) nrm[q >> 1][q & 1] += res * res;
             if (rok) {
-               if (px[q]) px[q][r] = x;
+               if (px[q]) px[q][r] = (xres & (1u << q)) ? res : x;
                if (py[q]) py[q][r] = (yres & (1u << q)) ? res : y;
             }
             if (MT > 0)
@@ -695,6 +701,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) vwxr_mma_kernel(VwxrArgs a, cons
                   if (a.Wo.ptr && cc >= a.Wo.cb && cc < a.Wo.ce)
                      a.Wo.ptr[r + (size_t)(cc - a.Wo.cb) * a.Wo.ld] = y;
                   if (inR) a.R.ptr[r + (size_t)(cc - a.R.cb) * a.R.ld] = res;
+                  if (inR && a.R2) a.R2[r + (size_t)(cc - a.R.cb) * a.ldR2] = res;
                }
                if (MT > 0) xw[j ? pcol1 : pcol0] = inR ? res : 0.0;
             }
@@ -883,6 +890,11 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
    const int nn = (nR + nr) > 0 ? nh : 0;
    int cnt = nn + a.nG * a.nG + a.nH * a.nH;
    if (o->P_host && nR <= 0) return PB200_ERR_ARG;
+   if (o->R2 && !o->P_host) return PB200_ERR_ARG;  // second residual destination: fused sweep only
+   if (o->R2) {
+      if ((((uintptr_t)o->R2) & 15) != 0 || o->ldR2 % 2 != 0) return PB200_ERR_ARG;
+      a.R2 = o->R2, a.ldR2 = o->ldR2;
+   }
    {
       int gb = (a.nG + 1) / 2, hb = (a.nH + 1) / 2;
       if (gb * gb + hb * hb > 768) return PB200_ERR_ARG;
@@ -915,7 +927,7 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
    for (int t = 0; t < 3; t++)
       if (a.X[t].ptr) ocols += a.X[t].ce - a.X[t].cb;
    if (a.Wo.ptr) ocols += a.Wo.ce - a.Wo.cb;
-   if (a.R.ptr) ocols += a.R.ce - a.R.cb;
+   if (a.R.ptr) ocols += (a.R.ce - a.R.cb) * (a.R2 ? 2 : 1);
    const double abytes = 8.0 * (double)n * ((a.need_y ? 2.0 : 1.0) * m + ocols);
 
    // ---- wide plan: restart sweep (TMA-staged, Gram blocks) ----

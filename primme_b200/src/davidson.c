@@ -125,6 +125,10 @@ static int candidates_sweep(pb_solver *S, int basisSize, const double *hblk, con
       if (S->fuse_enabled && X == S->V + (size_t)S->ld * basisSize &&
             pb200_dvwxr_can_fuse_gram(S->dev, S->n, S->V, S->W, basisSize, S->ld, nb, &o)) {
          o.P_host = S->fusedP, o.ldP = S->maxBasis + 8;
+         /* the residuals go straight into the basis tail as well (the Ritz vectors are not needed
+          * by this correction): no copy kernel in solve_correction */
+         o.X[0].ptr = NULL;
+         o.R2 = X, o.ldR2 = S->ld;
          fused = 1;
       }
    } else {
@@ -404,7 +408,9 @@ static int solve_correction(pb_solver *S, double *evals, int numLocked, int basi
          for (int b = 0; b < blockSize; b++) olsenEps[b] = -olsenEps[b];
          rc = pb200_daxpy_columns(S->dev, S->n, olsenEps, x, S->ld, r, S->ld, blockSize);
       }
-      if (!rc) rc = pb_apply_precond(S, r, S->ld, x, S->ld, blockSize);
+      if (!rc && !(S->fusedP_nb == blockSize && blockSize > 0 && !cp->precondition))
+         rc = pb_apply_precond(S, r, S->ld, x, S->ld, blockSize);
+      /* else: the candidates sweep already wrote the residual block into x (fused path) */
    }
    primme->ShiftsForPreconditioner = NULL;
    if (owns) free(sorted), free(ilev);

@@ -33,6 +33,18 @@ def setup_rank(lib, api, csr, rank, world, local):
     dist.broadcast(uid, 0)
     raw = bytes(uid.cpu().numpy().tobytes())
     assert lib.pb200_ctx_comm_init(ctx, world, rank, raw) == 0
+    # peer-memory panel exchange: all-gather the IPC handles of the exchange buffers
+    if dist.get_backend() == "nccl" or torch.cuda.is_available():
+        hbuf = (C.c_char * 64)()
+        assert lib.pb200_ctx_peer_export(ctx, hbuf) == 0
+        mine = torch.frombuffer(bytearray(hbuf.raw), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            mine = mine.cuda()
+        allh = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+        rc = lib.pb200_ctx_peer_attach(ctx, world, rank, blob)
+        assert rc in (0, 1), rc
     lip = np.ascontiguousarray(ip[lo:hi + 1] - ip[lo], dtype=np.int64)
     lix = np.ascontiguousarray(ix[ip[lo]:ip[hi]], dtype=np.int32)
     lda = np.ascontiguousarray(da[ip[lo]:ip[hi]], dtype=np.float64)
@@ -50,6 +62,9 @@ def declare(lib):
     lib.pb200_ctx_comm_free.restype, lib.pb200_ctx_comm_free.argtypes = i32, [vp]
     lib.pb200_dist_csr_create.restype, lib.pb200_dist_csr_create.argtypes = i32, [vp, vp, vp, i32, C.POINTER(vp)]
     lib.pb200_dist_csr_destroy.restype, lib.pb200_dist_csr_destroy.argtypes = i32, [vp, vp]
+    lib.pb200_ctx_peer_export.restype, lib.pb200_ctx_peer_export.argtypes = i32, [vp, vp]
+    lib.pb200_ctx_peer_attach.restype, lib.pb200_ctx_peer_attach.argtypes = i32, [vp, i32, i32, C.c_char_p]
+    lib.pb200_ctx_peer_active.restype, lib.pb200_ctx_peer_active.argtypes = i32, [vp]
 
 
 def sharded_solve(lib, api, ctx, D, n, nloc, rank, world, devecs, evals, rn, **workload):
@@ -99,7 +114,8 @@ def main():
         res = np.linalg.norm(AX - Xf * evals, axis=0)
         print("RESULT " + json.dumps(dict(rc=rc, evals=evals.tolist(), res=res.tolist(),
                                           orth=float(np.abs(Xf.T @ Xf - np.eye(k)).max()),
-                                          matvecs=p.stats.numMatvecs, launches=lib.pb200_ctx_launches(ctx))))
+                                          matvecs=p.stats.numMatvecs, launches=lib.pb200_ctx_launches(ctx),
+                                          peer_exchange=lib.pb200_ctx_peer_active(ctx))))
     lib.pb200_free(ctx, devecs)
     lib.pb200_dist_csr_destroy(ctx, D)
     lib.pb200_csr_destroy(ctx, A)

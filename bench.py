@@ -222,6 +222,7 @@ def main():
     k = WORKLOAD["numEvals"]
 
     sharded = world > 1 and args.multi == "sharded"
+    peer_active = False
     D = None
     nloc = n
     if sharded:
@@ -229,6 +230,7 @@ def main():
         MG.declare(lib)
         ctx, A, D, counts, (lo, hi) = MG.setup_rank(lib, api, csr, rank, world, local)
         nloc = hi - lo
+        peer_active = bool(lib.pb200_ctx_peer_active(ctx))
     else:
         ctx = C.c_void_p()
         assert lib.pb200_ctx_create(C.byref(ctx), local) == 0
@@ -394,7 +396,8 @@ def main():
                 "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args.side), "n": n, "nnz": nnz,
-                           "parallelism": (f"row-sharded x{world}, NCCL panel all-reduce + NCCL halo exchange" if sharded
+                           "parallelism": (f"row-sharded x{world}, " + ("in-kernel panel all-reduce over NVLink peer memory" if peer_active
+                                                                         else "NCCL panel all-reduce") + " + NCCL halo all-gather" if sharded
                                            else "replicas only" if args.gpus > 1 else "single GPU"),
                            "l2": "working set per sweep (V,W 2x320 MB at n=1e6) exceeds the 126 MB L2; no flush",
                            "outer_iterations": stats["numOuterIterations"], "restarts": stats["numRestarts"],

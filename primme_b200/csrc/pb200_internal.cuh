@@ -138,7 +138,7 @@ __device__ __forceinline__ void pb_fin_store(const PbFin &f, int e, double s) {
          unsigned long long spins = 0;
          do {
             asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "l"(src) : "memory");
-         } while (__double_as_longlong(vy) != f.tag && ++spins < (1ull << 28));  // bounded: a lost peer must not hang the GPU
+         } while (__double_as_longlong(vy) != f.tag && ++spins < (1ull << 27));  // bounded: a lost peer must not hang the GPU
          tot += (__double_as_longlong(vy) == f.tag) ? vx : __longlong_as_double(0x7ff8000000000000ll);
       }
       s = tot;

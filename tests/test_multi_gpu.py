@@ -31,6 +31,7 @@ def test_two_gpu_row_sharded_solve(bs):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1][7:])
     assert out["rc"] == 0 and out["launches"] > 0
+    assert out["peer_exchange"] == 1  # panels all-reduced inside the kernels over NVLink peer memory
     shape = (32, 29, 37)
     lam = [2 - 2 * np.cos(np.pi * np.arange(1, s + 1) / (s + 1)) for s in shape]
     exact = np.sort((lam[0][:, None, None] + lam[1][None, :, None] + lam[2][None, None, :]).ravel())[:6]

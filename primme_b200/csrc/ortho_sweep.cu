@@ -34,7 +34,6 @@ struct SweepArgs {
    int bt;              // leading dimension of Y / column count of the packed C (b padded to 1,2,4,8)
    int stage_doubles;   // size of the stage ring of the MMA kernel (>= the end-of-kernel panel scratch)
    int qpad, xcol0;     // MMA kernel: virtual column of the first V / first X column
-   int dbg;             // timing experiments only (PB200_DBG): wrong results when non-zero
    unsigned long long *trace;  // PB200_TRACE: [cta][8] %globaltimer stamps
    const double *Cdev;  // (q+mv) x BT, column stride = (q+mv)
    const double *Ydev;  // BT x BT, column stride BT
@@ -331,7 +330,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_kernel(SweepArgs
          const double *pa = st + offu;
          const double *pc = cpu;
 #pragma unroll 2
-         for (int i = 0; i < ((a.dbg & 2) ? 0 : nks2); i++) {
+         for (int i = 0; i < nks2; i++) {
             const double a0 = pa[0], a1 = pa[4 * S];
             dmma884(d0, d1, a0, pc[0]);
             dmma884(e0, e1, a1, pc[4 * CS_LD]);
@@ -358,21 +357,21 @@ __global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_kernel(SweepArgs
          // CS_LD): the Gram below takes its X operand from there (the stage itself is only ever
          // written by the TMA unit, so no proxy fence is needed before it is refilled)
          const int64_t r = tile * TR + r0w + g;
-         if (2 * t < a.b && r < a.n && !(a.dbg & 1)) a.X[r + (size_t)(2 * t) * a.ldx] = d0;
-         if (2 * t + 1 < a.b && r < a.n && !(a.dbg & 1)) a.X[r + (size_t)(2 * t + 1) * a.ldx] = d1;
+         if (2 * t < a.b && r < a.n) a.X[r + (size_t)(2 * t) * a.ldx] = d0;
+         if (2 * t + 1 < a.b && r < a.n) a.X[r + (size_t)(2 * t + 1) * a.ldx] = d1;
          xw[(2 * t) * CS_LD + g] = d0;
          xw[(2 * t + 1) * CS_LD + g] = d1;
          __syncwarp();
          xb = xw + g * CS_LD + t;
       }
-      if (a.do_gram && !(a.dbg & 8)) {
+      if (a.do_gram) {
          const double *pg = st + offg;
 #pragma unroll
          for (int ks = 0; ks < 2; ks++) {
             const double bf = xb[4 * ks];
 #pragma unroll
             for (int mt = 0; mt < MT; mt++)
-               if (mt < nmtv) dmma884(acc[mt][0], acc[mt][1], (a.dbg & 16) ? bf : pg[mt * 8 * S + 4 * ks], bf);
+               if (mt < nmtv) dmma884(acc[mt][0], acc[mt][1], pg[mt * 8 * S + 4 * ks], bf);
             // X'X block: A(column g, row t) and B(row t, column g) are the same element
             if (a.xx) dmma884(accx[0], accx[1], bf, bf);
          }
@@ -736,7 +735,6 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
    // ---- main (TMA + DMMA) kernel eligibility: 16-byte aligned columns (tensor maps), enough
    // rows, a ring of >= 2 stages in shared memory ----
    a.bt = BT;
-   a.dbg = getenv("PB200_DBG") ? atoi(getenv("PB200_DBG")) : 0;
    // virtual column layout of a stage (see the kernel): Q padded to 4, V padded so that X starts
    // at a multiple of 8, X padded to 8
    const int qpad = mv > 0 ? (q + 3) & ~3 : (q + 7) & ~7;
@@ -805,7 +803,7 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
       if (tracing) clock_gettime(CLOCK_MONOTONIC, &th1);
 #define PB_MMA(MT_, NW_) rc = launch_sweep_mma<MT_, NW_>(ctx, a, maps, grid, shmem, nstages, cnt)
       // steady-state shapes (no locked vectors, Gram wanted, update always with xx): specialised
-      const bool exact = ctx->ortho_exact && nw == 16 && q == 0 && mv > 0 && a.do_gram && !a.dbg && !a.trace &&
+      const bool exact = ctx->ortho_exact && nw == 16 && q == 0 && mv > 0 && a.do_gram && !a.trace &&
                          (!a.do_update || a.xx) && nmtv >= 3 && nmtv <= 5;
       if (exact) {
          rc = nmtv == 3 ? dispatch_exact<3>(ctx, a, maps, grid, shmem, nstages, cnt)

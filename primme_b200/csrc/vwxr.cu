@@ -39,7 +39,6 @@ struct VwxrArgs {
    int rb, re;
    int nG, nH;
    int need_y;              // whether W*h is needed at all
-   int dbg;                 // timing experiments only (PB200_DBG): wrong results when non-zero
    double *R2;              // second destination of the residual columns (MMA kernel only)
    int64_t ldR2;
    int nP;                  // > 0: also P = [V R]^T R, (m + nP) x nP with nP = R.ce - R.cb (MMA kernel only)
@@ -592,9 +591,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) vwxr_mma_kernel(VwxrArgs a, cons
    unsigned yres = 0, xres = 0, wnorm = 0, slow = 0;
 #pragma unroll
    for (int q = 0; q < NQ; q++) {
-      // (dbg & 8, timing experiment with wrong results: the store pattern of a transposed epilogue,
-      // every warp store covers 32 consecutive rows of one column)
-      const int cc = (a.dbg & 8) ? 4 * q + (warp & 3) : 8 * (q >> 1) + 2 * t + (q & 1);
+      const int cc = 8 * (q >> 1) + 2 * t + (q & 1);
       px[q] = py[q] = nullptr;
       thv[q] = th[cc];
       int nx = 0, ny = 0;
@@ -652,7 +649,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) vwxr_mma_kernel(VwxrArgs a, cons
       {
          const double *pv = st + offu, *pw = pv + mpad * S, *pb = hb;
 #pragma unroll 2
-         for (int ks = 0; ks < ((a.dbg & 4) ? 1 : nks); ks++) {
+         for (int ks = 0; ks < nks; ks++) {
             const double av = pv[0], aw = pw[0];
 #pragma unroll
             for (int i = 0; i < NT8; i++) {
@@ -668,8 +665,8 @@ __global__ void __launch_bounds__(NW * 32 + 32) vwxr_mma_kernel(VwxrArgs a, cons
          if (lane == 0) pbtma::mbar_arrive(&empty[s]);
       }
       // ---- residuals, norms, scatter (fragment layout: row g, columns 8 i + 2 t + j) ----
-      const int64_t r = (a.dbg & 8) ? tile * TR + (warp >> 2) * 32 + lane : tile * TR + r0w + g;
-      const bool rok = r < a.n && !(a.dbg & 1);
+      const int64_t r = tile * TR + r0w + g;
+      const bool rok = r < a.n;
       if (!slow) {
 #pragma unroll
          for (int q = 0; q < NQ; q++) {
@@ -721,7 +718,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) vwxr_mma_kernel(VwxrArgs a, cons
          }
          __syncwarp();
          if (lane == 0) pbtma::mbar_arrive(&empty[s]);
-      } else if (gh && !(a.dbg & 2)) {
+      } else if (gh) {
          // every tile of G (upper) and H is accumulated, whatever nG and nH: columns past them
          // are simply not read back
 #pragma unroll
@@ -885,7 +882,6 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
    a.nG = o->G_host ? o->nG : 0;
    a.nH = o->H_host ? o->nH : 0;
    a.need_y = (a.Wo.ptr || a.R.ptr || a.re > a.rb || a.nH > 0) ? 1 : 0;
-   a.dbg = getenv("PB200_DBG") ? atoi(getenv("PB200_DBG")) : 0;
    const int nR = a.R.ptr ? a.R.ce - a.R.cb : 0, nr = a.re - a.rb;
    const int nn = (nR + nr) > 0 ? nh : 0;
    int cnt = nn + a.nG * a.nG + a.nH * a.nH;
@@ -984,7 +980,8 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
             return st >= 2 && *shm <= 227 * 1024;
          };
          int nw = (nt8 == 1 && mt <= 5) ? 16 : 8;
-         if (nw == 16 && !(plan(16, &mma_nst, &mma_shm) && mma_nst >= 3)) nw = 8;
+         static const int min_st16 = getenv("PB200_VWXR_MIN_STAGES16") ? atoi(getenv("PB200_VWXR_MIN_STAGES16")) : 2;
+         if (nw == 16 && !(plan(16, &mma_nst, &mma_shm) && mma_nst >= min_st16)) nw = 8;
          ok = plan(nw, &mma_nst, &mma_shm);
          if (ok) {
             memset(&maps, 0, sizeof(maps));

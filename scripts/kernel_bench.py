@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--config", default="c2")
     ap.add_argument("--side", type=int, default=100)
+    ap.add_argument("--mbar", type=int, default=0, help="basis size of the steady-state shapes (default 28 / 48)")
     args = ap.parse_args()
     lib = api.load_library(os.environ.get("PB200_LIB"))  # PB200_LIB: experimental build variants
     ctx = C.c_void_p()
@@ -31,6 +32,8 @@ def main():
     else:
         n, mmax, b, mbar, rs = 1250000, 64, 8, 48, 32
         csr = M.power_law_symmetric(n, mean_degree=15.0, seed=7)
+    if args.mbar > 0:
+        mbar = args.mbar
     ld = (n + 15) // 16 * 16
     rng = np.random.default_rng(0)
 

@@ -221,6 +221,13 @@ pb200_ctx *primme_b200_solver_ctx(const struct primme_params *primme);
 int primme_b200_dprimme_csr(double *evals, double *evecs_host, double *resNorms,
       struct primme_params *primme, const int64_t *rowptr_host, const int32_t *colind_host,
       const double *vals_host, int index_base);
+/* Built-in operator of the SVD front end (cublas_dprimme_svds): primme_svds.matrix = pb200_csr*
+ * of the m x n matrix with its transposed copy (pb200_csr_build_transpose), primme_svds.matrixMatvec
+ * = this function; y = A x or A' x on device blocks (reference user callback contract
+ * include/primme_svds.h:113-116, examples/ex_svds_dseq.c:188-230). */
+struct primme_svds_params;
+void primme_b200_svds_csr_matvec(void *x, int64_t *ldx, void *y, int64_t *ldy, int *blockSize,
+      int *transpose, struct primme_svds_params *primme_svds, int *ierr);
 
 #ifdef __cplusplus
 }

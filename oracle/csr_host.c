@@ -80,3 +80,33 @@ void csr_host_jacobi(void *x, PRIMME_INT *ldx, void *y, PRIMME_INT *ldy, int *bl
    }
    *ierr = 0;
 }
+
+/* ---- rectangular operator with the SVD callback signature (reference examples/ex_svds_dseq.c:188-230,
+ * tests/COMMON/mat.c CSRMatrixMatvecSVD): y = A x (transpose == 0) or y = A' x, host blocks ---- */
+typedef struct csr_host_rect {
+   int64_t m, n;
+   const int64_t *rowptr; /* m + 1, 0-based */
+   const int32_t *colind;
+   const double *vals;
+} csr_host_rect;
+
+void csr_host_svds_matvec(void *x, PRIMME_INT *ldx, void *y, PRIMME_INT *ldy, int *blockSize, int *transpose,
+      primme_svds_params *primme_svds, int *ierr) {
+   const csr_host_rect *A = (const csr_host_rect *)primme_svds->matrix;
+   for (int c = 0; c < *blockSize; c++) {
+      const double *xc = (const double *)x + (size_t)c * *ldx;
+      double *yc = (double *)y + (size_t)c * *ldy;
+      if (!*transpose) {
+         for (int64_t i = 0; i < A->m; i++) {
+            double t = 0.0;
+            for (int64_t k = A->rowptr[i]; k < A->rowptr[i + 1]; k++) t += A->vals[k] * xc[A->colind[k]];
+            yc[i] = t;
+         }
+      } else {
+         for (int64_t j = 0; j < A->n; j++) yc[j] = 0.0;
+         for (int64_t i = 0; i < A->m; i++)
+            for (int64_t k = A->rowptr[i]; k < A->rowptr[i + 1]; k++) yc[A->colind[k]] += A->vals[k] * xc[i];
+      }
+   }
+   *ierr = 0;
+}

@@ -22,6 +22,11 @@ def declared_functions():
     for base in re.findall(r"^PRIMME_DECLARE_SOLVERS_\((\w+),", eigs, flags=re.M):
         names |= {base, "magma_" + base, "cublas_" + base}
     names |= set(re.findall(r"^(?:int|void|primme_params \*)\s*\*?(primme_\w+)\(", eigs, flags=re.M))
+    # SVD front end: every solver flavour and the parameter API
+    svds = open(os.path.join(ROOT, "include", "primme_svds.h")).read()
+    for base in re.findall(r"^PRIMME_DECLARE_SVDS_ALL_\((\w+),", svds, flags=re.M):
+        names |= {base, "magma_" + base, "cublas_" + base}
+    names |= set(re.findall(r"^(?:int|void|primme_svds_params \*)\s*\*?(primme_svds_\w+)\(", svds, flags=re.M))
     # reference-internal entry points of the reference's own test driver
     internal = open(os.path.join(ROOT, "include", "primme_ref_internal.h")).read()
     internal = re.sub(r"/\*.*?\*/", "", internal, flags=re.S)

@@ -982,6 +982,10 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
          int nw = (nt8 == 1 && mt <= 5) ? 16 : 8;
          static const int min_st16 = getenv("PB200_VWXR_MIN_STAGES16") ? atoi(getenv("PB200_VWXR_MIN_STAGES16")) : 2;
          if (nw == 16 && !(plan(16, &mma_nst, &mma_shm) && mma_nst >= min_st16)) nw = 8;
+         // restart shape (3 tiles of h): 10 consumer warps (80-row tiles) when 3 stages still fit --
+         // the kernel is bound by the instruction latency of its few warps, registers allow 10
+         static const int nw_restart = getenv("PB200_VWXR_RESTART_WARPS") ? atoi(getenv("PB200_VWXR_RESTART_WARPS")) : 10;
+         if (nt8 == 3 && nw == 8 && nw_restart == 10 && plan(10, &mma_nst, &mma_shm) && mma_nst >= 3) nw = 10;
          ok = plan(nw, &mma_nst, &mma_shm);
          if (ok) {
             memset(&maps, 0, sizeof(maps));
@@ -1019,7 +1023,7 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
    if (mma_nt8) {
 #define VM(NT8_, MT_, NW_) \
    if (mma_nt8 == NT8_ && mma_mt == MT_ && mma_nw == NW_) rc = launch_vwxr_mma<NT8_, MT_, NW_>(ctx, a, maps, grid, mma_shm, mma_nst);
-      VM(1, 0, 16) VM(1, 5, 16) VM(1, 0, 8) VM(1, 5, 8) VM(1, 9, 8) VM(2, 0, 8) VM(3, 0, 8) VM(4, 0, 8)
+      VM(1, 0, 16) VM(1, 5, 16) VM(1, 0, 8) VM(1, 5, 8) VM(1, 9, 8) VM(2, 0, 8) VM(3, 0, 8) VM(3, 0, 10) VM(4, 0, 8)
 #undef VM
    } else if (wide_nst >= 2) {
 #define VW3(NTH_, NG_) \

@@ -982,9 +982,9 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
          int nw = (nt8 == 1 && mt <= 5) ? 16 : 8;
          static const int min_st16 = getenv("PB200_VWXR_MIN_STAGES16") ? atoi(getenv("PB200_VWXR_MIN_STAGES16")) : 2;
          if (nw == 16 && !(plan(16, &mma_nst, &mma_shm) && mma_nst >= min_st16)) nw = 8;
-         // restart shape (3 tiles of h): 10 consumer warps (80-row tiles) when 3 stages still fit --
-         // the kernel is bound by the instruction latency of its few warps, registers allow 10
-         static const int nw_restart = getenv("PB200_VWXR_RESTART_WARPS") ? atoi(getenv("PB200_VWXR_RESTART_WARPS")) : 10;
+         // restart shape (3 tiles of h): optional 10 consumer warps (80-row tiles); measured equal to
+         // 8 warps (397 vs 390 us at C2), so 8 warps with the deeper ring stay the default
+         static const int nw_restart = getenv("PB200_VWXR_RESTART_WARPS") ? atoi(getenv("PB200_VWXR_RESTART_WARPS")) : 8;
          if (nt8 == 3 && nw == 8 && nw_restart == 10 && plan(10, &mma_nst, &mma_shm) && mma_nst >= 3) nw = 10;
          ok = plan(nw, &mma_nst, &mma_shm);
          if (ok) {

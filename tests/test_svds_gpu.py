@@ -50,7 +50,8 @@ def test_cublas_dprimme_svds_builtin_operator(shape, k):
     S.set_member(lib, p, "eps", 1e-9)
     assert lib.primme_svds_set_method(S.primme_svds_normalequations, api.PRIMME_GD_Olsen_plusK, api.PRIMME_DEFAULT_METHOD, p) == 0
     inner = S.get_member(lib, p, "primme")  # address of the first-stage primme_params
-    lib.primme_b200_attach_ctx(C.c_void_p(inner), ctx)
+    inner_p = C.cast(C.c_void_p(inner), C.POINTER(api.PrimmeParams))
+    lib.primme_b200_attach_ctx(inner_p, ctx)
     dsvecs = C.c_void_p()
     assert lib.pb200_malloc(ctx, 8 * (m + n) * k, C.byref(dsvecs)) == 0
     svals, rn = np.zeros(k), np.zeros(k)
@@ -69,7 +70,7 @@ def test_cublas_dprimme_svds_builtin_operator(shape, k):
     assert np.allclose(np.sort(svals)[::-1], want, rtol=1e-8)
     assert np.abs(V.T @ V - np.eye(k)).max() < 1e-8 and np.abs(U.T @ U - np.eye(k)).max() < 1e-6
     assert np.linalg.norm(As @ V - U * svals, axis=0).max() < 1e-7 * want[0]
-    lib.primme_b200_attach_ctx(C.c_void_p(inner), None)
+    lib.primme_b200_attach_ctx(inner_p, None)
     lib.pb200_free(ctx, dsvecs)
     lib.primme_svds_params_destroy(p)
     lib.pb200_csr_destroy(ctx, A)

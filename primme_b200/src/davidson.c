@@ -379,7 +379,39 @@ static int solve_correction(pb_solver *S, double *evals, int numLocked, int basi
 
    double *r = S->W + (size_t)S->ld * basisSize; /* block residuals */
    double *x = S->V + (size_t)S->ld * basisSize; /* block Ritz vectors, receives the corrections */
-   if (cp->projectors.RightX && cp->projectors.SkewX) {
+   if (cp->maxInnerIterations != 0) {
+      /* inner-outer JDQMR (correction.c:385-447, setup_JD_projectors :862-999 for the presets
+       * without right projectors): Q = [constraints locked] when LeftQ; the Ritz vector joins Q
+       * when the block is a single vector, else every system is projected against its own x_i */
+      const int sizeEvecs = primme->numOrthoConst + (primme->locking ? numLocked : 0);
+      const double *Q = NULL;
+      int nQ = 0, useX = 0;
+      if (cp->projectors.LeftQ) {
+         nQ = sizeEvecs, Q = S->evecs;
+         if (cp->projectors.LeftX) {
+            if (blockSize <= 1) {
+               rc = pb200_copy_d2d(S->dev, x, S->ld, S->evecs + (size_t)S->ldevecs * sizeEvecs, S->ldevecs, S->n,
+                     blockSize, 8);
+               nQ += blockSize;
+            } else
+               useX = 1;
+         }
+      } else if (cp->projectors.LeftX)
+         useX = 1;
+      if (!rc && !S->jd_work)
+         rc = pb200_malloc(S->dev, sizeof(double) * (size_t)S->ld * 5 * PB_MAX(primme->maxBlockSize, 1),
+               (void **)&S->jd_work);
+      if (!rc) {
+         double blockRitzVals[8];
+         for (int b = 0; b < blockSize; b++) blockRitzVals[b] = ritzVals[iev[b]];
+         double *sol = S->jd_work + (size_t)S->ld * 4 * PB_MAX(primme->maxBlockSize, 1);
+         int touch1 = S->touch;
+         rc = pb_inner_solve(S, blockSize, x, S->ld, r, S->ld, blockNorms, Q, S->ldevecs, nQ, useX, sol, S->ld,
+               blockRitzVals, shifts, &touch1, S->jd_work);
+         S->touch = PB_MAX(S->touch, touch1);
+         if (!rc) rc = pb200_copy_d2d(S->dev, sol, S->ld, x, S->ld, S->n, blockSize, 8);
+      }
+   } else if (cp->projectors.RightX && cp->projectors.SkewX) {
       /* exact Olsen projector (correction.c:695-774): x <- K^{-1}r - (x'K^{-1}r / x'K^{-1}x) K^{-1}x */
       double *tmp = NULL;
       rc = pb200_malloc(S->dev, sizeof(double) * (size_t)S->ld * blockSize * 2, (void **)&tmp);
@@ -570,6 +602,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
                /* fused first Gram panel: only when the correction below is a plain copy of the
                 * residuals and the block is orthogonalised against the basis alone */
                S->fuse_enabled = S->fuse_allowed && S->VtBV != NULL && !primme->correctionParams.precondition &&
+                                 primme->correctionParams.maxInnerIterations == 0 &&
                                  !(primme->correctionParams.projectors.RightX && primme->correctionParams.projectors.SkewX) &&
                                  !(primme->correctionParams.projectors.RightX && primme->locking &&
                                        primme->orth == primme_orth_implicit_I) &&
@@ -590,6 +623,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
             }
 
             numConverged += recentlyConverged;
+            if (recentlyConverged > 0) S->touch = 0; /* main_iter.c:597-599 */
 
             CHK(pb_monitor(S, S->hVals, basisSize, flags, iev, blockSize, S->basisNorms,
                   numConverged, evals, numLocked, S->lockedFlags, resNorms, -1, -1.0, NULL, 0.0,

@@ -309,8 +309,9 @@ static int check_scope(primme_params *p) {
             (p->globalSumReal && p->globalSumReal_type != primme_op_default &&
                   p->globalSumReal_type != primme_op_double))
       why = "callback datatypes other than double";
-   else if (p->correctionParams.maxInnerIterations != 0)
-      why = "inner QMR iterations (JDQMR family)";
+   else if (p->correctionParams.maxInnerIterations != 0 &&
+            (p->correctionParams.projectors.RightQ || p->correctionParams.projectors.RightX))
+      why = "inner QMR iterations with right / skew projectors (only the JDQMR and JDQMR_ETol presets)";
    else if (p->maxBlockSize > 8) why = "maxBlockSize > 8";
    if (!why) return 0;
    if (p->outputFile && p->printLevel >= 1 && p->procID == 0)
@@ -325,6 +326,7 @@ static void free_solver(pb_solver *S, int own_evecs) {
    }
    free(S->hstage), free(S->hstage2);
    free(S->H), free(S->hVecs), free(S->prevhVecs), free(S->VtBV), free(S->fVtBV), free(S->fusedP);
+   if (S->dev && S->jd_work) pb200_free(S->dev, S->jd_work);
    free(S->hVals), free(S->prevRitzVals), free(S->blockNorms), free(S->basisNorms);
    free(S->flags), free(S->map), free(S->iev), free(S->perm), free(S->lockedFlags);
    if (S->dev) pb200_ctx_destroy(S->dev);

@@ -49,6 +49,9 @@ typedef struct pb_solver {
    double *fusedP;
    int fusedP_m, fusedP_nb; /* fusedP_nb > 0: valid for basis size m and a block of nb columns */
    int fuse_allowed, fuse_enabled, fuse_sweeps;
+   /* inner QMR solver (JDQMR family): g, d, delta, w, sol -- 5 x ld x maxBlockSize, device */
+   double *jd_work;
+   int touch; /* stopping-criterion state of the inner solver (main_iter.c:206,597-599) */
 } pb_solver;
 
 /* error propagation in the style of the reference's CHKERR (common.h:484-494) */
@@ -103,6 +106,11 @@ int pb_ortho_single_iteration(pb_solver *S, const double *Q, int nQ, int64_t ldQ
       double *norms);
 int pb_ortho_local(double *V, int ldV, double *R, int b1, int b2, double *locked, int ldLocked,
       int numLocked, int n, const double *B, int ldB, long long *iseed);
+
+/* dav_jdqmr.c */
+int pb_inner_solve(pb_solver *S, int blockSize, double *x, int64_t ldx, double *r, int64_t ldr, const double *rnorm,
+      const double *Q, int64_t ldQ, int nQ, int useX, double *sol, int64_t ldsol, const double *eval, double *shift,
+      int *touch, double *work);
 
 /* dav_restart.c */
 int pb_restart(pb_solver *S, int basisSize, int *ievSize, double *evals, double *resNorms,

@@ -5,9 +5,9 @@ through the public API with the reference's host CSR matvec / Jacobi preconditio
 check_solution (tests/COMMON/ioandtest.c:86-150) verifies eigenvalues, residual norms,
 orthogonality and the angle to the STORED reference solutions tests/sol_00N_double, and
 checkInterface exercises primme_get_member/set_member on every field.  Exit code 0 = all checks
-passed.  test_006 selects PRIMME_DEFAULT_MIN_TIME (JDQMR inner solver) and
-test_007 refined extraction: the product must refuse them with PRIMME_FUNCTION_UNAVAILABLE rather
-than run something else."""
+passed.  test_006 selects PRIMME_DEFAULT_MIN_TIME (JDQMR_ETol with the Jacobi preconditioner of the
+driver).  test_007 asks for refined extraction: the product must refuse it with
+PRIMME_FUNCTION_UNAVAILABLE rather than run something else."""
 import os
 import subprocess
 
@@ -24,7 +24,7 @@ def run(cfg):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cfg", ["test_001", "test_002", "test_003", "test_004", "test_005"])
+@pytest.mark.parametrize("cfg", ["test_001", "test_002", "test_003", "test_004", "test_005", "test_006"])
 def test_reference_driver_passes_its_own_checks(cfg):
     if not os.path.exists(DRIVER):
         pytest.skip("driver binary not built (needs the reference tree at build time)")
@@ -33,9 +33,9 @@ def test_reference_driver_passes_its_own_checks(cfg):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cfg", ["test_006", "test_007"])
+@pytest.mark.parametrize("cfg", ["test_007"])
 def test_reference_driver_out_of_scope_config_is_refused(cfg):
-    """test_006: PRIMME_DEFAULT_MIN_TIME (JDQMR inner solver); test_007: refined extraction"""
+    """test_007: refined extraction"""
     if not os.path.exists(DRIVER):
         pytest.skip("driver binary not built")
     r = run(cfg)

@@ -1,0 +1,64 @@
+"""JDQMR family: the inner QMR solver and the Jacobi-Davidson correction of the
+host logic (primme_b200/src/dav_jdqmr.c, davidson.c) against the UNMODIFIED reference on the same
+matrices, callbacks and parameters.  Single-vector blocks and the ETol variants follow the
+reference decision for decision (identical outer iteration, restart and matvec counts); blocks > 1
+differ by rounding only (the reference's fused host loop vs separate kernels), so their counts are
+compared within 6 %."""
+import numpy as np
+import pytest
+
+import harness as H
+from golden.cases import MATRICES
+from primme_b200 import api, matrices as M
+
+KEYS = ("numOuterIterations", "numMatvecs", "numRestarts")
+LAP = lambda: M.laplacian_nd((12, 11, 10))
+
+EXACT = {
+    "lap3d_jdqmr": (LAP, 4, dict(method=api.PRIMME_JDQMR, eps=1e-9)),
+    "lap3d_jdqmr_etol_jacobi": (LAP, 4, dict(method=api.PRIMME_JDQMR_ETol, eps=1e-9, jacobi=True)),
+    "lap3d_jdqmr_locking": (LAP, 5, dict(method=api.PRIMME_JDQMR, eps=1e-9, locking=1, jacobi=True)),
+    "lap3d_etol_largest": (LAP, 4, dict(method=api.PRIMME_JDQMR_ETol, eps=1e-9, target=api.primme_largest, jacobi=True)),
+    "lap3d_jdqmr_block2": (LAP, 4, dict(method=api.PRIMME_JDQMR, eps=1e-9, maxBlockSize=2, jacobi=True)),
+    "lap3d_etol_block3": (LAP, 6, dict(method=api.PRIMME_JDQMR_ETol, eps=1e-9, maxBlockSize=3)),
+    "lap3d_min_time": (LAP, 4, dict(method=api.PRIMME_DEFAULT_MIN_TIME, eps=1e-9, jacobi=True)),
+    "lap3d_min_matvecs": (LAP, 4, dict(method=api.PRIMME_DEFAULT_MIN_MATVECS, eps=1e-9, jacobi=True)),
+    "lap3d_closest_abs": (LAP, 3, dict(method=api.PRIMME_JDQMR, eps=1e-8, target=api.primme_closest_abs,
+                                       targetShifts=[1.0], jacobi=True)),
+    "aniso_jdqmr_jacobi": (MATRICES["aniso3d"], 5, dict(method=api.PRIMME_JDQMR, eps=1e-9, jacobi=True)),
+    "aniso_etol_locking": (MATRICES["aniso3d"], 5, dict(method=api.PRIMME_JDQMR_ETol, eps=1e-9, jacobi=True, locking=1)),
+    "lap2d_jdqmr_noprec": (MATRICES["lap2d"], 3, dict(method=api.PRIMME_JDQMR, eps=1e-8)),
+}
+CLOSE = {
+    "aniso_jdqmr_block4": (MATRICES["aniso3d"], 6, dict(method=api.PRIMME_JDQMR, eps=1e-9, maxBlockSize=4, jacobi=True)),
+    "powerlaw_jdqmr": (MATRICES["powerlaw_4k"], 5, dict(method=api.PRIMME_JDQMR, eps=1e-9, jacobi=True,
+                                                        target=api.primme_largest)),
+}
+
+
+def run_pair(case):
+    mat, k, kw = case
+    csr = mat()
+    ref = H.solve("reference", csr, k, **kw)
+    got = H.solve("hostcheck", csr, k, **kw)
+    assert ref["ret"] == 0 and got["ret"] == 0 and got["initSize"] == k
+    scale = max(1.0, np.abs(ref["evals"]).max())
+    assert np.abs(got["evals"] - ref["evals"]).max() <= 1e-10 * scale * 10
+    X = got["evecs"]
+    R = M.csr_matvec(*csr, X) - X * got["evals"]
+    anorm = np.abs(np.asarray(csr[2])).sum() / (len(csr[0]) - 1) * 4
+    assert np.linalg.norm(R, axis=0).max() <= 10 * kw["eps"] * anorm
+    return ref, got
+
+
+@pytest.mark.parametrize("name", sorted(EXACT))
+def test_jdqmr_same_decisions_as_reference(name):
+    ref, got = run_pair(EXACT[name])
+    assert {k: got["stats"][k] for k in KEYS} == {k: ref["stats"][k] for k in KEYS}
+
+
+@pytest.mark.parametrize("name", sorted(CLOSE))
+def test_jdqmr_blocks_close_to_reference(name):
+    ref, got = run_pair(CLOSE[name])
+    for k in ("numOuterIterations", "numMatvecs"):
+        assert abs(got["stats"][k] - ref["stats"][k]) <= max(2, 0.06 * ref["stats"][k]), (got["stats"], ref["stats"])

@@ -72,6 +72,6 @@ def test_error_codes():
     p = api.new_params(lib, 10, numEvals=20, method=api.PRIMME_GD)
     ev = np.zeros(20)
     assert lib.dprimme(ev.ctypes.data, ev.ctypes.data, ev.ctypes.data, C.byref(p)) == -7  # no matvec
-    p = api.new_params(lib, 10, numEvals=2, method=api.PRIMME_JDQMR)
+    p = api.new_params(lib, 10, numEvals=2, method=api.PRIMME_JDQR)  # right / skew projectors: out of scope
     p.matrixMatvec = 1
-    assert lib.dprimme(ev.ctypes.data, ev.ctypes.data, ev.ctypes.data, C.byref(p)) == -44  # out of scope
+    assert lib.dprimme(ev.ctypes.data, ev.ctypes.data, ev.ctypes.data, C.byref(p)) == -44

@@ -57,6 +57,9 @@ int pb200_allreduce_host(pb200_ctx *ctx, double *buf_host, int count);
 int pb200_bcast_host(pb200_ctx *ctx, double *buf_host, int count, int root);
 
 int pb200_malloc(pb200_ctx *ctx, size_t bytes, void **dptr);
+/* Workspace owned by the context (slot 0..3), grown on demand and kept until pb200_ctx_destroy:
+ * the solver's basis arrays when the caller attached a long-lived context. */
+int pb200_ctx_workspace(pb200_ctx *ctx, int slot, size_t bytes, void **dptr);
 int pb200_free(pb200_ctx *ctx, void *dptr);
 int pb200_memset0(pb200_ctx *ctx, void *dptr, size_t bytes);
 /* 2-D copies, element size es bytes; replaces Num_set_matrix/get_matrix/copy_matrix

@@ -22,6 +22,8 @@
 struct pb200_ctx {
    int64_t launches;
    int nranks, rank;
+   void *ws_ptr[4];
+   size_t ws_bytes[4];
 };
 
 struct pb200_csr {
@@ -43,6 +45,8 @@ int pb200_ctx_create(pb200_ctx **ctx, int device) {
    return 0;
 }
 int pb200_ctx_destroy(pb200_ctx *ctx) {
+   if (ctx)
+      for (int s = 0; s < 4; s++) free(ctx->ws_ptr[s]);
    free(ctx);
    return 0;
 }
@@ -98,6 +102,16 @@ int pb200_free(pb200_ctx *ctx, void *dptr) {
    (void)ctx;
    free(dptr);
    return 0;
+}
+int pb200_ctx_workspace(pb200_ctx *ctx, int slot, size_t bytes, void **dptr) {
+   if (slot < 0 || slot >= 4) return PB200_ERR_ARG;
+   if (bytes > ctx->ws_bytes[slot]) {
+      free(ctx->ws_ptr[slot]);
+      ctx->ws_ptr[slot] = malloc(bytes ? bytes : 1);
+      ctx->ws_bytes[slot] = ctx->ws_ptr[slot] ? bytes : 0;
+   }
+   *dptr = ctx->ws_ptr[slot];
+   return *dptr ? 0 : PB200_ERR_ALLOC;
 }
 int pb200_memset0(pb200_ctx *ctx, void *dptr, size_t bytes) {
    (void)ctx;

@@ -70,6 +70,7 @@ extern "C" int pb200_ctx_destroy(pb200_ctx *ctx) {
    cudaFree(ctx->d_gpart);
    cudaFree(ctx->d_counters);
    cudaFree(ctx->d_scratch);
+   for (int s = 0; s < PB_WS_SLOTS; s++) cudaFree(ctx->ws_ptr[s]);
    for (int p = 0; p < PB_MAX_PEERS; p++)
       if (ctx->peer_on && p != ctx->rank && ctx->xchg_peer[p]) cudaIpcCloseMemHandle(ctx->xchg_peer[p]);
    cudaFree(ctx->xchg_local);
@@ -369,6 +370,29 @@ extern "C" int pb200_free(pb200_ctx *ctx, void *dptr) {
    PB_CUDA(cudaFree(dptr));
    return 0;
 }
+// Basis workspace that survives between solves on the same context: V and W (2 x ld x maxBasisSize,
+// hundreds of MB) are not re-allocated and freed by every dprimme call (cudaFree synchronises the
+// device; on a busy host both calls showed up as 0.1-1 s outliers of the end-to-end time).
+extern "C" int pb200_ctx_workspace(pb200_ctx *ctx, int slot, size_t bytes, void **dptr) {
+   if (slot < 0 || slot >= PB_WS_SLOTS) return PB200_ERR_ARG;
+   if (bytes > ctx->ws_bytes[slot]) {
+      if (ctx->ws_ptr[slot]) {
+         PB_CUDA(cudaStreamSynchronize(ctx->stream));
+         PB_CUDA(cudaFree(ctx->ws_ptr[slot]));
+         ctx->ws_ptr[slot] = NULL, ctx->ws_bytes[slot] = 0;
+      }
+      cudaError_t e = cudaMalloc(&ctx->ws_ptr[slot], bytes ? bytes : 16);
+      if (e != cudaSuccess) {
+         cudaGetLastError();
+         *dptr = NULL;
+         return PB200_ERR_ALLOC;
+      }
+      ctx->ws_bytes[slot] = bytes;
+   }
+   *dptr = ctx->ws_ptr[slot];
+   return 0;
+}
+
 extern "C" int pb200_memset0(pb200_ctx *ctx, void *dptr, size_t bytes) {
    PB_CUDA(cudaMemsetAsync(dptr, 0, bytes, ctx->stream));
    return 0;

@@ -36,6 +36,7 @@ struct PbCoef {
    double v[PB_COEF_MAX];
 };
 
+#define PB_WS_SLOTS 4
 #define PB_MAX_PEERS 8
 #define PB_XCHG_SLOTS 4
 #define PB_XCHG_CAP 4096   // pairs per (slot, rank)
@@ -82,6 +83,9 @@ struct pb200_ctx {
    double prof_ms[8];
    double prof_bytes[8];
    int64_t prof_cnt[8];
+   // basis workspace kept between solves (pb200_ctx_workspace)
+   void *ws_ptr[PB_WS_SLOTS];
+   size_t ws_bytes[PB_WS_SLOTS];
    // peer-memory panel exchange (see PbFin)
    double2 *xchg_local;
    double2 *xchg_peer[PB_MAX_PEERS];

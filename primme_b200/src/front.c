@@ -416,8 +416,15 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
    const int mb = S->maxBasis, mr = S->maxRank;
    const int nevecs = primme->numOrthoConst + PB_MAX(primme->numEvals, primme->initSize);
 
-   rc = pb200_malloc(S->dev, sizeof(double) * (size_t)PB_MAX(S->ld, 1) * mb, (void **)&S->V);
-   if (!rc) rc = pb200_malloc(S->dev, sizeof(double) * (size_t)PB_MAX(S->ld, 1) * mb, (void **)&S->W);
+   /* a caller-attached (long-lived) context keeps the basis arrays between solves */
+   const size_t basis_bytes = sizeof(double) * (size_t)PB_MAX(S->ld, 1) * mb;
+   if (own_ctx) {
+      rc = pb200_malloc(S->dev, basis_bytes, (void **)&S->V);
+      if (!rc) rc = pb200_malloc(S->dev, basis_bytes, (void **)&S->W);
+   } else {
+      rc = pb200_ctx_workspace(S->dev, 0, basis_bytes, (void **)&S->V);
+      if (!rc) rc = pb200_ctx_workspace(S->dev, 1, basis_bytes, (void **)&S->W);
+   }
    int own_evecs = 0;
    if (!rc) {
       if (device_mode) {
@@ -454,9 +461,10 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
    if (rc || !S->H || !S->hVecs || !S->prevhVecs || !S->hVals) {
       pb_registry_set_solver(primme, NULL);
       if (!own_ctx) {
-         pb200_free(S->dev, S->V), pb200_free(S->dev, S->W);
+         /* V and W belong to the attached context (pb200_ctx_workspace) */
          if (own_evecs) pb200_free(S->dev, S->evecs);
-         S->V = S->W = S->evecs = NULL;
+         if (S->jd_work) pb200_free(S->dev, S->jd_work);
+         S->V = S->W = S->evecs = S->jd_work = NULL;
          S->dev = NULL;
       }
       free_solver(S, own_evecs);
@@ -491,9 +499,10 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
             (long long)primme->stats.numOuterIterations, (long long)primme->stats.numRestarts,
             (long long)primme->stats.numMatvecs);
    if (!own_ctx) {
-      pb200_free(S->dev, S->V), pb200_free(S->dev, S->W);
+      /* V and W belong to the attached context (pb200_ctx_workspace) */
       if (own_evecs) pb200_free(S->dev, S->evecs);
-      S->V = S->W = S->evecs = NULL;
+      if (S->jd_work) pb200_free(S->dev, S->jd_work);
+      S->V = S->W = S->evecs = S->jd_work = NULL;
       S->dev = NULL;
    }
    free_solver(S, own_evecs);

@@ -5,7 +5,7 @@
 TAG=${1:-r01}
 mkdir -p gpurun_out
 echo "=== ncu full (kernel bench, 1 rep)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ortho_sweep|spmm|vwxr" -c 24 -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ortho_sweep|spmm|vwxr" -c 21 -f \
    -o gpurun_out/prof_${TAG}_kernels python scripts/kernel_bench.py --reps 1 > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -3 gpurun_out/ncu_full_$TAG.log
 echo "=== ncu launch list of one bench solve (first 4000 launches)"

@@ -56,7 +56,8 @@ def main():
                        numProcs=world, procID=rank, nLocal=nloc)
     p.matrixMatvec = C.cast(mv, C.c_void_p).value
     p.globalSumReal = C.cast(gs, C.c_void_p).value
-    assert lib.primme_set_method(api.PRIMME_GD_Olsen_plusK, C.byref(p)) == 0
+    method = getattr(api, os.environ.get("PB_METHOD", "PRIMME_GD_Olsen_plusK"))
+    assert lib.primme_set_method(method, C.byref(p)) == 0
     p.ldevecs = nloc
     evals, rn, evecs = np.zeros(k), np.zeros(k), np.zeros((k, nloc))
     rc = lib.cublas_dprimme(evals.ctypes.data, evecs.ctypes.data, rn.ctypes.data, C.byref(p))

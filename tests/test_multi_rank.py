@@ -11,11 +11,13 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("bs", [1, 3])
-def test_two_rank_row_sharded_solve(bs):
-    env = dict(os.environ, PB_BS=str(bs), OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
+@pytest.mark.parametrize("bs,method", [(1, "PRIMME_GD_Olsen_plusK"), (3, "PRIMME_GD_Olsen_plusK"),
+                                       (1, "PRIMME_JDQMR_ETol"), (2, "PRIMME_JDQMR")])
+def test_two_rank_row_sharded_solve(bs, method):
+    env = dict(os.environ, PB_BS=str(bs), PB_METHOD=method, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
+    port = 29511 + bs + (10 if "JDQMR" in method else 0)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-           "--master-addr", "127.0.0.1", "--master-port", str(29511 + bs), os.path.join(HERE, "multi_rank_worker.py")]
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "multi_rank_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1]

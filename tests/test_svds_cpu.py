@@ -55,3 +55,48 @@ def test_svds_out_of_scope_is_refused():
     csr = S.random_rect(m, n, 4, 9)
     r = S.solve("hostcheck", csr, (m, n), 2, method=S.primme_svds_hybrid, eps=1e-8)
     assert r["ret"] == api.PRIMME_FUNCTION_UNAVAILABLE and r["initSize"] == 0
+
+
+@pytest.mark.parametrize("m,n,target,preset,stage1", [
+    (300, 100, S.primme_svds_largest, S.primme_svds_normalequations, api.PRIMME_DEFAULT_METHOD),
+    (100, 300, S.primme_svds_smallest, S.primme_svds_normalequations, api.PRIMME_GD_Olsen_plusK),
+    (500, 500, S.primme_svds_largest, S.primme_svds_default, api.PRIMME_DEFAULT_METHOD),
+    (200, 50, S.primme_svds_closest_abs, S.primme_svds_augmented, api.PRIMME_JDQMR),
+])
+def test_svds_parameter_api_matches_reference(m, n, target, preset, stage1):
+    """primme_svds_initialize / set_member / set_method / get_member: every scalar member of
+    primme_svds_params and the derived first- and second-stage primme_params equal the reference's
+    (primme_svds_interface.c:107-420)"""
+    import ctypes as C
+    vals = {}
+    for which in ("reference", "hostcheck"):
+        lib = {"reference": H.lib_reference, "hostcheck": H.lib_hostcheck}[which]()
+        S.declare(lib)
+        p = lib.primme_svds_params_create()
+        for name, v in (("m", m), ("n", n), ("numSvals", 3), ("target", target), ("maxBasisSize", 24), ("maxBlockSize", 2),
+                        ("aNorm", 7.5), ("eps", 1e-7), ("locking", 1), ("printLevel", 0), ("mLocal", m), ("nLocal", n)):
+            S.set_member(lib, p, name, v)
+        shifts = (C.c_double * 1)(0.25)
+        if target == S.primme_svds_closest_abs:
+            S.set_member(lib, p, "numTargetShifts", 1)
+            S.set_member(lib, p, "targetShifts", C.addressof(shifts))
+        assert lib.primme_svds_set_method(preset, stage1, api.PRIMME_DEFAULT_METHOD, p) == 0
+        got = {name: S.get_member(lib, p, name) for name, (ident, kind) in S.LABEL.items()
+               if kind in ("I", "D") and not name.startswith("stats_")}
+        for stage in ("primme", "primmeStage2"):
+            inner = C.cast(C.c_void_p(S.get_member(lib, p, stage)), C.POINTER(api.PrimmeParams)).contents
+            for f in ("n", "nLocal", "numEvals", "target", "numTargetShifts", "locking", "initSize", "numOrthoConst",
+                      "maxBasisSize", "minRestartSize", "maxBlockSize", "maxMatvecs", "aNorm", "eps", "printLevel",
+                      "dynamicMethodSwitch", "initBasisMode"):
+                got[stage + "." + f] = getattr(inner, f)
+            got[stage + ".maxPrevRetain"] = inner.restartingParams.maxPrevRetain
+            got[stage + ".maxInnerIterations"] = inner.correctionParams.maxInnerIterations
+            got[stage + ".precondition"] = inner.correctionParams.precondition
+            got[stage + ".convTest"] = inner.correctionParams.convTest
+            got[stage + ".projection"] = inner.projectionParams.projection
+            pr = inner.correctionParams.projectors
+            got[stage + ".projectors"] = (pr.LeftQ, pr.LeftX, pr.RightQ, pr.RightX, pr.SkewQ, pr.SkewX)
+        vals[which] = got
+        lib.primme_svds_params_destroy(p)
+    diff = {k: (vals["reference"][k], vals["hostcheck"][k]) for k in vals["reference"] if vals["reference"][k] != vals["hostcheck"][k]}
+    assert not diff, diff

@@ -524,8 +524,9 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
    const int maxBasis = primme->maxBasisSize, ldh = maxBasis;
    double smallestResNorm;
    int *flags = S->flags, *iev = S->iev, *map = S->map;
-   const int gdNoPrecLocking = primme->locking && !primme->correctionParams.precondition &&
-                               primme->correctionParams.maxInnerIterations == 0;
+   /* evaluated at every use: PRIMME_DYNAMIC changes maxInnerIterations while iterating */
+#define gdNoPrecLocking \
+   (primme->locking && !primme->correctionParams.precondition && primme->correctionParams.maxInnerIterations == 0)
 
    *ret = PRIMME_MAIN_ITER_FAILURE;
    *numRet = 0;
@@ -550,8 +551,17 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
    if (rc) return rc;
    primme->initSize = 0;
 
-   /* dynamic method switching (main_iter.c:427-437) is driven by wall-clock timings in the
-    * reference; here the GD+k side of the switch is always taken (see front.c) */
+   /* dynamic method switching: inner iterations are allowed or not from run-time timings
+    * (main_iter.c:423-437) */
+   if (primme->dynamicMethodSwitch > 0) {
+      pb_dyn_init(&S->cost, primme);
+      S->cost.MV = primme->stats.timeMatvec / (double)PB_MAX(primme->stats.numMatvecs, 1);
+      if (primme->numEvals < 5 || primme->maxBasisSize + (primme->locking ? primme->numEvals : 0) >= primme->n)
+         primme->dynamicMethodSwitch = 1; /* tentatively GD+k */
+      else
+         primme->dynamicMethodSwitch = 3; /* GD+k for the first pair */
+      primme->correctionParams.maxInnerIterations = 0;
+   }
 
    while (primme->stats.numMatvecs < primme->maxMatvecs &&
           (primme->maxOuterIterations == 0 ||
@@ -624,6 +634,20 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
 
             numConverged += recentlyConverged;
             if (recentlyConverged > 0) S->touch = 0; /* main_iter.c:597-599 */
+            if (primme->dynamicMethodSwitch > 0) {
+               /* main_iter.c:601-624 */
+               if (S->cost.resid_0 == -1.0) S->cost.resid_0 = S->blockNorms[0];
+               if (recentlyConverged > 0 || primme->dynamicMethodSwitch == 2) {
+                  S->cost.MV = primme->stats.timeMatvec / (double)PB_MAX(primme->stats.numMatvecs, 1);
+                  if (pb_dyn_update_statistics(&S->cost, primme, S->tstart, recentlyConverged, 0, numConverged,
+                            S->blockNorms[0])) {
+                     if (primme->dynamicMethodSwitch == 3)
+                        CHK(pb_dyn_switch_from_gdpk(S, &S->cost));
+                     else if (primme->dynamicMethodSwitch == 2 || primme->dynamicMethodSwitch == 4)
+                        CHK(pb_dyn_switch_from_jdqmr(S, &S->cost));
+                  }
+               }
+            }
 
             CHK(pb_monitor(S, S->hVals, basisSize, flags, iev, blockSize, S->basisNorms,
                   numConverged, evals, numLocked, S->lockedFlags, resNorms, -1, -1.0, NULL, 0.0,
@@ -637,7 +661,11 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
                break;
             }
 
-            if (blockSize > 0) CHK(solve_correction(S, evals, numLocked, basisSize, blockSize));
+            if (blockSize > 0) {
+               S->tstart = hl_wtime(); /* the model accumulates the time spent in the correction */
+               CHK(solve_correction(S, evals, numLocked, basisSize, blockSize));
+               if (primme->dynamicMethodSwitch > 0) S->cost.time_in_inner += hl_wtime() - S->tstart;
+            }
 
             /* with locking, GD and no preconditioner the practical convergence of the block is
              * judged after orthogonalisation from V_locked' r (main_iter.c:674-797) */
@@ -831,6 +859,13 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
 
          primme->stats.numRestarts++;
          primme->initSize = numConverged;
+         /* with few eigenvalues GD+k is evaluated against JDQMR after every restart (main_iter.c:1181-1187) */
+         if (primme->dynamicMethodSwitch == 1) {
+            S->tstart = hl_wtime();
+            S->cost.MV = primme->stats.timeMatvec / (double)PB_MAX(primme->stats.numMatvecs, 1);
+            pb_dyn_update_statistics(&S->cost, primme, S->tstart, 0, 1, numConverged, S->blockNorms[0]);
+            CHK(pb_dyn_switch_from_gdpk(S, &S->cost));
+         }
          for (i = 0; i < maxBasis; i++) map[i] = i;
       } /* restart loop */
 
@@ -838,6 +873,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
 
       if (primme->locking) {
          CHK(copy_back_candidates(S, basisSize, evals, resNorms, targetShiftIndex, numConverged, numRet));
+         pb_dyn_recommend(primme, &S->cost);
          primme->stats.lockingIssue = LockingProblem;
          *ret = (numConverged == primme->numEvals || wholeSpace) ? 0 : PRIMME_MAIN_ITER_FAILURE;
          goto clean;
@@ -859,6 +895,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
                primme->numEvals, 8));
          *numRet = primme->numEvals;
          primme->initSize = numConverged;
+         pb_dyn_recommend(primme, &S->cost);
          *ret = numConverged >= primme->numEvals ? 0 : PRIMME_MAIN_ITER_FAILURE;
          goto clean;
       }
@@ -882,3 +919,4 @@ clean:
          primme->initSize);
    return rc;
 }
+#undef gdNoPrecLocking

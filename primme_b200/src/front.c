@@ -350,12 +350,6 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
       primme->procID = 0;
    }
    primme_set_defaults(primme);
-   int dynamic = primme->dynamicMethodSwitch > 0;
-   if (dynamic) {
-      /* The reference's dynamic mode starts as GD+k and may switch to JDQMR from run-time
-       * timings (main_iter.c:427-437); this build always stays on the GD+k side. */
-      primme->correctionParams.maxInnerIterations = 0;
-   }
    if (primme->orth == primme_orth_default)
       primme->orth = primme->maxBlockSize > 1 ? primme_orth_explicit_I : primme_orth_implicit_I;
    /* free to choose (reference primme_c.c:325-332 takes nLocal): round up to 16 elements so every
@@ -486,7 +480,6 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
    } else {
       primme->initSize = 0;
    }
-   if (dynamic) primme->dynamicMethodSwitch = -1; /* recommendation: GD+k (main_iter.c:1195) */
    pb200_ctx_sync(S->dev);
    pb_registry_set_solver(primme, NULL);
    primme->stats.elapsedTime = hl_wtime() - S->t0;

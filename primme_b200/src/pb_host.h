@@ -18,6 +18,18 @@ enum { UNCONVERGED = 0, SKIP_UNTIL_RESTART = 1, CONVERGED = 2, PRACTICALLY_CONVE
 void primme_set_defaults(primme_params *primme);
 void primme_display_params_prefix(const char *prefix, primme_params primme);
 
+/* run-time cost model of PRIMME_DYNAMIC (reference main_iter_private.h:60-110) */
+typedef struct pb_cost_model {
+   double MV_PR, MV, PR, qmr_only, qmr_plus_MV_PR, gdk_plus_MV_PR, gdk_plus_MV, project_locked, reortho_locked;
+   double gdk_conv_rate, jdq_conv_rate, JDQMR_slowdown, ratio_MV_outer;
+   int nextReset;
+   double gdk_sum_logResReductions, jdq_sum_logResReductions, gdk_sum_MV, jdq_sum_MV;
+   int nevals_by_gdk, nevals_by_jdq;
+   PRIMME_INT numIt_0, numMV_0;
+   double timer_0, time_in_inner, resid_0;
+   double accum_jdq_gdk, accum_jdq, accum_gdk;
+} pb_cost_model;
+
 /* Solver state shared by the pieces of the outer iteration. */
 typedef struct pb_solver {
    primme_params *primme;
@@ -52,6 +64,8 @@ typedef struct pb_solver {
    /* inner QMR solver (JDQMR family): g, d, delta, w, sol -- 5 x ld x maxBlockSize, device */
    double *jd_work;
    int touch; /* stopping-criterion state of the inner solver (main_iter.c:206,597-599) */
+   pb_cost_model cost; /* PRIMME_DYNAMIC */
+   double tstart;      /* start of the last correction / restart evaluation (main_iter.c:260,655,1182) */
 } pb_solver;
 
 /* error propagation in the style of the reference's CHKERR (common.h:484-494) */
@@ -106,6 +120,15 @@ int pb_ortho_single_iteration(pb_solver *S, const double *Q, int nQ, int64_t ldQ
       double *norms);
 int pb_ortho_local(double *V, int ldV, double *R, int b1, int b2, double *locked, int ldLocked,
       int numLocked, int n, const double *B, int ldB, long long *iseed);
+
+/* dav_dynamic.c */
+void pb_dyn_init(pb_cost_model *m, primme_params *primme);
+int pb_dyn_update_statistics(pb_cost_model *m, primme_params *primme, double current_time, int recentConv,
+      int calledAtRestart, int numConverged, double currentResNorm);
+struct pb_solver;
+int pb_dyn_switch_from_jdqmr(pb_solver *S, pb_cost_model *m);
+int pb_dyn_switch_from_gdpk(pb_solver *S, pb_cost_model *m);
+void pb_dyn_recommend(primme_params *primme, const pb_cost_model *m);
 
 /* dav_jdqmr.c */
 int pb_inner_solve(pb_solver *S, int blockSize, double *x, int64_t ldx, double *r, int64_t ldr, const double *rnorm,

@@ -29,16 +29,26 @@ def test_fixture_is_current(name):
         g["numOuterIterations"], g["numRestarts"], g["numMatvecs"])
 
 
-def test_dynamic_method_runs_as_gdk():
-    """PRIMME_DYNAMIC: the reference switches GD+k <-> JDQMR from wall-clock timings
-    (main_iter.c:427-437), so only eigenvalues/residuals are a parity criterion"""
+def test_dynamic_method():
+    """PRIMME_DYNAMIC: GD+k <-> JDQMR chosen at run time from wall-clock timings by the reference's
+    cost model (main_iter.c:427-437,601-624,1181-1187,1943-2440; dav_dynamic.c), so only
+    eigenvalues / residuals are a parity criterion, plus the recommendation left in
+    dynamicMethodSwitch (-1 GD+k, -2 JDQMR_ETol, -3 dynamic)"""
     from primme_b200 import api, matrices as M
     csr = M.laplacian_1d(100)
     r = H.solve("hostcheck", csr, 10, method=api.PRIMME_DYNAMIC, eps=1e-9, jacobi=True)
     SC.check_invariants(csr, r, 1e-9, 0.0)
     exact = 2 - 2 * np.cos(np.pi * np.arange(1, 11) / 101)
     assert np.allclose(r["evals"], exact, rtol=1e-10)
-    assert r["params"].dynamicMethodSwitch == -1
+    assert r["params"].dynamicMethodSwitch in (-1, -2, -3)
+    # a problem large enough for restarts: both methods get measured, the eigenvalues equal the
+    # reference's (non-degenerate spectrum)
+    csr = M.laplacian_nd((12, 11, 10))
+    ref = H.solve("reference", csr, 6, method=api.PRIMME_DYNAMIC, eps=1e-9, jacobi=True)
+    got = H.solve("hostcheck", csr, 6, method=api.PRIMME_DYNAMIC, eps=1e-9, jacobi=True)
+    assert got["ret"] == 0 and np.allclose(got["evals"], ref["evals"], rtol=1e-9)
+    SC.check_invariants(csr, got, 1e-9, 0.0)
+    assert got["params"].dynamicMethodSwitch in (-1, -2, -3)
 
 
 def test_initial_guesses_and_constraints():

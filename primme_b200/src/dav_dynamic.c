@@ -32,6 +32,9 @@ void pb_dyn_init(pb_cost_model *m, primme_params *primme) {
    m->accum_jdq_gdk = 1.0;
 }
 
+/* first sample, then the mean of the previous estimate and the new sample */
+static double blend(double estimate, double sample) { return estimate == 0.0 ? sample : (estimate + sample) / 2.0; }
+
 static double ratio_jdqmr_gdpk(const pb_cost_model *m, int numLocked, double slowdown, double ratio_MV_outer) {
    return slowdown *
           (m->qmr_plus_MV_PR + m->project_locked * numLocked +
@@ -79,7 +82,7 @@ int pb_dyn_update_statistics(pb_cost_model *m, primme_params *primme, double cur
    } else
       low_res = currentResNorm;
 
-   m->gdk_plus_MV = m->gdk_plus_MV == 0.0 ? time_in_outer / kout : (m->gdk_plus_MV + time_in_outer / kout) / 2.0;
+   m->gdk_plus_MV = blend(m->gdk_plus_MV, time_in_outer / kout);
 
    /* the averaging window of the convergence rates restarts every 10 converged pairs (:2239-2258) */
    if (numConverged / 10 >= m->nextReset) {
@@ -95,7 +98,7 @@ int pb_dyn_update_statistics(pb_cost_model *m, primme_params *primme, double cur
    switch (primme->dynamicMethodSwitch) {
    case 1:
    case 3: /* GD+k is running */
-      m->PR = m->PR == 0.0 ? m->time_in_inner / kout : (m->PR + m->time_in_inner / kout) / 2.0;
+      m->PR = blend(m->PR, m->time_in_inner / kout);
       m->gdk_plus_MV_PR = m->gdk_plus_MV + m->PR;
       m->MV_PR = m->MV + m->PR;
       if (low_res <= m->resid_0) m->gdk_sum_logResReductions += log(low_res / m->resid_0);
@@ -135,66 +138,63 @@ static int average_over_ranks(pb_solver *S, double *ratio) {
    return 0;
 }
 
-int pb_dyn_switch_from_jdqmr(pb_solver *S, pb_cost_model *m) {
-   primme_params *primme = S->primme;
-   int switchto = 0;
-   double ratio;
-   if (primme->dynamicMethodSwitch == 2) {
-      /* few eigenvalues: with the first timings, decide whether JDQMR can ever pay off (:1955-1973) */
-      ratio = ratio_jdqmr_gdpk(m, 0, 1.1, 1000);
-      CHK(average_over_ranks(S, &ratio));
-      if (ratio > 1.05) {
-         primme->dynamicMethodSwitch = -1;
-         primme->correctionParams.maxInnerIterations = 0;
-         primme->correctionParams.projectors.RightX = 1;
-         return 0;
-      }
-   }
-   switch (primme->dynamicMethodSwitch) {
-   case 2: switchto = 1; break;
-   case 4: switchto = 3; break;
-   }
-   ratio = ratio_jdqmr_gdpk(m, 0, m->JDQMR_slowdown, m->ratio_MV_outer);
-   CHK(average_over_ranks(S, &ratio));
-   if (ratio > 1.05) {
-      primme->dynamicMethodSwitch = switchto;
-      primme->correctionParams.maxInnerIterations = 0;
-      primme->correctionParams.projectors.RightX = 1;
-   }
+/* book-keeping shared by both directions: expected accumulated times for the final recommendation */
+static void account(pb_cost_model *m, double ratio) {
    m->accum_jdq += m->gdk_plus_MV_PR * ratio;
    m->accum_gdk += m->gdk_plus_MV_PR;
    m->accum_jdq_gdk = m->accum_jdq / m->accum_gdk;
+}
+
+static void run_gdpk(primme_params *primme, int state) {
+   primme->dynamicMethodSwitch = state;
+   primme->correctionParams.maxInnerIterations = 0;
+   primme->correctionParams.projectors.RightX = 1;
+}
+
+static void run_jdqmr(primme_params *primme, int state) {
+   primme->dynamicMethodSwitch = state;
+   primme->correctionParams.maxInnerIterations = -1;
+   primme->correctionParams.projectors.RightX = 0;
+}
+
+/* states: 1 GD+k (few eigenvalues, evaluated at restarts), 2 its JDQMR counterpart (evaluated every
+ * iteration), 3 GD+k for many eigenvalues (evaluated when a pair converges), 4 its JDQMR counterpart */
+int pb_dyn_switch_from_jdqmr(pb_solver *S, pb_cost_model *m) {
+   primme_params *primme = S->primme;
+   double ratio;
+   if (primme->dynamicMethodSwitch == 2) {
+      /* few eigenvalues: with the first timings, decide whether JDQMR can ever pay off, assuming its
+       * best case -- slowdown 1.1, all the time in inner iterations (:1955-1973) */
+      ratio = ratio_jdqmr_gdpk(m, 0, 1.1, 1000);
+      CHK(average_over_ranks(S, &ratio));
+      if (ratio > 1.05) {
+         run_gdpk(primme, -1); /* GD+k for good: no further model updates */
+         return 0;
+      }
+   }
+   const int back_to = primme->dynamicMethodSwitch == 2 ? 1 : primme->dynamicMethodSwitch == 4 ? 3 : 0;
+   ratio = ratio_jdqmr_gdpk(m, 0, m->JDQMR_slowdown, m->ratio_MV_outer);
+   CHK(average_over_ranks(S, &ratio));
+   if (ratio > 1.05) run_gdpk(primme, back_to);
+   account(m, ratio);
    return 0;
 }
 
 int pb_dyn_switch_from_gdpk(pb_solver *S, pb_cost_model *m) {
    primme_params *primme = S->primme;
-   int switchto = 0;
-   double ratio;
    /* timings without a restart are incomplete; a basis that saturates the space stays on GD (:2058-2065) */
    if (primme->stats.numRestarts == 0 ||
          primme->maxBasisSize + (primme->locking ? primme->numEvals : 0) >= primme->n)
       return 0;
-   switch (primme->dynamicMethodSwitch) {
-   case 1: switchto = 2; break;
-   case 3: switchto = 4; break;
-   }
+   const int forward_to = primme->dynamicMethodSwitch == 1 ? 2 : primme->dynamicMethodSwitch == 3 ? 4 : 0;
    if (m->qmr_only == 0.0) { /* JDQMR never ran: take first measurements */
-      primme->dynamicMethodSwitch = switchto;
-      primme->correctionParams.maxInnerIterations = -1;
-      primme->correctionParams.projectors.RightX = 0;
+      run_jdqmr(primme, forward_to);
       return 0;
    }
-   ratio = ratio_jdqmr_gdpk(m, 0, m->JDQMR_slowdown, m->ratio_MV_outer);
+   double ratio = ratio_jdqmr_gdpk(m, 0, m->JDQMR_slowdown, m->ratio_MV_outer);
    CHK(average_over_ranks(S, &ratio));
-   if (ratio < 0.95) {
-      primme->dynamicMethodSwitch = switchto;
-      primme->correctionParams.maxInnerIterations = -1;
-      primme->correctionParams.projectors.RightX = 0;
-   }
-   m->accum_jdq += m->gdk_plus_MV_PR * ratio;
-   m->accum_gdk += m->gdk_plus_MV_PR;
-   m->accum_jdq_gdk = m->accum_jdq / m->accum_gdk;
+   if (ratio < 0.95) run_jdqmr(primme, forward_to);
+   account(m, ratio);
    return 0;
 }
 

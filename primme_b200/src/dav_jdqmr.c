@@ -238,7 +238,7 @@ int pb_inner_solve(pb_solver *S, int blockSize, double *x, int64_t ldx, double *
                continue;
             }
             const double tol = PB_MIN(tau[pi] / LTolerance_factor, eres_updated[pi] / ETolerance_factor);
-            CHK(pb_conv_test(S, eval_updated, tol, &isConv));
+            CHK(pb_conv_test(S, eval_updated, NULL, tol, &isConv));
             if (numIts > 0 && isConv) {
                (*touch)++;
                perm_set_value_on_pos(p0, i, blockSize - ++conv, blockSize);
@@ -253,7 +253,7 @@ int pb_inner_solve(pb_solver *S, int blockSize, double *x, int64_t ldx, double *
             }
          } else {
             /* the QMR residual can be sqrt(iterations) away from the true one (:574-580) */
-            CHK(pb_conv_test(S, eval[pi], tau[pi] / LTolerance_factor * sqrt((double)numIts), &isConv));
+            CHK(pb_conv_test(S, eval[pi], NULL, tau[pi] / LTolerance_factor * sqrt((double)numIts), &isConv));
             if (numIts > 0 && isConv) {
                perm_set_value_on_pos(p0, i, blockSize - ++conv, blockSize);
                continue;

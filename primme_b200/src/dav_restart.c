@@ -65,7 +65,6 @@ int pb_check_convergence(pb_solver *S, double *X, int64_t ldX, int givenX, doubl
       int64_t ldR, int givenR, int numLocked, int left, int right, int *flags,
       double *blockNorms, double *hVals, int *reset, int practConvCheck) {
    primme_params *primme = S->primme;
-   (void)X, (void)ldX, (void)givenX;
    if (right <= left) return 0;
    int *toProject = (int *)malloc(sizeof(int) * (right - left));
    int numToProject = 0;
@@ -88,7 +87,7 @@ int pb_check_convergence(pb_solver *S, double *X, int64_t ldX, int givenX, doubl
          continue;
       }
       int isConv = 0;
-      int rc = pb_conv_test(S, hVals[i], rn, &isConv);
+      int rc = pb_conv_test(S, hVals[i], (X && givenX) ? X + (size_t)ldX * (i - left) : NULL, rn, &isConv);
       if (rc) {
          free(toProject);
          return rc;

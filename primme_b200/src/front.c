@@ -135,10 +135,25 @@ int pb_bcast_int(pb_solver *S, int *buf, int count) {
    return rc;
 }
 
-int pb_conv_test(pb_solver *S, double eval, double rnorm, int *isconv) {
+static void conv_test_absolute(double *eval, void *evec, double *rNorm, int *isConv,
+      primme_params *primme, int *ierr);
+
+/* convTestFun_ (auxiliary_eigs_normal.c:408-443): the vector, when the caller has it, is handed to
+ * the callback in the memory space of its contract -- as is for cublas_dprimme, through a host copy
+ * for dprimme (skipped for the built-in test, which ignores it) */
+int pb_conv_test(pb_solver *S, double eval, const double *evec, double rnorm, int *isconv) {
    primme_params *primme = S->primme;
    int ierr = 0;
-   primme->convTestFun(&eval, NULL, &rnorm, isconv, primme, &ierr);
+   void *v = (void *)evec;
+   if (evec && !S->device_callbacks) {
+      v = NULL;
+      if (primme->convTestFun != conv_test_absolute) {
+         CHK(host_block(S, 1));
+         CHK(pb200_copy_d2h(S->dev, evec, S->n, S->hstage, S->n, S->n, 1, 8));
+         v = S->hstage;
+      }
+   }
+   primme->convTestFun(&eval, v, &rnorm, isconv, primme, &ierr);
    if (ierr) {
       pb_report(primme, __FILE__, __LINE__, ierr, "convTestFun");
       return PRIMME_UNEXPECTED_FAILURE;

@@ -87,7 +87,7 @@ int pb_apply_precond(pb_solver *S, double *X, int64_t ldx, double *Y, int64_t ld
 int pb_global_sum(pb_solver *S, double *buf, int count);
 int pb_bcast(pb_solver *S, double *buf, int count);
 int pb_bcast_int(pb_solver *S, int *buf, int count);
-int pb_conv_test(pb_solver *S, double eval, double rnorm, int *isconv);
+int pb_conv_test(pb_solver *S, double eval, const double *evec, double rnorm, int *isconv);
 int pb_monitor(pb_solver *S, double *basisEvals, int basisSize, int *basisFlags, int *iblock,
       int blockSize, double *basisNorms, int numConverged, double *lockedEvals, int numLocked,
       int *lockedFlags, double *lockedNorms, int inner_its, double LSRes, const char *msg,

@@ -1,26 +1,37 @@
-/* svds.c -- singular value front end, normal-equations path.
+/* svds.c -- singular value front end.
  *
- * dprimme_svds / cublas_dprimme_svds with primme_svds_normalequations: the singular triplets of A
- * (m x n) are the eigenpairs of A'A (n <= m) or AA' (n > m); the eigenproblem runs through the
- * same Davidson hot path as dprimme with a matvec that applies the user's operator twice.
- * Restates, for one stage and fp64:
+ * dprimme_svds / cublas_dprimme_svds: the singular triplets of A (m x n) through eigenproblems run by
+ * the same Davidson hot path as dprimme --
+ *    primme_svds_normalequations   A'A (n <= m) or AA', the matvec applies the user's operator twice;
+ *    primme_svds_augmented         [0 A'; A 0] on vectors [v; u];
+ *    primme_svds_hybrid (default)  normal equations first, then the augmented operator started from the
+ *                                  first stage's triplets, the ones that already pass the test kept as
+ *                                  orthogonality constraints.
+ * Restates, for fp64:
  *    primme_svds_initialize / set_method / set_defaults   src/svds/primme_svds_interface.c:107-420
- *    wrapper_svds                                         src/svds/primme_svds_c.c:388-540
- *    copy_last_params_from_svds / _to_svds                :551-1000
- *    matrixMatvec_eigs (A'A, AA')                         :1323-1383
- *    convTestFunATA / default_convTestFun                 :1594-1690
- * Out of scope here (refused with PRIMME_FUNCTION_UNAVAILABLE = -44, like a reference build
- * without the feature): the augmented operator and therefore primme_svds_hybrid / the second
- * stage (needs refined extraction and JDQMR), primme_svds_closest_abs, preconditioning, every
- * precision but double.
+ *    wrapper_svds (both stages)                           src/svds/primme_svds_c.c:388-540
+ *    copy_last_params_from_svds / _to_svds                :551-1030
+ *    matrixMatvec_eigs, applyPreconditioner_eigs          :1323-1417
+ *    compute_resNorm, default_convTestFun, convTestFunATA, convTestFunAug   :1512-1745
+ * Refused with PRIMME_FUNCTION_UNAVAILABLE = -44 like a reference build without the feature: every
+ * precision but double, numProcs > 1; and by the eigensolver underneath (front.c:check_scope) what it
+ * does not cover -- refined extraction, which the augmented operator selects for smallest /
+ * closest_abs targets (primme_svds_interface.c:385-391).
  */
 #include "pb_host.h"
 #include "../../include/primme_svds.h"
+#include <float.h>
 #include <limits.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+
+#define CHK_RC(call)            \
+   do {                         \
+      int chk_rc_ = (call);     \
+      if (chk_rc_) return chk_rc_; \
+   } while (0)
 
 /* ------------------------------------------------------------------ parameter interface ---- */
 primme_svds_params *primme_svds_params_create(void) {
@@ -346,6 +357,7 @@ int primme_svds_enum_member_info(primme_svds_params_label label, int *value, con
 typedef struct svds_run {
    primme_svds_params *svds;
    int device_mode; /* callbacks and svecs live in device memory (cublas_dprimme_svds) */
+   pb200_ctx *ctx;  /* kernel context of the call (device mode) */
    double *aux;     /* m x maxBlockSize (A'A) or n x maxBlockSize (AA') intermediate block */
    int64_t aux_rows;
    int aux_cols;
@@ -359,6 +371,10 @@ static svds_run *find_run(const primme_svds_params *s) {
    return NULL;
 }
 
+static primme_svds_operator stage_method(const primme_svds_params *s, const primme_params *primme) {
+   return &s->primme == primme ? s->method : s->methodStage2;
+}
+
 static int call_svds_matvec(primme_svds_params *s, double *x, PRIMME_INT ldx, double *y, PRIMME_INT ldy,
       int bs, int trans) {
    int ierr = 0;
@@ -366,29 +382,117 @@ static int call_svds_matvec(primme_svds_params *s, double *x, PRIMME_INT ldx, do
    return ierr;
 }
 
-/* y = A'(A x) or A(A' x) in blocks of maxBlockSize columns (primme_svds_c.c:1337-1371) */
-static void matvec_normal_equations(void *x_, PRIMME_INT *ldx, void *y_, PRIMME_INT *ldy, int *blockSize,
+/* the operator applied outside the eigensolver: counted in the SVD statistics (matrixMatvecSVDS,
+ * primme_svds_c.c:1118-1171) */
+static int counted_svds_matvec(primme_svds_params *s, double *x, PRIMME_INT ldx, double *y, PRIMME_INT ldy,
+      int bs, int trans) {
+   if (bs <= 0) return 0;
+   const double t0 = hl_wtime();
+   if (call_svds_matvec(s, x, ldx, y, ldy, bs, trans)) return PRIMME_USER_FAILURE;
+   s->stats.timeMatvec += hl_wtime() - t0;
+   s->stats.numMatvecs += bs;
+   return 0;
+}
+
+/* ---- n-long helpers on the singular vectors: host loops (dprimme_svds) or kernels of the C-ABI
+ * (cublas_dprimme_svds) ---- */
+static int vec_alloc(svds_run *run, size_t elems, double **p) {
+   const size_t bytes = sizeof(double) * PB_MAX(elems, (size_t)1);
+   if (run->device_mode) return pb200_malloc(run->ctx, bytes, (void **)p) ? PRIMME_MALLOC_FAILURE : 0;
+   *p = (double *)malloc(bytes);
+   return *p ? 0 : PRIMME_MALLOC_FAILURE;
+}
+
+static void vec_free(svds_run *run, double *p) {
+   if (!p) return;
+   if (run->device_mode) pb200_free(run->ctx, p);
+   else free(p);
+}
+
+static int vec_copy(svds_run *run, const double *src, int64_t lds, double *dst, int64_t ldd, int64_t rows, int cols) {
+   if (rows <= 0 || cols <= 0 || src == dst) return 0;
+   if (run->device_mode) return pb200_copy_d2d(run->ctx, src, lds, dst, ldd, rows, cols, 8);
+   /* columns may overlap when packing to the left: move column by column in increasing order */
+   for (int j = 0; j < cols; j++) memmove(dst + (size_t)ldd * j, src + (size_t)lds * j, sizeof(double) * rows);
+   return 0;
+}
+
+/* X(:,j) *= alpha[j] */
+static int vec_scale(svds_run *run, double *X, int64_t ldx, int64_t rows, int cols, const double *alpha) {
+   if (rows <= 0 || cols <= 0) return 0;
+   if (run->device_mode) {
+      for (int j = 0; j < cols; j += 8)
+         if (pb200_dscale_columns(run->ctx, rows, alpha + j, X + (size_t)ldx * j, ldx, PB_MIN(8, cols - j)))
+            return PRIMME_UNEXPECTED_FAILURE;
+      return 0;
+   }
+   for (int j = 0; j < cols; j++)
+      for (int64_t r = 0; r < rows; r++) X[r + (size_t)ldx * j] *= alpha[j];
+   return 0;
+}
+
+/* out[j] = X(:,j)' Y(:,j) */
+static int vec_dots(svds_run *run, const double *X, int64_t ldx, const double *Y, int64_t ldy, int64_t rows, int cols,
+      double *out) {
+   if (run->device_mode) {
+      for (int j = 0; j < cols; j += 8)
+         if (pb200_dcolumn_dots(run->ctx, rows, X + (size_t)ldx * j, ldx, Y + (size_t)ldy * j, ldy, PB_MIN(8, cols - j),
+                   out + j))
+            return PRIMME_UNEXPECTED_FAILURE;
+      return 0;
+   }
+   for (int j = 0; j < cols; j++) out[j] = hl_dot((int)rows, X + (size_t)ldx * j, Y + (size_t)ldy * j);
+   return 0;
+}
+
+/* y += alpha x (one column) */
+static int vec_axpy(svds_run *run, int64_t rows, double alpha, const double *x, double *y) {
+   if (rows <= 0) return 0;
+   if (run->device_mode) return pb200_daxpy_columns(run->ctx, rows, &alpha, x, rows, y, rows, 1) ? PRIMME_UNEXPECTED_FAILURE : 0;
+   for (int64_t r = 0; r < rows; r++) y[r] += alpha * x[r];
+   return 0;
+}
+
+/* uniform(-1,1) column from the eigensolver's evolving seed (Num_larnv, always generated on the host) */
+static int vec_random(svds_run *run, primme_params *primme, int64_t rows, double *x) {
+   long long seed[4];
+   for (int i = 0; i < 4; i++) seed[i] = primme->iseed[i];
+   int rc = 0;
+   if (run->device_mode) {
+      double *h = (double *)malloc(sizeof(double) * PB_MAX(rows, 1));
+      if (!h) return PRIMME_MALLOC_FAILURE;
+      hl_larnv2(seed, rows, h);
+      rc = pb200_copy_h2d(run->ctx, h, PB_MAX(rows, 1), x, PB_MAX(rows, 1), rows, 1, 8) ? PRIMME_UNEXPECTED_FAILURE : 0;
+      if (!rc) pb200_ctx_sync(run->ctx);
+      free(h);
+   } else
+      hl_larnv2(seed, rows, x);
+   for (int i = 0; i < 4; i++) primme->iseed[i] = seed[i];
+   return rc;
+}
+
+/* y = A'(A x), A(A' x) in blocks of maxBlockSize columns, or [0 A'; A 0] x (primme_svds_c.c:1323-1383) */
+static void matvec_eigs(void *x_, PRIMME_INT *ldx, void *y_, PRIMME_INT *ldy, int *blockSize,
       primme_params *primme, int *ierr) {
    primme_svds_params *s = (primme_svds_params *)primme->matrix;
    svds_run *run = find_run(s);
    double *x = (double *)x_, *y = (double *)y_;
    *ierr = 1;
    if (!run) return;
-   const int ata = s->method == primme_svds_op_AtA;
+   const primme_svds_operator method = stage_method(s, primme);
+   if (method == primme_svds_op_augmented) {
+      int e = call_svds_matvec(s, x + s->nLocal, *ldx, y, *ldy, *blockSize, 1);
+      if (!e) e = call_svds_matvec(s, x, *ldx, y + s->nLocal, *ldy, *blockSize, 0);
+      *ierr = e;
+      return;
+   }
+   const int ata = method == primme_svds_op_AtA;
    const PRIMME_INT rows = ata ? s->mLocal : s->nLocal;
    const int cap = PB_MAX(1, PB_MIN(primme->maxBlockSize, *blockSize));
    if (!run->aux || run->aux_cols < cap || run->aux_rows < rows) {
-      pb200_ctx *ctx = primme_b200_solver_ctx(primme);
-      if (run->aux) {
-         if (run->device_mode) pb200_free(ctx, run->aux);
-         else free(run->aux);
-         run->aux = NULL;
-      }
-      const size_t bytes = sizeof(double) * (size_t)PB_MAX(rows, 1) * cap;
-      if (run->device_mode) {
-         if (!ctx || pb200_malloc(ctx, bytes, (void **)&run->aux)) return;
-      } else if (!(run->aux = (double *)malloc(bytes)))
-         return;
+      vec_free(run, run->aux);
+      run->aux = NULL;
+      if (vec_alloc(run, (size_t)PB_MAX(rows, 1) * cap, &run->aux)) return;
       run->aux_cols = cap, run->aux_rows = rows;
    }
    for (int i = 0; i < *blockSize; i += cap) {
@@ -403,11 +507,73 @@ static void matvec_normal_equations(void *x_, PRIMME_INT *ldx, void *y_, PRIMME_
    *ierr = 0;
 }
 
-/* primme_svds_c.c:1594-1620 (the augmented re-check does not apply to the normal equations) */
+/* the user's preconditioner told which operator it is approximating (primme_svds_c.c:1404-1417) */
+static void precond_eigs(void *x, PRIMME_INT *ldx, void *y, PRIMME_INT *ldy, int *blockSize, primme_params *primme,
+      int *ierr) {
+   primme_svds_params *s = (primme_svds_params *)primme->preconditioner;
+   int method = (int)stage_method(s, primme);
+   s->applyPreconditioner(x, ldx, y, ldy, blockSize, &method, s, ierr);
+}
+
+/* primme_svds_c.c:1200-1252 */
+static int conv_test_svds(primme_svds_params *s, double sval, double *left, double *right, double rNorm, int method,
+      int *isConv) {
+   int ierr = 0;
+   s->convTestFun(&sval, left, right, &rNorm, &method, isConv, s, &ierr);
+   return ierr ? -1 : 0;
+}
+
+/* residual norm of the triplet (u, v): sqrt(|A v/|v| - s u/|u||^2 + |A' u/|u| - s v/|v||^2) with
+ * s = u'Av / (|u| |v|)   (primme_svds_c.c:1512-1572) */
+static int compute_res_norm(svds_run *run, double *left, double *right, double *rNorm) {
+   primme_svds_params *s = run->svds;
+   const PRIMME_INT mL = s->mLocal, nL = s->nLocal;
+   double *Atu = NULL;
+   int rc = vec_alloc(run, (size_t)(mL + nL), &Atu);
+   if (rc) return rc;
+   double *Av = Atu + nL;
+   double ip[3];
+   rc = counted_svds_matvec(s, left, mL, Atu, nL, 1, 1);
+   if (!rc) rc = counted_svds_matvec(s, right, nL, Av, mL, 1, 0);
+   if (!rc) rc = vec_dots(run, right, nL, right, nL, nL, 1, &ip[0]);
+   if (!rc) rc = vec_dots(run, left, mL, left, mL, mL, 1, &ip[1]);
+   if (!rc) rc = vec_dots(run, left, mL, Av, mL, mL, 1, &ip[2]);
+   if (!rc) {
+      ip[0] = sqrt(ip[0]), ip[1] = sqrt(ip[1]);
+      const double sval = ip[2] / ip[0] / ip[1];
+      if (sval < -0.0) {
+         *rNorm = DBL_MAX; /* u'Av negative: not a triplet */
+      } else {
+         double a = 1.0 / ip[1], b = 1.0 / ip[0], nrm2 = 0.0;
+         rc = vec_scale(run, Atu, nL, nL, 1, &a);
+         if (!rc) rc = vec_axpy(run, nL, -sval / ip[0], right, Atu);
+         if (!rc) rc = vec_scale(run, Av, mL, mL, 1, &b);
+         if (!rc) rc = vec_axpy(run, mL, -sval / ip[1], left, Av);
+         if (!rc) rc = vec_dots(run, Atu, mL + nL, Atu, mL + nL, mL + nL, 1, &nrm2);
+         *rNorm = sqrt(nrm2);
+      }
+   }
+   if (run->device_mode) pb200_ctx_sync(run->ctx);
+   vec_free(run, Atu);
+   return rc;
+}
+
+/* primme_svds_c.c:1594-1620: with the augmented operator the eigensolver's residual is only an
+ * estimate of the triplet's, so a pair that passes is re-checked with the actual residual */
 static void default_conv_test_svds(double *sval, void *leftsvec, void *rightsvec, double *rNorm, int *method,
       int *isConv, primme_svds_params *s, int *ierr) {
-   (void)sval, (void)leftsvec, (void)rightsvec, (void)method;
-   *isConv = *rNorm < PB_MAX(s->eps, PB_EPS * 3.16) * s->aNorm;
+   (void)sval;
+   const double aNorm = s->aNorm;
+   *isConv = *rNorm < PB_MAX(s->eps, PB_EPS * 3.16) * aNorm;
+   if (*isConv && *method == primme_svds_op_augmented && leftsvec && rightsvec) {
+      svds_run *run = find_run(s);
+      double rn = 0.0;
+      if (!run || compute_res_norm(run, (double *)leftsvec, (double *)rightsvec, &rn)) {
+         *ierr = 1;
+         return;
+      }
+      *isConv = rn < PB_MAX(s->eps, PB_EPS * 3.16) * aNorm;
+   }
    *ierr = 0;
 }
 
@@ -415,6 +581,7 @@ static void default_conv_test_svds(double *sval, void *leftsvec, void *rightsvec
 static void conv_test_normal_equations(double *eval, void *evec, double *rNorm, int *isConv, primme_params *primme,
       int *ierr) {
    primme_svds_params *s = (primme_svds_params *)primme->matrix;
+   const primme_svds_operator method = stage_method(s, primme);
    const double aNorm = primme->aNorm > 0.0 ? primme->aNorm : primme->stats.estimateLargestSVal;
    const double maxaNorm = PB_MAX(primme->aNorm, primme->stats.estimateLargestSVal);
    if (rNorm && *rNorm < PB_EPS * maxaNorm * 3.16) {
@@ -425,9 +592,27 @@ static void conv_test_normal_equations(double *eval, void *evec, double *rNorm, 
    if (s->aNorm <= 0.0) s->aNorm = sqrt(aNorm);
    double sval = eval ? sqrt(fabs(*eval)) : 0.0;
    double srNorm = (rNorm && eval) ? *rNorm / sval : 0.0;
-   int method = (int)s->method;
-   const int aat = s->method == primme_svds_op_AAt;
-   s->convTestFun(&sval, aat ? evec : NULL, aat ? NULL : evec, &srNorm, &method, isConv, s, ierr);
+   const int aat = method == primme_svds_op_AAt;
+   *ierr = conv_test_svds(s, sval, aat ? (double *)evec : NULL, aat ? NULL : (double *)evec, srNorm, (int)method, isConv)
+                 ? 1
+                 : 0;
+   s->aNorm = oldaNorm;
+}
+
+/* convergence of an eigenpair [v; u] of the augmented operator (primme_svds_c.c:1710-1745); the
+ * machine-precision shortcut is deliberately absent: null-space pairs must never pass */
+static void conv_test_augmented(double *eval, void *evec, double *rNorm, int *isConv, primme_params *primme,
+      int *ierr) {
+   primme_svds_params *s = (primme_svds_params *)primme->matrix;
+   const double aNorm = primme->aNorm > 0.0 ? primme->aNorm : primme->stats.estimateLargestSVal;
+   const double oldaNorm = s->aNorm;
+   if (s->aNorm <= 0.0) s->aNorm = aNorm;
+   double sval = eval ? fabs(*eval) : 0.0;
+   double srNorm = rNorm ? *rNorm * sqrt(2.0) : 0.0;
+   *ierr = conv_test_svds(s, sval, evec ? (double *)evec + s->nLocal : NULL, (double *)evec, srNorm,
+                 (int)primme_svds_op_augmented, isConv)
+                 ? 1
+                 : 0;
    s->aNorm = oldaNorm;
 }
 
@@ -457,14 +642,10 @@ static int svds_check_input(void *svals, void *svecs, void *resNorms, primme_svd
 
 static int svds_out_of_scope(primme_svds_params *s) {
    const char *why = NULL;
-   if (s->method == primme_svds_op_augmented || s->methodStage2 != primme_svds_op_none)
-      why = "the augmented operator / second stage (primme_svds_hybrid, primme_svds_augmented)";
-   else if (s->target == primme_svds_closest_abs)
-      why = "primme_svds_closest_abs (needs refined extraction)";
-   else if (s->applyPreconditioner || s->precondition > 0)
-      why = "preconditioning of the normal equations";
-   else if ((s->matrixMatvec_type != primme_op_default && s->matrixMatvec_type != primme_op_double) ||
-            (s->internalPrecision != primme_op_default && s->internalPrecision != primme_op_double))
+   if ((s->matrixMatvec_type != primme_op_default && s->matrixMatvec_type != primme_op_double) ||
+         (s->applyPreconditioner && s->applyPreconditioner_type != primme_op_default &&
+               s->applyPreconditioner_type != primme_op_double) ||
+         (s->internalPrecision != primme_op_default && s->internalPrecision != primme_op_double))
       why = "callbacks / internal precision other than double";
    else if (s->numProcs > 1)
       why = "the distributed SVD front end";
@@ -474,14 +655,245 @@ static int svds_out_of_scope(primme_svds_params *s) {
    return PRIMME_FUNCTION_UNAVAILABLE;
 }
 
-/* device or host copy / scale helpers for the post-processing of the vectors */
-static int vec_copy(pb200_ctx *ctx, int dev, const double *src, int64_t lds, double *dst, int64_t ldd, int64_t rows,
-      int cols) {
-   if (rows <= 0 || cols <= 0 || src == dst) return 0;
-   if (dev) return pb200_copy_d2d(ctx, src, lds, dst, ldd, rows, cols, 8);
-   /* columns may overlap when packing to the left: move column by column in increasing order */
-   for (int j = 0; j < cols; j++) memmove(dst + (size_t)ldd * j, src + (size_t)lds * j, sizeof(double) * rows);
+static int cmp_double(const void *a, const void *b) { return *(const double *)a <= *(const double *)b ? -1 : 1; }
+
+/* Prepare the eigensolver of one stage: callbacks, norms, vectors in the layout it works on, seeds,
+ * shifts (copy_last_params_from_svds, primme_svds_c.c:551-830).  *out_svecs is the evecs argument. */
+static int stage_begin(svds_run *run, int stage, double *svals, double *svecs, double *rnorms, int *allocatedShifts,
+      double **out_svecs) {
+   primme_svds_params *s = run->svds;
+   primme_params *primme = stage == 0 ? &s->primme : &s->primmeStage2;
+   const primme_svds_operator method = stage == 0 ? s->method : s->methodStage2;
+   const PRIMME_INT mL = s->mLocal, nL = s->nLocal;
+   *out_svecs = svecs;
+   *allocatedShifts = 0;
+   if (method == primme_svds_op_none) {
+      primme->maxMatvecs = 0;
+      return 0;
+   }
+   if (!primme->matrixMatvec) {
+      primme->matrixMatvec = matvec_eigs;
+      primme->matrixMatvec_type = primme_op_double;
+      primme->matrix = s;
+   }
+   if (s->applyPreconditioner && !primme->applyPreconditioner) {
+      primme->applyPreconditioner = precond_eigs;
+      primme->applyPreconditioner_type = primme_op_double;
+      primme->preconditioner = s;
+   }
+   if (s->aNorm > 0.0) primme->aNorm = method == primme_svds_op_augmented ? s->aNorm : s->aNorm * s->aNorm;
+   primme->convTestFun = method == primme_svds_op_augmented ? conv_test_augmented : conv_test_normal_equations;
+   primme->convTestFun_type = primme_op_double;
+
+   /* svecs = [Uc U0 Vc V0]: constraints and initial guesses, left then right */
+   primme->initSize = s->initSize;
+   primme->numOrthoConst = s->numOrthoConst;
+   const int n0 = s->initSize + s->numOrthoConst;
+   const int nMax = PB_MAX(s->initSize, s->numSvals) + s->numOrthoConst;
+   if (method != primme_svds_op_augmented) {
+      /* the right vectors [Vc V0] move to the rightmost position of svecs, where the eigensolver
+       * works in place; with AA' only Vc moves and the eigensolver works on the left block */
+      const int ata = method == primme_svds_op_AtA;
+      double *aux = svecs + (size_t)nMax * mL;
+      CHK_RC(vec_copy(run, svecs + (size_t)mL * n0, nL, aux, nL, nL, ata ? n0 : s->numOrthoConst));
+      if (ata) *out_svecs = aux;
+      primme->ldevecs = ata ? nL : mL;
+   } else {
+      /* shuffle to [V; U] columns of height nL + mL; constraints get norm 1 (each half has norm 1) */
+      const PRIMME_INT N = mL + nL;
+      if (n0 > 0) {
+         double *aux = NULL;
+         CHK_RC(vec_alloc(run, (size_t)N * n0, &aux));
+         int rc = vec_copy(run, svecs, N * n0, aux, N * n0, N * n0, 1);
+         if (!rc) rc = vec_copy(run, aux + (size_t)mL * n0, nL, svecs, N, nL, n0);
+         if (!rc) rc = vec_copy(run, aux, mL, svecs + nL, N, mL, n0);
+         if (run->device_mode) pb200_ctx_sync(run->ctx);
+         vec_free(run, aux);
+         CHK_RC(rc);
+      }
+      double *isq2 = (double *)malloc(sizeof(double) * PB_MAX(s->numOrthoConst, 1));
+      for (int i = 0; i < s->numOrthoConst; i++) isq2[i] = 1. / sqrt(2.);
+      int rc = vec_scale(run, svecs, N, N, s->numOrthoConst, isq2);
+      free(isq2);
+      CHK_RC(rc);
+      primme->ldevecs = N;
+   }
+   for (int i = 0; i < 4; i++) primme->iseed[i] = s->iseed[i];
+   primme->maxMatvecs = stage == 0 ? s->maxMatvecs / 2 : s->maxMatvecs / 2 - s->primme.stats.numMatvecs;
+
+   if ((stage == 0 && s->numTargetShifts > 0) ||
+         (stage == 1 && primme->targetShifts == NULL && s->target == primme_svds_closest_abs)) {
+      primme->numTargetShifts = s->numTargetShifts;
+      if (stage == 0 && method != primme_svds_op_augmented) {
+         *allocatedShifts = 1;
+         primme->targetShifts = (double *)malloc(sizeof(double) * PB_MAX(s->numSvals, s->numTargetShifts));
+         if (!primme->targetShifts) return PRIMME_MALLOC_FAILURE;
+         for (int i = 0; i < primme->numTargetShifts; i++) primme->targetShifts[i] = s->targetShifts[i] * s->targetShifts[i];
+      } else
+         primme->targetShifts = s->targetShifts;
+   } else if (stage == 1 && primme->targetShifts == NULL && s->target == primme_svds_smallest) {
+      /* closest_geq to lower bounds of the values found by the first stage: the |m - n| null
+       * eigenvalues of the augmented operator are not singular values (:700-735) */
+      *allocatedShifts = 1;
+      primme->targetShifts = (double *)malloc(sizeof(double) * s->numSvals);
+      if (!primme->targetShifts) return PRIMME_MALLOC_FAILURE;
+      const double min_val = s->aNorm * PB_EPS;
+      int i;
+      for (i = 0; i < s->initSize; i++)
+         primme->targetShifts[i] = PB_MAX(sqrt(fabs(PB_MAX(svals[i] - rnorms[i], 0.0) * svals[i])), min_val);
+      for (; i < s->numSvals; i++) primme->targetShifts[i] = min_val;
+      qsort(primme->targetShifts, s->numSvals, sizeof(double), cmp_double);
+      primme->numTargetShifts = s->numSvals;
+   } else if (method == primme_svds_op_augmented && s->target == primme_svds_smallest && primme->targetShifts == NULL) {
+      *allocatedShifts = 1;
+      primme->targetShifts = (double *)malloc(sizeof(double));
+      if (!primme->targetShifts) return PRIMME_MALLOC_FAILURE;
+      primme->targetShifts[0] = 0.0;
+      primme->numTargetShifts = 1;
+   }
+
+   /* no guess for the augmented operator: start from [A'x; x] or [x; Ax], x random (:752-790) */
+   if (method == primme_svds_op_augmented && primme->initSize <= 0) {
+      const PRIMME_INT N = mL + nL;
+      double *v0 = svecs + (size_t)primme->numOrthoConst * N, n2[2];
+      if (s->m >= s->n) {
+         CHK_RC(vec_random(run, primme, mL, v0 + nL));
+         CHK_RC(counted_svds_matvec(s, v0 + nL, mL, v0, nL, 1, 1));
+      } else {
+         CHK_RC(vec_random(run, primme, nL, v0));
+         CHK_RC(counted_svds_matvec(s, v0, nL, v0 + nL, mL, 1, 0));
+      }
+      CHK_RC(vec_dots(run, v0, nL, v0, nL, nL, 1, &n2[0]));
+      CHK_RC(vec_dots(run, v0 + nL, mL, v0 + nL, mL, mL, 1, &n2[1]));
+      n2[0] = 1.0 / sqrt(n2[0]), n2[1] = 1.0 / sqrt(n2[1]);
+      CHK_RC(vec_scale(run, v0, nL, nL, 1, &n2[0]));
+      CHK_RC(vec_scale(run, v0 + nL, mL, mL, 1, &n2[1]));
+      primme->initSize = 1;
+      if (rnorms) rnorms[0] = DBL_MAX;
+      primme->initBasisMode = primme_init_user;
+   }
+
+   /* second stage: the leading triplets that already pass the convergence test become
+    * orthogonality constraints (:795-826) */
+   if (stage == 1) {
+      const PRIMME_INT N = mL + nL;
+      for (int i = 0; primme->initSize > 0; i++) {
+         int isConv = 0;
+         if (conv_test_svds(s, svals[i], svecs + (size_t)N * primme->numOrthoConst + nL,
+                   svecs + (size_t)N * primme->numOrthoConst, rnorms[i], (int)method, &isConv))
+            return -1;
+         if (!isConv) break;
+         primme->numOrthoConst++;
+         primme->initSize--;
+         primme->numEvals--;
+      }
+   }
+   if (s->locking >= 0) primme->locking = s->locking;
+   primme->queue = s->queue;
+   primme->profile = s->profile;
    return 0;
+}
+
+/* Results of one stage back into primme_svds and svecs = [Uc U Vc V] (copy_last_params_to_svds,
+ * primme_svds_c.c:838-1030). */
+static int stage_end(svds_run *run, int stage, double *svals, double *svecs, double *rnorms, int allocatedShifts) {
+   primme_svds_params *s = run->svds;
+   primme_params *primme = stage == 0 ? &s->primme : &s->primmeStage2;
+   const primme_svds_operator method = stage == 0 ? s->method : s->methodStage2;
+   const PRIMME_INT mL = s->mLocal, nL = s->nLocal;
+   if (method == primme_svds_op_none) {
+      primme->maxMatvecs = 0;
+      return 0;
+   }
+   if (primme->initSize < 0) primme->initSize = 0; /* failed solve: nothing to return */
+   if (stage == 1) {
+      const int nconv = s->numSvals - primme->numEvals;
+      primme->initSize += nconv;
+      primme->numOrthoConst -= nconv;
+      primme->numEvals += nconv;
+   }
+   s->stats.numOuterIterations += primme->stats.numOuterIterations;
+   s->stats.numRestarts += primme->stats.numRestarts;
+   s->stats.numMatvecs += primme->stats.numMatvecs * 2; /* every eigensolver matvec is A and A' (:56-58) */
+   s->stats.numPreconds += primme->stats.numPreconds;
+   s->stats.numGlobalSum += primme->stats.numGlobalSum;
+   s->stats.volumeGlobalSum += primme->stats.volumeGlobalSum;
+   s->stats.numBroadcast += primme->stats.numBroadcast;
+   s->stats.volumeBroadcast += primme->stats.volumeBroadcast;
+   s->stats.numOrthoInnerProds += primme->stats.numOrthoInnerProds;
+   s->stats.elapsedTime += primme->stats.elapsedTime;
+   s->stats.timeMatvec += primme->stats.timeMatvec;
+   s->stats.timePrecond += primme->stats.timePrecond;
+   s->stats.timeOrtho += primme->stats.timeOrtho;
+   s->stats.timeGlobalSum += primme->stats.timeGlobalSum;
+   s->stats.timeBroadcast += primme->stats.timeBroadcast;
+   s->stats.lockingIssue += primme->stats.lockingIssue;
+   if (primme->aNorm > 0.0) s->aNorm = method == primme_svds_op_augmented ? primme->aNorm : sqrt(primme->aNorm);
+   if (method != primme_svds_op_augmented)
+      for (int i = 0; i < primme->initSize; i++) svals[i] = sqrt(PB_MAX(0.0, svals[i]));
+
+   const int nMax = PB_MAX(s->initSize, s->numSvals) + s->numOrthoConst;
+   s->initSize = primme->initSize;
+   const int nconv = s->initSize;
+   const int n0 = s->initSize + s->numOrthoConst;
+   int rc = 0;
+   if (method != primme_svds_op_augmented) {
+      const int ata = method == primme_svds_op_AtA;
+      double *aux = svecs + (size_t)nMax * mL;
+      double *inv = (double *)malloc(sizeof(double) * PB_MAX(nconv, 1));
+      for (int i = 0; i < nconv; i++) inv[i] = 1.0 / svals[i];
+      if (ata) {
+         /* U = A V diag(1/sigma), then [Vc V] packed right after the n0 left vectors */
+         double *U = svecs + (size_t)mL * s->numOrthoConst;
+         double *V = aux + (size_t)nL * s->numOrthoConst;
+         rc = counted_svds_matvec(s, V, nL, U, mL, nconv, 0);
+         if (!rc) rc = vec_scale(run, U, mL, mL, nconv, inv);
+         if (!rc) rc = vec_copy(run, aux, nL, svecs + (size_t)mL * n0, nL, nL, n0);
+      } else {
+         /* the constraints Vc first, then V = A' U diag(1/sigma) */
+         rc = vec_copy(run, aux, nL, svecs + (size_t)mL * n0, nL, nL, s->numOrthoConst);
+         double *U = svecs + (size_t)mL * s->numOrthoConst;
+         double *V = svecs + (size_t)mL * n0 + (size_t)nL * s->numOrthoConst;
+         if (!rc) rc = counted_svds_matvec(s, U, mL, V, nL, nconv, 1);
+         if (!rc) rc = vec_scale(run, V, nL, nL, nconv, inv);
+      }
+      free(inv);
+   } else {
+      const PRIMME_INT N = mL + nL;
+      double *sq2 = (double *)malloc(sizeof(double) * PB_MAX(2 * n0, 1));
+      for (int i = 0; i < s->numOrthoConst; i++) sq2[i] = sqrt(2.);
+      rc = vec_scale(run, svecs, N, N, s->numOrthoConst, sq2);
+      /* [Vc V; Uc U] back to [Uc U Vc V], every column of U and of V normalised */
+      if (!rc && n0 > 0) {
+         double *aux = NULL;
+         rc = vec_alloc(run, (size_t)N * n0, &aux);
+         if (!rc) rc = vec_copy(run, svecs, N * n0, aux, N * n0, N * n0, 1);
+         if (!rc) rc = vec_copy(run, aux, N, svecs + (size_t)mL * n0, nL, nL, n0);
+         if (!rc) rc = vec_copy(run, aux + nL, N, svecs, mL, mL, n0);
+         if (run->device_mode) pb200_ctx_sync(run->ctx);
+         vec_free(run, aux);
+         double *U = svecs, *V = svecs + (size_t)mL * n0;
+         if (!rc) rc = vec_dots(run, U, mL, U, mL, mL, n0, sq2);
+         if (!rc) rc = vec_dots(run, V, nL, V, nL, nL, n0, sq2 + n0);
+         for (int i = 0; i < 2 * n0; i++) sq2[i] = 1.0 / sqrt(sq2[i]);
+         if (!rc) rc = vec_scale(run, U, mL, mL, n0, sq2);
+         if (!rc) rc = vec_scale(run, V, nL, nL, n0, sq2 + n0);
+      }
+      free(sq2);
+   }
+   if (run->device_mode && run->ctx) pb200_ctx_sync(run->ctx);
+   for (int i = 0; i < 4; i++) s->iseed[i] = primme->iseed[i];
+   if (allocatedShifts) {
+      free(primme->targetShifts);
+      primme->targetShifts = NULL;
+   }
+   /* normal equations: the residual of the triplet is the eigen-residual over sigma; augmented: the
+    * convergence test already replaced it by the actual one up to the sqrt(2) of the normalisation */
+   if (method != primme_svds_op_augmented)
+      for (int i = 0; i < nconv; i++) rnorms[i] = PB_MIN(rnorms[i] / svals[i], s->aNorm);
+   else
+      for (int i = 0; i < nconv; i++) rnorms[i] *= sqrt(2.0);
+   return rc;
 }
 
 static int svds_solve(double *svals, double *svecs, double *resNorms, primme_svds_params *s, int device_mode) {
@@ -507,127 +919,53 @@ static int svds_solve(double *svals, double *svecs, double *resNorms, primme_svd
    }
    memset(&s->stats, 0, sizeof(s->stats));
 
-   primme_params *primme = &s->primme;
-   const int ata = s->method == primme_svds_op_AtA;
-   const PRIMME_INT mL = s->mLocal, nL = s->nLocal;
-   const int nMax = PB_MAX(s->initSize, s->numSvals) + s->numOrthoConst;
-   int n0 = s->initSize + s->numOrthoConst;
-
    svds_run *run = find_run(NULL);
    if (!run) return PRIMME_MALLOC_FAILURE;
    memset(run, 0, sizeof(*run));
    run->svds = s, run->device_mode = device_mode;
 
-   /* ---- copy_last_params_from_svds, stage 0 (primme_svds_c.c:551-830) ---- */
-   if (!primme->matrixMatvec) {
-      primme->matrixMatvec = matvec_normal_equations;
-      primme->matrixMatvec_type = primme_op_double;
-      primme->matrix = s;
-   }
-   if (s->aNorm > 0.0) primme->aNorm = s->aNorm * s->aNorm;
-   primme->convTestFun = conv_test_normal_equations;
-   primme->convTestFun_type = primme_op_double;
-   primme->initSize = s->initSize;
-   primme->numOrthoConst = s->numOrthoConst;
-   /* a private context for the whole call when the caller attached none: the vector
-    * post-processing below needs it after the eigensolver returns */
-   pb200_ctx *ctx = primme_b200_attached_ctx(primme);
+   /* one kernel context for the whole call: the caller's (attached to the first-stage eigensolver)
+    * or a private one; the vector post-processing needs it outside the eigensolver */
+   pb200_ctx *ctx = primme_b200_attached_ctx(&s->primme);
    int own_ctx = 0;
    if (!ctx && device_mode) {
       if (pb200_ctx_create(&ctx, -1)) {
          run->svds = NULL;
+         s->initSize = 0;
          return PRIMME_FUNCTION_UNAVAILABLE;
       }
       own_ctx = 1;
-      primme_b200_attach_ctx(primme, ctx);
+      primme_b200_attach_ctx(&s->primme, ctx);
    }
-   /* the right vectors [Vc V0] move to the rightmost position of svecs, where the eigensolver
-    * works in place; with AA' only Vc moves and the eigensolver works on the left block */
-   double *aux = svecs + (size_t)nMax * mL;
-   rc = vec_copy(ctx, device_mode, svecs + (size_t)mL * n0, nL, aux, nL, nL, ata ? n0 : s->numOrthoConst);
-   double *evecs = ata ? aux : svecs;
-   for (int i = 0; i < 4; i++) primme->iseed[i] = s->iseed[i];
-   primme->maxMatvecs = s->maxMatvecs / 2;
-   if (s->locking >= 0) primme->locking = s->locking;
-   primme->queue = s->queue;
-   primme->profile = s->profile;
-   primme->ldevecs = ata ? nL : mL;
+   run->ctx = ctx;
+   const int attach2 = ctx && s->methodStage2 != primme_svds_op_none && !primme_b200_attached_ctx(&s->primmeStage2);
+   if (attach2) primme_b200_attach_ctx(&s->primmeStage2, ctx);
 
-   int ret = rc;
-   if (!ret) ret = device_mode ? cublas_dprimme(svals, evecs, resNorms, primme) : dprimme(svals, evecs, resNorms, primme);
-
-   /* ---- copy_last_params_to_svds, stage 0 (primme_svds_c.c:838-1000) ---- */
-   s->stats.numOuterIterations += primme->stats.numOuterIterations;
-   s->stats.numRestarts += primme->stats.numRestarts;
-   s->stats.numMatvecs += primme->stats.numMatvecs * 2; /* every eigensolver matvec is A and A' (:56-58) */
-   s->stats.numPreconds += primme->stats.numPreconds;
-   s->stats.numGlobalSum += primme->stats.numGlobalSum;
-   s->stats.volumeGlobalSum += primme->stats.volumeGlobalSum;
-   s->stats.numBroadcast += primme->stats.numBroadcast;
-   s->stats.volumeBroadcast += primme->stats.volumeBroadcast;
-   s->stats.numOrthoInnerProds += primme->stats.numOrthoInnerProds;
-   s->stats.elapsedTime += primme->stats.elapsedTime;
-   s->stats.timeMatvec += primme->stats.timeMatvec;
-   s->stats.timePrecond += primme->stats.timePrecond;
-   s->stats.timeOrtho += primme->stats.timeOrtho;
-   s->stats.timeGlobalSum += primme->stats.timeGlobalSum;
-   s->stats.timeBroadcast += primme->stats.timeBroadcast;
-   s->stats.lockingIssue += primme->stats.lockingIssue;
-   if (primme->aNorm > 0.0) s->aNorm = sqrt(primme->aNorm);
-   const int nconv = primme->initSize > 0 ? primme->initSize : 0;
-   for (int i = 0; i < nconv; i++) svals[i] = sqrt(PB_MAX(0.0, svals[i]));
-   s->initSize = nconv;
-   n0 = s->initSize + s->numOrthoConst;
-   int rc2 = 0;
-   if (nconv > 0) {
-      double *inv = (double *)malloc(sizeof(double) * nconv);
-      for (int i = 0; i < nconv; i++) inv[i] = 1.0 / svals[i];
-      if (ata) {
-         /* U = A V diag(1/sigma), then V packed right after the n0 left vectors */
-         double *U = svecs + (size_t)mL * s->numOrthoConst;
-         double *V = aux + (size_t)nL * s->numOrthoConst;
-         rc2 = call_svds_matvec(s, V, nL, U, mL, nconv, 0) ? PRIMME_USER_FAILURE : 0;
-         s->stats.numMatvecs += nconv;
-         if (!rc2) {
-            if (device_mode)
-               rc2 = pb200_dscale_columns(ctx, mL, inv, U, mL, nconv);
-            else
-               for (int j = 0; j < nconv; j++)
-                  for (PRIMME_INT r = 0; r < mL; r++) U[r + (size_t)mL * j] *= inv[j];
-         }
-         if (!rc2) rc2 = vec_copy(ctx, device_mode, aux, nL, svecs + (size_t)mL * n0, nL, nL, n0);
-      } else {
-         /* the constraints Vc first, then V = A' U diag(1/sigma) */
-         rc2 = vec_copy(ctx, device_mode, aux, nL, svecs + (size_t)mL * n0, nL, nL, s->numOrthoConst);
-         double *U = svecs + (size_t)mL * s->numOrthoConst;
-         double *V = svecs + (size_t)mL * n0 + (size_t)nL * s->numOrthoConst;
-         if (!rc2) rc2 = call_svds_matvec(s, U, mL, V, nL, nconv, 1) ? PRIMME_USER_FAILURE : 0;
-         s->stats.numMatvecs += nconv;
-         if (!rc2) {
-            if (device_mode)
-               rc2 = pb200_dscale_columns(ctx, nL, inv, V, nL, nconv);
-            else
-               for (int j = 0; j < nconv; j++)
-                  for (PRIMME_INT r = 0; r < nL; r++) V[r + (size_t)nL * j] *= inv[j];
-         }
-      }
-      free(inv);
-      if (device_mode && ctx) pb200_ctx_sync(ctx);
+   int ret = 0;
+   for (int stage = 0; stage < 2 && ret == 0 && rc == 0; stage++) {
+      primme_params *primme = stage == 0 ? &s->primme : &s->primmeStage2;
+      if (stage == 1 && s->methodStage2 == primme_svds_op_none) break;
+      int allocatedShifts = 0;
+      double *evecs = NULL;
+      rc = stage_begin(run, stage, svals, svecs, resNorms, &allocatedShifts, &evecs);
+      if (rc) break;
+      /* numSvals - numEvals triplets of the first stage are already converged (:505-508) */
+      const int skip = stage == 1 ? s->numSvals - primme->numEvals : 0;
+      ret = device_mode ? cublas_dprimme(svals + skip, evecs, resNorms + skip, primme)
+                        : dprimme(svals + skip, evecs, resNorms + skip, primme);
+      rc = stage_end(run, stage, svals, svecs, resNorms, allocatedShifts);
+      if (ret != 0) ret -= 100 * (stage + 1); /* errors of the first / second stage (:497,515) */
    }
-   for (int i = 0; i < 4; i++) s->iseed[i] = primme->iseed[i];
-   for (int i = 0; i < nconv; i++) resNorms[i] = PB_MIN(resNorms[i] / svals[i], s->aNorm);
 
-   if (run->aux) {
-      if (device_mode) pb200_free(ctx, run->aux);
-      else free(run->aux);
-   }
+   vec_free(run, run->aux);
    run->svds = NULL, run->aux = NULL;
+   if (attach2) primme_b200_attach_ctx(&s->primmeStage2, NULL);
    if (own_ctx) {
-      primme_b200_attach_ctx(primme, NULL);
+      primme_b200_attach_ctx(&s->primme, NULL);
       pb200_ctx_destroy(ctx);
    }
-   if (ret != 0) return ret - 100; /* errors of the first stage (primme_svds_c.c:497) */
-   return rc2;
+   if (ret != 0) return ret;
+   return rc;
 }
 
 int dprimme_svds(double *svals, double *svecs, double *resNorms, primme_svds_params *primme_svds) {

@@ -62,7 +62,7 @@ def get_member(lib, p, name):
 
 
 def solve(which, csr, shape, numSvals, target=primme_svds_largest, method=primme_svds_normalequations,
-          method_stage1=api.PRIMME_DEFAULT_METHOD, **kw):
+          method_stage1=api.PRIMME_DEFAULT_METHOD, method_stage2=api.PRIMME_DEFAULT_METHOD, **kw):
     """dprimme_svds through `which` in {"reference", "hostcheck", "product"}; host contract (host
     svecs, host matvec callback from oracle/csr_host.c).  Returns dict(svals, rnorms, U, V, ret, stats)."""
     m, n = shape
@@ -84,7 +84,7 @@ def solve(which, csr, shape, numSvals, target=primme_svds_largest, method=primme
     set_member(lib, p, "printLevel", 0)
     for k, v in kw.items():
         set_member(lib, p, k, v)
-    assert lib.primme_svds_set_method(method, method_stage1, api.PRIMME_DEFAULT_METHOD, p) == 0
+    assert lib.primme_svds_set_method(method, method_stage1, method_stage2, p) == 0
     svals, rn = np.zeros(numSvals), np.zeros(numSvals)
     svecs = np.zeros((m + n) * numSvals)
     rc = lib.dprimme_svds(svals.ctypes.data, svecs.ctypes.data, rn.ctypes.data, p)

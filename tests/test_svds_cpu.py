@@ -1,4 +1,4 @@
-"""SVD front end, normal equations: the host logic (primme_b200/src/svds.c
+"""SVD front end: normal equations, augmented operator and the two-stage hybrid: the host logic (primme_b200/src/svds.c
 linked against the CPU restatement of the kernels) against the UNMODIFIED reference's dprimme_svds
 on the same matrices, callbacks and parameters -- singular values, residual norms, vectors and the
 iteration / matvec counts."""
@@ -50,11 +50,60 @@ def test_svds_hostcheck_matches_reference(case):
     assert abs(got["aNorm"] - ref["aNorm"]) <= 1e-12 * ref["aNorm"]
 
 
-def test_svds_out_of_scope_is_refused():
-    m, n = 50, 20
-    csr = S.random_rect(m, n, 4, 9)
-    r = S.solve("hostcheck", csr, (m, n), 2, method=S.primme_svds_hybrid, eps=1e-8)
-    assert r["ret"] == api.PRIMME_FUNCTION_UNAVAILABLE and r["initSize"] == 0
+# hybrid (normal equations, then the augmented operator started from the first stage's triplets) and the
+# augmented operator alone; fixed methods in both stages so that the counts are comparable
+TWO_STAGE = {
+    # name: (m, n, per_row, seed, numSvals, preset, extra)
+    "hybrid_loose": (600, 150, 6, 1, 5, S.primme_svds_hybrid, dict(eps=1e-6)),          # second stage has nothing left to do
+    "hybrid_tight": (600, 150, 6, 1, 5, S.primme_svds_hybrid, dict(eps=1e-12)),         # second stage refines every triplet
+    "hybrid_wide": (150, 500, 8, 2, 4, S.primme_svds_hybrid, dict(eps=1e-12)),          # AA' first
+    "hybrid_block": (500, 200, 5, 3, 6, S.primme_svds_hybrid, dict(eps=1e-11, maxBlockSize=2, maxBasisSize=24)),
+    "hybrid_locking": (400, 120, 6, 5, 5, S.primme_svds_hybrid, dict(eps=1e-12, locking=1)),
+    "augmented": (600, 150, 6, 1, 5, S.primme_svds_augmented, dict(eps=1e-8)),
+    "augmented_wide": (120, 300, 6, 7, 3, S.primme_svds_augmented, dict(eps=1e-9)),
+}
+
+
+def check_two_stage(case, r):
+    m, n, per_row, seed, k, preset, kw = TWO_STAGE[case]
+    A = S.dense(S.random_rect(m, n, per_row, seed), (m, n))
+    sv = np.linalg.svd(A, compute_uv=False)
+    assert r["ret"] == 0 and r["initSize"] == k
+    assert np.allclose(np.sort(r["svals"])[::-1], sv[:k], rtol=0, atol=10 * kw["eps"] * sv[0])
+    U, V = r["U"], r["V"]
+    # every column of U and of V comes back normalised (primme_svds_c.c:958-985)
+    assert np.allclose(np.linalg.norm(U, axis=0), 1, atol=1e-12) and np.allclose(np.linalg.norm(V, axis=0), 1, atol=1e-12)
+    # the reported residual norm is the triplet's: sqrt(|A v - s u|^2 + |A' u - s v|^2) < eps |A|
+    R = np.sqrt(np.linalg.norm(A @ V - U * r["svals"], axis=0) ** 2 + np.linalg.norm(A.T @ U - V * r["svals"], axis=0) ** 2)
+    assert np.all(R < max(kw["eps"], 1e-15) * r["aNorm"] * 1.05 + 1e-13 * sv[0]), (R, kw["eps"] * r["aNorm"])
+
+
+@pytest.mark.parametrize("case", sorted(TWO_STAGE))
+def test_svds_two_stage_hostcheck_matches_reference(case):
+    m, n, per_row, seed, k, preset, kw = TWO_STAGE[case]
+    csr = S.random_rect(m, n, per_row, seed)
+    args = dict(method=preset, method_stage1=api.PRIMME_GD_Olsen_plusK, method_stage2=api.PRIMME_GD_Olsen_plusK, **kw)
+    ref = S.solve("reference", csr, (m, n), k, **args)
+    got = S.solve("hostcheck", csr, (m, n), k, **args)
+    check_two_stage(case, ref)
+    check_two_stage(case, got)
+    assert np.allclose(got["svals"], ref["svals"], rtol=1e-12)
+    assert got["stats"] == ref["stats"], (got["stats"], ref["stats"])
+    assert abs(got["aNorm"] - ref["aNorm"]) <= 1e-12 * ref["aNorm"]
+
+
+def test_svds_default_method_runs_like_reference():
+    """primme_svds_default = hybrid with PRIMME_DEFAULT_METHOD in both stages (run-time method choice:
+    values and residuals are the criterion, not counts)"""
+    m, n, k = 500, 120, 4
+    csr = S.random_rect(m, n, 6, 21)
+    ref = S.solve("reference", csr, (m, n), k, method=S.primme_svds_default, eps=1e-12)
+    got = S.solve("hostcheck", csr, (m, n), k, method=S.primme_svds_default, eps=1e-12)
+    assert ref["ret"] == 0 and got["ret"] == 0 and got["initSize"] == k
+    assert np.allclose(got["svals"], ref["svals"], rtol=1e-12)
+    # reported norms carry the sqrt(2) of the augmented normalisation (primme_svds_c.c:1017-1021)
+    for r in (ref, got):
+        assert np.all(r["rnorms"] < 2 * 1e-12 * r["aNorm"])
 
 
 @pytest.mark.parametrize("m,n,target,preset,stage1", [

@@ -27,8 +27,24 @@ def test_svds_product_host_contract_matches_reference(case):
         assert abs(got["stats"][key] - ref["stats"][key]) <= max(3, 0.03 * ref["stats"][key]), (got["stats"], ref["stats"])
 
 
-@pytest.mark.parametrize("shape,k", [((40000, 9000), 6), ((7000, 30000), 5)])
-def test_cublas_dprimme_svds_builtin_operator(shape, k):
+@pytest.mark.parametrize("case", ["hybrid_loose", "hybrid_tight", "hybrid_wide", "hybrid_block", "augmented"])
+def test_svds_two_stage_product_host_contract_matches_reference(case):
+    m, n, per_row, seed, k, preset, kw = T.TWO_STAGE[case]
+    csr = S.random_rect(m, n, per_row, seed)
+    args = dict(method=preset, method_stage1=api.PRIMME_GD_Olsen_plusK, method_stage2=api.PRIMME_GD_Olsen_plusK, **kw)
+    ref = S.solve("reference", csr, (m, n), k, **args)
+    got = S.solve("product", csr, (m, n), k, **args)
+    T.check_two_stage(case, got)
+    assert np.allclose(got["svals"], ref["svals"], rtol=1e-11)
+    for key in ("numOuterIterations", "numMatvecs"):
+        assert abs(got["stats"][key] - ref["stats"][key]) <= max(3, 0.05 * ref["stats"][key]), (got["stats"], ref["stats"])
+
+
+@pytest.mark.parametrize("shape,k,preset", [((40000, 9000), 6, S.primme_svds_normalequations),
+                                            ((7000, 30000), 5, S.primme_svds_normalequations),
+                                            ((30000, 8000), 4, S.primme_svds_hybrid),
+                                            ((6000, 20000), 3, S.primme_svds_augmented)])
+def test_cublas_dprimme_svds_builtin_operator(shape, k, preset):
     m, n = shape
     csr = S.random_rect(m, n, 6, 11)
     lib = H.lib_product()
@@ -47,8 +63,8 @@ def test_cublas_dprimme_svds_builtin_operator(shape, k):
                     ("maxBlockSize", 2), ("matrix", A.value),
                     ("matrixMatvec", C.cast(lib.primme_b200_svds_csr_matvec, C.c_void_p).value)):
         S.set_member(lib, p, name, v)
-    S.set_member(lib, p, "eps", 1e-9)
-    assert lib.primme_svds_set_method(S.primme_svds_normalequations, api.PRIMME_GD_Olsen_plusK, api.PRIMME_DEFAULT_METHOD, p) == 0
+    S.set_member(lib, p, "eps", 1e-9 if preset == S.primme_svds_normalequations else 1e-12)
+    assert lib.primme_svds_set_method(preset, api.PRIMME_GD_Olsen_plusK, api.PRIMME_GD_Olsen_plusK, p) == 0
     inner = S.get_member(lib, p, "primme")  # address of the first-stage primme_params
     inner_p = C.cast(C.c_void_p(inner), C.POINTER(api.PrimmeParams))
     lib.primme_b200_attach_ctx(inner_p, ctx)
@@ -70,6 +86,10 @@ def test_cublas_dprimme_svds_builtin_operator(shape, k):
     assert np.allclose(np.sort(svals)[::-1], want, rtol=1e-8)
     assert np.abs(V.T @ V - np.eye(k)).max() < 1e-8 and np.abs(U.T @ U - np.eye(k)).max() < 1e-6
     assert np.linalg.norm(As @ V - U * svals, axis=0).max() < 1e-7 * want[0]
+    if preset != S.primme_svds_normalequations:
+        # the second stage reaches what the normal equations cannot: both residuals at eps |A|
+        assert np.linalg.norm(As @ V - U * svals, axis=0).max() < 1e-11 * want[0]
+        assert np.linalg.norm(As.T @ U - V * svals, axis=0).max() < 1e-11 * want[0]
     lib.primme_b200_attach_ctx(inner_p, None)
     lib.pb200_free(ctx, dsvecs)
     lib.primme_svds_params_destroy(p)

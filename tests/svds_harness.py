@@ -62,7 +62,7 @@ def get_member(lib, p, name):
 
 
 def solve(which, csr, shape, numSvals, target=primme_svds_largest, method=primme_svds_normalequations,
-          method_stage1=api.PRIMME_DEFAULT_METHOD, method_stage2=api.PRIMME_DEFAULT_METHOD, **kw):
+          method_stage1=api.PRIMME_DEFAULT_METHOD, method_stage2=api.PRIMME_DEFAULT_METHOD, device_entry=False, **kw):
     """dprimme_svds through `which` in {"reference", "hostcheck", "product"}; host contract (host
     svecs, host matvec callback from oracle/csr_host.c).  Returns dict(svals, rnorms, U, V, ret, stats)."""
     m, n = shape
@@ -87,7 +87,10 @@ def solve(which, csr, shape, numSvals, target=primme_svds_largest, method=primme
     assert lib.primme_svds_set_method(method, method_stage1, method_stage2, p) == 0
     svals, rn = np.zeros(numSvals), np.zeros(numSvals)
     svecs = np.zeros((m + n) * numSvals)
-    rc = lib.dprimme_svds(svals.ctypes.data, svecs.ctypes.data, rn.ctypes.data, p)
+    # device_entry: cublas_dprimme_svds of the host-check library, where "device" memory is host memory --
+    # runs the device-contract code path (kernels of the C-ABI for every vector operation) on the CPU
+    entry = lib.cublas_dprimme_svds if device_entry else lib.dprimme_svds
+    rc = entry(svals.ctypes.data, svecs.ctypes.data, rn.ctypes.data, p)
     k = get_member(lib, p, "initSize")
     out = dict(ret=rc, svals=svals, rnorms=rn, initSize=k,
                U=svecs[: m * k].reshape(k, m).T.copy(), V=svecs[m * k: m * k + n * k].reshape(k, n).T.copy(),

@@ -92,6 +92,20 @@ def test_svds_two_stage_hostcheck_matches_reference(case):
     assert abs(got["aNorm"] - ref["aNorm"]) <= 1e-12 * ref["aNorm"]
 
 
+@pytest.mark.parametrize("case", ["hybrid_tight", "hybrid_wide", "augmented_wide"])
+def test_svds_two_stage_device_contract_code_path(case):
+    """cublas_dprimme_svds of the host-check build: same host logic, but every vector operation of the
+    front end goes through the C-ABI (here its CPU restatement) instead of host loops"""
+    m, n, per_row, seed, k, preset, kw = TWO_STAGE[case]
+    csr = S.random_rect(m, n, per_row, seed)
+    args = dict(method=preset, method_stage1=api.PRIMME_GD_Olsen_plusK, method_stage2=api.PRIMME_GD_Olsen_plusK, **kw)
+    ref = S.solve("reference", csr, (m, n), k, **args)
+    got = S.solve("hostcheck", csr, (m, n), k, device_entry=True, **args)
+    check_two_stage(case, got)
+    assert np.allclose(got["svals"], ref["svals"], rtol=1e-12)
+    assert got["stats"] == ref["stats"], (got["stats"], ref["stats"])
+
+
 def test_svds_default_method_runs_like_reference():
     """primme_svds_default = hybrid with PRIMME_DEFAULT_METHOD in both stages (run-time method choice:
     values and residuals are the criterion, not counts)"""

@@ -42,8 +42,8 @@ def test_svds_two_stage_product_host_contract_matches_reference(case):
 
 @pytest.mark.parametrize("shape,k,preset", [((40000, 9000), 6, S.primme_svds_normalequations),
                                             ((7000, 30000), 5, S.primme_svds_normalequations),
-                                            ((30000, 8000), 4, S.primme_svds_hybrid),
-                                            ((6000, 20000), 3, S.primme_svds_augmented)])
+                                            ((12000, 3000), 4, S.primme_svds_hybrid),
+                                            ((3000, 9000), 3, S.primme_svds_augmented)])
 def test_cublas_dprimme_svds_builtin_operator(shape, k, preset):
     m, n = shape
     csr = S.random_rect(m, n, 6, 11)

@@ -179,36 +179,67 @@ static void svds_set_defaults(primme_svds_params *s) {
    if (s->methodStage2 != primme_svds_op_none) copy_params_from_svds(s, 1);
 }
 
+/* the configuration in the reference's text format (primme_svds_interface.c:420-512): the test
+ * drivers print it and read it back (tests/COMMON/shared_utils.c) */
 void primme_svds_display_params(primme_svds_params s) {
    FILE *f = s.outputFile ? s.outputFile : stdout;
-   fprintf(f, "// ---------------------------------------------------\n");
-   fprintf(f, "//            primme_svds configuration               \n");
-   fprintf(f, "// ---------------------------------------------------\n");
+   static const char *ops[] = {"primme_svds_op_none", "primme_svds_op_AtA", "primme_svds_op_AAt", "primme_svds_op_augmented"};
+   fprintf(f, "// ---------------------------------------------------\n"
+              "//            primme_svds configuration               \n"
+              "// ---------------------------------------------------\n");
    fprintf(f, "primme_svds.m = %" PRIMME_INT_P "\n", s.m);
    fprintf(f, "primme_svds.n = %" PRIMME_INT_P "\n", s.n);
    fprintf(f, "primme_svds.mLocal = %" PRIMME_INT_P "\n", s.mLocal);
    fprintf(f, "primme_svds.nLocal = %" PRIMME_INT_P "\n", s.nLocal);
    fprintf(f, "primme_svds.numProcs = %d\n", s.numProcs);
    fprintf(f, "primme_svds.procID = %d\n", s.procID);
+   fprintf(f, "\n// Output and reporting\n");
+   fprintf(f, "primme_svds.printLevel = %d\n", s.printLevel);
+   fprintf(f, "\n// Solver parameters\n");
    fprintf(f, "primme_svds.numSvals = %d\n", s.numSvals);
    fprintf(f, "primme_svds.aNorm = %e\n", s.aNorm);
    fprintf(f, "primme_svds.eps = %e\n", s.eps);
    fprintf(f, "primme_svds.maxBasisSize = %d\n", s.maxBasisSize);
    fprintf(f, "primme_svds.maxBlockSize = %d\n", s.maxBlockSize);
    fprintf(f, "primme_svds.maxMatvecs = %" PRIMME_INT_P "\n", s.maxMatvecs);
-   fprintf(f, "primme_svds.target = %s\n", s.target == primme_svds_largest    ? "primme_svds_largest"
-                                            : s.target == primme_svds_smallest ? "primme_svds_smallest"
-                                                                               : "primme_svds_closest_abs");
+   if (s.target == primme_svds_smallest) fprintf(f, "primme_svds.target = primme_svds_smallest\n");
+   if (s.target == primme_svds_largest) fprintf(f, "primme_svds.target = primme_svds_largest\n");
+   if (s.target == primme_svds_closest_abs) fprintf(f, "primme_svds.target = primme_svds_closest_abs\n");
    fprintf(f, "primme_svds.numTargetShifts = %d\n", s.numTargetShifts);
+   if (s.numTargetShifts > 0) {
+      fprintf(f, "primme_svds.targetShifts =");
+      for (int i = 0; i < s.numTargetShifts; i++) fprintf(f, " %e", s.targetShifts[i]);
+      fprintf(f, "\n");
+   }
    fprintf(f, "primme_svds.locking = %d\n", s.locking);
    fprintf(f, "primme_svds.initSize = %d\n", s.initSize);
    fprintf(f, "primme_svds.numOrthoConst = %d\n", s.numOrthoConst);
-   fprintf(f, "primme_svds.printLevel = %d\n", s.printLevel);
-   static const char *ops[] = {"primme_svds_op_none", "primme_svds_op_AtA", "primme_svds_op_AAt", "primme_svds_op_augmented"};
-   fprintf(f, "primme_svds.method = %s\n", ops[s.method & 3]);
-   fprintf(f, "primme_svds.methodStage2 = %s\n", ops[s.methodStage2 & 3]);
-   if (s.method != primme_svds_op_none) primme_display_params_prefix("primme", s.primme);
-   if (s.methodStage2 != primme_svds_op_none) primme_display_params_prefix("primmeStage2", s.primmeStage2);
+   fprintf(f, "primme_svds.iseed =");
+   for (int i = 0; i < 4; i++) fprintf(f, " %" PRIMME_INT_P, s.iseed[i]);
+   fprintf(f, "\n");
+   fprintf(f, "primme_svds.precondition = %d\n", s.precondition);
+   if ((unsigned)s.method < 4) fprintf(f, "primme_svds.method = %s\n", ops[s.method]);
+   if ((unsigned)s.methodStage2 < 4) fprintf(f, "primme_svds.methodStage2 = %s\n", ops[s.methodStage2]);
+   if (s.internalPrecision == primme_op_half) fprintf(f, "primme_svds.internalPrecision = primme_op_half\n");
+   if (s.internalPrecision == primme_op_float) fprintf(f, "primme_svds.internalPrecision = primme_op_float\n");
+   if (s.internalPrecision == primme_op_double) fprintf(f, "primme_svds.internalPrecision = primme_op_double\n");
+   if (s.internalPrecision == primme_op_quad) fprintf(f, "primme_svds.internalPrecision = primme_op_quad\n");
+   if (s.method != primme_svds_op_none) {
+      fprintf(f, "\n"
+                 "// ---------------------------------------------------\n"
+                 "//            1st stage primme configuration          \n"
+                 "// ---------------------------------------------------\n");
+      s.primme.outputFile = f;
+      primme_display_params_prefix("primme", s.primme);
+   }
+   if (s.methodStage2 != primme_svds_op_none) {
+      fprintf(f, "\n"
+                 "// ---------------------------------------------------\n"
+                 "//            2st stage primme configuration          \n"
+                 "// ---------------------------------------------------\n");
+      s.primmeStage2.outputFile = f;
+      primme_display_params_prefix("primmeStage2", s.primmeStage2);
+   }
    fflush(f);
 }
 

@@ -16,11 +16,35 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 DRIVER = os.path.join(ROOT, "oracle", "_ref", "driver", "primme_double_b200")
+DRIVER_SVDS = os.path.join(ROOT, "oracle", "_ref", "driver", "primmesvds_double_b200")
 DATA = os.path.join(HERE, "golden", "driver")
 
 
-def run(cfg):
-    return subprocess.run([DRIVER, cfg], cwd=DATA, capture_output=True, text=True, timeout=600)
+def run(cfg, driver=DRIVER):
+    return subprocess.run([driver, cfg], cwd=DATA, capture_output=True, text=True, timeout=600)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", ["test_201", "test_202", "test_207"])
+def test_reference_svds_driver_passes_its_own_checks(cfg):
+    """tests/driversvds.c, unchanged: rect.mtx, 5 largest triplets with the default two-stage hybrid
+    (201: eps 1e-6, 202: eps 1e-12) and with the augmented operator alone (207); check_solution_svds
+    against the stored sol_20Nsvds_double"""
+    if not os.path.exists(DRIVER_SVDS):
+        pytest.skip("driver binary not built (needs the reference tree at build time)")
+    r = run(cfg, DRIVER_SVDS)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", ["test_203", "test_205"])
+def test_reference_svds_driver_out_of_scope_config_is_refused(cfg):
+    """smallest singular values: the second stage asks for refined extraction"""
+    if not os.path.exists(DRIVER_SVDS):
+        pytest.skip("driver binary not built")
+    r = run(cfg, DRIVER_SVDS)
+    assert r.returncode != 0
+    assert "-244" in r.stdout + r.stderr or "-44" in r.stdout + r.stderr
 
 
 @pytest.mark.gpu

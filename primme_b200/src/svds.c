@@ -13,8 +13,11 @@
  *    copy_last_params_from_svds / _to_svds                :551-1030
  *    matrixMatvec_eigs, applyPreconditioner_eigs          :1323-1417
  *    compute_resNorm, default_convTestFun, convTestFunATA, convTestFunAug   :1512-1745
+ * Row-partitioned runs (numProcs > 1, mLocal / nLocal rows of the left / right vectors per process): the
+ * eigensolver's collectives and the triplet-level sums go through primme_svds.globalSumReal or the
+ * communicator of the attached kernel context; the user's matrixMatvec owns the exchange of the operator.
  * Refused with PRIMME_FUNCTION_UNAVAILABLE = -44 like a reference build without the feature: every
- * precision but double, numProcs > 1; and by the eigensolver underneath (front.c:check_scope) what it
+ * precision but double; and by the eigensolver underneath (front.c:check_scope) what it
  * does not cover -- refined extraction, which the augmented operator selects for smallest /
  * closest_abs targets (primme_svds_interface.c:385-391).
  */
@@ -502,6 +505,26 @@ static int vec_random(svds_run *run, primme_params *primme, int64_t rows, double
    return rc;
 }
 
+/* sum over the processes of a row-partitioned run (globalSum_Rprimme_svds, primme_svds_c.c:1760-1800):
+ * the user's globalSumReal on host buffers, else the communicator of the kernel context */
+static int svds_global_sum(svds_run *run, double *buf, int count) {
+   primme_svds_params *s = run->svds;
+   if (s->numProcs <= 1 || count <= 0) return 0;
+   const double t0 = hl_wtime();
+   int ierr = 0;
+   if (s->globalSumReal) {
+      s->globalSumReal(buf, buf, &count, s, &ierr);
+      if (ierr) return PRIMME_USER_FAILURE;
+   } else if (run->ctx && pb200_ctx_nranks(run->ctx) > 1) {
+      if (pb200_allreduce_host(run->ctx, buf, count)) return PRIMME_PARALLEL_FAILURE;
+   } else
+      return PRIMME_PARALLEL_FAILURE;
+   s->stats.numGlobalSum++;
+   s->stats.volumeGlobalSum += count;
+   s->stats.timeGlobalSum += hl_wtime() - t0;
+   return 0;
+}
+
 /* y = A'(A x), A(A' x) in blocks of maxBlockSize columns, or [0 A'; A 0] x (primme_svds_c.c:1323-1383) */
 static void matvec_eigs(void *x_, PRIMME_INT *ldx, void *y_, PRIMME_INT *ldy, int *blockSize,
       primme_params *primme, int *ierr) {
@@ -569,6 +592,7 @@ static int compute_res_norm(svds_run *run, double *left, double *right, double *
    if (!rc) rc = vec_dots(run, right, nL, right, nL, nL, 1, &ip[0]);
    if (!rc) rc = vec_dots(run, left, mL, left, mL, mL, 1, &ip[1]);
    if (!rc) rc = vec_dots(run, left, mL, Av, mL, mL, 1, &ip[2]);
+   if (!rc) rc = svds_global_sum(run, ip, 3);
    if (!rc) {
       ip[0] = sqrt(ip[0]), ip[1] = sqrt(ip[1]);
       const double sval = ip[2] / ip[0] / ip[1];
@@ -581,6 +605,7 @@ static int compute_res_norm(svds_run *run, double *left, double *right, double *
          if (!rc) rc = vec_scale(run, Av, mL, mL, 1, &b);
          if (!rc) rc = vec_axpy(run, mL, -sval / ip[1], left, Av);
          if (!rc) rc = vec_dots(run, Atu, mL + nL, Atu, mL + nL, mL + nL, 1, &nrm2);
+         if (!rc) rc = svds_global_sum(run, &nrm2, 1);
          *rNorm = sqrt(nrm2);
       }
    }
@@ -678,8 +703,12 @@ static int svds_out_of_scope(primme_svds_params *s) {
                s->applyPreconditioner_type != primme_op_double) ||
          (s->internalPrecision != primme_op_default && s->internalPrecision != primme_op_double))
       why = "callbacks / internal precision other than double";
-   else if (s->numProcs > 1)
-      why = "the distributed SVD front end";
+   else if ((s->method != primme_svds_op_none && s->primme.projectionParams.projection != primme_proj_default &&
+                  s->primme.projectionParams.projection != primme_proj_RR) ||
+            (s->methodStage2 != primme_svds_op_none && s->primmeStage2.projectionParams.projection != primme_proj_default &&
+                  s->primmeStage2.projectionParams.projection != primme_proj_RR))
+      /* known before the first stage runs: smallest / closest_abs on the augmented operator */
+      why = "refined / harmonic extraction (augmented operator with smallest or closest_abs targets)";
    if (!why) return 0;
    if (s->outputFile && s->printLevel > 0)
       fprintf(s->outputFile, "PRIMME-B200: %s is outside the scope of this build\n", why);
@@ -796,6 +825,7 @@ static int stage_begin(svds_run *run, int stage, double *svals, double *svecs, d
       }
       CHK_RC(vec_dots(run, v0, nL, v0, nL, nL, 1, &n2[0]));
       CHK_RC(vec_dots(run, v0 + nL, mL, v0 + nL, mL, mL, 1, &n2[1]));
+      CHK_RC(svds_global_sum(run, n2, 2));
       n2[0] = 1.0 / sqrt(n2[0]), n2[1] = 1.0 / sqrt(n2[1]);
       CHK_RC(vec_scale(run, v0, nL, nL, 1, &n2[0]));
       CHK_RC(vec_scale(run, v0 + nL, mL, mL, 1, &n2[1]));
@@ -906,6 +936,7 @@ static int stage_end(svds_run *run, int stage, double *svals, double *svecs, dou
          double *U = svecs, *V = svecs + (size_t)mL * n0;
          if (!rc) rc = vec_dots(run, U, mL, U, mL, mL, n0, sq2);
          if (!rc) rc = vec_dots(run, V, nL, V, nL, nL, n0, sq2 + n0);
+         if (!rc) rc = svds_global_sum(run, sq2, 2 * n0);
          for (int i = 0; i < 2 * n0; i++) sq2[i] = 1.0 / sqrt(sq2[i]);
          if (!rc) rc = vec_scale(run, U, mL, mL, n0, sq2);
          if (!rc) rc = vec_scale(run, V, nL, nL, n0, sq2 + n0);

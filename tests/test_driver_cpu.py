@@ -43,3 +43,13 @@ def test_svds_driver_prints_the_configuration_like_the_reference(cfg):
     ref = run("primmesvds_double_ref", cfg).stdout.split("Error in")[0].split("Sval[")[0]
     assert "primme_svds.methodStage2" in ours
     assert ours == ref
+
+
+@pytest.mark.parametrize("cfg", ["test_203", "test_204", "test_205", "test_206"])
+def test_svds_driver_out_of_scope_config_is_refused_before_any_work(cfg):
+    """smallest singular values with the hybrid method: the second stage would need refined
+    extraction; refused up front (no first stage is run for a result that cannot be finished)"""
+    r = run("primmesvds_double_hostcheck", cfg)
+    assert r.returncode != 0
+    assert "outside the scope of this build" in r.stdout + r.stderr
+    assert "1st Matvecs     : 0" in r.stdout

@@ -31,3 +31,27 @@ def test_two_rank_row_sharded_solve(bs, method):
     anorm = 12.0
     assert max(out["res"]) < 1e-10 * anorm * 1.1
     assert out["globalsums"] > 0
+
+
+@pytest.mark.parametrize("preset,device_entry", [("primme_svds_normalequations", "0"), ("primme_svds_hybrid", "0"),
+                                                 ("primme_svds_hybrid", "1"), ("primme_svds_augmented", "1")])
+def test_two_rank_row_partitioned_svds(preset, device_entry):
+    """dprimme_svds / cublas_dprimme_svds with numProcs = 2 (the layout of BASELINE config C4): rows of A, of the
+    left and of the right vectors split over the ranks; singular values against a dense SVD, triplet
+    residuals and orthonormality of the gathered vectors"""
+    env = dict(os.environ, PB_PRESET=preset, PB_DEVICE_ENTRY=device_entry, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
+    port = 29560 + (1 if "hybrid" in preset else 0) + 2 * int(device_entry) + (4 if "augmented" in preset else 0)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "svds_multi_rank_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1][len("RESULT "):])
+    assert out["rc"] == 0 and out["initSize"] == 4
+    assert np.allclose(out["svals"], out["exact"], rtol=1e-10)
+    assert out["orthV"] < 1e-8 and out["orthU"] < 1e-6
+    tol = 1e-11 * out["aNorm"]
+    if preset == "primme_svds_normalequations":
+        assert max(out["res"]) < 1e-7 * out["aNorm"]      # accuracy of the normal equations
+    else:
+        assert max(out["res"]) < 1.05 * tol and max(out["rnorms"]) < 2 * tol
+    assert out["globalsums"] > 0

@@ -672,6 +672,206 @@ static void conv_test_augmented(double *eval, void *evec, double *rNorm, int *is
    s->aNorm = oldaNorm;
 }
 
+/* ---- progress reports: the eigensolver's events translated to singular-value terms and handed to
+ * primme_svds.monitorFun (monitorFunSVDS :1240-1320, default_monitor_svds :1775-1880,
+ * monitor_single_stage :1897-2020, monitor_stage1 :2035-2160, monitor_stage2 :2171-2280) ---- */
+static int svds_monitor(primme_svds_params *s, double *basisSvals, int basisSize, int *basisFlags, int *iblock,
+      int blockSize, double *basisNorms, int numConverged, double *lockedSvals, int numLocked, int *lockedFlags,
+      double *lockedNorms, int inner_its, double LSRes, const char *msg, double time, primme_event event, int stage) {
+   if (!s->monitorFun) return 0;
+   int err = 0;
+   s->monitorFun(basisSvals, &basisSize, basisFlags, iblock, &blockSize, basisNorms, &numConverged, lockedSvals,
+         &numLocked, lockedFlags, lockedNorms, inner_its >= 0 ? &inner_its : NULL, LSRes >= 0 ? &LSRes : NULL, msg, &time,
+         &event, &stage, s, &err);
+   return err ? -1 : 0;
+}
+
+static void default_monitor_svds(void *basisSvals_, int *basisSize, int *basisFlags, int *iblock, int *blockSize,
+      void *basisNorms_, int *numConverged, void *lockedSvals_, int *numLocked, int *lockedFlags, void *lockedNorms_,
+      int *inner_its, void *LSRes_, const char *msg, double *time, primme_event *event, int *stage,
+      primme_svds_params *s, int *err) {
+   (void)basisSize, (void)basisFlags, (void)inner_its;
+   double *basisSvals = (double *)basisSvals_, *basisNorms = (double *)basisNorms_;
+   double *lockedSvals = (double *)lockedSvals_, *lockedNorms = (double *)lockedNorms_, *LSRes = (double *)LSRes_;
+   FILE *f = s->outputFile;
+   *err = 0;
+   if (!f || !(s->procID == 0 || *event == primme_event_profile)) return;
+   switch (*event) {
+   case primme_event_outer_iteration:
+      if (s->printLevel >= 3)
+         for (int i = 0; i < *blockSize; i++)
+            fprintf(f, "OUT %" PRIMME_INT_P " conv %d blk %d MV %" PRIMME_INT_P " Sec %E SV %13E |r| %.3E stage %d\n",
+                  s->stats.numOuterIterations, *numConverged, i, s->stats.numMatvecs, s->stats.elapsedTime,
+                  basisSvals[iblock[i]], basisNorms[iblock[i]], *stage + 1);
+      break;
+   case primme_event_inner_iteration:
+      if (s->printLevel >= 4)
+         fprintf(f, "INN MV %" PRIMME_INT_P " Sec %e Sval %e Lin|r| %.3e SV|r| %.3e stage %d\n", s->stats.numMatvecs,
+               s->stats.elapsedTime, basisSvals[iblock[0]], *LSRes, basisNorms[iblock[0]], *stage + 1);
+      break;
+   case primme_event_converged:
+      if ((*stage == 0 && s->printLevel >= 2) || s->printLevel >= 5)
+         fprintf(f, "#Converged %d sval[ %d ]= %e norm %e Mvecs %" PRIMME_INT_P " Time %g stage %d\n", *numConverged,
+               iblock[0], basisSvals[iblock[0]], basisNorms[iblock[0]], s->stats.numMatvecs, s->stats.elapsedTime,
+               *stage + 1);
+      break;
+   case primme_event_locked:
+      if (s->printLevel >= 2)
+         fprintf(f, "Lock striplet[ %d ]= %e norm %.4e Mvecs %" PRIMME_INT_P " Time %.4e Flag %d stage %d\n",
+               *numLocked - 1, lockedSvals[*numLocked - 1], lockedNorms[*numLocked - 1], s->stats.numMatvecs,
+               s->stats.elapsedTime, lockedFlags[*numLocked - 1], *stage + 1);
+      break;
+   case primme_event_message:
+      if (s->printLevel >= 2 && msg) fprintf(f, "%s\n", msg);
+      break;
+   case primme_event_profile:
+      if (msg && time) {
+         if (s->printLevel >= 3 && *time < 0.0) fprintf(f, "entering in %s proc %d\n", msg, s->procID);
+         if (s->printLevel >= 2 && *time >= 0.0) fprintf(f, "time for %s : %g proc %d\n", msg, *time, s->procID);
+      }
+      break;
+   default: break;
+   }
+   fflush(f);
+}
+
+/* the running totals a report shows include the stage in progress (UPDATE_STATS around the call) */
+static primme_svds_stats stats_with_stage(primme_svds_params *s, const primme_params *primme) {
+   primme_svds_stats saved = s->stats;
+   s->stats.numOuterIterations += primme->stats.numOuterIterations;
+   s->stats.numRestarts += primme->stats.numRestarts;
+   s->stats.numMatvecs += primme->stats.numMatvecs * 2;
+   s->stats.numPreconds += primme->stats.numPreconds;
+   s->stats.numGlobalSum += primme->stats.numGlobalSum;
+   s->stats.numBroadcast += primme->stats.numBroadcast;
+   s->stats.volumeGlobalSum += primme->stats.volumeGlobalSum;
+   s->stats.volumeBroadcast += primme->stats.volumeBroadcast;
+   s->stats.numOrthoInnerProds += primme->stats.numOrthoInnerProds;
+   s->stats.elapsedTime += primme->stats.elapsedTime;
+   s->stats.timeMatvec += primme->stats.timeMatvec;
+   s->stats.timePrecond += primme->stats.timePrecond;
+   s->stats.timeOrtho += primme->stats.timeOrtho;
+   s->stats.timeGlobalSum += primme->stats.timeGlobalSum;
+   s->stats.timeBroadcast += primme->stats.timeBroadcast;
+   s->stats.lockingIssue += primme->stats.lockingIssue;
+   return saved;
+}
+
+static const char *profile_msg(primme_event event, const char *msg, int stage, char **owned) {
+   *owned = NULL;
+   if (event != primme_event_profile || !msg) return msg;
+   const size_t len = 12 + strlen(msg);
+   *owned = (char *)malloc(len);
+   if (!*owned) return msg;
+   snprintf(*owned, len, "~Sprimme%d%s", stage, msg);
+   return *owned;
+}
+
+#define MON_ARGS                                                                                                   \
+   void *basisEvals_, int *basisSize, int *basisFlags, int *iblock, int *blockSize, void *basisNorms_,             \
+         int *numConverged, void *lockedEvals_, int *numLocked, int *lockedFlags, void *lockedNorms_, int *inner_its, \
+         void *LSRes_, const char *msg, double *time, primme_event *event, primme_params *primme, int *err
+
+/* one-stage runs: values and norms of the basis and of the locked pairs in singular-value terms */
+static void monitor_single_stage(MON_ARGS) {
+   primme_svds_params *s = (primme_svds_params *)primme->matrix;
+   double *basisEvals = (double *)basisEvals_, *basisNorms = (double *)basisNorms_;
+   double *lockedEvals = (double *)lockedEvals_, *lockedNorms = (double *)lockedNorms_, *LSRes = (double *)LSRes_;
+   const int nb = basisEvals && basisSize ? *basisSize : 0, nl = lockedEvals && numLocked ? *numLocked : 0;
+   double *bs = (double *)calloc(2 * (size_t)PB_MAX(nb, 1), sizeof(double)), *bn = bs + PB_MAX(nb, 1);
+   double *ls = (double *)calloc(2 * (size_t)PB_MAX(nl, 1), sizeof(double)), *ln = ls + PB_MAX(nl, 1);
+   if (s->method != primme_svds_op_augmented) {
+      for (int i = 0; i < nb; i++) {
+         bs[i] = sqrt(fabs(basisEvals[i]));
+         bn[i] = bs[i] > 0.0 ? basisNorms[i] / bs[i] : basisNorms[i];
+      }
+      for (int i = 0; i < nl; i++) {
+         ls[i] = sqrt(fabs(lockedEvals[i]));
+         ln[i] = ls[i] > 0.0 ? lockedNorms[i] / ls[i] : lockedNorms[i];
+      }
+   } else {
+      /* the reference leaves the values of the augmented operator unset here (:1960-1975); they are
+       * the singular values themselves */
+      for (int i = 0; i < nb; i++) bs[i] = basisEvals[i], bn[i] = basisNorms ? basisNorms[i] / sqrt(2.0) : 0.0;
+      for (int i = 0; i < nl; i++) ls[i] = lockedEvals[i], ln[i] = lockedNorms[i] / sqrt(2.0);
+   }
+   char *owned;
+   msg = profile_msg(*event, msg, 0, &owned);
+   primme_svds_stats saved = stats_with_stage(s, primme);
+   *err = svds_monitor(s, bs, nb, basisFlags, iblock, blockSize ? *blockSize : 0, bn, numConverged ? *numConverged : 0, ls,
+                numLocked ? *numLocked : 0, lockedFlags, ln, inner_its ? *inner_its : 0, LSRes ? *LSRes : 0.0, msg,
+                time ? *time : 0.0, *event, 0)
+                ? 1
+                : 0;
+   s->stats = saved;
+   free(bs), free(ls), free(owned);
+}
+
+/* first stage of a two-stage run: locked pairs shown as converged pairs of the basis */
+static void monitor_stage1(MON_ARGS) {
+   primme_svds_params *s = (primme_svds_params *)primme->matrix;
+   double *basisEvals = (double *)basisEvals_, *basisNorms = (double *)basisNorms_;
+   double *lockedEvals = (double *)lockedEvals_, *lockedNorms = (double *)lockedNorms_, *LSRes = (double *)LSRes_;
+   *err = 0;
+   if (*event == primme_event_converged && primme->locking && primme->printLevel <= 4) return;
+   const int nl = lockedEvals && numLocked ? *numLocked : 0;
+   const int nb = (basisEvals && basisSize ? *basisSize : 0) + nl;
+   double *sv = (double *)calloc(2 * (size_t)PB_MAX(nb, 1), sizeof(double)), *sn = sv + PB_MAX(nb, 1);
+   int *fl = (int *)calloc((size_t)PB_MAX(nb, 1), sizeof(int));
+   int *ib = (int *)calloc((size_t)(blockSize && *blockSize > 0 ? *blockSize : 1), sizeof(int));
+   int j = 0;
+   for (int i = 0; i < nl; i++, j++) {
+      sv[j] = sqrt(fabs(lockedEvals[i]));
+      sn[j] = sv[i] > 0.0 ? lockedNorms[i] / sv[i] : lockedNorms[i];
+      fl[j] = lockedFlags[i];
+   }
+   for (int i = 0; i < nb - nl; i++, j++) {
+      sv[j] = sqrt(fabs(basisEvals[i]));
+      sn[j] = sv[i] > 0.0 ? basisNorms[i] / sv[i] : basisNorms[i]; /* sv[i], not sv[j]: as the reference (:2098) */
+      fl[j] = basisFlags ? basisFlags[i] : UNCONVERGED;
+   }
+   if (iblock && blockSize)
+      for (int i = 0; i < *blockSize; i++) ib[i] = iblock[i] + nl;
+   primme_event ev = *event;
+   if (ev == primme_event_locked) ev = primme_event_converged, ib[0] = *numLocked - 1;
+   char *owned;
+   msg = profile_msg(*event, msg, 0, &owned);
+   primme_svds_stats saved = stats_with_stage(s, primme);
+   *err = svds_monitor(s, sv, nb, fl, ib, blockSize ? *blockSize : 0, sn, numConverged ? *numConverged : nl, NULL, 0, NULL,
+                NULL, inner_its ? *inner_its : 0, LSRes ? *LSRes : 0.0, msg, time ? *time : 0.0, ev, 0)
+                ? 1
+                : 0;
+   s->stats = saved;
+   free(sv), free(fl), free(ib), free(owned);
+}
+
+/* second stage: the triplets the first stage converged count as locked */
+static void monitor_stage2(MON_ARGS) {
+   primme_svds_params *s = (primme_svds_params *)primme->matrix;
+   double *basisEvals = (double *)basisEvals_, *basisNorms = (double *)basisNorms_;
+   double *lockedEvals = (double *)lockedEvals_, *lockedNorms = (double *)lockedNorms_, *LSRes = (double *)LSRes_;
+   const int extra = lockedEvals && numLocked ? s->numSvals - primme->numEvals : 0;
+   const int nl = (lockedEvals && numLocked ? *numLocked : 0) + extra;
+   const int nb = basisEvals && basisSize ? *basisSize : 0;
+   double *bs = (double *)calloc(2 * (size_t)PB_MAX(nb, 1), sizeof(double)), *bn = bs + PB_MAX(nb, 1);
+   double *ls = (double *)calloc(2 * (size_t)PB_MAX(nl, 1), sizeof(double)), *ln = ls + PB_MAX(nl, 1);
+   int *lf = (int *)calloc((size_t)PB_MAX(nl, 1), sizeof(int));
+   for (int i = 0; i < nb; i++) bs[i] = basisEvals[i], bn[i] = basisNorms[i] / sqrt(2.0);
+   /* lockedEvals / lockedNorms point into the caller's svals / resNorms past the first stage's triplets */
+   if (lockedEvals) lockedEvals -= extra, lockedNorms -= extra;
+   for (int i = 0; i < extra; i++) ls[i] = lockedEvals[i], ln[i] = lockedNorms[i], lf[i] = CONVERGED;
+   for (int i = extra; i < nl; i++) ls[i] = lockedEvals[i], ln[i] = lockedNorms[i] / sqrt(2.0), lf[i] = lockedFlags[i - extra];
+   char *owned;
+   msg = profile_msg(*event, msg, 1, &owned);
+   primme_svds_stats saved = stats_with_stage(s, primme);
+   *err = svds_monitor(s, bs, nb, basisFlags, iblock, blockSize ? *blockSize : 0, bn, numConverged ? *numConverged : 0, ls, nl,
+                lf, ln, inner_its ? *inner_its : 0, LSRes ? *LSRes : 0.0, msg, time ? *time : 0.0, *event, 1)
+                ? 1
+                : 0;
+   s->stats = saved;
+   free(bs), free(ls), free(lf), free(owned);
+}
+
 static int svds_check_input(void *svals, void *svecs, void *resNorms, primme_svds_params *s) {
    if (!s) return -4;
    if (s->n < 0 || s->m < 0 || s->nLocal < 0 || s->mLocal < 0 || s->nLocal > s->n || s->mLocal > s->m) return -5;
@@ -844,12 +1044,25 @@ static int stage_begin(svds_run *run, int stage, double *svals, double *svecs, d
                    svecs + (size_t)N * primme->numOrthoConst, rnorms[i], (int)method, &isConv))
             return -1;
          if (!isConv) break;
+         /* reported as locked by the first stage */
+         {
+            int *flags = (int *)malloc(sizeof(int) * (size_t)(i + 1));
+            for (int t = 0; t <= i; t++) flags[t] = CONVERGED;
+            int e = svds_monitor(s, NULL, 0, NULL, NULL, 0, NULL, 0, svals, i + 1, flags, rnorms, 0, 0.0, NULL, 0.0,
+                  primme_event_locked, 0);
+            free(flags);
+            if (e) return -1;
+         }
          primme->numOrthoConst++;
          primme->initSize--;
          primme->numEvals--;
       }
    }
    if (s->locking >= 0) primme->locking = s->locking;
+   if (!primme->monitorFun) {
+      primme->monitorFun = s->methodStage2 == primme_svds_op_none ? monitor_single_stage : stage == 0 ? monitor_stage1 : monitor_stage2;
+      primme->monitorFun_type = primme_op_double;
+   }
    primme->queue = s->queue;
    primme->profile = s->profile;
    return 0;
@@ -978,6 +1191,10 @@ static int svds_solve(double *svals, double *svecs, double *resNorms, primme_svd
       s->convTestFun = default_conv_test_svds;
       s->convTestFun_type = primme_op_double;
       if (s->eps == 0.0) s->eps = PB_EPS * 1e4; /* after set_defaults, as in the reference (:427-434) */
+   }
+   if (!s->monitorFun) {
+      s->monitorFun = default_monitor_svds;
+      s->monitorFun_type = primme_op_double;
    }
    memset(&s->stats, 0, sizeof(s->stats));
 

@@ -20,6 +20,7 @@ ROOT = os.path.dirname(HERE)
 PRIMME_INT = C.c_int64
 
 # enums (reference include/primme_eigs.h:47-107,256-273)
+primme_proj_default, primme_proj_RR, primme_proj_harmonic, primme_proj_refined = range(4)
 primme_smallest, primme_largest, primme_closest_geq, primme_closest_leq, primme_closest_abs, primme_largest_abs = range(6)
 (PRIMME_DEFAULT_METHOD, PRIMME_DYNAMIC, PRIMME_DEFAULT_MIN_TIME, PRIMME_DEFAULT_MIN_MATVECS, PRIMME_Arnoldi,
  PRIMME_GD, PRIMME_GD_plusK, PRIMME_GD_Olsen_plusK, PRIMME_JD_Olsen_plusK, PRIMME_RQI, PRIMME_JDQR, PRIMME_JDQMR,
@@ -189,6 +190,8 @@ def new_params(lib, n, numEvals=1, target=primme_smallest, method=None, **kw):
     for key, val in kw.items():
         if key == "maxPrevRetain":
             p.restartingParams.maxPrevRetain = val
+        elif key == "projection":
+            p.projectionParams.projection = val
         elif key == "iseed":
             for i in range(4):
                 p.iseed[i] = val[i]

@@ -51,24 +51,27 @@ static int decomposition(const double *C, int n, int ldC, double *Y, int ldY, do
 }
 
 /* Append columns n0..n-1 to the Cholesky factor of VtBV (:1200-1220). */
-int pb_update_cholesky(pb_solver *S, int n0, int n) {
-   if (!S->fVtBV || n <= n0) return 0;
-   const int ld = S->maxRank;
+int pb_update_cholesky_gram(const double *G, double *fG, int ld, int n0, int n) {
+   if (!fG || n <= n0) return 0;
    double *A = (double *)malloc(sizeof(double) * (size_t)n * (n - n0));
    if (!A) return PRIMME_MALLOC_FAILURE;
-   hl_copy(&S->VtBV[(size_t)ld * n0], n, n - n0, ld, A, n);
-   hl_trsm('L', 'U', 'C', 'N', n0, n - n0, 1.0, S->fVtBV, ld, A, n);
+   hl_copy(&G[(size_t)ld * n0], n, n - n0, ld, A, n);
+   hl_trsm('L', 'U', 'C', 'N', n0, n - n0, 1.0, fG, ld, A, n);
    hl_gemm('C', 'N', n - n0, n - n0, n0, -1.0, A, n, A, n, 1.0, &A[n0], n);
    hl_potrf_upper(n - n0, &A[n0], n); /* failure is tolerated exactly as in the reference */
-   hl_copy(A, n, n - n0, n, &S->fVtBV[(size_t)ld * n0], ld);
+   hl_copy(A, n, n - n0, n, &fG[(size_t)ld * n0], ld);
    free(A);
    return 0;
+}
+
+int pb_update_cholesky(pb_solver *S, int n0, int n) {
+   return pb_update_cholesky_gram(S->VtBV, S->fVtBV, S->maxRank, n0, n);
 }
 
 /* ------------------------------------------------------------------------------------------
  * CGS with reorthogonalisation, device version (no Gram matrix carried).
  * ---------------------------------------------------------------------------------------- */
-static int ortho_cgs(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const double *locked,
+static int ortho_cgs(pb_solver *S, double *V, int64_t ldV, double *R, int ldR, int b1, int b2, const double *locked,
       int64_t ldLocked, int numLocked, double *RLocked, int ldRLocked, int *b2_out) {
    primme_params *primme = S->primme;
    const int maxNumOrthos = 3, maxNumRandoms = 10;
@@ -77,6 +80,7 @@ static int ortho_cgs(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const
    const double t0 = hl_wtime();
    int rc = 0;
 
+   if (R) hl_zero(&R[(size_t)ldR * b1], b2 + 1, b2 - b1 + 1, ldR); /* (:146-149) */
    if (RLocked) hl_zero(RLocked, numLocked, b2 - b1 + 1, ldRLocked);
    double *panel = (double *)calloc((size_t)(numLocked + b2 + 2), sizeof(double));
    double *coef = (double *)calloc((size_t)(numLocked + b2 + 2), sizeof(double));
@@ -86,10 +90,12 @@ static int ortho_cgs(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const
    for (int i = b1; i <= b2; i++) {
       double *v = V + (size_t)ldV * i;
       const int k = numLocked + i;
-      int nOrth = 0, randomizations = 0, updateR = RLocked ? 1 : 0, have_panel = 0;
+      int nOrth = 0, randomizations = 0, updateR = (R || RLocked) ? 1 : 0, have_panel = 0;
       double s0 = 0.0, s02 = 0.0, s1 = 0.0, s12 = 0.0;
       for (;;) {
          if (nOrth >= maxNumOrthos) {
+            /* the column is replaced: it no longer factors the input (:183-188) */
+            if (updateR && R) R[(size_t)ldR * i + i] = 0.0;
             updateR = 0;
             if (randomizations >= maxNumRandoms) goto done;
             rc = pb_fill_random(S, v, ldV, 1);
@@ -109,7 +115,9 @@ static int ortho_cgs(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const
             primme->stats.numOrthoInnerProds += k + 1;
          }
          if (nOrth == 1) s02 = panel[k];
-         if (updateR)
+         if (updateR && R)
+            for (int j = 0; j < i; j++) R[(size_t)ldR * i + j] += panel[numLocked + j];
+         if (updateR && RLocked)
             for (int j = 0; j < numLocked; j++) RLocked[(size_t)ldRLocked * (i - b1) + j] += panel[j];
          memcpy(coef, panel, sizeof(double) * k);
          /* v -= [locked V] * overlaps, then the overlaps and norm of the new v (:262-291) */
@@ -129,6 +137,7 @@ static int ortho_cgs(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const
          } else if (s1 <= tol * s0) {
             s0 = s1, s02 = s12; /* reorthogonalise */
          } else {
+            if (updateR && R) R[(size_t)ldR * i + i] = s1;
             double inv = 1.0 / s1;
             if (isfinite(inv)) {
                rc = pb200_dscale_columns(S->dev, S->n, &inv, v, ldV, 1);
@@ -151,6 +160,10 @@ done:
  * With S->VtBV: iterated CholQR/SVQB (:497-803); columns b1..b2 of the Gram matrix
  * [locked V]'[locked V] and of its Cholesky factor are updated.  Without: CGS.
  * ---------------------------------------------------------------------------------------- */
+static int ortho_block_gram(pb_solver *S, double *G, double *fG, int ldG, int maxRank, double *V, int64_t ldV,
+      double *R, int ldR, int b1, int b2, const double *locked, int64_t ldLocked, int numLocked, double *RLocked,
+      int ldRLocked, int *b2_out, const double *P0, int ldP0);
+
 int pb_ortho_block(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const double *locked,
       int64_t ldLocked, int numLocked, double *RLocked, int ldRLocked, int *b2_out) {
    return pb_ortho_block_p0(S, V, ldV, b1, b2, locked, ldLocked, numLocked, RLocked, ldRLocked, b2_out, NULL, 0);
@@ -159,14 +172,28 @@ int pb_ortho_block(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const d
 int pb_ortho_block_p0(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const double *locked,
       int64_t ldLocked, int numLocked, double *RLocked, int ldRLocked, int *b2_out, const double *P0,
       int ldP0) {
+   return ortho_block_gram(S, S->VtBV, S->fVtBV, S->maxRank, S->maxRank, V, ldV, NULL, 0, b1, b2, locked, ldLocked,
+         numLocked, RLocked, ldRLocked, b2_out, P0, ldP0);
+}
+
+/* ortho_block (ortho.c:477-493) of a second set of vectors with its own Gram matrix (or none: CGS), returning
+ * the factor R with input = output * R: the QR factorisation of (A - tau I) V kept by the refined extraction */
+int pb_ortho_block_R(pb_solver *S, double *Q, int64_t ldQ, double *QtQ, double *fQtQ, int ldQtQ, int maxRank,
+      double *R, int ldR, int b1, int b2, int *b2_out) {
+   return ortho_block_gram(S, QtQ, fQtQ, ldQtQ, maxRank, Q, ldQ, R, ldR, b1, b2, NULL, 0, 0, NULL, 0, b2_out, NULL, 0);
+}
+
+static int ortho_block_gram(pb_solver *S, double *G, double *fG, int ldG, int maxRank, double *V, int64_t ldV,
+      double *R, int ldR, int b1, int b2, const double *locked, int64_t ldLocked, int numLocked, double *RLocked,
+      int ldRLocked, int *b2_out, const double *P0, int ldP0) {
    primme_params *primme = S->primme;
    b2++; /* C range convention from here on */
    if (b2 <= b1) {
       *b2_out = b2;
       return 0;
    }
-   if (!S->VtBV)
-      return ortho_cgs(S, V, ldV, b1, b2 - 1, locked, ldLocked, numLocked, RLocked, ldRLocked, b2_out);
+   if (!G)
+      return ortho_cgs(S, V, ldV, R, ldR, b1, b2 - 1, locked, ldLocked, numLocked, RLocked, ldRLocked, b2_out);
 
    /* the device sweep handles at most 8 columns at a time: larger blocks (initial guesses,
     * re-orthogonalisation of the whole basis) go chunk by chunk */
@@ -174,8 +201,10 @@ int pb_ortho_block_p0(pb_solver *S, double *V, int64_t ldV, int b1, int b2, cons
       int cur = b1;
       while (cur < b2) {
          int hi = PB_MIN(cur + 8, b2), out = 0;
-         CHK(pb_ortho_block(S, V, ldV, cur, hi - 1, locked, ldLocked, numLocked,
-               RLocked ? RLocked + (size_t)ldRLocked * (cur - b1) : NULL, ldRLocked, &out));
+         CHK(ortho_block_gram(S, G, fG, ldG, maxRank, V, ldV, R, ldR, cur, hi - 1, locked, ldLocked, numLocked,
+               RLocked ? RLocked + (size_t)ldRLocked * (cur - b1) : NULL, ldRLocked, &out, NULL, 0));
+         /* chunk by chunk the factor is block upper triangular with 8-column blocks */
+         if (R) hl_zero(&R[(size_t)ldR * cur + hi], b2 - hi, hi - cur, ldR);
          if (out < hi) {
             *b2_out = out;
             return 0;
@@ -188,8 +217,7 @@ int pb_ortho_block_p0(pb_solver *S, double *V, int64_t ldV, int b1, int b2, cons
 
    const double eps_orth = PB_EPS;
    const double t0 = hl_wtime();
-   const int nb = b2 - b1, nVL = b1 + numLocked, ldG = S->maxRank;
-   double *G = S->VtBV, *fG = S->fVtBV;
+   const int nb = b2 - b1, nVL = b1 + numLocked;
    double *A = &G[(size_t)ldG * nVL]; /* new columns of the Gram matrix */
    int rc = 0;
 
@@ -198,10 +226,20 @@ int pb_ortho_block_p0(pb_solver *S, double *V, int64_t ldV, int b1, int b2, cons
    double *Y = (double *)malloc(sizeof(double) * nb * nb), *Yapply = (double *)malloc(sizeof(double) * nb * nb);
    double *C = (double *)malloc(sizeof(double) * nb * nb), *r = NULL;
    if (!D || !N || !GdA || !Y || !C || !Yapply) return PRIMME_MALLOC_FAILURE;
+   double *r_own = NULL;
+   int ldr = nb;
+   if (R) {
+      /* the diagonal block of R accumulates the rotations of the block itself (:556-580) */
+      hl_zero(&R[(size_t)ldR * b1], b1, nb, ldR);
+      r = &R[(size_t)ldR * b1 + b1], ldr = ldR;
+   }
    if (RLocked) {
       hl_zero(RLocked, numLocked, nb, ldRLocked);
-      r = (double *)calloc((size_t)nb * nb, sizeof(double));
-      for (int i = 0; i < nb; i++) r[(size_t)nb * i + i] = 1.0;
+      if (!r) r = r_own = (double *)malloc(sizeof(double) * (size_t)nb * nb);
+   }
+   if (r) {
+      hl_zero(r, nb, nb, ldr);
+      for (int i = 0; i < nb; i++) r[(size_t)ldr * i + i] = 1.0;
    }
 
    *b2_out = b2;
@@ -240,7 +278,7 @@ int pb_ortho_block_p0(pb_solver *S, double *V, int64_t ldV, int b1, int b2, cons
       primme->stats.numOrthoInnerProds += (double)nVL * nb + (double)nb * nb;
 
       /* stop one sweep after the block first looks well conditioned (:652-665) */
-      if (rank_estimation(G, nVL, numLocked + b2, S->maxRank, ldG) == numLocked + b2) {
+      if (rank_estimation(G, nVL, numLocked + b2, maxRank, ldG) == numLocked + b2) {
          if (its >= plus1) {
             int i;
             for (i = b1; i < b2 && fabs(G[(size_t)ldG * (numLocked + i) + numLocked + i] - 1.0) < .8; i++)
@@ -272,24 +310,25 @@ int pb_ortho_block_p0(pb_solver *S, double *V, int64_t ldV, int b1, int b2, cons
       if (rc) goto done;
       for (int i = 0; i < nb; i++) D[i] = sqrt(PB_MAX(D[i], eps_orth * nb));
 
-      if (RLocked) {
-         /* accumulate the rotations applied to the block (:718-757) */
-         hl_gemm('N', 'N', numLocked, nb, nb, 1.0, GdA, nVL > 0 ? nVL : 1, r, nb, 1.0, RLocked, ldRLocked);
+      /* accumulate the rotations applied to the block (:718-757) */
+      if (RLocked) hl_gemm('N', 'N', numLocked, nb, nb, 1.0, GdA, nVL > 0 ? nVL : 1, r, ldr, 1.0, RLocked, ldRLocked);
+      if (R) hl_gemm('N', 'N', b1, nb, nb, 1.0, &GdA[numLocked], nVL > 0 ? nVL : 1, r, ldr, 1.0, &R[(size_t)ldR * b1], ldR);
+      if (r) {
          for (int i = 0; i < nb; i++)
-            for (int j = 0; j < nb; j++) r[(size_t)nb * i + j] *= N[j];
+            for (int j = 0; j < nb; j++) r[(size_t)ldr * i + j] *= N[j];
          if (Yortho)
-            hl_gemm('C', 'N', nb, nb, nb, 1.0, Y, nb, r, nb, 0.0, C, nb);
+            hl_gemm('C', 'N', nb, nb, nb, 1.0, Y, nb, r, ldr, 0.0, C, nb);
          else {
             /* C = U * r */
             for (int j = 0; j < nb; j++)
                for (int i = 0; i < nb; i++) {
                   double s = 0.0;
-                  for (int l = i; l < nb; l++) s += Y[(size_t)nb * l + i] * r[(size_t)nb * j + l];
+                  for (int l = i; l < nb; l++) s += Y[(size_t)nb * l + i] * r[(size_t)ldr * j + l];
                   C[(size_t)nb * j + i] = s;
                }
          }
          for (int i = 0; i < nb; i++)
-            for (int j = 0; j < nb; j++) r[(size_t)nb * i + j] = D[j] * C[(size_t)nb * i + j];
+            for (int j = 0; j < nb; j++) r[(size_t)ldr * i + j] = D[j] * C[(size_t)nb * i + j];
       }
 
       /* fold the column scaling into Y (:760-772) */
@@ -302,11 +341,11 @@ int pb_ortho_block_p0(pb_solver *S, double *V, int64_t ldV, int b1, int b2, cons
       }
    }
 
-   b2 = rank_estimation(G, nVL, numLocked + b2, S->maxRank, ldG) - numLocked;
+   b2 = rank_estimation(G, nVL, numLocked + b2, maxRank, ldG) - numLocked;
    *b2_out = b2;
-   rc = pb_update_cholesky(S, nVL, numLocked + b2);
+   rc = pb_update_cholesky_gram(G, fG, ldG, nVL, numLocked + b2);
 done:
-   free(D), free(N), free(GdA), free(Y), free(Yapply), free(C), free(r);
+   free(D), free(N), free(GdA), free(Y), free(Yapply), free(C), free(r_own);
    primme->stats.timeOrtho += hl_wtime() - t0;
    return rc;
 }
@@ -345,14 +384,14 @@ int pb_ortho_single_iteration(pb_solver *S, const double *Q, int nQ, int64_t ldQ
  * and V(:,0:b1).  R (column stride 1 x 1 use only) receives the final norm or 0 if the vector
  * had to be replaced by a random one.  Returns 0 or -3.
  * ---------------------------------------------------------------------------------------- */
-int pb_ortho_local(double *V, int ldV, double *R, int b1, int b2, double *locked, int ldLocked,
+static int ortho_local_gen(double *V, int ldV, double *R, int ldR, int b1, int b2, double *locked, int ldLocked,
       int numLocked, int n, const double *B, int ldB, long long *iseed) {
    const int maxNumOrthos = 7, maxNumRandoms = 10;
    const double tol = sqrt(2.0) / 2.0, eps_orth = PB_EPS;
    double *overlaps = (double *)calloc((size_t)(b2 + 2 + numLocked), sizeof(double));
    double *Bx = (double *)malloc(sizeof(double) * (n > 0 ? n : 1));
    int ok = 1;
-   if (R) R[0] = 0.0; /* callers use ldR == 1, b1 == b2 == 0 */
+   if (R && b2 >= b1) hl_zero(&R[(size_t)ldR * b1], b2 + 1, b2 - b1 + 1, ldR); /* (:146-149) */
    for (int i = b1; i <= b2 && ok; i++) {
       double *v = &V[(size_t)ldV * i];
       int nOrth = 0, randomizations = 0, updateR = R ? 1 : 0, Bx_update = 0;
@@ -360,7 +399,7 @@ int pb_ortho_local(double *V, int ldV, double *R, int b1, int b2, double *locked
       for (;;) {
          if (nOrth >= maxNumOrthos) {
             if (updateR) {
-               if (R) R[0] = 0.0;
+               if (R) R[(size_t)ldR * i + i] = 0.0;
                updateR = 0;
             }
             if (randomizations >= maxNumRandoms) {
@@ -386,6 +425,8 @@ int pb_ortho_local(double *V, int ldV, double *R, int b1, int b2, double *locked
          if (numLocked > 0)
             hl_gemm('C', 'N', numLocked, 1, n, 1.0, locked, ldLocked, bx, n, 0.0, &overlaps[i], numLocked);
          overlaps[i + numLocked] = s02;
+         if (updateR && R)
+            for (int j = 0; j < i; j++) R[(size_t)ldR * i + j] += overlaps[j]; /* (:226-229) */
          if (numLocked > 0)
             hl_gemm('N', 'N', n, 1, numLocked, -1.0, locked, ldLocked, &overlaps[i], numLocked, 1.0, v, n);
          if (i > 0) hl_gemm('N', 'N', n, 1, i, -1.0, V, ldV, overlaps, i, 1.0, v, n);
@@ -405,7 +446,7 @@ int pb_ortho_local(double *V, int ldV, double *R, int b1, int b2, double *locked
          } else if (s1 <= tol * s0 || nOrth < maxNumOrthos) {
             s0 = s1, s02 = s12;
          } else {
-            if (updateR && R) R[0] = s1;
+            if (updateR && R) R[(size_t)ldR * i + i] = s1;
             double inv = 1.0 / s1;
             if (isfinite(inv)) {
                for (int t = 0; t < n; t++) v[t] *= inv;
@@ -417,4 +458,16 @@ int pb_ortho_local(double *V, int ldV, double *R, int b1, int b2, double *locked
    }
    free(overlaps), free(Bx);
    return ok ? 0 : -3;
+}
+
+int pb_ortho_local(double *V, int ldV, double *R, int b1, int b2, double *locked, int ldLocked,
+      int numLocked, int n, const double *B, int ldB, long long *iseed) {
+   return ortho_local_gen(V, ldV, R, 1, b1, b2, locked, ldLocked, numLocked, n, B, ldB, iseed);
+}
+
+/* same with the full factor: V(:,b1..b2) = V_out * R(:,b1..b2), R with leading dimension ldR */
+int pb_ortho_local_R(double *V, int ldV, double *R, int ldR, int b1, int b2, int n, const double *B, int ldB,
+      long long *iseed) {
+   if (b2 < b1) return 0;
+   return ortho_local_gen(V, ldV, R, ldR, b1, b2, NULL, 0, 0, n, B, ldB, iseed);
 }

@@ -520,7 +520,7 @@ static int restart_locking(pb_solver *S, int *restartSize, int basisSize, int *r
 /* ------------------------------------------------------------------------------------------
  * Projected matrices after the restart (restart.c:1614-1735, RR only)
  * ---------------------------------------------------------------------------------------- */
-static int compute_submatrix(const double *X, int nX, int ldX, const double *H, int nH, int ldH,
+int pb_compute_submatrix(const double *X, int nX, int ldX, const double *H, int nH, int ldH,
       double *R, int ldR) {
    if (nH == 0 || nX == 0) return 0;
    double *rw = (double *)calloc((size_t)nH * nX, sizeof(double));
@@ -541,7 +541,7 @@ static int restart_RR(pb_solver *S, int restartSize, int basisSize, int numConve
    if (primme->orth == primme_orth_implicit_I) {
       /* H = diag(hVals) except the block of the retained directions (:1636-1664) */
       double *sub = (double *)calloc((size_t)(numPrevRetained > 0 ? numPrevRetained : 1) * (numPrevRetained > 0 ? numPrevRetained : 1), sizeof(double));
-      compute_submatrix(&hVecs[(size_t)ldh * indexOfPreviousVecs], numPrevRetained, ldh, H,
+      pb_compute_submatrix(&hVecs[(size_t)ldh * indexOfPreviousVecs], numPrevRetained, ldh, H,
             basisSize, ldH, sub, numPrevRetained > 0 ? numPrevRetained : 1);
       hl_zero(H, restartSize, restartSize, ldH);
       for (j = 0; j < numPrevRetained; j++)
@@ -641,6 +641,7 @@ int pb_restart(pb_solver *S, int basisSize, int *ievSize, double *evals, double 
 
    int indexOfPreviousVecs =
          primme->locking ? restartSize + *numConverged - *numLocked : restartSize;
+   const int indexOfPreviousVecsBeforeRestart = indexOfPreviousVecs;
    const int nLocked = primme->numOrthoConst + *numLocked;
    CHK(ortho_coefficient_vectors(S, basisSize, indexOfPreviousVecs,
          S->VtBV ? &S->VtBV[(size_t)S->maxRank * nLocked + nLocked] : NULL, nprevhVecs,
@@ -678,7 +679,10 @@ int pb_restart(pb_solver *S, int basisSize, int *ievSize, double *evals, double 
       S->numPrevRitzVals = restartSize;
    }
 
-   if (!rc)
+   if (!rc && S->refined)
+      rc = pb_restart_refined(S, restartSize, basisSize, *numConverged, numPrevRetained, indexOfPreviousVecs,
+            indexOfPreviousVecsBeforeRestart, restartPerm, hVecsPerm, targetShiftIndex);
+   else if (!rc)
       rc = restart_RR(S, restartSize, basisSize, *numConverged, numPrevRetained,
             indexOfPreviousVecs, hVecsPerm, targetShiftIndex);
    free(restartPerm);

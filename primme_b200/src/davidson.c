@@ -22,6 +22,13 @@
 
 #define VtBV_BLK(S, off) ((S)->VtBV ? &(S)->VtBV[(size_t)(S)->maxRank * (off) + (off)] : NULL)
 
+/* solve_H (solve_projection.c:95-154): Rayleigh-Ritz pairs of (H, V'V) or the refined vectors from R */
+static int solve_projected(pb_solver *S, int basisSize, int nLocked, int numConverged) {
+   if (S->refined) return pb_solve_H_ref(S, basisSize, VtBV_BLK(S, nLocked), S->maxRank, numConverged);
+   return pb_solve_H(S, S->H, S->maxBasis, basisSize, VtBV_BLK(S, nLocked), S->maxRank, S->hVecs, S->maxBasis, S->hVals,
+         numConverged, 1);
+}
+
 /* ------------------------------------------------------------------------------------------
  * Initial basis (init.c:125-323)
  * ---------------------------------------------------------------------------------------- */
@@ -232,9 +239,12 @@ static int prepare_candidates(pb_solver *S, int basisSize, double *X, double *R,
          lasti = iev[blki];
       }
 
-      /* next candidates after the last pair visited (:1629-1643; prepare_vecs is a no-op for
-       * Rayleigh-Ritz) */
+      /* well conditioned coefficient vectors for the next candidates (prepare_vecs: a no-op for
+       * Rayleigh-Ritz), then the candidates after the last pair visited (:1629-1643) */
       blki = *blockSize;
+      rc = pb_prepare_vecs(S, basisSize, lasti + 1, maxBlockSize - blki, targetShiftIndex, &S->numArbitraryVecs,
+            *smallestResNorm, flags, 1);
+      if (rc) goto done;
       for (i = lasti + 1; i < basisSize && blki < maxBlockSize; i++)
          if (flags[i] == UNCONVERGED) iev[blki++] = i;
       if (blki == *blockSize || *recentlyConverged >= remainedEvals) break;
@@ -342,6 +352,8 @@ static int solve_correction(pb_solver *S, double *evals, int numLocked, int basi
          int si = ilev[b];
          if (fabs(sorted[si] - t) < blockNorms[b] * sqrtInvB)
             shifts[b] = t;
+         else if (S->refined)
+            shifts[b] = sorted[si]; /* |Ritz value - target| <= singular value: trusted earlier (:226-228) */
          else
             shifts[b] = sorted[si] + (blockNorms[b] * sqrtInvB) * (t - sorted[si]) / fabs(t - sorted[si]);
          olsenEps[b] = si < S->numPrevRitzVals ? fabs(prevRitzVals[si] - sorted[si])
@@ -571,10 +583,15 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
       reset = 0;
       for (i = 0; i < maxBasis; i++) flags[i] = UNCONVERGED;
       targetShiftIndex = 0;
+      if (S->refined) {
+         int nQ = 0;
+         CHK(pb_update_Q(S, primme->targetShifts[targetShiftIndex], 0, basisSize, &nQ));
+         if (basisSize != nQ) return PRIMME_UNEXPECTED_FAILURE; /* "Not supported deficient QR" (:466) */
+      }
 
       CHK(pb_update_projection(S, 0, basisSize));
-      CHK(pb_solve_H(S, S->H, ldh, basisSize, VtBV_BLK(S, primme->numOrthoConst + numLocked),
-            S->maxRank, S->hVecs, ldh, S->hVals, numConverged, 1));
+      CHK(solve_projected(S, basisSize, primme->numOrthoConst + numLocked, numConverged));
+      S->numArbitraryVecs = 0;
 
       maxRecentlyConverged = availableBlockSize = blockSize = 0;
       smallestResNorm = HUGE_VAL;
@@ -598,8 +615,14 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
 
             primme->stats.numOuterIterations++;
 
-            availableBlockSize = primme->maxBlockSize;
-            maxRecentlyConverged = PB_MAX(0, primme->numEvals - numConverged);
+            if (primme->numTargetShifts > numConverged + 1 && S->refined) {
+               /* one pair at a time while the QR factorisation depends on the shift (:525-528) */
+               availableBlockSize = 1;
+               maxRecentlyConverged = numConverged - numLocked + 1;
+            } else {
+               availableBlockSize = primme->maxBlockSize;
+               maxRecentlyConverged = PB_MAX(0, primme->numEvals - numConverged);
+            }
             availableBlockSize = PB_MIN(availableBlockSize, maxBasis - basisSize);
             availableBlockSize = PB_MIN(availableBlockSize, maxRecentlyConverged + 1);
 
@@ -655,8 +678,12 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
 
             if (numConverged >= primme->numEvals ||
                   (primme->locking && numConverged > numLocked &&
-                        primme->target != primme_smallest && primme->target != primme_largest) ||
+                        primme->target != primme_smallest && primme->target != primme_largest &&
+                        (!S->refined || primme->target == primme_closest_geq || primme->target == primme_closest_leq)) ||
                   targetShiftIndex < 0 || (blockSize == 0 && recentlyConverged > 0) ||
+                  (S->refined && fabs(primme->targetShifts[targetShiftIndex] -
+                                       primme->targetShifts[PB_MIN(primme->numTargetShifts - 1, numConverged)]) >=
+                                       PB_MAX(primme->aNorm, primme->stats.estimateLargestSVal)) ||
                   (numConverged >= nextGuess - primme->numOrthoConst && numGuesses > 0)) {
                break;
             }
@@ -730,13 +757,23 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
                free(Rlocked);
                Rlocked = NULL;
                if (numConverged > numLocked && primme->target != primme_smallest &&
-                     primme->target != primme_largest)
+                     primme->target != primme_largest &&
+                     (!S->refined || primme->target == primme_closest_geq || primme->target == primme_closest_leq))
                   break;
             }
 
             /* W(:,new) = A V(:,new);  H(:,new) = V' W(:,new) */
             CHK(pb_apply_matvec(S, S->V + (size_t)S->ld * basisSize, S->ld,
                   S->W + (size_t)S->ld * basisSize, S->ld, blockSize));
+            if (S->refined) {
+               int nQ = basisSize;
+               CHK(pb_update_Q(S, primme->targetShifts[targetShiftIndex], basisSize, blockSize, &nQ));
+               if (basisSize + blockSize != nQ) {
+                  blockSize = 0;
+                  reset = 1;
+                  break;
+               }
+            }
             CHK(pb_update_projection(S, basisSize, blockSize));
 
             hl_copy(S->hVecs, basisSize, basisSize, ldh, S->prevhVecs, ldh);
@@ -746,10 +783,19 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
             basisSize += blockSize;
             blockSize = 0;
 
-            CHK(pb_solve_H(S, S->H, ldh, basisSize,
-                  VtBV_BLK(S, primme->numOrthoConst + numLocked), S->maxRank, S->hVecs, ldh,
-                  S->hVals, numConverged, 1));
+            CHK(solve_projected(S, basisSize, primme->numOrthoConst + numLocked, numConverged));
+            S->numArbitraryVecs = 0;
             candidates_prepared = 0;
+
+            /* |l_0 - tau| <= s_0 must hold for the smallest triplet of R: otherwise the factorisation has
+             * accumulated too much error and is rebuilt (:852-884) */
+            if (S->refined && basisSize > 0 && restartsSinceReset > 1 && targetShiftIndex >= 0 &&
+                  fabs(primme->targetShifts[targetShiftIndex] - S->hVals[0]) -
+                              PB_MAX(primme->aNorm, primme->stats.estimateLargestSVal) * PB_EPS >
+                        S->hSVals[0]) {
+               reset = 2;
+               break;
+            }
          } /* expansion loop */
 
          if (basisSize >= primme->n - primme->numOrthoConst - numLocked) {
@@ -781,7 +827,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
 
             if (availableBlockSize <= 0 ||
                   primme->minRestartSize + primme->restartingParams.maxPrevRetain + availableBlockSize < maxBasis ||
-                  primme->numOrthoConst + numLocked + basisSize >= primme->n) {
+                  primme->numOrthoConst + numLocked + basisSize >= primme->n || S->refined) {
                double dummyZero = 0.0;
                double *srn = (primme->target == primme_closest_abs || primme->target == primme_largest_abs)
                                    ? &dummyZero
@@ -789,6 +835,11 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
                CHK(prepare_candidates(S, basisSize, NULL, NULL, 0, maxRecentlyConverged, blockSize,
                      availableBlockSize, numLocked, evals, resNorms, targetShiftIndex, &blockSize,
                      &recentlyConverged, srn, numConverged, &reset, nprevhVecs, 0));
+
+               /* with several shifts, a pair that converged may be the closest to another target: no
+                * candidates for the next iteration (:1003-1006) */
+               if (S->refined && numConverged + recentlyConverged > numLocked && primme->numTargetShifts > numLocked + 1)
+                  blockSize = 0;
 
                for (i = 0, numConverged = numLocked; i < basisSize; i++)
                   if (flags[i] != UNCONVERGED && numConverged < primme->numEvals &&
@@ -811,6 +862,14 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
                hl_permute_cols(S->hVals, 1, basisSize, 1, iwork);
                hl_permute_cols(S->hVecs, basisSize, basisSize, ldh, iwork);
                hl_permute_ints(flags, basisSize, iwork);
+               if (S->hVecsRot) {
+                  hl_zero(&S->hVecsRot[(size_t)ldh * S->numArbitraryVecs], maxBasis, basisSize - S->numArbitraryVecs, ldh);
+                  for (i = S->numArbitraryVecs; i < basisSize; i++) S->hVecsRot[(size_t)ldh * i + i] = 1.0;
+                  hl_permute_cols(S->hVecsRot, basisSize, basisSize, ldh, iwork);
+                  for (i = j = 0; i < basisSize; i++)
+                     if (iwork[i] != i) j = i + 1;
+                  S->numArbitraryVecs = PB_MAX(S->numArbitraryVecs, j);
+               }
                free(iwork);
             } else {
                blockSize = availableBlockSize;
@@ -850,11 +909,15 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
             numNew = basisSizeOut - basisSize;
             CHK(pb_apply_matvec(S, S->V + (size_t)S->ld * basisSize, S->ld,
                   S->W + (size_t)S->ld * basisSize, S->ld, numNew));
+            if (S->refined) {
+               int nQ = basisSize;
+               CHK(pb_update_Q(S, primme->targetShifts[targetShiftIndex], basisSize, numNew, &nQ));
+               if (basisSize + numNew != nQ) return PRIMME_UNEXPECTED_FAILURE;
+            }
             CHK(pb_update_projection(S, basisSize, numNew));
             basisSize += numNew;
-            CHK(pb_solve_H(S, S->H, ldh, basisSize,
-                  VtBV_BLK(S, primme->numOrthoConst + numLocked), S->maxRank, S->hVecs, ldh,
-                  S->hVals, numConverged, 1));
+            CHK(solve_projected(S, basisSize, primme->numOrthoConst + numLocked, numConverged));
+            if (numNew > 0) S->numArbitraryVecs = 0;
          }
 
          primme->stats.numRestarts++;

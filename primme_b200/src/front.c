@@ -315,7 +315,7 @@ static int check_input(void *evals, void *evecs, void *resNorms, primme_params *
 static int check_scope(primme_params *p) {
    const char *why = NULL;
    if (p->massMatrixMatvec) why = "generalized problems (massMatrixMatvec)";
-   else if (p->projectionParams.projection != primme_proj_RR) why = "harmonic/refined extraction";
+   else if (p->projectionParams.projection == primme_proj_harmonic) why = "harmonic extraction";
    else if (p->internalPrecision != primme_op_default && p->internalPrecision != primme_op_double)
       why = "internalPrecision other than double";
    else if ((p->matrixMatvec_type != primme_op_default && p->matrixMatvec_type != primme_op_double) ||
@@ -341,6 +341,8 @@ static void free_solver(pb_solver *S, int own_evecs) {
    }
    free(S->hstage), free(S->hstage2);
    free(S->H), free(S->hVecs), free(S->prevhVecs), free(S->VtBV), free(S->fVtBV), free(S->fusedP);
+   free(S->R), free(S->hU), free(S->hVecsRot), free(S->QtQ), free(S->fQtQ), free(S->hSVals);
+   if (S->dev && S->Q) pb200_free(S->dev, S->Q);
    if (S->dev && S->jd_work) pb200_free(S->dev, S->jd_work);
    free(S->hVals), free(S->prevRitzVals), free(S->blockNorms), free(S->basisNorms);
    free(S->flags), free(S->map), free(S->iev), free(S->perm), free(S->lockedFlags);
@@ -457,6 +459,20 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
       S->VtBV = (double *)calloc((size_t)mr * mr, sizeof(double));
       S->fVtBV = (double *)calloc((size_t)mr * mr, sizeof(double));
    }
+   S->refined = primme->projectionParams.projection == primme_proj_refined;
+   if (S->refined) {
+      /* Q next to V and W, its small factors on the host (main_iter.c:284-320) */
+      if (!rc) rc = pb200_malloc(S->dev, basis_bytes, (void **)&S->Q);
+      S->R = (double *)calloc((size_t)mb * mb, sizeof(double));
+      S->hU = (double *)calloc((size_t)mb * mb, sizeof(double));
+      S->hVecsRot = (double *)calloc((size_t)mb * mb, sizeof(double));
+      S->hSVals = (double *)calloc(mb, sizeof(double));
+      if (primme->orth == primme_orth_explicit_I) {
+         S->QtQ = (double *)calloc((size_t)mb * mb, sizeof(double));
+         S->fQtQ = (double *)calloc((size_t)mb * mb, sizeof(double));
+      }
+      if (!S->R || !S->hU || !S->hVecsRot || !S->hSVals) rc = PRIMME_MALLOC_FAILURE;
+   }
    S->hVals = (double *)calloc(mb, sizeof(double));
    S->prevRitzVals = (double *)calloc(mb + primme->numEvals, sizeof(double));
    S->blockNorms = (double *)calloc(PB_MAX(primme->maxBlockSize, 1), sizeof(double));
@@ -473,7 +489,8 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
          /* V and W belong to the attached context (pb200_ctx_workspace) */
          if (own_evecs) pb200_free(S->dev, S->evecs);
          if (S->jd_work) pb200_free(S->dev, S->jd_work);
-         S->V = S->W = S->evecs = S->jd_work = NULL;
+         if (S->Q) pb200_free(S->dev, S->Q);
+         S->V = S->W = S->evecs = S->jd_work = S->Q = NULL;
          S->dev = NULL;
       }
       free_solver(S, own_evecs);
@@ -510,7 +527,8 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
       /* V and W belong to the attached context (pb200_ctx_workspace) */
       if (own_evecs) pb200_free(S->dev, S->evecs);
       if (S->jd_work) pb200_free(S->dev, S->jd_work);
-      S->V = S->W = S->evecs = S->jd_work = NULL;
+      if (S->Q) pb200_free(S->dev, S->Q);
+      S->V = S->W = S->evecs = S->jd_work = S->Q = NULL;
       S->dev = NULL;
    }
    free_solver(S, own_evecs);

@@ -14,6 +14,10 @@ extern void dsymm_(const char *, const char *, const int *, const int *, const d
 extern void dtrsm_(const char *, const char *, const char *, const char *, const int *,
       const int *, const double *, const double *, const int *, double *, const int *);
 extern void dpotrf_(const char *, const int *, double *, const int *, int *);
+extern void dtrmm_(const char *, const char *, const char *, const char *, const int *,
+      const int *, const double *, const double *, const int *, double *, const int *);
+extern void dgesvd_(const char *, const char *, const int *, const int *, double *, const int *, double *,
+      double *, const int *, double *, const int *, double *, const int *, int *);
 extern void dsyevx_(const char *, const char *, const char *, const int *, double *, const int *,
       const double *, const double *, const int *, const int *, const double *, int *, double *,
       double *, const int *, double *, const int *, int *, int *, int *);
@@ -119,6 +123,30 @@ int hl_sygv_upper(int n, double *A, int lda, const double *B, int ldb, double *w
    }
    if (info == 0) hl_copy(z, n, n, n, A, lda);
    free(z), free(iwork), free(ifail), free(b);
+   return info;
+}
+
+void hl_trmm(char side, char uplo, char trans, char diag, int m, int n, double alpha, const double *A,
+      int lda, double *B, int ldb) {
+   if (m == 0 || n == 0) return;
+   dtrmm_(&side, &uplo, &trans, &diag, &m, &n, &alpha, A, &lda, B, &ldb);
+}
+
+/* dgesvd jobu = 'S', jobvt = 'O' (reference Num_gesvd, blaslapack.c:1350-1403, as called by
+ * solve_H_Ref): on return U holds the left singular vectors, A the transposed right ones, s the
+ * singular values in descending order.  Workspace from the query, like the reference. */
+int hl_gesvd_SO(int m, int n, double *A, int lda, double *s, double *U, int ldu) {
+   if (m == 0 || n == 0) return 0;
+   int info = 0, lwork = -1;
+   double wq = 0.0;
+   dgesvd_("S", "O", &m, &n, A, &lda, s, U, &ldu, A, &lda, &wq, &lwork, &info);
+   if (info == 0) {
+      lwork = (int)wq;
+      if (lwork < 1) lwork = 1;
+      double *work = (double *)malloc(sizeof(double) * lwork);
+      dgesvd_("S", "O", &m, &n, A, &lda, s, U, &ldu, A, &lda, work, &lwork, &info);
+      free(work);
+   }
    return info;
 }
 

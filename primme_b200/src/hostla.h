@@ -32,7 +32,11 @@ void hl_symm_lu(int m, int n, double alpha, const double *A, int lda, const doub
       double beta, double *C, int ldc);
 void hl_trsm(char side, char uplo, char trans, char diag, int m, int n, double alpha,
       const double *A, int lda, double *B, int ldb);
+void hl_trmm(char side, char uplo, char trans, char diag, int m, int n, double alpha,
+      const double *A, int lda, double *B, int ldb);
 int hl_potrf_upper(int n, double *A, int lda); /* returns LAPACK info */
+/* singular value decomposition, left vectors in U, transposed right vectors overwrite A */
+int hl_gesvd_SO(int m, int n, double *A, int lda, double *s, double *U, int ldu);
 /* eigen-decomposition of the symmetric matrix stored in the upper triangle of A (n x n, lda);
  * on return A holds the eigenvectors, w ascending eigenvalues.  B != NULL: generalized problem
  * A x = w B x (upper triangle of B referenced, B not modified).  Returns LAPACK info. */

@@ -64,6 +64,13 @@ typedef struct pb_solver {
    /* inner QMR solver (JDQMR family): g, d, delta, w, sol -- 5 x ld x maxBlockSize, device */
    double *jd_work;
    int touch; /* stopping-criterion state of the inner solver (main_iter.c:206,597-599) */
+   /* refined extraction (dav_refined.c): (A - tau I) V = Q R next to V and W */
+   int refined;
+   double *Q;          /* device, ld x maxBasisSize */
+   double *R, *hU, *hVecsRot; /* maxBasis x maxBasis */
+   double *QtQ, *fQtQ; /* Q'Q and its Cholesky factor when orth is explicit, else NULL */
+   double *hSVals;     /* singular values of R */
+   int numArbitraryVecs;
    pb_cost_model cost; /* PRIMME_DYNAMIC */
    double tstart;      /* start of the last correction / restart evaluation (main_iter.c:260,655,1182) */
 } pb_solver;
@@ -115,11 +122,26 @@ int pb_ortho_block_p0(pb_solver *S, double *V, int64_t ldV, int b1, int b2, cons
       int64_t ldLocked, int numLocked, double *RLocked, int ldRLocked, int *b2_out, const double *P0,
       int ldP0);
 int pb_update_cholesky(pb_solver *S, int n0, int n);
+int pb_update_cholesky_gram(const double *G, double *fG, int ld, int n0, int n);
+int pb_ortho_block_R(pb_solver *S, double *Q, int64_t ldQ, double *QtQ, double *fQtQ, int ldQtQ, int maxRank,
+      double *R, int ldR, int b1, int b2, int *b2_out);
 int pb_ortho_single_iteration(pb_solver *S, const double *Q, int nQ, int64_t ldQ,
       const double *QtQ, int ldQtQ, double *X, const int *inX, int nX, int64_t ldX,
       double *norms);
 int pb_ortho_local(double *V, int ldV, double *R, int b1, int b2, double *locked, int ldLocked,
       int numLocked, int n, const double *B, int ldB, long long *iseed);
+
+/* dav_refined.c */
+int pb_update_Q(pb_solver *S, double shift, int basisSize, int blockSize, int *nQ);
+int pb_solve_H_ref(pb_solver *S, int n, const double *VtBVblk, int ldVtBV, int numConverged);
+int pb_prepare_vecs(pb_solver *S, int basisSize, int i0, int blockSize, int targetShiftIndex, int *arbitraryVecs,
+      double smallestResNorm, const int *flags, int RRForAll);
+int pb_restart_refined(pb_solver *S, int restartSize, int basisSize, int numConverged, int numPrevRetained,
+      int indexOfPreviousVecs, int indexOfPreviousVecsBeforeRestart, const int *restartPerm, const int *hVecsPerm,
+      int *targetShiftIndex);
+int pb_compute_submatrix(const double *X, int nX, int ldX, const double *H, int nH, int ldH, double *R, int ldR);
+int pb_ortho_local_R(double *V, int ldV, double *R, int ldR, int b1, int b2, int n, const double *B, int ldB,
+      long long *iseed);
 
 /* dav_dynamic.c */
 void pb_dyn_init(pb_cost_model *m, primme_params *primme);

@@ -903,12 +903,9 @@ static int svds_out_of_scope(primme_svds_params *s) {
                s->applyPreconditioner_type != primme_op_double) ||
          (s->internalPrecision != primme_op_default && s->internalPrecision != primme_op_double))
       why = "callbacks / internal precision other than double";
-   else if ((s->method != primme_svds_op_none && s->primme.projectionParams.projection != primme_proj_default &&
-                  s->primme.projectionParams.projection != primme_proj_RR) ||
-            (s->methodStage2 != primme_svds_op_none && s->primmeStage2.projectionParams.projection != primme_proj_default &&
-                  s->primmeStage2.projectionParams.projection != primme_proj_RR))
-      /* known before the first stage runs: smallest / closest_abs on the augmented operator */
-      why = "refined / harmonic extraction (augmented operator with smallest or closest_abs targets)";
+   else if ((s->method != primme_svds_op_none && s->primme.projectionParams.projection == primme_proj_harmonic) ||
+            (s->methodStage2 != primme_svds_op_none && s->primmeStage2.projectionParams.projection == primme_proj_harmonic))
+      why = "harmonic extraction"; /* known before the first stage runs */
    if (!why) return 0;
    if (s->outputFile && s->printLevel > 0)
       fprintf(s->outputFile, "PRIMME-B200: %s is outside the scope of this build\n", why);

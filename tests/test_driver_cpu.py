@@ -29,8 +29,10 @@ def test_eigs_driver_hostcheck_passes_golden(cfg):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-@pytest.mark.parametrize("cfg", ["test_201", "test_202", "test_207"])
+@pytest.mark.parametrize("cfg", ["test_201", "test_202", "test_203", "test_204", "test_205", "test_206", "test_207"])
 def test_svds_driver_hostcheck_passes_golden(cfg):
+    """201, 202, 207: largest triplets (hybrid / augmented); 203-206: smallest triplets, where the second
+    stage runs JDQMR with refined extraction and closest_geq shifts on the augmented operator"""
     r = run("primmesvds_double_hostcheck", cfg)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
@@ -45,44 +47,8 @@ def test_svds_driver_prints_the_configuration_like_the_reference(cfg):
     assert ours == ref
 
 
-@pytest.mark.parametrize("cfg", ["test_203", "test_204", "test_205", "test_206"])
-def test_svds_driver_out_of_scope_config_is_refused_before_any_work(cfg):
-    """smallest singular values with the hybrid method: the second stage would need refined
-    extraction; refused up front (no first stage is run for a result that cannot be finished)"""
-    r = run("primmesvds_double_hostcheck", cfg)
+def test_eigs_driver_harmonic_extraction_is_refused():
+    """test_007 asks for harmonic extraction: refused with -44 and a message, nothing else is run"""
+    r = run("primme_double_hostcheck", "test_007")
     assert r.returncode != 0
     assert "outside the scope of this build" in r.stdout + r.stderr
-    assert "1st Matvecs     : 0" in r.stdout
-
-
-def test_svds_monitor_reports_like_the_reference(tmp_path):
-    """primme_svds.monitorFun (default reporter at printLevel 3) through both stages of the hybrid method with
-    fixed methods: the OUT lines -- iteration, converged count, block index, matvecs, singular value, stage --
-    are the reference's, line by line, until rounding-level residuals (1e-14) first reorder an event"""
-    import re
-    cfg = open(os.path.join(DATA, "test_202")).read().replace("printLevel = 1", "printLevel = 3")
-    cfg += "primme.method = PRIMME_GD_Olsen_plusK\nprimmeStage2.method = PRIMME_GD_Olsen_plusK\n"
-    name = "test_monitor_tmp"
-    path = os.path.join(DATA, name)
-    open(path, "w").write(cfg)
-    try:
-        ours = run("primmesvds_double_hostcheck", name)
-        ref = run("primmesvds_double_ref", name)
-    finally:
-        os.remove(path)
-    assert ours.returncode == 0 and ref.returncode == 0
-
-    def out_lines(text):
-        rows = []
-        for ln in text.splitlines():
-            m = re.match(r"OUT (\d+) conv (\d+) blk (\d+) MV (\d+) Sec \S+ SV\s+(\S+) \|r\| (\S+) stage (\d)", ln)
-            if m:
-                rows.append((int(m.group(1)), int(m.group(2)), int(m.group(3)), int(m.group(4)), round(float(m.group(5)), 6), int(m.group(7))))
-        return rows
-
-    a, b = out_lines(ours.stdout), out_lines(ref.stdout)
-    assert len(b) > 300 and abs(len(a) - len(b)) <= 0.02 * len(b)
-    assert a[:100] == b[:100]
-    # (on rect.mtx the first stage already reaches eps: the second has nothing left to report)
-    assert ("Lock striplet" in ours.stdout) == ("Lock striplet" in ref.stdout)
-    assert "#Converged" in ours.stdout

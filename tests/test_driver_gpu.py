@@ -6,7 +6,7 @@ check_solution (tests/COMMON/ioandtest.c:86-150) verifies eigenvalues, residual 
 orthogonality and the angle to the STORED reference solutions tests/sol_00N_double, and
 checkInterface exercises primme_get_member/set_member on every field.  Exit code 0 = all checks
 passed.  test_006 selects PRIMME_DEFAULT_MIN_TIME (JDQMR_ETol with the Jacobi preconditioner of the
-driver).  test_007 asks for refined extraction: the product must refuse it with
+driver).  test_007 asks for harmonic extraction: the product must refuse it with
 PRIMME_FUNCTION_UNAVAILABLE rather than run something else."""
 import os
 import subprocess
@@ -25,26 +25,18 @@ def run(cfg, driver=DRIVER):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cfg", ["test_201", "test_202", "test_207"])
+@pytest.mark.parametrize("cfg", ["test_201", "test_202", "test_205", "test_206", "test_207"])
 def test_reference_svds_driver_passes_its_own_checks(cfg):
-    """tests/driversvds.c, unchanged: rect.mtx, 5 largest triplets with the default two-stage hybrid
-    (201: eps 1e-6, 202: eps 1e-12) and with the augmented operator alone (207); check_solution_svds
-    against the stored sol_20Nsvds_double"""
+    """tests/driversvds.c, unchanged: rect.mtx / lund_b.mtx; 5 largest triplets with the default two-stage
+    hybrid (201: eps 1e-6, 202: eps 1e-12) and with the augmented operator alone (207); the smallest
+    triplet with the Jacobi-type preconditioner of the driver (205, 206: second stage = JDQMR with refined
+    extraction on the augmented operator); check_solution_svds against the stored sol_20Nsvds_double.
+    (203 and 204 -- 5 smallest, tens of thousands of iterations -- run on the CPU host-check build,
+    tests/test_driver_cpu.py.)"""
     if not os.path.exists(DRIVER_SVDS):
         pytest.skip("driver binary not built (needs the reference tree at build time)")
     r = run(cfg, DRIVER_SVDS)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("cfg", ["test_203", "test_205"])
-def test_reference_svds_driver_out_of_scope_config_is_refused(cfg):
-    """smallest singular values: the second stage asks for refined extraction"""
-    if not os.path.exists(DRIVER_SVDS):
-        pytest.skip("driver binary not built")
-    r = run(cfg, DRIVER_SVDS)
-    assert r.returncode != 0
-    assert "outside the scope of this build" in r.stdout + r.stderr
 
 
 @pytest.mark.gpu
@@ -59,7 +51,7 @@ def test_reference_driver_passes_its_own_checks(cfg):
 @pytest.mark.gpu
 @pytest.mark.parametrize("cfg", ["test_007"])
 def test_reference_driver_out_of_scope_config_is_refused(cfg):
-    """test_007: refined extraction"""
+    """test_007: harmonic extraction"""
     if not os.path.exists(DRIVER):
         pytest.skip("driver binary not built")
     r = run(cfg)

@@ -106,6 +106,37 @@ def test_svds_two_stage_device_contract_code_path(case):
     assert got["stats"] == ref["stats"], (got["stats"], ref["stats"])
 
 
+# smallest singular values through the hybrid method: the second stage is the augmented operator with
+# refined extraction, closest_geq to lower bounds of the first stage's values, hard locking
+SMALLEST = {
+    "tall": (300, 60, 5, 4, 3, dict(eps=1e-11)),
+    "wide": (120, 300, 5, 4, 2, dict(eps=1e-11)),
+    "tall_jdqmr": (400, 90, 6, 8, 2, dict(eps=1e-12)),
+}
+
+
+@pytest.mark.parametrize("case", sorted(SMALLEST))
+def test_svds_smallest_hybrid_hostcheck_matches_reference(case):
+    m, n, per_row, seed, k, kw = SMALLEST[case]
+    csr = S.random_rect(m, n, per_row, seed)
+    st2 = api.PRIMME_JDQMR if "jdqmr" in case else api.PRIMME_GD_Olsen_plusK
+    args = dict(target=S.primme_svds_smallest, method=S.primme_svds_hybrid, method_stage1=api.PRIMME_GD_Olsen_plusK,
+                method_stage2=st2, maxMatvecs=400000, **kw)
+    ref = S.solve("reference", csr, (m, n), k, **args)
+    got = S.solve("hostcheck", csr, (m, n), k, **args)
+    A = S.dense(csr, (m, n))
+    sv = np.linalg.svd(A, compute_uv=False)[::-1][:k]
+    for r in (ref, got):
+        assert r["ret"] == 0 and r["initSize"] == k
+        assert np.allclose(np.sort(r["svals"]), sv, rtol=0, atol=1e-9 * r["aNorm"])
+        U, V = r["U"], r["V"]
+        R = np.sqrt(np.linalg.norm(A @ V - U * r["svals"], axis=0) ** 2 + np.linalg.norm(A.T @ U - V * r["svals"], axis=0) ** 2)
+        assert np.all(R < kw["eps"] * r["aNorm"] * 1.05 + 1e-13 * r["aNorm"])
+    assert np.allclose(got["svals"], ref["svals"], rtol=1e-10)
+    for key in ("numOuterIterations", "numMatvecs"):
+        assert abs(got["stats"][key] - ref["stats"][key]) <= max(4, 0.05 * ref["stats"][key]), (got["stats"], ref["stats"])
+
+
 def test_svds_default_method_runs_like_reference():
     """primme_svds_default = hybrid with PRIMME_DEFAULT_METHOD in both stages (run-time method choice:
     values and residuals are the criterion, not counts)"""

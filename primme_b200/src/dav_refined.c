@@ -1,4 +1,5 @@
-/* dav_refined.c -- refined extraction: the QR factorisation (A - tau I) V = Q R carried next to V and W.
+/* dav_refined.c -- refined and harmonic extraction: the QR factorisation (A - tau I) V = Q R carried next
+ * to V and W.
  *
  * Restates, for B = I and fp64:
  *   update_Q              src/eigs/update_W.c:69-113        new columns of Q and R
@@ -6,6 +7,9 @@
  *   prepare_vecs          src/eigs/solve_projection.c:842-985   Rayleigh-Ritz inside clusters of
  *                                                            close singular values
  *   restart_refined       src/eigs/restart.c:1837-2160      Q, R after V <- V*hVecs
+ *   solve_H_Harm          src/eigs/solve_projection.c:395-470    harmonic Ritz pairs from (Q'V inv(R), Q'Q)
+ *   restart_harmonic      src/eigs/restart.c:2256-2326      QR, Q'V and the projected problem again
+ *   update_projection (unsymmetric)  src/eigs/update_projection.c:81-165   new columns and rows of Q'V
  * The n-long work is the same three kernel families as the rest of the solver: the residual
  * utility (Q = W - tau V), the block-ortho sweep (on Q, with its own Gram matrix when orth is
  * explicit) and the VWXR sweep (Q <- Q*hU with Q'Q).  Everything else is maxBasis x maxBasis host
@@ -290,5 +294,110 @@ int pb_restart_refined(pb_solver *S, int restartSize, int basisSize, int numConv
    hl_zero(hVecs, restartSize, *numArbitraryVecs, ld);
    for (j = 0; j < *numArbitraryVecs; j++) hVecs[(size_t)ld * j + hVecsPerm[j]] = 1.0;
    (void)indexOfPreviousVecs;
+   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Harmonic extraction
+ * ---------------------------------------------------------------------------------------- */
+/* QtV(0:m, numCols:m) = Q(:,0:m)' V(:,numCols:m) and QtV(numCols:m, 0:numCols) = Q(:,numCols:m)' V(:,0:numCols),
+ * m = numCols + blockSize: two row sweeps of the projection kernel */
+int pb_update_QtV(pb_solver *S, int numCols, int blockSize) {
+   if (blockSize <= 0 || !S->QtV) return 0;
+   const int ld = S->maxBasis, m = numCols + blockSize;
+   for (int c0 = 0; c0 < blockSize; c0 += 8) {
+      const int bc = PB_MIN(8, blockSize - c0);
+      double *P = &S->QtV[(size_t)ld * (numCols + c0)];
+      CHK(pb200_dortho_sweep(S->dev, S->n, NULL, 0, 0, S->Q, m, S->ld, S->V + (size_t)S->ld * (numCols + c0), bc, S->ld,
+            NULL, 0, NULL, 0, 0, P, ld));
+      CHK(pb_reduce_panel(S, P, m, bc, ld));
+   }
+   if (numCols > 0) {
+      /* the new rows are the transposed panel V(:,0:numCols)' Q(:,numCols:m) */
+      double *P = (double *)malloc(sizeof(double) * (size_t)numCols * 8);
+      if (!P) return PRIMME_MALLOC_FAILURE;
+      for (int c0 = 0; c0 < blockSize; c0 += 8) {
+         const int bc = PB_MIN(8, blockSize - c0);
+         CHK(pb200_dortho_sweep(S->dev, S->n, NULL, 0, 0, S->V, numCols, S->ld, S->Q + (size_t)S->ld * (numCols + c0), bc,
+               S->ld, NULL, 0, NULL, 0, 0, P, numCols));
+         CHK(pb_reduce_panel(S, P, numCols, bc, numCols));
+         for (int j = 0; j < bc; j++)
+            for (int i = 0; i < numCols; i++) S->QtV[(size_t)ld * i + numCols + c0 + j] = P[(size_t)numCols * j + i];
+      }
+      free(P);
+   }
+   return 0;
+}
+
+/* eigenpairs of (Q'V inv(R), Q'Q) ordered as the harmonic values 1/(theta - tau), mapped back with
+ * hVecs = inv(R) g, orthonormalised in the V'V inner product; Rayleigh quotients as values */
+int pb_solve_H_harm(pb_solver *S, int n, const double *VtBVblk, int ldVtBV, int numConverged) {
+   primme_params *primme = S->primme;
+   (void)numConverged;
+   if (n == 0) return 0;
+   const double t0 = hl_wtime();
+   const int ld = S->maxBasis;
+   double *hVecs = S->hVecs, *hVals = S->hVals;
+   double *fR = (double *)malloc(sizeof(double) * (size_t)n * n);
+   int *piv = (int *)malloc(sizeof(int) * n);
+   if (!fR || !piv) return PRIMME_MALLOC_FAILURE;
+   int rc = 0;
+   hl_copy(S->R, n, n, ld, fR, n);
+   if (hl_getrf(n, n, fR, n, piv) != 0) rc = PRIMME_LAPACK_FAILURE;
+   if (!rc) {
+      for (int j = 0; j < n; j++)
+         for (int i = 0; i < n; i++) hVecs[(size_t)ld * j + i] = S->QtV[(size_t)ld * i + j];
+      if (hl_getrs('C', n, n, fR, n, piv, hVecs, ld) != 0) rc = PRIMME_LAPACK_FAILURE;
+   }
+   if (!rc) {
+      double zero = 0.0, *oldShifts = primme->targetShifts;
+      const primme_target oldTarget = primme->target;
+      primme->targetShifts = &zero;
+      primme->target = oldTarget == primme_closest_geq   ? primme_largest
+                       : oldTarget == primme_closest_leq ? primme_smallest
+                                                         : primme_largest_abs;
+      rc = pb_solve_H(S, hVecs, ld, n, S->QtQ, ld, hVecs, ld, hVals, 0, 0);
+      primme->targetShifts = oldShifts;
+      primme->target = oldTarget;
+   }
+   if (!rc) {
+      hl_copy(hVecs, n, n, ld, S->hU, ld);
+      if (hl_getrs('N', n, n, fR, n, piv, hVecs, ld) != 0) rc = PRIMME_LAPACK_FAILURE;
+   }
+   if (!rc) {
+      long long seed[4];
+      for (int i = 0; i < 4; i++) seed[i] = primme->iseed[i];
+      rc = pb_ortho_local_R(hVecs, ld, NULL, 0, 0, n - 1, n, VtBVblk, ldVtBV, seed) ? PRIMME_UNEXPECTED_FAILURE : 0;
+      for (int i = 0; i < 4; i++) primme->iseed[i] = seed[i];
+   }
+   if (!rc) {
+      double *rw = (double *)calloc((size_t)n * n, sizeof(double));
+      hl_symm_lu(n, n, 1.0, S->H, ld, hVecs, ld, 0.0, rw, n);
+      for (int i = 0; i < n; i++) hVals[i] = hl_dot(n, &hVecs[(size_t)ld * i], &rw[(size_t)n * i]);
+      free(rw);
+      for (int i = 0; i < n; i++) {
+         primme->stats.estimateMinEVal = PB_MIN(primme->stats.estimateMinEVal, hVals[i]);
+         primme->stats.estimateMaxEVal = PB_MAX(primme->stats.estimateMaxEVal, hVals[i]);
+         primme->stats.estimateLargestSVal = PB_MAX(primme->stats.estimateLargestSVal, fabs(hVals[i]));
+      }
+   }
+   free(fR), free(piv);
+   S->tSolveH += hl_wtime() - t0;
+   return rc;
+}
+
+/* after V <- V*hVecs, W <- W*hVecs: everything that depends on Q from scratch */
+int pb_restart_harmonic(pb_solver *S, int restartSize, int basisSize, int numConverged, int *targetShiftIndex) {
+   primme_params *primme = S->primme;
+   const int ld = S->maxBasis, ldG = S->maxRank;
+   if (primme->orth == primme_orth_implicit_I) pb_compute_submatrix(S->hVecs, restartSize, ld, S->H, basisSize, ld, S->H, ld);
+   *targetShiftIndex = PB_MIN(primme->numTargetShifts - 1, numConverged);
+   int nQ = 0;
+   CHK(pb_update_Q(S, primme->targetShifts[*targetShiftIndex], 0, restartSize, &nQ));
+   if (restartSize != nQ) return PRIMME_UNEXPECTED_FAILURE;
+   CHK(pb_update_QtV(S, 0, restartSize));
+   const int nLocked = primme->numOrthoConst + (primme->locking ? numConverged : 0);
+   CHK(pb_solve_H_harm(S, restartSize, S->VtBV ? &S->VtBV[(size_t)ldG * nLocked + nLocked] : NULL, ldG, numConverged));
+   S->numArbitraryVecs = 0;
    return 0;
 }

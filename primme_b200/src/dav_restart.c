@@ -679,7 +679,9 @@ int pb_restart(pb_solver *S, int basisSize, int *ievSize, double *evals, double 
       S->numPrevRitzVals = restartSize;
    }
 
-   if (!rc && S->refined)
+   if (!rc && S->QtV)
+      rc = pb_restart_harmonic(S, restartSize, basisSize, *numConverged, targetShiftIndex);
+   else if (!rc && S->refined)
       rc = pb_restart_refined(S, restartSize, basisSize, *numConverged, numPrevRetained, indexOfPreviousVecs,
             indexOfPreviousVecsBeforeRestart, restartPerm, hVecsPerm, targetShiftIndex);
    else if (!rc)

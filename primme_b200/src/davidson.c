@@ -24,6 +24,7 @@
 
 /* solve_H (solve_projection.c:95-154): Rayleigh-Ritz pairs of (H, V'V) or the refined vectors from R */
 static int solve_projected(pb_solver *S, int basisSize, int nLocked, int numConverged) {
+   if (S->QtV) return pb_solve_H_harm(S, basisSize, VtBV_BLK(S, nLocked), S->maxRank, numConverged);
    if (S->refined) return pb_solve_H_ref(S, basisSize, VtBV_BLK(S, nLocked), S->maxRank, numConverged);
    return pb_solve_H(S, S->H, S->maxBasis, basisSize, VtBV_BLK(S, nLocked), S->maxRank, S->hVecs, S->maxBasis, S->hVals,
          numConverged, 1);
@@ -583,13 +584,14 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
       reset = 0;
       for (i = 0; i < maxBasis; i++) flags[i] = UNCONVERGED;
       targetShiftIndex = 0;
-      if (S->refined) {
+      if (S->numQR) {
          int nQ = 0;
          CHK(pb_update_Q(S, primme->targetShifts[targetShiftIndex], 0, basisSize, &nQ));
          if (basisSize != nQ) return PRIMME_UNEXPECTED_FAILURE; /* "Not supported deficient QR" (:466) */
       }
 
       CHK(pb_update_projection(S, 0, basisSize));
+      CHK(pb_update_QtV(S, 0, basisSize));
       CHK(solve_projected(S, basisSize, primme->numOrthoConst + numLocked, numConverged));
       S->numArbitraryVecs = 0;
 
@@ -615,7 +617,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
 
             primme->stats.numOuterIterations++;
 
-            if (primme->numTargetShifts > numConverged + 1 && S->refined) {
+            if (primme->numTargetShifts > numConverged + 1 && S->numQR) {
                /* one pair at a time while the QR factorisation depends on the shift (:525-528) */
                availableBlockSize = 1;
                maxRecentlyConverged = numConverged - numLocked + 1;
@@ -679,9 +681,9 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
             if (numConverged >= primme->numEvals ||
                   (primme->locking && numConverged > numLocked &&
                         primme->target != primme_smallest && primme->target != primme_largest &&
-                        (!S->refined || primme->target == primme_closest_geq || primme->target == primme_closest_leq)) ||
+                        (!S->numQR || primme->target == primme_closest_geq || primme->target == primme_closest_leq)) ||
                   targetShiftIndex < 0 || (blockSize == 0 && recentlyConverged > 0) ||
-                  (S->refined && fabs(primme->targetShifts[targetShiftIndex] -
+                  (S->numQR && fabs(primme->targetShifts[targetShiftIndex] -
                                        primme->targetShifts[PB_MIN(primme->numTargetShifts - 1, numConverged)]) >=
                                        PB_MAX(primme->aNorm, primme->stats.estimateLargestSVal)) ||
                   (numConverged >= nextGuess - primme->numOrthoConst && numGuesses > 0)) {
@@ -758,14 +760,14 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
                Rlocked = NULL;
                if (numConverged > numLocked && primme->target != primme_smallest &&
                      primme->target != primme_largest &&
-                     (!S->refined || primme->target == primme_closest_geq || primme->target == primme_closest_leq))
+                     (!S->numQR || primme->target == primme_closest_geq || primme->target == primme_closest_leq))
                   break;
             }
 
             /* W(:,new) = A V(:,new);  H(:,new) = V' W(:,new) */
             CHK(pb_apply_matvec(S, S->V + (size_t)S->ld * basisSize, S->ld,
                   S->W + (size_t)S->ld * basisSize, S->ld, blockSize));
-            if (S->refined) {
+            if (S->numQR) {
                int nQ = basisSize;
                CHK(pb_update_Q(S, primme->targetShifts[targetShiftIndex], basisSize, blockSize, &nQ));
                if (basisSize + blockSize != nQ) {
@@ -775,6 +777,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
                }
             }
             CHK(pb_update_projection(S, basisSize, blockSize));
+            CHK(pb_update_QtV(S, basisSize, blockSize));
 
             hl_copy(S->hVecs, basisSize, basisSize, ldh, S->prevhVecs, ldh);
             hl_zero(&S->prevhVecs[basisSize], maxBasis - basisSize, basisSize, ldh);
@@ -827,7 +830,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
 
             if (availableBlockSize <= 0 ||
                   primme->minRestartSize + primme->restartingParams.maxPrevRetain + availableBlockSize < maxBasis ||
-                  primme->numOrthoConst + numLocked + basisSize >= primme->n || S->refined) {
+                  primme->numOrthoConst + numLocked + basisSize >= primme->n || S->numQR) {
                double dummyZero = 0.0;
                double *srn = (primme->target == primme_closest_abs || primme->target == primme_largest_abs)
                                    ? &dummyZero
@@ -838,7 +841,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
 
                /* with several shifts, a pair that converged may be the closest to another target: no
                 * candidates for the next iteration (:1003-1006) */
-               if (S->refined && numConverged + recentlyConverged > numLocked && primme->numTargetShifts > numLocked + 1)
+               if (S->numQR && numConverged + recentlyConverged > numLocked && primme->numTargetShifts > numLocked + 1)
                   blockSize = 0;
 
                for (i = 0, numConverged = numLocked; i < basisSize; i++)
@@ -909,12 +912,13 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
             numNew = basisSizeOut - basisSize;
             CHK(pb_apply_matvec(S, S->V + (size_t)S->ld * basisSize, S->ld,
                   S->W + (size_t)S->ld * basisSize, S->ld, numNew));
-            if (S->refined) {
+            if (S->numQR) {
                int nQ = basisSize;
                CHK(pb_update_Q(S, primme->targetShifts[targetShiftIndex], basisSize, numNew, &nQ));
                if (basisSize + numNew != nQ) return PRIMME_UNEXPECTED_FAILURE;
             }
             CHK(pb_update_projection(S, basisSize, numNew));
+            CHK(pb_update_QtV(S, basisSize, numNew));
             basisSize += numNew;
             CHK(solve_projected(S, basisSize, primme->numOrthoConst + numLocked, numConverged));
             if (numNew > 0) S->numArbitraryVecs = 0;

@@ -315,7 +315,9 @@ static int check_input(void *evals, void *evecs, void *resNorms, primme_params *
 static int check_scope(primme_params *p) {
    const char *why = NULL;
    if (p->massMatrixMatvec) why = "generalized problems (massMatrixMatvec)";
-   else if (p->projectionParams.projection == primme_proj_harmonic) why = "harmonic extraction";
+   else if (p->projectionParams.projection == primme_proj_harmonic && p->target != primme_closest_geq &&
+            p->target != primme_closest_leq && p->target != primme_closest_abs)
+      why = "harmonic extraction with a target other than closest_geq / closest_leq / closest_abs";
    else if (p->internalPrecision != primme_op_default && p->internalPrecision != primme_op_double)
       why = "internalPrecision other than double";
    else if ((p->matrixMatvec_type != primme_op_default && p->matrixMatvec_type != primme_op_double) ||
@@ -341,7 +343,7 @@ static void free_solver(pb_solver *S, int own_evecs) {
    }
    free(S->hstage), free(S->hstage2);
    free(S->H), free(S->hVecs), free(S->prevhVecs), free(S->VtBV), free(S->fVtBV), free(S->fusedP);
-   free(S->R), free(S->hU), free(S->hVecsRot), free(S->QtQ), free(S->fQtQ), free(S->hSVals);
+   free(S->R), free(S->hU), free(S->hVecsRot), free(S->QtQ), free(S->fQtQ), free(S->hSVals), free(S->QtV);
    if (S->dev && S->Q) pb200_free(S->dev, S->Q);
    if (S->dev && S->jd_work) pb200_free(S->dev, S->jd_work);
    free(S->hVals), free(S->prevRitzVals), free(S->blockNorms), free(S->basisNorms);
@@ -460,7 +462,12 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
       S->fVtBV = (double *)calloc((size_t)mr * mr, sizeof(double));
    }
    S->refined = primme->projectionParams.projection == primme_proj_refined;
-   if (S->refined) {
+   S->numQR = primme->projectionParams.projection != primme_proj_RR;
+   if (primme->projectionParams.projection == primme_proj_harmonic) {
+      S->QtV = (double *)calloc((size_t)mb * mb, sizeof(double));
+      if (!S->QtV) rc = PRIMME_MALLOC_FAILURE;
+   }
+   if (S->numQR) {
       /* Q next to V and W, its small factors on the host (main_iter.c:284-320) */
       if (!rc) rc = pb200_malloc(S->dev, basis_bytes, (void **)&S->Q);
       S->R = (double *)calloc((size_t)mb * mb, sizeof(double));

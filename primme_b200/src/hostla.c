@@ -14,6 +14,9 @@ extern void dsymm_(const char *, const char *, const int *, const int *, const d
 extern void dtrsm_(const char *, const char *, const char *, const char *, const int *,
       const int *, const double *, const double *, const int *, double *, const int *);
 extern void dpotrf_(const char *, const int *, double *, const int *, int *);
+extern void dgetrf_(const int *, const int *, double *, const int *, int *, int *);
+extern void dgetrs_(const char *, const int *, const int *, const double *, const int *, const int *, double *,
+      const int *, int *);
 extern void dtrmm_(const char *, const char *, const char *, const char *, const int *,
       const int *, const double *, const double *, const int *, double *, const int *);
 extern void dgesvd_(const char *, const char *, const int *, const int *, double *, const int *, double *,
@@ -123,6 +126,20 @@ int hl_sygv_upper(int n, double *A, int lda, const double *B, int ldb, double *w
    }
    if (info == 0) hl_copy(z, n, n, n, A, lda);
    free(z), free(iwork), free(ifail), free(b);
+   return info;
+}
+
+int hl_getrf(int m, int n, double *A, int lda, int *ipiv) {
+   int info = 0;
+   if (m == 0 || n == 0) return 0;
+   dgetrf_(&m, &n, A, &lda, ipiv, &info);
+   return info;
+}
+
+int hl_getrs(char trans, int n, int nrhs, const double *A, int lda, const int *ipiv, double *B, int ldb) {
+   int info = 0;
+   if (n == 0 || nrhs == 0) return 0;
+   dgetrs_(&trans, &n, &nrhs, A, &lda, ipiv, B, &ldb, &info);
    return info;
 }
 

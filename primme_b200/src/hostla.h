@@ -35,6 +35,9 @@ void hl_trsm(char side, char uplo, char trans, char diag, int m, int n, double a
 void hl_trmm(char side, char uplo, char trans, char diag, int m, int n, double alpha,
       const double *A, int lda, double *B, int ldb);
 int hl_potrf_upper(int n, double *A, int lda); /* returns LAPACK info */
+/* LU with partial pivoting and its solves (reference Num_getrf / Num_getrs, blaslapack.c) */
+int hl_getrf(int m, int n, double *A, int lda, int *ipiv);
+int hl_getrs(char trans, int n, int nrhs, const double *A, int lda, const int *ipiv, double *B, int ldb);
 /* singular value decomposition, left vectors in U, transposed right vectors overwrite A */
 int hl_gesvd_SO(int m, int n, double *A, int lda, double *s, double *U, int ldu);
 /* eigen-decomposition of the symmetric matrix stored in the upper triangle of A (n x n, lda);

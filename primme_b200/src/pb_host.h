@@ -65,7 +65,9 @@ typedef struct pb_solver {
    double *jd_work;
    int touch; /* stopping-criterion state of the inner solver (main_iter.c:206,597-599) */
    /* refined extraction (dav_refined.c): (A - tau I) V = Q R next to V and W */
-   int refined;
+   int refined;        /* primme_proj_refined */
+   int numQR;          /* refined or harmonic: Q and R are carried (main_iter.c:268-273) */
+   double *QtV;        /* harmonic: Q'V, maxBasis x maxBasis */
    double *Q;          /* device, ld x maxBasisSize */
    double *R, *hU, *hVecsRot; /* maxBasis x maxBasis */
    double *QtQ, *fQtQ; /* Q'Q and its Cholesky factor when orth is explicit, else NULL */
@@ -139,6 +141,9 @@ int pb_prepare_vecs(pb_solver *S, int basisSize, int i0, int blockSize, int targ
 int pb_restart_refined(pb_solver *S, int restartSize, int basisSize, int numConverged, int numPrevRetained,
       int indexOfPreviousVecs, int indexOfPreviousVecsBeforeRestart, const int *restartPerm, const int *hVecsPerm,
       int *targetShiftIndex);
+int pb_update_QtV(pb_solver *S, int numCols, int blockSize);
+int pb_solve_H_harm(pb_solver *S, int n, const double *VtBVblk, int ldVtBV, int numConverged);
+int pb_restart_harmonic(pb_solver *S, int restartSize, int basisSize, int numConverged, int *targetShiftIndex);
 int pb_compute_submatrix(const double *X, int nX, int ldX, const double *H, int nH, int ldH, double *R, int ldR);
 int pb_ortho_local_R(double *V, int ldV, double *R, int ldR, int b1, int b2, int n, const double *B, int ldB,
       long long *iseed);

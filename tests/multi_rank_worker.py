@@ -52,8 +52,15 @@ def main():
 
     mv, gs = api.BLOCK_OP(matvec), api.GLOBAL_SUM(gsum)
     k = 6
-    p = api.new_params(lib, n, numEvals=k, maxBlockSize=int(os.environ.get("PB_BS", "3")), eps=1e-10,
-                       numProcs=world, procID=rank, nLocal=nloc)
+    extra = {}
+    proj = os.environ.get("PB_PROJ", "")
+    if proj:
+        # interior pairs with the QR factorisation of (A - tau I) V carried next to V and W
+        k = 3
+        extra = dict(target=api.primme_closest_abs, targetShifts=[0.35],
+                     projection=api.primme_proj_refined if proj == "refined" else api.primme_proj_harmonic)
+    p = api.new_params(lib, n, numEvals=k, maxBlockSize=int(os.environ.get("PB_BS", "3")), eps=1e-8 if proj else 1e-10,
+                       numProcs=world, procID=rank, nLocal=nloc, **extra)
     p.matrixMatvec = C.cast(mv, C.c_void_p).value
     p.globalSumReal = C.cast(gs, C.c_void_p).value
     method = getattr(api, os.environ.get("PB_METHOD", "PRIMME_GD_Olsen_plusK"))

@@ -55,3 +55,24 @@ def test_two_rank_row_partitioned_svds(preset, device_entry):
     else:
         assert max(out["res"]) < 1.05 * tol and max(out["rnorms"]) < 2 * tol
     assert out["globalsums"] > 0
+
+
+@pytest.mark.parametrize("proj,bs", [("refined", 2), ("harmonic", 1)])
+def test_two_rank_refined_and_harmonic_extraction(proj, bs):
+    """row-sharded solve with Q next to V and W: the panels of the Q orthogonalisation, of Q'V and of the Q
+    restart are reduced over the ranks like every other panel"""
+    env = dict(os.environ, PB_BS=str(bs), PB_METHOD="PRIMME_GD_Olsen_plusK", PB_PROJ=proj, OMP_NUM_THREADS="1",
+               OPENBLAS_NUM_THREADS="1")
+    port = 29580 + bs + (3 if proj == "harmonic" else 0)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "multi_rank_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1][len("RESULT "):])
+    assert out["rc"] == 0
+    shape = (8, 11, 13)
+    lam = [2 - 2 * np.cos(np.pi * np.arange(1, s + 1) / (s + 1)) for s in shape]
+    spec = (lam[0][:, None, None] + lam[1][None, :, None] + lam[2][None, None, :]).ravel()
+    exact = spec[np.argsort(np.abs(spec - 0.35))][:3]
+    assert np.allclose(np.sort(out["evals"]), np.sort(exact), rtol=1e-7)
+    assert out["orth"] < 1e-7 and max(out["res"]) < 1e-8 * 12.0 * 1.1

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
+#include <pthread.h>
 
 /* ---- registry: which kernel context serves which primme_params (a handful of entries) ---- */
 #define PB_MAX_ACTIVE 64
@@ -22,6 +23,10 @@ static struct {
    pb200_ctx *solver; /* set for the duration of a solve */
    pb200_ctx *user;   /* attached by the caller (e.g. with an NCCL communicator) */
 } registry[PB_MAX_ACTIVE];
+
+/* solves on different primme_params may run on different threads (the reference is re-entrant per
+ * primme_params): slot allocation and release are serialised */
+static pthread_mutex_t reg_lock = PTHREAD_MUTEX_INITIALIZER;
 
 static int reg_find(const primme_params *p, int create) {
    int free_slot = -1;
@@ -37,29 +42,42 @@ static int reg_find(const primme_params *p, int create) {
 }
 
 int primme_b200_attach_ctx(primme_params *primme, pb200_ctx *ctx) {
-   int i = reg_find(primme, ctx != NULL);
-   if (i < 0) return ctx ? PRIMME_MALLOC_FAILURE : 0;
-   registry[i].user = ctx;
-   if (!registry[i].user && !registry[i].solver) registry[i].primme = NULL;
-   return 0;
+   pthread_mutex_lock(&reg_lock);
+   int i = reg_find(primme, ctx != NULL), rc = 0;
+   if (i < 0)
+      rc = ctx ? PRIMME_MALLOC_FAILURE : 0;
+   else {
+      registry[i].user = ctx;
+      if (!registry[i].user && !registry[i].solver) registry[i].primme = NULL;
+   }
+   pthread_mutex_unlock(&reg_lock);
+   return rc;
 }
 
 pb200_ctx *primme_b200_attached_ctx(const primme_params *primme) {
+   pthread_mutex_lock(&reg_lock);
    int i = reg_find(primme, 0);
-   return i < 0 ? NULL : registry[i].user;
+   pb200_ctx *c = i < 0 ? NULL : registry[i].user;
+   pthread_mutex_unlock(&reg_lock);
+   return c;
 }
 
 void pb_registry_set_solver(const primme_params *primme, pb200_ctx *ctx) {
+   pthread_mutex_lock(&reg_lock);
    int i = reg_find(primme, ctx != NULL);
-   if (i < 0) return;
-   registry[i].solver = ctx;
-   if (!registry[i].user && !registry[i].solver) registry[i].primme = NULL;
+   if (i >= 0) {
+      registry[i].solver = ctx;
+      if (!registry[i].user && !registry[i].solver) registry[i].primme = NULL;
+   }
+   pthread_mutex_unlock(&reg_lock);
 }
 
 pb200_ctx *primme_b200_solver_ctx(const primme_params *primme) {
+   pthread_mutex_lock(&reg_lock);
    int i = reg_find(primme, 0);
-   if (i < 0) return NULL;
-   return registry[i].solver ? registry[i].solver : registry[i].user;
+   pb200_ctx *c = i < 0 ? NULL : (registry[i].solver ? registry[i].solver : registry[i].user);
+   pthread_mutex_unlock(&reg_lock);
+   return c;
 }
 
 /* ---- CSR block matvec: y = A x on device pointers ---- */

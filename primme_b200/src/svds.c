@@ -25,6 +25,7 @@
 #include "../../include/primme_svds.h"
 #include <float.h>
 #include <limits.h>
+#include <pthread.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -399,10 +400,36 @@ typedef struct svds_run {
 #define SVDS_MAX_RUNS 16
 static svds_run runs[SVDS_MAX_RUNS];
 
+/* concurrent solves on different primme_svds_params: claiming and releasing a slot is serialised */
+static pthread_mutex_t runs_lock = PTHREAD_MUTEX_INITIALIZER;
+
 static svds_run *find_run(const primme_svds_params *s) {
-   for (int i = 0; i < SVDS_MAX_RUNS; i++)
-      if (runs[i].svds == s) return &runs[i];
-   return NULL;
+   svds_run *hit = NULL;
+   pthread_mutex_lock(&runs_lock);
+   for (int i = 0; i < SVDS_MAX_RUNS && !hit; i++)
+      if (runs[i].svds == s) hit = &runs[i];
+   pthread_mutex_unlock(&runs_lock);
+   return hit;
+}
+
+/* a free slot bound to s */
+static svds_run *claim_run(primme_svds_params *s, int device_mode) {
+   svds_run *hit = NULL;
+   pthread_mutex_lock(&runs_lock);
+   for (int i = 0; i < SVDS_MAX_RUNS && !hit; i++)
+      if (runs[i].svds == NULL) hit = &runs[i];
+   if (hit) {
+      memset(hit, 0, sizeof(*hit));
+      hit->svds = s, hit->device_mode = device_mode;
+   }
+   pthread_mutex_unlock(&runs_lock);
+   return hit;
+}
+
+static void release_run(svds_run *run) {
+   pthread_mutex_lock(&runs_lock);
+   run->svds = NULL, run->aux = NULL;
+   pthread_mutex_unlock(&runs_lock);
 }
 
 static primme_svds_operator stage_method(const primme_svds_params *s, const primme_params *primme) {
@@ -1195,10 +1222,8 @@ static int svds_solve(double *svals, double *svecs, double *resNorms, primme_svd
    }
    memset(&s->stats, 0, sizeof(s->stats));
 
-   svds_run *run = find_run(NULL);
+   svds_run *run = claim_run(s, device_mode);
    if (!run) return PRIMME_MALLOC_FAILURE;
-   memset(run, 0, sizeof(*run));
-   run->svds = s, run->device_mode = device_mode;
 
    /* one kernel context for the whole call: the caller's (attached to the first-stage eigensolver)
     * or a private one; the vector post-processing needs it outside the eigensolver */
@@ -1206,7 +1231,7 @@ static int svds_solve(double *svals, double *svecs, double *resNorms, primme_svd
    int own_ctx = 0;
    if (!ctx && device_mode) {
       if (pb200_ctx_create(&ctx, -1)) {
-         run->svds = NULL;
+         release_run(run);
          s->initSize = 0;
          return PRIMME_FUNCTION_UNAVAILABLE;
       }
@@ -1224,7 +1249,10 @@ static int svds_solve(double *svals, double *svecs, double *resNorms, primme_svd
       int allocatedShifts = 0;
       double *evecs = NULL;
       rc = stage_begin(run, stage, svals, svecs, resNorms, &allocatedShifts, &evecs);
-      if (rc) break;
+      if (rc) {
+         if (allocatedShifts) free(primme->targetShifts), primme->targetShifts = NULL;
+         break;
+      }
       /* numSvals - numEvals triplets of the first stage are already converged (:505-508) */
       const int skip = stage == 1 ? s->numSvals - primme->numEvals : 0;
       ret = device_mode ? cublas_dprimme(svals + skip, evecs, resNorms + skip, primme)
@@ -1234,7 +1262,7 @@ static int svds_solve(double *svals, double *svecs, double *resNorms, primme_svd
    }
 
    vec_free(run, run->aux);
-   run->svds = NULL, run->aux = NULL;
+   release_run(run);
    if (attach2) primme_b200_attach_ctx(&s->primmeStage2, NULL);
    if (own_ctx) {
       primme_b200_attach_ctx(&s->primme, NULL);

@@ -214,33 +214,178 @@ def stats_dict(p):
     return {k: getattr(s, k) for k, _ in PrimmeStats._fields_}
 
 
-def eigsh_csr(indptr, indices, data, k=6, which="SA", tol=0.0, method=PRIMME_GD_Olsen_plusK, maxBlockSize=1,
-              maxBasisSize=0, aNorm=0.0, lib=None, return_stats=False, **kw):
+def _target_from_which(which, sigma):
+    """`which` / `sigma` of the reference's Python eigsh (Python/primme.pyx:508-544)"""
+    table = {"LM": (primme_largest_abs, True), "LA": (primme_largest, False), "SA": (primme_smallest, False),
+             "SM": (primme_closest_abs, True), "CLT": (primme_closest_leq, True), "CGT": (primme_closest_geq, True)}
+    if isinstance(which, str):
+        if which not in table:
+            raise ValueError("which must be one of 'LM', 'SM', 'LA', 'SA', 'CLT', 'CGT' or a number")
+        target, shifted = table[which]
+        sigma = (0.0 if sigma is None else float(sigma)) if shifted else None
+    else:
+        if sigma is not None:
+            raise ValueError("Giving a numeric value in `which`, and also giving `sigma`. Set only one of those.")
+        target, sigma = primme_closest_abs, float(which)
+    return target, sigma
+
+
+def eigsh_csr(indptr, indices, data, k=6, sigma=None, which="SA", v0=None, ncv=None, maxiter=None, tol=0.0,
+              return_eigenvectors=True, lock=None, method=PRIMME_GD_Olsen_plusK, maxBlockSize=1, maxBasisSize=0,
+              minRestartSize=0, maxPrevRetain=0, aNorm=0.0, projection=None, lib=None, return_stats=False,
+              raise_for_unconverged=True, **kw):
     """Eigenpairs of the symmetric CSR matrix (indptr, indices, data) on the GPU.
 
-    SciPy-flavoured front end (cf. reference Python/primme.pyx eigsh): host CSR in, host
-    eigenpairs out; the matrix upload, the Davidson iteration and the download all go through
-    ``primme_b200_dprimme_csr``."""
+    SciPy-flavoured front end with the option names of the reference's Python ``eigsh``
+    (Python/primme.pyx:284-600): ``which`` in 'LA', 'SA', 'LM', 'SM', 'CLT', 'CGT' or a number, ``sigma``,
+    ``v0`` (n x i initial guesses), ``ncv`` (maxBasisSize), ``maxiter`` (maxOuterIterations), ``lock``,
+    ``projection`` ('RR', 'refined', 'harmonic').  Host CSR in, host eigenpairs out; the matrix upload, the
+    Davidson iteration and the download all go through ``primme_b200_dprimme_csr``."""
     lib = lib or load_library()
     n = len(indptr) - 1
-    target = {"SA": primme_smallest, "LA": primme_largest}[which]
+    target, sigma = _target_from_which(which, sigma)
+    extra = dict(kw)
+    if sigma is not None:
+        extra["targetShifts"] = [sigma]
+    if ncv:
+        maxBasisSize = int(ncv)
+    if maxiter:
+        extra["maxOuterIterations"] = int(maxiter)
+    if lock is not None:
+        extra["locking"] = 1 if lock else 0
+    if minRestartSize:
+        extra["minRestartSize"] = int(minRestartSize)
+    if maxPrevRetain:
+        extra["maxPrevRetain"] = int(maxPrevRetain)
+    if projection is not None:
+        extra["projection"] = {"RR": primme_proj_RR, "refined": primme_proj_refined, "harmonic": primme_proj_harmonic}[projection]
+    init = None
+    if v0 is not None:
+        init = np.atleast_2d(np.asarray(v0, dtype=np.float64).T).T.reshape(n, -1)
+        extra["initSize"] = min(init.shape[1], k)
     p = new_params(lib, n, numEvals=k, target=target, maxBlockSize=maxBlockSize, maxBasisSize=maxBasisSize,
-                   eps=tol, aNorm=aNorm, method=method, **kw)
+                   eps=tol, aNorm=aNorm, method=method, **extra)
     rp = np.ascontiguousarray(indptr, dtype=np.int64)
     ci = np.ascontiguousarray(indices, dtype=np.int32)
     va = np.ascontiguousarray(data, dtype=np.float64)
     evals = np.zeros(k)
     rnorms = np.zeros(k)
-    evecs = np.zeros((k, n))  # column-major n x k
+    evecs = np.zeros((max(k, p.initSize), n))  # column-major n x k
+    if init is not None:
+        evecs[:p.initSize] = init[:, :p.initSize].T
     p.ldevecs = n
     rc = lib.primme_b200_dprimme_csr(evals.ctypes.data, evecs.ctypes.data, rnorms.ctypes.data, C.byref(p),
                                      rp.ctypes.data, ci.ctypes.data, va.ctypes.data, 0)
     if rc == PRIMME_FUNCTION_UNAVAILABLE:
         raise RuntimeError("primme_b200: no CUDA device (or feature outside the build's scope); "
                            "this package has no CPU fallback")
-    if rc != 0:
+    if rc != 0 and (raise_for_unconverged or rc != PRIMME_MAIN_ITER_FAILURE):
         raise RuntimeError(f"dprimme returned {rc}")
-    out = (evals, evecs.T.copy())
+    nconv = max(p.initSize, 0) if rc != 0 else k
+    out = (evals[:nconv], evecs[:nconv].T.copy()) if return_eigenvectors else (evals[:nconv],)
     if return_stats:
-        out = out + (dict(stats_dict(p), rnorms=rnorms, initSize=p.initSize),)
-    return out
+        out = out + (dict(stats_dict(p), rnorms=rnorms[:nconv], initSize=p.initSize),)
+    return out if len(out) > 1 else out[0]
+
+
+def svds_csr(indptr, indices, data, shape, k=6, ncv=None, tol=0.0, which="LM", maxiter=None,
+             return_singular_vectors=True, method="hybrid", methodStage1=PRIMME_DEFAULT_METHOD,
+             methodStage2=PRIMME_DEFAULT_METHOD, maxBlockSize=0, lib=None, return_stats=False):
+    """Singular triplets of the m x n CSR matrix on the GPU, with the option names of the reference's Python
+    ``svds`` (Python/primme.pyx:1074-1400): ``which`` 'LM' / 'SM' / a number (closest singular values),
+    ``method`` 'hybrid' (default) / 'normalequations' / 'augmented'.  Returns (U, s, Vt) like SciPy.
+
+    The matrix and its transposed copy are uploaded once; ``cublas_dprimme_svds`` runs with the built-in
+    device operator (``primme_b200_svds_csr_matvec``); the triplets come back to the host."""
+    import re
+    lib = lib or load_library()
+    m, n = shape
+    here = os.path.dirname(os.path.abspath(__file__))
+    txt = open(os.path.join(os.path.dirname(here), "include", "primme_svds.h")).read()
+    label = {mm.group(1): (int(mm.group(2)), mm.group(4)) for mm in
+             re.finditer(r"X\((\w+),\s*(\d+),\s*([\w\.]+),\s*(\w+)\)", txt[txt.index("PRIMME_SVDS_PARAM_TABLE"):])}
+    vp, i32 = C.c_void_p, C.c_int
+    lib.primme_svds_params_create.restype = vp
+    lib.primme_svds_set_member.argtypes = [vp, i32, vp]
+    lib.primme_svds_get_member.argtypes = [vp, i32, vp]
+    lib.primme_svds_set_method.argtypes = [i32, i32, i32, vp]
+    lib.primme_svds_params_destroy.argtypes = [vp]
+    lib.cublas_dprimme_svds.argtypes = [vp, vp, vp, vp]
+    lib.pb200_csr_build_transpose.argtypes = [vp, vp]
+
+    def put(p, name, value):
+        ident, kind = label[name]
+        v = C.c_int64(int(value)) if kind == "I" else C.c_double(float(value)) if kind == "D" else None
+        rc = lib.primme_svds_set_member(p, ident, C.byref(v) if v is not None else C.c_void_p(value))
+        if rc:
+            raise ValueError(name)
+
+    def get(p, name):
+        ident, kind = label[name]
+        v = C.c_int64() if kind == "I" else C.c_double() if kind == "D" else C.c_void_p()
+        lib.primme_svds_get_member(p, ident, C.byref(v))
+        return v.value
+
+    rp = np.ascontiguousarray(indptr, dtype=np.int64)
+    ci = np.ascontiguousarray(indices, dtype=np.int32)
+    va = np.ascontiguousarray(data, dtype=np.float64)
+    ctx, A, dsvecs = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    if lib.pb200_ctx_create(C.byref(ctx), -1) != 0:
+        raise RuntimeError("primme_b200: no CUDA device; this package has no CPU fallback")
+    p = None
+    try:
+        if lib.pb200_csr_create(ctx, m, n, len(ci), rp.ctypes.data, ci.ctypes.data, va.ctypes.data, 0, 0, C.byref(A)) != 0 \
+                or lib.pb200_csr_build_transpose(ctx, A) != 0:
+            raise RuntimeError("primme_b200: could not upload the matrix")
+        p = lib.primme_svds_params_create()
+        shifts = None
+        if which == "LM":
+            target = 0
+        elif which == "SM":
+            target = 1
+        else:
+            target = 2
+            shifts = (C.c_double * 1)(float(which))
+        for name, v in (("m", m), ("n", n), ("numSvals", k), ("target", target), ("printLevel", 0), ("eps", tol),
+                        ("matrix", A.value), ("matrixMatvec", C.cast(lib.primme_b200_svds_csr_matvec, C.c_void_p).value)):
+            put(p, name, v)
+        if shifts is not None:
+            put(p, "numTargetShifts", 1)
+            put(p, "targetShifts", C.addressof(shifts))
+        if ncv:
+            put(p, "maxBasisSize", ncv)
+        if maxiter:
+            put(p, "maxMatvecs", maxiter)
+        if maxBlockSize:
+            put(p, "maxBlockSize", maxBlockSize)
+        preset = {"hybrid": 1, "normalequations": 2, "augmented": 3}[method]
+        if lib.primme_svds_set_method(preset, methodStage1, methodStage2, p) != 0:
+            raise ValueError("primme_svds_set_method")
+        inner = C.cast(C.c_void_p(get(p, "primme")), C.POINTER(PrimmeParams))
+        lib.primme_b200_attach_ctx(inner, ctx)
+        if lib.pb200_malloc(ctx, 8 * (m + n) * k, C.byref(dsvecs)) != 0:
+            raise MemoryError
+        svals, rn = np.zeros(k), np.zeros(k)
+        rc = lib.cublas_dprimme_svds(svals.ctypes.data, dsvecs, rn.ctypes.data, p)
+        lib.primme_b200_attach_ctx(inner, None)
+        if rc != 0:
+            raise RuntimeError(f"dprimme_svds returned {rc}")
+        kk = get(p, "initSize")
+        host = np.zeros((m + n) * k)
+        lib.pb200_copy_d2h(ctx, dsvecs, (m + n) * k, host.ctypes.data, (m + n) * k, (m + n) * kk, 1, 8)
+        U = host[: m * kk].reshape(kk, m).T.copy()
+        Vt = host[m * kk: (m + n) * kk].reshape(kk, n).copy()
+        stats = {s_: get(p, "stats_" + s_) for s_ in ("numOuterIterations", "numRestarts", "numMatvecs")}
+        stats.update(rnorms=rn[:kk], aNorm=get(p, "aNorm"))
+    finally:
+        if p:
+            lib.primme_svds_params_destroy(p)
+        if dsvecs:
+            lib.pb200_free(ctx, dsvecs)
+        if A:
+            lib.pb200_csr_destroy(ctx, A)
+        lib.pb200_ctx_destroy(ctx)
+    out = (U, svals[:kk], Vt) if return_singular_vectors else (svals[:kk],)
+    if return_stats:
+        out = out + (stats,)
+    return out if len(out) > 1 else out[0]

@@ -3,9 +3,10 @@
  *
  * Restates reference src/eigs/inner_solve.c:132-636 (inner_solve_Sprimme) and its helpers
  * apply_projected_preconditioner :714-744, apply_skew_projector :769-812, apply_projected_matrix
- * :838-890 for the projector configurations of the JDQMR / JDQMR_ETol presets
- * (primme_interface.c: LeftQ = precondition, LeftX = 1, RightQ = SkewQ = RightX = 0): the operator
- * is (I - QQ')(I - xx')(A - shift I), the preconditioner is applied unprojected, B = I.
+ * :838-890: the operator is (I - QQ')(I - xx')(A - shift I) with the left projectors the method selects,
+ * the preconditioner is followed by the right projectors (I - RX x'/x'RX)(I - QQ') when the method asks for
+ * them (PRIMME_JDQR, user settings); the skew-Q projector with a preconditioner (evecsHat, M = Q'K^{-1}Q
+ * and its factorisation) is the one configuration left out; B = I.
  *
  * Every n-long operation is a kernel of the C-ABI (column dots, column axpy / scale, permutes, the
  * fused ortho sweep for Q'v and v - Q(Q'v)); the scalar recurrences stay on the host exactly as in
@@ -62,6 +63,37 @@ static int apply_projected_matrix(pb_solver *S, double *v, int64_t ldv, const do
    return 0;
 }
 
+/* right projectors of the correction equation (setup_JD_projectors, correction.c:942-980): applied after the
+ * preconditioner,  result <- (I - RX_i x_i'/xKinvBx_i)(I - RQ RQ') K^{-1} v  (inner_solve.c:714-812 with no
+ * skew-Q factorisation: RQ = the locked vectors themselves) */
+typedef struct right_projectors {
+   const double *RQ; /* evecs, nRQ columns */
+   int64_t ldRQ;
+   int nRQ;
+   double *RX;       /* x (orthogonal) or K^{-1}x (skew), n x blockSize; permuted with the systems */
+   int64_t ldRX;
+   int nRX;          /* 0 or the current block size */
+   double *xKinvBx;  /* x_i' K^{-1} x_i, or ones; indexed by POSITION (permuted with the systems) */
+} right_projectors;
+
+static int apply_projected_preconditioner(pb_solver *S, right_projectors *rp, double *v, int64_t ldv, const double *x,
+      int64_t ldx, double *result, int64_t ldr, int bs) {
+   primme_params *primme = S->primme;
+   CHK(pb_apply_precond(S, v, ldv, result, ldr, bs));
+   if (!rp) return 0;
+   CHK(project_out(S, rp->RQ, rp->ldRQ, rp->nRQ, result, ldr, bs));
+   if (rp->nRX <= 0) return 0;
+   const double t0 = hl_wtime();
+   double ov[8];
+   CHK(pb200_dcolumn_dots(S->dev, S->n, x, ldx, result, ldr, bs, ov));
+   primme->stats.numOrthoInnerProds += bs;
+   CHK(pb_reduce_panel(S, ov, bs, 1, bs));
+   for (int i = 0; i < bs; i++) ov[i] = -ov[i] / rp->xKinvBx[i];
+   CHK(pb200_daxpy_columns(S->dev, S->n, ov, rp->RX, rp->ldRX, result, ldr, bs));
+   primme->stats.timeOrtho += hl_wtime() - t0;
+   return 0;
+}
+
 static void perm_set_value_on_pos(int *p, int val, int pos, int n) {
    for (int i = 0; i < n; i++)
       if (p[i] == val) {
@@ -81,7 +113,9 @@ static int dots_real(pb_solver *S, const double *a, int64_t lda, const double *b
  * rnorm / eval are indexed by original position, shift travels with the permutation. */
 int pb_inner_solve(pb_solver *S, int blockSize, double *x, int64_t ldx, double *r, int64_t ldr, const double *rnorm,
       const double *Q, int64_t ldQ, int nQ, int useX, double *sol, int64_t ldsol, const double *eval, double *shift,
-      int *touch, double *work) {
+      int *touch, double *work, const double *RQ, int64_t ldRQ, int nRQ, double *RX, int64_t ldRX, double *xKinvBx) {
+   right_projectors rpv = {RQ, ldRQ, nRQ, RX, ldRX, RX ? blockSize : 0, xKinvBx};
+   right_projectors *rp = (nRQ > 0 || RX) ? &rpv : NULL;
    primme_params *primme = S->primme;
    const correction_params *cp = &primme->correctionParams;
    const int64_t n = S->n, ldw = S->ld;
@@ -119,9 +153,9 @@ int pb_inner_solve(pb_solver *S, int blockSize, double *x, int64_t ldx, double *
    if (maxIterations > INT_MAX) maxIterations = INT_MAX;
    if (cp->maxInnerIterations > 0) maxIterations = PB_MIN((PRIMME_INT)cp->maxInnerIterations, maxIterations);
 
-   /* g = r, d = K^{-1} g (no right projectors in the supported presets) */
+   /* g = r, d = (right projectors) K^{-1} g */
    CHK(pb200_copy_d2d(S->dev, r, ldr, g, ldw, n, blockSize, 8));
-   CHK(pb_apply_precond(S, g, ldw, d, ldw, blockSize));
+   CHK(apply_projected_preconditioner(S, rp, g, ldw, x, ldx, d, ldw, blockSize));
    for (i = 0; i < blockSize; i++) Theta_prev[i] = 0.0, eval_prev[i] = eval[i];
    CHK(dots_real(S, g, ldw, d, ldw, blockSize, rho_prev));
    for (i = 0; i < blockSize; i++)
@@ -166,6 +200,11 @@ int pb_inner_solve(pb_solver *S, int blockSize, double *x, int64_t ldx, double *
       CHK(pb200_dpermute_columns(S->dev, n, r, ldr, p0, blockSize));                              \
       CHK(pb200_dpermute_columns(S->dev, n, x, ldx, p0, blockSize));                              \
       CHK(pb200_dpermute_columns(S->dev, n, sol, ldsol, p0, blockSize));                          \
+      if (rp && rp->nRX) {                                                                        \
+         hl_permute_cols(rp->xKinvBx, 1, blockSize, 1, p0);                                       \
+         if (rp->RX != x) CHK(pb200_dpermute_columns(S->dev, n, rp->RX, rp->ldRX, p0, blockSize)); \
+         rp->nRX -= conv;                                                                         \
+      }                                                                                           \
       blockSize -= conv;                                                                          \
       if (sizeX) sizeX -= conv;                                                                   \
    } while (0)
@@ -269,7 +308,7 @@ int pb_inner_solve(pb_solver *S, int blockSize, double *x, int64_t ldx, double *
       if (blockSize <= 0) break;
 
       if (numIts + 1 < maxIterations) {
-         CHK(pb_apply_precond(S, g, ldw, w, ldw, blockSize));
+         CHK(apply_projected_preconditioner(S, rp, g, ldw, x, ldx, w, ldw, blockSize));
          double beta_pos[8];
          CHK(dots_real(S, g, ldw, w, ldw, blockSize, rho));
          for (i = 0; i < blockSize; i++) {

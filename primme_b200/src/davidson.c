@@ -4,8 +4,9 @@
  * prepare_candidates :1470-1709, copy_back_candidates :1745-1841, verify_norms :1864-1894),
  * src/eigs/init.c (init_basis :125-238, init_block_krylov :258-323) and the GD/Olsen branch of
  * src/eigs/correction.c (:134-381, computeRobustShift :524-601, mergeSort :637-693) for the
- * configuration this library covers: Hermitian standard problem (B = I), Rayleigh-Ritz
- * extraction, GD-family corrections (no inner QMR yet).  Decisions (flags, block selection,
+ * configuration this library covers: Hermitian standard problem (B = I); Rayleigh-Ritz, refined and
+ * harmonic extraction (dav_refined.c); GD-family corrections and the inner QMR solver (dav_jdqmr.c).
+ * Decisions (flags, block selection,
  * restart sizes, tolerances) follow the reference line by line so that iteration counts match;
  * every n-long operation is a call into the sm_100a kernel layer (include/primme_b200.h):
  *     candidates X,R,|R|   -> pb200_dvwxr            (Num_update_VWXR)
@@ -414,16 +415,34 @@ static int solve_correction(pb_solver *S, double *evals, int numLocked, int basi
       if (!rc && !S->jd_work)
          rc = pb200_malloc(S->dev, sizeof(double) * (size_t)S->ld * 5 * PB_MAX(primme->maxBlockSize, 1),
                (void **)&S->jd_work);
+      /* right projectors (:942-980): the locked vectors, and x or K^{-1}x with x'K^{-1}x */
+      const double *RQ = NULL;
+      double *RX = NULL, *KinvX = NULL, xKinvBx[8];
+      int nRQ = 0;
+      if (cp->projectors.RightQ) RQ = S->evecs, nRQ = sizeEvecs;
+      if (!rc && cp->projectors.RightX) {
+         if (cp->precondition && cp->projectors.SkewX) {
+            rc = pb200_malloc(S->dev, sizeof(double) * (size_t)S->ld * blockSize, (void **)&KinvX);
+            if (!rc) rc = pb_apply_precond(S, x, S->ld, KinvX, S->ld, blockSize);
+            if (!rc) rc = pb200_dcolumn_dots(S->dev, S->n, x, S->ld, KinvX, S->ld, blockSize, xKinvBx);
+            if (!rc) rc = pb_reduce_panel(S, xKinvBx, blockSize, 1, blockSize);
+            RX = KinvX;
+         } else {
+            RX = x;
+            for (int b = 0; b < blockSize; b++) xKinvBx[b] = 1.0;
+         }
+      }
       if (!rc) {
          double blockRitzVals[8];
          for (int b = 0; b < blockSize; b++) blockRitzVals[b] = ritzVals[iev[b]];
          double *sol = S->jd_work + (size_t)S->ld * 4 * PB_MAX(primme->maxBlockSize, 1);
          int touch1 = S->touch;
          rc = pb_inner_solve(S, blockSize, x, S->ld, r, S->ld, blockNorms, Q, S->ldevecs, nQ, useX, sol, S->ld,
-               blockRitzVals, shifts, &touch1, S->jd_work);
+               blockRitzVals, shifts, &touch1, S->jd_work, RQ, S->ldevecs, nRQ, RX, S->ld, xKinvBx);
          S->touch = PB_MAX(S->touch, touch1);
          if (!rc) rc = pb200_copy_d2d(S->dev, sol, S->ld, x, S->ld, S->n, blockSize, 8);
       }
+      if (KinvX) pb200_free(S->dev, KinvX);
    } else if (cp->projectors.RightX && cp->projectors.SkewX) {
       /* exact Olsen projector (correction.c:695-774): x <- K^{-1}r - (x'K^{-1}r / x'K^{-1}x) K^{-1}x */
       double *tmp = NULL;

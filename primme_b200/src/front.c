@@ -326,9 +326,9 @@ static int check_scope(primme_params *p) {
             (p->globalSumReal && p->globalSumReal_type != primme_op_default &&
                   p->globalSumReal_type != primme_op_double))
       why = "callback datatypes other than double";
-   else if (p->correctionParams.maxInnerIterations != 0 &&
-            (p->correctionParams.projectors.RightQ || p->correctionParams.projectors.RightX))
-      why = "inner QMR iterations with right / skew projectors (only the JDQMR and JDQMR_ETol presets)";
+   else if (p->correctionParams.maxInnerIterations != 0 && p->correctionParams.precondition > 0 &&
+            p->correctionParams.projectors.RightQ && p->correctionParams.projectors.SkewQ)
+      why = "inner QMR iterations with the skew-Q projector and a preconditioner (K^{-1}Q and its factorised Gram matrix)";
    else if (p->maxBlockSize > 8) why = "maxBlockSize > 8";
    if (!why) return 0;
    if (p->outputFile && p->printLevel >= 1 && p->procID == 0)

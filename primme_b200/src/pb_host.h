@@ -160,7 +160,7 @@ void pb_dyn_recommend(primme_params *primme, const pb_cost_model *m);
 /* dav_jdqmr.c */
 int pb_inner_solve(pb_solver *S, int blockSize, double *x, int64_t ldx, double *r, int64_t ldr, const double *rnorm,
       const double *Q, int64_t ldQ, int nQ, int useX, double *sol, int64_t ldsol, const double *eval, double *shift,
-      int *touch, double *work);
+      int *touch, double *work, const double *RQ, int64_t ldRQ, int nRQ, double *RX, int64_t ldRX, double *xKinvBx);
 
 /* dav_restart.c */
 int pb_restart(pb_solver *S, int basisSize, int *ievSize, double *evals, double *resNorms,

@@ -66,7 +66,7 @@ class CsrHost(C.Structure):
 
 
 def solve(which, csr, numEvals, target=api.primme_smallest, method=api.PRIMME_GD_Olsen_plusK, jacobi=False,
-          nthreads=1, init_vecs=None, **kw):
+          nthreads=1, init_vecs=None, projectors=None, **kw):
     """Run dprimme through `which` in {"reference", "hostcheck", "product"} on the CSR triple.
     Returns dict(evals, rnorms, evecs (n x k, column order), ret, stats, initSize)."""
     indptr, indices, data = csr
@@ -100,6 +100,9 @@ def solve(which, csr, numEvals, target=api.primme_smallest, method=api.PRIMME_GD
             p.applyPreconditioner = C.cast(lib.primme_b200_jacobi_apply, C.c_void_p).value
     if method is not None:
         assert lib.primme_set_method(method, C.byref(p)) == 0
+    if projectors is not None:   # (LeftQ, LeftX, RightQ, RightX, SkewQ, SkewX) on top of the preset
+        pr = p.correctionParams.projectors
+        pr.LeftQ, pr.LeftX, pr.RightQ, pr.RightX, pr.SkewQ, pr.SkewX = projectors
 
     ncols = p.numOrthoConst + max(numEvals, p.initSize)
     evals = np.zeros(numEvals)

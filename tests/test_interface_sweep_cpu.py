@@ -4,8 +4,8 @@ pairs x smallest / largest / closest_abs / closest_geq x Rayleigh-Ritz / refined
 reference's own driver (compiled unchanged, linked against the host-check build: product host code over the
 CPU restatement of the kernels) and verified by its check_solution against the STORED solutions
 tests/sol_testi-*_double.  Everything inside the scope of this library must pass; the rest must be refused
-with PRIMME_FUNCTION_UNAVAILABLE (-44) before any work: PRIMME_JDQR (right / skew projectors) and the presets
-whose block size equals numEvals when that exceeds the 8-column panels of the kernels."""
+with PRIMME_FUNCTION_UNAVAILABLE (-44) before any work: the presets whose block size equals numEvals when
+that exceeds the 8-column panels of the kernels."""
 import os
 import shutil
 import subprocess
@@ -21,8 +21,6 @@ DRIVER = os.path.join(ROOT, "oracle", "_ref", "driver", "primme_double_hostcheck
 
 
 def out_of_scope(name, method):
-    if method == "JDQR":
-        return True
     n, nevals = int(name.split("-")[1]), int(name.split("-")[-3])
     return method in ("STEEPEST_DESCENT", "LOBPCG_OrthoBasis") and nevals > 8      # maxBlockSize = numEvals
 
@@ -52,5 +50,5 @@ def test_generated_interface_configurations(tmp_path):
         elif rc != 0:
             wrong.append((name, rc, tail[-200:]))
     assert not wrong, wrong[:10]
-    assert refused == 310 and len(results) - refused == 2882
+    assert refused == 10 and len(results) - refused == 3182
     shutil.rmtree(work, ignore_errors=True)

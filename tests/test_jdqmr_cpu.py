@@ -28,6 +28,17 @@ EXACT = {
     "aniso_jdqmr_jacobi": (MATRICES["aniso3d"], 5, dict(method=api.PRIMME_JDQMR, eps=1e-9, jacobi=True)),
     "aniso_etol_locking": (MATRICES["aniso3d"], 5, dict(method=api.PRIMME_JDQMR_ETol, eps=1e-9, jacobi=True, locking=1)),
     "lap2d_jdqmr_noprec": (MATRICES["lap2d"], 3, dict(method=api.PRIMME_JDQMR, eps=1e-8)),
+    # right projectors (correction.c:942-980, inner_solve.c:714-812): PRIMME_JDQR without a preconditioner
+    # (orthogonal right projectors on the locked vectors and on x), and the skew-X projector
+    # (I - K^{-1}x x' / x'K^{-1}x) with the Jacobi preconditioner on top of the JDQMR presets
+    "aniso_jdqr": (MATRICES["aniso3d"], 4, dict(method=api.PRIMME_JDQR, eps=1e-9)),
+    "aniso_jdqr_largest_block2": (MATRICES["aniso3d"], 4, dict(method=api.PRIMME_JDQR, eps=1e-9, target=api.primme_largest, maxBlockSize=2)),
+    "lap2d_jdqr_locking": (MATRICES["lap2d"], 5, dict(method=api.PRIMME_JDQR, eps=1e-9, locking=1)),
+    "aniso_jdqr_block3_locking": (MATRICES["aniso3d"], 6, dict(method=api.PRIMME_JDQR, eps=1e-9, locking=1, maxBlockSize=3)),
+    "aniso_jdqmr_skewX_jacobi": (MATRICES["aniso3d"], 4, dict(method=api.PRIMME_JDQMR, eps=1e-9, jacobi=True, projectors=(1, 1, 0, 1, 0, 1))),
+    "aniso_jdqmr_rightQ_skewX_block2": (MATRICES["aniso3d"], 4, dict(method=api.PRIMME_JDQMR, eps=1e-9, jacobi=True, maxBlockSize=2,
+                                                                      locking=1, projectors=(1, 1, 1, 1, 0, 1))),
+    "lap2d_etol_rightX": (MATRICES["lap2d"], 4, dict(method=api.PRIMME_JDQMR_ETol, eps=1e-9, jacobi=True, projectors=(0, 1, 0, 1, 0, 0))),
 }
 CLOSE = {
     "aniso_jdqmr_block4": (MATRICES["aniso3d"], 6, dict(method=api.PRIMME_JDQMR, eps=1e-9, maxBlockSize=4, jacobi=True)),

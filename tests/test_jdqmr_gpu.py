@@ -11,7 +11,9 @@ from primme_b200 import matrices as M
 pytestmark = pytest.mark.gpu
 
 CASES = ["lap3d_jdqmr", "lap3d_jdqmr_etol_jacobi", "lap3d_jdqmr_locking", "lap3d_etol_largest", "lap3d_jdqmr_block2",
-         "lap3d_min_time", "lap3d_closest_abs", "aniso_jdqmr_jacobi", "aniso_etol_locking", "lap2d_jdqmr_noprec"]
+         "lap3d_min_time", "lap3d_closest_abs", "aniso_jdqmr_jacobi", "aniso_etol_locking", "lap2d_jdqmr_noprec",
+         # right projectors: PRIMME_JDQR without a preconditioner, skew-X projector with the Jacobi preconditioner
+         "aniso_jdqr", "aniso_jdqr_block3_locking", "aniso_jdqmr_skewX_jacobi"]
 
 
 @pytest.mark.parametrize("name", CASES)

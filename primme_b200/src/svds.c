@@ -472,9 +472,24 @@ static void vec_free(svds_run *run, double *p) {
 
 static int vec_copy(svds_run *run, const double *src, int64_t lds, double *dst, int64_t ldd, int64_t rows, int cols) {
    if (rows <= 0 || cols <= 0 || src == dst) return 0;
-   if (run->device_mode) return pb200_copy_d2d(run->ctx, src, lds, dst, ldd, rows, cols, 8);
-   /* columns may overlap when packing to the left: move column by column in increasing order */
-   for (int j = 0; j < cols; j++) memmove(dst + (size_t)ldd * j, src + (size_t)lds * j, sizeof(double) * rows);
+   /* source and destination may overlap (the right vectors slide inside svecs): like the reference's
+    * Num_copy_matrix, never read a column after it has been overwritten */
+   const double *s_end = src + (size_t)lds * (cols - 1) + rows, *d_end = dst + (size_t)ldd * (cols - 1) + rows;
+   const int overlap = src < d_end && dst < s_end;
+   if (run->device_mode) {
+      if (!overlap) return pb200_copy_d2d(run->ctx, src, lds, dst, ldd, rows, cols, 8);
+      double *tmp = NULL;
+      if (pb200_malloc(run->ctx, sizeof(double) * (size_t)rows * cols, (void **)&tmp)) return PRIMME_MALLOC_FAILURE;
+      int rc = pb200_copy_d2d(run->ctx, src, lds, tmp, rows, rows, cols, 8);
+      if (!rc) rc = pb200_copy_d2d(run->ctx, tmp, rows, dst, ldd, rows, cols, 8);
+      pb200_ctx_sync(run->ctx);
+      pb200_free(run->ctx, tmp);
+      return rc;
+   }
+   if (dst < src)
+      for (int j = 0; j < cols; j++) memmove(dst + (size_t)ldd * j, src + (size_t)lds * j, sizeof(double) * rows);
+   else
+      for (int j = cols - 1; j >= 0; j--) memmove(dst + (size_t)ldd * j, src + (size_t)lds * j, sizeof(double) * rows);
    return 0;
 }
 

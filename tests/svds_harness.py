@@ -62,7 +62,7 @@ def get_member(lib, p, name):
 
 
 def solve(which, csr, shape, numSvals, target=primme_svds_largest, method=primme_svds_normalequations,
-          method_stage1=api.PRIMME_DEFAULT_METHOD, method_stage2=api.PRIMME_DEFAULT_METHOD, device_entry=False, **kw):
+          method_stage1=api.PRIMME_DEFAULT_METHOD, method_stage2=api.PRIMME_DEFAULT_METHOD, device_entry=False, constraints=None, guesses=None, **kw):
     """dprimme_svds through `which` in {"reference", "hostcheck", "product"}; host contract (host
     svecs, host matvec callback from oracle/csr_host.c).  Returns dict(svals, rnorms, U, V, ret, stats)."""
     m, n = shape
@@ -84,16 +84,31 @@ def solve(which, csr, shape, numSvals, target=primme_svds_largest, method=primme
     set_member(lib, p, "printLevel", 0)
     for k, v in kw.items():
         set_member(lib, p, k, v)
+    # svecs on input = [Uc U0 Vc V0]: orthogonality constraints and initial guesses, left then right
+    nc = constraints[0].shape[1] if constraints is not None else 0
+    ng = guesses[0].shape[1] if guesses is not None else 0
+    if nc:
+        set_member(lib, p, "numOrthoConst", nc)
+    if ng:
+        set_member(lib, p, "initSize", ng)
     assert lib.primme_svds_set_method(method, method_stage1, method_stage2, p) == 0
     svals, rn = np.zeros(numSvals), np.zeros(numSvals)
-    svecs = np.zeros((m + n) * numSvals)
+    ncols = nc + max(numSvals, ng)
+    svecs = np.zeros((m + n) * ncols)
+    if nc or ng:
+        left = [a for a in (constraints[0] if nc else None, guesses[0] if ng else None) if a is not None]
+        right = [a for a in (constraints[1] if nc else None, guesses[1] if ng else None) if a is not None]
+        L, Rr = np.hstack(left), np.hstack(right)
+        svecs[: m * (nc + ng)] = L.T.ravel()
+        svecs[m * (nc + ng): (m + n) * (nc + ng)] = Rr.T.ravel()
     # device_entry: cublas_dprimme_svds of the host-check library, where "device" memory is host memory --
     # runs the device-contract code path (kernels of the C-ABI for every vector operation) on the CPU
     entry = lib.cublas_dprimme_svds if device_entry else lib.dprimme_svds
     rc = entry(svals.ctypes.data, svecs.ctypes.data, rn.ctypes.data, p)
     k = get_member(lib, p, "initSize")
+    kt = k + nc   # the constraints come back in front of the triplets found
     out = dict(ret=rc, svals=svals, rnorms=rn, initSize=k,
-               U=svecs[: m * k].reshape(k, m).T.copy(), V=svecs[m * k: m * k + n * k].reshape(k, n).T.copy(),
+               U=svecs[: m * kt].reshape(kt, m).T[:, nc:].copy(), V=svecs[m * kt: (m + n) * kt].reshape(kt, n).T[:, nc:].copy(),
                stats={s: get_member(lib, p, "stats_" + s) for s in ("numOuterIterations", "numRestarts", "numMatvecs")},
                aNorm=get_member(lib, p, "aNorm"))
     lib.primme_svds_params_destroy(p)

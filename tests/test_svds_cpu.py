@@ -137,6 +137,33 @@ def test_svds_smallest_hybrid_hostcheck_matches_reference(case):
         assert abs(got["stats"][key] - ref["stats"][key]) <= max(4, 0.05 * ref["stats"][key]), (got["stats"], ref["stats"])
 
 
+@pytest.mark.parametrize("preset", [S.primme_svds_normalequations, S.primme_svds_hybrid, S.primme_svds_augmented])
+@pytest.mark.parametrize("shape", [(300, 80), (90, 260)])
+def test_svds_constraints_and_initial_guesses(preset, shape):
+    """svecs on input = [Uc U0 Vc V0] (primme_svds_c.c:640-668): the two leading triplets as orthogonality
+    constraints, perturbed next ones as initial guesses; the solver must return the triplets that follow"""
+    m, n = shape
+    csr = S.random_rect(m, n, 6, 17)
+    A = S.dense(csr, (m, n))
+    U, sv, Vt = np.linalg.svd(A, full_matrices=False)
+    rng = np.random.default_rng(3)
+    cons = (U[:, :2].copy(), Vt[:2].T.copy())
+    guess = (U[:, 2:4] + 1e-3 * rng.standard_normal((m, 2)), Vt[2:4].T + 1e-3 * rng.standard_normal((n, 2)))
+    args = dict(method=preset, method_stage1=api.PRIMME_GD_Olsen_plusK, method_stage2=api.PRIMME_GD_Olsen_plusK,
+                eps=1e-9 if preset == S.primme_svds_normalequations else 1e-11, constraints=cons, guesses=guess)
+    ref = S.solve("reference", csr, (m, n), 3, **args)
+    got = S.solve("hostcheck", csr, (m, n), 3, **args)
+    for r in (ref, got):
+        assert r["ret"] == 0 and r["initSize"] == 3
+        assert np.allclose(np.sort(r["svals"])[::-1], sv[2:5], rtol=1e-8)
+        assert np.abs(r["V"].T @ cons[1]).max() < 1e-7          # orthogonal to the constraints
+    assert np.allclose(got["svals"], ref["svals"], rtol=1e-10)
+    assert got["stats"] == ref["stats"], (got["stats"], ref["stats"])
+    # device-contract code path of the same (vector shuffles through the C-ABI)
+    dev = S.solve("hostcheck", csr, (m, n), 3, device_entry=True, **args)
+    assert dev["ret"] == 0 and np.allclose(dev["svals"], ref["svals"], rtol=1e-10) and dev["stats"] == got["stats"]
+
+
 def test_svds_default_method_runs_like_reference():
     """primme_svds_default = hybrid with PRIMME_DEFAULT_METHOD in both stages (run-time method choice:
     values and residuals are the criterion, not counts)"""

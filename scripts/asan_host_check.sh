@@ -14,5 +14,5 @@ trap "cp $TMP/orig.so $ROOT/oracle/_build/libprimme_hostcheck.so" EXIT
 cp $TMP/libprimme_hostcheck.so $ROOT/oracle/_build/libprimme_hostcheck.so
 LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 \
    python -m pytest $ROOT/tests/test_jdqmr_cpu.py $ROOT/tests/test_svds_cpu.py $ROOT/tests/test_host_logic.py \
-   $ROOT/tests/test_reference_golden_cpu.py $ROOT/tests/test_driver_cpu.py -q 2>&1 | tee $TMP/out.txt | tail -3
+   $ROOT/tests/test_reference_golden_cpu.py $ROOT/tests/test_driver_cpu.py $ROOT/tests/test_refined_cpu.py $ROOT/tests/test_edge_cases_cpu.py $ROOT/tests/test_python_api.py -q -m "not gpu" 2>&1 | tee $TMP/out.txt | tail -3
 echo "sanitizer reports: $(grep -c 'AddressSanitizer\|runtime error' $TMP/out.txt || true)"

@@ -102,7 +102,13 @@ int pb200_ctx_comm_free(pb200_ctx *ctx);
  * panel kernel then all-reduces its own panel over NVLink peer memory instead of a separate NCCL
  * call (see PbFin in csrc/pb200_internal.cuh).  export: allocates this rank's exchange buffer and
  * returns its cudaIpcMemHandle_t (64 bytes); the launcher all-gathers the handles; attach: opens the
- * peers' buffers (returns 1 and keeps NCCL for the panels if peer access is not possible). */
+ * peers' buffers.  attach is COLLECTIVE over the context's communicator: the ranks agree on the
+ * outcome, so it returns 0 on every rank (exchange on) or 1 on every rank (some rank could not open a
+ * peer buffer, or PB200_NO_PEER_EXCHANGE is set somewhere: all panels stay on NCCL).
+ * Platform assumption of the exchange (csrc/pb200_internal.cuh, PbFin): a 16-byte aligned
+ * st.volatile.v2.f64 to peer or mapped host memory is observed as one unit (true on x86-64 hosts
+ * and NVLink/PCIe peers of this platform; the tag sits in the upper 8 bytes and the host reads it
+ * with an acquire fence before the value). */
 int pb200_ctx_peer_export(pb200_ctx *ctx, void *handle64);
 int pb200_ctx_peer_attach(pb200_ctx *ctx, int nranks, int rank, const void *handles);
 int pb200_ctx_peer_active(pb200_ctx *ctx);

@@ -275,6 +275,8 @@ static int pb_poll_tagged(pb200_ctx *ctx, int cnt, long long seq) {
             }
          }
       }
+      // the value must not be read before the tag was seen (weakly ordered hosts, e.g. aarch64)
+      __atomic_thread_fence(__ATOMIC_ACQUIRE);
       ctx->h_pinned[e] = tv[2 * e];
    }
    return 0;
@@ -443,8 +445,13 @@ extern "C" int pb200_ctx_peer_export(pb200_ctx *ctx, void *handle64) {
 
 extern "C" int pb200_ctx_peer_attach(pb200_ctx *ctx, int nranks, int rank, const void *handles) {
    if (nranks < 1 || nranks > PB_MAX_PEERS || rank < 0 || rank >= nranks || !ctx->xchg_local) return PB200_ERR_ARG;
-   if (getenv("PB200_NO_PEER_EXCHANGE")) return 0;  // keep the NCCL all-reduce of the panels
-   for (int p = 0; p < nranks; p++) {
+   // The decision is COLLECTIVE: a rank that cannot open a peer's buffer (or has the exchange switched
+   // off) must not leave the others spinning for its pairs, so the local outcome is summed over the
+   // communicator (pb200_ctx_comm_init / pb200_ctx_set_comm must have run) and the exchange is
+   // enabled only if every rank succeeded.  Returns 0 (exchange on, everywhere) or 1 (panels stay on
+   // NCCL, everywhere).
+   int failed = getenv("PB200_NO_PEER_EXCHANGE") ? 1 : 0;
+   for (int p = 0; p < nranks && !failed; p++) {
       if (p == rank) {
          ctx->xchg_peer[p] = ctx->xchg_local;
          continue;
@@ -457,11 +464,26 @@ extern "C" int pb200_ctx_peer_attach(pb200_ctx *ctx, int nranks, int rank, const
          fprintf(stderr, "primme_b200: cudaIpcOpenMemHandle(rank %d) failed: %s -- panels stay on NCCL\n", p,
                cudaGetErrorString(e));
          cudaGetLastError();
-         for (int q = 0; q < p; q++)
-            if (q != rank && ctx->xchg_peer[q]) cudaIpcCloseMemHandle(ctx->xchg_peer[q]), ctx->xchg_peer[q] = NULL;
-         return 1;
+         failed = 1;
+         break;
       }
       ctx->xchg_peer[p] = (double2 *)ptr;
+   }
+   if (nranks > 1) {
+      if (!ctx->comm || ctx->nranks != nranks || ctx->rank != rank) {
+         // no communicator to agree over: refuse rather than risk a one-sided decision
+         failed = 1;
+      } else {
+         double f = (double)failed;
+         PB_CHK(pb200_allreduce_host(ctx, &f, 1));
+         failed = f > 0.0;
+      }
+   }
+   if (failed) {
+      for (int q = 0; q < nranks; q++)
+         if (q != rank && ctx->xchg_peer[q]) cudaIpcCloseMemHandle(ctx->xchg_peer[q]), ctx->xchg_peer[q] = NULL;
+      ctx->peer_on = 0;
+      return 1;
    }
    ctx->nranks = nranks, ctx->rank = rank;
    ctx->peer_on = 1;

@@ -495,14 +495,14 @@ static int restart_locking(pb_solver *S, int *restartSize, int basisSize, int *r
          int src = numLocked0 + i - left + primme->numOrthoConst;
          int dst = *numLocked + primme->numOrthoConst;
          if (src != dst)
-            CHK(pb200_copy_d2d(S->dev, S->evecs + (size_t)S->ldevecs * src, S->ldevecs,
-                  S->evecs + (size_t)S->ldevecs * dst, S->ldevecs, S->n, 1, 8));
+            CHKX(pb200_copy_d2d(S->dev, S->evecs + (size_t)S->ldevecs * src, S->ldevecs,
+                  S->evecs + (size_t)S->ldevecs * dst, S->ldevecs, S->n, 1, 8), free(ifailed));
          (*numLocked)++;
          if (S->lockedFlags) S->lockedFlags[*numLocked - 1] = flags[i];
-         CHK(pb_monitor(S, NULL, 0, NULL, NULL, 0, NULL, 0, evals, *numLocked, S->lockedFlags,
-               resNorms, -1, 0.0, NULL, 0.0, primme_event_locked));
-         CHK(pb_insertion_sort(eval, evals, resNorm, resNorms, flags[i], S->lockedFlags, S->perm,
-               *numLocked - 1, 0, primme));
+         CHKX(pb_monitor(S, NULL, 0, NULL, NULL, 0, NULL, 0, evals, *numLocked, S->lockedFlags,
+               resNorms, -1, 0.0, NULL, 0.0, primme_event_locked), free(ifailed));
+         CHKX(pb_insertion_sort(eval, evals, resNorm, resNorms, flags[i], S->lockedFlags, S->perm,
+               *numLocked - 1, 0, primme), free(ifailed));
          if (flags[i] == CONVERGED)
             primme->stats.maxConvTol = PB_MAX(primme->stats.maxConvTol, resNorm);
       }

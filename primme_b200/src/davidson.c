@@ -726,13 +726,13 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
             for (i = 0; i < maxNumRandoms; i++) {
                int basisSizeOut;
                const int useP0 = i == 0 && S->fusedP_nb == blockSize && S->fusedP_nb > 0;
-               CHK(pb_ortho_block_p0(S, S->V, S->ld, basisSize, basisSize + blockSize - 1, S->evecs,
+               CHKX(pb_ortho_block_p0(S, S->V, S->ld, basisSize, basisSize + blockSize - 1, S->evecs,
                      S->ldevecs, primme->numOrthoConst + numLocked, i == 0 ? Rlocked : NULL,
-                     ldRlocked, &basisSizeOut, useP0 ? S->fusedP : NULL, S->maxBasis + 8));
+                     ldRlocked, &basisSizeOut, useP0 ? S->fusedP : NULL, S->maxBasis + 8), free(Rlocked));
                S->fusedP_nb = 0;
                blockSize = basisSizeOut - basisSize;
                if (blockSize > 0 || availableBlockSize <= 0) break;
-               CHK(pb_fill_random(S, S->V + (size_t)S->ld * basisSize, S->ld, 1));
+               CHKX(pb_fill_random(S, S->V + (size_t)S->ld * basisSize, S->ld, 1), free(Rlocked));
                blockSize = 1;
             }
             if (i >= maxNumRandoms) {
@@ -762,16 +762,16 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
                            &Rlocked[(size_t)ldRlocked * i]));
                      double bn = S->blockNorms[i];
                      double newBlockNorm = sqrt(PB_MAX(bn * bn - normR * (1. + normXx), 0.0));
-                     CHK(pb_check_convergence(S, S->V + (size_t)S->ld * (basisSize + i), S->ld, 1,
+                     CHKX(pb_check_convergence(S, S->V + (size_t)S->ld * (basisSize + i), S->ld, 1,
                            NULL, 0, 0, numLocked, 0, 1, &flags[iev[i]], &newBlockNorm,
-                           &S->hVals[iev[i]], &reset, -1));
+                           &S->hVals[iev[i]], &reset, -1), free(Rlocked));
                      S->basisNorms[iev[i]] = newBlockNorm;
                      if (flags[iev[i]] == CONVERGED) {
                         flags[iev[i]] = PRACTICALLY_CONVERGED;
                         numConverged++;
-                        CHK(pb_monitor(S, S->hVals, basisSize, flags, &iev[i], 1, S->basisNorms,
+                        CHKX(pb_monitor(S, S->hVals, basisSize, flags, &iev[i], 1, S->basisNorms,
                               numConverged, NULL, 0, NULL, NULL, -1, -1.0, NULL, 0.0,
-                              primme_event_converged));
+                              primme_event_converged), free(Rlocked));
                      }
                   }
                }

@@ -371,9 +371,12 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
    primme_set_defaults(primme);
    if (primme->orth == primme_orth_default)
       primme->orth = primme->maxBlockSize > 1 ? primme_orth_explicit_I : primme_orth_implicit_I;
-   /* free to choose (reference primme_c.c:325-332 takes nLocal): round up to 16 elements so every
-    * basis column starts on a 128-byte boundary (bulk-copy / vector-load alignment) */
-   if (primme->ldOPs == -1) primme->ldOPs = (primme->nLocal + 15) / 16 * 16;
+   /* primme.ldOPs as the reference leaves it (primme_c.c:325-332: nLocal).  The basis itself is
+    * free to use a padded leading dimension (16 elements: every column starts on a 128-byte
+    * boundary for bulk copies / vector loads); that choice lives in S->ld only, so the caller's
+    * struct can be reused for a later, larger problem */
+   const int ld_default = primme->ldOPs == -1 || primme->ldOPs == 0;
+   if (ld_default) primme->ldOPs = primme->nLocal;
    if (evals == NULL && evecs == NULL && resNorms == NULL) return 0;
 
    if (primme->iseed[0] < 0 || primme->iseed[0] > 4095) primme->iseed[0] = primme->procID % 4096;
@@ -418,12 +421,13 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
    }
    if (device_mode && pb200_is_device_pointer(evecs) != 1) {
       if (own_ctx) pb200_ctx_destroy(S->dev);
+      primme->initSize = 0;
       return -31;
    }
    pb_registry_set_solver(primme, S->dev);
 
    S->n = primme->nLocal;
-   S->ld = primme->ldOPs;
+   S->ld = ld_default ? (primme->nLocal + 15) / 16 * 16 : primme->ldOPs;
    S->maxBasis = primme->maxBasisSize;
    S->maxRank = primme->numOrthoConst + primme->maxBasisSize + (primme->locking ? primme->numEvals : 0);
    const int mb = S->maxBasis, mr = S->maxRank;
@@ -456,7 +460,9 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
    S->hVecs = (double *)calloc((size_t)mb * mb, sizeof(double));
    S->prevhVecs = (double *)calloc((size_t)mb * mb, sizeof(double));
    S->fusedP = (double *)calloc((size_t)(mb + 8) * 8, sizeof(double));
-   S->fuse_allowed = getenv("PB200_NO_FUSE_GRAM") ? 0 : 1;
+   /* the fused candidates sweep leaves residuals, not Ritz vectors, in the block: only the
+    * built-in test (which ignores evec) may run on it */
+   S->fuse_allowed = (getenv("PB200_NO_FUSE_GRAM") || primme->convTestFun != conv_test_absolute) ? 0 : 1;
    if (primme->orth == primme_orth_explicit_I) {
       S->VtBV = (double *)calloc((size_t)mr * mr, sizeof(double));
       S->fVtBV = (double *)calloc((size_t)mr * mr, sizeof(double));

@@ -86,6 +86,16 @@ typedef struct pb_solver {
          return chk_err_;                                                                \
       }                                                                                  \
    } while (0)
+/* same, releasing the function's temporaries first */
+#define CHKX(call, cleanup)                                                              \
+   do {                                                                                  \
+      int chk_err_ = (call);                                                             \
+      if (chk_err_ != 0) {                                                               \
+         cleanup;                                                                        \
+         pb_report(S ? S->primme : NULL, __FILE__, __LINE__, chk_err_, #call);           \
+         return chk_err_;                                                                \
+      }                                                                                  \
+   } while (0)
 void pb_report(primme_params *primme, const char *file, int line, int err, const char *what);
 
 /* davidson.c */

@@ -17,9 +17,9 @@
  * eigensolver's collectives and the triplet-level sums go through primme_svds.globalSumReal or the
  * communicator of the attached kernel context; the user's matrixMatvec owns the exchange of the operator.
  * Refused with PRIMME_FUNCTION_UNAVAILABLE = -44 like a reference build without the feature: every
- * precision but double; and by the eigensolver underneath (front.c:check_scope) what it
- * does not cover -- refined extraction, which the augmented operator selects for smallest /
- * closest_abs targets (primme_svds_interface.c:385-391).
+ * precision but double; and whatever the eigensolver underneath refuses (front.c:check_scope).  The
+ * refined extraction that the augmented operator selects for smallest / closest_abs targets
+ * (primme_svds_interface.c:385-391) runs (dav_refined.c).
  */
 #include "pb_host.h"
 #include "../../include/primme_svds.h"
@@ -552,6 +552,9 @@ static int vec_random(svds_run *run, primme_params *primme, int64_t rows, double
 static int svds_global_sum(svds_run *run, double *buf, int count) {
    primme_svds_params *s = run->svds;
    if (s->numProcs <= 1 || count <= 0) return 0;
+   /* every buffer summed here comes from vec_dots; with a multi-rank kernel context those dots were
+    * already all-reduced on the device (pb200_dcolumn_dots), as in the eigensolver's pb_reduce_panel */
+   if (run->device_mode && run->ctx && pb200_ctx_nranks(run->ctx) > 1) return 0;
    const double t0 = hl_wtime();
    int ierr = 0;
    if (s->globalSumReal) {

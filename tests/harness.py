@@ -66,7 +66,7 @@ class CsrHost(C.Structure):
 
 
 def solve(which, csr, numEvals, target=api.primme_smallest, method=api.PRIMME_GD_Olsen_plusK, jacobi=False,
-          nthreads=1, init_vecs=None, projectors=None, **kw):
+          nthreads=1, init_vecs=None, projectors=None, tweak=None, **kw):
     """Run dprimme through `which` in {"reference", "hostcheck", "product"} on the CSR triple.
     Returns dict(evals, rnorms, evecs (n x k, column order), ret, stats, initSize)."""
     indptr, indices, data = csr
@@ -104,6 +104,8 @@ def solve(which, csr, numEvals, target=api.primme_smallest, method=api.PRIMME_GD
         pr = p.correctionParams.projectors
         pr.LeftQ, pr.LeftX, pr.RightQ, pr.RightX, pr.SkewQ, pr.SkewX = projectors
 
+    if tweak is not None:        # last-minute edits of the struct (custom callbacks, ...)
+        tweak(p)
     ncols = p.numOrthoConst + max(numEvals, p.initSize)
     evals = np.zeros(numEvals)
     rnorms = np.zeros(numEvals)

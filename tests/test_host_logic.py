@@ -89,3 +89,38 @@ def test_error_codes():
     assert lib.primme_set_method(api.PRIMME_JDQR, C.byref(p)) == 0
     p.matrixMatvec = 1
     assert lib.dprimme(ev.ctypes.data, ev.ctypes.data, ev.ctypes.data, C.byref(p)) == -44
+
+
+def test_custom_conv_test_sees_unit_ritz_vectors():
+    """A user convTestFun is handed the Ritz VECTOR as evec (reference auxiliary_eigs_normal.c:408-443),
+    never the residual block of the fused candidates sweep; with a block size > 1 and no preconditioner
+    (the shape that fuses with the built-in test) the counts equal the reference's with the same callback."""
+    import ctypes as C
+    from primme_b200 import api, matrices as M
+    csr = M.laplacian_nd((14, 11))
+    n = len(csr[0]) - 1
+    CONV = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int),
+                       C.c_void_p, C.POINTER(C.c_int))
+    out = {}
+    for which in ("reference", "hostcheck"):
+        norms = []
+
+        def conv(eval_, evec, rnorm, isconv, primme, ierr, norms=norms):
+            if evec:
+                v = np.ctypeslib.as_array(C.cast(evec, C.POINTER(C.c_double)), shape=(n,))
+                norms.append(float(np.linalg.norm(v)))
+            isconv[0] = 1 if rnorm[0] < 1e-9 * 8.0 else 0
+            ierr[0] = 0
+
+        cb = CONV(conv)
+
+        def tweak(p, cb=cb):
+            p.convTestFun = C.cast(cb, C.c_void_p).value
+
+        r = H.solve(which, csr, 4, method=api.PRIMME_GD_Olsen_plusK, maxBlockSize=2, maxBasisSize=20, aNorm=8.0,
+                    eps=1e-9, tweak=tweak)
+        assert r["ret"] == 0
+        assert len(norms) > 10 and np.allclose(norms, 1.0, atol=1e-8), (which, min(norms), max(norms))
+        out[which] = (r["stats"]["numOuterIterations"], r["stats"]["numMatvecs"], r["evals"])
+    assert out["reference"][:2] == out["hostcheck"][:2]
+    assert np.allclose(out["reference"][2], out["hostcheck"][2], rtol=1e-10)

@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--sampler", default="nvml", choices=["nvml", "smi", "none"],
                     help="clock/throttle sampling during the timed region (none: measurement experiments only)")
     ap.add_argument("--sampler-period", type=float, default=0.25)
+    ap.add_argument("--c5-n", type=int, default=10**7,
+                    help="rows of the power-law matrix of config C5 reported in the `c5` block (0: skip)")
+    ap.add_argument("--c5-steps", type=int, default=2)
     ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
                     help="N>1: row-sharded solve with NCCL (strong scaling) or independent replicas")
     return ap.parse_args()
@@ -172,6 +175,112 @@ def run_reference(args, csr, rank):
             times.append(r["stats"]["elapsedTime"] or dt)
             mvs.append(r["stats"]["numMatvecs"])
     return sum(mvs) / sum(times), sum(times) / len(times), ncores, mvs[0]
+
+
+C5 = dict(numEvals=20, maxBasisSize=64, maxBlockSize=8, eps=1e-8)
+
+
+def run_c5(args, lib, api, M, ctx, rank, world, dist):
+    """Config C5 (BASELINE.json configs[4]): dprimme, symmetric power-law CSR n = 1e7, nnz ~ 1.5e8, 20 largest,
+    GD_Olsen_plusK, maxBlockSize 8, maxBasisSize 64, eps 1e-8; the SAME matrix row-sharded over the ranks
+    (every rank generates only its rows), compacted halo pushed over NVLink peer memory, panels all-reduced
+    inside the kernels.  Returns the `c5` block of the JSON line (rank 0) -- the strong-scaling curve of the
+    configuration the 8-GPU target is quoted on."""
+    import torch
+    n = args.c5_n
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    nloc = hi - lo
+    t0 = time.perf_counter()
+    ip, ix, da = M.power_law_rows(n, lo, hi)
+    t_gen = time.perf_counter() - t0
+    nnz_loc = len(ix)
+    A, D = C.c_void_p(), C.c_void_p()
+    assert lib.pb200_csr_create(ctx, nloc, n, nnz_loc, ip.ctypes.data, ix.ctypes.data, da.ctypes.data, 0, 0, C.byref(A)) == 0
+    del ip, ix, da
+    counts = np.array([n * (r + 1) // world - n * r // world for r in range(world)], dtype=np.int64)
+    halo = {}
+    if world > 1:
+        import multi_gpu_worker as MG
+        MG.declare(lib)
+        assert lib.pb200_dist_csr_create(ctx, A, counts.ctypes.data, world, C.byref(D)) == 0
+        nl, nh, sent, peer = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+        lib.pb200_dist_csr_info(D, C.byref(nl), C.byref(nh), C.byref(sent), C.byref(peer))
+        halo = dict(rows_received_per_block=nh.value, rows_pushed_per_block=sent.value, peer_memory=peer.value)
+    k = C5["numEvals"]
+    devecs = C.c_void_p()
+    assert lib.pb200_malloc(ctx, 8 * max(nloc, 1) * k, C.byref(devecs)) == 0
+    evals, rn = np.zeros(k), np.zeros(k)
+
+    def solve():
+        p = api.new_params(lib, n, target=api.primme_largest, **C5)
+        assert lib.primme_set_method(api.PRIMME_GD_Olsen_plusK, C.byref(p)) == 0
+        if world > 1:
+            p.numProcs, p.procID, p.nLocal, p.ldevecs = world, rank, nloc, max(nloc, 1)
+            p.matrix = D
+            p.matrixMatvec = C.cast(lib.primme_b200_dist_csr_matvec, C.c_void_p).value
+        else:
+            p.ldevecs = n
+            p.matrix = A
+            p.matrixMatvec = C.cast(lib.primme_b200_csr_matvec, C.c_void_p).value
+        lib.primme_b200_attach_ctx(C.byref(p), ctx)
+        rc = lib.cublas_dprimme(evals.ctypes.data, devecs, rn.ctypes.data, C.byref(p))
+        lib.primme_b200_attach_ctx(C.byref(p), None)
+        assert rc == 0, rc
+        return p
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    solve()  # warm-up: allocations, gather-layout timing, first-launch attributes
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    mv = 0
+    for _ in range(args.c5_steps):
+        p = solve()
+        mv += p.stats.numMatvecs
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    stats = api.stats_dict(p)
+    lib.pb200_ctx_set_profiling(ctx, 1)
+    tw = time.perf_counter()
+    solve()
+    wall = time.perf_counter() - tw
+    kinds = ["spmm", "ortho_sweep", "vwxr", "utils", "panel_reduce"]
+    kern = {}
+    dev_ms = 0.0
+    for i, name in enumerate(kinds):
+        cnt, pms, pby = C.c_int64(), C.c_double(), C.c_double()
+        lib.pb200_ctx_get_profile(ctx, i, C.byref(cnt), C.byref(pms), C.byref(pby))
+        dev_ms += pms.value
+        kern[name] = {"GBps": round((pby.value / 1e9) / (pms.value / 1e3), 1) if pms.value > 0 else 0.0,
+                      "ms": round(pms.value, 3), "launches": cnt.value}
+    lib.pb200_ctx_set_profiling(ctx, 0)
+    nnz = nnz_loc
+    if world > 1:
+        t = torch.tensor([float(nnz_loc)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        nnz = int(t.item())
+    out = {"workload": f"dprimme power-law CSR n={n}, 20 largest, GD_Olsen_plusK, blockSize=8, maxBasisSize=64, eps=1e-8",
+           "n": n, "nnz": nnz, "n_gpus": world, "scaling": "strong",
+           "ms_per_solve": ms / args.c5_steps, "matvecs_per_s": mv / (ms * 1e-3),
+           "matvecs_per_solve": stats["numMatvecs"], "outer_iterations": stats["numOuterIterations"],
+           "restarts": stats["numRestarts"], "largest_eval": float(evals[0]), "max_resnorm": float(rn.max()),
+           "kernels_rank0": kern, "device_time_share_of_solve_rank0": dev_ms / (wall * 1e3),
+           "halo_rank0": dict(halo, bytes_pushed_per_block=halo.get("rows_pushed_per_block", 0) * 64),
+           "generate_s_rank0": round(t_gen, 1)}
+    lib.pb200_free(ctx, devecs)
+    if world > 1:
+        lib.pb200_dist_csr_destroy(ctx, D)
+    lib.pb200_csr_destroy(ctx, A)
+    return out
 
 
 def main():
@@ -390,6 +499,13 @@ def main():
             cpu_baseline = {"value": None, "unit": "matvecs/s", "cores": os.cpu_count(), "kind": "reference",
                             "sample": f"unavailable: {e}"}
 
+    c5 = None
+    if args.c5_n > 0 and (sharded or world == 1):
+        try:
+            c5 = run_c5(args, lib, api, M, ctx, rank, world, dist if world > 1 else None)
+        except Exception as e:  # never lose the headline line
+            c5 = {"error": repr(e)}
+
     if rank == 0:
         line = {"metric": "matvecs_per_s", "value": value, "unit": "matvecs/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -407,7 +523,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "matvecs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e / max(1, min(args.steps, 3))},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "c5": c5}
         print(json.dumps(line))
 
     lib.pb200_free(ctx, devecs)

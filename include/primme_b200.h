@@ -84,6 +84,10 @@ int pb200_csr_destroy(pb200_ctx *ctx, pb200_csr *A);
 int64_t pb200_csr_nnz(const pb200_csr *A);
 int pb200_dspmm(pb200_ctx *ctx, const pb200_csr *A, const double *X, int64_t ldx, double *Y,
       int64_t ldy, int ncols);
+/* complex twin (zprimme): A created with is_complex = 1; X, Y interleaved (re,im), column-major,
+ * leading dimensions in complex elements */
+int pb200_zspmm(pb200_ctx *ctx, const pb200_csr *A, const void *X, int64_t ldx, void *Y,
+      int64_t ldy, int ncols);
 /* Y = A^T X (used by the SVD normal-equations operator, src/svds/primme_svds_c.c:1337-1351);
  * requires the transposed copy built by pb200_csr_build_transpose. */
 int pb200_csr_build_transpose(pb200_ctx *ctx, pb200_csr *A);
@@ -92,8 +96,14 @@ int pb200_dspmm_t(pb200_ctx *ctx, const pb200_csr *A, const double *X, int64_t l
 
 /* ---- row-sharded operator (one process per GPU) --------------------------------
  * A_local holds this rank's rows with GLOBAL column indices; counts_host[r] = rows of rank r.
- * Y_local = A_local * allgather(X_local): the SpMV halo is one grouped NCCL exchange over
- * NVLink.  Replaces the MPI matvec of reference examples/ex_eigs_mpi.c. */
+ * pb200_dist_csr_create (collective over the context's communicator) finds the distinct remote
+ * columns each rank references, exchanges the lists, REMAPS A_local's column indices in place to
+ * [own rows | compacted halo] (A_local then belongs to the operator: do not use it with pb200_dspmm)
+ * and maps every rank's gather buffer into its peers (CUDA IPC over NVLink).  Per block:
+ * Y_local = A_local * [X_local; halo]: one kernel packs the local block and pushes the rows each peer
+ * needs into the peer's buffer, the SpMM kernel waits for the peers' flags -- no NCCL call on the data
+ * path (compacted ncclSend/ncclRecv only if peer mapping is unavailable).  Replaces the MPI matvec of
+ * reference examples/ex_eigs_mpi.c:106-112,209-218. */
 typedef struct pb200_dist_csr pb200_dist_csr;
 int pb200_comm_unique_id(void *id128);
 int pb200_ctx_comm_init(pb200_ctx *ctx, int nranks, int rank, const void *id128);
@@ -117,6 +127,12 @@ int pb200_dist_csr_create(pb200_ctx *ctx, pb200_csr *A_local, const int64_t *cou
 int pb200_dist_csr_destroy(pb200_ctx *ctx, pb200_dist_csr *D);
 int pb200_ddist_spmm(pb200_ctx *ctx, pb200_dist_csr *D, const double *X, int64_t ldx, double *Y,
       int64_t ldy, int ncols);
+int pb200_zdist_spmm(pb200_ctx *ctx, pb200_dist_csr *D, const void *X, int64_t ldx, void *Y,
+      int64_t ldy, int ncols);
+/* local rows, compacted halo rows received per block, rows pushed to peers per block, 1 if the halo
+ * travels over peer memory (0: NCCL point-to-point) */
+int pb200_dist_csr_info(const pb200_dist_csr *D, int64_t *nloc, int64_t *nhalo, int64_t *rows_sent_per_block,
+      int *peer_halo);
 
 /* ------------------------------------------------- K2/K3/K4: fused block-ortho row sweep -- */
 /* One pass over the rows of [Q V X]:

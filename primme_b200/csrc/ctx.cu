@@ -54,6 +54,7 @@ extern "C" int pb200_ctx_create(pb200_ctx **out, int device) {
    ctx->ortho_exact = getenv("PB200_NO_ORTHO_EXACT") ? 0 : 1;
    ctx->use_tma_vwxr = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_VWXR")) ? 0 : 1;
    ctx->use_tma_spmm = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_SPMM")) ? 0 : 1;
+   ctx->spmm_v3 = getenv("PB200_SPMM_V3") ? atoi(getenv("PB200_SPMM_V3")) : 2;
    *out = ctx;
    return 0;
 }
@@ -522,6 +523,12 @@ static nccl_void_fn p_ncclGroupStart = NULL, p_ncclGroupEnd = NULL;
 static nccl_uid_fn p_ncclGetUniqueId = NULL;
 static nccl_init_fn p_ncclCommInitRank = NULL;
 static nccl_destroy_fn p_ncclCommDestroy = NULL;
+typedef int (*nccl_allgather_fn)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef int (*nccl_send_fn)(const void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_recv_fn)(void *, size_t, int, int, void *, cudaStream_t);
+static nccl_allgather_fn p_ncclAllGather = NULL;
+static nccl_send_fn p_ncclSend = NULL;
+static nccl_recv_fn p_ncclRecv = NULL;
 enum { PB_NCCL_FLOAT64 = 8, PB_NCCL_SUM = 0 };
 
 static int pb_nccl_load(void) {
@@ -539,8 +546,12 @@ static int pb_nccl_load(void) {
    p_ncclGetUniqueId = (nccl_uid_fn)dlsym(h, "ncclGetUniqueId");
    p_ncclCommInitRank = (nccl_init_fn)dlsym(h, "ncclCommInitRank");
    p_ncclCommDestroy = (nccl_destroy_fn)dlsym(h, "ncclCommDestroy");
+   p_ncclAllGather = (nccl_allgather_fn)dlsym(h, "ncclAllGather");
+   p_ncclSend = (nccl_send_fn)dlsym(h, "ncclSend");
+   p_ncclRecv = (nccl_recv_fn)dlsym(h, "ncclRecv");
    return (p_ncclAllReduce && p_ncclBroadcast && p_ncclGroupStart && p_ncclGroupEnd &&
-                p_ncclGetUniqueId && p_ncclCommInitRank && p_ncclCommDestroy)
+                p_ncclGetUniqueId && p_ncclCommInitRank && p_ncclCommDestroy && p_ncclAllGather && p_ncclSend &&
+                p_ncclRecv)
                 ? 0
                 : PB200_ERR_CUDA;
 }
@@ -585,6 +596,22 @@ int pb_nccl_allgatherv_cols(pb200_ctx *ctx, const double *X, int64_t ldx, double
       }
    if (p_ncclGroupEnd() != 0) return PB200_ERR_CUDA;
    return 0;
+}
+
+// byte-wise helpers for the setup of the row-sharded operator (dist.cu); device buffers, in-stream
+int pb_nccl_allgather(pb200_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank) {
+   if (ctx->nranks <= 1 || !ctx->comm) return PB200_ERR_ARG;
+   return p_ncclAllGather(send, recv, bytes_per_rank, 0 /* ncclInt8 */, ctx->comm, ctx->stream) == 0 ? 0 : PB200_ERR_CUDA;
+}
+int pb_nccl_group(pb200_ctx *ctx, int start) {
+   (void)ctx;
+   return (start ? p_ncclGroupStart() : p_ncclGroupEnd()) == 0 ? 0 : PB200_ERR_CUDA;
+}
+int pb_nccl_send(pb200_ctx *ctx, const void *buf, size_t bytes, int peer) {
+   return p_ncclSend(buf, bytes, 0, peer, ctx->comm, ctx->stream) == 0 ? 0 : PB200_ERR_CUDA;
+}
+int pb_nccl_recv(pb200_ctx *ctx, void *buf, size_t bytes, int peer) {
+   return p_ncclRecv(buf, bytes, 0, peer, ctx->comm, ctx->stream) == 0 ? 0 : PB200_ERR_CUDA;
 }
 
 extern "C" int pb200_ctx_set_comm(pb200_ctx *ctx, void *nccl_comm, int nranks, int rank) {

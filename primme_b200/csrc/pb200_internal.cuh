@@ -67,6 +67,7 @@ struct pb200_ctx {
    int64_t launches;
    int use_tma_vwxr;      // same switch for the VWXR kernel alone
    int use_tma_spmm;      // persistent bulk-copy SpMM (v2)
+   int spmm_v3;           // gather layout for b >= 2: 0 column-major (v2), 1 row-major copy (v3), 2 timed once per matrix (default)
    int use_wide;          // v3 wide VWXR kernel for the restart sweep
    int use_mma_vwxr;      // tensor-map TMA + DMMA VWXR kernel (default)
    int fuse_gram;         // candidates sweep also delivers the first Gram panel of the block ortho
@@ -217,6 +218,50 @@ __device__ __forceinline__ void pb_finish_device(const PbFin &f, int tid, int nt
 }
 #endif
 
+// ------------------------------------------------------------------ CSR matrix (spmm.cu) ----
+struct pb200_csr {
+   int64_t nrows, ncols, nnz;
+   int64_t *d_rowptr;  // nrows+1, 0-based
+   int32_t *d_colind;  // 0-based
+   double *d_vals;
+   int is_complex;
+   // schedule
+   int nblocks;
+   int64_t *d_blk_row0;  // nblocks+1 : first row of each block (long-row chunks repeat the row)
+   int64_t *d_blk_nz0;   // nblocks   : first nonzero handled by the block
+   int32_t *d_blk_nnz;   // nblocks   : nonzeros handled by the block
+   int32_t *d_blk_kind;  // 0 = group of whole rows, 1 = chunk of one long row
+   int nlong;            // number of long-row chunks
+   int lpr;              // lanes per row for group blocks
+   double *d_long_part;  // partial sums of long-row chunks [nlongchunks][16]
+   int32_t *d_long_slot; // per block: slot index in d_long_part (kind 1) else -1
+   // fix-up list for long rows
+   int nlongrows;
+   int64_t *d_lr_row;    // row id
+   int32_t *d_lr_slot0;  // first slot
+   int32_t *d_lr_nslots; // number of chunks
+   pb200_csr *T;
+   // row-major gather buffer of the v3 kernel: G[col][bp] = X(col, 0:b) (packed per call)
+   double *d_G;
+   size_t G_cap;  // doubles
+   int layout_choice[4];  // per block width 1/2/4/8: 0 not timed yet, 1 column-major gathers (v2), 2 row-major (v3)
+};
+
+// halo protocol of the row-sharded operator (dist.cu) seen by the SpMM kernel: wait until every
+// source rank in src_mask has flagged block `seq` in this rank's flags[] before the first gather;
+// when the grid is done, store `seq` to ack[r] (peer memory) for every r in ack_mask
+struct PbSpSync {
+   const unsigned long long *flags;
+   unsigned long long seq;
+   unsigned int src_mask, ack_mask;
+   unsigned int *counter;
+   unsigned long long *ack[PB_MAX_PEERS];
+};
+int pb_spmm_bp(int b);
+int pb_spmm_pack(pb200_ctx *ctx, const void *X, int64_t ldx, int64_t nrows, int b, int bp, int is_complex, double *G);
+int pb_spmm_gathered(pb200_ctx *ctx, const pb200_csr *A, const double *G, int bp, void *Y, int64_t ldy, int b,
+      const PbSpSync *sync);
+
 // grow helpers (host side)
 int pb_ensure_partials(pb200_ctx *ctx, size_t doubles);
 int pb_ensure_scratch(pb200_ctx *ctx, size_t bytes);
@@ -236,6 +281,10 @@ int pb_collect_panel(pb200_ctx *ctx, const PbFin *f);
 // (the caller then uses the NCCL path), 0 with the reduced panel in ctx->h_pinned[0..cnt)
 int pb_fin_contribute_zeros(pb200_ctx *ctx, int cnt);
 int pb_nccl_allreduce_dev(pb200_ctx *ctx, double *dbuf, int count);
+int pb_nccl_allgather(pb200_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);
+int pb_nccl_group(pb200_ctx *ctx, int start);
+int pb_nccl_send(pb200_ctx *ctx, const void *buf, size_t bytes, int peer);
+int pb_nccl_recv(pb200_ctx *ctx, void *buf, size_t bytes, int peer);
 int pb_nccl_allgatherv_cols(pb200_ctx *ctx, const double *X, int64_t ldx, double *Y, int64_t ldy,
       const int64_t *counts, const int64_t *displs, int ncols);
 

@@ -19,29 +19,6 @@
 #include <string.h>
 #include <vector>
 
-struct pb200_csr {
-   int64_t nrows, ncols, nnz;
-   int64_t *d_rowptr;  // nrows+1, 0-based
-   int32_t *d_colind;  // 0-based
-   double *d_vals;
-   int is_complex;
-   // schedule
-   int nblocks;
-   int64_t *d_blk_row0;  // nblocks+1 : first row of each block (long-row chunks repeat the row)
-   int64_t *d_blk_nz0;   // nblocks   : first nonzero handled by the block
-   int32_t *d_blk_nnz;   // nblocks   : nonzeros handled by the block
-   int32_t *d_blk_kind;  // 0 = group of whole rows, 1 = chunk of one long row
-   int nlong;            // number of long-row chunks
-   int lpr;              // lanes per row for group blocks
-   double *d_long_part;  // partial sums of long-row chunks [nlongchunks][8]
-   int32_t *d_long_slot; // per block: slot index in d_long_part (kind 1) else -1
-   // fix-up list for long rows
-   int nlongrows;
-   int64_t *d_lr_row;    // row id
-   int32_t *d_lr_slot0;  // first slot
-   int32_t *d_lr_nslots; // number of chunks
-   pb200_csr *T;
-};
 
 namespace {
 
@@ -127,7 +104,7 @@ __global__ void __launch_bounds__(SP_THREADS) spmm_kernel(const int64_t *__restr
       if (tid < BT) {
          double s = 0.0;
          for (int w = 0; w < SP_THREADS / 32; w++) s += s_red[w][tid];
-         long_part[(size_t)long_slot[blk] * 8 + tid] = s;
+         long_part[(size_t)long_slot[blk] * 16 + tid] = s;
       }
    }
 }
@@ -141,7 +118,7 @@ __global__ void spmm_long_fixup(const int64_t *__restrict__ lr_row,
    int lr = i / 8, c = i % 8;
    if (lr >= nlongrows || c >= b) return;
    double s = 0.0;
-   for (int t = 0; t < lr_nslots[lr]; t++) s += long_part[(size_t)(lr_slot0[lr] + t) * 8 + c];
+   for (int t = 0; t < lr_nslots[lr]; t++) s += long_part[(size_t)(lr_slot0[lr] + t) * 16 + c];
    Y[lr_row[lr] + (size_t)c * ldy] = s;
 }
 
@@ -308,7 +285,7 @@ __global__ void __launch_bounds__(SPT_THREADS, 2) spmm_tma_kernel(const int64_t 
          if (tid < BT) {
             double sum = 0.0;
             for (int w = 0; w < SPT_CONS / 32; w++) sum += s_red[w][tid];
-            long_part[(size_t)slot * 8 + tid] = sum;
+            long_part[(size_t)slot * 16 + tid] = sum;
          }
          pbtma::named_bar_sync(1, SPT_CONS);  // s_red is reused by the next long chunk
       }
@@ -380,6 +357,351 @@ int launch_spmm(pb200_ctx *ctx, const pb200_csr *A, const double *X, int64_t ldx
    return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// v3: same persistent producer/consumer pipeline as v2, but the right-hand sides are gathered
+// from a ROW-MAJOR copy G[col][NR] of the block (NR = b padded to 1/2/4/8 doubles, twice that for
+// complex): one 32-byte (LDG.E.256) or 16-byte load per nonzero and 4 columns instead of b 8-byte
+// loads from b different cache lines.  The copy is made by spmm_pack_kernel (2 x 8nb bytes of
+// traffic against 12 B per nonzero; for matrices without locality it cuts the gather sectors per
+// nonzero from b to b/4) -- and it is ALSO the halo exchange format of the row-sharded operator
+// (dist.cu): peers write their rows of G straight into this rank's copy over NVLink, the kernel
+// waits for their flags (PbSpSync) before its first gather and acknowledges when it is done.
+// CPLX: values and right-hand sides are interleaved (re, im) pairs.
+template <int NR>
+__device__ __forceinline__ void sp_ld_row(const double *p, double (&x)[NR]) {
+   if constexpr (NR == 1) {
+      asm("ld.global.f64 %0, [%1];" : "=d"(x[0]) : "l"(p));
+   } else if constexpr (NR == 2) {
+      asm("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(x[0]), "=d"(x[1]) : "l"(p));
+   } else {
+#pragma unroll
+      for (int k = 0; k < NR; k += 4)
+         asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+             : "=d"(x[k]), "=d"(x[k + 1]), "=d"(x[k + 2]), "=d"(x[k + 3])
+             : "l"(p + k));
+   }
+}
+
+template <bool CPLX> struct SpVal { typedef double type; };
+template <> struct SpVal<true> { typedef double2 type; };
+
+template <int NR, bool CPLX>
+__device__ __forceinline__ void sp_fma(double (&acc)[NR], typename SpVal<CPLX>::type v, const double (&x)[NR]) {
+   if constexpr (CPLX) {
+#pragma unroll
+      for (int c = 0; c < NR; c += 2) {
+         acc[c] = fma(v.x, x[c], acc[c]);
+         acc[c] = fma(-v.y, x[c + 1], acc[c]);
+         acc[c + 1] = fma(v.x, x[c + 1], acc[c + 1]);
+         acc[c + 1] = fma(v.y, x[c], acc[c + 1]);
+      }
+   } else {
+#pragma unroll
+      for (int c = 0; c < NR; c++) acc[c] = fma(v, x[c], acc[c]);
+   }
+}
+template <bool CPLX> __device__ __forceinline__ typename SpVal<CPLX>::type sp_zero();
+template <> __device__ __forceinline__ double sp_zero<false>() { return 0.0; }
+template <> __device__ __forceinline__ double2 sp_zero<true>() { return make_double2(0.0, 0.0); }
+
+template <bool CPLX> struct Sp3Stage {
+   static constexpr size_t BYTES =
+         ((size_t)SPT_VALS * (CPLX ? 16 : 8) + (size_t)SPT_VALS * 4 + (size_t)SPT_RP * 8 + 64 + 127) / 128 * 128;
+};
+
+template <int BT, int NR, bool CPLX>
+__device__ __forceinline__ void sp_store_row(double *__restrict__ Y, int64_t ldy, int64_t row, int b, const double (&acc)[NR]) {
+   if constexpr (CPLX) {
+      double2 *Y2 = reinterpret_cast<double2 *>(Y);
+#pragma unroll
+      for (int c = 0; c < BT; c++)
+         if (c < b) Y2[row + (size_t)c * ldy] = make_double2(acc[2 * c], acc[2 * c + 1]);
+   } else {
+#pragma unroll
+      for (int c = 0; c < BT; c++)
+         if (c < b) Y[row + (size_t)c * ldy] = acc[c];
+   }
+}
+
+template <int BT, int LPR, bool CPLX>
+__global__ void __launch_bounds__(SPT_THREADS, 2) spmm_rm_kernel(const int64_t *__restrict__ rowptr,
+      const int32_t *__restrict__ colind, const void *__restrict__ vals_,
+      const int64_t *__restrict__ blk_row0, const int64_t *__restrict__ blk_nz0,
+      const int32_t *__restrict__ blk_nnz, const int32_t *__restrict__ blk_kind,
+      const int32_t *__restrict__ long_slot, double *__restrict__ long_part, int nblocks,
+      const double *G, double *__restrict__ Y, int64_t ldy, int b, int nstages, const PbSpSync sync) {
+   typedef typename SpVal<CPLX>::type VT;
+   constexpr int NR = CPLX ? 2 * BT : BT;       // doubles per row of G
+   constexpr int UN = NR >= 16 ? 1 : NR >= 8 ? 2 : 4;  // nonzeros in flight per lane (60 registers per thread)
+   constexpr size_t STAGE = Sp3Stage<CPLX>::BYTES;
+   constexpr size_t OFF_COL = (size_t)SPT_VALS * sizeof(VT);
+   constexpr size_t OFF_RP = OFF_COL + (size_t)SPT_VALS * 4;
+   constexpr size_t OFF_HDR = OFF_RP + (size_t)SPT_RP * 8;
+   const VT *__restrict__ vals = reinterpret_cast<const VT *>(vals_);
+   extern __shared__ __align__(128) unsigned char smraw[];
+   __shared__ uint64_t full[8], empty[8];
+   __shared__ double s_red[SPT_CONS / 32][NR];
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   if (tid == 0) {
+      for (int s = 0; s < nstages; s++) {
+         pbtma::mbar_init(&full[s], 1);
+         pbtma::mbar_init(&empty[s], SPT_CONS / 32);
+      }
+      pbtma::fence_barrier_init();
+   }
+   __syncthreads();
+
+   if (warp == SPT_CONS / 32) {
+      // -------- producer: the matrix stream does not depend on the halo --------
+      if (lane != 0) return;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+         const int64_t nz0 = blk_nz0[blk];
+         const int nnzb = blk_nnz[blk];
+         const int kind = blk_kind[blk];
+         const int64_t row0 = blk_row0[blk];
+         const int nrows = kind == 0 ? (int)(blk_row0[blk + 1] - row0) : 1;
+         const int slot = long_slot[blk];
+         pbtma::mbar_wait(&empty[s], ph ^ 1);
+         unsigned char *st = smraw + (size_t)s * STAGE;
+         SpStageHdr *hdr = reinterpret_cast<SpStageHdr *>(st + OFF_HDR);
+         const int64_t nzbase = nz0 & ~(int64_t)3;
+         const int cnt = (int)((nz0 + nnzb - nzbase + 3) & ~(int64_t)3);
+         const int64_t rpbase = row0 & ~(int64_t)1;
+         const int rpcnt = kind == 0 ? (int)((row0 + nrows + 1 - rpbase + 1) & ~(int64_t)1) : 0;
+         hdr->row0 = row0, hdr->nzbase = nzbase, hdr->rpbase = rpbase;
+         hdr->nrows = nrows, hdr->nnzb = nnzb, hdr->kind = kind, hdr->slot = slot;
+         hdr->off = (int32_t)(nz0 - nzbase);
+         const uint32_t bytes = (uint32_t)cnt * (uint32_t)(sizeof(VT) + 4) + (uint32_t)rpcnt * 8u;
+         pbtma::mbar_arrive_expect_tx(&full[s], bytes);
+         if (cnt > 0) {
+            pbtma::bulk_g2s(st, vals + nzbase, (uint32_t)cnt * (uint32_t)sizeof(VT), &full[s]);
+            pbtma::bulk_g2s(st + OFF_COL, colind + nzbase, (uint32_t)cnt * 4u, &full[s]);
+         }
+         if (rpcnt > 0) pbtma::bulk_g2s(st + OFF_RP, rowptr + rpbase, (uint32_t)rpcnt * 8u, &full[s]);
+         if (++s == nstages) s = 0, ph ^= 1;
+      }
+      return;
+   }
+
+   // -------- consumers --------
+   if (sync.src_mask) {
+      // halo rows of G are written by the peers: no gather before every source has flagged this block
+      if (lane == 0) {
+         for (int r = 0; r < PB_MAX_PEERS; r++)
+            if (sync.src_mask & (1u << r)) {
+               unsigned long long f;
+               unsigned long long spins = 0;
+               do {
+                  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(sync.flags + r) : "memory");
+               } while (f < sync.seq && ++spins < (1ull << 31));
+            }
+      }
+      __syncwarp();
+   }
+   int s = 0;
+   uint32_t ph = 0;
+   constexpr int RPP = SPT_CONS / LPR;  // rows per pass
+   const int sub = tid % LPR;
+   for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+      pbtma::mbar_wait(&full[s], ph);
+      const unsigned char *st = smraw + (size_t)s * STAGE;
+      const VT *s_val = reinterpret_cast<const VT *>(st);
+      const int32_t *s_col = reinterpret_cast<const int32_t *>(st + OFF_COL);
+      const int64_t *s_rp = reinterpret_cast<const int64_t *>(st + OFF_RP);
+      const SpStageHdr *hdr = reinterpret_cast<const SpStageHdr *>(st + OFF_HDR);
+      const int64_t row0 = hdr->row0, nzbase = hdr->nzbase;
+      const int nrows = hdr->nrows, nnzb = hdr->nnzb, kind = hdr->kind, slot = hdr->slot;
+      const int rpoff = (int)(row0 - hdr->rpbase);
+      if (kind == 0) {
+         // rows longer than LONGT nonzeros would serialise their LPR lanes while the rest of the warp
+         // idles (power-law graphs): they are skipped here and taken by whole warps below
+         constexpr int LONGT = LPR >= 32 ? 0x7fffffff : 4 * UN * LPR;
+         for (int base = 0; base < nrows; base += RPP) {
+            const int rl = base + tid / LPR;
+            bool active = rl < nrows;
+            int sidx = 0, e = 0;
+            if (active) sidx = (int)(s_rp[rpoff + rl] - nzbase), e = (int)(s_rp[rpoff + rl + 1] - nzbase);
+            if (e - sidx > LONGT) active = false, e = sidx;
+            double acc[NR];
+#pragma unroll
+            for (int c = 0; c < NR; c++) acc[c] = 0.0;
+            for (int i = sidx + sub; i < e; i += UN * LPR) {
+               VT v[UN];
+               double xv[UN][NR];
+#pragma unroll
+               for (int u = 0; u < UN; u++) {
+                  const int iu = i + u * LPR;
+                  const bool on = iu < e;
+                  v[u] = on ? s_val[iu] : sp_zero<CPLX>();
+                  sp_ld_row<NR>(G + (size_t)(on ? s_col[iu] : s_col[i]) * NR, xv[u]);
+               }
+#pragma unroll
+               for (int u = 0; u < UN; u++) sp_fma<NR, CPLX>(acc, v[u], xv[u]);
+            }
+            if (LPR > 1) {
+#pragma unroll
+               for (int c = 0; c < NR; c++)
+#pragma unroll
+                  for (int o = LPR / 2; o > 0; o >>= 1)
+                     acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o, LPR);
+            }
+            if (active && sub == 0) sp_store_row<BT, NR, CPLX>(Y, ldy, row0 + rl, b, acc);
+         }
+         if (LPR < 32) {
+            // warp-wide pass over the long rows of the block, dealt round-robin to the warps
+            int nlong = 0;
+            for (int base = 0; base < nrows; base += 32) {
+               const int rl = base + lane;
+               int len = 0;
+               if (rl < nrows) len = (int)(s_rp[rpoff + rl + 1] - s_rp[rpoff + rl]);
+               unsigned m = __ballot_sync(0xffffffffu, len > LONGT);
+               while (m) {
+                  const int j = __ffs(m) - 1;
+                  m &= m - 1;
+                  if ((nlong++ % (SPT_CONS / 32)) != warp) continue;
+                  const int rr = base + j;
+                  const int sidx = (int)(s_rp[rpoff + rr] - nzbase), e = (int)(s_rp[rpoff + rr + 1] - nzbase);
+                  double acc[NR];
+#pragma unroll
+                  for (int c = 0; c < NR; c++) acc[c] = 0.0;
+                  for (int i = sidx + lane; i < e; i += UN * 32) {
+                     VT v[UN];
+                     double xv[UN][NR];
+#pragma unroll
+                     for (int u = 0; u < UN; u++) {
+                        const int iu = i + u * 32;
+                        const bool on = iu < e;
+                        v[u] = on ? s_val[iu] : sp_zero<CPLX>();
+                        sp_ld_row<NR>(G + (size_t)(on ? s_col[iu] : s_col[i]) * NR, xv[u]);
+                     }
+#pragma unroll
+                     for (int u = 0; u < UN; u++) sp_fma<NR, CPLX>(acc, v[u], xv[u]);
+                  }
+#pragma unroll
+                  for (int c = 0; c < NR; c++)
+#pragma unroll
+                     for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+                  if (lane == 0) sp_store_row<BT, NR, CPLX>(Y, ldy, row0 + rr, b, acc);
+               }
+            }
+         }
+      } else {
+         const int off = hdr->off;
+         double acc[NR];
+#pragma unroll
+         for (int c = 0; c < NR; c++) acc[c] = 0.0;
+         for (int i = tid; i < nnzb; i += SPT_CONS) {
+            double xv[NR];
+            sp_ld_row<NR>(G + (size_t)s_col[off + i] * NR, xv);
+            sp_fma<NR, CPLX>(acc, s_val[off + i], xv);
+         }
+#pragma unroll
+         for (int c = 0; c < NR; c++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+            if (lane == 0) s_red[warp][c] = acc[c];
+         }
+         pbtma::named_bar_sync(1, SPT_CONS);
+         if (tid < NR) {
+            double sum = 0.0;
+            for (int w = 0; w < SPT_CONS / 32; w++) sum += s_red[w][tid];
+            long_part[(size_t)slot * 16 + tid] = sum;
+         }
+         pbtma::named_bar_sync(1, SPT_CONS);  // s_red is reused by the next long chunk
+      }
+      __syncwarp();
+      if (lane == 0) pbtma::mbar_arrive(&empty[s]);
+      if (++s == nstages) s = 0, ph ^= 1;
+   }
+   if (sync.ack_mask) {
+      // every gather of this grid is done: tell the peers that write into G that this buffer is free
+      pbtma::named_bar_sync(1, SPT_CONS);
+      if (tid == 0) {
+         __threadfence();
+         const unsigned int t = atomicAdd(sync.counter, 1u);
+         if (t == gridDim.x - 1) {
+            *sync.counter = 0u;
+            __threadfence_system();
+            for (int r = 0; r < PB_MAX_PEERS; r++)
+               if (sync.ack_mask & (1u << r))
+                  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(sync.ack[r]), "l"(sync.seq) : "memory");
+         }
+      }
+   }
+}
+
+// G[r][0:bp) = X(r, 0:b) (zero padded): flat element index so that the stores are fully coalesced and
+// the loads touch whole 32-byte sectors (bp columns x 32/bp consecutive rows per warp)
+template <typename VT>
+__global__ void __launch_bounds__(256) spmm_pack_kernel(const VT *__restrict__ X, int64_t ldx, int64_t nrows, int b,
+      int bp, VT *__restrict__ G) {
+   const int64_t total = nrows * bp;
+   const int sh = bp == 1 ? 0 : bp == 2 ? 1 : bp == 4 ? 2 : 3;
+   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = e >> sh;
+      const int c = (int)(e & (bp - 1));
+      VT v;
+      if (c < b) v = X[r + (size_t)c * ldx];
+      else memset(&v, 0, sizeof(v));
+      G[e] = v;
+   }
+}
+
+template <int BT, int LPR, bool CPLX>
+int launch_spmm_rm_l(pb200_ctx *ctx, const pb200_csr *A, const double *G, double *Y, int64_t ldy, int b,
+      const PbSpSync *sync) {
+   auto kern = spmm_rm_kernel<BT, LPR, CPLX>;
+   static int cached_occ = 0;
+   const int nstages = CPLX ? 2 : 4;
+   const size_t shmem = nstages * Sp3Stage<CPLX>::BYTES;
+   if (!cached_occ) {
+      PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+      int occ = 0;
+      PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SPT_THREADS, shmem));
+      cached_occ = occ > 0 ? occ : 1;
+   }
+   int grid = ctx->num_sms * cached_occ;
+   if (grid > A->nblocks) grid = A->nblocks;
+   if (grid < 1) grid = 1;   // a rank without rows still takes part in the flag / acknowledge protocol
+   PbSpSync sy;
+   if (sync) sy = *sync;
+   else memset(&sy, 0, sizeof(sy));
+   kern<<<grid, SPT_THREADS, shmem, ctx->stream>>>(A->d_rowptr, A->d_colind, A->d_vals, A->d_blk_row0,
+         A->d_blk_nz0, A->d_blk_nnz, A->d_blk_kind, A->d_long_slot, A->d_long_part, A->nblocks, G, Y, ldy, b,
+         nstages, sy);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   return 0;
+}
+
+template <int BT, bool CPLX>
+int launch_spmm_rm(pb200_ctx *ctx, const pb200_csr *A, const double *G, double *Y, int64_t ldy, int b,
+      const PbSpSync *sync) {
+   switch (A->lpr) {
+   case 1: return launch_spmm_rm_l<BT, 1, CPLX>(ctx, A, G, Y, ldy, b, sync);
+   case 2: return launch_spmm_rm_l<BT, 2, CPLX>(ctx, A, G, Y, ldy, b, sync);
+   case 4: return launch_spmm_rm_l<BT, 4, CPLX>(ctx, A, G, Y, ldy, b, sync);
+   case 8: return launch_spmm_rm_l<BT, 8, CPLX>(ctx, A, G, Y, ldy, b, sync);
+   case 16: return launch_spmm_rm_l<BT, 16, CPLX>(ctx, A, G, Y, ldy, b, sync);
+   default: return launch_spmm_rm_l<BT, 32, CPLX>(ctx, A, G, Y, ldy, b, sync);
+   }
+}
+
+// long-row fix-up for v3 (real and complex): NR accumulators per slot
+__global__ void spmm_long_fixup3(const int64_t *__restrict__ lr_row, const int32_t *__restrict__ lr_slot0,
+      const int32_t *__restrict__ lr_nslots, const double *__restrict__ long_part, int nlongrows,
+      double *__restrict__ Y, int64_t ldy, int b, int cplx) {
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   int lr = i / 16, c = i % 16;
+   if (lr >= nlongrows || c >= (cplx ? 2 * b : b)) return;
+   double s = 0.0;
+   for (int t = 0; t < lr_nslots[lr]; t++) s += long_part[(size_t)(lr_slot0[lr] + t) * 16 + c];
+   if (cplx) Y[2 * (lr_row[lr] + (size_t)(c >> 1) * ldy) + (c & 1)] = s;
+   else Y[lr_row[lr] + (size_t)c * ldy] = s;
+}
+
 template <typename T>
 int upload(pb200_ctx *ctx, const std::vector<T> &h, T **d) {
    size_t bytes = sizeof(T) * (h.size() ? h.size() : 1);
@@ -445,27 +767,28 @@ int build_schedule(pb200_ctx *ctx, pb200_csr *A, const int64_t *rp) {
    PB_CHK(upload(ctx, lr_row, &A->d_lr_row));
    PB_CHK(upload(ctx, lr_slot0, &A->d_lr_slot0));
    PB_CHK(upload(ctx, lr_nslots, &A->d_lr_nslots));
-   PB_CUDA(cudaMalloc((void **)&A->d_long_part, sizeof(double) * 8 * (nslots ? nslots : 1)));
+   PB_CUDA(cudaMalloc((void **)&A->d_long_part, sizeof(double) * 16 * (nslots ? nslots : 1)));
    return 0;
 }
 
 int csr_from_host(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
-      const int64_t *rp0 /*0-based*/, const int32_t *ci0 /*0-based*/, const double *vals,
+      const int64_t *rp0 /*0-based*/, const int32_t *ci0 /*0-based*/, const void *vals, int is_complex,
       pb200_csr **out) {
    pb200_csr *A = (pb200_csr *)calloc(1, sizeof(pb200_csr));
    if (!A) return PB200_ERR_ALLOC;
-   A->nrows = nrows, A->ncols = ncols, A->nnz = nnz;
+   A->nrows = nrows, A->ncols = ncols, A->nnz = nnz, A->is_complex = is_complex;
+   const size_t vs = is_complex ? 16 : 8;
    // 64 bytes of zeroed slack after each array: the bulk copies of the v2 kernel read aligned slices
    PB_CUDA(cudaMalloc((void **)&A->d_rowptr, sizeof(int64_t) * (nrows + 1) + 64));
    PB_CUDA(cudaMemsetAsync(A->d_rowptr, 0, sizeof(int64_t) * (nrows + 1) + 64, ctx->stream));
    PB_CUDA(cudaMalloc((void **)&A->d_colind, sizeof(int32_t) * nnz + 64));
    PB_CUDA(cudaMemsetAsync(A->d_colind, 0, sizeof(int32_t) * nnz + 64, ctx->stream));
-   PB_CUDA(cudaMalloc((void **)&A->d_vals, sizeof(double) * nnz + 64));
-   PB_CUDA(cudaMemsetAsync(A->d_vals, 0, sizeof(double) * nnz + 64, ctx->stream));
+   PB_CUDA(cudaMalloc((void **)&A->d_vals, vs * nnz + 64));
+   PB_CUDA(cudaMemsetAsync(A->d_vals, 0, vs * nnz + 64, ctx->stream));
    PB_CUDA(cudaMemcpyAsync(A->d_rowptr, rp0, sizeof(int64_t) * (nrows + 1), cudaMemcpyHostToDevice, ctx->stream));
    if (nnz) {
       PB_CUDA(cudaMemcpyAsync(A->d_colind, ci0, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
-      PB_CUDA(cudaMemcpyAsync(A->d_vals, vals, sizeof(double) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+      PB_CUDA(cudaMemcpyAsync(A->d_vals, vals, vs * nnz, cudaMemcpyHostToDevice, ctx->stream));
    }
    PB_CUDA(cudaStreamSynchronize(ctx->stream));
    PB_CHK(build_schedule(ctx, A, rp0));
@@ -478,7 +801,6 @@ int csr_from_host(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
 extern "C" int pb200_csr_create(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
       const int64_t *rowptr_host, const int32_t *colind_host, const void *vals_host,
       int index_base, int is_complex, pb200_csr **out) {
-   if (is_complex) return PB200_ERR_ARG;  // complex CSR: not built yet
    std::vector<int64_t> rp(nrows + 1);
    for (int64_t i = 0; i <= nrows; i++) rp[i] = rowptr_host[i] - index_base;
    const int32_t *ci = colind_host;
@@ -489,7 +811,7 @@ extern "C" int pb200_csr_create(pb200_ctx *ctx, int64_t nrows, int64_t ncols, in
       ci = ci0.data();
    }
    // keep a host copy of the 0-based structure for the optional transpose
-   int rc = csr_from_host(ctx, nrows, ncols, nnz, rp.data(), ci, (const double *)vals_host, out);
+   int rc = csr_from_host(ctx, nrows, ncols, nnz, rp.data(), ci, vals_host, is_complex ? 1 : 0, out);
    return rc;
 }
 
@@ -501,48 +823,171 @@ extern "C" int pb200_csr_destroy(pb200_ctx *ctx, pb200_csr *A) {
    cudaFree(A->d_blk_row0), cudaFree(A->d_blk_nz0), cudaFree(A->d_blk_nnz), cudaFree(A->d_blk_kind);
    cudaFree(A->d_long_slot), cudaFree(A->d_long_part);
    cudaFree(A->d_lr_row), cudaFree(A->d_lr_slot0), cudaFree(A->d_lr_nslots);
+   cudaFree(A->d_G);
    free(A);
    return 0;
 }
 
 extern "C" int64_t pb200_csr_nnz(const pb200_csr *A) { return A->nnz; }
 
-extern "C" int pb200_dspmm(pb200_ctx *ctx, const pb200_csr *A, const double *X, int64_t ldx,
-      double *Y, int64_t ldy, int ncols) {
-   if (A->nrows == 0) return 0;
-   for (int c0 = 0; c0 < ncols; c0 += 8) {
-      int b = ncols - c0 < 8 ? ncols - c0 : 8;
-      const double *Xc = X + (size_t)c0 * ldx;
-      double *Yc = Y + (size_t)c0 * ldy;
-      int rc;
-      // algorithmic bytes: nnz*(8+4) + (n+1)*8 (64-bit row pointers) + 2*n*b*8  
-      const double abytes = 12.0 * (double)A->nnz + 8.0 * (double)(A->nrows + 1) +
-                            8.0 * (double)b * (double)(A->nrows + A->ncols);
-      int ps = pb_prof_begin(ctx, PB_K_SPMM);
-      if (ctx->use_tma_spmm) {
-         if (b <= 1) rc = launch_spmm_tma<1>(ctx, A, Xc, ldx, Yc, ldy, b);
-         else if (b <= 2) rc = launch_spmm_tma<2>(ctx, A, Xc, ldx, Yc, ldy, b);
-         else if (b <= 4) rc = launch_spmm_tma<4>(ctx, A, Xc, ldx, Yc, ldy, b);
-         else rc = launch_spmm_tma<8>(ctx, A, Xc, ldx, Yc, ldy, b);
-      } else if (b <= 1) rc = launch_spmm<1>(ctx, A, Xc, ldx, Yc, ldy, b);
-      else if (b <= 2) rc = launch_spmm<2>(ctx, A, Xc, ldx, Yc, ldy, b);
-      else if (b <= 4) rc = launch_spmm<4>(ctx, A, Xc, ldx, Yc, ldy, b);
-      else rc = launch_spmm<8>(ctx, A, Xc, ldx, Yc, ldy, b);
-      pb_prof_end(ctx, ps, abytes);
-      PB_CHK(rc);
-      if (A->nlongrows > 0) {
-         int tot = A->nlongrows * 8;
-         spmm_long_fixup<<<(tot + 127) / 128, 128, 0, ctx->stream>>>(A->d_lr_row, A->d_lr_slot0,
-               A->d_lr_nslots, A->d_long_part, A->nlongrows, Yc, ldy, b);
-         ctx->launches++;
-         PB_CUDA(cudaGetLastError());
-      }
+// Y = A * (rows of G): the v3 kernel on an already packed block (dist.cu calls this with the peer-
+// filled buffer and the flag protocol in `sync`)
+int pb_spmm_gathered(pb200_ctx *ctx, const pb200_csr *A, const double *G, int bp, void *Y, int64_t ldy, int b,
+      const PbSpSync *sync) {
+   int rc;
+   if (A->is_complex) {
+      if (bp <= 1) rc = launch_spmm_rm<1, true>(ctx, A, G, (double *)Y, ldy, b, sync);
+      else if (bp <= 2) rc = launch_spmm_rm<2, true>(ctx, A, G, (double *)Y, ldy, b, sync);
+      else if (bp <= 4) rc = launch_spmm_rm<4, true>(ctx, A, G, (double *)Y, ldy, b, sync);
+      else rc = launch_spmm_rm<8, true>(ctx, A, G, (double *)Y, ldy, b, sync);
+   } else {
+      if (bp <= 1) rc = launch_spmm_rm<1, false>(ctx, A, G, (double *)Y, ldy, b, sync);
+      else if (bp <= 2) rc = launch_spmm_rm<2, false>(ctx, A, G, (double *)Y, ldy, b, sync);
+      else if (bp <= 4) rc = launch_spmm_rm<4, false>(ctx, A, G, (double *)Y, ldy, b, sync);
+      else rc = launch_spmm_rm<8, false>(ctx, A, G, (double *)Y, ldy, b, sync);
+   }
+   PB_CHK(rc);
+   if (A->nlongrows > 0) {
+      int tot = A->nlongrows * 16;
+      spmm_long_fixup3<<<(tot + 127) / 128, 128, 0, ctx->stream>>>(A->d_lr_row, A->d_lr_slot0, A->d_lr_nslots,
+            A->d_long_part, A->nlongrows, (double *)Y, ldy, b, A->is_complex);
+      ctx->launches++;
+      PB_CUDA(cudaGetLastError());
    }
    return 0;
 }
 
+int pb_spmm_bp(int b) { return b <= 1 ? 1 : b <= 2 ? 2 : b <= 4 ? 4 : 8; }
+
+// G[r][0:bp) = X(r, 0:b)
+int pb_spmm_pack(pb200_ctx *ctx, const void *X, int64_t ldx, int64_t nrows, int b, int bp, int is_complex,
+      double *G) {
+   if (nrows <= 0) return 0;
+   int64_t blocks = (nrows * bp + 255) / 256 / 4;
+   const int64_t cap = (int64_t)ctx->num_sms * 16;
+   if (blocks > cap) blocks = cap;
+   if (blocks < 1) blocks = 1;
+   if (is_complex)
+      spmm_pack_kernel<double2><<<(int)blocks, 256, 0, ctx->stream>>>((const double2 *)X, ldx, nrows, b, bp, (double2 *)G);
+   else
+      spmm_pack_kernel<double><<<(int)blocks, 256, 0, ctx->stream>>>((const double *)X, ldx, nrows, b, bp, G);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   return 0;
+}
+
+// v3 path on a column-major block: pack into the matrix's own gather buffer, then gather
+static int run_v3(pb200_ctx *ctx, const pb200_csr *A, const void *Xc, int64_t ldx, void *Yc, int64_t ldy, int b) {
+   const int bp = pb_spmm_bp(b);
+   pb200_csr *Am = const_cast<pb200_csr *>(A);
+   const size_t need = (size_t)(A->ncols > 0 ? A->ncols : 1) * bp * (A->is_complex ? 2 : 1);
+   if (need > Am->G_cap) {
+      PB_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (Am->d_G) PB_CUDA(cudaFree(Am->d_G));
+      const size_t cap = (size_t)(A->ncols > 0 ? A->ncols : 1) * 8 * (A->is_complex ? 2 : 1);
+      Am->d_G = NULL, Am->G_cap = 0;
+      PB_CUDA(cudaMalloc((void **)&Am->d_G, cap * sizeof(double)));
+      Am->G_cap = cap;
+   }
+   PB_CHK(pb_spmm_pack(ctx, Xc, ldx, A->ncols, b, bp, A->is_complex, Am->d_G));
+   return pb_spmm_gathered(ctx, A, Am->d_G, bp, Yc, ldy, b, NULL);
+}
+
+// v2 (column-major gathers; real only) or the plain per-block kernel
+static int run_v2(pb200_ctx *ctx, const pb200_csr *A, const double *Xd, int64_t ldx, double *Yd, int64_t ldy, int b) {
+   int rc;
+   if (ctx->use_tma_spmm) {
+      if (b <= 1) rc = launch_spmm_tma<1>(ctx, A, Xd, ldx, Yd, ldy, b);
+      else if (b <= 2) rc = launch_spmm_tma<2>(ctx, A, Xd, ldx, Yd, ldy, b);
+      else if (b <= 4) rc = launch_spmm_tma<4>(ctx, A, Xd, ldx, Yd, ldy, b);
+      else rc = launch_spmm_tma<8>(ctx, A, Xd, ldx, Yd, ldy, b);
+   } else if (b <= 1) rc = launch_spmm<1>(ctx, A, Xd, ldx, Yd, ldy, b);
+   else if (b <= 2) rc = launch_spmm<2>(ctx, A, Xd, ldx, Yd, ldy, b);
+   else if (b <= 4) rc = launch_spmm<4>(ctx, A, Xd, ldx, Yd, ldy, b);
+   else rc = launch_spmm<8>(ctx, A, Xd, ldx, Yd, ldy, b);
+   PB_CHK(rc);
+   if (A->nlongrows > 0) {
+      int tot = A->nlongrows * 8;
+      spmm_long_fixup<<<(tot + 127) / 128, 128, 0, ctx->stream>>>(A->d_lr_row, A->d_lr_slot0,
+            A->d_lr_nslots, A->d_long_part, A->nlongrows, Yd, ldy, b);
+      ctx->launches++;
+      PB_CUDA(cudaGetLastError());
+   }
+   return 0;
+}
+
+// First block of a given width on this matrix: time both gather layouts once (after a warm-up pass
+// of each) and keep the faster -- banded matrices gather coalesced from the column-major block and do
+// not repay the packing pass, matrices without locality gain 3-4x from the 32-byte row gathers.
+static int tune_layout(pb200_ctx *ctx, const pb200_csr *A, const void *Xc, int64_t ldx, void *Yc, int64_t ldy, int b,
+      int idx) {
+   pb200_csr *Am = const_cast<pb200_csr *>(A);
+   cudaEvent_t ev[3];
+   for (int i = 0; i < 3; i++) PB_CUDA(cudaEventCreate(&ev[i]));
+   int rc = run_v3(ctx, A, Xc, ldx, Yc, ldy, b);
+   if (!rc) rc = run_v2(ctx, A, (const double *)Xc, ldx, (double *)Yc, ldy, b);
+   cudaEventRecord(ev[0], ctx->stream);
+   if (!rc) rc = run_v3(ctx, A, Xc, ldx, Yc, ldy, b);
+   cudaEventRecord(ev[1], ctx->stream);
+   if (!rc) rc = run_v2(ctx, A, (const double *)Xc, ldx, (double *)Yc, ldy, b);
+   cudaEventRecord(ev[2], ctx->stream);
+   PB_CUDA(cudaStreamSynchronize(ctx->stream));
+   float t3 = 0.f, t2 = 0.f;
+   cudaEventElapsedTime(&t3, ev[0], ev[1]);
+   cudaEventElapsedTime(&t2, ev[1], ev[2]);
+   for (int i = 0; i < 3; i++) cudaEventDestroy(ev[i]);
+   Am->layout_choice[idx] = (t3 < t2) ? 2 : 1;
+   if (getenv("PB200_DEBUG"))
+      fprintf(stderr, "primme_b200: SpMM b=%d on %lld x %lld (nnz %lld): row-major gathers %.1f us, column-major %.1f us\n", b,
+            (long long)A->nrows, (long long)A->ncols, (long long)A->nnz, 1e3 * t3, 1e3 * t2);
+   return rc;
+}
+
+static int spmm_any(pb200_ctx *ctx, const pb200_csr *A, const void *X, int64_t ldx, void *Y, int64_t ldy, int ncols) {
+   if (A->nrows == 0) return 0;
+   const size_t es = A->is_complex ? 16 : 8;
+   for (int c0 = 0; c0 < ncols; c0 += 8) {
+      int b = ncols - c0 < 8 ? ncols - c0 : 8;
+      const char *Xc = (const char *)X + (size_t)c0 * ldx * es;
+      char *Yc = (char *)Y + (size_t)c0 * ldy * es;
+      // algorithmic bytes: nnz*(s+4) + (n+1)*8 (64-bit row pointers) + (nrows+ncols)*b*s  
+      const double abytes = (double)(es + 4) * (double)A->nnz + 8.0 * (double)(A->nrows + 1) +
+                            (double)es * (double)b * (double)(A->nrows + A->ncols);
+      int v3;
+      if (A->is_complex) v3 = 1;
+      else if (!ctx->use_tma_spmm || b < 2) v3 = 0;
+      else if (ctx->spmm_v3 != 2) v3 = ctx->spmm_v3 ? 1 : 0;
+      else {
+         const int bp = pb_spmm_bp(b), idx = bp == 2 ? 1 : bp == 4 ? 2 : 3;
+         if (!A->layout_choice[idx]) {
+            PB_CHK(tune_layout(ctx, A, Xc, ldx, Yc, ldy, b, idx));
+            continue;  // the last timed pass already left the product in Y
+         }
+         v3 = A->layout_choice[idx] == 2;
+      }
+      int ps = pb_prof_begin(ctx, PB_K_SPMM);
+      int rc = v3 ? run_v3(ctx, A, Xc, ldx, Yc, ldy, b) : run_v2(ctx, A, (const double *)Xc, ldx, (double *)Yc, ldy, b);
+      pb_prof_end(ctx, ps, abytes);
+      PB_CHK(rc);
+   }
+   return 0;
+}
+
+extern "C" int pb200_dspmm(pb200_ctx *ctx, const pb200_csr *A, const double *X, int64_t ldx,
+      double *Y, int64_t ldy, int ncols) {
+   if (A->is_complex) return PB200_ERR_ARG;
+   return spmm_any(ctx, A, X, ldx, Y, ldy, ncols);
+}
+// complex twin: A created with is_complex = 1 (interleaved re,im values), X and Y complex column-major
+extern "C" int pb200_zspmm(pb200_ctx *ctx, const pb200_csr *A, const void *X, int64_t ldx, void *Y,
+      int64_t ldy, int ncols) {
+   if (!A->is_complex) return PB200_ERR_ARG;
+   return spmm_any(ctx, A, X, ldx, Y, ldy, ncols);
+}
+
 extern "C" int pb200_csr_build_transpose(pb200_ctx *ctx, pb200_csr *A) {
    if (A->T) return 0;
+   if (A->is_complex) return PB200_ERR_ARG;  // the SVD operator is real
    // pull the structure back, transpose on the host once (setup cost, not on the hot path)
    std::vector<int64_t> rp(A->nrows + 1);
    std::vector<int32_t> ci(A->nnz ? A->nnz : 1);
@@ -564,7 +1009,7 @@ extern "C" int pb200_csr_build_transpose(pb200_ctx *ctx, pb200_csr *A) {
          tci[p] = (int32_t)i;
          tva[p] = va[k];
       }
-   return csr_from_host(ctx, A->ncols, A->nrows, A->nnz, trp.data(), tci.data(), tva.data(), &A->T);
+   return csr_from_host(ctx, A->ncols, A->nrows, A->nnz, trp.data(), tci.data(), tva.data(), 0, &A->T);
 }
 
 extern "C" int pb200_dspmm_t(pb200_ctx *ctx, const pb200_csr *A, const double *X, int64_t ldx,

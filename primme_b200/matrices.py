@@ -104,3 +104,93 @@ def csr_matvec(indptr, indices, data, x):
         return np.bincount(rows, weights=data * x[indices], minlength=len(indptr) - 1)
     return np.stack([np.bincount(rows, weights=data * x[indices, j], minlength=len(indptr) - 1)
                      for j in range(x.shape[1])], axis=1)
+
+
+def _plaw_params(n, mean_degree, exponent):
+    """weight profile w(x) = min(c x^-alpha, wmax), x = (rank + 0.5) / n, scaled to the mean degree"""
+    alpha = 1.0 / (exponent - 1.0)
+    wmax = np.sqrt(n * mean_degree)
+
+    def mean_w(c):
+        x0 = min(1.0, (c / wmax) ** (1.0 / alpha))
+        return wmax * x0 + c * (1.0 - x0 ** (1.0 - alpha)) / (1.0 - alpha), x0
+
+    lo, hi = 1e-6, mean_degree
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        if mean_w(mid)[0] < mean_degree:
+            lo = mid
+        else:
+            hi = mid
+    c = 0.5 * (lo + hi)
+    return alpha, wmax, c, mean_w(c)[1]
+
+
+def _stable_argsort(key):
+    """stable argsort of int64 keys; on a GPU box the 10^8-key sort of the C5 matrix runs on the device
+    (same permutation: stable sorts are unique)"""
+    if key.size > 1 << 22:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                k = torch.from_numpy(key).cuda()
+                order = torch.sort(k, stable=True).indices.cpu().numpy()
+                del k
+                torch.cuda.empty_cache()
+                return order
+        except Exception:
+            pass
+    return np.argsort(key, kind="stable")
+
+
+def power_law_rows(n, lo=0, hi=None, mean_degree=15.0, exponent=2.1, seed=7, chunk=1 << 22):
+    """Rows [lo, hi) of the symmetric Chung-Lu power-law graph of config C5 (expected degrees
+    ~ k^-exponent truncated at sqrt(n * mean_degree), mean `mean_degree`, values U(0,1) mirrored,
+    duplicate edges merged, largest value kept).  The edge stream is generated in fixed chunks from
+    counter-seeded generators, so every row shard of the SAME matrix can be produced independently
+    (one process per GPU builds only its rows); node ids are a fixed random permutation of the weight
+    ranks, so contiguous row shards are balanced.  Returns (indptr[hi-lo+1], indices (global), data)."""
+    hi = n if hi is None else hi
+    alpha, wmax, c, x0 = _plaw_params(n, mean_degree, exponent)
+    perm = np.random.default_rng([seed, 0xC5]).permutation(n).astype(np.int64)
+    m = int(n * mean_degree / 2)
+    head = wmax * x0
+    one_a = 1.0 - alpha
+    x0p = x0 ** one_a
+    total = head + c * (1.0 - x0p) / one_a
+
+    def node(u):
+        u = u * total
+        x = np.where(u < head, u / wmax, np.power(x0p + one_a * np.maximum(u - head, 0.0) / c, 1.0 / one_a))
+        k = np.minimum((x * n).astype(np.int64), n - 1)
+        return perm[k]
+
+    R, Cc, Vv = [], [], []
+    for j, start in enumerate(range(0, m, chunk)):
+        cnt = min(chunk, m - start)
+        rng = np.random.default_rng([seed, 1, j])
+        u = rng.random((3, cnt))
+        a, b, v = node(u[0]), node(u[1]), u[2]
+        keep = a != b
+        for r_, c_ in ((a, b), (b, a)):
+            sel = keep & (r_ >= lo) & (r_ < hi)
+            R.append((r_[sel] - lo).astype(np.int32)); Cc.append(c_[sel].astype(np.int32)); Vv.append(v[sel])
+    rows = np.concatenate(R); cols = np.concatenate(Cc); vals = np.concatenate(Vv)
+    del R, Cc, Vv
+    key = rows.astype(np.int64) * n + cols
+    del rows, cols
+    order = _stable_argsort(key)
+    key = key[order]; vals = vals[order]
+    del order
+    first = np.ones(key.size, dtype=bool)
+    first[1:] = key[1:] != key[:-1]
+    start_idx = np.flatnonzero(first)
+    # duplicates keep the LARGEST value: independent of the order of the stream, so A is exactly symmetric
+    vals = np.maximum.reduceat(vals, start_idx) if key.size else vals
+    key = key[first]
+    rloc = (key // n).astype(np.int64)
+    indices = (key % n).astype(np.int32)
+    indptr = np.zeros(hi - lo + 1, dtype=np.int64)
+    indptr[1:] = np.bincount(rloc, minlength=hi - lo)
+    indptr = np.cumsum(indptr)
+    return indptr, indices, vals.astype(np.float64)

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--side", type=int, default=100)
     ap.add_argument("--mbar", type=int, default=0, help="basis size of the steady-state shapes (default 28 / 48)")
+    ap.add_argument("--only", default="", help="comma list of name prefixes to run (default all)")
     args = ap.parse_args()
     lib = api.load_library(os.environ.get("PB200_LIB"))  # PB200_LIB: experimental build variants
     ctx = C.c_void_p()
@@ -31,7 +32,7 @@ def main():
         csr = M.laplacian_nd((args.side,) * 3)
     else:
         n, mmax, b, mbar, rs = 1250000, 64, 8, 48, 32
-        csr = M.power_law_symmetric(n, mean_degree=15.0, seed=7)
+        csr = M.power_law_rows(n, mean_degree=15.0, seed=7)
     if args.mbar > 0:
         mbar = args.mbar
     ld = (n + 15) // 16 * 16
@@ -55,7 +56,11 @@ def main():
 
     results = {}
 
+    only = [x for x in args.only.split(",") if x]
+
     def measure(name, kind, fn):
+        if only and not any(name.startswith(o) for o in only):
+            return
         fn(); fn()
         lib.pb200_ctx_set_profiling(ctx, 1)
         for _ in range(args.reps):
@@ -72,7 +77,11 @@ def main():
     Cm = rng.standard_normal((b, mmax + 1)) * 1e-3
     Y = np.eye(b) + 1e-3 * rng.standard_normal((b, b))
     m = mbar
-    measure(f"spmm b={b}", 0, lambda: lib.pb200_dspmm(ctx, A, off(V, m), ld, off(W, m), ld, b))
+    tag = "v3" if os.environ.get("PB200_SPMM_V3", "1") != "0" else "v2"
+    measure(f"spmm {tag} b={b}", 0, lambda: lib.pb200_dspmm(ctx, A, off(V, m), ld, off(W, m), ld, b))
+    if only == ["spmm"]:
+        print(json.dumps(results))
+        return
     measure(f"ortho gram m={m} b={b}", 1, lambda: lib.pb200_dortho_sweep(
         ctx, n, None, 0, ld, V, m, ld, off(V, m), b, ld, None, 0, None, 0, 1, P.ctypes.data, mmax + b + 1))
     measure(f"ortho update+gram m={m} b={b}", 1, lambda: lib.pb200_dortho_sweep(

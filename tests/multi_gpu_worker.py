@@ -65,6 +65,55 @@ def declare(lib):
     lib.pb200_ctx_peer_export.restype, lib.pb200_ctx_peer_export.argtypes = i32, [vp, vp]
     lib.pb200_ctx_peer_attach.restype, lib.pb200_ctx_peer_attach.argtypes = i32, [vp, i32, i32, C.c_char_p]
     lib.pb200_ctx_peer_active.restype, lib.pb200_ctx_peer_active.argtypes = i32, [vp]
+    lib.pb200_ddist_spmm.restype, lib.pb200_ddist_spmm.argtypes = i32, [vp, vp, vp, i64, vp, i64, i32]
+    lib.pb200_zdist_spmm.restype, lib.pb200_zdist_spmm.argtypes = i32, [vp, vp, vp, i64, vp, i64, i32]
+    lib.pb200_dist_csr_info.restype = i32
+    lib.pb200_dist_csr_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
+
+
+def dist_spmm_check(lib, ctx, csr, rank, world, counts, lo, hi, complex_vals=False, reps=3, bs=(1, 4, 8, 11)):
+    """Y_local = (A X)[lo:hi] through the compacted peer-memory halo; several blocks back to back so that
+    both gather buffers, the flags and the acknowledgements are exercised.  Returns max abs error / scale."""
+    from primme_b200 import matrices as M
+    ip, ix, da = csr
+    n = len(ip) - 1
+    nloc = hi - lo
+    rng = np.random.default_rng(17)
+    vals = da + (1j * rng.standard_normal(len(da)) if complex_vals else 0)
+    es = 16 if complex_vals else 8
+    lip = np.ascontiguousarray(ip[lo:hi + 1] - ip[lo], dtype=np.int64)
+    lix = np.ascontiguousarray(ix[ip[lo]:ip[hi]], dtype=np.int32)
+    lva = np.ascontiguousarray(vals[ip[lo]:ip[hi]], dtype=np.complex128 if complex_vals else np.float64)
+    A, D = C.c_void_p(), C.c_void_p()
+    assert lib.pb200_csr_create(ctx, nloc, n, len(lix), lip.ctypes.data, lix.ctypes.data, lva.ctypes.data, 0,
+                                1 if complex_vals else 0, C.byref(A)) == 0
+    assert lib.pb200_dist_csr_create(ctx, A, counts.ctypes.data, world, C.byref(D)) == 0
+    nl, nh, sent, peer = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
+    lib.pb200_dist_csr_info(D, C.byref(nl), C.byref(nh), C.byref(sent), C.byref(peer))
+    rows = np.repeat(np.arange(n), np.diff(ip))
+    worst = 0.0
+    for b in bs:
+        dX, dY = C.c_void_p(), C.c_void_p()
+        assert lib.pb200_malloc(ctx, es * max(nloc, 1) * b, C.byref(dX)) == 0
+        assert lib.pb200_malloc(ctx, es * max(nloc, 1) * b, C.byref(dY)) == 0
+        for rep in range(reps):
+            X = rng.standard_normal((b, n)) + (1j * rng.standard_normal((b, n)) if complex_vals else 0)
+            Xl = np.ascontiguousarray(X[:, lo:hi])
+            assert lib.pb200_copy_h2d(ctx, Xl.ctypes.data, nloc, dX, nloc, nloc, b, es) == 0
+            fn = lib.pb200_zdist_spmm if complex_vals else lib.pb200_ddist_spmm
+            assert fn(ctx, D, dX, nloc, dY, nloc, b) == 0
+            Yl = np.zeros((b, nloc), dtype=X.dtype)
+            assert lib.pb200_copy_d2h(ctx, dY, nloc, Yl.ctypes.data, nloc, nloc, b, es) == 0
+            for j in range(b):
+                prod = vals * X[j, ix]
+                ref = np.bincount(rows, weights=prod.real, minlength=n)
+                if complex_vals:
+                    ref = ref + 1j * np.bincount(rows, weights=prod.imag, minlength=n)
+                worst = max(worst, float(np.abs(Yl[j] - ref[lo:hi]).max() / (np.abs(ref).max() + 1)))
+        lib.pb200_free(ctx, dX), lib.pb200_free(ctx, dY)
+    lib.pb200_dist_csr_destroy(ctx, D)
+    lib.pb200_csr_destroy(ctx, A)
+    return dict(err=worst, nhalo=nh.value, sent=sent.value, peer_halo=peer.value)
 
 
 def sharded_solve(lib, api, ctx, D, n, nloc, rank, world, devecs, evals, rn, **workload):
@@ -95,6 +144,15 @@ def main():
     n = len(csr[0]) - 1
     ctx, A, D, counts, (lo, hi) = setup_rank(lib, api, csr, rank, world, local)
     nloc = hi - lo
+    # halo exchange on a matrix without locality (power law), real and complex
+    pl = M.power_law_rows(30011, mean_degree=12.0, seed=3)
+    npl = len(pl[0]) - 1
+    cpl = np.array([npl * (r + 1) // world - npl * r // world for r in range(world)], dtype=np.int64)
+    spmm_real = dist_spmm_check(lib, ctx, pl, rank, world, cpl, npl * rank // world, npl * (rank + 1) // world)
+    spmm_cplx = dist_spmm_check(lib, ctx, pl, rank, world, cpl, npl * rank // world, npl * (rank + 1) // world,
+                                complex_vals=True, bs=(1, 3, 8))
+    errs = torch.tensor([spmm_real["err"], spmm_cplx["err"]], dtype=torch.float64)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
     k = 6
     devecs = C.c_void_p()
     assert lib.pb200_malloc(ctx, 8 * max(nloc, 1) * k, C.byref(devecs)) == 0
@@ -115,7 +173,8 @@ def main():
         print("RESULT " + json.dumps(dict(rc=rc, evals=evals.tolist(), res=res.tolist(),
                                           orth=float(np.abs(Xf.T @ Xf - np.eye(k)).max()),
                                           matvecs=p.stats.numMatvecs, launches=lib.pb200_ctx_launches(ctx),
-                                          peer_exchange=lib.pb200_ctx_peer_active(ctx))))
+                                          peer_exchange=lib.pb200_ctx_peer_active(ctx),
+                                          spmm_err=errs.tolist(), spmm_halo=spmm_real)))
     lib.pb200_free(ctx, devecs)
     lib.pb200_dist_csr_destroy(ctx, D)
     lib.pb200_csr_destroy(ctx, A)

@@ -224,9 +224,12 @@ def _csr_case(name):
     raise KeyError(name)
 
 
+@pytest.mark.parametrize("v3", [1, 0])
 @pytest.mark.parametrize("name", ["lap3d", "lap1d", "powerlaw", "longrow", "emptyrows"])
 @pytest.mark.parametrize("b", [1, 3, 4, 8, 11])
-def test_spmm(libs, name, b):
+def test_spmm(libs, name, b, v3, monkeypatch):
+    """v3 = 1: row-major gather copy + 32-byte gathers (default for b >= 2); 0: column-major gathers"""
+    monkeypatch.setenv("PB200_SPMM_V3", str(v3))
     ip, ix, da = _csr_case(name)
     nrows = len(ip) - 1
     ncols = max(int(ix.max()) + 1, nrows) if len(ix) else nrows
@@ -258,6 +261,41 @@ def test_spmm(libs, name, b):
         assert np.allclose(Z, zt, rtol=0, atol=1e-11 * (np.abs(zt).max() + 1) * 50)
         lib.pb200_csr_destroy(d.ctx, A)
         d.close()
+
+
+@pytest.mark.parametrize("name", ["lap3d", "powerlaw", "longrow", "emptyrows"])
+@pytest.mark.parametrize("b", [1, 2, 3, 8, 9])
+def test_zspmm(name, b):
+    """complex Hermitian-patterned CSR x complex block (zprimme's matvec): values get a random imaginary
+    part; the product is compared with numpy complex arithmetic"""
+    lib = H.lib_product()
+    ip, ix, da = _csr_case(name)
+    nrows = len(ip) - 1
+    ncols = max(int(ix.max()) + 1, nrows) if len(ix) else nrows
+    rng = np.random.default_rng(11)
+    vz = da + 1j * rng.standard_normal(len(da))
+    X = rng.standard_normal((b, ncols + 2)) + 1j * rng.standard_normal((b, ncols + 2))
+    rows = np.repeat(np.arange(nrows), np.diff(ip))
+    ref = np.zeros((nrows, b), dtype=complex)
+    for j in range(b):
+        prod = vz * X[j, ix]
+        ref[:, j] = np.bincount(rows, weights=prod.real, minlength=nrows) + 1j * np.bincount(rows, weights=prod.imag, minlength=nrows)
+    d = Dev(lib)
+    lib.pb200_zspmm.restype = C.c_int
+    lib.pb200_zspmm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int]
+    A = C.c_void_p()
+    rp = np.ascontiguousarray(ip, dtype=np.int64)
+    ci = np.ascontiguousarray(ix, dtype=np.int32)
+    va = np.ascontiguousarray(vz, dtype=np.complex128)
+    assert lib.pb200_csr_create(d.ctx, nrows, ncols, len(ci), rp.ctypes.data, ci.ctypes.data, va.ctypes.data, 0, 1, C.byref(A)) == 0
+    dX = d.up(np.ascontiguousarray(X).view(np.float64))              # (b, 2*(ncols+2)) doubles
+    dY = d.up(np.zeros((b, 2 * (nrows + 1))))
+    assert lib.pb200_zspmm(d.ctx, A, dX, ncols + 2, dY, nrows + 1, b) == 0
+    Y = d.down(dY, b, 2 * (nrows + 1)).view(np.complex128)[:, :nrows].T
+    scale = np.abs(ref).max() + 1
+    assert np.allclose(Y, ref, rtol=0, atol=1e-12 * scale * 50), (name, b)
+    lib.pb200_csr_destroy(d.ctx, A)
+    d.close()
 
 
 def test_utilities(libs):

@@ -32,6 +32,9 @@ def test_two_gpu_row_sharded_solve(bs):
     out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1][7:])
     assert out["rc"] == 0 and out["launches"] > 0
     assert out["peer_exchange"] == 1  # panels all-reduced inside the kernels over NVLink peer memory
+    # compacted halo pushed over peer memory: power-law SpMM (real and complex) exact to rounding
+    assert max(out["spmm_err"]) < 1e-13 and out["spmm_halo"]["peer_halo"] == 1
+    assert 0 < out["spmm_halo"]["nhalo"] < 30011
     shape = (32, 29, 37)
     lam = [2 - 2 * np.cos(np.pi * np.arange(1, s + 1) / (s + 1)) for s in shape]
     exact = np.sort((lam[0][:, None, None] + lam[1][None, :, None] + lam[2][None, None, :]).ravel())[:6]

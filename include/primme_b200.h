@@ -216,6 +216,36 @@ int pb200_dresidual_inplace(pb200_ctx *ctx, int64_t n, const double *theta_host,
 int pb200_djacobi(pb200_ctx *ctx, int64_t n, const double *diag, const double *shifts_host,
       double minabs, const double *X, int64_t ldx, double *Y, int64_t ldy, int ncols);
 
+/* ------------------------------------------------ complex twins of K2-K6 (zprimme / C3) ----
+ * Same operations and argument lists as the d functions above on interleaved (re,im) fp64 data:
+ * device arrays column-major with leading dimensions in COMPLEX elements; host coefficient blocks
+ * and panels complex (C, Y, P, h, G, H, alpha, dots); Ritz values, norms, shifts and the Jacobi
+ * diagonal real.  "^H" is the conjugate transpose: P = [Q V X]^H X, G = X^H X, H = X^H Y,
+ * dots[j] = X(:,j)^H Y(:,j).  pb200_vwxr_out is shared: its column pointers and G_host / H_host /
+ * P_host point to complex data.  They are what zprimme / cublas_zprimme (reference
+ * include/primme_eigs.h:392,416; instantiation src/include/template_types.h:51-204) run on. */
+int pb200_zortho_sweep(pb200_ctx *ctx, int64_t n, const void *Q, int q, int64_t ldq, const void *V, int mv,
+      int64_t ldv, void *X, int b, int64_t ldx, const void *C_host, int ldc, const void *Y_host, int ldy, int xx,
+      void *P_host, int ldp);
+int pb200_zvwxr(pb200_ctx *ctx, int64_t n, const void *V, const void *W, int m, int64_t ld, const void *h_host,
+      int ldh, int nh, const double *theta_host, const pb200_vwxr_out *out);
+int pb200_zvwxr_can_fuse_gram(pb200_ctx *ctx, int64_t n, const void *V, const void *W, int m, int64_t ld, int nh,
+      const pb200_vwxr_out *out);
+int pb200_zpermute_columns(pb200_ctx *ctx, int64_t n, void *X, int64_t ldx, const int *perm_host, int ncols);
+int pb200_zcopy_columns(pb200_ctx *ctx, int64_t n, const void *X, int64_t ldx, const int *xin_host, void *Y,
+      int64_t ldy, const int *yin_host, int ncols);
+int pb200_zaxpy_columns(pb200_ctx *ctx, int64_t n, const void *alpha_host, const void *X, int64_t ldx, void *Y,
+      int64_t ldy, int ncols);
+int pb200_zscale_columns(pb200_ctx *ctx, int64_t n, const void *alpha_host, void *X, int64_t ldx, int ncols);
+int pb200_zcolumn_dots(pb200_ctx *ctx, int64_t n, const void *X, int64_t ldx, const void *Y, int64_t ldy,
+      int ncols, void *out_host);
+int pb200_zresidual_inplace(pb200_ctx *ctx, int64_t n, const double *theta_host, const void *V, int64_t ldv,
+      void *W, int64_t ldw, int ncols, double *out_host);
+int pb200_zjacobi(pb200_ctx *ctx, int64_t n, const double *diag, const double *shifts_host, double minabs,
+      const void *X, int64_t ldx, void *Y, int64_t ldy, int ncols);
+/* 1 when the matrix holds complex values */
+int pb200_csr_is_complex(const pb200_csr *A);
+
 /* ------------------------------------------------- ready-made PRIMME callbacks (operators.c) --
  * Same signature as primme_params.matrixMatvec / applyPreconditioner (reference
  * include/primme_eigs.h:170-180); x and y are DEVICE pointers (cublas_dprimme contract). */
@@ -246,6 +276,10 @@ pb200_ctx *primme_b200_solver_ctx(const struct primme_params *primme);
 int primme_b200_dprimme_csr(double *evals, double *evecs_host, double *resNorms,
       struct primme_params *primme, const int64_t *rowptr_host, const int32_t *colind_host,
       const double *vals_host, int index_base);
+int primme_b200_zprimme_csr(double *evals, void *evecs_host, double *resNorms, struct primme_params *primme,
+      const int64_t *rowptr_host, const int32_t *colind_host, const void *vals_host, int index_base);
+void primme_b200_zjacobi_apply(void *x, int64_t *ldx, void *y, int64_t *ldy, int *blockSize,
+      struct primme_params *primme, int *ierr);
 /* Built-in operator of the SVD front end (cublas_dprimme_svds): primme_svds.matrix = pb200_csr*
  * of the m x n matrix with its transposed copy (pb200_csr_build_transpose), primme_svds.matrixMatvec
  * = this function; y = A x or A' x on device blocks (reference user callback contract

@@ -50,6 +50,17 @@ int Num_larnv_dprimme(int idist, PRIMME_INT *iseed, PRIMME_INT length, double *x
 int ortho_single_iteration_dprimme(double *Q, int nQ, PRIMME_INT ldQ, double *BQ, PRIMME_INT ldBQ,
       double *QtBQ, int ldQtBQ, double *X, int *inX, int nX, PRIMME_INT ldX, double *norms,
       primme_context_mirror ctx);
+/* complex double flavours (the driver built with -DUSE_DOUBLECOMPLEX links these) */
+PRIMME_COMPLEX_DOUBLE Num_dot_zprimme(PRIMME_INT n, PRIMME_COMPLEX_DOUBLE *x, PRIMME_INT incx,
+      PRIMME_COMPLEX_DOUBLE *y, PRIMME_INT incy, primme_context_mirror ctx);
+int Num_gemv_zprimme(const char *transa, PRIMME_INT m, PRIMME_INT n, PRIMME_COMPLEX_DOUBLE alpha,
+      PRIMME_COMPLEX_DOUBLE *a, PRIMME_INT lda, PRIMME_COMPLEX_DOUBLE *x, PRIMME_INT incx,
+      PRIMME_COMPLEX_DOUBLE beta, PRIMME_COMPLEX_DOUBLE *y, PRIMME_INT incy, primme_context_mirror ctx);
+int Num_larnv_zprimme(int idist, PRIMME_INT *iseed, PRIMME_INT length, PRIMME_COMPLEX_DOUBLE *x,
+      primme_context_mirror ctx);
+int ortho_single_iteration_zprimme(PRIMME_COMPLEX_DOUBLE *Q, int nQ, PRIMME_INT ldQ, PRIMME_COMPLEX_DOUBLE *BQ,
+      PRIMME_INT ldBQ, PRIMME_COMPLEX_DOUBLE *QtBQ, int ldQtBQ, PRIMME_COMPLEX_DOUBLE *X, int *inX, int nX,
+      PRIMME_INT ldX, double *norms, primme_context_mirror ctx);
 /* layout of the mirrored context as this library was compiled (tests/test_abi.py) */
 int primme_b200_ref_context_size(void);
 int primme_b200_ref_context_offset(int field);

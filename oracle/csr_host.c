@@ -81,6 +81,61 @@ void csr_host_jacobi(void *x, PRIMME_INT *ldx, void *y, PRIMME_INT *ldy, int *bl
    *ierr = 0;
 }
 
+/* ---- complex Hermitian twins (zprimme reference runs): vals interleaved (re,im), diag real ---- */
+#include <complex.h>
+typedef double _Complex csr_zc;
+
+static void *zmv_worker(void *arg) {
+   mv_job *j = (mv_job *)arg;
+   const csr_host *A = j->A;
+   const csr_zc *vals = (const csr_zc *)A->vals;
+   for (int c = 0; c < j->bs; c++) {
+      const csr_zc *x = (const csr_zc *)j->x + (size_t)c * j->ldx;
+      csr_zc *y = (csr_zc *)j->y + (size_t)c * j->ldy;
+      for (int64_t i = j->r0; i < j->r1; i++) {
+         csr_zc t = 0.0;
+         for (int64_t k = A->rowptr[i]; k < A->rowptr[i + 1]; k++) t += vals[k] * x[A->colind[k]];
+         y[i] = t;
+      }
+   }
+   return NULL;
+}
+
+void csr_host_zmatvec(void *x, PRIMME_INT *ldx, void *y, PRIMME_INT *ldy, int *blockSize,
+      primme_params *primme, int *ierr) {
+   const csr_host *A = (const csr_host *)primme->matrix;
+   int nt = A->nthreads > 0 ? A->nthreads : 1;
+   if (nt > 256) nt = 256;
+   if (A->n < 4096) nt = 1;
+   mv_job jobs[256];
+   pthread_t th[256];
+   for (int t = 0; t < nt; t++) {
+      jobs[t].A = A, jobs[t].x = (const double *)x, jobs[t].y = (double *)y;
+      jobs[t].ldx = *ldx, jobs[t].ldy = *ldy, jobs[t].bs = *blockSize;
+      jobs[t].r0 = A->n * t / nt, jobs[t].r1 = A->n * (t + 1) / nt;
+   }
+   for (int t = 1; t < nt; t++) pthread_create(&th[t], NULL, zmv_worker, &jobs[t]);
+   zmv_worker(&jobs[0]);
+   for (int t = 1; t < nt; t++) pthread_join(th[t], NULL);
+   *ierr = 0;
+}
+
+void csr_host_zjacobi(void *x, PRIMME_INT *ldx, void *y, PRIMME_INT *ldy, int *blockSize,
+      primme_params *primme, int *ierr) {
+   const csr_host *A = (const csr_host *)primme->preconditioner;
+   for (int c = 0; c < *blockSize; c++) {
+      double sh = (A->use_shifts && primme->ShiftsForPreconditioner) ? primme->ShiftsForPreconditioner[c] : 0.0;
+      const csr_zc *xc = (const csr_zc *)x + (size_t)c * *ldx;
+      csr_zc *yc = (csr_zc *)y + (size_t)c * *ldy;
+      for (int64_t i = 0; i < A->n; i++) {
+         double d = A->diag[i] - sh;
+         if (fabs(d) < A->minabs) d = d < 0 ? -A->minabs : A->minabs;
+         yc[i] = xc[i] / d;
+      }
+   }
+   *ierr = 0;
+}
+
 /* ---- rectangular operator with the SVD callback signature (reference examples/ex_svds_dseq.c:188-230,
  * tests/COMMON/mat.c CSRMatrixMatvecSVD): y = A x (transpose == 0) or y = A' x, host blocks ---- */
 typedef struct csr_host_rect {

@@ -19,21 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-struct pb200_ctx {
-   int64_t launches;
-   int nranks, rank;
-   void *ws_ptr[4];
-   size_t ws_bytes[4];
-};
-
-struct pb200_csr {
-   int64_t nrows, ncols, nnz;
-   int64_t *rowptr; /* 0-based */
-   int32_t *colind; /* 0-based */
-   double *vals;    /* nnz (or 2*nnz if complex) */
-   int is_complex;
-   struct pb200_csr *T;
-};
+#include "kernels_ref.h"
 
 int pb200_device_count(void) { return 1; /* the CPU itself; oracle only */ }
 
@@ -91,6 +77,11 @@ int pb200_ctx_comm_free(pb200_ctx *ctx) { (void)ctx; return 0; }
 int pb200_dist_csr_create(pb200_ctx *ctx, pb200_csr *A, const int64_t *c, int nr, pb200_dist_csr **D) { (void)ctx, (void)A, (void)c, (void)nr, (void)D; return PB200_ERR_ARG; }
 int pb200_dist_csr_destroy(pb200_ctx *ctx, pb200_dist_csr *D) { (void)ctx, (void)D; return 0; }
 int pb200_ddist_spmm(pb200_ctx *ctx, pb200_dist_csr *D, const double *X, int64_t ldx, double *Y, int64_t ldy, int nc) { (void)ctx, (void)D, (void)X, (void)ldx, (void)Y, (void)ldy, (void)nc; return PB200_ERR_ARG; }
+int pb200_zdist_spmm(pb200_ctx *ctx, pb200_dist_csr *D, const void *X, int64_t ldx, void *Y, int64_t ldy, int nc) { (void)ctx, (void)D, (void)X, (void)ldx, (void)Y, (void)ldy, (void)nc; return PB200_ERR_ARG; }
+int pb200_dist_csr_info(const pb200_dist_csr *D, int64_t *a, int64_t *b, int64_t *c, int *d) { (void)D, (void)a, (void)b, (void)c, (void)d; return PB200_ERR_ARG; }
+int pb200_ctx_peer_export(pb200_ctx *ctx, void *h) { (void)ctx, (void)h; return PB200_ERR_ARG; }
+int pb200_ctx_peer_attach(pb200_ctx *ctx, int n, int r, const void *h) { (void)ctx, (void)n, (void)r, (void)h; return PB200_ERR_ARG; }
+int pb200_ctx_peer_active(pb200_ctx *ctx) { (void)ctx; return 0; }
 void primme_b200_dist_csr_matvec(void *x, int64_t *ldx, void *y, int64_t *ldy, int *bs, struct primme_params *p, int *ierr) { (void)x, (void)ldx, (void)y, (void)ldy, (void)bs, (void)p; *ierr = -1; }
 
 int pb200_malloc(pb200_ctx *ctx, size_t bytes, void **dptr) {
@@ -173,9 +164,11 @@ int pb200_csr_destroy(pb200_ctx *ctx, pb200_csr *A) {
    return 0;
 }
 int64_t pb200_csr_nnz(const pb200_csr *A) { return A->nnz; }
+int pb200_csr_is_complex(const pb200_csr *A) { return A->is_complex; }
 
 int pb200_dspmm(pb200_ctx *ctx, const pb200_csr *A, const double *X, int64_t ldx, double *Y,
       int64_t ldy, int ncols) {
+   if (A->is_complex) return PB200_ERR_ARG;
    ctx->launches++;
    for (int c = 0; c < ncols; c++) {
       const double *x = X + (size_t)c * ldx;

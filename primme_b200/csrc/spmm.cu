@@ -829,6 +829,7 @@ extern "C" int pb200_csr_destroy(pb200_ctx *ctx, pb200_csr *A) {
 }
 
 extern "C" int64_t pb200_csr_nnz(const pb200_csr *A) { return A->nnz; }
+extern "C" int pb200_csr_is_complex(const pb200_csr *A) { return A->is_complex; }
 
 // Y = A * (rows of G): the v3 kernel on an already packed block (dist.cu calls this with the peer-
 // filled buffer and the flag protocol in `sync`)

@@ -13,6 +13,7 @@
 #include "pb_host.h"
 #include <math.h>
 
+#ifndef PB_COMPLEX
 void pb_dyn_init(pb_cost_model *m, primme_params *primme) {
    m->MV_PR = m->MV = m->PR = m->qmr_only = m->qmr_plus_MV_PR = 0.0;
    m->gdk_plus_MV_PR = m->gdk_plus_MV = m->project_locked = m->reortho_locked = 0.0;
@@ -33,6 +34,7 @@ void pb_dyn_init(pb_cost_model *m, primme_params *primme) {
 }
 
 /* first sample, then the mean of the previous estimate and the new sample */
+#endif
 static double blend(double estimate, double sample) { return estimate == 0.0 ? sample : (estimate + sample) / 2.0; }
 
 static double ratio_jdqmr_gdpk(const pb_cost_model *m, int numLocked, double slowdown, double ratio_MV_outer) {
@@ -63,6 +65,7 @@ static void update_slowdown(pb_cost_model *m) {
 }
 
 /* returns 1 when the model was updated and the methods can be compared */
+#ifndef PB_COMPLEX
 int pb_dyn_update_statistics(pb_cost_model *m, primme_params *primme, double current_time, int recentConv,
       int calledAtRestart, int numConverged, double currentResNorm) {
    const double elapsed = current_time - m->timer_0;
@@ -132,6 +135,7 @@ int pb_dyn_update_statistics(pb_cost_model *m, primme_params *primme, double cur
    return 1;
 }
 
+#endif
 static int average_over_ranks(pb_solver *S, double *ratio) {
    CHK(pb_global_sum(S, ratio, 1));
    *ratio /= (double)S->primme->numProcs;
@@ -198,6 +202,7 @@ int pb_dyn_switch_from_gdpk(pb_solver *S, pb_cost_model *m) {
    return 0;
 }
 
+#ifndef PB_COMPLEX
 /* recommendation for future runs left in primme.dynamicMethodSwitch (main_iter.c:1221-1228) */
 void pb_dyn_recommend(primme_params *primme, const pb_cost_model *m) {
    if (primme->dynamicMethodSwitch <= 0) return;
@@ -205,3 +210,4 @@ void pb_dyn_recommend(primme_params *primme, const pb_cost_model *m) {
    else if (m->accum_jdq_gdk > 1.04) primme->dynamicMethodSwitch = -1; /* GD+k */
    else primme->dynamicMethodSwitch = -3;                              /* close call: dynamic */
 }
+#endif

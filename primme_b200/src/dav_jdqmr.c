@@ -21,11 +21,11 @@
 #include <string.h>
 
 /* v(:,0:bs) <- (I - Q Q') v: overlaps through the fused sweep (one Gram pass, one update pass) */
-static int project_out(pb_solver *S, const double *Q, int64_t ldQ, int nQ, double *v, int64_t ldv, int bs) {
+static int project_out(pb_solver *S, const SCALAR *Q, int64_t ldQ, int nQ, SCALAR *v, int64_t ldv, int bs) {
    primme_params *primme = S->primme;
    if (nQ <= 0 || bs <= 0) return 0;
    const double t0 = hl_wtime();
-   double *ov = (double *)malloc(sizeof(double) * (size_t)nQ * bs);
+   SCALAR *ov = (SCALAR *)malloc(sizeof(SCALAR) * (size_t)nQ * bs);
    if (!ov) return PRIMME_MALLOC_FAILURE;
    int rc = pb200_dortho_sweep(S->dev, S->n, Q, nQ, ldQ, NULL, 0, 0, v, bs, ldv, NULL, 0, NULL, 0, 0, ov, nQ);
    primme->stats.numOrthoInnerProds += (double)nQ * bs;
@@ -37,11 +37,11 @@ static int project_out(pb_solver *S, const double *Q, int64_t ldQ, int nQ, doubl
 }
 
 /* v_i <- (I - x_i x_i') v_i for every column: one batch of dots, one batch of axpys */
-static int project_out_each(pb_solver *S, const double *x, int64_t ldx, double *v, int64_t ldv, int bs) {
+static int project_out_each(pb_solver *S, const SCALAR *x, int64_t ldx, SCALAR *v, int64_t ldv, int bs) {
    primme_params *primme = S->primme;
    if (bs <= 0) return 0;
    const double t0 = hl_wtime();
-   double ov[8];
+   SCALAR ov[8];
    int rc = pb200_dcolumn_dots(S->dev, S->n, x, ldx, v, ldv, bs, ov);
    primme->stats.numOrthoInnerProds += bs;
    if (!rc) rc = pb_reduce_panel(S, ov, bs, 1, bs);
@@ -52,10 +52,10 @@ static int project_out_each(pb_solver *S, const double *x, int64_t ldx, double *
 }
 
 /* result = (I - x x')(I - Q Q')(A - shift) v   (inner_solve.c:838-890 with B = I) */
-static int apply_projected_matrix(pb_solver *S, double *v, int64_t ldv, const double *shift, const double *Q,
-      int64_t ldQ, int nQ, const double *X, int64_t ldX, int nX, int bs, double *result, int64_t ldr) {
+static int apply_projected_matrix(pb_solver *S, SCALAR *v, int64_t ldv, const double *shift, const SCALAR *Q,
+      int64_t ldQ, int nQ, const SCALAR *X, int64_t ldX, int nX, int bs, SCALAR *result, int64_t ldr) {
    CHK(pb_apply_matvec(S, v, ldv, result, ldr, bs));
-   double ms[8];
+   SCALAR ms[8];
    for (int i = 0; i < bs; i++) ms[i] = -shift[i];
    CHK(pb200_daxpy_columns(S->dev, S->n, ms, v, ldv, result, ldr, bs));
    CHK(project_out(S, Q, ldQ, nQ, result, ldr, bs));
@@ -67,24 +67,24 @@ static int apply_projected_matrix(pb_solver *S, double *v, int64_t ldv, const do
  * preconditioner,  result <- (I - RX_i x_i'/xKinvBx_i)(I - RQ RQ') K^{-1} v  (inner_solve.c:714-812 with no
  * skew-Q factorisation: RQ = the locked vectors themselves) */
 typedef struct right_projectors {
-   const double *RQ; /* evecs, nRQ columns */
+   const SCALAR *RQ; /* evecs, nRQ columns */
    int64_t ldRQ;
    int nRQ;
-   double *RX;       /* x (orthogonal) or K^{-1}x (skew), n x blockSize; permuted with the systems */
+   SCALAR *RX;       /* x (orthogonal) or K^{-1}x (skew), n x blockSize; permuted with the systems */
    int64_t ldRX;
    int nRX;          /* 0 or the current block size */
-   double *xKinvBx;  /* x_i' K^{-1} x_i, or ones; indexed by POSITION (permuted with the systems) */
+   SCALAR *xKinvBx;  /* x_i' K^{-1} x_i, or ones; indexed by POSITION (permuted with the systems) */
 } right_projectors;
 
-static int apply_projected_preconditioner(pb_solver *S, right_projectors *rp, double *v, int64_t ldv, const double *x,
-      int64_t ldx, double *result, int64_t ldr, int bs) {
+static int apply_projected_preconditioner(pb_solver *S, right_projectors *rp, SCALAR *v, int64_t ldv, const SCALAR *x,
+      int64_t ldx, SCALAR *result, int64_t ldr, int bs) {
    primme_params *primme = S->primme;
    CHK(pb_apply_precond(S, v, ldv, result, ldr, bs));
    if (!rp) return 0;
    CHK(project_out(S, rp->RQ, rp->ldRQ, rp->nRQ, result, ldr, bs));
    if (rp->nRX <= 0) return 0;
    const double t0 = hl_wtime();
-   double ov[8];
+   SCALAR ov[8];
    CHK(pb200_dcolumn_dots(S->dev, S->n, x, ldx, result, ldr, bs, ov));
    primme->stats.numOrthoInnerProds += bs;
    CHK(pb_reduce_panel(S, ov, bs, 1, bs));
@@ -103,17 +103,33 @@ static void perm_set_value_on_pos(int *p, int val, int pos, int n) {
       }
 }
 
-static int dots_real(pb_solver *S, const double *a, int64_t lda, const double *b, int64_t ldb, int bs, double *out) {
-   CHK(pb200_dcolumn_dots(S->dev, S->n, a, lda, b, ldb, bs, out));
-   return pb_reduce_panel(S, out, bs, 1, bs);
+/* real parts of the column dots (Num_dist_dots_real, auxiliary_eigs.c:662-700) */
+static int dots_real(pb_solver *S, const SCALAR *a, int64_t lda, const SCALAR *b, int64_t ldb, int bs, double *out) {
+   SCALAR tmp[8];
+   CHK(pb200_dcolumn_dots(S->dev, S->n, a, lda, b, ldb, bs, tmp));
+   CHK(pb_reduce_panel(S, tmp, bs, 1, bs));
+   for (int i = 0; i < bs; i++) out[i] = PB_REAL(tmp[i]);
+   return 0;
+}
+/* the recurrences' scalars are real in every precision (inner_solve.c:155-182) */
+static int axpy_real(pb_solver *S, int64_t n, const double *alpha, const SCALAR *X, int64_t ldx, SCALAR *Y, int64_t ldy,
+      int bs) {
+   SCALAR a[8];
+   for (int i = 0; i < bs; i++) a[i] = alpha[i];
+   return pb200_daxpy_columns(S->dev, n, a, X, ldx, Y, ldy, bs);
+}
+static int scale_real(pb_solver *S, int64_t n, const double *alpha, SCALAR *X, int64_t ldx, int bs) {
+   SCALAR a[8];
+   for (int i = 0; i < bs; i++) a[i] = alpha[i];
+   return pb200_dscale_columns(S->dev, n, a, X, ldx, bs);
 }
 
 /* x, r, sol: n x blockSize device blocks (leading dimension S->ld for x and r, ldsol for sol);
  * Q: the left projector (nQ columns, may be NULL); useX: project against every x_i as well.
  * rnorm / eval are indexed by original position, shift travels with the permutation. */
-int pb_inner_solve(pb_solver *S, int blockSize, double *x, int64_t ldx, double *r, int64_t ldr, const double *rnorm,
-      const double *Q, int64_t ldQ, int nQ, int useX, double *sol, int64_t ldsol, const double *eval, double *shift,
-      int *touch, double *work, const double *RQ, int64_t ldRQ, int nRQ, double *RX, int64_t ldRX, double *xKinvBx) {
+int pb_inner_solve(pb_solver *S, int blockSize, SCALAR *x, int64_t ldx, SCALAR *r, int64_t ldr, const double *rnorm,
+      const SCALAR *Q, int64_t ldQ, int nQ, int useX, SCALAR *sol, int64_t ldsol, const double *eval, double *shift,
+      int *touch, SCALAR *work, const SCALAR *RQ, int64_t ldRQ, int nRQ, SCALAR *RX, int64_t ldRX, SCALAR *xKinvBx) {
    right_projectors rpv = {RQ, ldRQ, nRQ, RX, ldRX, RX ? blockSize : 0, xKinvBx};
    right_projectors *rp = (nRQ > 0 || RX) ? &rpv : NULL;
    primme_params *primme = S->primme;
@@ -121,7 +137,7 @@ int pb_inner_solve(pb_solver *S, int blockSize, double *x, int64_t ldx, double *
    const int64_t n = S->n, ldw = S->ld;
    const int bs0 = blockSize;
    int sizeX = useX ? blockSize : 0;
-   double *g = work, *d = g + (size_t)ldw * bs0, *delta = d + (size_t)ldw * bs0, *w = delta + (size_t)ldw * bs0;
+   SCALAR *g = work, *d = g + (size_t)ldw * bs0, *delta = d + (size_t)ldw * bs0, *w = delta + (size_t)ldw * bs0;
    double sigma_prev[8], rho_prev[8], rho[8], alpha_prev[8], Theta_prev[8], Theta[8], tau_init[8], tau_prev[8],
          tau[8], Beta_prev[8], Delta_prev[8], Psi_prev[8], eta[8], eval_prev[8], eres_updated[8], Gamma_prev[8],
          Phi_prev[8], gamma[8], dot_sol[8], one[8];
@@ -154,14 +170,14 @@ int pb_inner_solve(pb_solver *S, int blockSize, double *x, int64_t ldx, double *
    if (cp->maxInnerIterations > 0) maxIterations = PB_MIN((PRIMME_INT)cp->maxInnerIterations, maxIterations);
 
    /* g = r, d = (right projectors) K^{-1} g */
-   CHK(pb200_copy_d2d(S->dev, r, ldr, g, ldw, n, blockSize, 8));
+   CHK(pb200_copy_d2d(S->dev, r, ldr, g, ldw, n, blockSize, PB_ES));
    CHK(apply_projected_preconditioner(S, rp, g, ldw, x, ldx, d, ldw, blockSize));
    for (i = 0; i < blockSize; i++) Theta_prev[i] = 0.0, eval_prev[i] = eval[i];
    CHK(dots_real(S, g, ldw, d, ldw, blockSize, rho_prev));
    for (i = 0; i < blockSize; i++)
       Beta_prev[i] = Delta_prev[i] = Psi_prev[i] = Gamma_prev[i] = Phi_prev[i] = eres_updated[i] = 0.0, one[i] = 1.0;
-   CHK(pb200_memset0(S->dev, delta, sizeof(double) * (size_t)ldw * blockSize));
-   for (i = 0; i < blockSize; i++) CHK(pb200_memset0(S->dev, sol + (size_t)ldsol * i, sizeof(double) * (size_t)n));
+   CHK(pb200_memset0(S->dev, delta, sizeof(SCALAR) * (size_t)ldw * blockSize));
+   for (i = 0; i < blockSize; i++) CHK(pb200_memset0(S->dev, sol + (size_t)ldsol * i, sizeof(SCALAR) * (size_t)n));
 
    for (i = 0; i < blockSize; i++) p[i] = i;
    for (PRIMME_INT numIts = 0; numIts < maxIterations && blockSize > 0; numIts++) {
@@ -175,25 +191,25 @@ int pb_inner_solve(pb_solver *S, int blockSize, double *x, int64_t ldx, double *
       for (i = 0; i < blockSize; i++) p0[i] = i, alpha_neg[i] = 0.0;
       for (i = 0; i < blockSize; i++) {
          if (!isfinite(sigma_prev[p[i]]) || sigma_prev[p[i]] == 0.0) {
-            if (numIts == 0) CHK(pb200_copy_d2d(S->dev, r + (size_t)ldr * i, ldr, sol + (size_t)ldsol * i, ldsol, n, 1, 8));
+            if (numIts == 0) CHK(pb200_copy_d2d(S->dev, r + (size_t)ldr * i, ldr, sol + (size_t)ldsol * i, ldsol, n, 1, PB_ES));
             perm_set_value_on_pos(p0, i, blockSize - ++conv, blockSize);
             continue;
          }
          alpha_prev[p[i]] = rho_prev[p[i]] / sigma_prev[p[i]];
          if (!isfinite(alpha_prev[p[i]]) || fabs(alpha_prev[p[i]]) < PB_EPS || fabs(alpha_prev[p[i]]) > 1.0 / PB_EPS) {
-            if (numIts == 0) CHK(pb200_copy_d2d(S->dev, r + (size_t)ldr * i, ldr, sol + (size_t)ldsol * i, ldsol, n, 1, 8));
+            if (numIts == 0) CHK(pb200_copy_d2d(S->dev, r + (size_t)ldr * i, ldr, sol + (size_t)ldsol * i, ldsol, n, 1, PB_ES));
             perm_set_value_on_pos(p0, i, blockSize - ++conv, blockSize);
             continue;
          }
          alpha_neg[i] = -alpha_prev[p[i]];
       }
       /* g_i -= alpha_i w_i for the systems still running (alpha = 0 leaves the others untouched) */
-      CHK(pb200_daxpy_columns(S->dev, n, alpha_neg, w, ldw, g, ldw, blockSize));
+      CHK(axpy_real(S, n, alpha_neg, w, ldw, g, ldw, blockSize));
 
 #define PB_PERMUTE_BLOCK()                                                                        \
    do {                                                                                           \
       hl_permute_ints(p, blockSize, p0);                                                          \
-      hl_permute_cols(shift, 1, blockSize, 1, p0);                                                \
+      hl_permute_reals(shift, blockSize, p0);                                                     \
       CHK(pb200_dpermute_columns(S->dev, n, g, ldw, p0, blockSize));                              \
       CHK(pb200_dpermute_columns(S->dev, n, d, ldw, p0, blockSize));                              \
       CHK(pb200_dpermute_columns(S->dev, n, delta, ldw, p0, blockSize));                          \
@@ -223,9 +239,9 @@ int pb_inner_solve(pb_solver *S, int blockSize, double *x, int64_t ldx, double *
          gam_pos[i] = gamma[p[i]], eta_pos[i] = eta[p[i]];
       }
       /* delta = gamma delta + eta d; sol += delta; |sol|^2 (device flavour of :395-413) */
-      CHK(pb200_dscale_columns(S->dev, n, gam_pos, delta, ldw, blockSize));
-      CHK(pb200_daxpy_columns(S->dev, n, eta_pos, d, ldw, delta, ldw, blockSize));
-      CHK(pb200_daxpy_columns(S->dev, n, one, delta, ldw, sol, ldsol, blockSize));
+      CHK(scale_real(S, n, gam_pos, delta, ldw, blockSize));
+      CHK(axpy_real(S, n, eta_pos, d, ldw, delta, ldw, blockSize));
+      CHK(axpy_real(S, n, one, delta, ldw, sol, ldsol, blockSize));
       if (adaptive) CHK(dots_real(S, sol, ldsol, sol, ldsol, blockSize, dot_sol));
 
       conv = 0;
@@ -317,8 +333,8 @@ int pb_inner_solve(pb_solver *S, int blockSize, double *x, int64_t ldx, double *
             tau_prev[p[i]] = tau[p[i]];
             Theta_prev[p[i]] = Theta[p[i]];
          }
-         CHK(pb200_daxpy_columns(S->dev, n, beta_pos, d, ldw, w, ldw, blockSize));
-         double *ptmp = d; /* alternate the buffers instead of copying (:618-622) */
+         CHK(axpy_real(S, n, beta_pos, d, ldw, w, ldw, blockSize));
+         SCALAR *ptmp = d; /* alternate the buffers instead of copying (:618-622) */
          d = w, w = ptmp;
       }
    }

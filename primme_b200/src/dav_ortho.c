@@ -21,20 +21,20 @@
 
 /* Number of leading columns n0..i-1 judged linearly independent from the Gram matrix G:
  * positive diagonal and |cos| to every earlier column below 0.8/maxRank (:1165-1181). */
-static int rank_estimation(const double *G, int n0, int n1, int maxRank, int ldG) {
+static int rank_estimation(const SCALAR *G, int n0, int n1, int maxRank, int ldG) {
    int i, j;
    for (i = n0; i < n1; i++) {
-      double gii = G[(size_t)i * ldG + i];
+      double gii = PB_REAL(G[(size_t)i * ldG + i]);
       if (!isfinite(gii) || gii <= 0.0) break;
       for (j = 0; j < i; j++)
-         if (fabs(G[(size_t)i * ldG + j]) > .8 / maxRank * sqrt(gii * G[(size_t)j * ldG + j])) break;
+         if (PB_ABS(G[(size_t)i * ldG + j]) > .8 / maxRank * sqrt(gii * PB_REAL(G[(size_t)j * ldG + j]))) break;
       if (j < i) break;
    }
    return i;
 }
 
 /* Cholesky if possible, else eigen-decomposition with descending eigenvalues (:1097-1137). */
-static int decomposition(const double *C, int n, int ldC, double *Y, int ldY, double *evals,
+static int decomposition(const SCALAR *C, int n, int ldC, SCALAR *Y, int ldY, double *evals,
       int *Yortho) {
    hl_copy(C, n, n, ldC, Y, ldY);
    if (hl_potrf_upper(n, Y, ldY) == 0) {
@@ -51,9 +51,9 @@ static int decomposition(const double *C, int n, int ldC, double *Y, int ldY, do
 }
 
 /* Append columns n0..n-1 to the Cholesky factor of VtBV (:1200-1220). */
-int pb_update_cholesky_gram(const double *G, double *fG, int ld, int n0, int n) {
+int pb_update_cholesky_gram(const SCALAR *G, SCALAR *fG, int ld, int n0, int n) {
    if (!fG || n <= n0) return 0;
-   double *A = (double *)malloc(sizeof(double) * (size_t)n * (n - n0));
+   SCALAR *A = (SCALAR *)malloc(sizeof(SCALAR) * (size_t)n * (n - n0));
    if (!A) return PRIMME_MALLOC_FAILURE;
    hl_copy(&G[(size_t)ld * n0], n, n - n0, ld, A, n);
    hl_trsm('L', 'U', 'C', 'N', n0, n - n0, 1.0, fG, ld, A, n);
@@ -71,8 +71,8 @@ int pb_update_cholesky(pb_solver *S, int n0, int n) {
 /* ------------------------------------------------------------------------------------------
  * CGS with reorthogonalisation, device version (no Gram matrix carried).
  * ---------------------------------------------------------------------------------------- */
-static int ortho_cgs(pb_solver *S, double *V, int64_t ldV, double *R, int ldR, int b1, int b2, const double *locked,
-      int64_t ldLocked, int numLocked, double *RLocked, int ldRLocked, int *b2_out) {
+static int ortho_cgs(pb_solver *S, SCALAR *V, int64_t ldV, SCALAR *R, int ldR, int b1, int b2, const SCALAR *locked,
+      int64_t ldLocked, int numLocked, SCALAR *RLocked, int ldRLocked, int *b2_out) {
    primme_params *primme = S->primme;
    const int maxNumOrthos = 3, maxNumRandoms = 10;
    const double tol = sqrt(2.0) / 2.0; /* Daniel et al. test */
@@ -82,13 +82,13 @@ static int ortho_cgs(pb_solver *S, double *V, int64_t ldV, double *R, int ldR, i
 
    if (R) hl_zero(&R[(size_t)ldR * b1], b2 + 1, b2 - b1 + 1, ldR); /* (:146-149) */
    if (RLocked) hl_zero(RLocked, numLocked, b2 - b1 + 1, ldRLocked);
-   double *panel = (double *)calloc((size_t)(numLocked + b2 + 2), sizeof(double));
-   double *coef = (double *)calloc((size_t)(numLocked + b2 + 2), sizeof(double));
+   SCALAR *panel = (SCALAR *)calloc((size_t)(numLocked + b2 + 2), sizeof(SCALAR));
+   SCALAR *coef = (SCALAR *)calloc((size_t)(numLocked + b2 + 2), sizeof(SCALAR));
    if (!panel || !coef) return PRIMME_MALLOC_FAILURE;
    *b2_out = b1;
 
    for (int i = b1; i <= b2; i++) {
-      double *v = V + (size_t)ldV * i;
+      SCALAR *v = V + (size_t)ldV * i;
       const int k = numLocked + i;
       int nOrth = 0, randomizations = 0, updateR = (R || RLocked) ? 1 : 0, have_panel = 0;
       double s0 = 0.0, s02 = 0.0, s1 = 0.0, s12 = 0.0;
@@ -114,12 +114,12 @@ static int ortho_cgs(pb_solver *S, double *V, int64_t ldV, double *R, int ldR, i
             if (rc) goto done;
             primme->stats.numOrthoInnerProds += k + 1;
          }
-         if (nOrth == 1) s02 = panel[k];
+         if (nOrth == 1) s02 = PB_REAL(panel[k]);
          if (updateR && R)
             for (int j = 0; j < i; j++) R[(size_t)ldR * i + j] += panel[numLocked + j];
          if (updateR && RLocked)
             for (int j = 0; j < numLocked; j++) RLocked[(size_t)ldRLocked * (i - b1) + j] += panel[j];
-         memcpy(coef, panel, sizeof(double) * k);
+         memcpy(coef, panel, sizeof(SCALAR) * k);
          /* v -= [locked V] * overlaps, then the overlaps and norm of the new v (:262-291) */
          rc = pb200_dortho_sweep(S->dev, S->n, locked, numLocked, ldLocked, V, i, ldV, v, 1, ldV,
                coef, k, NULL, 0, 1, panel, k + 1);
@@ -129,7 +129,7 @@ static int ortho_cgs(pb_solver *S, double *V, int64_t ldV, double *R, int ldR, i
          have_panel = 1;
          primme->stats.numOrthoInnerProds += 2 * k + 1;
          if (nOrth == 1) s0 = sqrt(s02);
-         s12 = panel[k];
+         s12 = PB_REAL(panel[k]);
          s1 = sqrt(s12);
 
          if (!isfinite(s0) || !isfinite(s1) || s1 <= eps_orth * s0) {
@@ -140,7 +140,8 @@ static int ortho_cgs(pb_solver *S, double *V, int64_t ldV, double *R, int ldR, i
             if (updateR && R) R[(size_t)ldR * i + i] = s1;
             double inv = 1.0 / s1;
             if (isfinite(inv)) {
-               rc = pb200_dscale_columns(S->dev, S->n, &inv, v, ldV, 1);
+               SCALAR invs = inv;
+               rc = pb200_dscale_columns(S->dev, S->n, &invs, v, ldV, 1);
                if (rc) goto done;
                break;
             }
@@ -160,17 +161,17 @@ done:
  * With S->VtBV: iterated CholQR/SVQB (:497-803); columns b1..b2 of the Gram matrix
  * [locked V]'[locked V] and of its Cholesky factor are updated.  Without: CGS.
  * ---------------------------------------------------------------------------------------- */
-static int ortho_block_gram(pb_solver *S, double *G, double *fG, int ldG, int maxRank, double *V, int64_t ldV,
-      double *R, int ldR, int b1, int b2, const double *locked, int64_t ldLocked, int numLocked, double *RLocked,
-      int ldRLocked, int *b2_out, const double *P0, int ldP0);
+static int ortho_block_gram(pb_solver *S, SCALAR *G, SCALAR *fG, int ldG, int maxRank, SCALAR *V, int64_t ldV,
+      SCALAR *R, int ldR, int b1, int b2, const SCALAR *locked, int64_t ldLocked, int numLocked, SCALAR *RLocked,
+      int ldRLocked, int *b2_out, const SCALAR *P0, int ldP0);
 
-int pb_ortho_block(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const double *locked,
-      int64_t ldLocked, int numLocked, double *RLocked, int ldRLocked, int *b2_out) {
+int pb_ortho_block(pb_solver *S, SCALAR *V, int64_t ldV, int b1, int b2, const SCALAR *locked,
+      int64_t ldLocked, int numLocked, SCALAR *RLocked, int ldRLocked, int *b2_out) {
    return pb_ortho_block_p0(S, V, ldV, b1, b2, locked, ldLocked, numLocked, RLocked, ldRLocked, b2_out, NULL, 0);
 }
 
-int pb_ortho_block_p0(pb_solver *S, double *V, int64_t ldV, int b1, int b2, const double *locked,
-      int64_t ldLocked, int numLocked, double *RLocked, int ldRLocked, int *b2_out, const double *P0,
+int pb_ortho_block_p0(pb_solver *S, SCALAR *V, int64_t ldV, int b1, int b2, const SCALAR *locked,
+      int64_t ldLocked, int numLocked, SCALAR *RLocked, int ldRLocked, int *b2_out, const SCALAR *P0,
       int ldP0) {
    return ortho_block_gram(S, S->VtBV, S->fVtBV, S->maxRank, S->maxRank, V, ldV, NULL, 0, b1, b2, locked, ldLocked,
          numLocked, RLocked, ldRLocked, b2_out, P0, ldP0);
@@ -178,14 +179,14 @@ int pb_ortho_block_p0(pb_solver *S, double *V, int64_t ldV, int b1, int b2, cons
 
 /* ortho_block (ortho.c:477-493) of a second set of vectors with its own Gram matrix (or none: CGS), returning
  * the factor R with input = output * R: the QR factorisation of (A - tau I) V kept by the refined extraction */
-int pb_ortho_block_R(pb_solver *S, double *Q, int64_t ldQ, double *QtQ, double *fQtQ, int ldQtQ, int maxRank,
-      double *R, int ldR, int b1, int b2, int *b2_out) {
+int pb_ortho_block_R(pb_solver *S, SCALAR *Q, int64_t ldQ, SCALAR *QtQ, SCALAR *fQtQ, int ldQtQ, int maxRank,
+      SCALAR *R, int ldR, int b1, int b2, int *b2_out) {
    return ortho_block_gram(S, QtQ, fQtQ, ldQtQ, maxRank, Q, ldQ, R, ldR, b1, b2, NULL, 0, 0, NULL, 0, b2_out, NULL, 0);
 }
 
-static int ortho_block_gram(pb_solver *S, double *G, double *fG, int ldG, int maxRank, double *V, int64_t ldV,
-      double *R, int ldR, int b1, int b2, const double *locked, int64_t ldLocked, int numLocked, double *RLocked,
-      int ldRLocked, int *b2_out, const double *P0, int ldP0) {
+static int ortho_block_gram(pb_solver *S, SCALAR *G, SCALAR *fG, int ldG, int maxRank, SCALAR *V, int64_t ldV,
+      SCALAR *R, int ldR, int b1, int b2, const SCALAR *locked, int64_t ldLocked, int numLocked, SCALAR *RLocked,
+      int ldRLocked, int *b2_out, const SCALAR *P0, int ldP0) {
    primme_params *primme = S->primme;
    b2++; /* C range convention from here on */
    if (b2 <= b1) {
@@ -218,15 +219,15 @@ static int ortho_block_gram(pb_solver *S, double *G, double *fG, int ldG, int ma
    const double eps_orth = PB_EPS;
    const double t0 = hl_wtime();
    const int nb = b2 - b1, nVL = b1 + numLocked;
-   double *A = &G[(size_t)ldG * nVL]; /* new columns of the Gram matrix */
+   SCALAR *A = &G[(size_t)ldG * nVL]; /* new columns of the Gram matrix */
    int rc = 0;
 
    double *D = (double *)malloc(sizeof(double) * nb), *N = (double *)malloc(sizeof(double) * nb);
-   double *GdA = (double *)malloc(sizeof(double) * (size_t)(nVL > 0 ? nVL : 1) * nb);
-   double *Y = (double *)malloc(sizeof(double) * nb * nb), *Yapply = (double *)malloc(sizeof(double) * nb * nb);
-   double *C = (double *)malloc(sizeof(double) * nb * nb), *r = NULL;
+   SCALAR *GdA = (SCALAR *)malloc(sizeof(SCALAR) * (size_t)(nVL > 0 ? nVL : 1) * nb);
+   SCALAR *Y = (SCALAR *)malloc(sizeof(SCALAR) * nb * nb), *Yapply = (SCALAR *)malloc(sizeof(SCALAR) * nb * nb);
+   SCALAR *C = (SCALAR *)malloc(sizeof(SCALAR) * nb * nb), *r = NULL;
    if (!D || !N || !GdA || !Y || !C || !Yapply) return PRIMME_MALLOC_FAILURE;
-   double *r_own = NULL;
+   SCALAR *r_own = NULL;
    int ldr = nb;
    if (R) {
       /* the diagonal block of R accumulates the rotations of the block itself (:556-580) */
@@ -235,7 +236,7 @@ static int ortho_block_gram(pb_solver *S, double *G, double *fG, int ldG, int ma
    }
    if (RLocked) {
       hl_zero(RLocked, numLocked, nb, ldRLocked);
-      if (!r) r = r_own = (double *)malloc(sizeof(double) * (size_t)nb * nb);
+      if (!r) r = r_own = (SCALAR *)malloc(sizeof(SCALAR) * (size_t)nb * nb);
    }
    if (r) {
       hl_zero(r, nb, nb, ldr);
@@ -248,7 +249,7 @@ static int ortho_block_gram(pb_solver *S, double *G, double *fG, int ldG, int ma
    for (int its = 0; its < maxits; its++) {
       /* one row sweep: X <- (X - [locked V] GdA) Yapply (not in the first pass), then the
        * Gram panel A = [locked V(:,0:b2)]' X  (:631-636, kernel :963-1072) */
-      const double *Cc = NULL, *Yc = NULL;
+      const SCALAR *Cc = NULL, *Yc = NULL;
       if (its > 0) {
          Cc = GdA;
          if (Yortho) {
@@ -281,7 +282,7 @@ static int ortho_block_gram(pb_solver *S, double *G, double *fG, int ldG, int ma
       if (rank_estimation(G, nVL, numLocked + b2, maxRank, ldG) == numLocked + b2) {
          if (its >= plus1) {
             int i;
-            for (i = b1; i < b2 && fabs(G[(size_t)ldG * (numLocked + i) + numLocked + i] - 1.0) < .8; i++)
+            for (i = b1; i < b2 && PB_ABS(G[(size_t)ldG * (numLocked + i) + numLocked + i] - 1.0) < .8; i++)
                ;
             if (i >= b2) break;
          } else
@@ -290,7 +291,7 @@ static int ortho_block_gram(pb_solver *S, double *G, double *fG, int ldG, int ma
 
       /* overflowed norms: drop the inner products with the other vectors (:668-674) */
       for (int i = 0; i < nb; i++) {
-         if (A[(size_t)ldG * i + i] < DBL_MAX) continue;
+         if (PB_ABS(A[(size_t)ldG * i + i]) < DBL_MAX) continue;
          hl_zero(&G[(size_t)ldG * (numLocked + i)], numLocked + i, 1, ldG);
          A[(size_t)ldG * i + i] = DBL_MAX;
       }
@@ -302,7 +303,7 @@ static int ortho_block_gram(pb_solver *S, double *G, double *fG, int ldG, int ma
       hl_gemm('C', 'N', nb, nb, nVL, -1.0, GdA, nVL > 0 ? nVL : 1, GdA, nVL > 0 ? nVL : 1, 1.0, C, nb);
       hl_trsm('L', 'U', 'N', 'N', nVL, nb, 1.0, fG, ldG, GdA, nVL > 0 ? nVL : 1);
 
-      for (int i = 0; i < nb; i++) N[i] = sqrt(PB_MAX(fabs(C[(size_t)nb * i + i]), eps_orth));
+      for (int i = 0; i < nb; i++) N[i] = sqrt(PB_MAX(PB_ABS(C[(size_t)nb * i + i]), eps_orth));
       for (int i = 0; i < nb; i++)
          for (int j = 0; j <= i; j++) C[(size_t)nb * i + j] /= N[i] * N[j];
 
@@ -322,7 +323,7 @@ static int ortho_block_gram(pb_solver *S, double *G, double *fG, int ldG, int ma
             /* C = U * r */
             for (int j = 0; j < nb; j++)
                for (int i = 0; i < nb; i++) {
-                  double s = 0.0;
+                  SCALAR s = 0.0;
                   for (int l = i; l < nb; l++) s += Y[(size_t)nb * l + i] * r[(size_t)ldr * j + l];
                   C[(size_t)nb * j + i] = s;
                }
@@ -351,16 +352,16 @@ done:
 }
 
 /* X(:,inX) <- (I - Q inv(Q'Q) Q') X(:,inX), norms of the results (:826-934). */
-int pb_ortho_single_iteration(pb_solver *S, const double *Q, int nQ, int64_t ldQ,
-      const double *QtQ, int ldQtQ, double *X, const int *inX, int nX, int64_t ldX,
+int pb_ortho_single_iteration(pb_solver *S, const SCALAR *Q, int nQ, int64_t ldQ,
+      const SCALAR *QtQ, int ldQtQ, SCALAR *X, const int *inX, int nX, int64_t ldX,
       double *norms) {
    primme_params *primme = S->primme;
    const double t0 = hl_wtime();
    (void)QtQ, (void)ldQtQ; /* reference computes z = QtQ\y but applies y (:885-906): same here */
-   double *panel = (double *)malloc(sizeof(double) * (size_t)(nQ + 1));
+   SCALAR *panel = (SCALAR *)malloc(sizeof(SCALAR) * (size_t)(nQ + 1));
    if (!panel) return PRIMME_MALLOC_FAILURE;
    for (int j = 0; j < nX; j++) {
-      double *x = X + (size_t)ldX * (inX ? inX[j] : j);
+      SCALAR *x = X + (size_t)ldX * (inX ? inX[j] : j);
       CHK(pb200_dortho_sweep(S->dev, S->n, Q, nQ, ldQ, NULL, 0, 0, x, 1, ldX, NULL, 0, NULL, 0, 0,
             panel, nQ + 1));
       CHK(pb_reduce_panel(S, panel, nQ, 1, nQ + 1));
@@ -368,7 +369,7 @@ int pb_ortho_single_iteration(pb_solver *S, const double *Q, int nQ, int64_t ldQ
             0, 1, norms ? panel : NULL, nQ + 1));
       if (norms) {
          CHK(pb_reduce_panel(S, panel, nQ + 1, 1, nQ + 1));
-         norms[j] = sqrt(panel[nQ]);
+         norms[j] = sqrt(PB_REAL(panel[nQ]));
       }
    }
    primme->stats.numOrthoInnerProds += (double)nQ * nX + (norms ? nX : 0);
@@ -384,16 +385,16 @@ int pb_ortho_single_iteration(pb_solver *S, const double *Q, int nQ, int64_t ldQ
  * and V(:,0:b1).  R (column stride 1 x 1 use only) receives the final norm or 0 if the vector
  * had to be replaced by a random one.  Returns 0 or -3.
  * ---------------------------------------------------------------------------------------- */
-static int ortho_local_gen(double *V, int ldV, double *R, int ldR, int b1, int b2, double *locked, int ldLocked,
-      int numLocked, int n, const double *B, int ldB, long long *iseed) {
+static int ortho_local_gen(SCALAR *V, int ldV, SCALAR *R, int ldR, int b1, int b2, SCALAR *locked, int ldLocked,
+      int numLocked, int n, const SCALAR *B, int ldB, long long *iseed) {
    const int maxNumOrthos = 7, maxNumRandoms = 10;
    const double tol = sqrt(2.0) / 2.0, eps_orth = PB_EPS;
-   double *overlaps = (double *)calloc((size_t)(b2 + 2 + numLocked), sizeof(double));
-   double *Bx = (double *)malloc(sizeof(double) * (n > 0 ? n : 1));
+   SCALAR *overlaps = (SCALAR *)calloc((size_t)(b2 + 2 + numLocked), sizeof(SCALAR));
+   SCALAR *Bx = (SCALAR *)malloc(sizeof(SCALAR) * (n > 0 ? n : 1));
    int ok = 1;
    if (R && b2 >= b1) hl_zero(&R[(size_t)ldR * b1], b2 + 1, b2 - b1 + 1, ldR); /* (:146-149) */
    for (int i = b1; i <= b2 && ok; i++) {
-      double *v = &V[(size_t)ldV * i];
+      SCALAR *v = &V[(size_t)ldV * i];
       int nOrth = 0, randomizations = 0, updateR = R ? 1 : 0, Bx_update = 0;
       double s0 = 0, s02 = 0, s1 = 0, s12 = 0;
       for (;;) {
@@ -412,7 +413,7 @@ static int ortho_local_gen(double *V, int ldV, double *R, int ldR, int b1, int b
             Bx_update = 0;
          }
          nOrth++;
-         const double *bx = v;
+         const SCALAR *bx = v;
          if (B) {
             if (!Bx_update) {
                hl_zero(Bx, n, 1, n);
@@ -420,7 +421,7 @@ static int ortho_local_gen(double *V, int ldV, double *R, int ldR, int b1, int b
             }
             bx = Bx;
          }
-         if (nOrth == 1) s02 = hl_dot(n, v, bx);
+         if (nOrth == 1) s02 = PB_REAL(hl_dot(n, v, bx));
          if (i > 0) hl_gemm('C', 'N', i, 1, n, 1.0, V, ldV, bx, n, 0.0, overlaps, i);
          if (numLocked > 0)
             hl_gemm('C', 'N', numLocked, 1, n, 1.0, locked, ldLocked, bx, n, 0.0, &overlaps[i], numLocked);
@@ -431,7 +432,7 @@ static int ortho_local_gen(double *V, int ldV, double *R, int ldR, int b1, int b
             hl_gemm('N', 'N', n, 1, numLocked, -1.0, locked, ldLocked, &overlaps[i], numLocked, 1.0, v, n);
          if (i > 0) hl_gemm('N', 'N', n, 1, i, -1.0, V, ldV, overlaps, i, 1.0, v, n);
          Bx_update = 0;
-         if (nOrth == 1) s0 = sqrt(s02 = overlaps[i + numLocked]);
+         if (nOrth == 1) s0 = sqrt(s02 = PB_REAL(overlaps[i + numLocked]));
          if (B) {
             hl_zero(Bx, n, 1, n);
             hl_symm_lu(n, 1, 1.0, B, ldB, v, ldV > n ? ldV : n, 0.0, Bx, n);
@@ -439,7 +440,7 @@ static int ortho_local_gen(double *V, int ldV, double *R, int ldR, int b1, int b
             bx = Bx;
          } else
             bx = v;
-         s12 = hl_dot(n, v, bx);
+         s12 = PB_REAL(hl_dot(n, v, bx));
          s1 = sqrt(s12);
          if (!isfinite(s0) || !isfinite(s1) || s1 <= eps_orth * s0) {
             nOrth = maxNumOrthos;
@@ -460,13 +461,13 @@ static int ortho_local_gen(double *V, int ldV, double *R, int ldR, int b1, int b
    return ok ? 0 : -3;
 }
 
-int pb_ortho_local(double *V, int ldV, double *R, int b1, int b2, double *locked, int ldLocked,
-      int numLocked, int n, const double *B, int ldB, long long *iseed) {
+int pb_ortho_local(SCALAR *V, int ldV, SCALAR *R, int b1, int b2, SCALAR *locked, int ldLocked,
+      int numLocked, int n, const SCALAR *B, int ldB, long long *iseed) {
    return ortho_local_gen(V, ldV, R, 1, b1, b2, locked, ldLocked, numLocked, n, B, ldB, iseed);
 }
 
 /* same with the full factor: V(:,b1..b2) = V_out * R(:,b1..b2), R with leading dimension ldR */
-int pb_ortho_local_R(double *V, int ldV, double *R, int ldR, int b1, int b2, int n, const double *B, int ldB,
+int pb_ortho_local_R(SCALAR *V, int ldV, SCALAR *R, int ldR, int b1, int b2, int n, const SCALAR *B, int ldB,
       long long *iseed) {
    if (b2 < b1) return 0;
    return ortho_local_gen(V, ldV, R, ldR, b1, b2, NULL, 0, 0, n, B, ldB, iseed);

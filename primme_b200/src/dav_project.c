@@ -10,16 +10,17 @@
 #include <string.h>
 
 /* Sum a host panel over the ranks unless the kernel layer already did it on the device. */
-int pb_reduce_panel(pb_solver *S, double *P, int rows, int cols, int ldp) {
+int pb_reduce_panel(pb_solver *S, SCALAR *P, int rows, int cols, int ldp) {
    primme_params *primme = S->primme;
    if (primme->numProcs <= 1 || pb200_ctx_nranks(S->dev) > 1) return 0;
    int cnt = rows * cols;
    if (cnt <= 0) return 0;
-   if (ldp == rows) return pb_global_sum(S, P, cnt);
-   double *tmp = (double *)malloc(sizeof(double) * cnt);
+   const int rpe = PB_ES / 8; /* reals per element (globalSumReal counts reals, auxiliary_eigs.c:371-373) */
+   if (ldp == rows) return pb_global_sum(S, (double *)P, cnt * rpe);
+   SCALAR *tmp = (SCALAR *)malloc(sizeof(SCALAR) * cnt);
    if (!tmp) return PRIMME_MALLOC_FAILURE;
    hl_copy(P, rows, cols, ldp, tmp, rows);
-   int r = pb_global_sum(S, tmp, cnt);
+   int r = pb_global_sum(S, (double *)tmp, cnt * rpe);
    hl_copy(tmp, rows, cols, rows, P, ldp);
    free(tmp);
    return r;
@@ -30,10 +31,10 @@ int pb_reduce_panel(pb_solver *S, double *P, int rows, int cols, int ldp) {
 static int update_projection_impl(pb_solver *S, int numCols, int blockSize) {
    if (blockSize <= 0) return 0;
    const int m = numCols + blockSize;
-   double *Hcol = &S->H[(size_t)S->maxBasis * numCols];
+   SCALAR *Hcol = &S->H[(size_t)S->maxBasis * numCols];
    for (int c0 = 0; c0 < blockSize; c0 += 8) {
       int bc = PB_MIN(8, blockSize - c0);
-      double *P = Hcol + (size_t)S->maxBasis * c0;
+      SCALAR *P = Hcol + (size_t)S->maxBasis * c0;
       CHK(pb200_dortho_sweep(S->dev, S->n, NULL, 0, 0, S->V, m, S->ld,
             S->W + (size_t)S->ld * (numCols + c0), bc, S->ld, NULL, 0, NULL, 0, 0, P,
             S->maxBasis));
@@ -44,8 +45,8 @@ static int update_projection_impl(pb_solver *S, int numCols, int blockSize) {
 
 /* Solve the projected (generalized) eigenproblem and order the pairs by primme.target
  * (reference solve_projection.c:188-331). */
-static int solve_H_impl(pb_solver *S, const double *H, int ldH, int n, const double *VtBVblk, int ldVtBV,
-      double *hVecs, int ldhVecs, double *hVals, int numConverged, int updateStats) {
+static int solve_H_impl(pb_solver *S, const SCALAR *H, int ldH, int n, const SCALAR *VtBVblk, int ldVtBV,
+      SCALAR *hVecs, int ldhVecs, double *hVals, int numConverged, int updateStats) {
    primme_params *primme = S->primme;
    if (n == 0) return 0;
    const double sign = primme->target == primme_largest ? -1.0 : 1.0;
@@ -98,7 +99,7 @@ static int solve_H_impl(pb_solver *S, const double *H, int ldH, int n, const dou
                permu[index++] = j++;
          }
       }
-      hl_permute_cols(hVals, 1, n, 1, permu);
+      hl_permute_reals(hVals, n, permu);
       hl_permute_cols(hVecs, n, n, ldhVecs, permu);
       free(permu);
    }
@@ -117,18 +118,18 @@ static int solve_H_impl(pb_solver *S, const double *H, int ldH, int n, const dou
 
 /* For every column i in [n0,n) of W pick the not-yet-taken column of V with the largest
  * |cos| (reference solve_projection.c:1009-1064). */
-int pb_map_vecs(const double *V, int m, int nV, int ldV, const double *W, int n0, int n, int ldW,
+int pb_map_vecs(const SCALAR *V, int m, int nV, int ldV, const SCALAR *W, int n0, int n, int ldW,
       int *p) {
    double *Vnorms = (double *)malloc(sizeof(double) * (nV > 0 ? nV : 1));
-   double *ip = (double *)calloc((size_t)(nV > 0 ? nV : 1) * (n - n0 > 0 ? n - n0 : 1), sizeof(double));
+   SCALAR *ip = (SCALAR *)calloc((size_t)(nV > 0 ? nV : 1) * (n - n0 > 0 ? n - n0 : 1), sizeof(SCALAR));
    for (int i = 0; i < nV; i++)
-      Vnorms[i] = sqrt(hl_dot(m, &V[(size_t)ldV * i], &V[(size_t)ldV * i]));
+      Vnorms[i] = sqrt(PB_REAL(hl_dot(m, &V[(size_t)ldV * i], &V[(size_t)ldV * i])));
    hl_gemm('C', 'N', nV, n - n0, m, 1.0, V, ldV, &W[(size_t)ldW * n0], ldW, 0.0, ip, nV > 0 ? nV : 1);
    for (int i = n0; i < n; i++) {
       int jmax = -1;
       double ipmax = -1;
       for (int j = 0; j < nV; j++) {
-         double ipij = fabs(ip[(size_t)nV * (i - n0) + j]);
+         double ipij = PB_ABS(ip[(size_t)nV * (i - n0) + j]);
          if (ipij > ipmax * Vnorms[j]) {
             int k;
             for (k = 0; k < i && p[k] != j; k++)
@@ -153,8 +154,8 @@ int pb_update_projection(pb_solver *S, int numCols, int blockSize) {
    return rc;
 }
 
-int pb_solve_H(pb_solver *S, const double *H, int ldH, int n, const double *VtBVblk, int ldVtBV,
-      double *hVecs, int ldhVecs, double *hVals, int numConverged, int updateStats) {
+int pb_solve_H(pb_solver *S, const SCALAR *H, int ldH, int n, const SCALAR *VtBVblk, int ldVtBV,
+      SCALAR *hVecs, int ldhVecs, double *hVals, int numConverged, int updateStats) {
    const double t0 = hl_wtime();
    int rc = solve_H_impl(S, H, ldH, n, VtBVblk, ldVtBV, hVecs, ldhVecs, hVals, numConverged, updateStats);
    S->tSolveH += hl_wtime() - t0;

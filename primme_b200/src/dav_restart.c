@@ -16,6 +16,7 @@
 #include <string.h>
 
 /* ------------------------------------------------------------------------------------------ */
+#ifndef PB_COMPLEX
 int pb_insertion_sort(double newVal, double *evals, double newNorm, double *resNorms,
       int newFlag, int *flags, int *perm, int n, int initialShift, primme_params *primme) {
    int i;
@@ -55,13 +56,14 @@ int pb_insertion_sort(double newVal, double *evals, double newNorm, double *resN
    if (flags) flags[i] = newFlag;
    return 0;
 }
+#endif
 
 /* ------------------------------------------------------------------------------------------
  * Flag pairs [left,right) as converged / unconverged from their residual norms
  * (convergence.c:86-204).  R (device, optional) may lose its components along the locked
  * vectors when the practical-convergence test runs.
  * ---------------------------------------------------------------------------------------- */
-int pb_check_convergence(pb_solver *S, double *X, int64_t ldX, int givenX, double *R,
+int pb_check_convergence(pb_solver *S, SCALAR *X, int64_t ldX, int givenX, SCALAR *R,
       int64_t ldR, int givenR, int numLocked, int left, int right, int *flags,
       double *blockNorms, double *hVals, int *reset, int practConvCheck) {
    primme_params *primme = S->primme;
@@ -133,7 +135,7 @@ int pb_check_convergence(pb_solver *S, double *X, int64_t ldX, int givenX, doubl
  * (restart.c:2347-2408).
  * ---------------------------------------------------------------------------------------- */
 static int ortho_coefficient_vectors(pb_solver *S, int basisSize, int indexOfPreviousVecs,
-      const double *VtBVblk, int nprevhVecs, int *numPrevRetained) {
+      const SCALAR *VtBVblk, int nprevhVecs, int *numPrevRetained) {
    primme_params *primme = S->primme;
    const int ld = S->maxBasis;
    int retained = 0;
@@ -141,14 +143,14 @@ static int ortho_coefficient_vectors(pb_solver *S, int basisSize, int indexOfPre
                    indexOfPreviousVecs + retained < basisSize;
          i++) {
       if (primme->locking == 0 && S->flags[i] != UNCONVERGED) continue;
-      double R = 0.0;
+      SCALAR R = 0.0;
       long long seed[4];
       for (int t = 0; t < 4; t++) seed[t] = primme->iseed[t];
       int rc = pb_ortho_local(&S->prevhVecs[(size_t)ld * i], ld, &R, 0, 0, S->hVecs, ld,
             indexOfPreviousVecs + retained, basisSize, VtBVblk, S->maxRank, seed);
       for (int t = 0; t < 4; t++) primme->iseed[t] = seed[t];
       if (rc) return PRIMME_UNEXPECTED_FAILURE;
-      if (fabs(R) < PB_EPS * sqrt(retained + 1.0)) continue;
+      if (PB_ABS(R) < PB_EPS * sqrt(retained + 1.0)) continue;
       hl_copy(&S->prevhVecs[(size_t)ld * i], basisSize, 1, ld,
             &S->hVecs[(size_t)ld * (indexOfPreviousVecs + retained)], ld);
       retained++;
@@ -162,35 +164,35 @@ static int ortho_coefficient_vectors(pb_solver *S, int basisSize, int indexOfPre
  * h is S->hVecs (basisSize x nh).  evecsSize = numOrthoConst + numLocked (columns already in
  * evecs); columns [x2b,x2e) of V*h are appended to evecs.
  * ---------------------------------------------------------------------------------------- */
-static int aux_update_VWXR(pb_solver *S, int basisSize, int nh, int restartSize, double *X1,
-      int x1b, int x1e, int evecsSize, int x2b, int x2e, double *Rout, double *Rnorms, double *rnorms,
+static int aux_update_VWXR(pb_solver *S, int basisSize, int nh, int restartSize, SCALAR *X1,
+      int x1b, int x1e, int evecsSize, int x2b, int x2e, SCALAR *Rout, double *Rnorms, double *rnorms,
       int rb, int re, int Hfull) {
    primme_params *primme = S->primme;
    pb200_vwxr_out o;
    memset(&o, 0, sizeof(o));
    const double t0 = hl_wtime();
-   o.X[0].ptr = S->V, o.X[0].ld = S->ld, o.X[0].cb = 0, o.X[0].ce = restartSize;
-   if (X1 && x1e > x1b) o.X[1].ptr = X1, o.X[1].ld = S->ld, o.X[1].cb = x1b, o.X[1].ce = x1e;
+   o.X[0].ptr = PB_DP(S->V), o.X[0].ld = S->ld, o.X[0].cb = 0, o.X[0].ce = restartSize;
+   if (X1 && x1e > x1b) o.X[1].ptr = PB_DP(X1), o.X[1].ld = S->ld, o.X[1].cb = x1b, o.X[1].ce = x1e;
    if (x2e > x2b)
-      o.X[2].ptr = S->evecs + (size_t)S->ldevecs * evecsSize, o.X[2].ld = S->ldevecs,
+      o.X[2].ptr = PB_DP(S->evecs + (size_t)S->ldevecs * evecsSize), o.X[2].ld = S->ldevecs,
       o.X[2].cb = x2b, o.X[2].ce = x2e;
-   o.Wo.ptr = S->W, o.Wo.ld = S->ld, o.Wo.cb = 0, o.Wo.ce = restartSize;
-   if (Rout && x1e > x1b) o.R.ptr = Rout, o.R.ld = S->ld, o.R.cb = x1b, o.R.ce = x1e;
+   o.Wo.ptr = PB_DP(S->W), o.Wo.ld = S->ld, o.Wo.cb = 0, o.Wo.ce = restartSize;
+   if (Rout && x1e > x1b) o.R.ptr = PB_DP(Rout), o.R.ld = S->ld, o.R.cb = x1b, o.R.ce = x1e;
    o.Rnorms_host = Rnorms;
    if (rnorms && re > rb) o.rb = rb, o.re = re, o.rnorms_host = rnorms;
-   double *Gtmp = NULL;
+   SCALAR *Gtmp = NULL;
    if (S->VtBV) {
       o.nG = restartSize;
-      o.G_host = &S->VtBV[(size_t)S->maxRank * evecsSize + evecsSize];
+      o.G_host = PB_DP(&S->VtBV[(size_t)S->maxRank * evecsSize + evecsSize]);
       o.ldG = S->maxRank;
    }
-   if (Hfull) o.nH = restartSize, o.H_host = S->H, o.ldH = S->maxBasis;
+   if (Hfull) o.nH = restartSize, o.H_host = PB_DP(S->H), o.ldH = S->maxBasis;
 
    /* cross block VtBV(0:evecsSize, new) = VtBV(0:evecsSize, old) * h: needs the old columns,
     * which the G output overwrites only below row evecsSize -- compute it first */
-   double *cross = NULL;
+   SCALAR *cross = NULL;
    if (S->VtBV && evecsSize > 0) {
-      cross = (double *)calloc((size_t)evecsSize * restartSize, sizeof(double));
+      cross = (SCALAR *)calloc((size_t)evecsSize * restartSize, sizeof(SCALAR));
       hl_gemm('N', 'N', evecsSize, restartSize, basisSize, 1.0,
             &S->VtBV[(size_t)S->maxRank * evecsSize], S->maxRank, S->hVecs, S->maxBasis, 0.0,
             cross, evecsSize);
@@ -205,8 +207,8 @@ static int aux_update_VWXR(pb_solver *S, int basisSize, int nh, int restartSize,
    if (primme->numProcs > 1 && pb200_ctx_nranks(S->dev) <= 1) {
       /* host-callback reduction of everything the sweep produced */
       int nR = o.R.ptr ? o.R.ce - o.R.cb : 0, nr = o.rnorms_host ? re - rb : 0;
-      if (o.G_host) rc = pb_reduce_panel(S, o.G_host, o.nG, o.nG, o.ldG);
-      if (!rc && o.H_host) rc = pb_reduce_panel(S, o.H_host, o.nH, o.nH, o.ldH);
+      if (o.G_host) rc = pb_reduce_panel(S, (SCALAR *)o.G_host, o.nG, o.nG, o.ldG);
+      if (!rc && o.H_host) rc = pb_reduce_panel(S, (SCALAR *)o.H_host, o.nH, o.nH, o.ldH);
       if (!rc && Rnorms && nR) {
          for (int i = 0; i < nR; i++) Rnorms[i] *= Rnorms[i];
          rc = pb_global_sum(S, Rnorms, nR);
@@ -277,11 +279,11 @@ static int restart_soft_locking(pb_solver *S, int *restartSize, int basisSize, i
       else
          restartPerm[k++] = i;
    }
-   hl_permute_cols(hVals, 1, basisSize, 1, restartPerm);
+   hl_permute_reals(hVals, basisSize, restartPerm);
    hl_permute_cols(S->hVecs, basisSize, basisSize, S->maxBasis, restartPerm);
 
-   double *X = S->V + (size_t)S->ld * *restartSize;
-   double *R = S->W + (size_t)S->ld * *restartSize;
+   SCALAR *X = S->V + (size_t)S->ld * *restartSize;
+   SCALAR *R = S->W + (size_t)S->ld * *restartSize;
    int rc = aux_update_VWXR(S, basisSize, *restartSize, *restartSize, X, *numConverged,
          *numConverged + *ievSize, primme->numOrthoConst, 0, 0 /* evecs untouched: see below */,
          R, S->blockNorms, NULL, 0, 0, primme->orth == primme_orth_explicit_I);
@@ -301,34 +303,34 @@ static int restart_soft_locking(pb_solver *S, int *restartSize, int basisSize, i
 /* Device helper for hard locking: see reference compute_residual_columns (restart.c:2464-2536).
  *   x(:,0:n) <- x(:,p), Ax likewise; (xd, rd)(:,id) for id < nd = next block column taken either
  *   from (xo, ro) (when pd[id] == next xo index) or from a failed pair (x(:,p[i]), its residual). */
-static int residual_columns(pb_solver *S, const double *evals, double *x, int n, const int *p,
-      double *Ax, const double *xo, int no, const double *ro, double *xd, int nd, const int *pd,
-      double *rd) {
+static int residual_columns(pb_solver *S, const double *evals, SCALAR *x, int n, const int *p,
+      SCALAR *Ax, const SCALAR *xo, int no, const SCALAR *ro, SCALAR *xd, int nd, const int *pd,
+      SCALAR *rd) {
    const int64_t ld = S->ld, N = S->n;
-   double *tmp = NULL;
-   if (nd > 0) CHK(pb200_malloc(S->dev, sizeof(double) * (size_t)(N > 0 ? N : 1) * nd * 2, (void **)&tmp));
-   double *XD = tmp, *RD = tmp ? tmp + (size_t)N * nd : NULL;
+   SCALAR *tmp = NULL;
+   if (nd > 0) CHK(pb200_malloc(S->dev, sizeof(SCALAR) * (size_t)(N > 0 ? N : 1) * nd * 2, (void **)&tmp));
+   SCALAR *XD = tmp, *RD = tmp ? tmp + (size_t)N * nd : NULL;
    int i = 0, id = 0, io = 0, rc = 0;
    if (n == 0) {
       int c = PB_MIN(no, nd);
       if (c > 0) {
-         rc = pb200_copy_d2d(S->dev, xo, ld, XD, N, N, c, 8);
-         if (!rc) rc = pb200_copy_d2d(S->dev, ro, ld, RD, N, N, c, 8);
-         if (!rc) rc = pb200_copy_d2d(S->dev, XD, N, xd, ld, N, c, 8);
-         if (!rc) rc = pb200_copy_d2d(S->dev, RD, N, rd, ld, N, c, 8);
+         rc = pb200_copy_d2d(S->dev, xo, ld, XD, N, N, c, PB_ES);
+         if (!rc) rc = pb200_copy_d2d(S->dev, ro, ld, RD, N, N, c, PB_ES);
+         if (!rc) rc = pb200_copy_d2d(S->dev, XD, N, xd, ld, N, c, PB_ES);
+         if (!rc) rc = pb200_copy_d2d(S->dev, RD, N, rd, ld, N, c, PB_ES);
       }
       goto done;
    }
    for (i = id = io = 0; (i < n || id < nd) && !rc; id++) {
       if (id < nd && io < no && pd[id] == io) {
-         rc = pb200_copy_d2d(S->dev, xo + (size_t)ld * io, ld, XD + (size_t)N * id, N, N, 1, 8);
-         if (!rc) rc = pb200_copy_d2d(S->dev, ro + (size_t)ld * io, ld, RD + (size_t)N * id, N, N, 1, 8);
+         rc = pb200_copy_d2d(S->dev, xo + (size_t)ld * io, ld, XD + (size_t)N * id, N, N, 1, PB_ES);
+         if (!rc) rc = pb200_copy_d2d(S->dev, ro + (size_t)ld * io, ld, RD + (size_t)N * id, N, N, 1, PB_ES);
          io++;
       } else {
          if (id < nd && i < n) {
-            double alpha = -evals[p[i]];
-            rc = pb200_copy_d2d(S->dev, x + (size_t)ld * p[i], ld, XD + (size_t)N * id, N, N, 1, 8);
-            if (!rc) rc = pb200_copy_d2d(S->dev, Ax + (size_t)ld * p[i], ld, RD + (size_t)N * id, N, N, 1, 8);
+            SCALAR alpha = -evals[p[i]];
+            rc = pb200_copy_d2d(S->dev, x + (size_t)ld * p[i], ld, XD + (size_t)N * id, N, N, 1, PB_ES);
+            if (!rc) rc = pb200_copy_d2d(S->dev, Ax + (size_t)ld * p[i], ld, RD + (size_t)N * id, N, N, 1, PB_ES);
             if (!rc) rc = pb200_daxpy_columns(S->dev, N, &alpha, x + (size_t)ld * p[i], ld, RD + (size_t)N * id, N, 1);
          }
          i++;
@@ -337,12 +339,12 @@ static int residual_columns(pb_solver *S, const double *evals, double *x, int n,
    /* compaction of the failed pairs to the front (p is increasing: forward copies are safe) */
    for (i = 0; i < n && !rc; i++) {
       if (p[i] == i) continue;
-      rc = pb200_copy_d2d(S->dev, x + (size_t)ld * p[i], ld, x + (size_t)ld * i, ld, N, 1, 8);
-      if (!rc) rc = pb200_copy_d2d(S->dev, Ax + (size_t)ld * p[i], ld, Ax + (size_t)ld * i, ld, N, 1, 8);
+      rc = pb200_copy_d2d(S->dev, x + (size_t)ld * p[i], ld, x + (size_t)ld * i, ld, N, 1, PB_ES);
+      if (!rc) rc = pb200_copy_d2d(S->dev, Ax + (size_t)ld * p[i], ld, Ax + (size_t)ld * i, ld, N, 1, PB_ES);
    }
    if (!rc && nd > 0) {
-      rc = pb200_copy_d2d(S->dev, XD, N, xd, ld, N, nd, 8);
-      if (!rc) rc = pb200_copy_d2d(S->dev, RD, N, rd, ld, N, nd, 8);
+      rc = pb200_copy_d2d(S->dev, XD, N, xd, ld, N, nd, PB_ES);
+      if (!rc) rc = pb200_copy_d2d(S->dev, RD, N, rd, ld, N, nd, PB_ES);
    }
 done:
    if (tmp) pb200_free(S->dev, tmp);
@@ -381,12 +383,12 @@ static int restart_locking(pb_solver *S, int *restartSize, int basisSize, int *r
       }
    }
    *restartSize = left + numPacked;
-   hl_permute_cols(hVals, 1, basisSize, 1, restartPerm);
+   hl_permute_reals(hVals, basisSize, restartPerm);
    hl_permute_cols(S->hVecs, basisSize, basisSize, ldh, restartPerm);
 
    double *lockedResNorms = &resNorms[*numLocked];
-   double *X = S->V + (size_t)S->ld * *restartSize;
-   double *R = S->W + (size_t)S->ld * *restartSize;
+   SCALAR *X = S->V + (size_t)S->ld * *restartSize;
+   SCALAR *R = S->W + (size_t)S->ld * *restartSize;
    int rc = aux_update_VWXR(S, basisSize, *restartSize, *restartSize, X, 0, sizeBlockNorms,
          *numLocked + primme->numOrthoConst, left, left + numPacked, R, blockNorms,
          lockedResNorms, left, *restartSize, primme->orth == primme_orth_explicit_I);
@@ -442,13 +444,13 @@ static int restart_locking(pb_solver *S, int *restartSize, int basisSize, int *r
    /* same rearrangement on the small matrices */
    {
       /* compact hVecs(:,left+ifailed) and hVals to the front of the packed range */
-      double *tmp = (double *)malloc(sizeof(double) * (size_t)basisSize * (failed > 0 ? failed : 1));
+      SCALAR *tmp = (SCALAR *)malloc(sizeof(SCALAR) * (size_t)basisSize * (failed > 0 ? failed : 1));
       for (i = 0; i < failed; i++)
-         memcpy(tmp + (size_t)basisSize * i, &S->hVecs[(size_t)ldh * (left + ifailed[i])], sizeof(double) * basisSize);
+         memcpy(tmp + (size_t)basisSize * i, &S->hVecs[(size_t)ldh * (left + ifailed[i])], sizeof(SCALAR) * basisSize);
       for (i = 0; i < failed; i++)
-         memcpy(&S->hVecs[(size_t)ldh * (left + i)], tmp + (size_t)basisSize * i, sizeof(double) * basisSize);
+         memcpy(&S->hVecs[(size_t)ldh * (left + i)], tmp + (size_t)basisSize * i, sizeof(SCALAR) * basisSize);
       for (i = 0; i < failed; i++) tmp[i] = hVals[left + ifailed[i]];
-      for (i = 0; i < failed; i++) hVals[left + i] = tmp[i];
+      for (i = 0; i < failed; i++) hVals[left + i] = PB_REAL(tmp[i]);
       free(tmp);
       hl_permute_ints(&restartPerm[left], numPacked, ifailed);
    }
@@ -462,9 +464,9 @@ static int restart_locking(pb_solver *S, int *restartSize, int basisSize, int *r
       for (i = 0; i < left; i++) iV[i + numPacked - failed] = i;
       for (i = 0; i < failed; i++) iV[i + left + numPacked - failed] = ifailed[i] + left;
       /* the sweep wrote only the upper triangle's worth reliably? G is written full: use it */
-      double *rw = (double *)malloc(sizeof(double) * (size_t)nG * (nc > 0 ? nc : 1));
+      SCALAR *rw = (SCALAR *)malloc(sizeof(SCALAR) * (size_t)nG * (nc > 0 ? nc : 1));
       for (i = 0; i < nc; i++)
-         memcpy(rw + (size_t)nG * i, &S->VtBV[(size_t)ldG * (nLocked + iV[i])], sizeof(double) * nG);
+         memcpy(rw + (size_t)nG * i, &S->VtBV[(size_t)ldG * (nLocked + iV[i])], sizeof(SCALAR) * nG);
       hl_copy(rw, nLocked, nc, nG, &S->VtBV[(size_t)ldG * nLocked], ldG);
       for (j = 0; j < nc; j++)
          for (i = 0; i < nc; i++)
@@ -474,11 +476,11 @@ static int restart_locking(pb_solver *S, int *restartSize, int basisSize, int *r
    if (primme->orth == primme_orth_explicit_I) {
       /* H: failed pairs move right after the kept ones (:1114-1119) */
       const int ldH = S->maxBasis;
-      double *rw = (double *)malloc(sizeof(double) * (size_t)(left + numPacked) * (failed > 0 ? failed : 1));
+      SCALAR *rw = (SCALAR *)malloc(sizeof(SCALAR) * (size_t)(left + numPacked) * (failed > 0 ? failed : 1));
       for (i = 0; i < failed; i++)
-         memcpy(rw + (size_t)(left + numPacked) * i, &S->H[(size_t)ldH * (left + ifailed[i])], sizeof(double) * (left + numPacked));
+         memcpy(rw + (size_t)(left + numPacked) * i, &S->H[(size_t)ldH * (left + ifailed[i])], sizeof(SCALAR) * (left + numPacked));
       for (i = 0; i < failed; i++)
-         memcpy(&S->H[(size_t)ldH * (left + i)], rw + (size_t)(left + numPacked) * i, sizeof(double) * (left + numPacked));
+         memcpy(&S->H[(size_t)ldH * (left + i)], rw + (size_t)(left + numPacked) * i, sizeof(SCALAR) * (left + numPacked));
       /* rows */
       for (j = 0; j < left + failed; j++) {
          for (i = 0; i < failed; i++) rw[i] = S->H[(size_t)ldH * j + left + ifailed[i]];
@@ -496,7 +498,7 @@ static int restart_locking(pb_solver *S, int *restartSize, int basisSize, int *r
          int dst = *numLocked + primme->numOrthoConst;
          if (src != dst)
             CHKX(pb200_copy_d2d(S->dev, S->evecs + (size_t)S->ldevecs * src, S->ldevecs,
-                  S->evecs + (size_t)S->ldevecs * dst, S->ldevecs, S->n, 1, 8), free(ifailed));
+                  S->evecs + (size_t)S->ldevecs * dst, S->ldevecs, S->n, 1, PB_ES), free(ifailed));
          (*numLocked)++;
          if (S->lockedFlags) S->lockedFlags[*numLocked - 1] = flags[i];
          CHKX(pb_monitor(S, NULL, 0, NULL, NULL, 0, NULL, 0, evals, *numLocked, S->lockedFlags,
@@ -520,10 +522,10 @@ static int restart_locking(pb_solver *S, int *restartSize, int basisSize, int *r
 /* ------------------------------------------------------------------------------------------
  * Projected matrices after the restart (restart.c:1614-1735, RR only)
  * ---------------------------------------------------------------------------------------- */
-int pb_compute_submatrix(const double *X, int nX, int ldX, const double *H, int nH, int ldH,
-      double *R, int ldR) {
+int pb_compute_submatrix(const SCALAR *X, int nX, int ldX, const SCALAR *H, int nH, int ldH,
+      SCALAR *R, int ldR) {
    if (nH == 0 || nX == 0) return 0;
-   double *rw = (double *)calloc((size_t)nH * nX, sizeof(double));
+   SCALAR *rw = (SCALAR *)calloc((size_t)nH * nX, sizeof(SCALAR));
    hl_symm_lu(nH, nX, 1.0, H, ldH, X, ldX, 0.0, rw, nH);
    hl_gemm('C', 'N', nX, nX, nH, 1.0, X, ldX, rw, nH, 0.0, R, ldR);
    free(rw);
@@ -534,13 +536,14 @@ static int restart_RR(pb_solver *S, int restartSize, int basisSize, int numConve
       int numPrevRetained, int indexOfPreviousVecs, const int *hVecsPerm, int *targetShiftIndex) {
    primme_params *primme = S->primme;
    const int ldH = S->maxBasis, ldh = S->maxBasis, ldG = S->maxRank;
-   double *H = S->H, *hVecs = S->hVecs, *hVals = S->hVals;
+   SCALAR *H = S->H, *hVecs = S->hVecs;
+   double *hVals = S->hVals;
    double aNorm = PB_MAX(primme->aNorm, primme->stats.estimateLargestSVal);
    int i, j;
 
    if (primme->orth == primme_orth_implicit_I) {
       /* H = diag(hVals) except the block of the retained directions (:1636-1664) */
-      double *sub = (double *)calloc((size_t)(numPrevRetained > 0 ? numPrevRetained : 1) * (numPrevRetained > 0 ? numPrevRetained : 1), sizeof(double));
+      SCALAR *sub = (SCALAR *)calloc((size_t)(numPrevRetained > 0 ? numPrevRetained : 1) * (numPrevRetained > 0 ? numPrevRetained : 1), sizeof(SCALAR));
       pb_compute_submatrix(&hVecs[(size_t)ldh * indexOfPreviousVecs], numPrevRetained, ldh, H,
             basisSize, ldH, sub, numPrevRetained > 0 ? numPrevRetained : 1);
       hl_zero(H, restartSize, restartSize, ldH);
@@ -579,12 +582,12 @@ static int restart_RR(pb_solver *S, int restartSize, int basisSize, int numConve
       for (i = 0; i < restartSize; i++) hVecs[(size_t)ldh * j + i] = 0.0;
       hVecs[(size_t)ldh * j + hVecsPerm[j]] = 1.0;
    }
-   hl_permute_cols(hVals, 1, restartSize, 1, hVecsPerm);
+   hl_permute_reals(hVals, restartSize, hVecsPerm);
 
    if (numPrevRetained > 0) {
       /* small eigenproblem of the retained block; note the output goes to a shifted window
        * of hVecs, so solve into a scratch matrix first */
-      double *sub = (double *)malloc(sizeof(double) * numPrevRetained * numPrevRetained);
+      SCALAR *sub = (SCALAR *)malloc(sizeof(SCALAR) * numPrevRetained * numPrevRetained);
       double *w = (double *)malloc(sizeof(double) * numPrevRetained);
       int rc = pb_solve_H(S, &H[(size_t)ldH * indexOfPreviousVecs + indexOfPreviousVecs], ldH,
             numPrevRetained,
@@ -671,11 +674,11 @@ int pb_restart(pb_solver *S, int basisSize, int *ievSize, double *evals, double 
       double *prv = S->prevRitzVals;
       if (S->numPrevRitzVals > 0) {
          for (i = S->numPrevRitzVals; i < basisSize; i++) prv[i] = prv[S->numPrevRitzVals - 1];
-         hl_permute_cols(prv, 1, basisSize, 1, restartPerm);
+         hl_permute_reals(prv, basisSize, restartPerm);
       }
       for (i = 0; i < restartSize; i++)
          if (restartPerm[i] >= S->numPrevRitzVals) prv[i] = S->hVals[i];
-      hl_permute_cols(prv, 1, restartSize, 1, hVecsPerm);
+      hl_permute_reals(prv, restartSize, hVecsPerm);
       S->numPrevRitzVals = restartSize;
    }
 
@@ -705,8 +708,8 @@ int pb_restart(pb_solver *S, int basisSize, int *ievSize, double *evals, double 
       const int ldG = S->maxRank, nG = primme->numOrthoConst + *numLocked + restartSize;
       for (i = 0; i < nG; i++)
          for (int j = 0; j < i; j++) {
-            double g = S->VtBV[(size_t)i * ldG + j];
-            acc += 2 * g * g / fabs(S->VtBV[(size_t)i * ldG + i]) / fabs(S->VtBV[(size_t)j * ldG + j]);
+            SCALAR g = S->VtBV[(size_t)i * ldG + j];
+            acc += 2 * PB_REAL(PB_CONJ(g) * g) / PB_ABS(S->VtBV[(size_t)i * ldG + i]) / PB_ABS(S->VtBV[(size_t)j * ldG + j]);
          }
       fn = sqrt(acc);
    }

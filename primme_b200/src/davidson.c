@@ -21,6 +21,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* sums over the processes are still to be done on the host (no multi-rank kernel context) */
+#define primme_numProcs_gt1(S) ((S)->primme->numProcs > 1 && pb200_ctx_nranks((S)->dev) <= 1)
 #define VtBV_BLK(S, off) ((S)->VtBV ? &(S)->VtBV[(size_t)(S)->maxRank * (off) + (off)] : NULL)
 
 /* solve_H (solve_projection.c:95-154): Rayleigh-Ritz pairs of (H, V'V) or the refined vectors from R */
@@ -50,7 +52,7 @@ static int init_block_krylov(pb_solver *S, int dv1, int dv2, int numLocked) {
       /* next Krylov block: A*V(:,i-bs:...) lands in V(:,i:...), and is also W(:,i-bs:...) */
       CHK(pb_apply_matvec(S, S->V + (size_t)S->ld * (i - bs), S->ld, S->V + (size_t)S->ld * i, S->ld, mm));
       CHK(pb200_copy_d2d(S->dev, S->V + (size_t)S->ld * i, S->ld, S->W + (size_t)S->ld * (i - bs),
-            S->ld, S->n, mm, 8));
+            S->ld, S->n, mm, PB_ES));
       CHK(pb_ortho_block(S, S->V, S->ld, i, i + mm - 1, S->evecs, S->ldevecs, numLocked, NULL, 0, &nV));
       if (nV < i + mm) {
          CHK(pb_fill_random(S, S->V + (size_t)S->ld * nV, S->ld, i + mm - nV));
@@ -83,7 +85,7 @@ static int init_basis(pb_solver *S, int *basisSize, int *nextGuess, int *numGues
    *numGuesses = primme->initSize - initSize;
    *nextGuess = primme->numOrthoConst + initSize;
    CHK(pb200_copy_d2d(S->dev, S->evecs + (size_t)S->ldevecs * primme->numOrthoConst, S->ldevecs,
-         S->V, S->ld, S->n, initSize, 8));
+         S->V, S->ld, S->n, initSize, PB_ES));
 
    switch (primme->initBasisMode) {
    case primme_init_krylov: random = 0; break;
@@ -116,16 +118,16 @@ static int init_basis(pb_solver *S, int *basisSize, int *nextGuess, int *numGues
 /* ------------------------------------------------------------------------------------------
  * One candidates sweep: X = V*h, R = W*h - X*diag(theta), norms (main_iter.c:1656-1688)
  * ---------------------------------------------------------------------------------------- */
-static int candidates_sweep(pb_solver *S, int basisSize, const double *hblk, const double *theta,
-      int nb, double *X, double *R, int computeXR, double *norms) {
+static int candidates_sweep(pb_solver *S, int basisSize, const SCALAR *hblk, const double *theta,
+      int nb, SCALAR *X, SCALAR *R, int computeXR, double *norms) {
    primme_params *primme = S->primme;
    const double t0 = hl_wtime();
    pb200_vwxr_out o;
    memset(&o, 0, sizeof(o));
    int fused = 0;
    if (computeXR) {
-      o.X[0].ptr = X, o.X[0].ld = S->ld, o.X[0].cb = 0, o.X[0].ce = nb;
-      o.R.ptr = R, o.R.ld = S->ld, o.R.cb = 0, o.R.ce = nb;
+      o.X[0].ptr = PB_DP(X), o.X[0].ld = S->ld, o.X[0].cb = 0, o.X[0].ce = nb;
+      o.R.ptr = PB_DP(R), o.R.ld = S->ld, o.R.cb = 0, o.R.ce = nb;
       o.Rnorms_host = norms;
       /* the residual block becomes the new basis block unchanged (no preconditioner, no locked
        * vectors): the same sweep delivers the first Gram panel of its orthogonalisation */
@@ -133,11 +135,11 @@ static int candidates_sweep(pb_solver *S, int basisSize, const double *hblk, con
       S->fuse_sweeps++;
       if (S->fuse_enabled && X == S->V + (size_t)S->ld * basisSize &&
             pb200_dvwxr_can_fuse_gram(S->dev, S->n, S->V, S->W, basisSize, S->ld, nb, &o)) {
-         o.P_host = S->fusedP, o.ldP = S->maxBasis + 8;
+         o.P_host = PB_DP(S->fusedP), o.ldP = S->maxBasis + 8;
          /* the residuals go straight into the basis tail as well (the Ritz vectors are not needed
           * by this correction): no copy kernel in solve_correction */
          o.X[0].ptr = NULL;
-         o.R2 = X, o.ldR2 = S->ld;
+         o.R2 = PB_DP(X), o.ldR2 = S->ld;
          fused = 1;
       }
    } else {
@@ -162,7 +164,7 @@ static int candidates_sweep(pb_solver *S, int basisSize, const double *hblk, con
  * prepare_candidates (main_iter.c:1470-1709): fill the block with the first unconverged Ritz
  * pairs, computing residuals as needed.
  * ---------------------------------------------------------------------------------------- */
-static int prepare_candidates(pb_solver *S, int basisSize, double *X, double *R, int computeXR,
+static int prepare_candidates(pb_solver *S, int basisSize, SCALAR *X, SCALAR *R, int computeXR,
       int remainedEvals, int blockNormsSize, int maxBlockSize, int numLocked, double *evals,
       double *resNorms, int targetShiftIndex, int *blockSize, int *recentlyConverged,
       double *smallestResNorm, int numConverged, int *reset, int nprevhVecs,
@@ -176,7 +178,7 @@ static int prepare_candidates(pb_solver *S, int basisSize, double *X, double *R,
 
    *blockSize = 0;
    double *hValsBlock = (double *)malloc(sizeof(double) * (maxBlockSize > 0 ? maxBlockSize : 1));
-   double *hVecsBlock = (double *)malloc(sizeof(double) * (size_t)ldh * (maxBlockSize > 0 ? maxBlockSize : 1));
+   SCALAR *hVecsBlock = (SCALAR *)malloc(sizeof(SCALAR) * (size_t)ldh * (maxBlockSize > 0 ? maxBlockSize : 1));
    int *flagsBlock = (int *)malloc(sizeof(int) * (maxBlockSize > 0 ? maxBlockSize : 1));
 
    for (i = 0; i < blockNormsSize; i++) hValsBlock[i] = hVals[iev[*blockSize + i]];
@@ -230,10 +232,10 @@ static int prepare_candidates(pb_solver *S, int basisSize, double *X, double *R,
             iev[*blockSize] = iev[blki];
             if (computeXR && blki != *blockSize) {
                rc = pb200_copy_d2d(S->dev, X + (size_t)S->ld * blki, S->ld,
-                     X + (size_t)S->ld * *blockSize, S->ld, S->n, 1, 8);
+                     X + (size_t)S->ld * *blockSize, S->ld, S->n, 1, PB_ES);
                if (!rc)
                   rc = pb200_copy_d2d(S->dev, R + (size_t)S->ld * blki, S->ld,
-                        R + (size_t)S->ld * *blockSize, S->ld, S->n, 1, 8);
+                        R + (size_t)S->ld * *blockSize, S->ld, S->n, 1, PB_ES);
                if (rc) goto done;
             }
             (*blockSize)++;
@@ -255,7 +257,7 @@ static int prepare_candidates(pb_solver *S, int basisSize, double *X, double *R,
       for (i = 0; i < blockNormsSize; i++) {
          hValsBlock[i] = hVals[iev[*blockSize + i]];
          memcpy(&hVecsBlock[(size_t)ldh * i], &S->hVecs[(size_t)ldh * iev[*blockSize + i]],
-               sizeof(double) * basisSize);
+               sizeof(SCALAR) * basisSize);
       }
       rc = candidates_sweep(S, basisSize, hVecsBlock, hValsBlock, blockNormsSize,
             X ? X + (size_t)S->ld * *blockSize : NULL, R ? R + (size_t)S->ld * *blockSize : NULL,
@@ -391,21 +393,21 @@ static int solve_correction(pb_solver *S, double *evals, int numLocked, int basi
 
    primme->ShiftsForPreconditioner = shifts;
 
-   double *r = S->W + (size_t)S->ld * basisSize; /* block residuals */
-   double *x = S->V + (size_t)S->ld * basisSize; /* block Ritz vectors, receives the corrections */
+   SCALAR *r = S->W + (size_t)S->ld * basisSize; /* block residuals */
+   SCALAR *x = S->V + (size_t)S->ld * basisSize; /* block Ritz vectors, receives the corrections */
    if (cp->maxInnerIterations != 0) {
       /* inner-outer JDQMR (correction.c:385-447, setup_JD_projectors :862-999 for the presets
        * without right projectors): Q = [constraints locked] when LeftQ; the Ritz vector joins Q
        * when the block is a single vector, else every system is projected against its own x_i */
       const int sizeEvecs = primme->numOrthoConst + (primme->locking ? numLocked : 0);
-      const double *Q = NULL;
+      const SCALAR *Q = NULL;
       int nQ = 0, useX = 0;
       if (cp->projectors.LeftQ) {
          nQ = sizeEvecs, Q = S->evecs;
          if (cp->projectors.LeftX) {
             if (blockSize <= 1) {
                rc = pb200_copy_d2d(S->dev, x, S->ld, S->evecs + (size_t)S->ldevecs * sizeEvecs, S->ldevecs, S->n,
-                     blockSize, 8);
+                     blockSize, PB_ES);
                nQ += blockSize;
             } else
                useX = 1;
@@ -413,16 +415,16 @@ static int solve_correction(pb_solver *S, double *evals, int numLocked, int basi
       } else if (cp->projectors.LeftX)
          useX = 1;
       if (!rc && !S->jd_work)
-         rc = pb200_malloc(S->dev, sizeof(double) * (size_t)S->ld * 5 * PB_MAX(primme->maxBlockSize, 1),
+         rc = pb200_malloc(S->dev, sizeof(SCALAR) * (size_t)S->ld * 5 * PB_MAX(primme->maxBlockSize, 1),
                (void **)&S->jd_work);
       /* right projectors (:942-980): the locked vectors, and x or K^{-1}x with x'K^{-1}x */
-      const double *RQ = NULL;
-      double *RX = NULL, *KinvX = NULL, xKinvBx[8];
+      const SCALAR *RQ = NULL;
+      SCALAR *RX = NULL, *KinvX = NULL, xKinvBx[8];
       int nRQ = 0;
       if (cp->projectors.RightQ) RQ = S->evecs, nRQ = sizeEvecs;
       if (!rc && cp->projectors.RightX) {
          if (cp->precondition && cp->projectors.SkewX) {
-            rc = pb200_malloc(S->dev, sizeof(double) * (size_t)S->ld * blockSize, (void **)&KinvX);
+            rc = pb200_malloc(S->dev, sizeof(SCALAR) * (size_t)S->ld * blockSize, (void **)&KinvX);
             if (!rc) rc = pb_apply_precond(S, x, S->ld, KinvX, S->ld, blockSize);
             if (!rc) rc = pb200_dcolumn_dots(S->dev, S->n, x, S->ld, KinvX, S->ld, blockSize, xKinvBx);
             if (!rc) rc = pb_reduce_panel(S, xKinvBx, blockSize, 1, blockSize);
@@ -435,30 +437,30 @@ static int solve_correction(pb_solver *S, double *evals, int numLocked, int basi
       if (!rc) {
          double blockRitzVals[8];
          for (int b = 0; b < blockSize; b++) blockRitzVals[b] = ritzVals[iev[b]];
-         double *sol = S->jd_work + (size_t)S->ld * 4 * PB_MAX(primme->maxBlockSize, 1);
+         SCALAR *sol = S->jd_work + (size_t)S->ld * 4 * PB_MAX(primme->maxBlockSize, 1);
          int touch1 = S->touch;
          rc = pb_inner_solve(S, blockSize, x, S->ld, r, S->ld, blockNorms, Q, S->ldevecs, nQ, useX, sol, S->ld,
                blockRitzVals, shifts, &touch1, S->jd_work, RQ, S->ldevecs, nRQ, RX, S->ld, xKinvBx);
          S->touch = PB_MAX(S->touch, touch1);
-         if (!rc) rc = pb200_copy_d2d(S->dev, sol, S->ld, x, S->ld, S->n, blockSize, 8);
+         if (!rc) rc = pb200_copy_d2d(S->dev, sol, S->ld, x, S->ld, S->n, blockSize, PB_ES);
       }
       if (KinvX) pb200_free(S->dev, KinvX);
    } else if (cp->projectors.RightX && cp->projectors.SkewX) {
       /* exact Olsen projector (correction.c:695-774): x <- K^{-1}r - (x'K^{-1}r / x'K^{-1}x) K^{-1}x */
-      double *tmp = NULL;
-      rc = pb200_malloc(S->dev, sizeof(double) * (size_t)S->ld * blockSize * 2, (void **)&tmp);
+      SCALAR *tmp = NULL;
+      rc = pb200_malloc(S->dev, sizeof(SCALAR) * (size_t)S->ld * blockSize * 2, (void **)&tmp);
       if (!rc) {
-         double *Kx = tmp, *Kr = tmp + (size_t)S->ld * blockSize;
-         double *xKx = (double *)malloc(sizeof(double) * 2 * blockSize), *xKr = xKx + blockSize;
+         SCALAR *Kx = tmp, *Kr = tmp + (size_t)S->ld * blockSize;
+         SCALAR *xKx = (SCALAR *)malloc(sizeof(SCALAR) * 2 * blockSize), *xKr = xKx + blockSize;
          rc = pb_apply_precond(S, x, S->ld, Kx, S->ld, blockSize);
          if (!rc) rc = pb_apply_precond(S, r, S->ld, Kr, S->ld, blockSize);
          if (!rc) rc = pb200_dcolumn_dots(S->dev, S->n, x, S->ld, Kx, S->ld, blockSize, xKx);
          if (!rc) rc = pb_reduce_panel(S, xKx, blockSize, 1, blockSize);
          if (!rc) rc = pb200_dcolumn_dots(S->dev, S->n, x, S->ld, Kr, S->ld, blockSize, xKr);
          if (!rc) rc = pb_reduce_panel(S, xKr, blockSize, 1, blockSize);
-         if (!rc) rc = pb200_copy_d2d(S->dev, Kr, S->ld, x, S->ld, S->n, blockSize, 8);
+         if (!rc) rc = pb200_copy_d2d(S->dev, Kr, S->ld, x, S->ld, S->n, blockSize, PB_ES);
          if (!rc) {
-            for (int b = 0; b < blockSize; b++) xKr[b] = fabs(xKx[b]) > 0.0 ? -xKr[b] / xKx[b] : 0.0;
+            for (int b = 0; b < blockSize; b++) xKr[b] = PB_ABS(xKx[b]) > 0.0 ? -xKr[b] / xKx[b] : 0.0;
             rc = pb200_daxpy_columns(S->dev, S->n, xKr, Kx, S->ld, x, S->ld, blockSize);
          }
          free(xKx);
@@ -469,8 +471,9 @@ static int solve_correction(pb_solver *S, double *evals, int numLocked, int basi
       if (cp->projectors.RightX &&
             ((cp->precondition && primme->applyPreconditioner) ||
                   (primme->locking && primme->orth == primme_orth_implicit_I))) {
-         for (int b = 0; b < blockSize; b++) olsenEps[b] = -olsenEps[b];
-         rc = pb200_daxpy_columns(S->dev, S->n, olsenEps, x, S->ld, r, S->ld, blockSize);
+         SCALAR negEps[8];
+         for (int b = 0; b < blockSize; b++) negEps[b] = olsenEps[b] = -olsenEps[b];
+         rc = pb200_daxpy_columns(S->dev, S->n, negEps, x, S->ld, r, S->ld, blockSize);
       }
       if (!rc && !(S->fusedP_nb == blockSize && blockSize > 0 && !cp->precondition))
          rc = pb_apply_precond(S, r, S->ld, x, S->ld, blockSize);
@@ -487,7 +490,7 @@ static int solve_correction(pb_solver *S, double *evals, int numLocked, int basi
  * ---------------------------------------------------------------------------------------- */
 static int verify_norms(pb_solver *S, int nv, double *resNorms, int *numConverged) {
    CHK(pb200_dresidual_inplace(S->dev, S->n, S->hVals, S->V, S->ld, S->W, S->ld, nv, resNorms));
-   CHK(pb_reduce_panel(S, resNorms, nv, 1, nv));
+   if (primme_numProcs_gt1(S)) CHK(pb_global_sum(S, resNorms, nv));
    for (int i = 0; i < nv; i++) resNorms[i] = sqrt(resNorms[i]);
    CHK(pb_check_convergence(S, S->V, S->ld, 1, S->W, S->ld, 1, 0, 0, nv, S->flags, resNorms,
          S->hVals, NULL, 0));
@@ -505,14 +508,14 @@ static int copy_back_candidates(pb_solver *S, int basisSize, double *evals, doub
    primme_params *primme = S->primme;
    *numRet = numConverged; /* the locked vectors already sit in evecs: the host contract copies them back */
    if (numConverged >= primme->numEvals || basisSize <= 0) return 0;
-   double *ev = S->evecs + (size_t)S->ldevecs * primme->numOrthoConst;
+   SCALAR *ev = S->evecs + (size_t)S->ldevecs * primme->numOrthoConst;
    int i = 0;
    while (i < basisSize && numConverged < primme->numEvals) {
       int bs = PB_MAX(0, PB_MIN(primme->numEvals - numConverged, basisSize - i));
-      bs = PB_MIN(bs, 8);
+      bs = PB_MIN(bs, PB_ES);
       pb200_vwxr_out o;
       memset(&o, 0, sizeof(o));
-      o.X[0].ptr = ev + (size_t)S->ldevecs * numConverged, o.X[0].ld = S->ldevecs, o.X[0].cb = 0, o.X[0].ce = bs;
+      o.X[0].ptr = PB_DP(ev + (size_t)S->ldevecs * numConverged), o.X[0].ld = S->ldevecs, o.X[0].cb = 0, o.X[0].ce = bs;
       o.rb = 0, o.re = bs, o.rnorms_host = &resNorms[numConverged];
       CHK(pb200_dvwxr(S->dev, S->n, S->V, S->W, basisSize, S->ld, &S->hVecs[(size_t)S->maxBasis * i],
             S->maxBasis, bs, &S->hVals[i], &o));
@@ -533,7 +536,7 @@ static int copy_back_candidates(pb_solver *S, int basisSize, double *evals, doub
          resNorms[numConverged] = rn;
          if (numConverged != numConverged0 + blki)
             CHK(pb200_copy_d2d(S->dev, ev + (size_t)S->ldevecs * (numConverged0 + blki), S->ldevecs,
-                  ev + (size_t)S->ldevecs * numConverged, S->ldevecs, S->n, 1, 8));
+                  ev + (size_t)S->ldevecs * numConverged, S->ldevecs, S->n, 1, PB_ES));
          numConverged++;
       }
    }
@@ -717,11 +720,11 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
 
             /* with locking, GD and no preconditioner the practical convergence of the block is
              * judged after orthogonalisation from V_locked' r (main_iter.c:674-797) */
-            double *Rlocked = NULL;
+            SCALAR *Rlocked = NULL;
             const int ldRlocked = primme->numOrthoConst + numLocked;
             const int blockSize0 = blockSize;
             if (gdNoPrecLocking)
-               Rlocked = (double *)calloc((size_t)(ldRlocked > 0 ? ldRlocked : 1) * (blockSize > 0 ? blockSize : 1), sizeof(double));
+               Rlocked = (SCALAR *)calloc((size_t)(ldRlocked > 0 ? ldRlocked : 1) * (blockSize > 0 ? blockSize : 1), sizeof(SCALAR));
 
             for (i = 0; i < maxNumRandoms; i++) {
                int basisSizeOut;
@@ -751,14 +754,14 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
                      double normXx = 0.0;
                      if (primme->orth == primme_orth_explicit_I) {
                         /* Xx = VtBV(0:numLocked, numLocked: ) * hVecs(:,iev[i]) */
-                        double *Xx = (double *)calloc(numLocked, sizeof(double));
+                        SCALAR *Xx = (SCALAR *)calloc(numLocked, sizeof(SCALAR));
                         hl_gemm('N', 'N', numLocked, 1, basisSize, 1.0,
                               &S->VtBV[(size_t)S->maxRank * numLocked], S->maxRank,
                               &S->hVecs[(size_t)ldh * iev[i]], ldh, 0.0, Xx, numLocked);
-                        normXx = fabs(hl_dot(numLocked, Xx, Xx));
+                        normXx = PB_ABS(hl_dot(numLocked, Xx, Xx));
                         free(Xx);
                      }
-                     double normR = fabs(hl_dot(ldRlocked, &Rlocked[(size_t)ldRlocked * i],
+                     double normR = PB_ABS(hl_dot(ldRlocked, &Rlocked[(size_t)ldRlocked * i],
                            &Rlocked[(size_t)ldRlocked * i]));
                      double bn = S->blockNorms[i];
                      double newBlockNorm = sqrt(PB_MAX(bn * bn - normR * (1. + normXx), 0.0));
@@ -881,7 +884,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
                   else
                      iwork[numConverged - numLocked + blockSize + l++] = i;
                }
-               hl_permute_cols(S->hVals, 1, basisSize, 1, iwork);
+               hl_permute_reals(S->hVals, basisSize, iwork);
                hl_permute_cols(S->hVecs, basisSize, basisSize, ldh, iwork);
                hl_permute_ints(flags, basisSize, iwork);
                if (S->hVecsRot) {
@@ -922,7 +925,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
                numNew = cap > 0 ? (int)cap : 0;
             }
             CHK(pb200_copy_d2d(S->dev, S->evecs + (size_t)S->ldevecs * nextGuess, S->ldevecs,
-                  S->V + (size_t)S->ld * basisSize, S->ld, S->n, numNew, 8));
+                  S->V + (size_t)S->ld * basisSize, S->ld, S->n, numNew, PB_ES));
             nextGuess += numNew;
             numGuesses -= numNew;
             int basisSizeOut;
@@ -978,7 +981,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
          }
          CHK(pb200_copy_d2d(S->dev, S->V, S->ld,
                S->evecs + (size_t)S->ldevecs * primme->numOrthoConst, S->ldevecs, S->n,
-               primme->numEvals, 8));
+               primme->numEvals, PB_ES));
          *numRet = primme->numEvals;
          primme->initSize = numConverged;
          pb_dyn_recommend(primme, &S->cost);

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifndef PB_COMPLEX /* untyped helpers: defined once */
 void pb_report(primme_params *primme, const char *file, int line, int err, const char *what) {
    if (getenv("PB200_DEBUG")) fprintf(stderr, "PRIMME-B200: error %d at %s:%d in '%s'\n", err, file, line, what);
    if (primme && primme->procID == 0 && primme->outputFile && primme->printLevel >= 1) {
@@ -33,19 +34,20 @@ double pb_problem_norm(int overrideUserEstimations, primme_params *primme) {
       return primme->aNorm > 0.0 ? primme->aNorm : primme->stats.estimateLargestSVal;
    return PB_MAX(primme->aNorm > 0.0 ? primme->aNorm : 0.0, primme->stats.estimateLargestSVal);
 }
+#endif
 
 /* ------------------------------------------------------------------------- callbacks ---- */
 static int host_block(pb_solver *S, int cols) {
    if (cols <= S->hstage_cols) return 0;
    free(S->hstage), free(S->hstage2);
-   size_t bytes = sizeof(double) * (size_t)(S->n > 0 ? S->n : 1) * cols;
-   S->hstage = (double *)malloc(bytes);
-   S->hstage2 = (double *)malloc(bytes);
+   size_t bytes = sizeof(SCALAR) * (size_t)(S->n > 0 ? S->n : 1) * cols;
+   S->hstage = (SCALAR *)malloc(bytes);
+   S->hstage2 = (SCALAR *)malloc(bytes);
    S->hstage_cols = cols;
    return (S->hstage && S->hstage2) ? 0 : PRIMME_MALLOC_FAILURE;
 }
 
-static int call_block_op(pb_solver *S, primme_block_op_fn fn, double *X, int64_t ldx, double *Y,
+static int call_block_op(pb_solver *S, primme_block_op_fn fn, SCALAR *X, int64_t ldx, SCALAR *Y,
       int64_t ldy, int bs, const char *what) {
    primme_params *primme = S->primme;
    int ierr = 0;
@@ -56,9 +58,9 @@ static int call_block_op(pb_solver *S, primme_block_op_fn fn, double *X, int64_t
       /* host contract: stage the block through host memory */
       CHK(host_block(S, bs));
       PRIMME_INT ln = S->n;
-      CHK(pb200_copy_d2h(S->dev, X, ldx, S->hstage, S->n, S->n, bs, 8));
+      CHK(pb200_copy_d2h(S->dev, X, ldx, S->hstage, S->n, S->n, bs, PB_ES));
       fn(S->hstage, &ln, S->hstage2, &ln, &bs, primme, &ierr);
-      if (!ierr) CHK(pb200_copy_h2d(S->dev, S->hstage2, S->n, Y, ldy, S->n, bs, 8));
+      if (!ierr) CHK(pb200_copy_h2d(S->dev, S->hstage2, S->n, Y, ldy, S->n, bs, PB_ES));
    }
    if (ierr != 0) {
       pb_report(primme, __FILE__, __LINE__, ierr, what);
@@ -67,7 +69,7 @@ static int call_block_op(pb_solver *S, primme_block_op_fn fn, double *X, int64_t
    return 0;
 }
 
-int pb_apply_matvec(pb_solver *S, double *Vblk, int64_t ldv, double *Wblk, int64_t ldw, int bs) {
+int pb_apply_matvec(pb_solver *S, SCALAR *Vblk, int64_t ldv, SCALAR *Wblk, int64_t ldw, int bs) {
    primme_params *primme = S->primme;
    if (bs <= 0) return 0;
    const double t0 = hl_wtime();
@@ -79,7 +81,7 @@ int pb_apply_matvec(pb_solver *S, double *Vblk, int64_t ldv, double *Wblk, int64
    return 0;
 }
 
-int pb_apply_precond(pb_solver *S, double *X, int64_t ldx, double *Y, int64_t ldy, int bs) {
+int pb_apply_precond(pb_solver *S, SCALAR *X, int64_t ldx, SCALAR *Y, int64_t ldy, int bs) {
    primme_params *primme = S->primme;
    if (bs <= 0) return 0;
    const double t0 = hl_wtime();
@@ -87,7 +89,7 @@ int pb_apply_precond(pb_solver *S, double *X, int64_t ldx, double *Y, int64_t ld
       CHK(call_block_op(S, primme->applyPreconditioner, X, ldx, Y, ldy, bs, "applyPreconditioner"));
       primme->stats.numPreconds += bs;
    } else {
-      CHK(pb200_copy_d2d(S->dev, X, ldx, Y, ldy, S->n, bs, 8));
+      CHK(pb200_copy_d2d(S->dev, X, ldx, Y, ldy, S->n, bs, PB_ES));
    }
    primme->stats.timePrecond += hl_wtime() - t0;
    return 0;
@@ -141,7 +143,7 @@ static void conv_test_absolute(double *eval, void *evec, double *rNorm, int *isC
 /* convTestFun_ (auxiliary_eigs_normal.c:408-443): the vector, when the caller has it, is handed to
  * the callback in the memory space of its contract -- as is for cublas_dprimme, through a host copy
  * for dprimme (skipped for the built-in test, which ignores it) */
-int pb_conv_test(pb_solver *S, double eval, const double *evec, double rnorm, int *isconv) {
+int pb_conv_test(pb_solver *S, double eval, const SCALAR *evec, double rnorm, int *isconv) {
    primme_params *primme = S->primme;
    int ierr = 0;
    void *v = (void *)evec;
@@ -149,7 +151,7 @@ int pb_conv_test(pb_solver *S, double eval, const double *evec, double rnorm, in
       v = NULL;
       if (primme->convTestFun != conv_test_absolute) {
          CHK(host_block(S, 1));
-         CHK(pb200_copy_d2h(S->dev, evec, S->n, S->hstage, S->n, S->n, 1, 8));
+         CHK(pb200_copy_d2h(S->dev, evec, S->n, S->hstage, S->n, S->n, 1, PB_ES));
          v = S->hstage;
       }
    }
@@ -183,7 +185,7 @@ int pb_monitor(pb_solver *S, double *basisEvals, int basisSize, int *basisFlags,
 /* Random columns exactly as the reference generates them, even in its GPU builds
  * (cublas_wrapper.c:707-720): LAPACK dlarnv(2) on the host with the evolving primme.iseed,
  * then one upload. */
-int pb_fill_random(pb_solver *S, double *X, int64_t ldx, int ncols) {
+int pb_fill_random(pb_solver *S, SCALAR *X, int64_t ldx, int ncols) {
    primme_params *primme = S->primme;
    if (ncols <= 0) return 0;
    CHK(host_block(S, ncols));
@@ -191,7 +193,7 @@ int pb_fill_random(pb_solver *S, double *X, int64_t ldx, int ncols) {
    for (int i = 0; i < 4; i++) seed[i] = primme->iseed[i];
    for (int j = 0; j < ncols; j++) hl_larnv2(seed, S->n, S->hstage + (size_t)S->n * j);
    for (int i = 0; i < 4; i++) primme->iseed[i] = seed[i];
-   return pb200_copy_h2d(S->dev, S->hstage, S->n, X, ldx, S->n, ncols, 8);
+   return pb200_copy_h2d(S->dev, S->hstage, S->n, X, ldx, S->n, ncols, PB_ES);
 }
 
 /* ------------------------------------------------------------------- default callbacks -- */
@@ -330,6 +332,10 @@ static int check_scope(primme_params *p) {
             p->correctionParams.projectors.RightQ && p->correctionParams.projectors.SkewQ)
       why = "inner QMR iterations with the skew-Q projector and a preconditioner (K^{-1}Q and its factorised Gram matrix)";
    else if (p->maxBlockSize > 8) why = "maxBlockSize > 8";
+#ifdef PB_COMPLEX
+   else if (p->projectionParams.projection != primme_proj_default && p->projectionParams.projection != primme_proj_RR)
+      why = "refined / harmonic extraction in complex arithmetic (Rayleigh-Ritz only)";
+#endif
    if (!why) return 0;
    if (p->outputFile && p->printLevel >= 1 && p->procID == 0)
       fprintf(p->outputFile, "PRIMME-B200: %s is outside the scope of this build\n", why);
@@ -352,7 +358,7 @@ static void free_solver(pb_solver *S, int own_evecs) {
 }
 
 /* The body shared by dprimme and cublas_dprimme (wrapper_Sprimme, primme_c.c:278-422). */
-static int solve_d(double *evals, double *evecs, double *resNorms, primme_params *primme,
+static int solve_typed(double *evals, SCALAR *evecs, double *resNorms, primme_params *primme,
       int device_mode) {
    pb_solver Sv, *S = &Sv;
    memset(S, 0, sizeof(*S));
@@ -434,7 +440,7 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
    const int nevecs = primme->numOrthoConst + PB_MAX(primme->numEvals, primme->initSize);
 
    /* a caller-attached (long-lived) context keeps the basis arrays between solves */
-   const size_t basis_bytes = sizeof(double) * (size_t)PB_MAX(S->ld, 1) * mb;
+   const size_t basis_bytes = sizeof(SCALAR) * (size_t)PB_MAX(S->ld, 1) * mb;
    if (own_ctx) {
       rc = pb200_malloc(S->dev, basis_bytes, (void **)&S->V);
       if (!rc) rc = pb200_malloc(S->dev, basis_bytes, (void **)&S->W);
@@ -449,40 +455,40 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
          S->ldevecs = primme->ldevecs;
       } else {
          S->ldevecs = PB_MAX(S->n, 1);
-         rc = pb200_malloc(S->dev, sizeof(double) * (size_t)S->ldevecs * nevecs, (void **)&S->evecs);
+         rc = pb200_malloc(S->dev, sizeof(SCALAR) * (size_t)S->ldevecs * nevecs, (void **)&S->evecs);
          own_evecs = 1;
          if (!rc && primme->numOrthoConst + primme->initSize > 0)
             rc = pb200_copy_h2d(S->dev, evecs, primme->ldevecs, S->evecs, S->ldevecs, S->n,
-                  primme->numOrthoConst + primme->initSize, 8);
+                  primme->numOrthoConst + primme->initSize, PB_ES);
       }
    }
-   S->H = (double *)calloc((size_t)mb * mb, sizeof(double));
-   S->hVecs = (double *)calloc((size_t)mb * mb, sizeof(double));
-   S->prevhVecs = (double *)calloc((size_t)mb * mb, sizeof(double));
-   S->fusedP = (double *)calloc((size_t)(mb + 8) * 8, sizeof(double));
+   S->H = (SCALAR *)calloc((size_t)mb * mb, sizeof(SCALAR));
+   S->hVecs = (SCALAR *)calloc((size_t)mb * mb, sizeof(SCALAR));
+   S->prevhVecs = (SCALAR *)calloc((size_t)mb * mb, sizeof(SCALAR));
+   S->fusedP = (SCALAR *)calloc((size_t)(mb + 8) * 8, sizeof(SCALAR));
    /* the fused candidates sweep leaves residuals, not Ritz vectors, in the block: only the
     * built-in test (which ignores evec) may run on it */
    S->fuse_allowed = (getenv("PB200_NO_FUSE_GRAM") || primme->convTestFun != conv_test_absolute) ? 0 : 1;
    if (primme->orth == primme_orth_explicit_I) {
-      S->VtBV = (double *)calloc((size_t)mr * mr, sizeof(double));
-      S->fVtBV = (double *)calloc((size_t)mr * mr, sizeof(double));
+      S->VtBV = (SCALAR *)calloc((size_t)mr * mr, sizeof(SCALAR));
+      S->fVtBV = (SCALAR *)calloc((size_t)mr * mr, sizeof(SCALAR));
    }
    S->refined = primme->projectionParams.projection == primme_proj_refined;
    S->numQR = primme->projectionParams.projection != primme_proj_RR;
    if (primme->projectionParams.projection == primme_proj_harmonic) {
-      S->QtV = (double *)calloc((size_t)mb * mb, sizeof(double));
+      S->QtV = (SCALAR *)calloc((size_t)mb * mb, sizeof(SCALAR));
       if (!S->QtV) rc = PRIMME_MALLOC_FAILURE;
    }
    if (S->numQR) {
       /* Q next to V and W, its small factors on the host (main_iter.c:284-320) */
       if (!rc) rc = pb200_malloc(S->dev, basis_bytes, (void **)&S->Q);
-      S->R = (double *)calloc((size_t)mb * mb, sizeof(double));
-      S->hU = (double *)calloc((size_t)mb * mb, sizeof(double));
-      S->hVecsRot = (double *)calloc((size_t)mb * mb, sizeof(double));
+      S->R = (SCALAR *)calloc((size_t)mb * mb, sizeof(SCALAR));
+      S->hU = (SCALAR *)calloc((size_t)mb * mb, sizeof(SCALAR));
+      S->hVecsRot = (SCALAR *)calloc((size_t)mb * mb, sizeof(SCALAR));
       S->hSVals = (double *)calloc(mb, sizeof(double));
       if (primme->orth == primme_orth_explicit_I) {
-         S->QtQ = (double *)calloc((size_t)mb * mb, sizeof(double));
-         S->fQtQ = (double *)calloc((size_t)mb * mb, sizeof(double));
+         S->QtQ = (SCALAR *)calloc((size_t)mb * mb, sizeof(SCALAR));
+         S->fQtQ = (SCALAR *)calloc((size_t)mb * mb, sizeof(SCALAR));
       }
       if (!S->R || !S->hU || !S->hVecsRot || !S->hSVals) rc = PRIMME_MALLOC_FAILURE;
    }
@@ -519,7 +525,7 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
       if (!device_mode && numRet > 0)
          rc = pb200_copy_d2h(S->dev, S->evecs + (size_t)S->ldevecs * primme->numOrthoConst,
                     S->ldevecs, evecs + (size_t)primme->ldevecs * primme->numOrthoConst,
-                    primme->ldevecs, S->n, numRet, 8)
+                    primme->ldevecs, S->n, numRet, PB_ES)
                     ? PRIMME_UNEXPECTED_FAILURE
                     : ret;
    } else {
@@ -548,11 +554,21 @@ static int solve_d(double *evals, double *evecs, double *resNorms, primme_params
    return rc;
 }
 
+#ifdef PB_COMPLEX
+/* complex Hermitian twins (reference include/primme_eigs.h:392,416): evecs and the callback blocks are
+ * interleaved (re,im) fp64; evals and resNorms real */
+int zprimme(double *evals, PRIMME_COMPLEX_DOUBLE *evecs, double *resNorms, primme_params *primme) {
+   return solve_typed(evals, (SCALAR *)evecs, resNorms, primme, 0);
+}
+int cublas_zprimme(double *evals, PRIMME_COMPLEX_DOUBLE *evecs, double *resNorms, primme_params *primme) {
+   return solve_typed(evals, (SCALAR *)evecs, resNorms, primme, 1);
+}
+#else
 int dprimme(double *evals, double *evecs, double *resNorms, primme_params *primme) {
-   return solve_d(evals, evecs, resNorms, primme, 0);
+   return solve_typed(evals, evecs, resNorms, primme, 0);
 }
 int cublas_dprimme(double *evals, double *evecs, double *resNorms, primme_params *primme) {
-   return solve_d(evals, evecs, resNorms, primme, 1);
+   return solve_typed(evals, evecs, resNorms, primme, 1);
 }
 
 /* Entry points of precisions / back ends outside the scope: same behaviour as a reference build
@@ -571,10 +587,11 @@ PB_UNAVAILABLE3(kprimme, PRIMME_HALF, PRIMME_COMPLEX_HALF, PRIMME_HALF)
 PB_UNAVAILABLE3(sprimme, float, float, float)
 PB_UNAVAILABLE3(cprimme, float, PRIMME_COMPLEX_FLOAT, float)
 PB_UNAVAILABLE(magma_dprimme, double, double, double)
-PB_UNAVAILABLE3(zprimme, double, PRIMME_COMPLEX_DOUBLE, double)
+PB_UNAVAILABLE(magma_zprimme, double, PRIMME_COMPLEX_DOUBLE, double)
 PB_UNAVAILABLE3(hsprimme, float, PRIMME_HALF, float)
 PB_UNAVAILABLE3(ksprimme, float, PRIMME_COMPLEX_HALF, float)
 PB_UNAVAILABLE3(kprimme_normal, PRIMME_COMPLEX_HALF, PRIMME_COMPLEX_HALF, PRIMME_HALF)
 PB_UNAVAILABLE3(cprimme_normal, PRIMME_COMPLEX_FLOAT, PRIMME_COMPLEX_FLOAT, float)
 PB_UNAVAILABLE3(zprimme_normal, PRIMME_COMPLEX_DOUBLE, PRIMME_COMPLEX_DOUBLE, double)
 PB_UNAVAILABLE3(kcprimme_normal, PRIMME_COMPLEX_FLOAT, PRIMME_COMPLEX_HALF, float)
+#endif /* !PB_COMPLEX */

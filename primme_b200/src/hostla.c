@@ -78,6 +78,14 @@ void hl_permute_cols(SCALAR *x, int m, int n, int ld, const int *perm) {
 }
 
 #ifndef PB_COMPLEX
+void hl_permute_reals(double *x, int n, const int *perm) {
+   if (n <= 0) return;
+   double *tmp = (double *)malloc(sizeof(double) * n);
+   for (int i = 0; i < n; i++) tmp[i] = x[perm[i]];
+   memcpy(x, tmp, sizeof(double) * n);
+   free(tmp);
+}
+
 void hl_permute_ints(int *x, int n, const int *perm) {
    if (n <= 0) return;
    int *tmp = (int *)malloc(sizeof(int) * n);

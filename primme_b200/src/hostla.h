@@ -57,6 +57,7 @@ typedef double SCALAR;
 /* y(:,i) <- x(:,perm[i]) in place, for i < n (reference permute_vecs, auxiliary.c:716-793) */
 void hl_permute_cols(SCALAR *x, int m, int n, int ld, const int *perm);
 void hl_permute_ints(int *x, int n, const int *perm);
+void hl_permute_reals(double *x, int n, const int *perm);
 void hl_copy(const SCALAR *x, int m, int n, int ldx, SCALAR *y, int ldy);
 void hl_zero(SCALAR *x, int m, int n, int ld);
 

@@ -89,7 +89,9 @@ void primme_b200_csr_matvec(void *x, PRIMME_INT *ldx, void *y, PRIMME_INT *ldy, 
       *ierr = -1;
       return;
    }
-   *ierr = pb200_dspmm(ctx, A, (const double *)x, *ldx, (double *)y, *ldy, *blockSize);
+   /* the matrix knows its scalar type: the same callback serves dprimme and zprimme */
+   *ierr = pb200_csr_is_complex(A) ? pb200_zspmm(ctx, A, x, *ldx, y, *ldy, *blockSize)
+                                   : pb200_dspmm(ctx, A, (const double *)x, *ldx, (double *)y, *ldy, *blockSize);
 }
 
 /* ---- Jacobi (diagonal) preconditioner with per-column shifts ---- */
@@ -108,14 +110,27 @@ void primme_b200_jacobi_apply(void *x, PRIMME_INT *ldx, void *y, PRIMME_INT *ldy
          *ldx, (double *)y, *ldy, *blockSize);
 }
 
+/* complex blocks, real diagonal (the diagonal of a Hermitian matrix): zprimme's twin of the above */
+void primme_b200_zjacobi_apply(void *x, PRIMME_INT *ldx, void *y, PRIMME_INT *ldy, int *blockSize,
+      primme_params *primme, int *ierr) {
+   pb200_ctx *ctx = primme_b200_solver_ctx(primme);
+   const primme_b200_jacobi *J = (const primme_b200_jacobi *)primme->preconditioner;
+   if (!ctx || !J) {
+      *ierr = -1;
+      return;
+   }
+   const double *shifts = J->use_shifts ? primme->ShiftsForPreconditioner : NULL;
+   *ierr = pb200_zjacobi(ctx, primme->nLocal, J->diag_dev, shifts, J->minabs, x, *ldx, y, *ldy, *blockSize);
+}
+
 /* ---- one-call convenience: host CSR + host result arrays, everything else on the device ----
  * What a CSR user of the reference would bind: upload the matrix, run the device solver with
  * the built-in SpMM, download the eigenvectors.  evecs_host is n x (numOrthoConst +
  * max(numEvals, initSize)) with leading dimension primme->ldevecs (or n). */
-int primme_b200_dprimme_csr(double *evals, double *evecs_host, double *resNorms,
-      primme_params *primme, const int64_t *rowptr_host, const int32_t *colind_host,
-      const double *vals_host, int index_base) {
+static int solve_csr(double *evals, void *evecs_host, double *resNorms, primme_params *primme,
+      const int64_t *rowptr_host, const int32_t *colind_host, const void *vals_host, int index_base, int is_complex) {
    if (!primme || !rowptr_host) return -4;
+   const int es = is_complex ? 16 : 8;
    pb200_ctx *ctx = NULL;
    int own = 0, rc;
    ctx = primme_b200_attached_ctx(primme);
@@ -128,15 +143,15 @@ int primme_b200_dprimme_csr(double *evals, double *evecs_host, double *resNorms,
    const int64_t n = primme->numProcs > 1 ? primme->nLocal : primme->n;
    const int64_t nnz = rowptr_host[n] - index_base;
    pb200_csr *A = NULL;
-   double *devecs = NULL;
+   void *devecs = NULL;
    const double tc0 = hl_wtime();
-   rc = pb200_csr_create(ctx, n, primme->n, nnz, rowptr_host, colind_host, vals_host, index_base, 0, &A);
+   rc = pb200_csr_create(ctx, n, primme->n, nnz, rowptr_host, colind_host, vals_host, index_base, is_complex, &A);
    const double tc1 = hl_wtime();
    const int ncols = primme->numOrthoConst + PB_MAX(primme->numEvals, primme->initSize);
    const int64_t ldh = primme->ldevecs > 0 ? primme->ldevecs : n;
-   if (!rc) rc = pb200_malloc(ctx, sizeof(double) * (size_t)PB_MAX(n, 1) * PB_MAX(ncols, 1), (void **)&devecs);
+   if (!rc) rc = pb200_malloc(ctx, (size_t)es * (size_t)PB_MAX(n, 1) * PB_MAX(ncols, 1), &devecs);
    if (!rc && primme->numOrthoConst + primme->initSize > 0)
-      rc = pb200_copy_h2d(ctx, evecs_host, ldh, devecs, n, n, primme->numOrthoConst + primme->initSize, 8);
+      rc = pb200_copy_h2d(ctx, evecs_host, ldh, devecs, n, n, primme->numOrthoConst + primme->initSize, es);
    if (!rc) {
       void *old_matrix = primme->matrix;
       primme_block_op_fn old_mv = primme->matrixMatvec;
@@ -145,14 +160,15 @@ int primme_b200_dprimme_csr(double *evals, double *evecs_host, double *resNorms,
       primme->matrixMatvec = primme_b200_csr_matvec;
       primme->ldevecs = n;
       if (primme->numProcs <= 1) primme->nLocal = n;
-      rc = cublas_dprimme(evals, devecs, resNorms, primme);
+      rc = is_complex ? cublas_zprimme(evals, (PRIMME_COMPLEX_DOUBLE *)devecs, resNorms, primme)
+                      : cublas_dprimme(evals, (double *)devecs, resNorms, primme);
       primme->matrix = old_matrix;
       primme->matrixMatvec = old_mv;
       primme->ldevecs = old_ld;
       int nret = primme->numOrthoConst + (primme->initSize > 0 ? primme->initSize : 0);
       if (nret > ncols) nret = ncols;
       if (rc == 0 || rc == PRIMME_MAIN_ITER_FAILURE) {
-         int r2 = pb200_copy_d2h(ctx, devecs, n, evecs_host, ldh, n, PB_MAX(nret, primme->numOrthoConst + primme->numEvals < ncols ? primme->numOrthoConst + primme->numEvals : ncols), 8);
+         int r2 = pb200_copy_d2h(ctx, devecs, n, evecs_host, ldh, n, PB_MAX(nret, primme->numOrthoConst + primme->numEvals < ncols ? primme->numOrthoConst + primme->numEvals : ncols), es);
          if (r2 && !rc) rc = PRIMME_UNEXPECTED_FAILURE;
       }
    }
@@ -167,4 +183,14 @@ int primme_b200_dprimme_csr(double *evals, double *evecs_host, double *resNorms,
       pb200_ctx_destroy(ctx);
    }
    return rc;
+}
+
+int primme_b200_dprimme_csr(double *evals, double *evecs_host, double *resNorms, primme_params *primme,
+      const int64_t *rowptr_host, const int32_t *colind_host, const double *vals_host, int index_base) {
+   return solve_csr(evals, evecs_host, resNorms, primme, rowptr_host, colind_host, vals_host, index_base, 0);
+}
+/* complex Hermitian twin: vals_host and evecs_host interleaved (re,im) */
+int primme_b200_zprimme_csr(double *evals, void *evecs_host, double *resNorms, primme_params *primme,
+      const int64_t *rowptr_host, const int32_t *colind_host, const void *vals_host, int index_base) {
+   return solve_csr(evals, evecs_host, resNorms, primme, rowptr_host, colind_host, vals_host, index_base, 1);
 }

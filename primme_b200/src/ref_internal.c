@@ -262,3 +262,80 @@ int ortho_single_iteration_dprimme(double *Q, int nQ, PRIMME_INT ldQ, double *BQ
    free(y);
    return rc;
 }
+
+/* ---- complex double flavours (tests/driver.c built with -DUSE_DOUBLECOMPLEX) ---- */
+#include <complex.h>
+typedef double _Complex pb_z;
+extern void zgemv_(const char *, int *, int *, pb_z *, const pb_z *, int *, const pb_z *, int *, pb_z *, pb_z *, int *);
+
+pb_z Num_dot_zprimme(PRIMME_INT n, pb_z *x, PRIMME_INT incx, pb_z *y, PRIMME_INT incy, pb_ref_context ctx) {
+   (void)ctx;
+   pb_z s = 0.0; /* the reference's explicit zdotc (blaslapack.c:899-913) */
+   for (PRIMME_INT i = 0; i < n; i++) s += conj(x[i * incx]) * y[i * incy];
+   return s;
+}
+
+int Num_gemv_zprimme(const char *transa, PRIMME_INT m, PRIMME_INT n, pb_z alpha, pb_z *a, PRIMME_INT lda, pb_z *x,
+      PRIMME_INT incx, pb_z beta, pb_z *y, PRIMME_INT incy, pb_ref_context ctx) {
+   (void)ctx;
+   const int tr = (*transa == 'n' || *transa == 'N') ? 0 : 1;
+   const PRIMME_INT leny = tr ? n : m;
+   if (leny <= 0) return 0;
+   if ((tr ? m : n) <= 0) {
+      for (PRIMME_INT i = 0; i < leny; i++) y[i * incy] = beta == 0.0 ? 0.0 : beta * y[i * incy];
+      return 0;
+   }
+   if (m > 0x7fffffffLL || n > 0x7fffffffLL || lda > 0x7fffffffLL) return PRIMME_FUNCTION_UNAVAILABLE;
+   int lm = (int)m, ln = (int)n, llda = (int)lda, ix = (int)incx, iy = (int)incy;
+   zgemv_(transa, &lm, &ln, &alpha, a, &llda, x, &ix, &beta, y, &iy);
+   return 0;
+}
+
+int Num_larnv_zprimme(int idist, PRIMME_INT *iseed, PRIMME_INT length, pb_z *x, pb_ref_context ctx) {
+   /* the real generator on twice the length (blaslapack.c:938-949) */
+   return Num_larnv_dprimme(idist, iseed, 2 * length, (double *)x, ctx);
+}
+
+int ortho_single_iteration_zprimme(pb_z *Q, int nQ, PRIMME_INT ldQ, pb_z *BQ, PRIMME_INT ldBQ, pb_z *QtBQ, int ldQtBQ,
+      pb_z *X, int *inX, int nX, PRIMME_INT ldX, double *norms, pb_ref_context ctx) {
+   (void)QtBQ, (void)ldQtBQ;
+   primme_params *primme = ctx.primme;
+   if (!primme) return PRIMME_UNEXPECTED_FAILURE;
+   const PRIMME_INT n = primme->nLocal;
+   if (nX <= 0) return 0;
+   pb_z *y = (pb_z *)calloc((size_t)(nQ > 0 ? nQ : 1) * nX, sizeof(pb_z));
+   if (!y) return PRIMME_MALLOC_FAILURE;
+   for (int j = 0; j < nX; j++) {
+      const pb_z *x = X + (size_t)ldX * (inX ? inX[j] : j);
+      for (int i = 0; i < nQ; i++) {
+         const pb_z *q = Q + (size_t)ldQ * i;
+         pb_z s = 0.0;
+         for (PRIMME_INT r = 0; r < n; r++) s += conj(q[r]) * x[r];
+         y[i + (size_t)nQ * j] = s;
+      }
+   }
+   primme->stats.numOrthoInnerProds += (double)nQ * nX;
+   int rc = ctx.globalSum ? ctx.globalSum(y, primme_op_double, 2 * nQ * nX, ctx) : 0;
+   if (!rc) {
+      for (int j = 0; j < nX; j++) {
+         pb_z *x = X + (size_t)ldX * (inX ? inX[j] : j);
+         for (int i = 0; i < nQ; i++) {
+            const pb_z *bq = (BQ ? BQ : Q) + (size_t)(BQ ? ldBQ : ldQ) * i;
+            const pb_z c = y[i + (size_t)nQ * j];
+            for (PRIMME_INT r = 0; r < n; r++) x[r] -= bq[r] * c;
+         }
+         if (norms) {
+            double s = 0.0;
+            for (PRIMME_INT r = 0; r < n; r++) s += creal(conj(x[r]) * x[r]);
+            norms[j] = s;
+         }
+      }
+      if (norms) {
+         rc = ctx.globalSum ? ctx.globalSum(norms, primme_op_double, nX, ctx) : 0;
+         for (int j = 0; j < nX; j++) norms[j] = sqrt(norms[j]);
+         primme->stats.numOrthoInnerProds += nX;
+      }
+   }
+   free(y);
+   return rc;
+}

@@ -21,4 +21,12 @@ for i in range(1, 8):
     open(os.path.join(out, name), "w").write(re.sub(r"(sol_[^ \n]*)", r"\1_double", txt))
     shutil.copyfile(os.path.join(ref, "tests", "tests", f"sol_{i:03d}_double"),
                     os.path.join(out, "tests", f"sol_{i:03d}_double"))
+# complex Hermitian configurations test_101...106 (mhd1280b.mtx, sol_10N_doublecomplex)
+shutil.copyfile(os.path.join(ref, "tests", "mhd1280b.mtx"), os.path.join(out, "mhd1280b.mtx"))
+for i in range(101, 107):
+    name = f"test_{i:03d}"
+    txt = open(os.path.join(ref, "tests", "tests", name)).read()
+    open(os.path.join(out, name), "w").write(re.sub(r"(sol_[^ \n]*)", r"\1_doublecomplex", txt))
+    shutil.copyfile(os.path.join(ref, "tests", "tests", f"sol_{i:03d}_doublecomplex"),
+                    os.path.join(out, "tests", f"sol_{i:03d}_doublecomplex"))
 print("wrote", sorted(os.listdir(out)))

@@ -140,3 +140,69 @@ def solve(which, csr, numEvals, target=api.primme_smallest, method=api.PRIMME_GD
     if which != "reference":
         out["launches"] = launches
     return out
+
+
+def zsolve(which, csr, numEvals, target=api.primme_smallest, method=api.PRIMME_GD_Olsen_plusK, jacobi=False,
+           nthreads=1, tweak=None, **kw):
+    """zprimme through `which` in {"reference", "hostcheck", "product"}: csr = (indptr, indices, complex values) of a
+    Hermitian matrix.  Returns dict(evals, rnorms, evecs (n x k complex), ret, stats)."""
+    indptr, indices, data = csr
+    n = len(indptr) - 1
+    rp = np.ascontiguousarray(indptr, dtype=np.int64)
+    ci = np.ascontiguousarray(indices, dtype=np.int32)
+    va = np.ascontiguousarray(data, dtype=np.complex128)
+    diag = None
+    if jacobi:
+        diag = np.zeros(n)
+        rows = np.repeat(np.arange(n), np.diff(rp))
+        m = rows == ci
+        diag[rows[m]] = va[m].real
+    lib = {"reference": lib_reference, "hostcheck": lib_hostcheck, "product": lib_product}[which]()
+    p = api.new_params(lib, n, numEvals=numEvals, target=target, **kw)
+    keep = []
+    if which == "reference":
+        ok = lib_oracle_kernels()
+        A = CsrHost(n, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, nthreads,
+                    diag.ctypes.data if diag is not None else None, 1e-12 if jacobi else 0.0, 1)
+        keep.append(A)
+        p.matrix = C.addressof(A)
+        p.matrixMatvec = C.cast(ok.csr_host_zmatvec, C.c_void_p).value
+        if jacobi:
+            p.preconditioner = C.addressof(A)
+            p.applyPreconditioner = C.cast(ok.csr_host_zjacobi, C.c_void_p).value
+    elif jacobi:
+        p.applyPreconditioner = C.cast(lib.primme_b200_zjacobi_apply, C.c_void_p).value
+    if method is not None:
+        assert lib.primme_set_method(method, C.byref(p)) == 0
+    if tweak is not None:
+        tweak(p)
+    ncols = p.numOrthoConst + max(numEvals, p.initSize)
+    evals = np.zeros(numEvals)
+    rnorms = np.zeros(numEvals)
+    evecs = np.zeros((ncols, n), dtype=np.complex128)
+    p.ldevecs = n
+    vp = C.c_void_p
+    if which == "reference":
+        lib.zprimme.restype, lib.zprimme.argtypes = C.c_int, [vp, vp, vp, C.POINTER(api.PrimmeParams)]
+        rc = lib.zprimme(evals.ctypes.data, evecs.ctypes.data, rnorms.ctypes.data, C.byref(p))
+    else:
+        lib.primme_b200_zprimme_csr.restype = C.c_int
+        lib.primme_b200_zprimme_csr.argtypes = [vp, vp, vp, C.POINTER(api.PrimmeParams), vp, vp, vp, C.c_int]
+        ctx = C.c_void_p()
+        assert lib.pb200_ctx_create(C.byref(ctx), -1) == 0
+        lib.primme_b200_attach_ctx(C.byref(p), ctx)
+        ddiag = C.c_void_p()
+        if jacobi:
+            assert lib.pb200_malloc(ctx, 8 * n, C.byref(ddiag)) == 0
+            assert lib.pb200_copy_h2d(ctx, diag.ctypes.data, n, ddiag, n, n, 1, 8) == 0
+            jac = api.Jacobi(ddiag.value, 1e-12, 1)
+            keep.append(jac)
+            p.preconditioner = C.addressof(jac)
+        rc = lib.primme_b200_zprimme_csr(evals.ctypes.data, evecs.ctypes.data, rnorms.ctypes.data, C.byref(p),
+                                         rp.ctypes.data, ci.ctypes.data, va.ctypes.data, 0)
+        if jacobi:
+            lib.pb200_free(ctx, ddiag)
+        lib.primme_b200_attach_ctx(C.byref(p), None)
+        lib.pb200_ctx_destroy(ctx)
+    return dict(evals=evals, rnorms=rnorms, evecs=evecs[p.numOrthoConst:].T.copy(), ret=rc,
+                stats=api.stats_dict(p), initSize=p.initSize, params=p)

@@ -31,6 +31,14 @@ def test_eigs_driver_hostcheck_passes_golden(cfg):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+@pytest.mark.parametrize("cfg", ["test_101", "test_102", "test_103", "test_104", "test_105", "test_106"])
+def test_complex_eigs_driver_hostcheck_passes_golden(cfg):
+    """the reference's six complex Hermitian configurations (mhd1280b.mtx; zprimme): tests/driver.c compiled
+    UNCHANGED with -DUSE_DOUBLECOMPLEX, check_solution against the stored sol_10N_doublecomplex"""
+    r = run("primme_doublecomplex_hostcheck", cfg)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 @pytest.mark.parametrize("cfg", ["test_201", "test_202", "test_203", "test_204", "test_205", "test_206", "test_207"])
 def test_svds_driver_hostcheck_passes_golden(cfg):
     """201, 202, 207: largest triplets (hybrid / augmented); 203-206: smallest triplets, where the second

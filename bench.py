@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--c5-n", type=int, default=10**7,
                     help="rows of the power-law matrix of config C5 reported in the `c5` block (0: skip)")
     ap.add_argument("--c5-steps", type=int, default=2)
+    ap.add_argument("--c3-n", type=int, default=500000,
+                    help="rows of the complex Hermitian matrix of config C3 reported in the `c3` block at N=1 (0: skip)")
     ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
                     help="N>1: row-sharded solve with NCCL (strong scaling) or independent replicas")
     return ap.parse_args()
@@ -283,6 +285,75 @@ def run_c5(args, lib, api, M, ctx, rank, world, dist):
     return out
 
 
+def run_c3(args, lib, api, M, ctx):
+    """Config C3 (BASELINE.json configs[2]): zprimme, complex Hermitian CSR n = 5e5 (matrices.C3_MATRIX), 8 pairs
+    closest to sigma = 0.5, JDQMR_ETol, Jacobi preconditioner, 1 GPU.  Matrix and eigenvectors resident in HBM."""
+    import torch
+    n = args.c3_n
+    ip, ix, da = M.hermitian_c3(n, **M.C3_MATRIX)
+    rows = np.repeat(np.arange(n), np.diff(ip))
+    diag = np.zeros(n)
+    diag[rows[rows == ix]] = da[rows == ix].real
+    A = C.c_void_p()
+    assert lib.pb200_csr_create(ctx, n, n, len(ix), ip.ctypes.data, ix.ctypes.data, da.ctypes.data, 0, 1, C.byref(A)) == 0
+    ddiag, devecs = C.c_void_p(), C.c_void_p()
+    assert lib.pb200_malloc(ctx, 8 * n, C.byref(ddiag)) == 0
+    assert lib.pb200_copy_h2d(ctx, diag.ctypes.data, n, ddiag, n, n, 1, 8) == 0
+    k = 8
+    assert lib.pb200_malloc(ctx, 16 * n * k, C.byref(devecs)) == 0
+    jac = api.Jacobi(ddiag.value, 1e-12, 1)
+    evals, rn = np.zeros(k), np.zeros(k)
+    lib.cublas_zprimme.restype = C.c_int
+    lib.cublas_zprimme.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(api.PrimmeParams)]
+
+    def solve():
+        p = api.new_params(lib, n, numEvals=k, target=api.primme_closest_abs, targetShifts=[0.5], eps=1e-10)
+        p.applyPreconditioner = C.cast(lib.primme_b200_zjacobi_apply, C.c_void_p).value
+        assert lib.primme_set_method(api.PRIMME_JDQMR_ETol, C.byref(p)) == 0
+        p.preconditioner = C.addressof(jac)
+        p.matrix = A
+        p.matrixMatvec = C.cast(lib.primme_b200_csr_matvec, C.c_void_p).value
+        p.ldevecs = n
+        lib.primme_b200_attach_ctx(C.byref(p), ctx)
+        rc = lib.cublas_zprimme(evals.ctypes.data, devecs, rn.ctypes.data, C.byref(p))
+        lib.primme_b200_attach_ctx(C.byref(p), None)
+        assert rc == 0, rc
+        return p
+
+    solve()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.pb200_ctx_launches(ctx)
+    ev0.record()
+    mv = 0
+    for _ in range(args.c5_steps):
+        p = solve()
+        mv += p.stats.numMatvecs
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.pb200_ctx_launches(ctx) - l0
+    st = api.stats_dict(p)
+    lib.pb200_ctx_set_profiling(ctx, 1)
+    solve()
+    kern = {}
+    for i, name in enumerate(["spmm", "ortho_sweep", "vwxr", "utils", "panel_reduce"]):
+        cnt, pms, pby = C.c_int64(), C.c_double(), C.c_double()
+        lib.pb200_ctx_get_profile(ctx, i, C.byref(cnt), C.byref(pms), C.byref(pby))
+        kern[name] = {"GBps": round((pby.value / 1e9) / (pms.value / 1e3), 1) if pms.value > 0 else 0.0,
+                      "ms": round(pms.value, 3), "launches": cnt.value}
+    lib.pb200_ctx_set_profiling(ctx, 0)
+    out = {"workload": f"zprimme complex Hermitian CSR n={n}, 8 closest to 0.5, JDQMR_ETol, Jacobi, eps=1e-10",
+           "n": n, "nnz": int(len(ix)), "dtype": "c128", "ms_per_solve": ms / args.c5_steps,
+           "matvecs_per_s": mv / (ms * 1e-3), "matvecs_per_solve": st["numMatvecs"],
+           "outer_iterations": st["numOuterIterations"], "restarts": st["numRestarts"],
+           "evals": [float(x) for x in np.sort(evals)], "max_resnorm": float(rn.max()),
+           "gpu_launches_per_solve": launches / args.c5_steps, "kernels": kern}
+    lib.pb200_free(ctx, devecs), lib.pb200_free(ctx, ddiag)
+    lib.pb200_csr_destroy(ctx, A)
+    return out
+
+
 def main():
     args = parse()
     # OpenBLAS reads its thread count when the library is first loaded (the product links the same
@@ -506,10 +577,17 @@ def main():
         except Exception as e:  # never lose the headline line
             c5 = {"error": repr(e)}
 
+    c3 = None
+    if args.c3_n > 0 and world == 1:
+        try:
+            c3 = run_c3(args, lib, api, M, ctx)
+        except Exception as e:
+            c3 = {"error": repr(e)}
+
     if rank == 0:
         line = {"metric": "matvecs_per_s", "value": value, "unit": "matvecs/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+                "higher_is_better": True, "scaling": "strong" if (sharded or world == 1) else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args.side), "n": n, "nnz": nnz,
                            "parallelism": (f"row-sharded x{world}, " + ("in-kernel panel all-reduce over NVLink peer memory" if peer_active
@@ -523,7 +601,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "matvecs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e / max(1, min(args.steps, 3))},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "c5": c5}
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "c5": c5, "c3": c3}
         print(json.dumps(line))
 
     lib.pb200_free(ctx, devecs)

@@ -40,6 +40,9 @@ int pb200_device_count(void);
 int pb200_ctx_create(pb200_ctx **ctx, int device /* -1: current */);
 int pb200_ctx_destroy(pb200_ctx *ctx);
 int pb200_ctx_sync(pb200_ctx *ctx);
+/* marks the start of a solve on a long-lived context (resets the alternating row-sweep direction so
+ * that repeated solves are bitwise reproducible); dprimme / zprimme call it themselves */
+int pb200_ctx_begin_solve(pb200_ctx *ctx);
 void *pb200_ctx_stream(pb200_ctx *ctx); /* cudaStream_t */
 /* kernel-launch counter (bench.py reports it as gpu_launches) */
 int64_t pb200_ctx_launches(pb200_ctx *ctx);
@@ -78,6 +81,11 @@ int pb200_is_device_pointer(const void *p);
  * examples/ex_eigs_dcublas.c:238-263 and tests/COMMON/mat.c:68 (CSRMatrixMatvec).
  * index_base 0 or 1 (tests/COMMON/csr.c uses 1).  is_complex selects z values. */
 int pb200_csr_create(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
+      const int64_t *rowptr_host, const int32_t *colind_host, const void *vals_host,
+      int index_base, int is_complex, pb200_csr **A);
+/* same with the device arrays taken from the context's matrix pool (no cudaMalloc / cudaFree per
+ * matrix): for callers that upload a matrix per solve; valid until the next pooled create on ctx */
+int pb200_csr_create_pooled(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
       const int64_t *rowptr_host, const int32_t *colind_host, const void *vals_host,
       int index_base, int is_complex, pb200_csr **A);
 int pb200_csr_destroy(pb200_ctx *ctx, pb200_csr *A);
@@ -286,6 +294,20 @@ void primme_b200_zjacobi_apply(void *x, int64_t *ldx, void *y, int64_t *ldy, int
  * include/primme_svds.h:113-116, examples/ex_svds_dseq.c:188-230). */
 struct primme_svds_params;
 void primme_b200_svds_csr_matvec(void *x, int64_t *ldx, void *y, int64_t *ldy, int *blockSize,
+      int *transpose, struct primme_svds_params *primme_svds, int *ierr);
+
+/* Row-partitioned built-in operator of the SVD front end (config C4; primme_svds.numProcs > 1, mLocal /
+ * nLocal set): primme_svds.matrix = primme_b200_svds_dist*, primme_svds.matrixMatvec = this function.
+ *   A  : pb200_dist_csr over this rank's rows of A   (mLocal x n, global column ids; counts = the nLocal's)
+ *   At : pb200_dist_csr over this rank's rows of A^T (nLocal x m, global column ids; counts = the mLocal's)
+ * y = A x gathers the n-side block, y = A^T x gathers the m-side block, both over the compacted
+ * peer-memory halo of the row-sharded operator (no reduce-scatter).  Replaces the user's MPI operator
+ * around reference src/svds/primme_svds_c.c:1323-1383. */
+typedef struct primme_b200_svds_dist {
+   pb200_dist_csr *A;
+   pb200_dist_csr *At;
+} primme_b200_svds_dist;
+void primme_b200_svds_dist_csr_matvec(void *x, int64_t *ldx, void *y, int64_t *ldy, int *blockSize,
       int *transpose, struct primme_svds_params *primme_svds, int *ierr);
 
 #ifdef __cplusplus

@@ -36,6 +36,10 @@ int pb200_ctx_destroy(pb200_ctx *ctx) {
    free(ctx);
    return 0;
 }
+int pb200_ctx_begin_solve(pb200_ctx *ctx) {
+   (void)ctx;
+   return 0;
+}
 int pb200_ctx_sync(pb200_ctx *ctx) {
    (void)ctx;
    return 0;
@@ -82,6 +86,7 @@ int pb200_dist_csr_info(const pb200_dist_csr *D, int64_t *a, int64_t *b, int64_t
 int pb200_ctx_peer_export(pb200_ctx *ctx, void *h) { (void)ctx, (void)h; return PB200_ERR_ARG; }
 int pb200_ctx_peer_attach(pb200_ctx *ctx, int n, int r, const void *h) { (void)ctx, (void)n, (void)r, (void)h; return PB200_ERR_ARG; }
 int pb200_ctx_peer_active(pb200_ctx *ctx) { (void)ctx; return 0; }
+void primme_b200_svds_dist_csr_matvec(void *x, int64_t *ldx, void *y, int64_t *ldy, int *bs, int *tr, struct primme_svds_params *p, int *ierr) { (void)x, (void)ldx, (void)y, (void)ldy, (void)bs, (void)tr, (void)p; *ierr = -1; }
 void primme_b200_dist_csr_matvec(void *x, int64_t *ldx, void *y, int64_t *ldy, int *bs, struct primme_params *p, int *ierr) { (void)x, (void)ldx, (void)y, (void)ldy, (void)bs, (void)p; *ierr = -1; }
 
 int pb200_malloc(pb200_ctx *ctx, size_t bytes, void **dptr) {
@@ -156,6 +161,10 @@ int pb200_csr_create(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
    memcpy(A->vals, vals, sizeof(double) * (is_complex ? 2 : 1) * nnz);
    *out = A;
    return 0;
+}
+int pb200_csr_create_pooled(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz, const int64_t *rowptr,
+      const int32_t *colind, const void *vals, int index_base, int is_complex, pb200_csr **out) {
+   return pb200_csr_create(ctx, nrows, ncols, nnz, rowptr, colind, vals, index_base, is_complex, out);
 }
 int pb200_csr_destroy(pb200_ctx *ctx, pb200_csr *A) {
    if (!A) return 0;

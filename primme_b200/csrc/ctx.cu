@@ -54,6 +54,7 @@ extern "C" int pb200_ctx_create(pb200_ctx **out, int device) {
    ctx->ortho_exact = getenv("PB200_NO_ORTHO_EXACT") ? 0 : 1;
    ctx->use_tma_vwxr = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_VWXR")) ? 0 : 1;
    ctx->use_tma_spmm = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_SPMM")) ? 0 : 1;
+   ctx->sweep_alternate = getenv("PB200_NO_ALTERNATE") ? 0 : 1;
    ctx->spmm_v3 = getenv("PB200_SPMM_V3") ? atoi(getenv("PB200_SPMM_V3")) : 2;
    *out = ctx;
    return 0;
@@ -81,6 +82,13 @@ extern "C" int pb200_ctx_destroy(pb200_ctx *ctx) {
    }
    cudaStreamDestroy(ctx->stream);
    free(ctx);
+   return 0;
+}
+
+// Start of a solve on a long-lived context: the alternating sweep direction restarts, so that repeated
+// solves of the same problem visit the rows in the same order (bitwise identical panels, same counts)
+extern "C" int pb200_ctx_begin_solve(pb200_ctx *ctx) {
+   ctx->sweep_rev = 0;
    return 0;
 }
 

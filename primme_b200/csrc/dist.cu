@@ -22,6 +22,7 @@
 //   peer access the same compacted rows travel through grouped ncclSend/ncclRecv.
 #include "pb200_internal.cuh"
 #include "../../include/primme.h"
+#include "../../include/primme_svds.h"
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -139,7 +140,9 @@ extern "C" int pb200_dist_csr_create(pb200_ctx *ctx, pb200_csr *A_local, const i
    D->rowbytes_max = A_local->is_complex ? 128 : 64;
    *out = D;
    if (nranks <= 1) return 0;
-   if (A_local->nrows != D->nloc) return PB200_ERR_ARG;
+   // counts partitions the COLUMN space (the rows of the block x this operator is applied to); the
+   // local matrix may have any number of rows (square operators: nrows == counts[rank]; the two
+   // operators of the row-partitioned SVD, below, are rectangular)
    const int me = D->rank;
 
    // ---- distinct remote columns per owner, remapped column indices ----
@@ -413,4 +416,22 @@ extern "C" void primme_b200_dist_csr_matvec(void *x, int64_t *ldx, void *y, int6
       return;
    }
    *ierr = dist_spmm_any(ctx, D, x, *ldx, y, *ldy, *blockSize);
+}
+
+// ---- row-partitioned operator of the SVD front end (config C4: primme_svds with numProcs > 1) ----
+// PRIMME's SPMD model for svds (reference include/primme_svds.h: mLocal rows of the left vectors, nLocal rows
+// of the right vectors per process; src/svds/primme_svds_c.c:1323-1383 applies A then A^T): rank r owns the
+// rows [m-range r] of A -- `A` below, applied to an n-side block gathered from all ranks -- and the rows
+// [n-range r] of A^T -- `At`, applied to an m-side block.  Both directions are gather-type products over
+// the compacted peer-memory halo; A^T y needs no reduce-scatter and stays deterministic.
+extern "C" void primme_b200_svds_dist_csr_matvec(void *x, int64_t *ldx, void *y, int64_t *ldy, int *blockSize,
+      int *transpose, struct primme_svds_params *primme_svds, int *ierr) {
+   pb200_ctx *ctx = primme_b200_solver_ctx(&primme_svds->primme);
+   if (!ctx) ctx = primme_b200_attached_ctx(&primme_svds->primme);
+   const primme_b200_svds_dist *op = (const primme_b200_svds_dist *)primme_svds->matrix;
+   if (!ctx || !op || !op->A || !op->At) {
+      *ierr = -1;
+      return;
+   }
+   *ierr = dist_spmm_any(ctx, *transpose ? op->At : op->A, x, *ldx, y, *ldy, *blockSize);
 }

@@ -24,7 +24,11 @@ namespace {
 constexpr int TILE = 256;  // rows per tile == threads per CTA
 constexpr int NWARP = TILE / 32;
 
+// tile visited at step `t` of a CTA's walk: every other sweep runs back to front (a.rev) so that it starts on
+// the rows the previous sweep left in the 126 MB L2
+#define PB_TILE(t) (a.rev ? ntiles - 1 - (t) : (t))
 struct SweepArgs {
+   int rev;
    const double *Q;
    const double *V;
    double *X;
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_kernel(SweepArgs
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
          pbtma::mbar_wait(&empty[s], ph ^ 1);
          double *dst = stage0 + (size_t)s * stage_sz;
-         const int r0 = (int)(tile * TR);
+         const int r0 = (int)(PB_TILE(tile) * TR);
          pbtma::mbar_arrive_expect_tx(&full[s], bytes);
          if (qpad > 0) pbtma::tensor_g2s_2d(dst, &maps.q, r0, 0, &full[s]);
          if (xcol0 > qpad) pbtma::tensor_g2s_2d(dst + qpad * S, &maps.v, r0, 0, &full[s]);
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_kernel(SweepArgs
          // the new rows go to global memory and to this warp's scratch ([column][row], stride
          // CS_LD): the Gram below takes its X operand from there (the stage itself is only ever
          // written by the TMA unit, so no proxy fence is needed before it is refilled)
-         const int64_t r = tile * TR + r0w + g;
+         const int64_t r = PB_TILE(tile) * TR + r0w + g;
          if (2 * t < a.b && r < a.n) a.X[r + (size_t)(2 * t) * a.ldx] = d0;
          if (2 * t + 1 < a.b && r < a.n) a.X[r + (size_t)(2 * t + 1) * a.ldx] = d1;
          xw[(2 * t) * CS_LD + g] = d0;
@@ -462,7 +466,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_exact_kernel(Swe
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
          pbtma::mbar_wait(&empty[s], ph ^ 1);
          double *dst = stage0 + (size_t)s * STAGE;
-         const int r0 = (int)(tile * TR);
+         const int r0 = (int)(PB_TILE(tile) * TR);
          pbtma::mbar_arrive_expect_tx(&full[s], (uint32_t)(STAGE * sizeof(double)));
          pbtma::tensor_g2s_2d(dst, &maps.v, r0, 0, &full[s]);
          pbtma::tensor_g2s_2d(dst + XC0 * S, &maps.x, r0, 0, &full[s]);
@@ -521,7 +525,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) ortho_sweep_mma_exact_kernel(Swe
             const double v0 = __shfl_sync(0xffffffffu, d0, src), v1 = __shfl_sync(0xffffffffu, d1, src);
             dmma884(y0, y1, (t & 1) ? v1 : v0, yfr1);
          }
-         const int64_t roff = tile * TR;
+         const int64_t roff = PB_TILE(tile) * TR;
          if (roff + r0w + g < a.n) {
             if (st0) gx0[roff] = y0;
             if (st1) gx1[roff] = y1;
@@ -792,6 +796,7 @@ static int sweep_once(pb200_ctx *ctx, int64_t n, const double *Q, int q, int64_t
    }
    int ps = pb_prof_begin(ctx, PB_K_ORTHO);
    if (mma_ok) {
+      a.rev = ctx->sweep_alternate ? (ctx->sweep_rev ^= 1) : 0;
       const int tr = 8 * nw;
       const int64_t ntiles = (n + tr - 1) / tr;  // a partial last tile is zero-filled by the TMA unit
       grid = (int)(ntiles < (int64_t)ctx->num_sms * ctas_per_sm ? ntiles : (int64_t)ctx->num_sms * ctas_per_sm);

@@ -67,6 +67,8 @@ struct pb200_ctx {
    int64_t launches;
    int use_tma_vwxr;      // same switch for the VWXR kernel alone
    int use_tma_spmm;      // persistent bulk-copy SpMM (v2)
+   int sweep_alternate;   // 1 (default): consecutive TMA sweeps walk the rows in opposite directions (L2 reuse)
+   int sweep_rev;         // direction of the last sweep
    int spmm_v3;           // gather layout for b >= 2: 0 column-major (v2), 1 row-major copy (v3), 2 timed once per matrix (default)
    int use_wide;          // v3 wide VWXR kernel for the restart sweep
    int use_mma_vwxr;      // tensor-map TMA + DMMA VWXR kernel (default)
@@ -244,6 +246,7 @@ struct pb200_csr {
    // row-major gather buffer of the v3 kernel: G[col][bp] = X(col, 0:b) (packed per call)
    double *d_G;
    size_t G_cap;  // doubles
+   int pooled;            // device arrays live in the context's matrix pool (not freed by pb200_csr_destroy)
    int layout_choice[4];  // per block width 1/2/4/8: 0 not timed yet, 1 column-major gathers (v2), 2 row-major (v3)
 };
 

@@ -702,105 +702,145 @@ __global__ void spmm_long_fixup3(const int64_t *__restrict__ lr_row, const int32
    else Y[lr_row[lr] + (size_t)c * ldy] = s;
 }
 
+// Device storage of one matrix: either one cudaMalloc per array (pb200_csr_create) or sub-allocations of
+// the context's matrix pool (pb200_csr_create_pooled: a caller that uploads a matrix per solve -- the
+// host-facing primme_b200_dprimme_csr -- then pays no cudaMalloc / cudaFree, which cost 0.01-1 s per call
+// on a busy driver)
+struct CsrAlloc {
+   char *base;
+   size_t off, cap;
+   int err;
+};
 template <typename T>
-int upload(pb200_ctx *ctx, const std::vector<T> &h, T **d) {
-   size_t bytes = sizeof(T) * (h.size() ? h.size() : 1);
-   PB_CUDA(cudaMalloc((void **)d, bytes));
-   if (h.size())
-      PB_CUDA(cudaMemcpyAsync(*d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
-   PB_CUDA(cudaStreamSynchronize(ctx->stream));
+T *csr_alloc(CsrAlloc &al, size_t count, size_t slack_bytes) {
+   const size_t bytes = ((sizeof(T) * (count ? count : 1) + slack_bytes) + 255) / 256 * 256;
+   if (al.base) {
+      if (al.off + bytes > al.cap) {
+         al.err = PB200_ERR_ALLOC;
+         return NULL;
+      }
+      T *p = reinterpret_cast<T *>(al.base + al.off);
+      al.off += bytes;
+      return p;
+   }
+   void *p = NULL;
+   if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      al.err = PB200_ERR_ALLOC;
+      return NULL;
+   }
+   return reinterpret_cast<T *>(p);
+}
+template <typename T>
+int csr_put(pb200_ctx *ctx, CsrAlloc &al, const T *h, size_t count, size_t slack_bytes, T **d) {
+   *d = csr_alloc<T>(al, count, slack_bytes);
+   if (!*d) return al.err ? al.err : PB200_ERR_ALLOC;
+   if (slack_bytes) PB_CUDA(cudaMemsetAsync(reinterpret_cast<char *>(*d) + sizeof(T) * count, 0, slack_bytes, ctx->stream));
+   if (count) PB_CUDA(cudaMemcpyAsync(*d, h, sizeof(T) * count, cudaMemcpyHostToDevice, ctx->stream));
    return 0;
 }
 
-// Build the row-block schedule from a 0-based host rowptr.
-int build_schedule(pb200_ctx *ctx, pb200_csr *A, const int64_t *rp) {
+// row-block schedule of a 0-based host rowptr (host side only)
+struct Sched {
    std::vector<int64_t> row0, nz0, lr_row;
    std::vector<int32_t> bnnz, kind, slot, lr_slot0, lr_nslots;
-   int nslots = 0;
+   int nslots, lpr;
+};
+void make_schedule(int64_t nrows, int64_t nnz, const int64_t *rp, Sched &S) {
+   S.nslots = 0;
    int64_t r = 0;
-   while (r < A->nrows) {
+   while (r < nrows) {
       int64_t len = rp[r + 1] - rp[r];
       if (len > SP_NNZ) {
-         lr_row.push_back(r);
-         lr_slot0.push_back(nslots);
+         S.lr_row.push_back(r);
+         S.lr_slot0.push_back(S.nslots);
          int nch = 0;
          for (int64_t p = rp[r]; p < rp[r + 1]; p += SP_NNZ) {
             int64_t e = p + SP_NNZ < rp[r + 1] ? p + SP_NNZ : rp[r + 1];
-            row0.push_back(r), nz0.push_back(p), bnnz.push_back((int32_t)(e - p));
-            kind.push_back(1), slot.push_back(nslots++);
+            S.row0.push_back(r), S.nz0.push_back(p), S.bnnz.push_back((int32_t)(e - p));
+            S.kind.push_back(1), S.slot.push_back(S.nslots++);
             nch++;
          }
-         lr_nslots.push_back(nch);
+         S.lr_nslots.push_back(nch);
          r++;
          continue;
       }
       int64_t r1 = r;
       int64_t cnt = 0;
-      while (r1 < A->nrows && r1 - r < SP_ROWS && (rp[r1 + 1] - rp[r1]) <= SP_NNZ &&
+      while (r1 < nrows && r1 - r < SP_ROWS && (rp[r1 + 1] - rp[r1]) <= SP_NNZ &&
              cnt + (rp[r1 + 1] - rp[r1]) <= SP_NNZ) {
          cnt += rp[r1 + 1] - rp[r1];
          r1++;
       }
-      row0.push_back(r), nz0.push_back(rp[r]), bnnz.push_back((int32_t)cnt);
-      kind.push_back(0), slot.push_back(-1);
+      S.row0.push_back(r), S.nz0.push_back(rp[r]), S.bnnz.push_back((int32_t)cnt);
+      S.kind.push_back(0), S.slot.push_back(-1);
       r = r1;
    }
-   row0.push_back(A->nrows);
-   // group blocks need blk_row0[blk+1] = next row: true for kind 0 followed by anything since
-   // long-row chunks repeat their own row id and the next group starts at row+1; patch chunks:
-   A->nblocks = (int)bnnz.size();
-   for (int i = 0; i < A->nblocks; i++)
-      if (kind[i] == 0 && i + 1 < A->nblocks && kind[i + 1] == 1) {
-         // next block is a long row chunk whose row0 is the first row after this group: fine
-      }
-   A->nlong = nslots;
-   A->nlongrows = (int)lr_row.size();
-   double mean = A->nrows > 0 ? (double)A->nnz / (double)A->nrows : 1.0;
-   int lpr = 1;
-   while (lpr < 32 && lpr * 4 <= mean) lpr *= 2;  // ~4+ nonzeros per lane
-   A->lpr = lpr;
-   PB_CHK(upload(ctx, row0, &A->d_blk_row0));
-   PB_CHK(upload(ctx, nz0, &A->d_blk_nz0));
-   PB_CHK(upload(ctx, bnnz, &A->d_blk_nnz));
-   PB_CHK(upload(ctx, kind, &A->d_blk_kind));
-   PB_CHK(upload(ctx, slot, &A->d_long_slot));
-   PB_CHK(upload(ctx, lr_row, &A->d_lr_row));
-   PB_CHK(upload(ctx, lr_slot0, &A->d_lr_slot0));
-   PB_CHK(upload(ctx, lr_nslots, &A->d_lr_nslots));
-   PB_CUDA(cudaMalloc((void **)&A->d_long_part, sizeof(double) * 16 * (nslots ? nslots : 1)));
-   return 0;
+   S.row0.push_back(nrows);  // blk_row0[blk + 1] of the last group
+   const double mean = nrows > 0 ? (double)nnz / (double)nrows : 1.0;
+   S.lpr = 1;
+   while (S.lpr < 32 && S.lpr * 4 <= mean) S.lpr *= 2;  // ~4+ nonzeros per lane
 }
 
 int csr_from_host(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
       const int64_t *rp0 /*0-based*/, const int32_t *ci0 /*0-based*/, const void *vals, int is_complex,
-      pb200_csr **out) {
+      pb200_csr **out, int pooled = 0) {
    pb200_csr *A = (pb200_csr *)calloc(1, sizeof(pb200_csr));
    if (!A) return PB200_ERR_ALLOC;
    A->nrows = nrows, A->ncols = ncols, A->nnz = nnz, A->is_complex = is_complex;
    const size_t vs = is_complex ? 16 : 8;
-   // 64 bytes of zeroed slack after each array: the bulk copies of the v2 kernel read aligned slices
-   PB_CUDA(cudaMalloc((void **)&A->d_rowptr, sizeof(int64_t) * (nrows + 1) + 64));
-   PB_CUDA(cudaMemsetAsync(A->d_rowptr, 0, sizeof(int64_t) * (nrows + 1) + 64, ctx->stream));
-   PB_CUDA(cudaMalloc((void **)&A->d_colind, sizeof(int32_t) * nnz + 64));
-   PB_CUDA(cudaMemsetAsync(A->d_colind, 0, sizeof(int32_t) * nnz + 64, ctx->stream));
-   PB_CUDA(cudaMalloc((void **)&A->d_vals, vs * nnz + 64));
-   PB_CUDA(cudaMemsetAsync(A->d_vals, 0, vs * nnz + 64, ctx->stream));
-   PB_CUDA(cudaMemcpyAsync(A->d_rowptr, rp0, sizeof(int64_t) * (nrows + 1), cudaMemcpyHostToDevice, ctx->stream));
-   if (nnz) {
-      PB_CUDA(cudaMemcpyAsync(A->d_colind, ci0, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, ctx->stream));
-      PB_CUDA(cudaMemcpyAsync(A->d_vals, vals, vs * nnz, cudaMemcpyHostToDevice, ctx->stream));
+   Sched S;
+   make_schedule(nrows, nnz, rp0, S);
+   A->nblocks = (int)S.bnnz.size();
+   A->nlong = S.nslots;
+   A->nlongrows = (int)S.lr_row.size();
+   A->lpr = S.lpr;
+   CsrAlloc al = {NULL, 0, 0, 0};
+   const size_t gdoubles = (size_t)(ncols > 0 ? ncols : 1) * 8 * (is_complex ? 2 : 1);
+   if (pooled) {
+      // exact size of everything below, each piece rounded to 256 bytes
+      auto rnd = [](size_t b) { return (b + 255) / 256 * 256; };
+      size_t tot = rnd(8 * (size_t)(nrows + 1) + 64) + rnd(4 * (size_t)(nnz ? nnz : 1) + 64) + rnd(vs * (size_t)(nnz ? nnz : 1) + 64);
+      tot += 2 * rnd(8 * (S.row0.size() + 1)) + 3 * rnd(4 * (S.bnnz.size() + 1));
+      tot += rnd(8 * (S.lr_row.size() + 1)) + 2 * rnd(4 * (S.lr_row.size() + 1));
+      tot += rnd(8 * 16 * (size_t)(S.nslots ? S.nslots : 1)) + rnd(8 * gdoubles) + 4096;
+      void *base = NULL;
+      PB_CHK(pb200_ctx_workspace(ctx, 3, tot, &base));
+      al.base = (char *)base, al.cap = tot;
+      A->pooled = 1;
    }
+   // 64 bytes of zeroed slack after each array: the bulk copies of the kernels read aligned slices
+   PB_CHK(csr_put(ctx, al, rp0, (size_t)nrows + 1, 64, &A->d_rowptr));
+   PB_CHK(csr_put(ctx, al, ci0, (size_t)nnz, 64, &A->d_colind));
+   if (is_complex) PB_CHK(csr_put(ctx, al, (const double2 *)vals, (size_t)nnz, 64, (double2 **)&A->d_vals));
+   else PB_CHK(csr_put(ctx, al, (const double *)vals, (size_t)nnz, 64, &A->d_vals));
+   PB_CHK(csr_put(ctx, al, S.row0.data(), S.row0.size(), 0, &A->d_blk_row0));
+   PB_CHK(csr_put(ctx, al, S.nz0.data(), S.nz0.size(), 0, &A->d_blk_nz0));
+   PB_CHK(csr_put(ctx, al, S.bnnz.data(), S.bnnz.size(), 0, &A->d_blk_nnz));
+   PB_CHK(csr_put(ctx, al, S.kind.data(), S.kind.size(), 0, &A->d_blk_kind));
+   PB_CHK(csr_put(ctx, al, S.slot.data(), S.slot.size(), 0, &A->d_long_slot));
+   PB_CHK(csr_put(ctx, al, S.lr_row.data(), S.lr_row.size(), 0, &A->d_lr_row));
+   PB_CHK(csr_put(ctx, al, S.lr_slot0.data(), S.lr_slot0.size(), 0, &A->d_lr_slot0));
+   PB_CHK(csr_put(ctx, al, S.lr_nslots.data(), S.lr_nslots.size(), 0, &A->d_lr_nslots));
+   A->d_long_part = csr_alloc<double>(al, 16 * (size_t)(S.nslots ? S.nslots : 1), 0);
+   if (!A->d_long_part) return PB200_ERR_ALLOC;
+   if (pooled) {
+      A->d_G = csr_alloc<double>(al, gdoubles, 0);
+      if (!A->d_G) return PB200_ERR_ALLOC;
+      A->G_cap = gdoubles;
+   }
+   // the host vectors of the schedule die with this frame: everything must have left them
    PB_CUDA(cudaStreamSynchronize(ctx->stream));
-   PB_CHK(build_schedule(ctx, A, rp0));
    *out = A;
    return 0;
 }
 
 }  // namespace
 
-extern "C" int pb200_csr_create(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
-      const int64_t *rowptr_host, const int32_t *colind_host, const void *vals_host,
-      int index_base, int is_complex, pb200_csr **out) {
+static int csr_create_any(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz, const int64_t *rowptr_host,
+      const int32_t *colind_host, const void *vals_host, int index_base, int is_complex, pb200_csr **out, int pooled) {
+   if (index_base == 0)  // the common case: no host copy of the structure at all
+      return csr_from_host(ctx, nrows, ncols, nnz, rowptr_host, colind_host, vals_host, is_complex ? 1 : 0, out, pooled);
    std::vector<int64_t> rp(nrows + 1);
    for (int64_t i = 0; i <= nrows; i++) rp[i] = rowptr_host[i] - index_base;
    const int32_t *ci = colind_host;
@@ -811,14 +851,31 @@ extern "C" int pb200_csr_create(pb200_ctx *ctx, int64_t nrows, int64_t ncols, in
       ci = ci0.data();
    }
    // keep a host copy of the 0-based structure for the optional transpose
-   int rc = csr_from_host(ctx, nrows, ncols, nnz, rp.data(), ci, vals_host, is_complex ? 1 : 0, out);
+   int rc = csr_from_host(ctx, nrows, ncols, nnz, rp.data(), ci, vals_host, is_complex ? 1 : 0, out, pooled);
    return rc;
+}
+
+extern "C" int pb200_csr_create(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
+      const int64_t *rowptr_host, const int32_t *colind_host, const void *vals_host,
+      int index_base, int is_complex, pb200_csr **out) {
+   return csr_create_any(ctx, nrows, ncols, nnz, rowptr_host, colind_host, vals_host, index_base, is_complex, out, 0);
+}
+// Same, with the device arrays taken from the context's matrix pool (workspace slot 3): valid until the
+// next pooled create on this context; pb200_csr_destroy then releases the host handle only.
+extern "C" int pb200_csr_create_pooled(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
+      const int64_t *rowptr_host, const int32_t *colind_host, const void *vals_host,
+      int index_base, int is_complex, pb200_csr **out) {
+   return csr_create_any(ctx, nrows, ncols, nnz, rowptr_host, colind_host, vals_host, index_base, is_complex, out, 1);
 }
 
 extern "C" int pb200_csr_destroy(pb200_ctx *ctx, pb200_csr *A) {
    if (!A) return 0;
    if (ctx) cudaStreamSynchronize(ctx->stream);
    if (A->T) pb200_csr_destroy(ctx, A->T);
+   if (A->pooled) {
+      free(A);
+      return 0;
+   }
    cudaFree(A->d_rowptr), cudaFree(A->d_colind), cudaFree(A->d_vals);
    cudaFree(A->d_blk_row0), cudaFree(A->d_blk_nz0), cudaFree(A->d_blk_nnz), cudaFree(A->d_blk_kind);
    cudaFree(A->d_long_slot), cudaFree(A->d_long_part);

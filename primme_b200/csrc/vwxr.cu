@@ -24,7 +24,9 @@ namespace {
 
 constexpr int VT = 128;  // threads per CTA == rows per tile
 
+#define PB_TILE(t) (a.rev ? ntiles - 1 - (t) : (t))  // see ortho_sweep.cu
 struct VwxrArgs {
+   int rev;
    const double *V;
    const double *W;
    int64_t n, ld;
@@ -562,7 +564,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) vwxr_mma_kernel(VwxrArgs a, cons
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
          pbtma::mbar_wait(&empty[s], ph ^ 1);
          double *dst = stage0 + (size_t)s * stage_sz;
-         const int r0 = (int)(tile * TR);
+         const int r0 = (int)(PB_TILE(tile) * TR);
          pbtma::mbar_arrive_expect_tx(&full[s], bytes);
          pbtma::tensor_g2s_2d(dst, &maps.v, r0, 0, &full[s]);
          pbtma::tensor_g2s_2d(dst + mpad * S, &maps.w, r0, 0, &full[s]);
@@ -665,7 +667,7 @@ __global__ void __launch_bounds__(NW * 32 + 32) vwxr_mma_kernel(VwxrArgs a, cons
          if (lane == 0) pbtma::mbar_arrive(&empty[s]);
       }
       // ---- residuals, norms, scatter (fragment layout: row g, columns 8 i + 2 t + j) ----
-      const int64_t r = tile * TR + r0w + g;
+      const int64_t r = PB_TILE(tile) * TR + r0w + g;
       const bool rok = r < a.n;
       if (!slow) {
 #pragma unroll
@@ -999,6 +1001,7 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
 
    int grid = 1, ppc = 1, rc = 0;
    if (mma_nt8) {
+      a.rev = ctx->sweep_alternate ? (ctx->sweep_rev ^= 1) : 0;
       const int tr = 8 * mma_nw;
       const int64_t ntiles = (n + tr - 1) / tr;
       grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);

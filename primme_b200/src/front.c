@@ -431,6 +431,7 @@ static int solve_typed(double *evals, SCALAR *evecs, double *resNorms, primme_pa
       return -31;
    }
    pb_registry_set_solver(primme, S->dev);
+   pb200_ctx_begin_solve(S->dev);
 
    S->n = primme->nLocal;
    S->ld = ld_default ? (primme->nLocal + 15) / 16 * 16 : primme->ldOPs;

@@ -145,11 +145,16 @@ static int solve_csr(double *evals, void *evecs_host, double *resNorms, primme_p
    pb200_csr *A = NULL;
    void *devecs = NULL;
    const double tc0 = hl_wtime();
-   rc = pb200_csr_create(ctx, n, primme->n, nnz, rowptr_host, colind_host, vals_host, index_base, is_complex, &A);
+   /* a caller-attached (long-lived) context keeps the device storage of the matrix and of the eigenvectors
+    * between calls: no cudaMalloc / cudaFree inside an end-to-end solve */
+   rc = own ? pb200_csr_create(ctx, n, primme->n, nnz, rowptr_host, colind_host, vals_host, index_base, is_complex, &A)
+            : pb200_csr_create_pooled(ctx, n, primme->n, nnz, rowptr_host, colind_host, vals_host, index_base, is_complex, &A);
    const double tc1 = hl_wtime();
    const int ncols = primme->numOrthoConst + PB_MAX(primme->numEvals, primme->initSize);
    const int64_t ldh = primme->ldevecs > 0 ? primme->ldevecs : n;
-   if (!rc) rc = pb200_malloc(ctx, (size_t)es * (size_t)PB_MAX(n, 1) * PB_MAX(ncols, 1), &devecs);
+   if (!rc)
+      rc = own ? pb200_malloc(ctx, (size_t)es * (size_t)PB_MAX(n, 1) * PB_MAX(ncols, 1), &devecs)
+               : pb200_ctx_workspace(ctx, 2, (size_t)es * (size_t)PB_MAX(n, 1) * PB_MAX(ncols, 1), &devecs);
    if (!rc && primme->numOrthoConst + primme->initSize > 0)
       rc = pb200_copy_h2d(ctx, evecs_host, ldh, devecs, n, n, primme->numOrthoConst + primme->initSize, es);
    if (!rc) {
@@ -173,7 +178,7 @@ static int solve_csr(double *evals, void *evecs_host, double *resNorms, primme_p
       }
    }
    const double tc2 = hl_wtime();
-   if (devecs) pb200_free(ctx, devecs);
+   if (devecs && own) pb200_free(ctx, devecs);
    if (A) pb200_csr_destroy(ctx, A);
    if (getenv("PB200_DEBUG"))
       fprintf(stderr, "PRIMME-B200: dprimme_csr (s): csr upload+schedule %.4f, solve+download %.4f, release %.4f\n",

@@ -923,7 +923,12 @@ static int svds_check_input(void *svals, void *svecs, void *resNorms, primme_svd
    if (s->numProcs < 1) return -6;
    if (!s->matrixMatvec) return -7;
    if (!s->applyPreconditioner && s->precondition == 1) return -8;
-   if (s->numProcs > 1 && !s->globalSumReal) return -9;
+   /* the sums of a row-partitioned run: the user's callback, or the communicator of the attached kernel
+    * context (every device panel is then all-reduced by the kernel that produces it) */
+   if (s->numProcs > 1 && !s->globalSumReal) {
+      pb200_ctx *c = primme_b200_attached_ctx(&s->primme);
+      if (!c || pb200_ctx_nranks(c) <= 1) return -9;
+   }
    if (s->numSvals > PB_MIN(s->n, s->m)) return -10;
    if (s->numSvals < 1) return -11;
    if (s->target != primme_svds_smallest && s->target != primme_svds_largest && s->target != primme_svds_closest_abs)

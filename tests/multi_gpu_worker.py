@@ -116,6 +116,83 @@ def dist_spmm_check(lib, ctx, csr, rank, world, counts, lo, hi, complex_vals=Fal
     return dict(err=worst, nhalo=nh.value, sent=sent.value, peer_halo=peer.value)
 
 
+def svds_dist_check(lib, api, ctx, rank, world, m=30000, n=9000, per_row=8, k=5, eps=1e-9):
+    """Row-partitioned cublas_dprimme_svds with the built-in operator (config C4's layout): rank r owns rows
+    [m-range r] of A and rows [n-range r] of A^T; normal equations, GD_Olsen_plusK.  Returns on rank 0 the
+    singular values, those of a sparse SVD of the whole matrix, the triplet residuals and orthogonality."""
+    import torch
+    import torch.distributed as dist
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    import svds_harness as S
+    from primme_b200 import matrices as M
+    S.declare(lib)
+    ip, ix, da = M.random_rectangular(m, n, per_row=per_row, seed=2024)
+    As = sp.csr_matrix((da, ix, ip), shape=(m, n))
+    At = As.T.tocsr()
+    At.sort_indices()
+    mc = np.array([m * (r + 1) // world - m * r // world for r in range(world)], dtype=np.int64)
+    nc = np.array([n * (r + 1) // world - n * r // world for r in range(world)], dtype=np.int64)
+    mlo, nlo = int(mc[:rank].sum()), int(nc[:rank].sum())
+    mloc, nloc = int(mc[rank]), int(nc[rank])
+
+    def shard(mat, lo, cnt, ncols_global, counts):
+        sub = mat[lo:lo + cnt]
+        rp = np.ascontiguousarray(sub.indptr, dtype=np.int64)
+        ci = np.ascontiguousarray(sub.indices, dtype=np.int32)
+        va = np.ascontiguousarray(sub.data, dtype=np.float64)
+        A, D = C.c_void_p(), C.c_void_p()
+        assert lib.pb200_csr_create(ctx, cnt, ncols_global, len(ci), rp.ctypes.data, ci.ctypes.data, va.ctypes.data, 0, 0, C.byref(A)) == 0
+        assert lib.pb200_dist_csr_create(ctx, A, counts.ctypes.data, world, C.byref(D)) == 0
+        return A, D
+
+    A1, D1 = shard(As, mlo, mloc, n, nc)     # y = A x: x partitioned like the right vectors
+    A2, D2 = shard(At, nlo, nloc, m, mc)     # y = A^T x: x partitioned like the left vectors
+
+    class Op(C.Structure):
+        _fields_ = [("A", C.c_void_p), ("At", C.c_void_p)]
+
+    op = Op(D1.value, D2.value)
+    p = lib.primme_svds_params_create()
+    for name, v in (("m", m), ("n", n), ("mLocal", mloc), ("nLocal", nloc), ("numProcs", world), ("procID", rank),
+                    ("numSvals", k), ("target", S.primme_svds_largest), ("printLevel", 0), ("eps", eps), ("maxBlockSize", 2),
+                    ("matrix", C.addressof(op)),
+                    ("matrixMatvec", C.cast(lib.primme_b200_svds_dist_csr_matvec, C.c_void_p).value)):
+        S.set_member(lib, p, name, v)
+    assert lib.primme_svds_set_method(S.primme_svds_normalequations, api.PRIMME_GD_Olsen_plusK, api.PRIMME_GD_Olsen_plusK, p) == 0
+    inner = S.get_member(lib, p, "primme")
+    inner_p = C.cast(C.c_void_p(inner), C.POINTER(api.PrimmeParams))
+    lib.primme_b200_attach_ctx(inner_p, ctx)
+    dsvecs = C.c_void_p()
+    assert lib.pb200_malloc(ctx, 8 * (mloc + nloc) * k, C.byref(dsvecs)) == 0
+    svals, rn = np.zeros(k), np.zeros(k)
+    rc = lib.cublas_dprimme_svds(svals.ctypes.data, dsvecs, rn.ctypes.data, p)
+    kk = S.get_member(lib, p, "initSize")
+    host = np.zeros((mloc + nloc) * k)
+    assert lib.pb200_copy_d2h(ctx, dsvecs, (mloc + nloc) * k, host.ctypes.data, (mloc + nloc) * k, (mloc + nloc) * k, 1, 8) == 0
+    U = torch.from_numpy(host[: mloc * k].reshape(k, mloc).copy())
+    V = torch.from_numpy(host[mloc * k:].reshape(k, nloc).copy())
+    Us = [torch.empty((k, int(c)), dtype=torch.float64) for c in mc]
+    Vs = [torch.empty((k, int(c)), dtype=torch.float64) for c in nc]
+    dist.all_gather(Us, U)
+    dist.all_gather(Vs, V)
+    out = None
+    if rank == 0:
+        Uf, Vf = torch.cat(Us, dim=1).numpy().T, torch.cat(Vs, dim=1).numpy().T
+        want = np.sort(spl.svds(As, k=k, which="LM", tol=1e-12, return_singular_vectors=False))[::-1]
+        out = dict(rc=rc, initSize=kk, svals=np.sort(svals)[::-1].tolist(), exact=want.tolist(),
+                   res=float(np.linalg.norm(As @ Vf - Uf * svals, axis=0).max() / want[0]),
+                   orthU=float(np.abs(Uf.T @ Uf - np.eye(k)).max()), orthV=float(np.abs(Vf.T @ Vf - np.eye(k)).max()),
+                   matvecs=S.get_member(lib, p, "stats_numMatvecs"))
+    lib.primme_b200_attach_ctx(inner_p, None)
+    lib.pb200_free(ctx, dsvecs)
+    lib.primme_svds_params_destroy(p)
+    for A_, D_ in ((A1, D1), (A2, D2)):
+        lib.pb200_dist_csr_destroy(ctx, D_)
+        lib.pb200_csr_destroy(ctx, A_)
+    return out
+
+
 def sharded_solve(lib, api, ctx, D, n, nloc, rank, world, devecs, evals, rn, **workload):
     p = api.new_params(lib, n, numProcs=world, procID=rank, nLocal=nloc, **workload)
     assert lib.primme_set_method(api.PRIMME_GD_Olsen_plusK, C.byref(p)) == 0
@@ -153,6 +230,7 @@ def main():
                                 complex_vals=True, bs=(1, 3, 8))
     errs = torch.tensor([spmm_real["err"], spmm_cplx["err"]], dtype=torch.float64)
     dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    svds = svds_dist_check(lib, api, ctx, rank, world) if os.environ.get("PB_BS", "4") == "4" else None
     k = 6
     devecs = C.c_void_p()
     assert lib.pb200_malloc(ctx, 8 * max(nloc, 1) * k, C.byref(devecs)) == 0
@@ -174,7 +252,7 @@ def main():
                                           orth=float(np.abs(Xf.T @ Xf - np.eye(k)).max()),
                                           matvecs=p.stats.numMatvecs, launches=lib.pb200_ctx_launches(ctx),
                                           peer_exchange=lib.pb200_ctx_peer_active(ctx),
-                                          spmm_err=errs.tolist(), spmm_halo=spmm_real)))
+                                          spmm_err=errs.tolist(), spmm_halo=spmm_real, svds=svds)))
     lib.pb200_free(ctx, devecs)
     lib.pb200_dist_csr_destroy(ctx, D)
     lib.pb200_csr_destroy(ctx, A)

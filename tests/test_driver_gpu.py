@@ -47,6 +47,22 @@ def test_reference_driver_passes_its_own_checks(cfg):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+DRIVER_Z = os.path.join(ROOT, "oracle", "_ref", "driver", "primme_doublecomplex_b200")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", ["test_101", "test_102", "test_103", "test_104", "test_105", "test_106"])
+def test_reference_complex_driver_passes_its_own_checks(cfg):
+    """tests/driver.c compiled UNCHANGED with -DUSE_DOUBLECOMPLEX: the reference's six complex Hermitian
+    configurations (mhd1280b.mtx) through zprimme on the GPU -- GD_Olsen_plusK with locking and a large basis
+    (101), a basis of 3 (102), 50 pairs with soft locking (103), DEFAULT_MIN_TIME interior (104), Jacobi
+    preconditioner interior (105) and largest (106); check_solution against the stored sol_10N_doublecomplex"""
+    if not os.path.exists(DRIVER_Z):
+        pytest.skip("driver binary not built (needs the reference tree at build time)")
+    r = run(cfg, DRIVER_Z)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 def test_reference_driver_links_against_the_product():
     """CPU-side: the unchanged driver links (every reference-internal symbol it needs is exported)
     and, without a GPU, the product refuses to run instead of computing on the host"""

@@ -351,6 +351,9 @@ def test_panel_reduction_is_reproducible(libs):
     P1 = np.zeros((b, mv + b))
     P2 = np.zeros((b, mv + b))
     for P in (P1, P2):
+        # consecutive sweeps walk the rows in opposite directions (L2 reuse); a solve always starts forward
+        lib.pb200_ctx_begin_solve.argtypes = [C.c_void_p]
+        assert lib.pb200_ctx_begin_solve(d.ctx) == 0
         assert lib.pb200_dortho_sweep(d.ctx, n, None, 0, n, dV, mv, n, off(dV, 8 * n * mv), b, n, None, 0, None, 0, 1,
                                       P.ctypes.data, mv + b) == 0
     d.close()

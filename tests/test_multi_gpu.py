@@ -35,6 +35,12 @@ def test_two_gpu_row_sharded_solve(bs):
     # compacted halo pushed over peer memory: power-law SpMM (real and complex) exact to rounding
     assert max(out["spmm_err"]) < 1e-13 and out["spmm_halo"]["peer_halo"] == 1
     assert 0 < out["spmm_halo"]["nhalo"] < 30011
+    if out.get("svds"):
+        # config C4's layout: row-partitioned cublas_dprimme_svds (normal equations) with the built-in operator
+        sv = out["svds"]
+        assert sv["rc"] == 0 and sv["initSize"] == 5
+        assert np.allclose(sv["svals"], sv["exact"], rtol=1e-9)
+        assert sv["res"] < 1e-7 and sv["orthV"] < 1e-8 and sv["orthU"] < 1e-6
     shape = (32, 29, 37)
     lam = [2 - 2 * np.cos(np.pi * np.arange(1, s + 1) / (s + 1)) for s in shape]
     exact = np.sort((lam[0][:, None, None] + lam[1][None, :, None] + lam[2][None, None, :]).ravel())[:6]

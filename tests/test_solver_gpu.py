@@ -10,12 +10,18 @@ from golden.cases import CASES
 pytestmark = pytest.mark.gpu
 
 
+# Cases whose outer-iteration / restart / matvec counts on the GPU are NOT identical to the reference's although
+# the fixture marks them exact for the CPU kernels (different summation order in the panels): they must still be
+# within 5 %.  Every other `exact_counts` case is asserted IDENTICAL on the GPU.
+GPU_CLOSE = set()
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_product_matches_reference_fixture(name):
     r = SC.run_case("product", name)
-    got, want = SC.check_against_golden(name, r, counts="close")
+    got, want = SC.check_against_golden(name, r, counts="close" if name in GPU_CLOSE else "exact")
     assert r["launches"] > 0  # the CUDA path did the work
-    print(name, "counts", got, "reference", want)
+    print(name, "counts", got, "reference", want, "IDENTICAL" if got == want else "deviation")
 
 
 def test_c2_full_size_properties():

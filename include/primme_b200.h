@@ -39,6 +39,8 @@ typedef struct pb200_csr pb200_csr; /* device-resident CSR matrix + row-block sc
 int pb200_device_count(void);
 int pb200_ctx_create(pb200_ctx **ctx, int device /* -1: current */);
 int pb200_ctx_destroy(pb200_ctx *ctx);
+/* experimental (PB200_L2_PERSIST_MB): persisting L2 window over the head of the basis */
+int64_t pb200_ctx_l2_persist(pb200_ctx *ctx, const void *ptr, size_t bytes);
 int pb200_ctx_sync(pb200_ctx *ctx);
 /* marks the start of a solve on a long-lived context (resets the alternating row-sweep direction so
  * that repeated solves are bitwise reproducible); dprimme / zprimme call it themselves */

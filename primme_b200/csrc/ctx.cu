@@ -92,6 +92,52 @@ extern "C" int pb200_ctx_begin_solve(pb200_ctx *ctx) {
    return 0;
 }
 
+// Keep the head of the basis resident in L2 across sweeps: every panel kernel re-reads V(:,0:m) from its
+// first column on, so the leading `bytes` of the array (whole columns) are given a persisting access-policy
+// window on the context's stream.  bytes == 0 removes the window.  Returns the number of bytes actually set
+// aside (0: not supported / switched off with PB200_L2_PERSIST_MB=0).
+extern "C" int64_t pb200_ctx_l2_persist(pb200_ctx *ctx, const void *ptr, size_t bytes) {
+   static int max_persist = -1, max_window = -1;
+   if (max_persist < 0) {
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+      if (getenv("PB200_DEBUG"))
+         fprintf(stderr, "primme_b200: L2 persisting max %d MB, access-policy window max %d MB\n", max_persist >> 20,
+               max_window >> 20);
+   }
+   size_t want = getenv("PB200_L2_PERSIST_MB") ? (size_t)atoi(getenv("PB200_L2_PERSIST_MB")) << 20 : 0;
+   if (bytes == 0 || !ptr) want = 0;
+   if (want > bytes) want = bytes;
+   if (want > (size_t)max_persist) want = (size_t)max_persist;
+   if (want > (size_t)max_window) want = (size_t)max_window;
+   cudaStreamAttrValue attr;
+   memset(&attr, 0, sizeof(attr));
+   if (want == 0) {
+      if (!ctx->l2_window) return 0;
+      attr.accessPolicyWindow.num_bytes = 0;
+      cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaCtxResetPersistingL2Cache();
+      ctx->l2_window = 0;
+      cudaGetLastError();
+      return 0;
+   }
+   if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+   }
+   attr.accessPolicyWindow.base_ptr = const_cast<void *>(ptr);
+   attr.accessPolicyWindow.num_bytes = want;
+   attr.accessPolicyWindow.hitRatio = 1.0f;
+   attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+   attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+   if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+   }
+   ctx->l2_window = 1;
+   return (int64_t)want;
+}
+
 extern "C" int pb200_ctx_sync(pb200_ctx *ctx) {
    PB_CUDA(cudaStreamSynchronize(ctx->stream));
    return 0;

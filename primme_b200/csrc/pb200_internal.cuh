@@ -67,6 +67,7 @@ struct pb200_ctx {
    int64_t launches;
    int use_tma_vwxr;      // same switch for the VWXR kernel alone
    int use_tma_spmm;      // persistent bulk-copy SpMM (v2)
+   int l2_window;         // a persisting access-policy window is set on the stream
    int sweep_alternate;   // 1 (default): consecutive TMA sweeps walk the rows in opposite directions (L2 reuse)
    int sweep_rev;         // direction of the last sweep
    int spmm_v3;           // gather layout for b >= 2: 0 column-major (v2), 1 row-major copy (v3), 2 timed once per matrix (default)

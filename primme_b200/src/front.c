@@ -449,6 +449,7 @@ static int solve_typed(double *evals, SCALAR *evecs, double *resNorms, primme_pa
       rc = pb200_ctx_workspace(S->dev, 0, basis_bytes, (void **)&S->V);
       if (!rc) rc = pb200_ctx_workspace(S->dev, 1, basis_bytes, (void **)&S->W);
    }
+   if (!rc && getenv("PB200_L2_PERSIST_MB")) pb200_ctx_l2_persist(S->dev, S->V, basis_bytes);
    int own_evecs = 0;
    if (!rc) {
       if (device_mode) {

@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--c5-n", type=int, default=10**7,
                     help="rows of the power-law matrix of config C5 reported in the `c5` block (0: skip)")
     ap.add_argument("--c5-steps", type=int, default=2)
+    ap.add_argument("--c4-m", type=int, default=10**6,
+                    help="rows of the rectangular matrix of config C4 (columns = 2/5 of it), `c4` block at N <= 2 (0: skip)")
+    ap.add_argument("--c4-max-matvecs", type=int, default=4000)
     ap.add_argument("--c3-n", type=int, default=500000,
                     help="rows of the complex Hermitian matrix of config C3 reported in the `c3` block at N=1 (0: skip)")
     ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
@@ -282,6 +285,95 @@ def run_c5(args, lib, api, M, ctx, rank, world, dist):
     if world > 1:
         lib.pb200_dist_csr_destroy(ctx, D)
     lib.pb200_csr_destroy(ctx, A)
+    return out
+
+
+def run_c4(args, lib, api, M, ctx, rank, world, dist):
+    """Config C4 (BASELINE.json configs[3]): dprimme_svds, rectangular CSR 10^6 x 4*10^5, nnz 2*10^7, 10 largest
+    singular values, primme_svds_normalequations (stage 1 pinned to GD_Olsen_plusK), eps 1e-8,
+    rows of A and of A^T partitioned over the ranks (named on 2 GPUs), built-in device operator."""
+    import torch
+    import scipy.sparse as sp
+    import svds_harness as S
+    S.declare(lib)
+    m, n, k = args.c4_m, args.c4_m * 2 // 5, 10
+    t0 = time.perf_counter()
+    ip, ix, da = M.random_rectangular(m, n, per_row=20, seed=2024)
+    As = sp.csr_matrix((da, ix, ip), shape=(m, n))
+    At = As.T.tocsr()
+    At.sort_indices()
+    t_gen = time.perf_counter() - t0
+    mc = np.array([m * (r + 1) // world - m * r // world for r in range(world)], dtype=np.int64)
+    nc = np.array([n * (r + 1) // world - n * r // world for r in range(world)], dtype=np.int64)
+    mlo, nlo, mloc, nloc = int(mc[:rank].sum()), int(nc[:rank].sum()), int(mc[rank]), int(nc[rank])
+    keep = []
+
+    def shard(mat, lo, cnt, ncols_global, counts):
+        sub = mat[lo:lo + cnt]
+        rp = np.ascontiguousarray(sub.indptr, dtype=np.int64)
+        ci = np.ascontiguousarray(sub.indices, dtype=np.int32)
+        va = np.ascontiguousarray(sub.data, dtype=np.float64)
+        A, D = C.c_void_p(), C.c_void_p()
+        assert lib.pb200_csr_create(ctx, cnt, ncols_global, len(ci), rp.ctypes.data, ci.ctypes.data, va.ctypes.data, 0, 0, C.byref(A)) == 0
+        assert lib.pb200_dist_csr_create(ctx, A, counts.ctypes.data, world, C.byref(D)) == 0
+        keep.append((A, D))
+        return D
+
+    class Op(C.Structure):
+        _fields_ = [("A", C.c_void_p), ("At", C.c_void_p)]
+
+    import multi_gpu_worker as MG
+    MG.declare(lib)
+    op = Op(shard(As, mlo, mloc, n, nc).value, shard(At, nlo, nloc, m, mc).value)
+    nnz = int(As.nnz)
+    del As, At
+    dsvecs = C.c_void_p()
+    assert lib.pb200_malloc(ctx, 8 * (mloc + nloc) * k, C.byref(dsvecs)) == 0
+    svals, rn = np.zeros(k), np.zeros(k)
+
+    def solve():
+        p = lib.primme_svds_params_create()
+        for name, v in (("m", m), ("n", n), ("mLocal", mloc), ("nLocal", nloc), ("numProcs", world), ("procID", rank),
+                        ("numSvals", k), ("target", S.primme_svds_largest), ("printLevel", 0), ("eps", 1e-8),
+                        ("maxBlockSize", 4), ("maxMatvecs", args.c4_max_matvecs), ("matrix", C.addressof(op)),
+                        ("matrixMatvec", C.cast(lib.primme_b200_svds_dist_csr_matvec, C.c_void_p).value)):
+            S.set_member(lib, p, name, v)
+        assert lib.primme_svds_set_method(S.primme_svds_normalequations, api.PRIMME_GD_Olsen_plusK, api.PRIMME_GD_Olsen_plusK, p) == 0
+        inner_p = C.cast(C.c_void_p(S.get_member(lib, p, "primme")), C.POINTER(api.PrimmeParams))
+        lib.primme_b200_attach_ctx(inner_p, ctx)
+        rc = lib.cublas_dprimme_svds(svals.ctypes.data, dsvecs, rn.ctypes.data, p)
+        out = dict(rc=rc, converged=S.get_member(lib, p, "initSize"), matvecs=S.get_member(lib, p, "stats_numMatvecs"),
+                   outer=S.get_member(lib, p, "stats_numOuterIterations"))
+        lib.primme_b200_attach_ctx(inner_p, None)
+        lib.primme_svds_params_destroy(p)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    solve()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    r = solve()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    out = {"workload": f"cublas_dprimme_svds rectangular CSR {m}x{n}, 10 largest, normal equations, GD_Olsen_plusK block 4, eps=1e-8",
+           "m": m, "n": n, "nnz": nnz, "n_gpus": world, "ms_per_solve": ms, "operator_applications": r["matvecs"],
+           "applications_per_s": r["matvecs"] / (ms * 1e-3), "outer_iterations": r["outer"], "rc": r["rc"],
+           "converged": r["converged"], "max_matvecs": args.c4_max_matvecs,
+           "svals": [float(x) for x in np.sort(svals)[::-1]], "max_resnorm": float(rn.max()), "generate_s_rank0": round(t_gen, 1)}
+    lib.pb200_free(ctx, dsvecs)
+    for A_, D_ in keep:
+        lib.pb200_dist_csr_destroy(ctx, D_)
+        lib.pb200_csr_destroy(ctx, A_)
     return out
 
 
@@ -584,6 +676,13 @@ def main():
         except Exception as e:
             c3 = {"error": repr(e)}
 
+    c4 = None
+    if args.c4_m > 0 and world <= 2 and (sharded or world == 1):
+        try:
+            c4 = run_c4(args, lib, api, M, ctx, rank, world, dist if world > 1 else None)
+        except Exception as e:
+            c4 = {"error": repr(e)}
+
     if rank == 0:
         line = {"metric": "matvecs_per_s", "value": value, "unit": "matvecs/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -601,7 +700,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "matvecs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e / max(1, min(args.steps, 3))},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "c5": c5, "c3": c3}
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "c5": c5, "c3": c3, "c4": c4}
         print(json.dumps(line))
 
     lib.pb200_free(ctx, devecs)

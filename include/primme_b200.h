@@ -39,7 +39,8 @@ typedef struct pb200_csr pb200_csr; /* device-resident CSR matrix + row-block sc
 int pb200_device_count(void);
 int pb200_ctx_create(pb200_ctx **ctx, int device /* -1: current */);
 int pb200_ctx_destroy(pb200_ctx *ctx);
-/* experimental (PB200_L2_PERSIST_MB): persisting L2 window over the head of the basis */
+/* persisting L2 window over the head of a basis array of `bytes` bytes that every sweep re-reads (0 bytes:
+ * remove it); dprimme / zprimme set it for V during a solve when the basis exceeds the L2 */
 int64_t pb200_ctx_l2_persist(pb200_ctx *ctx, const void *ptr, size_t bytes);
 int pb200_ctx_sync(pb200_ctx *ctx);
 /* marks the start of a solve on a long-lived context (resets the alternating row-sweep direction so
@@ -221,6 +222,12 @@ int pb200_dcolumn_dots(pb200_ctx *ctx, int64_t n, const double *X, int64_t ldx,
 /* W(:,j) -= theta[j] V(:,j); out[j] = ||W(:,j)||^2   (verify_norms, main_iter.c:1864-1881) */
 int pb200_dresidual_inplace(pb200_ctx *ctx, int64_t n, const double *theta_host,
       const double *V, int64_t ldv, double *W, int64_t ldw, int ncols, double *out_host);
+/* solution update of one QMR step in one pass (reference src/eigs/inner_solve.c:384-413):
+ * Delta(:,j) = gamma[j] Delta(:,j) + eta[j] D(:,j);  Sol(:,j) += Delta(:,j);  dots_host[j] = |Sol(:,j)|^2
+ * when dots_host != NULL.  Same roundings as scale + axpy + axpy + dot. */
+int pb200_dqmr_update(pb200_ctx *ctx, int64_t n, const double *gamma_host, const double *eta_host,
+      const double *D, int64_t ldd, double *Delta, int64_t ldl, double *Sol, int64_t lds, int ncols,
+      double *dots_host);
 /* y = x ./ (d - shift_j) style Jacobi preconditioner on a block (tests/COMMON/mat.c:137-165):
  * Y(:,j) = X(:,j) ./ safeguard(diag - shifts[j]) */
 int pb200_djacobi(pb200_ctx *ctx, int64_t n, const double *diag, const double *shifts_host,
@@ -253,6 +260,9 @@ int pb200_zresidual_inplace(pb200_ctx *ctx, int64_t n, const double *theta_host,
       void *W, int64_t ldw, int ncols, double *out_host);
 int pb200_zjacobi(pb200_ctx *ctx, int64_t n, const double *diag, const double *shifts_host, double minabs,
       const void *X, int64_t ldx, void *Y, int64_t ldy, int ncols);
+/* gamma, eta real (the recurrences of the inner solver are real in every precision) */
+int pb200_zqmr_update(pb200_ctx *ctx, int64_t n, const double *gamma_host, const double *eta_host, const void *D,
+      int64_t ldd, void *Delta, int64_t ldl, void *Sol, int64_t lds, int ncols, double *dots_host);
 /* 1 when the matrix holds complex values */
 int pb200_csr_is_complex(const pb200_csr *A);
 

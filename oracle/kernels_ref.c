@@ -433,3 +433,22 @@ int pb200_djacobi(pb200_ctx *ctx, int64_t n, const double *diag, const double *s
    }
    return 0;
 }
+
+/* restates the solution update of one QMR step (src/eigs/inner_solve.c:384-413) */
+int pb200_dqmr_update(pb200_ctx *ctx, int64_t n, const double *gamma, const double *eta, const double *D, int64_t ldd,
+      double *Delta, int64_t ldl, double *Sol, int64_t lds, int ncols, double *dots) {
+   ctx->launches++;
+   for (int j = 0; j < ncols; j++) {
+      double s2 = 0.0;
+      for (int64_t r = 0; r < n; r++) {
+         double t = Delta[r + (size_t)j * ldl] * gamma[j];
+         t += eta[j] * D[r + (size_t)j * ldd];
+         Delta[r + (size_t)j * ldl] = t;
+         const double s = Sol[r + (size_t)j * lds] + t;
+         Sol[r + (size_t)j * lds] = s;
+         s2 += s * s;
+      }
+      if (dots) dots[j] = s2;
+   }
+   return 0;
+}

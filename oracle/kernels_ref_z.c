@@ -241,3 +241,24 @@ int pb200_zjacobi(pb200_ctx *ctx, int64_t n, const double *diag, const double *s
    }
    return 0;
 }
+
+/* restates the solution update of one QMR step (src/eigs/inner_solve.c:384-413), complex vectors, real scalars */
+int pb200_zqmr_update(pb200_ctx *ctx, int64_t n, const double *gamma, const double *eta, const void *D_, int64_t ldd,
+      void *Delta_, int64_t ldl, void *Sol_, int64_t lds, int ncols, double *dots) {
+   ctx->launches++;
+   const zc *D = (const zc *)D_;
+   zc *Delta = (zc *)Delta_, *Sol = (zc *)Sol_;
+   for (int j = 0; j < ncols; j++) {
+      double s2 = 0.0;
+      for (int64_t r = 0; r < n; r++) {
+         zc t = Delta[r + (size_t)j * ldl] * gamma[j];
+         t += eta[j] * D[r + (size_t)j * ldd];
+         Delta[r + (size_t)j * ldl] = t;
+         const zc s = Sol[r + (size_t)j * lds] + t;
+         Sol[r + (size_t)j * lds] = s;
+         s2 += creal(s) * creal(s) + cimag(s) * cimag(s);
+      }
+      if (dots) dots[j] = s2;
+   }
+   return 0;
+}

@@ -55,6 +55,7 @@ extern "C" int pb200_ctx_create(pb200_ctx **out, int device) {
    ctx->use_tma_vwxr = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_VWXR")) ? 0 : 1;
    ctx->use_tma_spmm = (getenv("PB200_NO_TMA") || getenv("PB200_NO_TMA_SPMM")) ? 0 : 1;
    ctx->sweep_alternate = getenv("PB200_NO_ALTERNATE") ? 0 : 1;
+   ctx->spmm_evict_first = getenv("PB200_NO_EVICT_FIRST") ? 0 : 1;
    ctx->spmm_v3 = getenv("PB200_SPMM_V3") ? atoi(getenv("PB200_SPMM_V3")) : 2;
    *out = ctx;
    return 0;
@@ -93,9 +94,10 @@ extern "C" int pb200_ctx_begin_solve(pb200_ctx *ctx) {
 }
 
 // Keep the head of the basis resident in L2 across sweeps: every panel kernel re-reads V(:,0:m) from its
-// first column on, so the leading `bytes` of the array (whole columns) are given a persisting access-policy
-// window on the context's stream.  bytes == 0 removes the window.  Returns the number of bytes actually set
-// aside (0: not supported / switched off with PB200_L2_PERSIST_MB=0).
+// first column on, so the leading part of the array (whole columns) is given a persisting access-policy
+// window on the context's stream (cudaAccessPropertyPersisting; TMA loads honour it).  `bytes` = size of the
+// array (0 removes the window and releases the carve-out).  Returns the number of bytes set aside
+// (PB200_L2_PERSIST_MB overrides the size, 0 switches it off).
 extern "C" int64_t pb200_ctx_l2_persist(pb200_ctx *ctx, const void *ptr, size_t bytes) {
    static int max_persist = -1, max_window = -1;
    if (max_persist < 0) {
@@ -105,7 +107,10 @@ extern "C" int64_t pb200_ctx_l2_persist(pb200_ctx *ctx, const void *ptr, size_t 
          fprintf(stderr, "primme_b200: L2 persisting max %d MB, access-policy window max %d MB\n", max_persist >> 20,
                max_window >> 20);
    }
-   size_t want = getenv("PB200_L2_PERSIST_MB") ? (size_t)atoi(getenv("PB200_L2_PERSIST_MB")) << 20 : 0;
+   // default: 48 MB of a basis that does not fit the L2 anyway (measured on C2, n = 10^6: ortho sweeps 4.44 ->
+   // 4.65 TB/s, solve 635 -> 622 ms; 79 MB, the maximum, starves the SpMM's gathers: 644 ms)
+   size_t want = getenv("PB200_L2_PERSIST_MB") ? (size_t)atoi(getenv("PB200_L2_PERSIST_MB")) << 20
+                                               : (bytes > ((size_t)96 << 20) ? (size_t)48 << 20 : 0);
    if (bytes == 0 || !ptr) want = 0;
    if (want > bytes) want = bytes;
    if (want > (size_t)max_persist) want = (size_t)max_persist;

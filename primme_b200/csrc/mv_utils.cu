@@ -1,7 +1,8 @@
 // mv_utils.cu -- K6: multivector utilities (fp64): column permute/copy, per-column axpy/scale,
-// batched column dots, in-place residual, Jacobi preconditioner.  All are single-pass,
-// coalesced, grid-stride kernels; the per-column scalars come from the host through the
-// context's pinned staging buffer (replaces cublasAxpyEx/DotcEx/ScalEx + cudaMemcpy2D calls of
+// batched column dots, in-place residual, Jacobi preconditioner, the fused QMR solution update.  All are
+// single-pass, coalesced, grid-stride kernels; the per-column scalars and index lists travel as kernel
+// parameters (no staging copy, no stream synchronisation per call) and the reductions finish inside the
+// kernel (PbFin) -- one launch per operation (replaces cublasAxpyEx/DotcEx/ScalEx + cudaMemcpy2D calls of
 // reference src/linalg/cublas_wrapper.c:616-705,739-783 and the column-by-column permute of
 // src/linalg/auxiliary.c:763-779).
 #include "pb200_internal.cuh"
@@ -21,16 +22,15 @@ inline int grid_for(pb200_ctx *ctx, int64_t n) {
    return (int)g;
 }
 
-// Y(:, yin[j]) = X(:, xin[j])  (index arrays in device memory, -1 list = identity)
+// Y(:, idx.y[j]) = X(:, idx.x[j]); the index lists travel as kernel parameters
+struct ColIdx {
+   int x[32], y[32];
+};
 __global__ void copy_cols_kernel(int64_t n, const double *__restrict__ X, int64_t ldx,
-      const int *__restrict__ xin, double *__restrict__ Y, int64_t ldy,
-      const int *__restrict__ yin, int ncols) {
+      double *__restrict__ Y, int64_t ldy, int ncols, const ColIdx idx) {
    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n;
          r += (int64_t)gridDim.x * blockDim.x)
-      for (int j = 0; j < ncols; j++) {
-         int xs = xin ? xin[j] : j, ys = yin ? yin[j] : j;
-         Y[r + (size_t)ys * ldy] = X[r + (size_t)xs * ldx];
-      }
+      for (int j = 0; j < ncols; j++) Y[r + (size_t)idx.y[j] * ldy] = X[r + (size_t)idx.x[j] * ldx];
 }
 
 // in-place row-wise gather: each thread owns a row, reads all its entries, then writes
@@ -50,25 +50,72 @@ __global__ void permute_rows_kernel(
    }
 }
 
-__global__ void axpy_cols_kernel(int64_t n, const double *__restrict__ alpha,
+// per-column scalars travel in the kernel parameter space: no staging copy, no stream synchronisation
+struct DScal {
+   double v[8];
+};
+
+__global__ void axpy_cols_kernel(int64_t n, const DScal alpha,
       const double *__restrict__ X, int64_t ldx, double *__restrict__ Y, int64_t ldy, int ncols) {
    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n;
          r += (int64_t)gridDim.x * blockDim.x)
-      for (int j = 0; j < ncols; j++) Y[r + (size_t)j * ldy] += alpha[j] * X[r + (size_t)j * ldx];
+      for (int j = 0; j < ncols; j++) Y[r + (size_t)j * ldy] += alpha.v[j] * X[r + (size_t)j * ldx];
 }
 
 __global__ void scale_cols_kernel(
-      int64_t n, const double *__restrict__ alpha, double *__restrict__ X, int64_t ldx, int ncols) {
+      int64_t n, const DScal alpha, double *__restrict__ X, int64_t ldx, int ncols) {
    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n;
          r += (int64_t)gridDim.x * blockDim.x)
-      for (int j = 0; j < ncols; j++) X[r + (size_t)j * ldx] *= alpha[j];
+      for (int j = 0; j < ncols; j++) X[r + (size_t)j * ldx] *= alpha.v[j];
+}
+
+// one step of the QMR solution update (reference inner_solve.c:395-413), all columns in one pass:
+//   delta_j = gamma_j delta_j + eta_j d_j ;  sol_j += delta_j ;  partial |sol_j|^2 when wanted
+// (the same roundings as scale + axpy + axpy + dot, one read and one write of every vector)
+__global__ void __launch_bounds__(UT) qmr_update_kernel(int64_t n, const DScal gam, const DScal eta,
+      const double *__restrict__ D, int64_t ldd, double *__restrict__ Dl, int64_t ldl, double *__restrict__ S,
+      int64_t lds, int ncols, int want_dots, double *__restrict__ partials, const PbFin fin) {
+   __shared__ double red[UT / 32][8];
+   __shared__ int flag;
+   double acc[8];
+#pragma unroll
+   for (int j = 0; j < 8; j++) acc[j] = 0.0;
+   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+         if (j < ncols) {
+            double t = Dl[r + (size_t)j * ldl] * gam.v[j];
+            t += eta.v[j] * D[r + (size_t)j * ldd];
+            Dl[r + (size_t)j * ldl] = t;
+            const double s = S[r + (size_t)j * lds] + t;
+            S[r + (size_t)j * lds] = s;
+            acc[j] += s * s;
+         }
+   }
+   if (!want_dots) return;
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+   for (int j = 0; j < 8; j++) {
+      double v = acc[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][j] = v;
+   }
+   __syncthreads();
+   if (threadIdx.x < ncols) {
+      double s = 0.0;
+      for (int w = 0; w < UT / 32; w++) s += red[w][threadIdx.x];
+      partials[(size_t)blockIdx.x * ncols + threadIdx.x] = s;
+   }
+   pb_finish_device(fin, threadIdx.x, UT, 15, &flag);
 }
 
 // mode 0: out[j] = sum X_j .* Y_j ;  mode 1: W_j -= theta_j V_j (X=V, Y=W), out[j] = |W_j|^2
 template <int NC>
 __global__ void __launch_bounds__(UT) dots_kernel(int64_t n, const double *__restrict__ X,
       int64_t ldx, double *__restrict__ Y, int64_t ldy, int ncols, int mode,
-      const double *__restrict__ theta, double *__restrict__ partials) {
+      const DScal theta, double *__restrict__ partials, const PbFin fin) {
+   __shared__ int flag;
    double acc[NC];
 #pragma unroll
    for (int j = 0; j < NC; j++) acc[j] = 0.0;
@@ -79,7 +126,7 @@ __global__ void __launch_bounds__(UT) dots_kernel(int64_t n, const double *__res
          if (j < ncols) {
             double x = X[r + (size_t)j * ldx], y = Y[r + (size_t)j * ldy];
             if (mode == 1) {
-               y -= theta[j] * x;
+               y -= theta.v[j] * x;
                Y[r + (size_t)j * ldy] = y;
                acc[j] += y * y;
             } else
@@ -101,36 +148,54 @@ __global__ void __launch_bounds__(UT) dots_kernel(int64_t n, const double *__res
       for (int w = 0; w < UT / 32; w++) s += red[w][threadIdx.x];
       partials[(size_t)blockIdx.x * ncols + threadIdx.x] = s;
    }
+   pb_finish_device(fin, threadIdx.x, UT, 15, &flag);
 }
 
 __global__ void jacobi_kernel(int64_t n, const double *__restrict__ diag,
-      const double *__restrict__ shifts, int has_shifts, double minabs,
+      const DScal shifts, int has_shifts, double minabs,
       const double *__restrict__ X, int64_t ldx, double *__restrict__ Y, int64_t ldy, int ncols) {
    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n;
          r += (int64_t)gridDim.x * blockDim.x) {
       double d0 = diag[r];
       for (int j = 0; j < ncols; j++) {
-         double d = d0 - (has_shifts ? shifts[j] : 0.0);
+         double d = d0 - (has_shifts ? shifts.v[j] : 0.0);
          if (fabs(d) < minabs) d = d < 0 ? -minabs : minabs;
          Y[r + (size_t)j * ldy] = X[r + (size_t)j * ldx] / d;
       }
    }
 }
 
-int stage_doubles(pb200_ctx *ctx, const double *h, int cnt, size_t off) {
-   PB_CHK(pb_ensure_small(ctx, off + cnt));
-   memcpy(ctx->h_pinned + off, h, sizeof(double) * cnt);
-   PB_CUDA(cudaMemcpyAsync(ctx->d_small + off, ctx->h_pinned + off, sizeof(double) * cnt,
-         cudaMemcpyHostToDevice, ctx->stream));
+// partial-panel plumbing of the reducing utilities: in-kernel finish (PbFin: also the multi-rank peer
+// exchange) when the launch shape allows it, else one partial per CTA for pb_finish_panel
+int util_panel_setup(pb200_ctx *ctx, int grid, int cnt, PbFin *fin, double **partials) {
+   const int r = pb_fin_prepare(ctx, grid, 1, cnt, fin);
+   if (r < 0) return r;
+   if (r == 1) {
+      memset(fin, 0, sizeof(*fin));
+      PB_CHK(pb_ensure_partials(ctx, (size_t)grid * cnt));
+      *partials = ctx->d_partials;
+   } else
+      *partials = fin->partials;
    return 0;
 }
-int stage_ints(pb200_ctx *ctx, const int *h, int cnt, size_t off_doubles, const int **dev) {
-   size_t dbl = ((size_t)cnt + 1) / 2;
-   PB_CHK(pb_ensure_small(ctx, off_doubles + dbl));
-   memcpy(ctx->h_pinned + off_doubles, h, sizeof(int) * cnt);
-   PB_CUDA(cudaMemcpyAsync(ctx->d_small + off_doubles, ctx->h_pinned + off_doubles,
-         sizeof(int) * cnt, cudaMemcpyHostToDevice, ctx->stream));
-   *dev = (const int *)(ctx->d_small + off_doubles);
+int util_panel_collect(pb200_ctx *ctx, const PbFin *fin, int grid, int cnt) {
+   if (fin->cnt > 0) return pb_collect_panel(ctx, fin);
+   return pb_finish_panel(ctx, grid, cnt);
+}
+// a rank without local rows still takes part in the reduction; result (zeros summed with the others') in h_pinned
+int util_empty_panel(pb200_ctx *ctx, int cnt) {
+   if (ctx->nranks > 1) {
+      PB_CHK(pb_ensure_small(ctx, (size_t)cnt));
+      const int zr = pb_fin_contribute_zeros(ctx, cnt);
+      if (zr < 0) return zr;
+      if (zr == 1) {
+         PB_CUDA(cudaMemsetAsync(ctx->d_panel, 0, sizeof(double) * cnt, ctx->stream));
+         PB_CHK(pb_nccl_allreduce_dev(ctx, ctx->d_panel, cnt));
+         PB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_panel, sizeof(double) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+         PB_CUDA(cudaStreamSynchronize(ctx->stream));
+      }
+   } else
+      for (int j = 0; j < cnt; j++) ctx->h_pinned[j] = 0.0;
    return 0;
 }
 
@@ -138,15 +203,25 @@ int dots_impl(pb200_ctx *ctx, int64_t n, const double *X, int64_t ldx, double *Y
       int ncols, int mode, const double *theta_host, double *out_host) {
    for (int c0 = 0; c0 < ncols; c0 += 8) {
       int nc = ncols - c0 < 8 ? ncols - c0 : 8;
-      // the pinned buffer is reused by pb_finish_panel: wait for earlier users
-      if (mode == 1) PB_CHK(stage_doubles(ctx, theta_host + c0, nc, 0));
-      int grid = grid_for(ctx, n);
-      PB_CHK(pb_ensure_partials(ctx, (size_t)grid * nc));
-      dots_kernel<8><<<grid, UT, 0, ctx->stream>>>(n, X + (size_t)c0 * ldx, ldx,
-            Y + (size_t)c0 * ldy, ldy, nc, mode, ctx->d_small, ctx->d_partials);
-      ctx->launches++;
-      PB_CUDA(cudaGetLastError());
-      PB_CHK(pb_finish_panel(ctx, grid, nc));
+      if (n <= 0) {
+         PB_CHK(util_empty_panel(ctx, nc));
+      } else {
+         DScal th;
+         memset(&th, 0, sizeof(th));
+         if (mode == 1)
+            for (int j = 0; j < nc; j++) th.v[j] = theta_host[c0 + j];
+         int grid = grid_for(ctx, n);
+         PbFin fin;
+         double *partials = NULL;
+         PB_CHK(util_panel_setup(ctx, grid, nc, &fin, &partials));
+         int ps = pb_prof_begin(ctx, PB_K_UTIL);
+         dots_kernel<8><<<grid, UT, 0, ctx->stream>>>(n, X + (size_t)c0 * ldx, ldx,
+               Y + (size_t)c0 * ldy, ldy, nc, mode, th, partials, fin);
+         pb_prof_end(ctx, ps, 8.0 * (double)n * nc * (mode == 1 ? 3 : 2));
+         ctx->launches++;
+         PB_CUDA(cudaGetLastError());
+         PB_CHK(util_panel_collect(ctx, &fin, grid, nc));
+      }
       for (int j = 0; j < nc; j++) out_host[c0 + j] = ctx->h_pinned[j];
    }
    return 0;
@@ -157,14 +232,15 @@ int dots_impl(pb200_ctx *ctx, int64_t n, const double *X, int64_t ldx, double *Y
 extern "C" int pb200_dcopy_columns(pb200_ctx *ctx, int64_t n, const double *X, int64_t ldx,
       const int *xin_host, double *Y, int64_t ldy, const int *yin_host, int ncols) {
    if (ncols <= 0 || n <= 0) return 0;
-   const int *dx = NULL, *dy = NULL;
-   // earlier async uses of the pinned buffer must be complete before it is overwritten
-   PB_CUDA(cudaStreamSynchronize(ctx->stream));
-   if (xin_host) PB_CHK(stage_ints(ctx, xin_host, ncols, 0, &dx));
-   if (yin_host) PB_CHK(stage_ints(ctx, yin_host, ncols, (size_t)(ncols + 1) / 2 + 1, &dy));
-   copy_cols_kernel<<<grid_for(ctx, n), UT, 0, ctx->stream>>>(n, X, ldx, dx, Y, ldy, dy, ncols);
-   ctx->launches++;
-   PB_CUDA(cudaGetLastError());
+   for (int c0 = 0; c0 < ncols; c0 += 32) {
+      const int nc = ncols - c0 < 32 ? ncols - c0 : 32;
+      ColIdx idx;
+      for (int j = 0; j < nc; j++)
+         idx.x[j] = xin_host ? xin_host[c0 + j] : c0 + j, idx.y[j] = yin_host ? yin_host[c0 + j] : c0 + j;
+      copy_cols_kernel<<<grid_for(ctx, n), UT, 0, ctx->stream>>>(n, X, ldx, Y, ldy, nc, idx);
+      ctx->launches++;
+      PB_CUDA(cudaGetLastError());
+   }
    return 0;
 }
 
@@ -193,22 +269,34 @@ extern "C" int pb200_dpermute_columns(
 extern "C" int pb200_daxpy_columns(pb200_ctx *ctx, int64_t n, const double *alpha_host,
       const double *X, int64_t ldx, double *Y, int64_t ldy, int ncols) {
    if (ncols <= 0 || n <= 0) return 0;
-   PB_CUDA(cudaStreamSynchronize(ctx->stream));
-   PB_CHK(stage_doubles(ctx, alpha_host, ncols, 0));
-   axpy_cols_kernel<<<grid_for(ctx, n), UT, 0, ctx->stream>>>(n, ctx->d_small, X, ldx, Y, ldy, ncols);
-   ctx->launches++;
-   PB_CUDA(cudaGetLastError());
+   for (int c0 = 0; c0 < ncols; c0 += 8) {
+      const int nc = ncols - c0 < 8 ? ncols - c0 : 8;
+      DScal al;
+      memset(&al, 0, sizeof(al));
+      memcpy(al.v, alpha_host + c0, sizeof(double) * nc);
+      int ps = pb_prof_begin(ctx, PB_K_UTIL);
+      axpy_cols_kernel<<<grid_for(ctx, n), UT, 0, ctx->stream>>>(n, al, X + (size_t)c0 * ldx, ldx, Y + (size_t)c0 * ldy, ldy, nc);
+      pb_prof_end(ctx, ps, 24.0 * (double)n * nc);
+      ctx->launches++;
+      PB_CUDA(cudaGetLastError());
+   }
    return 0;
 }
 
 extern "C" int pb200_dscale_columns(
       pb200_ctx *ctx, int64_t n, const double *alpha_host, double *X, int64_t ldx, int ncols) {
    if (ncols <= 0 || n <= 0) return 0;
-   PB_CUDA(cudaStreamSynchronize(ctx->stream));
-   PB_CHK(stage_doubles(ctx, alpha_host, ncols, 0));
-   scale_cols_kernel<<<grid_for(ctx, n), UT, 0, ctx->stream>>>(n, ctx->d_small, X, ldx, ncols);
-   ctx->launches++;
-   PB_CUDA(cudaGetLastError());
+   for (int c0 = 0; c0 < ncols; c0 += 8) {
+      const int nc = ncols - c0 < 8 ? ncols - c0 : 8;
+      DScal al;
+      memset(&al, 0, sizeof(al));
+      memcpy(al.v, alpha_host + c0, sizeof(double) * nc);
+      int ps = pb_prof_begin(ctx, PB_K_UTIL);
+      scale_cols_kernel<<<grid_for(ctx, n), UT, 0, ctx->stream>>>(n, al, X + (size_t)c0 * ldx, ldx, nc);
+      pb_prof_end(ctx, ps, 16.0 * (double)n * nc);
+      ctx->launches++;
+      PB_CUDA(cudaGetLastError());
+   }
    return 0;
 }
 
@@ -221,7 +309,6 @@ extern "C" int pb200_dcolumn_dots(pb200_ctx *ctx, int64_t n, const double *X, in
 extern "C" int pb200_dresidual_inplace(pb200_ctx *ctx, int64_t n, const double *theta_host,
       const double *V, int64_t ldv, double *W, int64_t ldw, int ncols, double *out_host) {
    if (ncols <= 0) return 0;
-   PB_CUDA(cudaStreamSynchronize(ctx->stream));
    return dots_impl(ctx, n, V, ldv, W, ldw, ncols, 1, theta_host, out_host);
 }
 
@@ -229,11 +316,53 @@ extern "C" int pb200_djacobi(pb200_ctx *ctx, int64_t n, const double *diag,
       const double *shifts_host, double minabs, const double *X, int64_t ldx, double *Y,
       int64_t ldy, int ncols) {
    if (ncols <= 0 || n <= 0) return 0;
-   PB_CUDA(cudaStreamSynchronize(ctx->stream));
-   if (shifts_host) PB_CHK(stage_doubles(ctx, shifts_host, ncols, 0));
-   jacobi_kernel<<<grid_for(ctx, n), UT, 0, ctx->stream>>>(
-         n, diag, ctx->d_small, shifts_host != NULL, minabs, X, ldx, Y, ldy, ncols);
-   ctx->launches++;
-   PB_CUDA(cudaGetLastError());
+   for (int c0 = 0; c0 < ncols; c0 += 8) {
+      const int nc = ncols - c0 < 8 ? ncols - c0 : 8;
+      DScal sh;
+      memset(&sh, 0, sizeof(sh));
+      if (shifts_host) memcpy(sh.v, shifts_host + c0, sizeof(double) * nc);
+      int ps = pb_prof_begin(ctx, PB_K_UTIL);
+      jacobi_kernel<<<grid_for(ctx, n), UT, 0, ctx->stream>>>(n, diag, sh, shifts_host != NULL, minabs,
+            X + (size_t)c0 * ldx, ldx, Y + (size_t)c0 * ldy, ldy, nc);
+      pb_prof_end(ctx, ps, 16.0 * (double)n * nc + 8.0 * (double)n);
+      ctx->launches++;
+      PB_CUDA(cudaGetLastError());
+   }
+   return 0;
+}
+
+// delta_j = gamma_j delta_j + eta_j d_j;  sol_j += delta_j;  dots_host[j] = |sol_j|^2 when dots_host != NULL
+// (the solution update of one QMR step, reference src/eigs/inner_solve.c:384-413, in one pass)
+extern "C" int pb200_dqmr_update(pb200_ctx *ctx, int64_t n, const double *gamma_host, const double *eta_host,
+      const double *D, int64_t ldd, double *Delta, int64_t ldl, double *Sol, int64_t lds, int ncols,
+      double *dots_host) {
+   for (int c0 = 0; c0 < ncols; c0 += 8) {
+      const int nc = ncols - c0 < 8 ? ncols - c0 : 8;
+      if (n <= 0) {
+         if (dots_host) {
+            PB_CHK(util_empty_panel(ctx, nc));
+            for (int j = 0; j < nc; j++) dots_host[c0 + j] = ctx->h_pinned[j];
+         }
+         continue;
+      }
+      DScal g, e;
+      memset(&g, 0, sizeof(g)), memset(&e, 0, sizeof(e));
+      memcpy(g.v, gamma_host + c0, sizeof(double) * nc), memcpy(e.v, eta_host + c0, sizeof(double) * nc);
+      const int grid = grid_for(ctx, n);
+      PbFin fin;
+      memset(&fin, 0, sizeof(fin));
+      double *partials = NULL;
+      if (dots_host) PB_CHK(util_panel_setup(ctx, grid, nc, &fin, &partials));
+      int ps = pb_prof_begin(ctx, PB_K_UTIL);
+      qmr_update_kernel<<<grid, UT, 0, ctx->stream>>>(n, g, e, D + (size_t)c0 * ldd, ldd, Delta + (size_t)c0 * ldl, ldl,
+            Sol + (size_t)c0 * lds, lds, nc, dots_host != NULL, partials, fin);
+      pb_prof_end(ctx, ps, 40.0 * (double)n * nc);
+      ctx->launches++;
+      PB_CUDA(cudaGetLastError());
+      if (dots_host) {
+         PB_CHK(util_panel_collect(ctx, &fin, grid, nc));
+         for (int j = 0; j < nc; j++) dots_host[c0 + j] = ctx->h_pinned[j];
+      }
+   }
    return 0;
 }

@@ -4,15 +4,19 @@
 //    P  = [Q V (X)]^H X          (optional Gram panel; ortho.c:1043-1059, and
 //                                 update_projection.c:99-102 when X is the new W block)
 //
-// HBM-bound (0.5-2 flop/B): the basis is streamed exactly once per sweep.  Work decomposition
-// per CTA (256 threads, persistent over 256-row tiles):
-//   phase 1 (update): thread <-> row.  Coalesced column reads of [Q V], C and Y broadcast from
-//            shared memory, new X row written back and parked in shared memory.
-//   phase 2 (Gram):   warp <-> CPW basis columns, lane <-> rows of the tile.  k*b accumulators
-//            are spread over the CTA (CPW*BT per thread) and live in registers across all
-//            tiles; the tile of [Q V] touched in phase 1 is re-read through L1/L2, not HBM.
-//   epilogue: warp-shuffle reduction, one partial panel per CTA, fixed-order second stage
-//            (pb_finish_panel) => bitwise reproducible panels.
+// HBM-bound (0.5-2 flop/B): the basis is streamed exactly once per sweep.  Three kernels, one entry point:
+//   ortho_sweep_mma_exact_kernel<NMT,16,UPD,XX>   the steady-state instances (no locked vectors, 3-5 tiles of
+//            8 basis columns): persistent CTAs, one producer thread streams 128-row tiles of [V X] with 2-D
+//            tensor-map TMA into a ring of stages, 16 consumer warps own 8 rows each and do the update and
+//            the Gram with DMMA m8n8k4, all MMAs unconditional, accumulators in registers across tiles;
+//   ortho_sweep_mma_kernel<MT,NW>                 the same pipeline for any (q, mv, b) that fits the stages
+//            (locked vectors, wide C5 panels: 64-row tiles and 8 warps when the ring would be < 3 deep);
+//   ortho_sweep_kernel<BT,CPW>                    LDG fallback (unaligned columns, n < 256): thread <-> row
+//            update, warp <-> CPW basis columns Gram.
+// Every CTA leaves one partial panel; the CTAs finish it themselves in two fixed-order levels
+// (pb_finish_device) and the last one delivers (value, sequence number) pairs to mapped host memory, or
+// all-reduces over peer memory first => bitwise reproducible panels, no second launch.
+// Consecutive sweeps walk the row tiles in opposite directions (PB_TILE) for L2 reuse.
 #include "pb200_internal.cuh"
 #include "tma_pipe.cuh"
 #include <string.h>

@@ -70,6 +70,7 @@ struct pb200_ctx {
    int l2_window;         // a persisting access-policy window is set on the stream
    int sweep_alternate;   // 1 (default): consecutive TMA sweeps walk the rows in opposite directions (L2 reuse)
    int sweep_rev;         // direction of the last sweep
+   int spmm_evict_first;  // L2 evict_first policy on the CSR stream of the row-major SpMM (default 1)
    int spmm_v3;           // gather layout for b >= 2: 0 column-major (v2), 1 row-major copy (v3), 2 timed once per matrix (default)
    int use_wide;          // v3 wide VWXR kernel for the restart sweep
    int use_mma_vwxr;      // tensor-map TMA + DMMA VWXR kernel (default)

@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(SPT_THREADS, 2) spmm_rm_kernel(const int64_t *
       const int64_t *__restrict__ blk_row0, const int64_t *__restrict__ blk_nz0,
       const int32_t *__restrict__ blk_nnz, const int32_t *__restrict__ blk_kind,
       const int32_t *__restrict__ long_slot, double *__restrict__ long_part, int nblocks,
-      const double *G, double *__restrict__ Y, int64_t ldy, int b, int nstages, const PbSpSync sync) {
+      const double *G, double *__restrict__ Y, int64_t ldy, int b, int nstages, const PbSpSync sync, int evict_first) {
    typedef typename SpVal<CPLX>::type VT;
    constexpr int NR = CPLX ? 2 * BT : BT;       // doubles per row of G
    constexpr int UN = NR >= 16 ? 1 : NR >= 8 ? 2 : 4;  // nonzeros in flight per lane (60 registers per thread)
@@ -454,6 +454,8 @@ __global__ void __launch_bounds__(SPT_THREADS, 2) spmm_rm_kernel(const int64_t *
    if (warp == SPT_CONS / 32) {
       // -------- producer: the matrix stream does not depend on the halo --------
       if (lane != 0) return;
+      // read-once stream: evict first, the L2 belongs to the gathered rows of G
+      const uint64_t pol = evict_first ? pbtma::l2_policy_evict_first() : 0;
       int s = 0;
       uint32_t ph = 0;
       for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
@@ -475,11 +477,19 @@ __global__ void __launch_bounds__(SPT_THREADS, 2) spmm_rm_kernel(const int64_t *
          hdr->off = (int32_t)(nz0 - nzbase);
          const uint32_t bytes = (uint32_t)cnt * (uint32_t)(sizeof(VT) + 4) + (uint32_t)rpcnt * 8u;
          pbtma::mbar_arrive_expect_tx(&full[s], bytes);
-         if (cnt > 0) {
-            pbtma::bulk_g2s(st, vals + nzbase, (uint32_t)cnt * (uint32_t)sizeof(VT), &full[s]);
-            pbtma::bulk_g2s(st + OFF_COL, colind + nzbase, (uint32_t)cnt * 4u, &full[s]);
+         if (evict_first) {
+            if (cnt > 0) {
+               pbtma::bulk_g2s_hint(st, vals + nzbase, (uint32_t)cnt * (uint32_t)sizeof(VT), &full[s], pol);
+               pbtma::bulk_g2s_hint(st + OFF_COL, colind + nzbase, (uint32_t)cnt * 4u, &full[s], pol);
+            }
+            if (rpcnt > 0) pbtma::bulk_g2s_hint(st + OFF_RP, rowptr + rpbase, (uint32_t)rpcnt * 8u, &full[s], pol);
+         } else {
+            if (cnt > 0) {
+               pbtma::bulk_g2s(st, vals + nzbase, (uint32_t)cnt * (uint32_t)sizeof(VT), &full[s]);
+               pbtma::bulk_g2s(st + OFF_COL, colind + nzbase, (uint32_t)cnt * 4u, &full[s]);
+            }
+            if (rpcnt > 0) pbtma::bulk_g2s(st + OFF_RP, rowptr + rpbase, (uint32_t)rpcnt * 8u, &full[s]);
          }
-         if (rpcnt > 0) pbtma::bulk_g2s(st + OFF_RP, rowptr + rpbase, (uint32_t)rpcnt * 8u, &full[s]);
          if (++s == nstages) s = 0, ph ^= 1;
       }
       return;
@@ -670,7 +680,7 @@ int launch_spmm_rm_l(pb200_ctx *ctx, const pb200_csr *A, const double *G, double
    else memset(&sy, 0, sizeof(sy));
    kern<<<grid, SPT_THREADS, shmem, ctx->stream>>>(A->d_rowptr, A->d_colind, A->d_vals, A->d_blk_row0,
          A->d_blk_nz0, A->d_blk_nnz, A->d_blk_kind, A->d_long_slot, A->d_long_part, A->nblocks, G, Y, ldy, b,
-         nstages, sy);
+         nstages, sy, ctx->spmm_evict_first);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
    return 0;

@@ -51,6 +51,21 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
          "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
          : "memory");
 }
+// same with an L2 eviction policy for the source lines: a stream that is read exactly once (the CSR arrays of
+// the SpMM) is marked evict_first so that it does not push the gathered right-hand-side rows out of the L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+   uint64_t pol;
+   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+   return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+      uint64_t policy) {
+   asm volatile(
+         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+               smem_u32(dst_smem)),
+         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+         : "memory");
+}
 // global -> shared copy of one box of a 2-D tensor map (cp.async.bulk.tensor, SASS UTMALDG): the box
 // [c0, c0+box0) x [c1, c1+box1) lands densely in shared memory, elements outside the tensor are
 // zero-filled, and the FULL box byte count completes on `bar`.  dst must be 128-byte aligned.

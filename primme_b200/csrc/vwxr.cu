@@ -7,12 +7,15 @@
 //     R(r,:) = yrow - xrow .* theta, accumulate ||R_j||^2 (+ extra norms without storing)
 //     G += xrow(0:nG)^T xrow(0:nG),  H += xrow(0:nH)^T yrow(0:nH)
 //
-// HBM-bound.  thread <-> row: V and W are read column by column, coalesced across the threads of
-// a warp; h is broadcast from shared memory; the nh (<= NT) running sums of both products live
-// in registers, so every row of V and W is read exactly once and only then written (in-place
-// restart V <- V*h is safe: a row is owned by one thread).  G/H: the CTA parks its tile of
-// xrow/yrow in shared memory and accumulates 2x2 register blocks per thread across all tiles;
-// per-CTA partials are reduced in fixed order (pb_finish_panel).
+// HBM-bound for the candidates sweep, instruction-bound for the wide restart sweep.  Three kernels:
+//   vwxr_mma_kernel<NT8,MT,NW>   default: persistent CTAs, one producer thread streams row tiles of V and W with
+//            2-D tensor-map TMA, each consumer warp owns 8 rows and forms V h and W h with DMMA m8n8k4 (h fragments
+//            in registers / shared memory), residuals and norms in registers, G / H through a per-warp transposing
+//            scratch, optionally P = [V R]^T R (the first Gram panel of the next block orthogonalisation);
+//            a row is owned by one warp, so the in-place restart V <- V h is safe;
+//   vwxr_wide_kernel<NTH,NG>     bulk-copy staged FMA kernel for wide coefficient blocks the MMA instances do not take;
+//   vwxr_kernel<NT>              LDG fallback (thread <-> row), any alignment, n < 256.
+// Per-CTA partials (norms, G, H, P) are finished inside the kernel in a fixed order (pb_finish_device).
 #include "pb200_internal.cuh"
 #include "tma_pipe.cuh"
 #include <math.h>

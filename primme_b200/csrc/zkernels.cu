@@ -92,7 +92,14 @@ struct ZSweepArgs {
    int q, mv, b;
    int do_update, has_Y, do_gram, xx;
    const zc *coef;  // device: C (k x BT, row stride BT) then Y (BT x BT)
+   int coef_inline; // 1: the block travels in the kernel parameter space instead (ZCoef)
    ZPanel pan;
+};
+// coefficient block of the update by value: no staging copy and no stream synchronisation in front of the
+// launch (the CGS passes of C3 and the projectors of the inner solver update with <= 60 x 1 blocks)
+#define ZCOEF_MAX 448
+struct ZCoef {
+   zc v[ZCOEF_MAX];
 };
 __device__ __forceinline__ const zc *zcol(const ZSweepArgs &a, int j) {
    return j < a.q ? a.Q + (size_t)j * a.ldq : a.V + (size_t)(j - a.q) * a.ldv;
@@ -100,7 +107,7 @@ __device__ __forceinline__ const zc *zcol(const ZSweepArgs &a, int j) {
 
 // BT: block columns (padded), CPW: basis columns per warp in the Gram phase (k <= ZW * CPW)
 template <int BT, int CPW>
-__global__ void __launch_bounds__(ZT) zsweep_kernel(const ZSweepArgs a) {
+__global__ void __launch_bounds__(ZT) zsweep_kernel(const ZSweepArgs a, const __grid_constant__ ZCoef cf) {
    extern __shared__ __align__(16) unsigned char zsm[];
    const int k = a.q + a.mv;
    zc *Cs = reinterpret_cast<zc *>(zsm);   // k * BT
@@ -108,7 +115,8 @@ __global__ void __launch_bounds__(ZT) zsweep_kernel(const ZSweepArgs a) {
    zc *xs = Ys + BT * BT;                  // BT * ZT
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    if (a.do_update) {
-      for (int i = tid; i < k * BT + BT * BT; i += ZT) Cs[i] = a.coef[i];
+      const zc *src = a.coef_inline ? cf.v : a.coef;
+      for (int i = tid; i < k * BT + BT * BT; i += ZT) Cs[i] = src[i];
    }
    __syncthreads();
 
@@ -228,14 +236,14 @@ __global__ void __launch_bounds__(ZT) zsweep_kernel(const ZSweepArgs a) {
 }
 
 template <int BT, int CPW>
-int launch_zsweep(pb200_ctx *ctx, const ZSweepArgs &a, int grid, size_t shmem) {
+int launch_zsweep(pb200_ctx *ctx, const ZSweepArgs &a, const ZCoef &cf, int grid, size_t shmem) {
    auto kern = zsweep_kernel<BT, CPW>;
    static size_t attr = 0;
    if (shmem > 48 * 1024 && shmem > attr) {
       PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
       attr = shmem;
    }
-   kern<<<grid, ZT, shmem, ctx->stream>>>(a);
+   kern<<<grid, ZT, shmem, ctx->stream>>>(a, cf);
    ctx->launches++;
    PB_CUDA(cudaGetLastError());
    return 0;
@@ -243,10 +251,10 @@ int launch_zsweep(pb200_ctx *ctx, const ZSweepArgs &a, int grid, size_t shmem) {
 // basis columns one launch can take in its Gram phase
 inline int zsweep_kmax(int BT) { return ZW * (BT == 1 ? 12 : BT == 2 ? 8 : BT == 4 ? 4 : 2); }
 
-int dispatch_zsweep(pb200_ctx *ctx, const ZSweepArgs &a, int BT, int grid, size_t shmem) {
+int dispatch_zsweep(pb200_ctx *ctx, const ZSweepArgs &a, const ZCoef &cf, int BT, int grid, size_t shmem) {
    const int k = a.q + a.mv;
    const int cpw = a.do_gram ? (k + ZW - 1) / ZW : 1;
-#define ZS(B, C) return launch_zsweep<B, C>(ctx, a, grid, shmem)
+#define ZS(B, C) return launch_zsweep<B, C>(ctx, a, cf, grid, shmem)
    switch (BT) {
    case 1:
       if (cpw <= 1) ZS(1, 1);
@@ -284,12 +292,19 @@ int zsweep_once(pb200_ctx *ctx, int64_t n, const zc *Q, int q, int64_t ldq, cons
    a.do_gram = P_host != NULL;
    a.xx = xx ? 1 : 0;
    if (!a.do_update && !a.do_gram) return 0;
+   ZCoef cfv;  // host staging of the by-value block
    if (a.do_update) {
-      // coefficient block through the pinned staging buffer (complex: 2 doubles per entry)
-      const size_t need = 2 * ((size_t)k * BT + BT * BT);
-      PB_CHK(pb_ensure_small(ctx, need));
-      PB_CUDA(cudaStreamSynchronize(ctx->stream));  // the staging buffer may still feed an earlier copy
-      zc *hp = reinterpret_cast<zc *>(ctx->h_pinned);
+      const size_t ne = (size_t)k * BT + BT * BT;
+      zc *hp;
+      if (ne <= ZCOEF_MAX) {
+         a.coef_inline = 1;
+         hp = cfv.v;
+      } else {
+         // large blocks go through the pinned staging buffer (complex: 2 doubles per entry)
+         PB_CHK(pb_ensure_small(ctx, 2 * ne));
+         PB_CUDA(cudaStreamSynchronize(ctx->stream));  // the staging buffer may still feed an earlier copy
+         hp = reinterpret_cast<zc *>(ctx->h_pinned);
+      }
       for (int j = 0; j < k; j++)
          for (int c = 0; c < BT; c++)
             hp[(size_t)j * BT + c] = (c < b && C_host) ? C_host[j + (size_t)c * ldc] : zc{0.0, 0.0};
@@ -298,8 +313,10 @@ int zsweep_once(pb200_ctx *ctx, int64_t n, const zc *Q, int q, int64_t ldq, cons
          for (int c = 0; c < BT; c++)
             hy[r * BT + c] = Y_host ? ((r < b && c < b) ? Y_host[r + (size_t)c * ldy] : zc{0.0, 0.0})
                                     : zc{r == c ? 1.0 : 0.0, 0.0};
-      PB_CUDA(cudaMemcpyAsync(ctx->d_small, hp, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-      a.coef = reinterpret_cast<const zc *>(ctx->d_small);
+      if (!a.coef_inline) {
+         PB_CUDA(cudaMemcpyAsync(ctx->d_small, hp, 2 * ne * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+         a.coef = reinterpret_cast<const zc *>(ctx->d_small);
+      }
    }
    const int rows = k + (a.xx ? b : 0);
    const int cnt = a.do_gram ? 2 * rows * b : 0;
@@ -309,7 +326,7 @@ int zsweep_once(pb200_ctx *ctx, int64_t n, const zc *Q, int q, int64_t ldq, cons
    // algorithmic bytes: basis read once, X read (+ written when updated), 16 bytes per element
    const double abytes = 16.0 * (double)n * (k + b * (a.do_update ? 2 : 1));
    int ps = pb_prof_begin(ctx, PB_K_ORTHO);
-   int rc = dispatch_zsweep(ctx, a, BT, grid, shmem);
+   int rc = dispatch_zsweep(ctx, a, cfv, BT, grid, shmem);
    pb_prof_end(ctx, ps, abytes);
    PB_CHK(rc);
    if (a.do_gram) {
@@ -446,6 +463,50 @@ __global__ void __launch_bounds__(ZT) zdots_kernel(int64_t n, const zc *__restri
    }
    pb_finish_device(pan.fin, threadIdx.x, ZT, 15, &flag);
 }
+// complex vectors, REAL recurrence scalars (reference inner_solve.c:155-182): delta = gamma delta + eta d;
+// sol += delta; partial |sol|^2
+__global__ void __launch_bounds__(ZT) zqmr_update_kernel(int64_t n, const ZScal gam, const ZScal eta, const zc *__restrict__ D,
+      int64_t ldd, zc *__restrict__ Dl, int64_t ldl, zc *__restrict__ S, int64_t lds, int ncols, int want_dots,
+      const ZPanel pan) {
+   __shared__ double red[ZW][8];
+   __shared__ int flag;
+   double acc[8];
+#pragma unroll
+   for (int j = 0; j < 8; j++) acc[j] = 0.0;
+   for (int64_t r = (int64_t)blockIdx.x * ZT + threadIdx.x; r < n; r += (int64_t)gridDim.x * ZT) {
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+         if (j < ncols) {
+            // the same roundings as zscale (complex product with (gamma, 0)) + zaxpy + zaxpy + dot
+            zc t = zmake(0.0, 0.0);
+            zfma(t, gam.v[j], Dl[r + (size_t)j * ldl]);
+            zfma(t, eta.v[j], D[r + (size_t)j * ldd]);
+            Dl[r + (size_t)j * ldl] = t;
+            zc s = S[r + (size_t)j * lds];
+            zfma(s, zmake(1.0, 0.0), t);
+            S[r + (size_t)j * lds] = s;
+            acc[j] = fma(s.x, s.x, acc[j]);
+            acc[j] = fma(s.y, s.y, acc[j]);
+         }
+   }
+   if (!want_dots) return;
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+   for (int j = 0; j < 8; j++) {
+      double v = acc[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][j] = v;
+   }
+   __syncthreads();
+   if (threadIdx.x < ncols) {
+      double s = 0.0;
+      for (int w = 0; w < ZW; w++) s += red[w][threadIdx.x];
+      pan.partials[(size_t)blockIdx.x * ncols + threadIdx.x] = s;
+   }
+   pb_finish_device(pan.fin, threadIdx.x, ZT, 15, &flag);
+}
+
 __global__ void __launch_bounds__(ZT) zjacobi_kernel(int64_t n, const double *__restrict__ diag, const ZScal sh, double minabs,
       const zc *__restrict__ X, int64_t ldx, zc *__restrict__ Y, int64_t ldy, int ncols) {
    for (int64_t r = (int64_t)blockIdx.x * ZT + threadIdx.x; r < n; r += (int64_t)gridDim.x * ZT) {
@@ -666,6 +727,49 @@ extern "C" int pb200_zjacobi(pb200_ctx *ctx, int64_t n, const double *diag, cons
       pb_prof_end(ctx, ps, 32.0 * (double)n * nc + 8.0 * (double)n);
       ctx->launches++;
       PB_CUDA(cudaGetLastError());
+   }
+   return 0;
+}
+
+extern "C" int pb200_zqmr_update(pb200_ctx *ctx, int64_t n, const double *gamma_host, const double *eta_host, const void *D,
+      int64_t ldd, void *Delta, int64_t ldl, void *Sol, int64_t lds, int ncols, double *dots_host) {
+   for (int c0 = 0; c0 < ncols; c0 += 8) {
+      const int nc = ncols - c0 < 8 ? ncols - c0 : 8;
+      if (n <= 0) {
+         if (dots_host) {
+            if (ctx->nranks > 1) {
+               PB_CHK(pb_ensure_small(ctx, (size_t)nc));
+               const int zr = pb_fin_contribute_zeros(ctx, nc);
+               if (zr < 0) return zr;
+               if (zr == 1) {
+                  PB_CUDA(cudaMemsetAsync(ctx->d_panel, 0, sizeof(double) * nc, ctx->stream));
+                  PB_CHK(pb_nccl_allreduce_dev(ctx, ctx->d_panel, nc));
+                  PB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_panel, sizeof(double) * nc, cudaMemcpyDeviceToHost, ctx->stream));
+                  PB_CUDA(cudaStreamSynchronize(ctx->stream));
+               }
+            } else
+               for (int j = 0; j < nc; j++) ctx->h_pinned[j] = 0.0;
+            for (int j = 0; j < nc; j++) dots_host[c0 + j] = ctx->h_pinned[j];
+         }
+         continue;
+      }
+      ZScal g, e;
+      memset(&g, 0, sizeof(g)), memset(&e, 0, sizeof(e));
+      for (int j = 0; j < nc; j++) g.v[j].x = gamma_host[c0 + j], e.v[j].x = eta_host[c0 + j];
+      const int grid = grid_for(ctx, n, 4);
+      ZPanel pan;
+      memset(&pan, 0, sizeof(pan));
+      if (dots_host) PB_CHK(zpanel_setup(ctx, grid, nc, &pan));
+      int ps = pb_prof_begin(ctx, PB_K_UTIL);
+      zqmr_update_kernel<<<grid, ZT, 0, ctx->stream>>>(n, g, e, (const zc *)D + (size_t)c0 * ldd, ldd, (zc *)Delta + (size_t)c0 * ldl,
+            ldl, (zc *)Sol + (size_t)c0 * lds, lds, nc, dots_host != NULL, pan);
+      pb_prof_end(ctx, ps, 80.0 * (double)n * nc);
+      ctx->launches++;
+      PB_CUDA(cudaGetLastError());
+      if (dots_host) {
+         PB_CHK(zpanel_collect(ctx, &pan));
+         for (int j = 0; j < nc; j++) dots_host[c0 + j] = ctx->h_pinned[j];
+      }
    }
    return 0;
 }

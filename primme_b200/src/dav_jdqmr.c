@@ -94,6 +94,9 @@ static int apply_projected_preconditioner(pb_solver *S, right_projectors *rp, SC
    return 0;
 }
 
+/* sums over the processes still to be done through the host callback (no multi-rank kernel context) */
+#define primme_host_sums(S) ((S)->primme->numProcs > 1 && pb200_ctx_nranks((S)->dev) <= 1)
+
 static void perm_set_value_on_pos(int *p, int val, int pos, int n) {
    for (int i = 0; i < n; i++)
       if (p[i] == val) {
@@ -203,8 +206,17 @@ int pb_inner_solve(pb_solver *S, int blockSize, SCALAR *x, int64_t ldx, SCALAR *
          }
          alpha_neg[i] = -alpha_prev[p[i]];
       }
-      /* g_i -= alpha_i w_i for the systems still running (alpha = 0 leaves the others untouched) */
-      CHK(axpy_real(S, n, alpha_neg, w, ldw, g, ldw, blockSize));
+      /* g_i -= alpha_i w_i for the systems still running (alpha = 0 leaves the others untouched); with no
+       * system leaving the block the same pass also delivers |g_i|^2 (one launch instead of two) */
+      int have_theta = 0;
+      if (conv == 0) {
+         double alpha_pos[8];
+         for (i = 0; i < blockSize; i++) alpha_pos[i] = -alpha_neg[i];
+         CHK(pb200_dresidual_inplace(S->dev, n, alpha_pos, w, ldw, g, ldw, blockSize, Theta));
+         if (primme_host_sums(S)) CHK(pb_global_sum(S, Theta, blockSize));
+         have_theta = 1;
+      } else
+         CHK(axpy_real(S, n, alpha_neg, w, ldw, g, ldw, blockSize));
 
 #define PB_PERMUTE_BLOCK()                                                                        \
    do {                                                                                           \
@@ -228,7 +240,7 @@ int pb_inner_solve(pb_solver *S, int blockSize, SCALAR *x, int64_t ldx, SCALAR *
       if (conv > 0) PB_PERMUTE_BLOCK();
       if (blockSize <= 0) break;
 
-      CHK(dots_real(S, g, ldw, g, ldw, blockSize, Theta));
+      if (!have_theta) CHK(dots_real(S, g, ldw, g, ldw, blockSize, Theta));
       double gam_pos[8], eta_pos[8];
       for (i = 0; i < blockSize; i++) {
          Theta[p[i]] = sqrt(Theta[p[i]]) / tau_prev[p[i]];
@@ -239,10 +251,8 @@ int pb_inner_solve(pb_solver *S, int blockSize, SCALAR *x, int64_t ldx, SCALAR *
          gam_pos[i] = gamma[p[i]], eta_pos[i] = eta[p[i]];
       }
       /* delta = gamma delta + eta d; sol += delta; |sol|^2 (device flavour of :395-413) */
-      CHK(scale_real(S, n, gam_pos, delta, ldw, blockSize));
-      CHK(axpy_real(S, n, eta_pos, d, ldw, delta, ldw, blockSize));
-      CHK(axpy_real(S, n, one, delta, ldw, sol, ldsol, blockSize));
-      if (adaptive) CHK(dots_real(S, sol, ldsol, sol, ldsol, blockSize, dot_sol));
+      CHK(pb200_dqmr_update(S->dev, n, gam_pos, eta_pos, d, ldw, delta, ldw, sol, ldsol, blockSize, adaptive ? dot_sol : NULL));
+      if (adaptive && primme_host_sums(S)) CHK(pb_global_sum(S, dot_sol, blockSize));
 
       conv = 0;
       for (i = 0; i < blockSize; i++) p0[i] = i;

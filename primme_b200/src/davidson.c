@@ -471,9 +471,10 @@ static int solve_correction(pb_solver *S, double *evals, int numLocked, int basi
       if (cp->projectors.RightX &&
             ((cp->precondition && primme->applyPreconditioner) ||
                   (primme->locking && primme->orth == primme_orth_implicit_I))) {
-         SCALAR negEps[8];
+         SCALAR *negEps = (SCALAR *)malloc(sizeof(SCALAR) * blockSize);
          for (int b = 0; b < blockSize; b++) negEps[b] = olsenEps[b] = -olsenEps[b];
          rc = pb200_daxpy_columns(S->dev, S->n, negEps, x, S->ld, r, S->ld, blockSize);
+         free(negEps);
       }
       if (!rc && !(S->fusedP_nb == blockSize && blockSize > 0 && !cp->precondition))
          rc = pb_apply_precond(S, r, S->ld, x, S->ld, blockSize);

@@ -331,7 +331,10 @@ static int check_scope(primme_params *p) {
    else if (p->correctionParams.maxInnerIterations != 0 && p->correctionParams.precondition > 0 &&
             p->correctionParams.projectors.RightQ && p->correctionParams.projectors.SkewQ)
       why = "inner QMR iterations with the skew-Q projector and a preconditioner (K^{-1}Q and its factorised Gram matrix)";
-   else if (p->maxBlockSize > 8) why = "maxBlockSize > 8";
+   /* blocks wider than the kernels' 8-column panels are processed in chunks of 8 (dav_ortho.c, dav_project.c,
+    * the launchers); the inner QMR solver keeps its 8 systems per block */
+   else if (p->maxBlockSize > 8 && p->correctionParams.maxInnerIterations != 0)
+      why = "maxBlockSize > 8 with inner QMR iterations";
 #ifdef PB_COMPLEX
    else if (p->projectionParams.projection != primme_proj_default && p->projectionParams.projection != primme_proj_RR)
       why = "refined / harmonic extraction in complex arithmetic (Rayleigh-Ritz only)";
@@ -449,7 +452,10 @@ static int solve_typed(double *evals, SCALAR *evecs, double *resNorms, primme_pa
       rc = pb200_ctx_workspace(S->dev, 0, basis_bytes, (void **)&S->V);
       if (!rc) rc = pb200_ctx_workspace(S->dev, 1, basis_bytes, (void **)&S->W);
    }
-   if (!rc && getenv("PB200_L2_PERSIST_MB")) pb200_ctx_l2_persist(S->dev, S->V, basis_bytes);
+   /* persisting L2 window over the head of V: the panel sweeps of the GD-type methods re-read V from its first
+    * column every launch; with inner QMR iterations the hot set is the locked vectors instead, left to the L2 */
+   if (!rc && primme->correctionParams.maxInnerIterations == 0 && primme->dynamicMethodSwitch <= 0)
+      pb200_ctx_l2_persist(S->dev, S->V, basis_bytes);
    int own_evecs = 0;
    if (!rc) {
       if (device_mode) {
@@ -534,6 +540,7 @@ static int solve_typed(double *evals, SCALAR *evecs, double *resNorms, primme_pa
       primme->initSize = 0;
    }
    pb200_ctx_sync(S->dev);
+   pb200_ctx_l2_persist(S->dev, NULL, 0);
    pb_registry_set_solver(primme, NULL);
    primme->stats.elapsedTime = hl_wtime() - S->t0;
    if (getenv("PB200_DEBUG") && primme->procID == 0)

@@ -61,6 +61,7 @@
 #define pb200_dcolumn_dots pb200_zcolumn_dots
 #define pb200_dresidual_inplace pb200_zresidual_inplace
 #define pb200_djacobi pb200_zjacobi
+#define pb200_dqmr_update pb200_zqmr_update
 #endif
 #define PB_DP(p) ((double *)(p)) /* pb200_cols / pb200_vwxr_out carry untyped column pointers */
 

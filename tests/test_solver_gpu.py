@@ -95,3 +95,19 @@ def test_refined_extraction_product_matches_reference(kw):
     assert res.max() < 1e-8 * 12 * 1.1
     assert np.abs(X.T @ X - np.eye(k)).max() < 1e-7
     assert abs(got["stats"]["numOuterIterations"] - ref["stats"]["numOuterIterations"]) <= 0.35 * ref["stats"]["numOuterIterations"]
+
+
+@pytest.mark.parametrize("method,k", [("PRIMME_LOBPCG_OrthoBasis", 12), ("PRIMME_STEEPEST_DESCENT", 11)])
+def test_block_sizes_above_the_panel_width(method, k):
+    """the reference's LOBPCG / steepest-descent presets set maxBlockSize = numEvals (primme_interface.c:455,465):
+    blocks wider than the kernels' 8-column panels run in chunks of 8"""
+    from primme_b200 import api, matrices as M
+    csr = M.laplacian_nd((40, 31))
+    kw = dict(method=getattr(api, method), eps=1e-9, aNorm=8.0)
+    got = H.solve("product", csr, k, **kw)
+    ref = H.solve("reference", csr, k, **kw)
+    assert got["ret"] == 0 and ref["ret"] == 0
+    assert got["params"].maxBlockSize == k > 8
+    assert np.allclose(got["evals"], ref["evals"], rtol=1e-10)
+    SC.check_invariants(csr, got, 1e-9, 8.0)
+    assert got["launches"] > 0

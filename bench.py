@@ -151,10 +151,10 @@ def measured_peak():
 def ncu_traffic(kind, algorithmic_bytes_per_launch):
     """DRAM bytes per launch of the dominant kernel family: the ratio (dram__bytes_read.sum +
     dram__bytes_write.sum) / algorithmic bytes of the committed `ncu --set full` capture
-    (profiles/ncu_traffic_r01.json, made by scripts/gpu_profile.sh) applied to this run's
+    (profiles/ncu_traffic_r02.json, made by scripts/gpu_r2j.sh) applied to this run's
     algorithmic bytes per launch.  None when there is no capture for the family."""
     try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")) as f:
             ratio = json.load(f)["family_ratio"][kind]
         return ratio * algorithmic_bytes_per_launch
     except Exception:
@@ -173,8 +173,10 @@ def run_reference(args, csr, rank):
     times, mvs = [], []
     for step in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        r = H.solve("reference", csr, WORKLOAD["numEvals"], method=api.PRIMME_GD_Olsen_plusK, nthreads=ncores,
-                    maxMatvecs=args.ref_matvecs, **{k: v for k, v in WORKLOAD.items() if k != "numEvals"})
+        kw = {k: v for k, v in WORKLOAD.items() if k != "numEvals"}
+        if args.ref_matvecs > 0:     # bounded sample; <= 0: the whole solve (time-to-converge of the reference)
+            kw["maxMatvecs"] = args.ref_matvecs
+        r = H.solve("reference", csr, WORKLOAD["numEvals"], method=api.PRIMME_GD_Olsen_plusK, nthreads=ncores, **kw)
         dt = time.perf_counter() - t0
         if step >= args.warmup:
             times.append(r["stats"]["elapsedTime"] or dt)
@@ -472,7 +474,8 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args.side), "n": n, "nnz": nnz},
                 "cpu_baseline": {"value": val, "unit": "matvecs/s", "cores": ncores, "kind": "reference",
-                                 "sample": f"first {mv} matvecs of the solve (maxMatvecs bound), "
+                                 "sample": (f"first {mv} matvecs of the solve (maxMatvecs bound), " if args.ref_matvecs > 0
+                                            else f"the whole solve ({mv} matvecs, time to converge {sec:.1f} s), ") +
                                            f"OpenBLAS {ncores} threads + {ncores}-thread CSR callback"},
                 "e2e": {"value": val, "unit": "matvecs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -642,7 +645,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": prof[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": prof[dom]["gbs"] / peak, "peak_source": peak_src,
                 "traffic": ncu_traffic(dom, prof[dom]["bytes"] / max(1, prof[dom]["launches"])),
-                "traffic_source": "profiles/ncu_traffic_r01.json (ncu --set full DRAM bytes / algorithmic bytes at the C2 shapes)",
+                "traffic_source": "profiles/ncu_traffic_r02.json (ncu --set full DRAM bytes / algorithmic bytes at the C2 shapes, cold L2)",
                 "launches": prof[dom]["launches"], "avg_launch_us": 1e3 * prof[dom]["ms"] / max(1, prof[dom]["launches"]),
                 "algorithmic_bytes_per_launch": prof[dom]["bytes"] / max(1, prof[dom]["launches"]),
                 "all_kernels": {kname: {"GBps": round(v["gbs"], 1), "ms": round(v["ms"], 3), "launches": v["launches"]}

@@ -22,6 +22,7 @@
 #include <string.h>
 #include <vector>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace {
 
@@ -839,6 +840,302 @@ int launch_vwxr_mma(pb200_ctx *ctx, const VwxrArgs &a, const VwxrMaps &maps, int
    return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Restart kernel (8 < nh <= 48): the columns of h are split over the warps, so the register file
+// of a warp holds one 8-column tile of X = V h / Y = W h and a share of the Gram tiles instead of
+// all of them (the one-warp-per-8-rows kernel above needs 168 registers at nh = 24 and cannot
+// hold nh > 32 at all: 8 warps per SM, instruction-latency bound).
+//   warp (rg, CG): row group rg (16 rows of the tile), column tile CG (columns 8 CG .. 8 CG + 7)
+//   phase 1   X, Y for 2 x 8 rows: per k-step TWO 16-byte fragment loads (rows 2g, 2g+1 of column
+//             t + 4 ks of V and of W: fragment row g of the first / second 8-row half) feed FOUR DMMAs
+//             whose B fragment (h) is one 8-byte load; residuals, norms and the column scatter from
+//             the accumulator layout with 16-byte stores (two consecutive rows of a column)
+//   phase 2   the warps of a row group exchange their tiles through a double-buffered transposing
+//             scratch ([column][16 rows], one named barrier per tile) and each accumulates every
+//             NT8-th tile of G = X^T X (upper tiles) and H = X^T Y; the k index of these products
+//             is the row inside the group in the order 4 t + ks, so a fragment for all four k-steps
+//             is two 16-byte loads
+// 12-16 consumer warps per SM; a row is written by the warps of ONE row group after the whole
+// tile has landed in shared memory, so the in-place restart V <- V h stays safe.
+constexpr int CG_LD = 18;  // row stride (doubles) of the exchange scratch: conflict-free 16-byte stores and loads
+
+template <int NT8>
+struct CgTiles {
+   static constexpr int NGT = NT8 * (NT8 + 1) / 2, NHT = NT8 * NT8, NTILES = NGT + NHT;
+   // tile id -> (ti, tj): G ids tj (tj + 1) / 2 + ti (ti <= tj), H ids NGT + ti + NT8 tj
+   __host__ __device__ static constexpr int is_h(int e) { return e >= NGT; }
+   __host__ __device__ static constexpr int tj(int e) {
+      if (e >= NGT) return (e - NGT) / NT8;
+      int j = 0;
+      while ((j + 1) * (j + 2) / 2 <= e) j++;
+      return j;
+   }
+   __host__ __device__ static constexpr int ti(int e) {
+      if (e >= NGT) return (e - NGT) % NT8;
+      return e - tj(e) * (tj(e) + 1) / 2;
+   }
+};
+
+template <int I, int N, class F>
+__device__ __forceinline__ void cg_static_for(F &&f) {
+   if constexpr (I < N) {
+      f(std::integral_constant<int, I>{});
+      cg_static_for<I + 1, N>(f);
+   }
+}
+
+template <int NT8, int NRG, int CG>
+__device__ __forceinline__ void vwxr_cg_consumer(const VwxrArgs &a, const double *stage0, int stage_sz, const double *hs,
+      const double *th, double *scr0, uint64_t *full, uint64_t *empty, int nstages, int rgw, int lane) {
+   using T = CgTiles<NT8>;
+   constexpr int TR = 16 * NRG, S = TR + 4, NC = 8 * NT8, HS_LD = NC + 4;
+   constexpr int NA = (T::NTILES - CG + NT8 - 1) / NT8;  // tiles of G / H this warp accumulates
+   const int g = lane >> 2, t = lane & 3;
+   const int mpad = a.mpad, nks = mpad >> 2;
+   const int64_t ntiles = (a.n + TR - 1) / TR;
+   const bool gh = a.nG > 0 || a.nH > 0;
+   const int nR = a.R.ptr ? a.R.ce - a.R.cb : 0;
+
+   // store plan of this thread's two columns 8 CG + 2 t + j
+   double *px[2][3], *py[2], *pr[2];
+   double thv[2];
+   bool wn[2];
+#pragma unroll
+   for (int j = 0; j < 2; j++) {
+      const int cc = 8 * CG + 2 * t + j;
+      thv[j] = th[cc];
+#pragma unroll
+      for (int u = 0; u < 3; u++)
+         px[j][u] = (a.X[u].ptr && cc >= a.X[u].cb && cc < a.X[u].ce) ? a.X[u].ptr + (size_t)(cc - a.X[u].cb) * a.X[u].ld : nullptr;
+      py[j] = (a.Wo.ptr && cc >= a.Wo.cb && cc < a.Wo.ce) ? a.Wo.ptr + (size_t)(cc - a.Wo.cb) * a.Wo.ld : nullptr;
+      const bool inR = nR > 0 && cc >= a.R.cb && cc < a.R.ce;
+      pr[j] = inR ? a.R.ptr + (size_t)(cc - a.R.cb) * a.R.ld : nullptr;
+      wn[j] = inR || (cc >= a.rb && cc < a.re);
+   }
+   double nrm[2] = {0.0, 0.0};
+   double acc[NA][2];
+#pragma unroll
+   for (int i = 0; i < NA; i++) acc[i][0] = acc[i][1] = 0.0;
+
+   const int offu = t * S + 16 * rgw + 2 * g;
+   const double *hb = hs + t * HS_LD + 8 * CG + g;
+   double *scr = scr0 + (size_t)rgw * 2 * 2 * NC * CG_LD;       // [buffer][X | Y][column][CG_LD]
+   const int so = (8 * CG + 2 * t) * CG_LD + 2 * g;             // own tile, column 2 t, rows 2 g, 2 g + 1
+   const int lo = g * CG_LD + 4 * t;                            // operand: column g of a tile, rows 4 t .. 4 t + 3
+
+   int s = 0, it = 0;
+   uint32_t ph = 0;
+   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it ^= 1) {
+      pbtma::mbar_wait(&full[s], ph);
+      const double *st = stage0 + (size_t)s * stage_sz;
+      double X[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, Y[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // [row half][column 2 t + j]
+      {
+         const double *pv = st + offu, *pw = pv + mpad * S, *pb = hb;
+#pragma unroll 4
+         for (int ks = 0; ks < nks; ks++) {
+            const double2 av = *reinterpret_cast<const double2 *>(pv);
+            const double2 aw = *reinterpret_cast<const double2 *>(pw);
+            const double bf = pb[0];
+            vdmma884(X[0][0], X[0][1], av.x, bf);
+            vdmma884(X[1][0], X[1][1], av.y, bf);
+            vdmma884(Y[0][0], Y[0][1], aw.x, bf);
+            vdmma884(Y[1][0], Y[1][1], aw.y, bf);
+            pv += 4 * S, pw += 4 * S, pb += 4 * HS_LD;
+         }
+      }
+      __syncwarp();
+      if (lane == 0) pbtma::mbar_arrive(&empty[s]);
+      // ---- residuals, norms, scatter: rows r, r + 1 of columns 8 CG + 2 t + j ----
+      const int64_t r = PB_TILE(tile) * TR + 16 * rgw + 2 * g;
+      const bool ok2 = r + 1 < a.n, ok1 = r < a.n;
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+         const double x0 = X[0][j], x1 = X[1][j], y0 = Y[0][j], y1 = Y[1][j];
+         const double e0 = y0 - x0 * thv[j], e1 = y1 - x1 * thv[j];
+         if (wn[j]) nrm[j] += e0 * e0 + e1 * e1;
+         if (ok2) {
+#pragma unroll
+            for (int u = 0; u < 3; u++)
+               if (px[j][u]) *reinterpret_cast<double2 *>(px[j][u] + r) = make_double2(x0, x1);
+            if (py[j]) *reinterpret_cast<double2 *>(py[j] + r) = make_double2(y0, y1);
+            if (pr[j]) *reinterpret_cast<double2 *>(pr[j] + r) = make_double2(e0, e1);
+         } else if (ok1) {
+#pragma unroll
+            for (int u = 0; u < 3; u++)
+               if (px[j][u]) px[j][u][r] = x0;
+            if (py[j]) py[j][r] = y0;
+            if (pr[j]) pr[j][r] = e0;
+         }
+      }
+      if (gh) {
+         double *xs = scr + (size_t)it * 2 * NC * CG_LD, *ys = xs + NC * CG_LD;
+         *reinterpret_cast<double2 *>(xs + so) = make_double2(X[0][0], X[1][0]);
+         *reinterpret_cast<double2 *>(xs + so + CG_LD) = make_double2(X[0][1], X[1][1]);
+         *reinterpret_cast<double2 *>(ys + so) = make_double2(Y[0][0], Y[1][0]);
+         *reinterpret_cast<double2 *>(ys + so + CG_LD) = make_double2(Y[0][1], Y[1][1]);
+         pbtma::named_bar_sync(1 + rgw, 32 * NT8);
+#pragma unroll
+         for (int half = 0; half < 2; half++) {
+            double2 xf[NT8], yf[NT8];
+#pragma unroll
+            for (int i = 0; i < NT8; i++) {
+               xf[i] = *reinterpret_cast<const double2 *>(xs + 8 * i * CG_LD + lo + 2 * half);
+               yf[i] = *reinterpret_cast<const double2 *>(ys + 8 * i * CG_LD + lo + 2 * half);
+            }
+            cg_static_for<0, NA>([&](auto qc) {
+               constexpr int q = decltype(qc)::value, e = CG + q * NT8;
+               if constexpr (e < T::NTILES) {
+                  constexpr int ti = T::ti(e), tj = T::tj(e);
+                  const double2 af = xf[ti];
+                  const double2 bf = T::is_h(e) ? yf[tj] : xf[tj];
+                  vdmma884(acc[q][0], acc[q][1], af.x, bf.x);
+                  vdmma884(acc[q][0], acc[q][1], af.y, bf.y);
+               }
+            });
+         }
+      }
+      if (++s == nstages) s = 0, ph ^= 1;
+   }
+
+   // ---- per-warp tiles -> one partial panel per CTA: row groups summed in order, through the stage memory ----
+   const int nn = (nR + (a.re - a.rb)) > 0 ? a.nh : 0;
+   const int cnt = nn + a.nG * a.nG + a.nH * a.nH;
+   if (cnt <= 0) return;
+   constexpr int NCT = NT8 * NRG * 32;
+   constexpr int WSZ = T::NTILES * 64 + NC;  // doubles per row group
+   pbtma::named_bar_sync(8, NCT);  // every warp is done with the stages
+   double *red = const_cast<double *>(stage0) + (size_t)rgw * WSZ;
+   cg_static_for<0, NA>([&](auto qc) {
+      constexpr int q = decltype(qc)::value, e = CG + q * NT8;
+      if constexpr (e < T::NTILES)
+         *reinterpret_cast<double2 *>(red + ((size_t)e * 8 + g) * 8 + 2 * t) = make_double2(acc[q][0], acc[q][1]);
+   });
+#pragma unroll
+   for (int j = 0; j < 2; j++) {
+      double v = nrm[j];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (g == 0) red[T::NTILES * 64 + 8 * CG + 2 * t + j] = v;
+   }
+}
+
+template <int NT8, int NRG>
+__global__ void __launch_bounds__(NT8 * NRG * 32 + 32) vwxr_cg_kernel(VwxrArgs a, const __grid_constant__ PbCoef coef,
+      const __grid_constant__ VwxrMaps maps, int nstages) {
+   using T = CgTiles<NT8>;
+   constexpr int NW = NT8 * NRG, TR = 16 * NRG, S = TR + 4, NCT = NW * 32;
+   constexpr int NC = 8 * NT8, HS_LD = NC + 4;
+   extern __shared__ __align__(128) unsigned char smraw[];
+   const int m = a.m, mpad = a.mpad;
+   const int stage_sz = 2 * mpad * S;
+   double *stage0 = reinterpret_cast<double *>(smraw);
+   double *hs = stage0 + a.stage_doubles;    // mpad * HS_LD
+   double *th = hs + (size_t)mpad * HS_LD;   // NC
+   double *scr0 = th + NC;                   // NRG * 2 * 2 * NC * CG_LD
+   uint64_t *full = reinterpret_cast<uint64_t *>(scr0 + (size_t)NRG * 4 * NC * CG_LD);
+   uint64_t *empty = full + nstages;
+   int *flag = reinterpret_cast<int *>(empty + nstages);
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+   if (tid == 0) {
+      for (int s = 0; s < nstages; s++) {
+         pbtma::mbar_init(&full[s], 1);
+         pbtma::mbar_init(&empty[s], NW);
+      }
+      pbtma::fence_barrier_init();
+   }
+   {
+      const double *hg = a.coef_inline ? coef.v : a.hdev;
+      const double *tg = a.coef_inline ? coef.v + (size_t)m * a.nh : a.thetadev;
+      for (int i = tid; i < mpad * NC; i += NCT + 32) {
+         const int k = i / NC, c = i % NC;
+         hs[k * HS_LD + c] = (k < m && c < a.nh) ? hg[k + (size_t)c * m] : 0.0;
+      }
+      for (int i = tid; i < NC; i += NCT + 32) th[i] = i < a.nh ? tg[i] : 0.0;
+   }
+   __syncthreads();
+
+   const int64_t ntiles = (a.n + TR - 1) / TR;
+   if (warp == NW) {
+      if (lane != 0) return;
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t bytes = (uint32_t)(stage_sz * sizeof(double));
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+         pbtma::mbar_wait(&empty[s], ph ^ 1);
+         double *dst = stage0 + (size_t)s * stage_sz;
+         const int r0 = (int)(PB_TILE(tile) * TR);
+         pbtma::mbar_arrive_expect_tx(&full[s], bytes);
+         pbtma::tensor_g2s_2d(dst, &maps.v, r0, 0, &full[s]);
+         pbtma::tensor_g2s_2d(dst + mpad * S, &maps.w, r0, 0, &full[s]);
+         if (++s == nstages) s = 0, ph ^= 1;
+      }
+      return;
+   }
+   // warp -> (row group, column tile): the warps of a row group are consecutive
+   const int rgw = warp / NT8, cg = warp % NT8;
+#define PB_CG_CASE(C_) \
+   case C_: \
+      if constexpr (C_ < NT8) vwxr_cg_consumer<NT8, NRG, (C_ < NT8 ? C_ : 0)>(a, stage0, stage_sz, hs, th, scr0, full, empty, nstages, rgw, lane); \
+      break;
+   switch (cg) {
+      PB_CG_CASE(0) PB_CG_CASE(1) PB_CG_CASE(2) PB_CG_CASE(3) PB_CG_CASE(4) PB_CG_CASE(5)
+   }
+#undef PB_CG_CASE
+
+   const int nR = a.R.ptr ? a.R.ce - a.R.cb : 0;
+   const int nn = (nR + (a.re - a.rb)) > 0 ? a.nh : 0;
+   const int cnt = nn + a.nG * a.nG + a.nH * a.nH;
+   if (cnt <= 0) return;
+   constexpr int WSZ = T::NTILES * 64 + NC;
+   pbtma::named_bar_sync(8, NCT);
+   double *out = a.partials + (size_t)blockIdx.x * cnt;
+   const int offG = nn, offH = offG + a.nG * a.nG;
+   for (int e = tid; e < cnt; e += NCT) {
+      int idx;
+      if (e < offG) {
+         idx = T::NTILES * 64 + e;
+      } else if (e < offH) {
+         int i = (e - offG) % a.nG, j = (e - offG) / a.nG;
+         if (i > j) { const int sw = i; i = j, j = sw; }  // G is symmetric: upper tiles only
+         const int ti = i >> 3, tj = j >> 3;
+         idx = ((tj * (tj + 1) / 2 + ti) * 8 + (i & 7)) * 8 + (j & 7);
+      } else {
+         const int i = (e - offH) % a.nH, j = (e - offH) / a.nH;
+         idx = ((T::NGT + (i >> 3) + NT8 * (j >> 3)) * 8 + (i & 7)) * 8 + (j & 7);
+      }
+      double sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < NRG; w++) sum += stage0[(size_t)w * WSZ + idx];
+      out[e] = sum;
+   }
+   pb_finish_device(a.fin, tid, NCT, 15, flag);
+}
+
+template <int NT8, int NRG>
+int launch_vwxr_cg(pb200_ctx *ctx, const VwxrArgs &a, const VwxrMaps &maps, int grid, size_t shmem, int nstages) {
+   auto kern = vwxr_cg_kernel<NT8, NRG>;
+   static size_t attr_shmem = 0;
+   if (shmem > attr_shmem) {
+      PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+      attr_shmem = shmem;
+   }
+   if (getenv("PB200_DEBUG")) {
+      static size_t seen = 0;
+      if (seen != shmem) {
+         seen = shmem;
+         cudaFuncAttributes fa;
+         cudaFuncGetAttributes(&fa, kern);
+         fprintf(stderr, "primme_b200: vwxr_cg<%d,%d> dyn smem %zu regs %d stages %d\n", NT8, NRG, shmem, fa.numRegs, nstages);
+      }
+   }
+   kern<<<grid, NT8 * NRG * 32 + 32, shmem, ctx->stream>>>(a, ctx->coef, maps, nstages);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   return 0;
+}
+
 template <int NTH, int NG>
 int launch_vwxr_wide(pb200_ctx *ctx, const VwxrArgs &a, int grid, size_t shmem, int nstages, int park_cols) {
    auto kern = vwxr_wide_kernel<NTH, NG>;
@@ -1002,8 +1299,48 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
       if (mma_nt8) cnt += (m + a.nP) * a.nP;
    }
 
+   // ---- restart plan: columns of h split over the warps (8 < nh <= 48, no P panel) ----
+   int cg_nt8 = 0, cg_nrg = 0, cg_nst = 0;
+   size_t cg_shm = 0;
+   {
+      const int nt8 = (nh + 7) / 8;
+      const int ngh = a.nG > a.nH ? a.nG : a.nH;
+      static const int use_cg = getenv("PB200_VWXR_CG") ? atoi(getenv("PB200_VWXR_CG")) : 1;
+      auto al = [](const pb200_cols &c) { return !c.ptr || ((((uintptr_t)c.ptr) & 15) == 0 && c.ld % 2 == 0); };
+      bool ok = use_cg && ctx->use_tma_vwxr && ctx->use_mma_vwxr && a.need_y && !o->P_host && !a.R2 && nt8 >= 2 && nt8 <= 6 &&
+                ngh <= 8 * nt8 && m > 0 && m <= 96 && n >= 256 && (((uintptr_t)V) & 15) == 0 && (((uintptr_t)W) & 15) == 0 &&
+                ld % 2 == 0 && al(a.X[0]) && al(a.X[1]) && al(a.X[2]) && al(a.Wo) && al(a.R);
+      if (ok) {
+         static const int nrg_tab[7] = {0, 0, 4, 4, 3, 3, 2};
+         const int nrg = nrg_tab[nt8], NC = 8 * nt8, mpad = (m + 3) & ~3;
+         const size_t stage = (size_t)2 * mpad * (16 * nrg + 4);
+         const size_t wsz = (size_t)(nt8 * (nt8 + 1) / 2 + nt8 * nt8) * 64 + NC;
+         const size_t fixed = ((size_t)mpad * (NC + 4) + NC + (size_t)nrg * 4 * NC * CG_LD) * sizeof(double) + 2 * 8 * sizeof(uint64_t) + 64;
+         int st = (int)((227 * 1024 - fixed) / (stage * sizeof(double)));
+         if (st > 6) st = 6;
+         size_t ring = (size_t)(st > 0 ? st : 0) * stage;
+         if (ring < wsz * nrg) ring = wsz * nrg;
+         const size_t shm = ring * sizeof(double) + fixed;
+         ok = st >= 2 && shm <= 227 * 1024;
+         VwxrMaps cmaps;
+         memset(&cmaps, 0, sizeof(cmaps));
+         ok = ok && !pb_tensor_map_2d(&cmaps.v, V, n, m, ld, 16 * nrg + 4, mpad) && !pb_tensor_map_2d(&cmaps.w, W, n, m, ld, 16 * nrg + 4, mpad);
+         if (ok) {
+            cg_nt8 = nt8, cg_nrg = nrg, cg_nst = st, cg_shm = shm;
+            a.mpad = mpad, a.stage_doubles = (int)ring, a.nP = 0;
+            maps = cmaps;
+            mma_nt8 = 0;  // (no P panel in either plan here: cnt is unchanged)
+         }
+      }
+   }
+
    int grid = 1, ppc = 1, rc = 0;
-   if (mma_nt8) {
+   if (cg_nt8) {
+      a.rev = ctx->sweep_alternate ? (ctx->sweep_rev ^= 1) : 0;
+      const int tr = 16 * cg_nrg;
+      const int64_t ntiles = (n + tr - 1) / tr;
+      grid = (int)(ntiles < (int64_t)ctx->num_sms ? ntiles : (int64_t)ctx->num_sms);
+   } else if (mma_nt8) {
       a.rev = ctx->sweep_alternate ? (ctx->sweep_rev ^= 1) : 0;
       const int tr = 8 * mma_nw;
       const int64_t ntiles = (n + tr - 1) / tr;
@@ -1026,7 +1363,12 @@ static int vwxr_fast(pb200_ctx *ctx, int64_t n, const double *V, const double *W
       a.partials = ctx->d_partials;
    }
    int ps = pb_prof_begin(ctx, PB_K_VWXR);
-   if (mma_nt8) {
+   if (cg_nt8) {
+#define VC(NT8_, NRG_) \
+   if (cg_nt8 == NT8_ && cg_nrg == NRG_) rc = launch_vwxr_cg<NT8_, NRG_>(ctx, a, maps, grid, cg_shm, cg_nst);
+      VC(2, 4) VC(3, 4) VC(4, 3) VC(5, 3) VC(6, 2)
+#undef VC
+   } else if (mma_nt8) {
 #define VM(NT8_, MT_, NW_) \
    if (mma_nt8 == NT8_ && mma_mt == MT_ && mma_nw == NW_) rc = launch_vwxr_mma<NT8_, MT_, NW_>(ctx, a, maps, grid, mma_shm, mma_nst);
       VM(1, 0, 16) VM(1, 5, 16) VM(1, 0, 8) VM(1, 5, 8) VM(1, 9, 8) VM(2, 0, 8) VM(3, 0, 8) VM(3, 0, 10) VM(4, 0, 8)

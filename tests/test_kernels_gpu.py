@@ -138,6 +138,11 @@ def test_ortho_sweep(libs, n, q, mv, b, update, useY, xx):
     (4096 + 8, 33, 29, "lock"),     # four tiles
     (130000, 40, 24, "restart"),    # several tiles per CTA: ring wrap-around
     (150000, 28, 4, "candp"),
+    (5000 + 2, 64, 44, "restart"),  # six tiles of h: the column-split restart kernel <6,2>
+    (4097, 48, 40, "lock"),         # five tiles, odd n (single-row tail store), columns to evecs
+    (70000 + 6, 64, 40, "restart"), # C5 restart shape, several tiles per CTA
+    (9000, 24, 16, "restart"),      # two tiles <2,4>
+    (3001, 96, 28, "restart"),      # widest basis the staged kernels take (4 tiles)
 ])
 def test_vwxr(libs, n, m, nh, case):
     rng = np.random.default_rng(99 + n + m + nh)

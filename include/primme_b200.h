@@ -93,6 +93,10 @@ int pb200_csr_create_pooled(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_
       int index_base, int is_complex, pb200_csr **A);
 int pb200_csr_destroy(pb200_ctx *ctx, pb200_csr *A);
 int64_t pb200_csr_nnz(const pb200_csr *A);
+/* gather layout the product of width ncols runs with on this matrix, decided by timing at the first
+ * product: 0 not decided yet, 1 column-major gathers, 2 row-major gather copy, 3 windowed right-hand
+ * sides staged in shared memory (matrices with column locality; see csrc/spmm.cu) */
+int pb200_csr_layout(const pb200_csr *A, int ncols);
 int pb200_dspmm(pb200_ctx *ctx, const pb200_csr *A, const double *X, int64_t ldx, double *Y,
       int64_t ldy, int ncols);
 /* complex twin (zprimme): A created with is_complex = 1; X, Y interleaved (re,im), column-major,

@@ -249,7 +249,16 @@ struct pb200_csr {
    double *d_G;
    size_t G_cap;  // doubles
    int pooled;            // device arrays live in the context's matrix pool (not freed by pb200_csr_destroy)
-   int layout_choice[4];  // per block width 1/2/4/8: 0 not timed yet, 1 column-major gathers (v2), 2 row-major (v3)
+   int layout_choice[4];  // per block width 1/2/4/8: 0 not timed yet, 1 column-major gathers (v2), 2 row-major (v3), 3 windowed (v4)
+   // windowed right-hand sides (v4, spmm.cu): row blocks of <= 512 rows, per block the runs of 32-column
+   // segments its nonzeros touch and 16-bit window offsets instead of column indices
+   int win_state;         // 0 not analysed, 1 usable, -1 not usable (no locality, long rows, complex)
+   int win_nblocks, win_maxseg;
+   int64_t *d_w_row0;     // win_nblocks + 1
+   int32_t *d_w_nrun;     // win_nblocks
+   void *d_w_run;         // win_nblocks x 32 (int2: first segment, window slot << 16 | segments)
+   uint16_t *d_wcol;      // nnz
+   int *d_w_state;        // [0] not usable, [1] max segments per block
 };
 
 // halo protocol of the row-sharded operator (dist.cu) seen by the SpMM kernel: wait until every

@@ -712,6 +712,259 @@ __global__ void spmm_long_fixup3(const int64_t *__restrict__ lr_row, const int32
    else Y[lr_row[lr] + (size_t)c * ldy] = s;
 }
 
+// ------------------------------------------------------------------------------------------
+// v4: WINDOWED right-hand sides for matrices with column locality (banded / stencil matrices).
+// The rows of a block of <= SW_ROWS rows reference a few short runs of columns (a 7-point stencil:
+// three runs around r - n1 n2, r, r + n1 n2).  spmm_win_analyze (once per matrix, on the device)
+// finds, per row block, the distinct 32-column segments its nonzeros touch, merges consecutive
+// segments into runs and rewrites every column index as a 16-bit offset into the block's window.
+// The kernel's producer warp then stages, per block, the matrix slice (8 + 2 bytes per nonzero
+// instead of 8 + 4) AND the window of every right-hand-side column (one bulk copy per run and
+// column, straight from the column-major block: no packing pass), and the consumers read x from
+// shared memory.  Traffic from L2 per row drops from one gather per nonzero (7 for the stencil)
+// to the window length per row (3.4-4), none of it through L1/LSU.  A matrix qualifies when EVERY
+// block fits the limits below; which layout runs is still decided by timing (tune_layout).
+constexpr int SW_NNZ = 4096;     // staged nonzeros per block
+constexpr int SW_ROWS = 512;     // rows per block
+constexpr int SW_SEG = 32;       // columns per segment (256 bytes of a column of X)
+constexpr int SW_MAXSEG = 96;    // distinct segments per block (window of 3072 columns)
+constexpr int SW_MAXRUN = 32;    // runs of consecutive segments per block (one producer lane each)
+constexpr int SW_VALS = SW_NNZ + 16;
+constexpr int SW_RP = SW_ROWS + 4;
+constexpr size_t SW_OFF_COL = (size_t)SW_VALS * 8;
+constexpr size_t SW_OFF_RP = SW_OFF_COL + (size_t)SW_VALS * 2;
+constexpr size_t SW_OFF_HDR = SW_OFF_RP + (size_t)SW_RP * 8;
+constexpr size_t SW_OFF_WIN = (SW_OFF_HDR + 64 + 127) / 128 * 128;
+
+// state[0]: 1 = some block does not fit (matrix not windowable), state[1]: max segments of a block
+__global__ void __launch_bounds__(256) spmm_win_analyze(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+      const int64_t *__restrict__ w_row0, int nwb, int32_t *__restrict__ w_nrun, int2 *__restrict__ w_run,
+      uint16_t *__restrict__ wcol, int *state) {
+   __shared__ uint32_t tab[256];
+   __shared__ uint32_t sorted[SW_MAXSEG + 1];
+   __shared__ int s_nd, s_nrun;
+   const int tid = threadIdx.x;
+   for (int blk = blockIdx.x; blk < nwb; blk += gridDim.x) {
+      if (*(volatile int *)&state[0]) return;
+      const int64_t r0 = w_row0[blk], r1 = w_row0[blk + 1];
+      const int64_t nz0 = rowptr[r0];
+      const int nnzb = (int)(rowptr[r1] - nz0);
+      tab[tid] = 0xffffffffu;
+      if (tid == 0) s_nd = 0, s_nrun = 0;
+      __syncthreads();
+      for (int i = tid; i < nnzb; i += 256) {
+         const uint32_t seg = (uint32_t)colind[nz0 + i] / SW_SEG;
+         uint32_t h = (seg * 2654435761u) >> 24;
+         for (int probe = 0; probe < 256; probe++) {
+            if (*(volatile int *)&s_nd > SW_MAXSEG) break;
+            const uint32_t old = atomicCAS(&tab[h], 0xffffffffu, seg);
+            if (old == 0xffffffffu) {
+               atomicAdd(&s_nd, 1);
+               break;
+            }
+            if (old == seg) break;
+            h = (h + 1) & 255;
+         }
+      }
+      __syncthreads();
+      const int nd = s_nd;
+      if (nd > SW_MAXSEG) {
+         if (tid == 0) atomicExch(&state[0], 1);
+         return;
+      }
+      // rank sort of the distinct segments
+      {
+         const uint32_t mine = tab[tid];
+         if (mine != 0xffffffffu) {
+            int rank = 0;
+            for (int j = 0; j < 256; j++) rank += tab[j] < mine;  // empty slots hold 0xffffffff
+            sorted[rank] = mine;
+         }
+      }
+      __syncthreads();
+      if (tid == 0) {
+         int nrun = 0;
+         for (int j = 0; j < nd;) {
+            int k = j + 1;
+            while (k < nd && sorted[k] == sorted[k - 1] + 1) k++;
+            if (nrun < SW_MAXRUN) w_run[(size_t)blk * SW_MAXRUN + nrun] = make_int2((int)sorted[j], (j << 16) | (k - j));
+            nrun++;
+            j = k;
+         }
+         s_nrun = nrun;
+         w_nrun[blk] = nrun;
+         if (nrun > SW_MAXRUN) atomicExch(&state[0], 1);
+         atomicMax(&state[1], nd);
+      }
+      __syncthreads();
+      if (s_nrun > SW_MAXRUN) return;
+      for (int i = tid; i < nnzb; i += 256) {
+         const uint32_t col = (uint32_t)colind[nz0 + i], seg = col / SW_SEG;
+         int lo = 0, hi = nd - 1;
+         while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (sorted[mid] < seg) lo = mid + 1;
+            else hi = mid;
+         }
+         wcol[nz0 + i] = (uint16_t)(lo * SW_SEG + (col % SW_SEG));
+      }
+      __syncthreads();
+   }
+}
+
+struct SwStageHdr {
+   int64_t row0, nzbase, rpbase;
+   int32_t nrows, pad_[5];
+};
+
+template <int BT, int LPR>
+__global__ void __launch_bounds__(SPT_THREADS, 1) spmm_win_kernel(const int64_t *__restrict__ rowptr,
+      const uint16_t *__restrict__ wcol, const double *__restrict__ vals, const int64_t *__restrict__ w_row0,
+      const int32_t *__restrict__ w_nrun, const int2 *__restrict__ w_run, int nwb, int64_t ncols,
+      const double *__restrict__ X, int64_t ldx, double *__restrict__ Y, int64_t ldy, int b, int nstages,
+      int wlen /*doubles per column window*/, uint32_t stage_bytes) {
+   extern __shared__ __align__(128) unsigned char smraw[];
+   __shared__ uint64_t full[8], empty[8];
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   if (tid == 0) {
+      for (int s = 0; s < nstages; s++) {
+         pbtma::mbar_init(&full[s], 1);
+         pbtma::mbar_init(&empty[s], SPT_CONS / 32);
+      }
+      pbtma::fence_barrier_init();
+   }
+   __syncthreads();
+
+   if (warp == SPT_CONS / 32) {
+      // -------- producer warp: lane 0 streams the matrix slice, lane r the windows of run r --------
+      int s = 0;
+      uint32_t ph = 0;
+      const uint64_t pol = pbtma::l2_policy_evict_first();
+      for (int blk = blockIdx.x; blk < nwb; blk += gridDim.x) {
+         const int64_t row0 = w_row0[blk], row1 = w_row0[blk + 1];
+         const int nrows = (int)(row1 - row0);
+         const int nrun = w_nrun[blk];
+         int2 run = make_int2(0, 0);
+         if (lane < nrun) run = w_run[(size_t)blk * SW_MAXRUN + lane];
+         const int64_t c0 = (int64_t)run.x * SW_SEG;
+         int64_t len = (int64_t)(run.y & 0xffff) * SW_SEG;
+         if (c0 + len > ncols) len = ((ncols - c0) + 1) & ~(int64_t)1;  // last segment: even count, inside ldx
+         if (lane >= nrun) len = 0;
+         const uint32_t wbytes = (uint32_t)len * 8u;
+         uint32_t tot = wbytes * (uint32_t)b;
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+         unsigned char *st = smraw + (size_t)s * stage_bytes;
+         if (lane == 0) {
+            const int64_t nz0 = rowptr[row0], nz1 = rowptr[row1];
+            const int64_t nzbase = nz0 & ~(int64_t)7;
+            const int cnt = (int)((nz1 - nzbase + 7) & ~(int64_t)7);
+            const int64_t rpbase = row0 & ~(int64_t)1;
+            const int rpcnt = (int)((row1 + 1 - rpbase + 1) & ~(int64_t)1);
+            pbtma::mbar_wait(&empty[s], ph ^ 1);
+            SwStageHdr *hdr = reinterpret_cast<SwStageHdr *>(st + SW_OFF_HDR);
+            hdr->row0 = row0, hdr->nzbase = nzbase, hdr->rpbase = rpbase, hdr->nrows = nrows;
+            pbtma::mbar_arrive_expect_tx(&full[s], tot + (uint32_t)cnt * 10u + (uint32_t)rpcnt * 8u);
+            if (cnt > 0) {
+               pbtma::bulk_g2s_hint(st, vals + nzbase, (uint32_t)cnt * 8u, &full[s], pol);
+               pbtma::bulk_g2s_hint(st + SW_OFF_COL, wcol + nzbase, (uint32_t)cnt * 2u, &full[s], pol);
+            }
+            pbtma::bulk_g2s(st + SW_OFF_RP, rowptr + rpbase, (uint32_t)rpcnt * 8u, &full[s]);
+         }
+         __syncwarp();  // the stage is free and the transaction count is armed
+         if (wbytes > 0) {
+            double *win = reinterpret_cast<double *>(st + SW_OFF_WIN) + (size_t)(run.y >> 16) * SW_SEG;
+            for (int c = 0; c < b; c++)
+               pbtma::bulk_g2s(win + (size_t)c * wlen, X + (size_t)c * ldx + c0, wbytes, &full[s]);
+         }
+         if (++s == nstages) s = 0, ph ^= 1;
+      }
+      return;
+   }
+
+   // -------- consumers --------
+   int s = 0;
+   uint32_t ph = 0;
+   constexpr int RPP = SPT_CONS / LPR;  // rows per pass
+   const int sub = tid % LPR;
+   for (int blk = blockIdx.x; blk < nwb; blk += gridDim.x) {
+      pbtma::mbar_wait(&full[s], ph);
+      const unsigned char *st = smraw + (size_t)s * stage_bytes;
+      const double *s_val = reinterpret_cast<const double *>(st);
+      const uint16_t *s_col = reinterpret_cast<const uint16_t *>(st + SW_OFF_COL);
+      const int64_t *s_rp = reinterpret_cast<const int64_t *>(st + SW_OFF_RP);
+      const SwStageHdr *hdr = reinterpret_cast<const SwStageHdr *>(st + SW_OFF_HDR);
+      const double *win = reinterpret_cast<const double *>(st + SW_OFF_WIN);
+      const int64_t row0 = hdr->row0, nzbase = hdr->nzbase;
+      const int nrows = hdr->nrows;
+      const int rpoff = (int)(row0 - hdr->rpbase);
+      for (int base = 0; base < nrows; base += RPP) {
+         const int rl = base + tid / LPR;
+         const bool active = rl < nrows;
+         int sidx = 0, e = 0;
+         if (active) sidx = (int)(s_rp[rpoff + rl] - nzbase), e = (int)(s_rp[rpoff + rl + 1] - nzbase);
+         double acc[BT];
+#pragma unroll
+         for (int c = 0; c < BT; c++) acc[c] = 0.0;
+         for (int i = sidx + sub; i < e; i += LPR) {
+            const double v = s_val[i];
+            const double *xp = win + s_col[i];
+#pragma unroll
+            for (int c = 0; c < BT; c++)
+               if (c < b) acc[c] = fma(v, xp[(size_t)c * wlen], acc[c]);
+         }
+         if (LPR > 1) {
+#pragma unroll
+            for (int c = 0; c < BT; c++)
+#pragma unroll
+               for (int o = LPR / 2; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o, LPR);
+         }
+         if (active && sub == 0) {
+            const int64_t row = row0 + rl;
+#pragma unroll
+            for (int c = 0; c < BT; c++)
+               if (c < b) Y[row + (size_t)c * ldy] = acc[c];
+         }
+      }
+      __syncwarp();
+      if (lane == 0) pbtma::mbar_arrive(&empty[s]);
+      if (++s == nstages) s = 0, ph ^= 1;
+   }
+}
+
+template <int BT, int LPR>
+int launch_spmm_win_l(pb200_ctx *ctx, const pb200_csr *A, const double *X, int64_t ldx, double *Y, int64_t ldy, int b) {
+   auto kern = spmm_win_kernel<BT, LPR>;
+   const int wlen = A->win_maxseg * SW_SEG;
+   const size_t stage = (SW_OFF_WIN + (size_t)wlen * b * 8 + 127) / 128 * 128;
+   int nstages = (int)((size_t)(227 * 1024 - 256) / stage);
+   if (nstages > 4) nstages = 4;
+   if (nstages < 2) return PB200_ERR_ARG;
+   const size_t shmem = nstages * stage;
+   static size_t attr_shmem = 0;
+   if (shmem > attr_shmem) {
+      PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+      attr_shmem = shmem;
+   }
+   int grid = ctx->num_sms;
+   if (grid > A->win_nblocks) grid = A->win_nblocks;
+   kern<<<grid, SPT_THREADS, shmem, ctx->stream>>>(A->d_rowptr, A->d_wcol, A->d_vals, A->d_w_row0, A->d_w_nrun,
+         (const int2 *)A->d_w_run, A->win_nblocks, A->ncols, X, ldx, Y, ldy, b, nstages, wlen, (uint32_t)stage);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   return 0;
+}
+
+template <int BT>
+int launch_spmm_win(pb200_ctx *ctx, const pb200_csr *A, const double *X, int64_t ldx, double *Y, int64_t ldy, int b) {
+   switch (A->lpr) {
+   case 1: return launch_spmm_win_l<BT, 1>(ctx, A, X, ldx, Y, ldy, b);
+   case 2: return launch_spmm_win_l<BT, 2>(ctx, A, X, ldx, Y, ldy, b);
+   case 4: return launch_spmm_win_l<BT, 4>(ctx, A, X, ldx, Y, ldy, b);
+   default: return launch_spmm_win_l<BT, 8>(ctx, A, X, ldx, Y, ldy, b);
+   }
+}
+
 // Device storage of one matrix: either one cudaMalloc per array (pb200_csr_create) or sub-allocations of
 // the context's matrix pool (pb200_csr_create_pooled: a caller that uploads a matrix per solve -- the
 // host-facing primme_b200_dprimme_csr -- then pays no cudaMalloc / cudaFree, which cost 0.01-1 s per call
@@ -754,6 +1007,7 @@ int csr_put(pb200_ctx *ctx, CsrAlloc &al, const T *h, size_t count, size_t slack
 struct Sched {
    std::vector<int64_t> row0, nz0, lr_row;
    std::vector<int32_t> bnnz, kind, slot, lr_slot0, lr_nslots;
+   std::vector<int64_t> w_row0;  // windowed kernel: blocks of <= SW_ROWS rows / SW_NNZ nonzeros (empty: not usable)
    int nslots, lpr;
 };
 void make_schedule(int64_t nrows, int64_t nnz, const int64_t *rp, Sched &S) {
@@ -787,6 +1041,15 @@ void make_schedule(int64_t nrows, int64_t nnz, const int64_t *rp, Sched &S) {
       r = r1;
    }
    S.row0.push_back(nrows);  // blk_row0[blk + 1] of the last group
+   if (S.lr_row.empty() && nnz > 0) {
+      for (int64_t r0 = 0; r0 < nrows;) {
+         int64_t r1 = r0 + SW_ROWS < nrows ? r0 + SW_ROWS : nrows;
+         while (rp[r1] - rp[r0] > SW_NNZ) r1--;  // no row is longer than SP_NNZ < SW_NNZ: r1 > r0
+         S.w_row0.push_back(r0);
+         r0 = r1;
+      }
+      S.w_row0.push_back(nrows);
+   }
    const double mean = nrows > 0 ? (double)nnz / (double)nrows : 1.0;
    S.lpr = 1;
    while (S.lpr < 32 && S.lpr * 4 <= mean) S.lpr *= 2;  // ~4+ nonzeros per lane
@@ -814,6 +1077,9 @@ int csr_from_host(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
       tot += 2 * rnd(8 * (S.row0.size() + 1)) + 3 * rnd(4 * (S.bnnz.size() + 1));
       tot += rnd(8 * (S.lr_row.size() + 1)) + 2 * rnd(4 * (S.lr_row.size() + 1));
       tot += rnd(8 * 16 * (size_t)(S.nslots ? S.nslots : 1)) + rnd(8 * gdoubles) + 4096;
+      if (!is_complex && !S.w_row0.empty())
+         tot += rnd(8 * S.w_row0.size()) + rnd(4 * S.w_row0.size()) + rnd(8 * SW_MAXRUN * S.w_row0.size()) +
+                rnd(2 * (size_t)nnz + 64) + rnd(64);
       void *base = NULL;
       PB_CHK(pb200_ctx_workspace(ctx, 3, tot, &base));
       al.base = (char *)base, al.cap = tot;
@@ -834,6 +1100,17 @@ int csr_from_host(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
    PB_CHK(csr_put(ctx, al, S.lr_nslots.data(), S.lr_nslots.size(), 0, &A->d_lr_nslots));
    A->d_long_part = csr_alloc<double>(al, 16 * (size_t)(S.nslots ? S.nslots : 1), 0);
    if (!A->d_long_part) return PB200_ERR_ALLOC;
+   A->win_state = -1;
+   if (!is_complex && !S.w_row0.empty()) {
+      A->win_nblocks = (int)S.w_row0.size() - 1;
+      PB_CHK(csr_put(ctx, al, S.w_row0.data(), S.w_row0.size(), 0, &A->d_w_row0));
+      A->d_w_nrun = csr_alloc<int32_t>(al, S.w_row0.size(), 0);
+      A->d_w_run = csr_alloc<int2>(al, (size_t)SW_MAXRUN * S.w_row0.size(), 0);
+      A->d_wcol = csr_alloc<uint16_t>(al, (size_t)nnz, 64);
+      A->d_w_state = csr_alloc<int>(al, 16, 0);
+      if (!A->d_w_nrun || !A->d_w_run || !A->d_wcol || !A->d_w_state) return PB200_ERR_ALLOC;
+      A->win_state = 0;  // analysed at the first product (win_prepare)
+   }
    if (pooled) {
       A->d_G = csr_alloc<double>(al, gdoubles, 0);
       if (!A->d_G) return PB200_ERR_ALLOC;
@@ -891,11 +1168,16 @@ extern "C" int pb200_csr_destroy(pb200_ctx *ctx, pb200_csr *A) {
    cudaFree(A->d_long_slot), cudaFree(A->d_long_part);
    cudaFree(A->d_lr_row), cudaFree(A->d_lr_slot0), cudaFree(A->d_lr_nslots);
    cudaFree(A->d_G);
+   cudaFree(A->d_w_row0), cudaFree(A->d_w_nrun), cudaFree(A->d_w_run), cudaFree(A->d_wcol), cudaFree(A->d_w_state);
    free(A);
    return 0;
 }
 
 extern "C" int64_t pb200_csr_nnz(const pb200_csr *A) { return A->nnz; }
+extern "C" int pb200_csr_layout(const pb200_csr *A, int ncols) {
+   const int bp = pb_spmm_bp(ncols < 8 ? ncols : 8);
+   return A->layout_choice[bp == 1 ? 0 : bp == 2 ? 1 : bp == 4 ? 2 : 3];
+}
 extern "C" int pb200_csr_is_complex(const pb200_csr *A) { return A->is_complex; }
 
 // Y = A * (rows of G): the v3 kernel on an already packed block (dist.cu calls this with the peer-
@@ -984,6 +1266,41 @@ static int run_v2(pb200_ctx *ctx, const pb200_csr *A, const double *Xd, int64_t 
    return 0;
 }
 
+// windowed layout: analyse the matrix once (device kernel), then the product is one launch
+static int win_prepare(pb200_ctx *ctx, pb200_csr *A) {
+   if (A->win_state != 0) return 0;
+   A->win_state = -1;
+   static const int use_win = getenv("PB200_SPMM_WIN") ? atoi(getenv("PB200_SPMM_WIN")) : 1;
+   if (!use_win || !ctx->use_tma_spmm) return 0;
+   PB_CUDA(cudaMemsetAsync(A->d_w_state, 0, 16 * sizeof(int), ctx->stream));
+   PB_CUDA(cudaMemsetAsync(A->d_wcol + A->nnz, 0, 64, ctx->stream));
+   int grid = ctx->num_sms * 8;
+   if (grid > A->win_nblocks) grid = A->win_nblocks;
+   spmm_win_analyze<<<grid, 256, 0, ctx->stream>>>(A->d_rowptr, A->d_colind, A->d_w_row0, A->win_nblocks, A->d_w_nrun,
+         (int2 *)A->d_w_run, A->d_wcol, A->d_w_state);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   int st[2] = {1, 0};
+   PB_CUDA(cudaMemcpyAsync(st, A->d_w_state, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+   PB_CUDA(cudaStreamSynchronize(ctx->stream));
+   if (st[0] == 0 && st[1] > 0) A->win_state = 1, A->win_maxseg = st[1];
+   if (getenv("PB200_DEBUG"))
+      fprintf(stderr, "primme_b200: SpMM window analysis: %s, %d blocks, max %d segments per block\n",
+            A->win_state == 1 ? "usable" : "not usable", A->win_nblocks, st[1]);
+   return 0;
+}
+static bool win_ok(const pb200_csr *A, const double *Xd, int64_t ldx, int b) {
+   if (A->win_state != 1 || (((uintptr_t)Xd) & 15) != 0 || ldx % 2 != 0 || ldx < A->ncols) return false;
+   const size_t stage = (SW_OFF_WIN + (size_t)A->win_maxseg * SW_SEG * b * 8 + 127) / 128 * 128;
+   return 2 * stage <= (size_t)(227 * 1024 - 256);
+}
+static int run_v4(pb200_ctx *ctx, const pb200_csr *A, const double *Xd, int64_t ldx, double *Yd, int64_t ldy, int b) {
+   if (b <= 1) return launch_spmm_win<1>(ctx, A, Xd, ldx, Yd, ldy, b);
+   if (b <= 2) return launch_spmm_win<2>(ctx, A, Xd, ldx, Yd, ldy, b);
+   if (b <= 4) return launch_spmm_win<4>(ctx, A, Xd, ldx, Yd, ldy, b);
+   return launch_spmm_win<8>(ctx, A, Xd, ldx, Yd, ldy, b);
+}
+
 // First block of a given width on this matrix: time both gather layouts once (after a warm-up pass
 // of each) and keep the faster -- banded matrices gather coalesced from the column-major block and do
 // not repay the packing pass, matrices without locality gain 3-4x from the 32-byte row gathers.
@@ -1000,14 +1317,23 @@ static int tune_layout(pb200_ctx *ctx, const pb200_csr *A, const void *Xc, int64
    if (!rc) rc = run_v2(ctx, A, (const double *)Xc, ldx, (double *)Yc, ldy, b);
    cudaEventRecord(ev[2], ctx->stream);
    PB_CUDA(cudaStreamSynchronize(ctx->stream));
-   float t3 = 0.f, t2 = 0.f;
+   float t3 = 0.f, t2 = 0.f, t4 = 1e30f;
    cudaEventElapsedTime(&t3, ev[0], ev[1]);
    cudaEventElapsedTime(&t2, ev[1], ev[2]);
+   if (!rc) rc = win_prepare(ctx, Am);
+   if (!rc && win_ok(A, (const double *)Xc, ldx, b)) {
+      rc = run_v4(ctx, A, (const double *)Xc, ldx, (double *)Yc, ldy, b);
+      cudaEventRecord(ev[0], ctx->stream);
+      if (!rc) rc = run_v4(ctx, A, (const double *)Xc, ldx, (double *)Yc, ldy, b);
+      cudaEventRecord(ev[1], ctx->stream);
+      PB_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaEventElapsedTime(&t4, ev[0], ev[1]);
+   }
    for (int i = 0; i < 3; i++) cudaEventDestroy(ev[i]);
-   Am->layout_choice[idx] = (t3 < t2) ? 2 : 1;
+   Am->layout_choice[idx] = (t4 < t3 && t4 < t2) ? 3 : (t3 < t2) ? 2 : 1;
    if (getenv("PB200_DEBUG"))
-      fprintf(stderr, "primme_b200: SpMM b=%d on %lld x %lld (nnz %lld): row-major gathers %.1f us, column-major %.1f us\n", b,
-            (long long)A->nrows, (long long)A->ncols, (long long)A->nnz, 1e3 * t3, 1e3 * t2);
+      fprintf(stderr, "primme_b200: SpMM b=%d on %lld x %lld (nnz %lld): row-major gathers %.1f us, column-major %.1f us, windowed %.1f us\n", b,
+            (long long)A->nrows, (long long)A->ncols, (long long)A->nnz, 1e3 * t3, 1e3 * t2, t4 < 1e29f ? 1e3 * t4 : -1.0);
    return rc;
 }
 
@@ -1024,17 +1350,24 @@ static int spmm_any(pb200_ctx *ctx, const pb200_csr *A, const void *X, int64_t l
       int v3;
       if (A->is_complex) v3 = 1;
       else if (!ctx->use_tma_spmm || b < 2) v3 = 0;
-      else if (ctx->spmm_v3 != 2) v3 = ctx->spmm_v3 ? 1 : 0;
+      else if (ctx->spmm_v3 == 3) {  // forced windowed layout (tests): column-major gathers when the matrix does not qualify
+         PB_CHK(win_prepare(ctx, const_cast<pb200_csr *>(A)));
+         v3 = win_ok(A, (const double *)Xc, ldx, b) ? 2 : 0;
+         const int bp = pb_spmm_bp(b);
+         const_cast<pb200_csr *>(A)->layout_choice[bp == 1 ? 0 : bp == 2 ? 1 : bp == 4 ? 2 : 3] = v3 ? 3 : 1;
+      } else if (ctx->spmm_v3 != 2) v3 = ctx->spmm_v3 ? 1 : 0;
       else {
          const int bp = pb_spmm_bp(b), idx = bp == 2 ? 1 : bp == 4 ? 2 : 3;
          if (!A->layout_choice[idx]) {
             PB_CHK(tune_layout(ctx, A, Xc, ldx, Yc, ldy, b, idx));
             continue;  // the last timed pass already left the product in Y
          }
-         v3 = A->layout_choice[idx] == 2;
+         v3 = A->layout_choice[idx] == 3 ? 2 : A->layout_choice[idx] == 2;
       }
       int ps = pb_prof_begin(ctx, PB_K_SPMM);
-      int rc = v3 ? run_v3(ctx, A, Xc, ldx, Yc, ldy, b) : run_v2(ctx, A, (const double *)Xc, ldx, (double *)Yc, ldy, b);
+      int rc;
+      if (v3 == 2 && win_ok(A, (const double *)Xc, ldx, b)) rc = run_v4(ctx, A, (const double *)Xc, ldx, (double *)Yc, ldy, b);
+      else rc = v3 == 1 ? run_v3(ctx, A, Xc, ldx, Yc, ldy, b) : run_v2(ctx, A, (const double *)Xc, ldx, (double *)Yc, ldy, b);
       pb_prof_end(ctx, ps, abytes);
       PB_CHK(rc);
    }

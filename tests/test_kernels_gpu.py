@@ -268,6 +268,58 @@ def test_spmm(libs, name, b, v3, monkeypatch):
         d.close()
 
 
+def _banded_random(n, offsets, seed):
+    rng = np.random.default_rng(seed)
+    rows, cols, vals = [], [], []
+    for o in offsets:
+        r = np.arange(max(0, -o), min(n, n - o))
+        keep = rng.random(len(r)) < 0.8
+        rows.append(r[keep]), cols.append(r[keep] + o), vals.append(rng.standard_normal(int(keep.sum())))
+    return M._assemble(n, np.concatenate(rows), np.concatenate(cols), np.concatenate(vals))
+
+
+@pytest.mark.parametrize("name,expect", [("lap3d_big", 3), ("lap1d", 3), ("banded", 3), ("emptyrows", 3),
+                                         ("banded_wide", 1), ("powerlaw", 1), ("longrow", 1)])
+@pytest.mark.parametrize("b", [2, 4, 5, 8])
+def test_spmm_windowed(libs, name, b, expect, monkeypatch):
+    """windowed layout (v4): the right-hand-side windows of a row block are staged in shared memory by bulk
+    copies; forced with PB200_SPMM_V3=3, matrices that do not qualify (no column locality, long rows) must fall
+    back to the column-major gathers -- same product either way, compared with the CPU restatement / numpy"""
+    monkeypatch.setenv("PB200_SPMM_V3", "3")
+    if name == "lap3d_big":
+        ip, ix, da = M.laplacian_nd((41, 30, 23))
+    elif name == "banded_wide":  # more distinct column segments per row block than a window holds
+        ip, ix, da = _banded_random(30011, [-7000, -3001, -130, -1, 0, 1, 2, 64, 2999, 7000, 11000], 17)
+    elif name == "banded":
+        ip, ix, da = _banded_random(30011, [-3001, -130, -1, 0, 1, 2, 64, 2999], 17)
+    else:
+        ip, ix, da = _csr_case(name)
+    nrows = len(ip) - 1
+    ncols = max(int(ix.max()) + 1, nrows) if len(ix) else nrows
+    ld = (ncols + 2) // 2 * 2 + 2
+    rng = np.random.default_rng(7)
+    X = rng.standard_normal((b, ld))
+    ref = M.csr_matvec(ip, ix, da, X[:, :ncols].T)
+    lib = libs[0]
+    d = Dev(lib)
+    A = C.c_void_p()
+    rp = np.ascontiguousarray(ip, dtype=np.int64)
+    ci = np.ascontiguousarray(ix, dtype=np.int32)
+    va = np.ascontiguousarray(da, dtype=np.float64)
+    assert lib.pb200_csr_create(d.ctx, nrows, ncols, len(ci), rp.ctypes.data, ci.ctypes.data, va.ctypes.data, 0, 0, C.byref(A)) == 0
+    dX = d.up(X)
+    dY = d.up(np.zeros((b, nrows + 1)))
+    for _ in range(2):
+        assert lib.pb200_dspmm(d.ctx, A, dX, ld, dY, nrows + 1, b) == 0
+    lib.pb200_csr_layout.restype = C.c_int
+    assert lib.pb200_csr_layout(A, b) == expect, (name, lib.pb200_csr_layout(A, b))
+    Y = d.down(dY, b, nrows + 1)[:, :nrows].T
+    scale = np.abs(ref).max() + 1
+    assert np.allclose(Y, ref, rtol=0, atol=1e-12 * scale * 50), (name, b)
+    lib.pb200_csr_destroy(d.ctx, A)
+    d.close()
+
+
 @pytest.mark.parametrize("name", ["lap3d", "powerlaw", "longrow", "emptyrows"])
 @pytest.mark.parametrize("b", [1, 2, 3, 8, 9])
 def test_zspmm(name, b):

@@ -409,17 +409,18 @@ template <bool CPLX> struct Sp3Stage {
          ((size_t)SPT_VALS * (CPLX ? 16 : 8) + (size_t)SPT_VALS * 4 + (size_t)SPT_RP * 8 + 64 + 127) / 128 * 128;
 };
 
-template <int BT, int NR, bool CPLX>
-__device__ __forceinline__ void sp_store_row(double *__restrict__ Y, int64_t ldy, int64_t row, int b, const double (&acc)[NR]) {
+// acc holds NR doubles of the row starting at column c0 (real) / complex column c0
+template <int NR, bool CPLX>
+__device__ __forceinline__ void sp_store_row(double *__restrict__ Y, int64_t ldy, int64_t row, int b, int c0, const double (&acc)[NR]) {
    if constexpr (CPLX) {
       double2 *Y2 = reinterpret_cast<double2 *>(Y);
 #pragma unroll
-      for (int c = 0; c < BT; c++)
-         if (c < b) Y2[row + (size_t)c * ldy] = make_double2(acc[2 * c], acc[2 * c + 1]);
+      for (int c = 0; c < NR / 2; c++)
+         if (c0 + c < b) Y2[row + (size_t)(c0 + c) * ldy] = make_double2(acc[2 * c], acc[2 * c + 1]);
    } else {
 #pragma unroll
-      for (int c = 0; c < BT; c++)
-         if (c < b) Y[row + (size_t)c * ldy] = acc[c];
+      for (int c = 0; c < NR; c++)
+         if (c0 + c < b) Y[row + (size_t)(c0 + c) * ldy] = acc[c];
    }
 }
 
@@ -432,7 +433,12 @@ __global__ void __launch_bounds__(SPT_THREADS, 2) spmm_rm_kernel(const int64_t *
       const double *G, double *__restrict__ Y, int64_t ldy, int b, int nstages, const PbSpSync sync, int evict_first) {
    typedef typename SpVal<CPLX>::type VT;
    constexpr int NR = CPLX ? 2 * BT : BT;       // doubles per row of G
-   constexpr int UN = NR >= 16 ? 1 : NR >= 8 ? 2 : 4;  // nonzeros in flight per lane (60 registers per thread)
+   // A row of G longer than 32 bytes is shared by LPN adjacent lanes (NRL doubles each): ONE warp-wide load then
+   // covers 32 / LPN whole rows, one L1 wavefront per gathered row instead of one per 32-byte piece issued by
+   // separate instructions (the L1 wavefront queue, ~2 cycles per distinct line, is what bounds random gathers)
+   constexpr int LPN = NR >= 16 ? 4 : NR >= 8 ? 2 : 1;
+   constexpr int NRL = NR / LPN;                // doubles per lane: 4 (one 32-byte load) or fewer
+   constexpr int UN = 4;                        // nonzeros in flight per lane
    constexpr size_t STAGE = Sp3Stage<CPLX>::BYTES;
    constexpr size_t OFF_COL = (size_t)SPT_VALS * sizeof(VT);
    constexpr size_t OFF_RP = OFF_COL + (size_t)SPT_VALS * 4;
@@ -441,6 +447,8 @@ __global__ void __launch_bounds__(SPT_THREADS, 2) spmm_rm_kernel(const int64_t *
    extern __shared__ __align__(128) unsigned char smraw[];
    __shared__ uint64_t full[8], empty[8];
    __shared__ double s_red[SPT_CONS / 32][NR];
+   const int part = (threadIdx.x % LPN);        // which NRL-double piece of a row this lane gathers
+   const int c0 = CPLX ? part * (NRL / 2) : part * NRL;  // first (complex) column of that piece
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    if (tid == 0) {
       for (int s = 0; s < nstages; s++) {
@@ -512,8 +520,10 @@ __global__ void __launch_bounds__(SPT_THREADS, 2) spmm_rm_kernel(const int64_t *
    }
    int s = 0;
    uint32_t ph = 0;
-   constexpr int RPP = SPT_CONS / LPR;  // rows per pass
-   const int sub = tid % LPR;
+   constexpr int LPRE = LPR * LPN > 32 ? 32 / LPN : LPR;  // nonzero slots per row group (a group stays inside a warp)
+   constexpr int GL = LPRE * LPN;       // lanes per row
+   constexpr int RPP = SPT_CONS / GL;   // rows per pass
+   const int sub = (tid % GL) / LPN;    // nonzero slot of this lane inside its row group
    for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
       pbtma::mbar_wait(&full[s], ph);
       const unsigned char *st = smraw + (size_t)s * STAGE;
@@ -524,43 +534,45 @@ __global__ void __launch_bounds__(SPT_THREADS, 2) spmm_rm_kernel(const int64_t *
       const int64_t row0 = hdr->row0, nzbase = hdr->nzbase;
       const int nrows = hdr->nrows, nnzb = hdr->nnzb, kind = hdr->kind, slot = hdr->slot;
       const int rpoff = (int)(row0 - hdr->rpbase);
+      const double *Gp = G + part * NRL;
       if (kind == 0) {
          // rows longer than LONGT nonzeros would serialise their LPR lanes while the rest of the warp
          // idles (power-law graphs): they are skipped here and taken by whole warps below
-         constexpr int LONGT = LPR >= 32 ? 0x7fffffff : 4 * UN * LPR;
+         constexpr int LONGT = GL >= 32 ? 0x7fffffff : 4 * UN * LPRE;
          for (int base = 0; base < nrows; base += RPP) {
-            const int rl = base + tid / LPR;
+            const int rl = base + tid / GL;
             bool active = rl < nrows;
             int sidx = 0, e = 0;
             if (active) sidx = (int)(s_rp[rpoff + rl] - nzbase), e = (int)(s_rp[rpoff + rl + 1] - nzbase);
             if (e - sidx > LONGT) active = false, e = sidx;
-            double acc[NR];
+            double acc[NRL];
 #pragma unroll
-            for (int c = 0; c < NR; c++) acc[c] = 0.0;
-            for (int i = sidx + sub; i < e; i += UN * LPR) {
+            for (int c = 0; c < NRL; c++) acc[c] = 0.0;
+            for (int i = sidx + sub; i < e; i += UN * LPRE) {
                VT v[UN];
-               double xv[UN][NR];
+               double xv[UN][NRL];
 #pragma unroll
                for (int u = 0; u < UN; u++) {
-                  const int iu = i + u * LPR;
+                  const int iu = i + u * LPRE;
                   const bool on = iu < e;
                   v[u] = on ? s_val[iu] : sp_zero<CPLX>();
-                  sp_ld_row<NR>(G + (size_t)(on ? s_col[iu] : s_col[i]) * NR, xv[u]);
+                  sp_ld_row<NRL>(Gp + (size_t)(on ? s_col[iu] : s_col[i]) * NR, xv[u]);
                }
 #pragma unroll
-               for (int u = 0; u < UN; u++) sp_fma<NR, CPLX>(acc, v[u], xv[u]);
+               for (int u = 0; u < UN; u++) sp_fma<NRL, CPLX>(acc, v[u], xv[u]);
             }
-            if (LPR > 1) {
+            if (LPRE > 1) {
 #pragma unroll
-               for (int c = 0; c < NR; c++)
+               for (int c = 0; c < NRL; c++)
 #pragma unroll
-                  for (int o = LPR / 2; o > 0; o >>= 1)
-                     acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o, LPR);
+                  for (int o = GL / 2; o >= LPN; o >>= 1)
+                     acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o, GL);
             }
-            if (active && sub == 0) sp_store_row<BT, NR, CPLX>(Y, ldy, row0 + rl, b, acc);
+            if (active && sub == 0) sp_store_row<NRL, CPLX>(Y, ldy, row0 + rl, b, c0, acc);
          }
-         if (LPR < 32) {
+         if (GL < 32) {
             // warp-wide pass over the long rows of the block, dealt round-robin to the warps
+            const int wsub = lane / LPN;
             int nlong = 0;
             for (int base = 0; base < nrows; base += 32) {
                const int rl = base + lane;
@@ -573,45 +585,54 @@ __global__ void __launch_bounds__(SPT_THREADS, 2) spmm_rm_kernel(const int64_t *
                   if ((nlong++ % (SPT_CONS / 32)) != warp) continue;
                   const int rr = base + j;
                   const int sidx = (int)(s_rp[rpoff + rr] - nzbase), e = (int)(s_rp[rpoff + rr + 1] - nzbase);
-                  double acc[NR];
+                  double acc[NRL];
 #pragma unroll
-                  for (int c = 0; c < NR; c++) acc[c] = 0.0;
-                  for (int i = sidx + lane; i < e; i += UN * 32) {
+                  for (int c = 0; c < NRL; c++) acc[c] = 0.0;
+                  for (int i = sidx + wsub; i < e; i += UN * (32 / LPN)) {
                      VT v[UN];
-                     double xv[UN][NR];
+                     double xv[UN][NRL];
 #pragma unroll
                      for (int u = 0; u < UN; u++) {
-                        const int iu = i + u * 32;
+                        const int iu = i + u * (32 / LPN);
                         const bool on = iu < e;
                         v[u] = on ? s_val[iu] : sp_zero<CPLX>();
-                        sp_ld_row<NR>(G + (size_t)(on ? s_col[iu] : s_col[i]) * NR, xv[u]);
+                        sp_ld_row<NRL>(Gp + (size_t)(on ? s_col[iu] : s_col[i]) * NR, xv[u]);
                      }
 #pragma unroll
-                     for (int u = 0; u < UN; u++) sp_fma<NR, CPLX>(acc, v[u], xv[u]);
+                     for (int u = 0; u < UN; u++) sp_fma<NRL, CPLX>(acc, v[u], xv[u]);
                   }
 #pragma unroll
-                  for (int c = 0; c < NR; c++)
+                  for (int c = 0; c < NRL; c++)
 #pragma unroll
-                     for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-                  if (lane == 0) sp_store_row<BT, NR, CPLX>(Y, ldy, row0 + rr, b, acc);
+                     for (int o = 16; o >= LPN; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+                  if (wsub == 0) sp_store_row<NRL, CPLX>(Y, ldy, row0 + rr, b, c0, acc);
                }
             }
          }
       } else {
          const int off = hdr->off;
-         double acc[NR];
+         const int tsub = tid / LPN;
+         double acc[NRL];
 #pragma unroll
-         for (int c = 0; c < NR; c++) acc[c] = 0.0;
-         for (int i = tid; i < nnzb; i += SPT_CONS) {
-            double xv[NR];
-            sp_ld_row<NR>(G + (size_t)s_col[off + i] * NR, xv);
-            sp_fma<NR, CPLX>(acc, s_val[off + i], xv);
+         for (int c = 0; c < NRL; c++) acc[c] = 0.0;
+         for (int i = tsub; i < nnzb; i += UN * (SPT_CONS / LPN)) {  // UN gathers in flight per thread
+            VT v[UN];
+            double xv[UN][NRL];
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+               const int iu = i + u * (SPT_CONS / LPN);
+               const bool on = iu < nnzb;
+               v[u] = on ? s_val[off + iu] : sp_zero<CPLX>();
+               sp_ld_row<NRL>(Gp + (size_t)s_col[off + (on ? iu : i)] * NR, xv[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < UN; u++) sp_fma<NRL, CPLX>(acc, v[u], xv[u]);
          }
 #pragma unroll
-         for (int c = 0; c < NR; c++) {
+         for (int c = 0; c < NRL; c++) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-            if (lane == 0) s_red[warp][c] = acc[c];
+            for (int o = 16; o >= LPN; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+            if (lane < LPN) s_red[warp][part * NRL + c] = acc[c];
          }
          pbtma::named_bar_sync(1, SPT_CONS);
          if (tid < NR) {
@@ -1010,12 +1031,20 @@ struct Sched {
    std::vector<int64_t> w_row0;  // windowed kernel: blocks of <= SW_ROWS rows / SW_NNZ nonzeros (empty: not usable)
    int nslots, lpr;
 };
+// rows longer than this get CTAs of their own (chunks of <= SP_NNZ nonzeros, all warps gather, fixed-order
+// fix-up): inside a group block a long row is walked by ONE warp, one gather latency per 64 nonzeros, while
+// the other warps run out of blocks to prefetch (power-law graphs: 1 % of the rows hold half of the nonzeros)
+static int long_row_threshold() {
+   static const int t = getenv("PB200_SPMM_LONGROW") ? atoi(getenv("PB200_SPMM_LONGROW")) : 1024;
+   return t < 64 ? 64 : t > SP_NNZ ? SP_NNZ : t;
+}
 void make_schedule(int64_t nrows, int64_t nnz, const int64_t *rp, Sched &S) {
    S.nslots = 0;
    int64_t r = 0;
+   const int64_t lrt = long_row_threshold();
    while (r < nrows) {
       int64_t len = rp[r + 1] - rp[r];
-      if (len > SP_NNZ) {
+      if (len > lrt) {
          S.lr_row.push_back(r);
          S.lr_slot0.push_back(S.nslots);
          int nch = 0;
@@ -1031,7 +1060,7 @@ void make_schedule(int64_t nrows, int64_t nnz, const int64_t *rp, Sched &S) {
       }
       int64_t r1 = r;
       int64_t cnt = 0;
-      while (r1 < nrows && r1 - r < SP_ROWS && (rp[r1 + 1] - rp[r1]) <= SP_NNZ &&
+      while (r1 < nrows && r1 - r < SP_ROWS && (rp[r1 + 1] - rp[r1]) <= lrt &&
              cnt + (rp[r1 + 1] - rp[r1]) <= SP_NNZ) {
          cnt += rp[r1 + 1] - rp[r1];
          r1++;
@@ -1050,9 +1079,30 @@ void make_schedule(int64_t nrows, int64_t nnz, const int64_t *rp, Sched &S) {
       }
       S.w_row0.push_back(nrows);
    }
-   const double mean = nrows > 0 ? (double)nnz / (double)nrows : 1.0;
+   // lanes per row from the MEDIAN row length (sampled): with rows of very different lengths (power-law graphs: the
+   // median is a third of the mean) lanes sharing a short row only waste gather slots, and the rows longer than
+   // 4 UN lanes-per-row nonzeros are taken by whole warps anyway (C5 shape: 545 us with 4 lanes, 493-500 with 1-2)
+   double typical = nrows > 0 ? (double)nnz / (double)nrows : 1.0;
+   if (nrows > 0) {
+      int64_t hist[66] = {0}, cnt = 0;
+      const int64_t stride = nrows / 65536 > 0 ? nrows / 65536 : 1;
+      for (int64_t i = 0; i < nrows; i += stride, cnt++) {
+         const int64_t len = rp[i + 1] - rp[i];
+         hist[len < 65 ? len : 65]++;
+      }
+      int64_t acc = 0;
+      for (int k = 0; k < 66; k++) {
+         acc += hist[k];
+         if (2 * acc >= cnt) {
+            if (k < 65 && (double)k < typical) typical = (double)k;
+            break;
+         }
+      }
+   }
    S.lpr = 1;
-   while (S.lpr < 32 && S.lpr * 4 <= mean) S.lpr *= 2;  // ~4+ nonzeros per lane
+   while (S.lpr < 32 && S.lpr * 4 <= typical) S.lpr *= 2;  // ~4+ nonzeros per lane
+   static const int force_lpr = getenv("PB200_SPMM_LPR") ? atoi(getenv("PB200_SPMM_LPR")) : 0;
+   if (force_lpr > 0) S.lpr = force_lpr;
 }
 
 int csr_from_host(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,

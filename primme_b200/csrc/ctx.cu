@@ -217,6 +217,27 @@ int pb_tensor_map_2d(CUtensorMap *tm, const double *base, int64_t rows, int cols
    }
    if (!encode || rows <= 0 || cols <= 0 || box_cols > 256 || box_rows > 256) return 1;
    if ((((uintptr_t)base) & 15) != 0 || (ld % 2) != 0 || rows > 0x7fffffffLL) return 1;
+   // A descriptor is a pure function of its six arguments, and a solve asks for the same few dozen over and over
+   // (the basis grows by a block per outer iteration and every restart starts the cycle again): a small
+   // direct-mapped cache takes the driver call out of the launch path of every sweep.
+   struct MapKey {
+      const double *base;
+      int64_t rows, ld;
+      int cols, box_rows, box_cols, valid;
+   };
+   static thread_local MapKey keys[64];
+   static thread_local CUtensorMap vals[64];
+   static const int use_cache = getenv("PB200_TMAP_CACHE") ? atoi(getenv("PB200_TMAP_CACHE")) : 1;
+   const unsigned h = (unsigned)((((uintptr_t)base >> 4) * 0x9E3779B97F4A7C15ull + (uint64_t)cols * 0x85EBCA6Bu + (uint64_t)box_rows * 31u +
+                                  (uint64_t)box_cols * 131u + (uint64_t)rows * 0xC2B2AE35u) >> 58) & 63;
+   if (use_cache) {
+      const MapKey &k = keys[h];
+      if (k.valid && k.base == base && k.rows == rows && k.ld == ld && k.cols == cols && k.box_rows == box_rows &&
+            k.box_cols == box_cols) {
+         *tm = vals[h];
+         return 0;
+      }
+   }
    const cuuint64_t gdim[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
    const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
    const cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
@@ -224,6 +245,10 @@ int pb_tensor_map_2d(CUtensorMap *tm, const double *base, int64_t rows, int cols
    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, gdim, gstride, box, estr,
          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+   if (r == CUDA_SUCCESS && use_cache) {
+      keys[h] = MapKey{base, rows, ld, cols, box_rows, box_cols, 1};
+      vals[h] = *tm;
+   }
    return r == CUDA_SUCCESS ? 0 : 1;
 }
 

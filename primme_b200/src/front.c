@@ -330,7 +330,13 @@ static int check_scope(primme_params *p) {
       why = "callback datatypes other than double";
    else if (p->correctionParams.maxInnerIterations != 0 && p->correctionParams.precondition > 0 &&
             p->correctionParams.projectors.RightQ && p->correctionParams.projectors.SkewQ)
-      why = "inner QMR iterations with the skew-Q projector and a preconditioner (K^{-1}Q and its factorised Gram matrix)";
+      /* The reference cannot run this configuration either: restart_projection applies the preconditioner to
+       * &Bevecs[...] with Bevecs == NULL when there is no mass matrix (restart.c:1511-1515; init.c:163 has the
+       * `Bevecs ? Bevecs : evecs` guard, this call does not) and factorises M with ldMfact == 0
+       * (main_iter.c:1089 -> factorize.c:218-222).  PRIMME 3.2 built unchanged segfaults inside the
+       * user's preconditioner at the first restart after a pair converged (tests/test_jdqmr_cpu.py runs it in a
+       * child process); refusing with -44 before any work is the defined behaviour here. */
+      why = "inner QMR iterations with the skew-Q projector and a preconditioner (the reference crashes in this configuration: restart.c:1511)";
    /* blocks wider than the kernels' 8-column panels are processed in chunks of 8 (dav_ortho.c, dav_project.c,
     * the launchers); the inner QMR solver keeps its 8 systems per block */
    else if (p->maxBlockSize > 8 && p->correctionParams.maxInnerIterations != 0)

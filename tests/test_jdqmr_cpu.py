@@ -73,3 +73,30 @@ def test_jdqmr_blocks_close_to_reference(name):
     ref, got = run_pair(CLOSE[name])
     for k in ("numOuterIterations", "numMatvecs"):
         assert abs(got["stats"][k] - ref["stats"][k]) <= max(2, 0.06 * ref["stats"][k]), (got["stats"], ref["stats"])
+
+
+def test_reference_crashes_with_skewQ_and_preconditioner():
+    """Why the skew-Q projector with a preconditioner (PRIMME_JDQR + applyPreconditioner) has no oracle and is
+    refused with PRIMME_FUNCTION_UNAVAILABLE: the unmodified reference dies in this configuration.  Its
+    restart_projection hands `&Bevecs[ldBevecs * (evecsSize + numOrthoConst)]` to the preconditioner with
+    Bevecs == NULL when there is no mass matrix (reference src/eigs/restart.c:1511-1515; src/eigs/init.c:163 has the
+    `Bevecs ? Bevecs : evecs` guard, this call does not), so the user's callback reads from address 0 at the first
+    restart after a pair converged; with that fixed it would still factorise M with ldMfact == 0
+    (main_iter.c:1089 -> factorize.c:218-222).  The child process below runs the reference as built by oracle/Makefile
+    and must end with a signal; the product returns -44 before any work (tests/test_host_logic.py)."""
+    import os
+    import subprocess
+    import sys
+    if not H.have_reference():
+        pytest.skip("reference library not built")
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = (
+        "import harness as H\n"
+        "from golden.cases import MATRICES\n"
+        "from primme_b200 import api\n"
+        "r = H.solve('reference', MATRICES['aniso3d'](), 5, method=api.PRIMME_JDQR, eps=1e-9, jacobi=True, locking=1)\n"
+        "print('returned', r['ret'])\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([here, os.path.dirname(here)]))
+    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=here, capture_output=True, text=True, timeout=600)
+    assert out.returncode < 0 or "returned 0" not in out.stdout, (out.returncode, out.stdout[-300:], out.stderr[-300:])
+    assert out.returncode == -11, f"expected SIGSEGV from the reference, got {out.returncode}: {out.stdout[-200:]}"

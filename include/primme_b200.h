@@ -237,6 +237,11 @@ int pb200_dqmr_update(pb200_ctx *ctx, int64_t n, const double *gamma_host, const
 int pb200_djacobi(pb200_ctx *ctx, int64_t n, const double *diag, const double *shifts_host,
       double minabs, const double *X, int64_t ldx, double *Y, int64_t ldy, int ncols);
 
+/* X(0:col_len, 0:ncols) = the next col_len * ncols values of LAPACK's dlarnv(idist = 2, iseed), bit for bit,
+ * generated on the device (reference Num_larnv, src/linalg/blaslapack.c:953-977, fills its random vectors on the
+ * host); iseed (entries 0..4095) is advanced as dlarnv would.  Complex blocks: col_len = 2 n, ld = 2 ldx. */
+int pb200_dlarnv(pb200_ctx *ctx, long long iseed[4], int64_t col_len, int ncols, double *X, int64_t ld);
+
 /* ------------------------------------------------ complex twins of K2-K6 (zprimme / C3) ----
  * Same operations and argument lists as the d functions above on interleaved (re,im) fp64 data:
  * device arrays column-major with leading dimensions in COMPLEX elements; host coefficient blocks

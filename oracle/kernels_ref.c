@@ -453,3 +453,22 @@ int pb200_dqmr_update(pb200_ctx *ctx, int64_t n, const double *gamma, const doub
    }
    return 0;
 }
+
+/* the device generator's reference: LAPACK's dlarnv itself, column after column */
+extern void dlarnv_(const int *idist, int *iseed, const int *n, double *x);
+int pb200_dlarnv(pb200_ctx *ctx, long long iseed[4], int64_t col_len, int ncols, double *X, int64_t ld) {
+   (void)ctx;
+   int idist = 2, seed[4];
+   for (int i = 0; i < 4; i++) seed[i] = (int)iseed[i];
+   for (int j = 0; j < ncols; j++) {
+      int64_t left = col_len;
+      double *x = X + (size_t)j * ld;
+      while (left > 0) {
+         int chunk = left > 0x7ffffff0LL ? 0x7ffffff0 : (int)left;
+         dlarnv_(&idist, seed, &chunk, x);
+         x += chunk, left -= chunk;
+      }
+   }
+   for (int i = 0; i < 4; i++) iseed[i] = seed[i];
+   return 0;
+}

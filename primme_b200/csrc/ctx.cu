@@ -338,7 +338,26 @@ __global__ void __launch_bounds__(256) pb_reduce_partials_kernel(
 }
 
 // wait until the (value, sequence number) pairs of panel `seq` have landed in mapped host memory
+// PB200_HOST_PROFILE: wall time the host spends waiting for panels (front.c prints it next to the solve time)
+static double g_wait_s = 0.0;
+static long g_wait_n = 0;
+extern "C" double pb200_debug_wait_seconds(long *calls) {
+   if (calls) *calls = g_wait_n;
+   return g_wait_s;
+}
+static int pb_poll_tagged_(pb200_ctx *ctx, int cnt, long long seq);
 static int pb_poll_tagged(pb200_ctx *ctx, int cnt, long long seq) {
+   static const int prof = getenv("PB200_HOST_PROFILE") != NULL;
+   if (!prof) return pb_poll_tagged_(ctx, cnt, seq);
+   struct timespec a, b;
+   clock_gettime(CLOCK_MONOTONIC, &a);
+   const int rc = pb_poll_tagged_(ctx, cnt, seq);
+   clock_gettime(CLOCK_MONOTONIC, &b);
+   g_wait_s += (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
+   g_wait_n++;
+   return rc;
+}
+static int pb_poll_tagged_(pb200_ctx *ctx, int cnt, long long seq) {
    volatile const long long *tg = (volatile const long long *)ctx->h_tagged;
    volatile const double *tv = (volatile const double *)ctx->h_tagged;
    unsigned long spins = 0;

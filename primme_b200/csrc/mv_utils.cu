@@ -366,3 +366,68 @@ extern "C" int pb200_dqmr_update(pb200_ctx *ctx, int64_t n, const double *gamma_
    }
    return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// LAPACK's dlarnv(idist = 2) on the device, bit for bit.  The reference fills its random vectors on the
+// host (Num_larnv, src/linalg/blaslapack.c:953-977 -> dlarnv -> dlaruv): at n = 10^6 and a block of 4 that
+// is 40 ms of a 0.6 s solve, and the vector still has to cross PCIe.  dlaruv is a 48-bit multiplicative
+// congruential generator, x_k = a^k x_0 mod 2^48 with a = 33952834046453 (its table MM holds a^1 .. a^128
+// in base 4096), value k = x_k / 2^48 assembled from the four 12-bit digits (exact in fp64), dlarnv maps
+// it to 2 u - 1.  A power of a is reached by square-and-multiply, so every thread starts its own run of
+// the SAME sequence; the seed returned is x_n in dlaruv's digit form, exactly what dlarnv leaves behind.
+namespace {
+constexpr unsigned long long LARNV_A = 33952834046453ull, LARNV_MASK = (1ull << 48) - 1;
+__host__ __device__ inline unsigned long long larnv_pow(unsigned long long k) {
+   unsigned long long r = 1, b = LARNV_A;
+   while (k) {
+      if (k & 1) r = (r * b) & LARNV_MASK;
+      b = (b * b) & LARNV_MASK;
+      k >>= 1;
+   }
+   return r;
+}
+constexpr int LARNV_RUN = 64;  // consecutive values per thread
+__global__ void __launch_bounds__(256) larnv_kernel(unsigned long long x0, int64_t count, int64_t col_len, int64_t ld,
+      double *__restrict__ X) {
+   // value k of the stream (k = 0 .. count-1) is element (k % col_len) of column k / col_len
+   const int64_t nruns = (count + LARNV_RUN - 1) / LARNV_RUN;
+   for (int64_t run = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; run < nruns; run += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t k0 = run * LARNV_RUN;
+      unsigned long long x = (x0 * larnv_pow((unsigned long long)k0 + 1)) & LARNV_MASK;
+      const int64_t k1 = k0 + LARNV_RUN < count ? k0 + LARNV_RUN : count;
+      int64_t col = k0 / col_len, row = k0 % col_len;
+      for (int64_t k = k0; k < k1; k++) {
+         const double r = 1.0 / 4096.0;
+         const double u = r * ((double)(x >> 36) + r * ((double)((x >> 24) & 4095) + r * ((double)((x >> 12) & 4095) + r * (double)(x & 4095))));
+         X[row + col * ld] = 2.0 * u - 1.0;
+         x = (x * LARNV_A) & LARNV_MASK;
+         if (++row == col_len) row = 0, col++;
+      }
+   }
+}
+}  // namespace
+
+// X(0:col_len, 0:ncols) (leading dimension ld, in doubles) = the next col_len * ncols values of dlarnv(2, iseed):
+// column after column, like ncols successive calls; iseed is advanced as dlarnv would.  For complex blocks pass
+// col_len = 2 n and ld = 2 ldx (interleaved parts, the reference draws 2 n values per column).
+extern "C" int pb200_dlarnv(pb200_ctx *ctx, long long iseed[4], int64_t col_len, int ncols, double *X, int64_t ld) {
+   if (col_len <= 0 || ncols <= 0) return 0;
+   for (int i = 0; i < 4; i++)
+      if (iseed[i] < 0 || iseed[i] > 4095) return PB200_ERR_ARG;
+   const unsigned long long x0 = ((unsigned long long)iseed[0] << 36) | ((unsigned long long)iseed[1] << 24) |
+                                 ((unsigned long long)iseed[2] << 12) | (unsigned long long)iseed[3];
+   const int64_t count = col_len * ncols;
+   const int64_t nruns = (count + LARNV_RUN - 1) / LARNV_RUN;
+   int64_t blocks = (nruns + 255) / 256;
+   const int64_t cap = (int64_t)ctx->num_sms * 8;
+   if (blocks > cap) blocks = cap;
+   int ps = pb_prof_begin(ctx, PB_K_UTIL);
+   larnv_kernel<<<(int)blocks, 256, 0, ctx->stream>>>(x0, count, col_len, ld, X);
+   pb_prof_end(ctx, ps, 8.0 * (double)count);
+   ctx->launches++;
+   PB_CUDA(cudaGetLastError());
+   const unsigned long long xn = (x0 * larnv_pow((unsigned long long)count)) & LARNV_MASK;
+   iseed[0] = (long long)(xn >> 36), iseed[1] = (long long)((xn >> 24) & 4095), iseed[2] = (long long)((xn >> 12) & 4095),
+   iseed[3] = (long long)(xn & 4095);
+   return 0;
+}

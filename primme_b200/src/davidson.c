@@ -26,6 +26,30 @@
 #define VtBV_BLK(S, off) ((S)->VtBV ? &(S)->VtBV[(size_t)(S)->maxRank * (off) + (off)] : NULL)
 
 /* solve_H (solve_projection.c:95-154): Rayleigh-Ritz pairs of (H, V'V) or the refined vectors from R */
+/* PB200_HOST_PROFILE: host-only time per section of the outer iteration (wall - panel waits - eigen-solves) */
+#ifndef PB_COMPLEX
+double pb_sect_host[8];
+int pb_sect_on = -1;
+#else
+extern double pb_sect_host[8];
+extern int pb_sect_on;
+#endif
+extern double pb200_debug_wait_seconds(long *calls) __attribute__((weak));
+extern double hl_prof_eig_s;
+static double sect_now(void) {
+   return hl_wtime() - (pb200_debug_wait_seconds ? pb200_debug_wait_seconds(NULL) : 0.0) - hl_prof_eig_s;
+}
+#define SECT(i, call)                                         \
+   do {                                                       \
+      if (pb_sect_on > 0) {                                   \
+         const double t_ = sect_now();                        \
+         call;                                                \
+         pb_sect_host[i] += sect_now() - t_;                  \
+      } else {                                                \
+         call;                                                \
+      }                                                       \
+   } while (0)
+
 static int solve_projected(pb_solver *S, int basisSize, int nLocked, int numConverged) {
    if (S->QtV) return pb_solve_H_harm(S, basisSize, VtBV_BLK(S, nLocked), S->maxRank, numConverged);
    if (S->refined) return pb_solve_H_ref(S, basisSize, VtBV_BLK(S, nLocked), S->maxRank, numConverged);
@@ -566,6 +590,8 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
 
    *ret = PRIMME_MAIN_ITER_FAILURE;
    *numRet = 0;
+   if (pb_sect_on < 0) pb_sect_on = getenv("PB200_HOST_PROFILE") != NULL;
+   if (pb_sect_on > 0) memset(pb_sect_host, 0, sizeof(pb_sect_host));
 
    /* counters (main_iter.c:371-396) */
    memset(&primme->stats, 0, sizeof(primme->stats));
@@ -583,7 +609,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
       goto clean;
    }
 
-   rc = init_basis(S, &basisSize, &nextGuess, &numGuesses);
+   SECT(7, rc = init_basis(S, &basisSize, &nextGuess, &numGuesses));
    if (rc) return rc;
    primme->initSize = 0;
 
@@ -666,11 +692,11 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
                                        primme->orth == primme_orth_implicit_I) &&
                                  primme->numOrthoConst + numLocked == 0;
                S->fuse_sweeps = 0, S->fusedP_nb = 0;
-               CHK(prepare_candidates(S, basisSize, S->V + (size_t)S->ld * basisSize,
+               SECT(0, CHK(prepare_candidates(S, basisSize, S->V + (size_t)S->ld * basisSize,
                      S->W + (size_t)S->ld * basisSize, 1, maxRecentlyConverged, blockSize,
                      availableBlockSize, numLocked, evals, resNorms, targetShiftIndex, &blockSize,
                      &recentlyConverged, &smallestResNorm, numConverged, &reset, nprevhVecs,
-                     practConvCheck));
+                     practConvCheck)));
                /* valid only if ONE sweep produced exactly the final block, in place and in order */
                if (!(S->fuse_sweeps == 1 && S->fusedP_nb == blockSize && S->fusedP_m == basisSize && blockSize > 0))
                   S->fusedP_nb = 0;
@@ -715,7 +741,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
 
             if (blockSize > 0) {
                S->tstart = hl_wtime(); /* the model accumulates the time spent in the correction */
-               CHK(solve_correction(S, evals, numLocked, basisSize, blockSize));
+               SECT(1, CHK(solve_correction(S, evals, numLocked, basisSize, blockSize)));
                if (primme->dynamicMethodSwitch > 0) S->cost.time_in_inner += hl_wtime() - S->tstart;
             }
 
@@ -730,9 +756,9 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
             for (i = 0; i < maxNumRandoms; i++) {
                int basisSizeOut;
                const int useP0 = i == 0 && S->fusedP_nb == blockSize && S->fusedP_nb > 0;
-               CHKX(pb_ortho_block_p0(S, S->V, S->ld, basisSize, basisSize + blockSize - 1, S->evecs,
+               SECT(2, CHKX(pb_ortho_block_p0(S, S->V, S->ld, basisSize, basisSize + blockSize - 1, S->evecs,
                      S->ldevecs, primme->numOrthoConst + numLocked, i == 0 ? Rlocked : NULL,
-                     ldRlocked, &basisSizeOut, useP0 ? S->fusedP : NULL, S->maxBasis + 8), free(Rlocked));
+                     ldRlocked, &basisSizeOut, useP0 ? S->fusedP : NULL, S->maxBasis + 8), free(Rlocked)));
                S->fusedP_nb = 0;
                blockSize = basisSizeOut - basisSize;
                if (blockSize > 0 || availableBlockSize <= 0) break;
@@ -788,8 +814,8 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
             }
 
             /* W(:,new) = A V(:,new);  H(:,new) = V' W(:,new) */
-            CHK(pb_apply_matvec(S, S->V + (size_t)S->ld * basisSize, S->ld,
-                  S->W + (size_t)S->ld * basisSize, S->ld, blockSize));
+            SECT(3, CHK(pb_apply_matvec(S, S->V + (size_t)S->ld * basisSize, S->ld,
+                  S->W + (size_t)S->ld * basisSize, S->ld, blockSize)));
             if (S->numQR) {
                int nQ = basisSize;
                CHK(pb_update_Q(S, primme->targetShifts[targetShiftIndex], basisSize, blockSize, &nQ));
@@ -799,7 +825,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
                   break;
                }
             }
-            CHK(pb_update_projection(S, basisSize, blockSize));
+            SECT(4, CHK(pb_update_projection(S, basisSize, blockSize)));
             CHK(pb_update_QtV(S, basisSize, blockSize));
 
             hl_copy(S->hVecs, basisSize, basisSize, ldh, S->prevhVecs, ldh);
@@ -809,7 +835,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
             basisSize += blockSize;
             blockSize = 0;
 
-            CHK(solve_projected(S, basisSize, primme->numOrthoConst + numLocked, numConverged));
+            SECT(5, CHK(solve_projected(S, basisSize, primme->numOrthoConst + numLocked, numConverged)));
             S->numArbitraryVecs = 0;
             candidates_prepared = 0;
 
@@ -909,8 +935,8 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
 
          {
             const double tr0 = hl_wtime();
-            CHK(pb_restart(S, basisSize, &blockSize, evals, resNorms, &numConverged, &numLocked,
-                  nprevhVecs, numGuesses, &basisSize, &targetShiftIndex, &restartsSinceReset));
+            SECT(6, CHK(pb_restart(S, basisSize, &blockSize, evals, resNorms, &numConverged, &numLocked,
+                  nprevhVecs, numGuesses, &basisSize, &targetShiftIndex, &restartsSinceReset)));
             S->tRestart += hl_wtime() - tr0;
          }
          restartsSinceReset++;
@@ -1001,6 +1027,11 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
    } /* verification loop */
 
 clean:
+   if (pb_sect_on > 0)
+      fprintf(stderr, "primme_b200 host profile, host-only ms per section: candidates %.1f, correction %.1f, ortho %.1f, "
+                      "matvec %.1f, projection %.1f, solve_H (without the eigen-solve) %.1f, restart %.1f, initial basis %.1f\n",
+            1e3 * pb_sect_host[0], 1e3 * pb_sect_host[1], 1e3 * pb_sect_host[2], 1e3 * pb_sect_host[3],
+            1e3 * pb_sect_host[4], 1e3 * pb_sect_host[5], 1e3 * pb_sect_host[6], 1e3 * pb_sect_host[7]);
    if (primme->aNorm <= 0.0)
       primme->aNorm = primme->stats.estimateLargestSVal / primme->stats.estimateInvBNorm;
    /* locked vectors are stored in order of convergence: sort them like evals (:1355-1357) */

@@ -188,9 +188,19 @@ int pb_monitor(pb_solver *S, double *basisEvals, int basisSize, int *basisFlags,
 int pb_fill_random(pb_solver *S, SCALAR *X, int64_t ldx, int ncols) {
    primme_params *primme = S->primme;
    if (ncols <= 0) return 0;
-   CHK(host_block(S, ncols));
+   /* the same numbers as the reference's Num_larnv (dlarnv, idist 2), drawn on the device */
    long long seed[4];
    for (int i = 0; i < 4; i++) seed[i] = primme->iseed[i];
+   const int w = (int)(sizeof(SCALAR) / sizeof(double));
+   int in_range = 1;
+   for (int i = 0; i < 4; i++) in_range = in_range && seed[i] >= 0 && seed[i] <= 4095;
+   if (in_range) {
+      CHK(pb200_dlarnv(S->dev, seed, (int64_t)w * S->n, ncols, (double *)X, (int64_t)w * ldx));
+      for (int i = 0; i < 4; i++) primme->iseed[i] = seed[i];
+      return 0;
+   }
+   /* seeds outside dlarnv's documented range: whatever LAPACK makes of them, on the host */
+   CHK(host_block(S, ncols));
    for (int j = 0; j < ncols; j++) hl_larnv2(seed, S->n, S->hstage + (size_t)S->n * j);
    for (int i = 0; i < 4; i++) primme->iseed[i] = seed[i];
    return pb200_copy_h2d(S->dev, S->hstage, S->n, X, ldx, S->n, ncols, PB_ES);
@@ -532,8 +542,26 @@ static int solve_typed(double *evals, SCALAR *evecs, double *resNorms, primme_pa
 
    int ret = 0, numRet = 0;
    const int blas_threads = hl_blas_threads(1);
+   const double tprof0 = hl_wtime();
    rc = pb_main_iter(S, evals, resNorms, &ret, &numRet);
    if (blas_threads > 0) hl_blas_threads(blas_threads);
+   if (getenv("PB200_HOST_PROFILE")) {
+      /* where the wall time of the solve went: waiting for panels (device + latency), the projected
+       * eigen-solves, everything else on the host (launch calls, small dense algebra, bookkeeping) */
+      extern double pb200_debug_wait_seconds(long *calls) __attribute__((weak));
+      extern double hl_prof_eig_s;
+      extern long hl_prof_eig_n;
+      static double wait_prev = 0.0, eig_prev = 0.0;
+      static long waitn_prev = 0, eign_prev = 0;
+      long wn = 0;
+      const double w = pb200_debug_wait_seconds ? pb200_debug_wait_seconds(&wn) : 0.0;
+      const double el = hl_wtime() - tprof0;
+      fprintf(stderr, "primme_b200 host profile: solve %.1f ms, %lld outer its; waiting for panels %.1f ms (%ld waits); "
+                      "projected eigen-solves %.1f ms (%ld calls); other host work %.1f ms\n",
+            1e3 * el, (long long)primme->stats.numOuterIterations, 1e3 * (w - wait_prev), wn - waitn_prev,
+            1e3 * (hl_prof_eig_s - eig_prev), hl_prof_eig_n - eign_prev, 1e3 * (el - (w - wait_prev) - (hl_prof_eig_s - eig_prev)));
+      wait_prev = w, waitn_prev = wn, eig_prev = hl_prof_eig_s, eign_prev = hl_prof_eig_n;
+   }
    if (rc == 0) {
       rc = ret;
       if (!device_mode && numRet > 0)

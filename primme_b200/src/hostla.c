@@ -138,7 +138,21 @@ int hl_potrf_upper(int n, SCALAR *A, int lda) {
    return info;
 }
 
+#ifndef PB_COMPLEX
+double hl_prof_eig_s = 0.0; /* PB200_HOST_PROFILE: time inside the projected eigen-solves */
+long hl_prof_eig_n = 0;
+#else
+extern double hl_prof_eig_s;
+extern long hl_prof_eig_n;
+#endif
+static int hl_sygv_upper_(int n, SCALAR *A, int lda, const SCALAR *B, int ldb, double *w);
 int hl_sygv_upper(int n, SCALAR *A, int lda, const SCALAR *B, int ldb, double *w) {
+   const double t0 = hl_wtime();
+   const int rc = hl_sygv_upper_(n, A, lda, B, ldb, w);
+   hl_prof_eig_s += hl_wtime() - t0, hl_prof_eig_n++;
+   return rc;
+}
+static int hl_sygv_upper_(int n, SCALAR *A, int lda, const SCALAR *B, int ldb, double *w) {
    if (n == 0) return 0;
    int info = 0, lwork = -1, nfound = 0, idum = 0, one = 1;
    double abstol = 0.0, rdum = 0.0;

@@ -416,3 +416,27 @@ def test_panel_reduction_is_reproducible(libs):
                                       P.ctypes.data, mv + b) == 0
     d.close()
     assert np.array_equal(P1, P2)
+
+
+@pytest.mark.parametrize("n,ncols,seed", [(1, 1, (0, 0, 0, 1)), (63, 1, (1, 2, 3, 5)), (64, 2, (4095, 4095, 4095, 4095)),
+                                          (65, 3, (7, 0, 11, 13)), (100003, 4, (0, 1, 2, 3)), (4097, 8, (1234, 567, 89, 1011)),
+                                          (300001, 1, (17, 4000, 2, 4093))])
+def test_dlarnv_on_device_is_lapack_dlarnv(libs, n, ncols, seed):
+    """pb200_dlarnv: the initial / replacement random vectors are drawn on the device; the values AND the seed
+    left behind must be LAPACK's dlarnv(idist=2) bit for bit (the oracle twin calls dlarnv_ itself), otherwise
+    every solve would start from a different vector than the reference's"""
+    out = []
+    ld = n + 3
+    for lib in libs:
+        d = Dev(lib)
+        dX = d.up(np.zeros((ncols, ld)))
+        iseed = (C.c_longlong * 4)(*seed)
+        lib.pb200_dlarnv.restype = C.c_int
+        lib.pb200_dlarnv.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.c_int64, C.c_int, C.c_void_p, C.c_int64]
+        assert lib.pb200_dlarnv(d.ctx, iseed, n, ncols, dX, ld) == 0
+        out.append((d.down(dX, ncols, ld)[:, :n].copy(), tuple(iseed)))
+        d.close()
+    (xg, sg), (xo, so) = out
+    assert sg == so
+    assert np.array_equal(xg, xo)
+    assert np.abs(xg).max() < 1.0 and xg.std() > 0.3 or n < 10

@@ -693,7 +693,7 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args.side), "n": n, "nnz": nnz,
                            "parallelism": (f"row-sharded x{world}, " + ("in-kernel panel all-reduce over NVLink peer memory" if peer_active
-                                                                         else "NCCL panel all-reduce") + " + NCCL halo all-gather" if sharded
+                                                                         else "NCCL panel all-reduce") + " + compacted SpMV halo pushed over NVLink peer memory" if sharded
                                            else "replicas only" if args.gpus > 1 else "single GPU"),
                            "l2": "working set per sweep (V,W 2x320 MB at n=1e6) exceeds the 126 MB L2; no flush",
                            "outer_iterations": stats["numOuterIterations"], "restarts": stats["numRestarts"],

@@ -446,7 +446,6 @@ __global__ void __launch_bounds__(SPT_THREADS, 2) spmm_rm_kernel(const int64_t *
    const VT *__restrict__ vals = reinterpret_cast<const VT *>(vals_);
    extern __shared__ __align__(128) unsigned char smraw[];
    __shared__ uint64_t full[8], empty[8];
-   __shared__ double s_red[SPT_CONS / 32][NR];
    const int part = (threadIdx.x % LPN);        // which NRL-double piece of a row this lane gathers
    const int c0 = CPLX ? part * (NRL / 2) : part * NRL;  // first (complex) column of that piece
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -628,19 +627,15 @@ __global__ void __launch_bounds__(SPT_THREADS, 2) spmm_rm_kernel(const int64_t *
 #pragma unroll
             for (int u = 0; u < UN; u++) sp_fma<NRL, CPLX>(acc, v[u], xv[u]);
          }
+         // one partial per WARP and chunk, summed in (chunk, warp) order by the fix-up kernel: no CTA-wide barrier
+         // here (ncu: 20 % of the stall samples of the power-law product sat behind the two barriers of a
+         // CTA-level reduction), the warps go on to the next block on their own
 #pragma unroll
          for (int c = 0; c < NRL; c++) {
 #pragma unroll
             for (int o = 16; o >= LPN; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-            if (lane < LPN) s_red[warp][part * NRL + c] = acc[c];
+            if (lane < LPN) long_part[((size_t)slot * (SPT_CONS / 32) + warp) * 16 + part * NRL + c] = acc[c];
          }
-         pbtma::named_bar_sync(1, SPT_CONS);
-         if (tid < NR) {
-            double sum = 0.0;
-            for (int w = 0; w < SPT_CONS / 32; w++) sum += s_red[w][tid];
-            long_part[(size_t)slot * 16 + tid] = sum;
-         }
-         pbtma::named_bar_sync(1, SPT_CONS);  // s_red is reused by the next long chunk
       }
       __syncwarp();
       if (lane == 0) pbtma::mbar_arrive(&empty[s]);
@@ -728,7 +723,8 @@ __global__ void spmm_long_fixup3(const int64_t *__restrict__ lr_row, const int32
    int lr = i / 16, c = i % 16;
    if (lr >= nlongrows || c >= (cplx ? 2 * b : b)) return;
    double s = 0.0;
-   for (int t = 0; t < lr_nslots[lr]; t++) s += long_part[(size_t)(lr_slot0[lr] + t) * 16 + c];
+   for (int t = 0; t < lr_nslots[lr]; t++)
+      for (int w = 0; w < SPT_CONS / 32; w++) s += long_part[((size_t)(lr_slot0[lr] + t) * (SPT_CONS / 32) + w) * 16 + c];
    if (cplx) Y[2 * (lr_row[lr] + (size_t)(c >> 1) * ldy) + (c & 1)] = s;
    else Y[lr_row[lr] + (size_t)c * ldy] = s;
 }
@@ -1126,7 +1122,7 @@ int csr_from_host(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
       size_t tot = rnd(8 * (size_t)(nrows + 1) + 64) + rnd(4 * (size_t)(nnz ? nnz : 1) + 64) + rnd(vs * (size_t)(nnz ? nnz : 1) + 64);
       tot += 2 * rnd(8 * (S.row0.size() + 1)) + 3 * rnd(4 * (S.bnnz.size() + 1));
       tot += rnd(8 * (S.lr_row.size() + 1)) + 2 * rnd(4 * (S.lr_row.size() + 1));
-      tot += rnd(8 * 16 * (size_t)(S.nslots ? S.nslots : 1)) + rnd(8 * gdoubles) + 4096;
+      tot += rnd(8 * 16 * (size_t)(SPT_CONS / 32) * (size_t)(S.nslots ? S.nslots : 1)) + rnd(8 * gdoubles) + 4096;
       if (!is_complex && !S.w_row0.empty())
          tot += rnd(8 * S.w_row0.size()) + rnd(4 * S.w_row0.size()) + rnd(8 * SW_MAXRUN * S.w_row0.size()) +
                 rnd(2 * (size_t)nnz + 64) + rnd(64);
@@ -1148,7 +1144,7 @@ int csr_from_host(pb200_ctx *ctx, int64_t nrows, int64_t ncols, int64_t nnz,
    PB_CHK(csr_put(ctx, al, S.lr_row.data(), S.lr_row.size(), 0, &A->d_lr_row));
    PB_CHK(csr_put(ctx, al, S.lr_slot0.data(), S.lr_slot0.size(), 0, &A->d_lr_slot0));
    PB_CHK(csr_put(ctx, al, S.lr_nslots.data(), S.lr_nslots.size(), 0, &A->d_lr_nslots));
-   A->d_long_part = csr_alloc<double>(al, 16 * (size_t)(S.nslots ? S.nslots : 1), 0);
+   A->d_long_part = csr_alloc<double>(al, 16 * (size_t)(SPT_CONS / 32) * (size_t)(S.nslots ? S.nslots : 1), 0);
    if (!A->d_long_part) return PB200_ERR_ALLOC;
    A->win_state = -1;
    if (!is_complex && !S.w_row0.empty()) {

@@ -46,6 +46,7 @@ struct pb200_dist_csr {
    unsigned int *d_counters;                                // [0] push kernel, [1] SpMM kernel
    double *d_stage;                                         // send staging of the NCCL fallback
    int64_t stat_blocks, stat_rows_sent;
+   double dbg_push_ms, dbg_spmm_ms;                         // PB200_DIST_TIMING: event times of the two kernels
 };
 
 namespace {
@@ -279,6 +280,10 @@ extern "C" int pb200_dist_csr_create(pb200_ctx *ctx, pb200_csr *A_local, const i
 extern "C" int pb200_dist_csr_destroy(pb200_ctx *ctx, pb200_dist_csr *D) {
    if (!D) return 0;
    if (ctx) cudaStreamSynchronize(ctx->stream);
+   if (D->stat_blocks > 0 && getenv("PB200_DIST_TIMING"))
+      fprintf(stderr, "primme_b200 dist timing, rank %d: %lld blocks, push kernel %.3f ms per block, gather kernel (incl. waiting for the peers' rows) %.3f ms per block, %lld rows pushed per block\n",
+            D->rank, (long long)D->stat_blocks, D->dbg_push_ms / (double)D->stat_blocks, D->dbg_spmm_ms / (double)D->stat_blocks,
+            (long long)(D->stat_rows_sent / D->stat_blocks));
    if (D->nranks > 1 && D->peer_on && ctx) {
       // nobody unmaps a region a peer may still be writing to
       double z = 0.0;
@@ -355,10 +360,17 @@ static int dist_spmm_any(pb200_ctx *ctx, pb200_dist_csr *D, const void *X, int64
       const int64_t cap = (int64_t)ctx->num_sms * 8;
       if (blocks > cap) blocks = cap;
       if (blocks < 1) blocks = 1;
+      static const int dbg_timing = getenv("PB200_DIST_TIMING") != NULL;
+      cudaEvent_t dbg_ev[3] = {NULL, NULL, NULL};
+      if (dbg_timing) {
+         for (int i = 0; i < 3; i++) cudaEventCreate(&dbg_ev[i]);
+         cudaEventRecord(dbg_ev[0], ctx->stream);
+      }
       if (cplx) dist_push_kernel<double2><<<(int)blocks, 256, 0, ctx->stream>>>(a);
       else dist_push_kernel<double><<<(int)blocks, 256, 0, ctx->stream>>>(a);
       ctx->launches++;
       PB_CUDA(cudaGetLastError());
+      if (dbg_timing) cudaEventRecord(dbg_ev[1], ctx->stream);
       D->stat_blocks++, D->stat_rows_sent += tot;
 
       PbSpSync sy;
@@ -389,6 +401,14 @@ static int dist_spmm_any(pb200_ctx *ctx, pb200_dist_csr *D, const void *X, int64
       }
       int rc = pb_spmm_gathered(ctx, D->A, (const double *)G, bp, Yc, ldy, b, D->peer_on ? &sy : NULL);
       pb_prof_end(ctx, ps, abytes);
+      if (dbg_timing) {
+         cudaEventRecord(dbg_ev[2], ctx->stream);
+         cudaEventSynchronize(dbg_ev[2]);
+         float t01 = 0.f, t12 = 0.f;
+         cudaEventElapsedTime(&t01, dbg_ev[0], dbg_ev[1]), cudaEventElapsedTime(&t12, dbg_ev[1], dbg_ev[2]);
+         D->dbg_push_ms += t01, D->dbg_spmm_ms += t12;
+         for (int i = 0; i < 3; i++) cudaEventDestroy(dbg_ev[i]);
+      }
       PB_CHK(rc);
    }
    return 0;

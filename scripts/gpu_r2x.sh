@@ -6,6 +6,12 @@ mkdir -p gpurun_out
 if [ "$N" = "2" ]; then
   timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -q --timeout 600 2>&1 | tail -4
 fi
+if [ -n "$DT" ]; then
+  # push / gather kernel times of the row-sharded SpMM (debug events, one synchronisation per block: not a bench number)
+  PB200_DIST_TIMING=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29543 \
+     bench.py --gpus $N --steps 1 --warmup 1 --c5-steps 1 --c4-m 0 > gpurun_out/bench_dt_n$N.json 2> gpurun_out/bench_dt_n$N.err
+  grep "dist timing" gpurun_out/bench_dt_n$N.err | sort | uniq | head -20
+fi
 PB200_HOST_PROFILE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 \
    bench.py --gpus $N --steps 2 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
 echo "bench N=$N exit $?"; grep "host profile: solve" gpurun_out/bench_n$N.err | tail -3

@@ -8,7 +8,8 @@ import subprocess
 import sys
 
 LIB = "primme_b200/libprimme_b200.so"
-HOT = ["ortho_sweep_mma_exact_kernel", "ortho_sweep_mma_kernel", "vwxr_mma_kernel", "spmm_rm_kernel", "spmm_tma_kernel",
+HOT = ["ortho_sweep_mma_exact_kernel", "ortho_sweep_mma_kernel", "vwxr_mma_kernel", "vwxr_cg_kernel", "spmm_rm_kernel", "spmm_tma_kernel",
+       "spmm_win_kernel", "spmm_win_analyze", "larnv_kernel",
        "dist_push_kernel", "zsweep_kernel", "ztall_kernel", "zdots_kernel", "spmm_pack_kernel"]
 KEYS = ["UTMALDG", "UBLKCP", "SYNCS", "DMMA", "DFMA", "LDG.E.ENL2.256", "LDG.E.128", "LDG.E.64", "STG.E.128", "STG.E.64",
         "LDS", "STS", "SHFL", "BAR", "ATOM", "RED", "STG.E.64.STRONG.SYS", "LDG.E.64.STRONG.SYS", "MEMBAR", "HMMA", "UTCMMA"]
@@ -24,7 +25,7 @@ def main():
         base = next((h for h in HOT if h in dem), None)
         if not base:
             continue
-        ins = re.findall(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", f)
+        ins = re.findall(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", f)
         c = collections.Counter()
         for i in ins:
             # longest key first so that the system-scope accesses are not counted as plain LDG/STG

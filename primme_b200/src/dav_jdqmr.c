@@ -5,8 +5,8 @@
  * apply_projected_preconditioner :714-744, apply_skew_projector :769-812, apply_projected_matrix
  * :838-890: the operator is (I - QQ')(I - xx')(A - shift I) with the left projectors the method selects,
  * the preconditioner is followed by the right projectors (I - RX x'/x'RX)(I - QQ') when the method asks for
- * them (PRIMME_JDQR, user settings); the skew-Q projector with a preconditioner (evecsHat, M = Q'K^{-1}Q
- * and its factorisation) is the one configuration left out; B = I.
+ * them (PRIMME_JDQR, user settings), orthogonal or skew (the skew-Q projector with a preconditioner applies
+ * evecsHat = K^{-1}Q and the factors of M = Q'K^{-1}Q maintained by pb_update_XKinvBX); B = I.
  *
  * Every n-long operation is a kernel of the C-ABI (column dots, column axpy / scale, permutes, the
  * fused ortho sweep for Q'v and v - Q(Q'v)); the scalar recurrences stay on the host exactly as in
@@ -74,14 +74,47 @@ typedef struct right_projectors {
    int64_t ldRX;
    int nRX;          /* 0 or the current block size */
    SCALAR *xKinvBx;  /* x_i' K^{-1} x_i, or ones; indexed by POSITION (permuted with the systems) */
+   /* skew-Q projector (I - RQ (Q'RQ)^{-1} Q') with RQ = K^{-1} Q: Q, and the Bunch-Kaufman factors of Q'RQ packed
+    * with leading dimension nRQ (pb_update_XKinvBX); skewQ == NULL: orthogonal projector (I - RQ RQ') */
+   const SCALAR *skewQ;
+   int64_t ldskewQ;
+   const SCALAR *Mfact;
+   const int *ipivot;
 } right_projectors;
+
+/* v <- (I - Qhat (Q'Qhat)^{-1} Q') v  (apply_skew_projector with Mfact, inner_solve.c:769-812; MSolve,
+ * factorize.c:268-297) */
+static int skew_project_out(pb_solver *S, const right_projectors *rp, SCALAR *v, int64_t ldv, int bs) {
+   primme_params *primme = S->primme;
+   const int nQ = rp->nRQ;
+   if (nQ <= 0 || bs <= 0) return 0;
+   const double t0 = hl_wtime();
+   SCALAR *ov = (SCALAR *)malloc(sizeof(SCALAR) * (size_t)nQ * bs);
+   if (!ov) return PRIMME_MALLOC_FAILURE;
+   int rc = pb200_dortho_sweep(S->dev, S->n, rp->skewQ, nQ, rp->ldskewQ, NULL, 0, 0, v, bs, ldv, NULL, 0, NULL, 0, 0, ov, nQ);
+   primme->stats.numOrthoInnerProds += (double)nQ * bs;
+   if (!rc) rc = pb_reduce_panel(S, ov, nQ, bs, nQ);
+   if (!rc) {
+      if (nQ == 1)
+         for (int i = 0; i < bs; i++) ov[i] = ov[i] / rp->Mfact[0];
+      else if (hl_hetrs_upper(nQ, bs, rp->Mfact, nQ, rp->ipivot, ov, nQ))
+         rc = PRIMME_LAPACK_FAILURE;
+   }
+   if (!rc) rc = pb200_dortho_sweep(S->dev, S->n, rp->RQ, nQ, rp->ldRQ, NULL, 0, 0, v, bs, ldv, ov, nQ, NULL, 0, 0, NULL, 0);
+   free(ov);
+   primme->stats.timeOrtho += hl_wtime() - t0;
+   return rc;
+}
 
 static int apply_projected_preconditioner(pb_solver *S, right_projectors *rp, SCALAR *v, int64_t ldv, const SCALAR *x,
       int64_t ldx, SCALAR *result, int64_t ldr, int bs) {
    primme_params *primme = S->primme;
    CHK(pb_apply_precond(S, v, ldv, result, ldr, bs));
    if (!rp) return 0;
-   CHK(project_out(S, rp->RQ, rp->ldRQ, rp->nRQ, result, ldr, bs));
+   if (rp->skewQ)
+      CHK(skew_project_out(S, rp, result, ldr, bs));
+   else
+      CHK(project_out(S, rp->RQ, rp->ldRQ, rp->nRQ, result, ldr, bs));
    if (rp->nRX <= 0) return 0;
    const double t0 = hl_wtime();
    SCALAR ov[8];
@@ -132,8 +165,9 @@ static int scale_real(pb_solver *S, int64_t n, const double *alpha, SCALAR *X, i
  * rnorm / eval are indexed by original position, shift travels with the permutation. */
 int pb_inner_solve(pb_solver *S, int blockSize, SCALAR *x, int64_t ldx, SCALAR *r, int64_t ldr, const double *rnorm,
       const SCALAR *Q, int64_t ldQ, int nQ, int useX, SCALAR *sol, int64_t ldsol, const double *eval, double *shift,
-      int *touch, SCALAR *work, const SCALAR *RQ, int64_t ldRQ, int nRQ, SCALAR *RX, int64_t ldRX, SCALAR *xKinvBx) {
-   right_projectors rpv = {RQ, ldRQ, nRQ, RX, ldRX, RX ? blockSize : 0, xKinvBx};
+      int *touch, SCALAR *work, const SCALAR *RQ, int64_t ldRQ, int nRQ, SCALAR *RX, int64_t ldRX, SCALAR *xKinvBx,
+      const SCALAR *skewQ, int64_t ldskewQ, const SCALAR *Mfact, const int *ipivot) {
+   right_projectors rpv = {RQ, ldRQ, nRQ, RX, ldRX, RX ? blockSize : 0, xKinvBx, nRQ > 0 ? skewQ : NULL, ldskewQ, Mfact, ipivot};
    right_projectors *rp = (nRQ > 0 || RX) ? &rpv : NULL;
    primme_params *primme = S->primme;
    const correction_params *cp = &primme->correctionParams;

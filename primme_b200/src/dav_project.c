@@ -161,3 +161,65 @@ int pb_solve_H(pb_solver *S, const SCALAR *H, int ldH, int n, const SCALAR *VtBV
    S->tSolveH += hl_wtime() - t0;
    return rc;
 }
+
+
+/* ------------------------------------------------------------------------------------------
+ * Skew-Q projector with a preconditioner (PRIMME_JDQR + applyPreconditioner).
+ * update_XKinvBX (factorize.c:183-235 with B = I): grow M = evecs' evecsHat by blockSize columns
+ * (update_projection.c:61-102: the new columns, rows 0 .. numCols + blockSize) and refactorise it
+ * (Bunch-Kaufman on the upper triangle, packed with leading dimension nM the way MSolve reads it,
+ * factorize.c:268-297).  numCols counts the orthogonality constraints too.
+ * NOTE (parity): the reference reaches this code with ldMfact == 0 (main_iter.c:1089) and crashes before it
+ * (restart.c:1511); the oracle of tests/test_jdqmr_cpu.py is the reference with those two lines fixed
+ * (oracle/Makefile: refskewq).
+ * ---------------------------------------------------------------------------------------- */
+int pb_update_XKinvBX(pb_solver *S, int numCols, int blockSize) {
+   const int ldM = S->maxEvecsSize, nM = numCols + blockSize;
+   for (int c0 = 0; c0 < blockSize; c0 += 8) {
+      const int nc = PB_MIN(8, blockSize - c0);
+      SCALAR *P = &S->Mskew[(size_t)ldM * (numCols + c0)];
+      for (int j = 0; j < nc; j++)
+         for (int i = 0; i < nM; i++) P[i + (size_t)ldM * j] = 0.0;
+      CHK(pb200_dortho_sweep(S->dev, S->n, S->evecs, nM, S->ldevecs, NULL, 0, 0,
+            S->evecsHat + (size_t)S->ld * (numCols + c0), nc, S->ld, NULL, 0, NULL, 0, 0, P, ldM));
+      CHK(pb_reduce_panel(S, P, nM, nc, ldM));
+   }
+   if (nM == 0) return 0;
+   if (nM == 1) {
+      S->Mfact[0] = S->Mskew[0];
+      return 0;
+   }
+   for (int j = 0; j < nM; j++)
+      for (int i = 0; i <= j; i++) S->Mfact[i + (size_t)nM * j] = S->Mskew[i + (size_t)ldM * j];
+   return hl_hetrf_upper(nM, S->Mfact, nM, S->ipivot) ? PRIMME_LAPACK_FAILURE : 0;
+}
+
+/* end of restart_projection (restart.c:1471-1531): K^{-1} of the vectors that joined evecs at this restart
+ * (all converged Ritz vectors when there is no locking: they change from one restart to the next), then M */
+int pb_skew_evecs_after_restart(pb_solver *S, int numConverged) {
+   primme_params *primme = S->primme;
+   if (!S->evecsHat) return 0;
+   if (!primme->locking) S->numConvergedStored = 0;
+   const int evecsSize = S->numConvergedStored, nOC = primme->numOrthoConst;
+   const int numRecentlyConverged = numConverged - evecsSize;
+   double *shifts = NULL;
+   int owned = 0;
+   if (numConverged <= primme->numTargetShifts)
+      shifts = &primme->targetShifts[evecsSize];
+   else if (primme->numTargetShifts > 0) {
+      shifts = (double *)malloc(sizeof(double) * PB_MAX(numConverged, 1));
+      for (int i = 0; i < numRecentlyConverged; i++)
+         shifts[i] = primme->targetShifts[PB_MIN(i + evecsSize, primme->numTargetShifts - 1)];
+      owned = 1;
+   }
+   primme->ShiftsForPreconditioner = shifts;
+   int rc = 0;
+   if (numRecentlyConverged > 0)
+      rc = pb_apply_precond(S, S->evecs + (size_t)S->ldevecs * (evecsSize + nOC), S->ldevecs,
+            S->evecsHat + (size_t)S->ld * (evecsSize + nOC), S->ld, numRecentlyConverged);
+   primme->ShiftsForPreconditioner = NULL;
+   if (owned) free(shifts);
+   if (!rc) rc = pb_update_XKinvBX(S, nOC + evecsSize, numRecentlyConverged);
+   S->numConvergedStored = numConverged;
+   return rc;
+}

@@ -285,13 +285,14 @@ static int restart_soft_locking(pb_solver *S, int *restartSize, int basisSize, i
    SCALAR *X = S->V + (size_t)S->ld * *restartSize;
    SCALAR *R = S->W + (size_t)S->ld * *restartSize;
    int rc = aux_update_VWXR(S, basisSize, *restartSize, *restartSize, X, *numConverged,
-         *numConverged + *ievSize, primme->numOrthoConst, 0, 0 /* evecs untouched: see below */,
+         *numConverged + *ievSize, primme->numOrthoConst, 0, S->evecsHat ? *numConverged : 0 /* see below */,
          R, S->blockNorms, NULL, 0, 0, primme->orth == primme_orth_explicit_I);
    if (rc) return rc;
    /* NOTE: the reference also copies the converged Ritz vectors into evecs here
     * (restart.c:694: X2 = columns [0,numConverged)); without locking evecs is overwritten by
     * V(:,0:numEvals) before returning (main_iter.c:1285), and nothing reads it in between for
-    * B = I and no skew projectors, so the copy is skipped. */
+    * B = I unless the skew-Q projector is on (evecsHat: the copy feeds K^{-1}Q and M at the end of the
+    * restart, pb_skew_evecs_after_restart), so the copy is made only then. */
 
    for (i = 0; i < basisSize; i++) hVecsPerm[restartPerm[i]] = i;
    for (i = 0; i < *ievSize; i++)
@@ -691,6 +692,7 @@ int pb_restart(pb_solver *S, int basisSize, int *ievSize, double *evals, double 
       rc = restart_RR(S, restartSize, basisSize, *numConverged, numPrevRetained,
             indexOfPreviousVecs, hVecsPerm, targetShiftIndex);
    free(restartPerm);
+   if (!rc) rc = pb_skew_evecs_after_restart(S, *numConverged);
 
    /* all wanted pairs converged: bring them to the front of V (:384-392) */
    if (!rc && *numConverged >= primme->numEvals && !primme->locking) {

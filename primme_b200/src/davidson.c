@@ -99,6 +99,12 @@ static int init_basis(pb_solver *S, int *basisSize, int *nextGuess, int *numGues
       int nV = 0;
       CHK(pb_ortho_block(S, S->evecs, S->ldevecs, 0, primme->numOrthoConst - 1, NULL, 0, 0, NULL, 0, &nV));
       if (nV != primme->numOrthoConst) return PRIMME_ORTHO_CONST_FAILURE;
+      /* the constraints join the skew projector (I - K^{-1}Q (Q'K^{-1}Q)^{-1} Q') (init.c:150-169) */
+      if (S->evecsHat) {
+         primme->ShiftsForPreconditioner = NULL;
+         CHK(pb_apply_precond(S, S->evecs, S->ldevecs, S->evecsHat, S->ld, primme->numOrthoConst));
+         CHK(pb_update_XKinvBX(S, 0, primme->numOrthoConst));
+      }
    }
    initSize = PB_MIN(primme->locking ? primme->minRestartSize : primme->maxBasisSize, primme->initSize);
    {
@@ -423,7 +429,7 @@ static int solve_correction(pb_solver *S, double *evals, int numLocked, int basi
       /* inner-outer JDQMR (correction.c:385-447, setup_JD_projectors :862-999 for the presets
        * without right projectors): Q = [constraints locked] when LeftQ; the Ritz vector joins Q
        * when the block is a single vector, else every system is projected against its own x_i */
-      const int sizeEvecs = primme->numOrthoConst + (primme->locking ? numLocked : 0);
+      const int sizeEvecs = primme->numOrthoConst + (primme->locking ? numLocked : S->numConvergedStored);
       const SCALAR *Q = NULL;
       int nQ = 0, useX = 0;
       if (cp->projectors.LeftQ) {
@@ -445,7 +451,14 @@ static int solve_correction(pb_solver *S, double *evals, int numLocked, int basi
       const SCALAR *RQ = NULL;
       SCALAR *RX = NULL, *KinvX = NULL, xKinvBx[8];
       int nRQ = 0;
-      if (cp->projectors.RightQ) RQ = S->evecs, nRQ = sizeEvecs;
+      /* right projector on Q: orthogonal (RQ = evecs) or, with a preconditioner and SkewQ, the skew one
+       * (RQ = evecsHat = K^{-1} evecs, overlaps with evecs solved through the factors of M; :948-954) */
+      int64_t ldRQ = S->ldevecs;
+      const SCALAR *skewQ = NULL;
+      if (cp->projectors.RightQ) {
+         RQ = S->evecs, nRQ = sizeEvecs;
+         if (cp->precondition && cp->projectors.SkewQ && S->evecsHat) RQ = S->evecsHat, ldRQ = S->ld, skewQ = S->evecs;
+      }
       if (!rc && cp->projectors.RightX) {
          if (cp->precondition && cp->projectors.SkewX) {
             rc = pb200_malloc(S->dev, sizeof(SCALAR) * (size_t)S->ld * blockSize, (void **)&KinvX);
@@ -464,7 +477,8 @@ static int solve_correction(pb_solver *S, double *evals, int numLocked, int basi
          SCALAR *sol = S->jd_work + (size_t)S->ld * 4 * PB_MAX(primme->maxBlockSize, 1);
          int touch1 = S->touch;
          rc = pb_inner_solve(S, blockSize, x, S->ld, r, S->ld, blockNorms, Q, S->ldevecs, nQ, useX, sol, S->ld,
-               blockRitzVals, shifts, &touch1, S->jd_work, RQ, S->ldevecs, nRQ, RX, S->ld, xKinvBx);
+               blockRitzVals, shifts, &touch1, S->jd_work, RQ, ldRQ, nRQ, RX, S->ld, xKinvBx, skewQ, S->ldevecs,
+               S->Mfact, S->ipivot);
          S->touch = PB_MAX(S->touch, touch1);
          if (!rc) rc = pb200_copy_d2d(S->dev, sol, S->ld, x, S->ld, S->n, blockSize, PB_ES);
       }
@@ -629,7 +643,7 @@ int pb_main_iter(pb_solver *S, double *evals, double *resNorms, int *ret, int *n
           (primme->maxOuterIterations == 0 ||
                 primme->stats.numOuterIterations < primme->maxOuterIterations)) {
 
-      primme->initSize = numConverged = numLocked;
+      primme->initSize = numConverged = S->numConvergedStored = numLocked;
       reset = 0;
       for (i = 0; i < maxBasis; i++) flags[i] = UNCONVERGED;
       targetShiftIndex = 0;

@@ -338,15 +338,6 @@ static int check_scope(primme_params *p) {
             (p->globalSumReal && p->globalSumReal_type != primme_op_default &&
                   p->globalSumReal_type != primme_op_double))
       why = "callback datatypes other than double";
-   else if (p->correctionParams.maxInnerIterations != 0 && p->correctionParams.precondition > 0 &&
-            p->correctionParams.projectors.RightQ && p->correctionParams.projectors.SkewQ)
-      /* The reference cannot run this configuration either: restart_projection applies the preconditioner to
-       * &Bevecs[...] with Bevecs == NULL when there is no mass matrix (restart.c:1511-1515; init.c:163 has the
-       * `Bevecs ? Bevecs : evecs` guard, this call does not) and factorises M with ldMfact == 0
-       * (main_iter.c:1089 -> factorize.c:218-222).  PRIMME 3.2 built unchanged segfaults inside the
-       * user's preconditioner at the first restart after a pair converged (tests/test_jdqmr_cpu.py runs it in a
-       * child process); refusing with -44 before any work is the defined behaviour here. */
-      why = "inner QMR iterations with the skew-Q projector and a preconditioner (the reference crashes in this configuration: restart.c:1511)";
    /* blocks wider than the kernels' 8-column panels are processed in chunks of 8 (dav_ortho.c, dav_project.c,
     * the launchers); the inner QMR solver keeps its 8 systems per block */
    else if (p->maxBlockSize > 8 && p->correctionParams.maxInnerIterations != 0)
@@ -371,6 +362,8 @@ static void free_solver(pb_solver *S, int own_evecs) {
    free(S->R), free(S->hU), free(S->hVecsRot), free(S->QtQ), free(S->fQtQ), free(S->hSVals), free(S->QtV);
    if (S->dev && S->Q) pb200_free(S->dev, S->Q);
    if (S->dev && S->jd_work) pb200_free(S->dev, S->jd_work);
+   if (S->dev && S->evecsHat) pb200_free(S->dev, S->evecsHat);
+   free(S->Mskew), free(S->Mfact), free(S->ipivot);
    free(S->hVals), free(S->prevRitzVals), free(S->blockNorms), free(S->basisNorms);
    free(S->flags), free(S->map), free(S->iev), free(S->perm), free(S->lockedFlags);
    if (S->dev) pb200_ctx_destroy(S->dev);
@@ -516,6 +509,17 @@ static int solve_typed(double *evals, SCALAR *evecs, double *resNorms, primme_pa
       }
       if (!S->R || !S->hU || !S->hVecsRot || !S->hSVals) rc = PRIMME_MALLOC_FAILURE;
    }
+   if (primme->correctionParams.precondition && primme->correctionParams.maxInnerIterations != 0 &&
+         primme->correctionParams.projectors.RightQ && primme->correctionParams.projectors.SkewQ) {
+      /* main_iter.c:324-333 */
+      S->maxEvecsSize = primme->numOrthoConst + primme->numEvals;
+      const size_t me = (size_t)PB_MAX(S->maxEvecsSize, 1);
+      if (!rc) rc = pb200_malloc(S->dev, sizeof(SCALAR) * (size_t)PB_MAX(S->ld, 1) * me, (void **)&S->evecsHat);
+      S->Mskew = (SCALAR *)calloc(me * me, sizeof(SCALAR));
+      S->Mfact = (SCALAR *)calloc(me * me, sizeof(SCALAR));
+      S->ipivot = (int *)calloc(me, sizeof(int));
+      if (!S->Mskew || !S->Mfact || !S->ipivot) rc = PRIMME_MALLOC_FAILURE;
+   }
    S->hVals = (double *)calloc(mb, sizeof(double));
    S->prevRitzVals = (double *)calloc(mb + primme->numEvals, sizeof(double));
    S->blockNorms = (double *)calloc(PB_MAX(primme->maxBlockSize, 1), sizeof(double));
@@ -533,7 +537,8 @@ static int solve_typed(double *evals, SCALAR *evecs, double *resNorms, primme_pa
          if (own_evecs) pb200_free(S->dev, S->evecs);
          if (S->jd_work) pb200_free(S->dev, S->jd_work);
          if (S->Q) pb200_free(S->dev, S->Q);
-         S->V = S->W = S->evecs = S->jd_work = S->Q = NULL;
+         if (S->evecsHat) pb200_free(S->dev, S->evecsHat);
+         S->V = S->W = S->evecs = S->jd_work = S->Q = S->evecsHat = NULL;
          S->dev = NULL;
       }
       free_solver(S, own_evecs);
@@ -590,7 +595,8 @@ static int solve_typed(double *evals, SCALAR *evecs, double *resNorms, primme_pa
       if (own_evecs) pb200_free(S->dev, S->evecs);
       if (S->jd_work) pb200_free(S->dev, S->jd_work);
       if (S->Q) pb200_free(S->dev, S->Q);
-      S->V = S->W = S->evecs = S->jd_work = S->Q = NULL;
+      if (S->evecsHat) pb200_free(S->dev, S->evecsHat);
+      S->V = S->W = S->evecs = S->jd_work = S->Q = S->evecsHat = NULL;
       S->dev = NULL;
    }
    free_solver(S, own_evecs);

@@ -15,6 +15,8 @@ extern void dtrsm_(const char *, const char *, const char *, const char *, const
       const int *, const double *, const double *, const int *, double *, const int *);
 extern void dpotrf_(const char *, const int *, double *, const int *, int *);
 extern void dgetrf_(const int *, const int *, double *, const int *, int *, int *);
+extern void dsytrf_(const char *, const int *, double *, const int *, int *, double *, const int *, int *);
+extern void dsytrs_(const char *, const int *, const int *, const double *, const int *, const int *, double *, const int *, int *);
 extern void dgetrs_(const char *, const int *, const int *, const double *, const int *, const int *, double *,
       const int *, int *);
 extern void dtrmm_(const char *, const char *, const char *, const char *, const int *,
@@ -42,6 +44,8 @@ extern void ztrmm_(const char *, const char *, const char *, const char *, const
       const SCALAR *, const int *, SCALAR *, const int *);
 extern void zpotrf_(const char *, const int *, SCALAR *, const int *, int *);
 extern void zgetrf_(const int *, const int *, SCALAR *, const int *, int *, int *);
+extern void zhetrf_(const char *, const int *, SCALAR *, const int *, int *, SCALAR *, const int *, int *);
+extern void zhetrs_(const char *, const int *, const int *, const SCALAR *, const int *, const int *, SCALAR *, const int *, int *);
 extern void zgetrs_(const char *, const int *, const int *, const SCALAR *, const int *, const int *, SCALAR *,
       const int *, int *);
 extern void zgesvd_(const char *, const char *, const int *, const int *, SCALAR *, const int *, double *, SCALAR *,
@@ -58,6 +62,8 @@ extern void zhegvx_(const int *, const char *, const char *, const char *, const
 #define XTRMM ztrmm_
 #define XPOTRF zpotrf_
 #define XGETRF zgetrf_
+#define XHETRF zhetrf_
+#define XHETRS zhetrs_
 #define XGETRS zgetrs_
 #else
 #define XGEMM dgemm_
@@ -66,6 +72,8 @@ extern void zhegvx_(const int *, const char *, const char *, const char *, const
 #define XTRMM dtrmm_
 #define XPOTRF dpotrf_
 #define XGETRF dgetrf_
+#define XHETRF dsytrf_
+#define XHETRS dsytrs_
 #define XGETRS dgetrs_
 #endif
 
@@ -216,6 +224,28 @@ int hl_getrs(char trans, int n, int nrhs, const SCALAR *A, int lda, const int *i
    int info = 0;
    if (n == 0 || nrhs == 0) return 0;
    XGETRS(&trans, &n, &nrhs, A, &lda, ipiv, B, &ldb, &info);
+   return info;
+}
+
+int hl_hetrf_upper(int n, SCALAR *A, int lda, int *ipiv) {
+   int info = 0, lwork = -1;
+   if (n == 0) return 0;
+   SCALAR wq = 0.0;
+   XHETRF("U", &n, A, &lda, ipiv, &wq, &lwork, &info); /* optimal workspace, like the reference */
+   if (info == 0) {
+      lwork = (int)PB_REAL(wq);
+      if (lwork < 1) lwork = 1;
+      SCALAR *work = (SCALAR *)malloc(sizeof(SCALAR) * lwork);
+      XHETRF("U", &n, A, &lda, ipiv, work, &lwork, &info);
+      free(work);
+   }
+   return info;
+}
+
+int hl_hetrs_upper(int n, int nrhs, const SCALAR *A, int lda, const int *ipiv, SCALAR *B, int ldb) {
+   int info = 0;
+   if (n == 0 || nrhs == 0) return 0;
+   XHETRS("U", &n, &nrhs, A, &lda, ipiv, B, &ldb, &info);
    return info;
 }
 

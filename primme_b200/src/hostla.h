@@ -42,6 +42,8 @@ typedef double SCALAR;
 #define hl_potrf_upper PB_SUF(hl_potrf_upper)
 #define hl_getrf PB_SUF(hl_getrf)
 #define hl_getrs PB_SUF(hl_getrs)
+#define hl_hetrf_upper PB_SUF(hl_hetrf_upper)
+#define hl_hetrs_upper PB_SUF(hl_hetrs_upper)
 #define hl_gesvd_SO PB_SUF(hl_gesvd_SO)
 #define hl_sygv_upper PB_SUF(hl_sygv_upper)
 #define hl_larnv2 PB_SUF(hl_larnv2)
@@ -75,6 +77,10 @@ int hl_potrf_upper(int n, SCALAR *A, int lda); /* returns LAPACK info */
 /* LU with partial pivoting and its solves (reference Num_getrf / Num_getrs, blaslapack.c) */
 int hl_getrf(int m, int n, SCALAR *A, int lda, int *ipiv);
 int hl_getrs(char trans, int n, int nrhs, const SCALAR *A, int lda, const int *ipiv, SCALAR *B, int ldb);
+/* Bunch-Kaufman factorisation / solve of a Hermitian matrix given by its upper triangle: dsytrf / zhetrf with the
+ * workspace from the query, dsytrs / zhetrs (reference Num_hetrf / Num_hetrs, blaslapack.c:1412-1560) */
+int hl_hetrf_upper(int n, SCALAR *A, int lda, int *ipiv);
+int hl_hetrs_upper(int n, int nrhs, const SCALAR *A, int lda, const int *ipiv, SCALAR *B, int ldb);
 /* singular value decomposition, left vectors in U, transposed right vectors overwrite A */
 int hl_gesvd_SO(int m, int n, SCALAR *A, int lda, double *s, SCALAR *U, int ldu);
 /* eigen-decomposition of the symmetric / Hermitian matrix stored in the upper triangle of A (n x n, lda);

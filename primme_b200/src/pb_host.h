@@ -24,6 +24,8 @@
 #define pb_monitor PB_SUF(pb_monitor)
 #define pb_fill_random PB_SUF(pb_fill_random)
 #define pb_update_projection PB_SUF(pb_update_projection)
+#define pb_update_XKinvBX PB_SUF(pb_update_XKinvBX)
+#define pb_skew_evecs_after_restart PB_SUF(pb_skew_evecs_after_restart)
 #define pb_solve_H PB_SUF(pb_solve_H)
 #define pb_map_vecs PB_SUF(pb_map_vecs)
 #define pb_reduce_panel PB_SUF(pb_reduce_panel)
@@ -117,6 +119,13 @@ typedef struct pb_solver {
    /* inner QMR solver (JDQMR family): g, d, delta, w, sol -- 5 x ld x maxBlockSize, device */
    SCALAR *jd_work;
    int touch; /* stopping-criterion state of the inner solver (main_iter.c:206,597-599) */
+   /* skew-Q projector with a preconditioner (PRIMME_JDQR + applyPreconditioner; main_iter.c:324-333,
+    * correction.c:948-954): evecsHat = K^{-1} evecs column by column, M = evecs' evecsHat (upper triangle) and its
+    * Bunch-Kaufman factors, maintained by pb_update_XKinvBX (factorize.c:183-235) */
+   SCALAR *evecsHat;      /* device, ld x maxEvecsSize, or NULL */
+   SCALAR *Mskew, *Mfact; /* host, maxEvecsSize x maxEvecsSize (Mfact packed with leading dimension nM) */
+   int *ipivot;
+   int maxEvecsSize, numConvergedStored; /* numConvergedStored: Ritz vectors kept in evecs without locking (:197) */
    /* refined extraction (dav_refined.c): (A - tau I) V = Q R next to V and W */
    int refined;        /* primme_proj_refined */
    int numQR;          /* refined or harmonic: Q and R are carried (main_iter.c:268-273) */
@@ -173,6 +182,8 @@ void pb_registry_set_solver(const primme_params *primme, pb200_ctx *ctx);
 
 /* dav_project.c */
 int pb_update_projection(pb_solver *S, int numCols, int blockSize);
+int pb_update_XKinvBX(pb_solver *S, int numCols, int blockSize);
+int pb_skew_evecs_after_restart(pb_solver *S, int numConverged);
 int pb_solve_H(pb_solver *S, const SCALAR *H, int ldH, int n, const SCALAR *VtBVblk, int ldVtBV,
       SCALAR *hVecs, int ldhVecs, double *hVals, int numConverged, int updateStats);
 int pb_map_vecs(const SCALAR *V, int m, int nV, int ldV, const SCALAR *W, int n0, int n, int ldW,
@@ -222,7 +233,8 @@ void pb_dyn_recommend(primme_params *primme, const pb_cost_model *m);
 /* dav_jdqmr.c */
 int pb_inner_solve(pb_solver *S, int blockSize, SCALAR *x, int64_t ldx, SCALAR *r, int64_t ldr, const double *rnorm,
       const SCALAR *Q, int64_t ldQ, int nQ, int useX, SCALAR *sol, int64_t ldsol, const double *eval, double *shift,
-      int *touch, SCALAR *work, const SCALAR *RQ, int64_t ldRQ, int nRQ, SCALAR *RX, int64_t ldRX, SCALAR *xKinvBx);
+      int *touch, SCALAR *work, const SCALAR *RQ, int64_t ldRQ, int nRQ, SCALAR *RX, int64_t ldRX, SCALAR *xKinvBx,
+      const SCALAR *skewQ, int64_t ldskewQ, const SCALAR *Mfact, const int *ipivot);
 
 /* dav_restart.c */
 int pb_restart(pb_solver *S, int basisSize, int *ievSize, double *evals, double *resNorms,

@@ -20,6 +20,7 @@ from primme_b200 import api  # noqa: E402
 HOSTCHECK = os.path.join(ROOT, "oracle", "_build", "libprimme_hostcheck.so")
 ORACLE_KERNELS = os.path.join(ROOT, "oracle", "_build", "liboracle_kernels.so")
 REFERENCE = os.path.join(ROOT, "oracle", "_ref", "libprimme_ref.so")
+REFERENCE_SKEWQ = os.path.join(ROOT, "oracle", "_ref", "libprimme_ref_skewq.so")
 
 
 def _ensure_built(path):
@@ -59,6 +60,13 @@ def lib_reference():
     return api.load_library(REFERENCE)
 
 
+def lib_reference_skewq():
+    """the reference with the two one-line fixes of oracle/Makefile (refskewq): the only build of it that can run
+    the skew-Q projector with a preconditioner; used by tests/test_jdqmr_cpu.py for that configuration alone"""
+    _ensure_built(REFERENCE_SKEWQ)
+    return api.load_library(REFERENCE_SKEWQ)
+
+
 class CsrHost(C.Structure):
     """mirror of oracle/csr_host.c:csr_host"""
     _fields_ = [("n", C.c_int64), ("rowptr", C.c_void_p), ("colind", C.c_void_p), ("vals", C.c_void_p),
@@ -81,10 +89,11 @@ def solve(which, csr, numEvals, target=api.primme_smallest, method=api.PRIMME_GD
         m = rows == ci
         diag[rows[m]] = va[m]
 
-    lib = {"reference": lib_reference, "hostcheck": lib_hostcheck, "product": lib_product}[which]()
+    lib = {"reference": lib_reference, "reference_skewq": lib_reference_skewq, "hostcheck": lib_hostcheck,
+           "product": lib_product}[which]()
     p = api.new_params(lib, n, numEvals=numEvals, target=target, **kw)
     keep = []
-    if which == "reference":
+    if which.startswith("reference"):
         ok = lib_oracle_kernels()
         A = CsrHost(n, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, nthreads,
                     diag.ctypes.data if diag is not None else None, 1e-12 if jacobi else 0.0, 1)
@@ -114,7 +123,7 @@ def solve(which, csr, numEvals, target=api.primme_smallest, method=api.PRIMME_GD
         evecs[: init_vecs.shape[1], :] = init_vecs.T
     p.ldevecs = n
 
-    if which == "reference":
+    if which.startswith("reference"):
         rc = lib.dprimme(evals.ctypes.data, evecs.ctypes.data, rnorms.ctypes.data, C.byref(p))
     else:
         ctx = C.c_void_p()
@@ -137,13 +146,13 @@ def solve(which, csr, numEvals, target=api.primme_smallest, method=api.PRIMME_GD
         lib.pb200_ctx_destroy(ctx)
     out = dict(evals=evals, rnorms=rnorms, evecs=evecs[p.numOrthoConst:].T.copy(), ret=rc,
                stats=api.stats_dict(p), initSize=p.initSize, params=p)
-    if which != "reference":
+    if not which.startswith("reference"):
         out["launches"] = launches
     return out
 
 
 def zsolve(which, csr, numEvals, target=api.primme_smallest, method=api.PRIMME_GD_Olsen_plusK, jacobi=False,
-           nthreads=1, tweak=None, **kw):
+           nthreads=1, tweak=None, projectors=None, **kw):
     """zprimme through `which` in {"reference", "hostcheck", "product"}: csr = (indptr, indices, complex values) of a
     Hermitian matrix.  Returns dict(evals, rnorms, evecs (n x k complex), ret, stats)."""
     indptr, indices, data = csr
@@ -157,10 +166,11 @@ def zsolve(which, csr, numEvals, target=api.primme_smallest, method=api.PRIMME_G
         rows = np.repeat(np.arange(n), np.diff(rp))
         m = rows == ci
         diag[rows[m]] = va[m].real
-    lib = {"reference": lib_reference, "hostcheck": lib_hostcheck, "product": lib_product}[which]()
+    lib = {"reference": lib_reference, "reference_skewq": lib_reference_skewq, "hostcheck": lib_hostcheck,
+           "product": lib_product}[which]()
     p = api.new_params(lib, n, numEvals=numEvals, target=target, **kw)
     keep = []
-    if which == "reference":
+    if which.startswith("reference"):
         ok = lib_oracle_kernels()
         A = CsrHost(n, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, nthreads,
                     diag.ctypes.data if diag is not None else None, 1e-12 if jacobi else 0.0, 1)
@@ -174,6 +184,9 @@ def zsolve(which, csr, numEvals, target=api.primme_smallest, method=api.PRIMME_G
         p.applyPreconditioner = C.cast(lib.primme_b200_zjacobi_apply, C.c_void_p).value
     if method is not None:
         assert lib.primme_set_method(method, C.byref(p)) == 0
+    if projectors is not None:   # (LeftQ, LeftX, RightQ, RightX, SkewQ, SkewX) on top of the preset
+        pr = p.correctionParams.projectors
+        pr.LeftQ, pr.LeftX, pr.RightQ, pr.RightX, pr.SkewQ, pr.SkewX = projectors
     if tweak is not None:
         tweak(p)
     ncols = p.numOrthoConst + max(numEvals, p.initSize)
@@ -182,7 +195,7 @@ def zsolve(which, csr, numEvals, target=api.primme_smallest, method=api.PRIMME_G
     evecs = np.zeros((ncols, n), dtype=np.complex128)
     p.ldevecs = n
     vp = C.c_void_p
-    if which == "reference":
+    if which.startswith("reference"):
         lib.zprimme.restype, lib.zprimme.argtypes = C.c_int, [vp, vp, vp, C.POINTER(api.PrimmeParams)]
         rc = lib.zprimme(evals.ctypes.data, evecs.ctypes.data, rnorms.ctypes.data, C.byref(p))
     else:

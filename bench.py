@@ -470,7 +470,7 @@ def main():
         val, sec, ncores, mv = run_reference(args, csr, rank)
         line = {"impl": "reference", "metric": "matvecs_per_s", "value": val, "unit": "matvecs/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args.side), "n": n, "nnz": nnz},
                 "cpu_baseline": {"value": val, "unit": "matvecs/s", "cores": ncores, "kind": "reference",

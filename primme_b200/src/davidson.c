@@ -449,7 +449,8 @@ static int solve_correction(pb_solver *S, double *evals, int numLocked, int basi
                (void **)&S->jd_work);
       /* right projectors (:942-980): the locked vectors, and x or K^{-1}x with x'K^{-1}x */
       const SCALAR *RQ = NULL;
-      SCALAR *RX = NULL, *KinvX = NULL, xKinvBx[8];
+      SCALAR *RX = NULL, *KinvX = NULL;
+      SCALAR *xKinvBx = (SCALAR *)malloc(sizeof(SCALAR) * PB_MAX(blockSize, 1));
       int nRQ = 0;
       /* right projector on Q: orthogonal (RQ = evecs) or, with a preconditioner and SkewQ, the skew one
        * (RQ = evecsHat = K^{-1} evecs, overlaps with evecs solved through the factors of M; :948-954) */
@@ -472,17 +473,30 @@ static int solve_correction(pb_solver *S, double *evals, int numLocked, int basi
          }
       }
       if (!rc) {
-         double blockRitzVals[8];
+         /* The systems of a block are independent (every scalar of the recurrences is per system, inner_solve.c:
+          * 155-182): blocks wider than the 8 systems the inner solver carries are solved in chunks of 8, every
+          * chunk starting from the same stopping-criterion state `touch`, whose increments add up as in one call
+          * (once per call for the decreasing tolerance, once per system stopped by the convergence test else). */
+         double *blockRitzVals = (double *)malloc(sizeof(double) * PB_MAX(blockSize, 1));
          for (int b = 0; b < blockSize; b++) blockRitzVals[b] = ritzVals[iev[b]];
          SCALAR *sol = S->jd_work + (size_t)S->ld * 4 * PB_MAX(primme->maxBlockSize, 1);
-         int touch1 = S->touch;
-         rc = pb_inner_solve(S, blockSize, x, S->ld, r, S->ld, blockNorms, Q, S->ldevecs, nQ, useX, sol, S->ld,
-               blockRitzVals, shifts, &touch1, S->jd_work, RQ, ldRQ, nRQ, RX, S->ld, xKinvBx, skewQ, S->ldevecs,
-               S->Mfact, S->ipivot);
-         S->touch = PB_MAX(S->touch, touch1);
+         const int touch0 = S->touch;
+         int inc = 0;
+         for (int c0 = 0; c0 < blockSize && !rc; c0 += 8) {
+            const int nc = PB_MIN(8, blockSize - c0);
+            int touch1 = touch0;
+            rc = pb_inner_solve(S, nc, x + (size_t)S->ld * c0, S->ld, r + (size_t)S->ld * c0, S->ld, blockNorms + c0, Q,
+                  S->ldevecs, nQ, useX, sol + (size_t)S->ld * c0, S->ld, blockRitzVals + c0, shifts + c0, &touch1,
+                  S->jd_work, RQ, ldRQ, nRQ, RX ? RX + (size_t)S->ld * c0 : NULL, S->ld, xKinvBx + c0, skewQ, S->ldevecs,
+                  S->Mfact, S->ipivot);
+            inc = cp->convTest == primme_decreasing_LTolerance ? PB_MAX(inc, touch1 - touch0) : inc + (touch1 - touch0);
+         }
+         S->touch = PB_MAX(S->touch, touch0 + inc);
          if (!rc) rc = pb200_copy_d2d(S->dev, sol, S->ld, x, S->ld, S->n, blockSize, PB_ES);
+         free(blockRitzVals);
       }
       if (KinvX) pb200_free(S->dev, KinvX);
+      free(xKinvBx);
    } else if (cp->projectors.RightX && cp->projectors.SkewX) {
       /* exact Olsen projector (correction.c:695-774): x <- K^{-1}r - (x'K^{-1}r / x'K^{-1}x) K^{-1}x */
       SCALAR *tmp = NULL;

@@ -340,8 +340,6 @@ static int check_scope(primme_params *p) {
       why = "callback datatypes other than double";
    /* blocks wider than the kernels' 8-column panels are processed in chunks of 8 (dav_ortho.c, dav_project.c,
     * the launchers); the inner QMR solver keeps its 8 systems per block */
-   else if (p->maxBlockSize > 8 && p->correctionParams.maxInnerIterations != 0)
-      why = "maxBlockSize > 8 with inner QMR iterations";
 #ifdef PB_COMPLEX
    else if (p->projectionParams.projection != primme_proj_default && p->projectionParams.projection != primme_proj_RR)
       why = "refined / harmonic extraction in complex arithmetic (Rayleigh-Ritz only)";

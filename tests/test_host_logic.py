@@ -82,11 +82,10 @@ def test_error_codes():
     p = api.new_params(lib, 10, numEvals=20, method=api.PRIMME_GD)
     ev = np.zeros(20)
     assert lib.dprimme(ev.ctypes.data, ev.ctypes.data, ev.ctypes.data, C.byref(p)) == -7  # no matvec
-    # inner QMR iterations keep at most 8 systems per block: wider blocks with them are refused before any work
+    # what IS outside the scope is refused before any work: e.g. a mass matrix (generalised problem)
     p = api.new_params(lib, 100, numEvals=2)
-    assert lib.primme_set_method(api.PRIMME_JDQMR, C.byref(p)) == 0
-    p.maxBlockSize = 9
     p.matrixMatvec = 1
+    p.massMatrixMatvec = 1
     assert lib.dprimme(ev.ctypes.data, ev.ctypes.data, ev.ctypes.data, C.byref(p)) == -44
 
 

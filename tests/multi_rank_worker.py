@@ -50,7 +50,23 @@ def main():
         r[:] = t.numpy()
         ierr[0] = 0
 
-    mv, gs = api.BLOCK_OP(matvec), api.GLOBAL_SUM(gsum)
+    def precond(x, ldx, y, ldy, bs, p, ierr):
+        # Jacobi, (diag - shift)^{-1} on the local rows, shifts from primme.ShiftsForPreconditioner (NULL: none)
+        b = bs[0]
+        xl = np.ctypeslib.as_array(C.cast(x, C.POINTER(C.c_double)), shape=(b * ldx[0],)).reshape(b, ldx[0])
+        yo = np.ctypeslib.as_array(C.cast(y, C.POINTER(C.c_double)), shape=(b * ldy[0],)).reshape(b, ldy[0])
+        sh = p.contents.ShiftsForPreconditioner
+        for j in range(b):
+            d = ldiag - (sh[j] if sh else 0.0)
+            d = np.where(np.abs(d) < 1e-12, 1e-12, d)
+            yo[j, :nloc] = xl[j, :nloc] / d
+        ierr[0] = 0
+
+    rows = np.repeat(np.arange(n), np.diff(ip))
+    diag = np.zeros(n)
+    diag[rows[rows == ix]] = da[rows == ix]
+    ldiag = diag[lo:hi]
+    mv, gs, pc = api.BLOCK_OP(matvec), api.GLOBAL_SUM(gsum), api.BLOCK_OP(precond)
     k = 6
     extra = {}
     proj = os.environ.get("PB_PROJ", "")
@@ -63,6 +79,8 @@ def main():
                        numProcs=world, procID=rank, nLocal=nloc, **extra)
     p.matrixMatvec = C.cast(mv, C.c_void_p).value
     p.globalSumReal = C.cast(gs, C.c_void_p).value
+    if os.environ.get("PB_JACOBI"):   # before primme_set_method: the preset decides `precondition` from it
+        p.applyPreconditioner = C.cast(pc, C.c_void_p).value
     method = getattr(api, os.environ.get("PB_METHOD", "PRIMME_GD_Olsen_plusK"))
     assert lib.primme_set_method(method, C.byref(p)) == 0
     p.ldevecs = nloc

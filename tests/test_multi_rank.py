@@ -12,10 +12,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.mark.parametrize("bs,method", [(1, "PRIMME_GD_Olsen_plusK"), (3, "PRIMME_GD_Olsen_plusK"),
-                                       (1, "PRIMME_JDQMR_ETol"), (2, "PRIMME_JDQMR")])
+                                       (1, "PRIMME_JDQMR_ETol"), (2, "PRIMME_JDQMR"),
+                                       # PRIMME_JDQR with a (Jacobi) preconditioner: the skew-Q projector, K^{-1}Q and
+                                       # M = Q'K^{-1}Q reduced over the ranks
+                                       (1, "PRIMME_JDQR+jacobi"), (2, "PRIMME_JDQR+jacobi")])
 def test_two_rank_row_sharded_solve(bs, method):
-    env = dict(os.environ, PB_BS=str(bs), PB_METHOD=method, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
-    port = 29511 + bs + (10 if "JDQMR" in method else 0)
+    env = dict(os.environ, PB_BS=str(bs), PB_METHOD=method.split("+")[0], OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
+    if method.endswith("+jacobi"):
+        env["PB_JACOBI"] = "1"
+    port = 29511 + bs + (10 if "JDQMR" in method else 0) + (20 if "JDQR" in method else 0)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "multi_rank_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)

@@ -118,6 +118,13 @@ struct pb200_ctx {
 // in its own buffer, sums them in rank order (identical bits on every rank) and delivers the result
 // to the host like a single-GPU panel.  Slots rotate with the sequence number; a rank cannot get
 // two panels ahead of a peer (it needs the peer's previous panel to proceed), so 4 slots suffice.
+// ASSUMPTION (platform contract of this protocol, x86-64 host + NVLink / PCIe on one node, checked by every
+// multi-GPU and host-contract test run): a naturally aligned 16-byte store (st.volatile.global.v2.f64 to peer or
+// mapped pinned memory) is observed as a whole -- the reader never sees the new tag with the old value.  CUDA
+// guarantees single-copy atomicity for 8 bytes only; the 16-byte pair travels as one NVLink / PCIe write of an
+// aligned 16-byte quantity on these platforms.  A platform without that property needs an LL-style layout (the
+// tag repeated next to every 8-byte word, as NCCL's LL protocol does); the host reader already orders the value
+// load after the tag load with an acquire fence (ctx.cu:pb_poll_tagged) for weakly ordered hosts.
 struct PbFin {
    double *partials;         // [nparts][cnt], CTA c owns slots [c*ppc, (c+1)*ppc)
    double *gpart;            // [ngroups][cnt]
